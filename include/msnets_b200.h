@@ -1,0 +1,207 @@
+/* msnets_b200.h -- C ABI of libmsnets_b200.so (hand-written sm_100a CUDA kernels).
+ *
+ * Drop-in boundary for the matching-space (MS) hot path of ccj5351/MS-Nets.
+ * Each entry point names the reference interface it replaces (paths relative to
+ * the reference checkout).  Plain pointers and sizes only; no torch / numpy /
+ * Boost types.  INTEGRATION.md shows the reference-side stubs that bind these.
+ *
+ * Conventions
+ *   - every function returns 0 on success, non-zero on failure; the message is
+ *     available from msn_last_error() (thread-local, never NULL).  The reference
+ *     functions never validate and never raise; this ABI checks
+ *     shapes/arguments and fails loudly instead of misreading memory.
+ *   - "*_host" entry points take HOST buffers (what the reference's Boost.Python
+ *     exports receive from NumPy): inputs are borrowed, outputs are caller-
+ *     allocated, the call is synchronous, and all host<->device copies happen
+ *     inside it on the device selected by msn_set_device().
+ *   - "*_dev" entry points take DEVICE buffers and a cudaStream_t (passed as
+ *     void*; NULL = legacy default stream).  They only enqueue work.
+ *   - images are uint8, row-major, contiguous [H][W] (pitch == W) unless a pitch
+ *     argument says otherwise.  Cost volumes are float32.  "fill" is
+ *     2147483648.0f == float(RAND_MAX) (matchers.cpp:65,251,377,462).
+ *   - there is NO CPU fallback: without a CUDA device every compute entry point
+ *     returns an error.
+ */
+#ifndef MSNETS_B200_H_
+#define MSNETS_B200_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#if defined(__GNUC__)
+#define MSN_API __attribute__((visibility("default")))
+#else
+#define MSN_API
+#endif
+
+#define MSN_FILL_VALUE 2147483648.0f
+#define MSN_ABI_VERSION 1
+
+/* ---------------------------------------------------------------- runtime -- */
+MSN_API const char* msn_last_error(void);
+MSN_API int msn_abi_version(void);
+MSN_API int msn_device_count(int* count);
+MSN_API int msn_set_device(int device);
+/* replaces initthreads() (matchers.cpp:556-563): the reference returns its
+ * OpenMP team size (THREADS_NUM_USED = 8, paramSetting.hpp:11); this returns the
+ * SM count of the current device. */
+MSN_API int msn_initthreads(int* count);
+
+/* ------------------------------------------------- libmatchers (host API) -- */
+/* census(left,right,ndisp,wsize) -> float32 [H][W][D]      matchers.cpp:232-353 */
+MSN_API int msn_census_host(const uint8_t* left, const uint8_t* right, int H, int W, int ndisp,
+                    int wsize, float* out_hwd);
+/* nccNister(left,right,ndisp,wsize) -> float32 [D][H][W]   matchers.cpp:47-228 */
+MSN_API int msn_ncc_host(const uint8_t* left, const uint8_t* right, int H, int W, int ndisp, int wsize,
+                 float* out_dhw);
+/* zsad(left,right,ndisp,wsize) -> float32 [D][H][W]        matchers.cpp:442-512 */
+MSN_API int msn_zsad_host(const uint8_t* left, const uint8_t* right, int H, int W, int ndisp, int wsize,
+                  float* out_dhw);
+/* sobel(img) -> float32 [H][W]                             matchers.cpp:515-554 */
+MSN_API int msn_sobel_host(const uint8_t* img, int H, int W, float* out_hw);
+/* sadsob(left_f32,right_f32,ndisp,wsize) -> float32 [D][H][W]   matchers.cpp:356-438 */
+MSN_API int msn_sadsob_host(const float* left, const float* right, int H, int W, int ndisp, int wsize,
+                    float* out_dhw);
+
+/* ---------------------------------------------- libfeatextract (host API) -- */
+/* swap_axes: [D][H][W] -> [H][W][D]                        featextract.cpp:49-76 */
+MSN_API int msn_swap_axes_host(const float* in_dhw, int D, int H, int W, float* out_hwd);
+/* swap_axes_back: [H][W][D] -> [D][H][W]                   featextract.cpp:78-105 */
+MSN_API int msn_swap_axes_back_host(const float* in_hwd, int H, int W, int D, float* out_dhw);
+/* get_right_cost: res[y][x][d] = c[y][x+d][d] (x < W-d), else c[0]   featextract.cpp:136-172 */
+MSN_API int msn_right_cost_host(const float* cost_hwd, int H, int W, int D, float* out_hwd);
+/* get_left_cost:  res[y][x][d] = c[y][x-d][d] (x >= d), else c[0]    featextract.cpp:464-499 */
+MSN_API int msn_left_cost_host(const float* cost_hwd, int H, int W, int D, float* out_hwd);
+/* extract_likelihood(vol[n][D], sigma) -> AML [n][D]       featextract.cpp:415-462 */
+MSN_API int msn_aml_host(const float* cost_nd, long long n, int D, float sigma, float* out_nd);
+/* extract_ratio(vol[n][D], e) -> (min+e)/(c+e) [n][D]      featextract.cpp:320-356 */
+MSN_API int msn_pkrn_host(const float* cost_nd, long long n, int D, float e, float* out_nd);
+
+/* ------------------------------------ cbmv_generator glue (host + device) -- */
+/* Parameters of get_costs + extract_features_{left,lr}
+ * (cbmv_generator.py:27-79, :258-308, :84-254; defaults :434-462). */
+typedef struct msn_ms_params {
+  int ndisp;          /* maxdisp handed to the matchers                         */
+  int censw, nccw, sadw, sobelw;   /* window sizes (defaults 11, 3, 5, 5)       */
+  int board_h;        /* rows cropped top AND bottom      (cbmv_generator.py:73-79) */
+  int board_w_left;   /* columns cropped on the left                            */
+  int board_w_right;  /* columns cropped on the right (0 = none)                */
+  float cens_sigma, ncc_sigma, sad_sigma;  /* AML sigmas 128, 0.02, 20000;      *
+                       * the sobel channel uses sad_sigma (cbmv_generator.py:298) */
+  int lr;             /* 0: 8 channels (extract_features_left); 1: 16 (.._lr)   */
+  int d_begin, d_count; /* disparity slab [d_begin, d_begin+d_count) to produce; *
+                       * d_count = 0 means the whole range (single-GPU case)    */
+} msn_ms_params;
+MSN_API void msn_ms_params_default(msn_ms_params* p);
+
+/* extract_features_left / _lr from four already cropped [h][w][D] volumes
+ * (census, ncc, sobel, sad) -> float32 [8 or 16][D][h][w]   cbmv_generator.py:258-308, :84-254 */
+MSN_API int msn_features_from_costs_host(const float* census_hwd, const float* ncc_hwd,
+                                 const float* sobel_hwd, const float* sad_hwd, int h, int w, int D,
+                                 float cens_sigma, float ncc_sigma, float sad_sigma, int lr,
+                                 float* out_cdhw);
+
+/* get_costs + extract_features_* in one call (what generate_test_cbmv chains,
+ * cbmv_generator.py:826-843) for N bordered pairs [N][H][W] uint8.
+ * Output [N][C][Dp][h][w] float32, C = 8 or 16, h = H-2*board_h,
+ * w = W-board_w_left-board_w_right, Dp = d_count (or ndisp). */
+MSN_API int msn_ms_features_host(const uint8_t* left, const uint8_t* right, int N, int H, int W,
+                         const msn_ms_params* p, float* out_ncdhw);
+MSN_API size_t msn_ms_features_workspace_bytes(int N, int H, int W, const msn_ms_params* p);
+MSN_API int msn_ms_features_dev(const uint8_t* d_left, const uint8_t* d_right, int N, int H, int W,
+                        const msn_ms_params* p, float* d_out_ncdhw, void* d_workspace,
+                        size_t workspace_bytes, void* stream);
+
+/* Disparity-slab sharding: the AML of a pixel needs min and
+ * sum over ALL disparities.  Phase A writes channels 0-3 for the slab, parks
+ * the raw costs in channels 4-7 and emits per-pixel slab minima [N][4][h][w];
+ * after an all-reduce(min) over ranks, phase B emits partial denominators
+ * [N][4][h][w]; after an all-reduce(sum), phase C turns the parked costs into
+ * AML values in place.  With one rank the three phases reproduce
+ * msn_ms_features_dev. */
+MSN_API size_t msn_ms_slab_workspace_bytes(int N, int H, int W, const msn_ms_params* p);
+/* d_first4: NULL, or (lr && d_begin > 0 only) device [N][4] floats holding voxel
+ * (d=0, y=board_h, x=board_w_left) of the four raw volumes -- the c[0] fill of
+ * get_right_cost (featextract.cpp:151), which lives on the rank that owns d = 0. */
+MSN_API int msn_ms_slab_phase_a_dev(const uint8_t* d_left, const uint8_t* d_right, int N, int H, int W,
+                            const msn_ms_params* p, const float* d_first4, float* d_out_ncdhw,
+                            float* d_min_n4hw, void* d_workspace, size_t workspace_bytes, void* stream);
+MSN_API int msn_ms_slab_phase_b_dev(const float* d_out_ncdhw, const float* d_min_n4hw, int N, int h, int w,
+                            const msn_ms_params* p, float* d_den_n4hw, void* stream);
+MSN_API int msn_ms_slab_phase_c_dev(float* d_out_ncdhw, const float* d_min_n4hw, const float* d_den_n4hw,
+                            int N, int h, int w, const msn_ms_params* p, void* stream);
+
+/* ----------------------------------------------------- device-level pieces -- */
+MSN_API int msn_census_dev(const uint8_t* d_left, const uint8_t* d_right, int H, int W, int ndisp, int wsize,
+                   float* d_out_hwd, void* stream);
+MSN_API int msn_ncc_dev(const uint8_t* d_left, const uint8_t* d_right, int H, int W, int ndisp, int wsize,
+                float* d_out_dhw, void* stream);
+MSN_API int msn_zsad_dev(const uint8_t* d_left, const uint8_t* d_right, int H, int W, int ndisp, int wsize,
+                 float* d_out_dhw, void* stream);
+MSN_API int msn_sobel_dev(const uint8_t* d_img, int H, int W, float* d_out_hw, void* stream);
+MSN_API int msn_sadsob_dev(const float* d_left, const float* d_right, int H, int W, int ndisp, int wsize,
+                   float* d_out_dhw, void* stream);
+MSN_API int msn_aml_dev(const float* d_cost_nd, long long n, int D, float sigma, float* d_out_nd, void* stream);
+MSN_API int msn_pkrn_dev(const float* d_cost_nd, long long n, int D, float e, float* d_out_nd, void* stream);
+
+/* ---------------------------------------- soft-argmin / WTA / confidence -- */
+/* softmax over D + expectation of d: replaces F.softmax + disparityregression
+ * (gcnet_3dcnn.py:127-141; duplicates psmnet_3dcnn.py:28-37, basic_convs.py:279-287).
+ * logits [N][D][H][W] float32 -> disp [N][H][W] float32. */
+MSN_API int msn_soft_argmin_dev(const float* d_logits, int N, int D, int H, int W, float* d_disp, void* stream);
+/* disparityregression alone (gcnet_3dcnn.py:132-141): prob [N][D][H][W] already
+ * normalised -> sum_d d * prob_d. */
+MSN_API int msn_expect_disp_dev(const float* d_prob, int N, int D, int H, int W, float* d_disp, void* stream);
+MSN_API int msn_soft_argmin_host(const float* logits, int N, int D, int H, int W, float* disp);
+/* Slab-sharded soft-argmin: per-pixel partial (max, sum e, sum d*e) over the
+ * local D slab whose first disparity is d_begin -> [N][3][H][W]; merged by
+ * msn_soft_argmin_merge_dev over `parts` gathered partials [parts][N][3][H][W]. */
+MSN_API int msn_soft_argmin_partial_dev(const float* d_logits, int N, int D, int H, int W, int d_begin,
+                                float* d_part_n3hw, void* stream);
+MSN_API int msn_soft_argmin_merge_dev(const float* d_parts, int parts, int N, int H, int W, float* d_disp,
+                              void* stream);
+
+/* Winner-take-all over D (np.argmin semantics of main_msnet.py:444-448: first
+ * minimal index wins) plus second minimum.  layout: 0 = [n][D] rows (D innermost,
+ * the reference's [H][W][D] volumes flattened; warp-shuffle reduction), 1 =
+ * [D][n] planes (the [C][D][h][w] feature layout; one thread per pixel).
+ * Outputs (any may be NULL): argmin int32 [n], min float [n], second-min float [n]. */
+MSN_API int msn_wta_dev(const float* d_cost, long long n, int D, int layout, int32_t* d_argmin, float* d_min1,
+                float* d_min2, void* stream);
+MSN_API int msn_wta_host(const float* cost, long long n, int D, int layout, int32_t* argmin, float* min1,
+                 float* min2);
+/* Slab merge key for WTA across ranks: order-preserving 64-bit key
+ * (float bits made monotonic) << 32 | (d_begin + d); all-reduce(min) over
+ * int64 then msn_wta_unpack_dev. */
+MSN_API int msn_wta_keys_dev(const float* d_cost, long long n, int D, int layout, int d_begin,
+                     long long* d_keys, void* stream);
+MSN_API int msn_wta_unpack_dev(const long long* d_keys, long long n, int32_t* d_argmin, float* d_min1,
+                       void* stream);
+/* peak-ratio confidence (min1+e)/(min2+e), 0 where min1 is fill (same algebra as
+ * featextract.cpp:349 evaluated at the runner-up; no reference caller). */
+MSN_API int msn_pkrn_conf_dev(const float* d_min1, const float* d_min2, long long n, float e, float* d_conf,
+                      void* stream);
+/* Left-right consistency on an [H][W][D] volume (no reference code; definition
+ * in oracle/ms_oracle.py:lr_consistency): dL, dR int32 [H][W], mask uint8 [H][W]. */
+MSN_API int msn_lrc_dev(const float* d_cost_hwd, int H, int W, int D, int thresh, int32_t* d_dl, int32_t* d_dr,
+                uint8_t* d_mask, void* stream);
+MSN_API int msn_lrc_host(const float* cost_hwd, int H, int W, int D, int thresh, int32_t* dl, int32_t* dr,
+                 uint8_t* mask);
+
+/* -------------------------------------------------- 4D cost-volume builder -- */
+/* GC-Net / PSMNet concat volume (the 64-channel input psmnet_3dcnn.py:96 expects;
+ * the reference has no builder): fl, fr [N][C][H][W] ->
+ * [N][2C][D][H][W]; x < d is zero.  diff: [N][C][D][H][W] = fl - fr(x-d). */
+MSN_API int msn_concat_volume_dev(const float* d_fl, const float* d_fr, int N, int C, int H, int W, int D,
+                          float* d_vol, void* stream);
+MSN_API int msn_diff_volume_dev(const float* d_fl, const float* d_fr, int N, int C, int H, int W, int D,
+                        float* d_vol, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* MSNETS_B200_H_ */

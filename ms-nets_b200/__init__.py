@@ -1,0 +1,49 @@
+"""msnets_b200 -- B200-native matching-space (MS) hot path of ccj5351/MS-Nets.
+
+Hand-written sm_100a CUDA kernels behind a C ABI (include/msnets_b200.h), with
+Python mirrors of the reference's interfaces for this path:
+
+    libmatchers      <- src.cpp.lib.libmatchers      (matchers.cpp)
+    libfeatextract   <- src.cpp.lib.libfeatextract   (featextract.cpp)
+    cbmv             <- src.dataloader.cbmv_generator (get_costs, extract_features_*)
+    regression       <- softmax + disparityregression (gcnet_3dcnn.py:127-141)
+    confidence       WTA / second-min / peak-ratio / left-right check
+    volume           concat / difference 4D volume
+    sharding         batch- and disparity-slab sharding over torch.distributed
+
+`install_dropin()` registers the two native-module mirrors under the reference's
+import names so its unmodified cbmv_generator.py picks them up.
+"""
+import sys
+
+from . import _lib
+from ._lib import MsnetsError, device_count
+
+__all__ = ["libmatchers", "libfeatextract", "cbmv", "regression", "confidence", "volume", "sharding",
+           "install_dropin", "MsnetsError", "device_count"]
+
+
+def __getattr__(name):
+    if name in ("libmatchers", "libfeatextract", "cbmv", "regression", "confidence", "volume", "sharding"):
+        import importlib
+        mod = importlib.import_module(__name__ + "." + name)
+        globals()[name] = mod
+        return mod
+    raise AttributeError(name)
+
+
+def install_dropin():
+    """Makes `import src.cpp.lib.libmatchers as mtc` / `...libfeatextract as fte`
+    (cbmv_generator.py:16-17) resolve to the CUDA-backed mirrors."""
+    import types
+    from . import libfeatextract, libmatchers
+    for pkg in ("src", "src.cpp", "src.cpp.lib"):
+        if pkg not in sys.modules:
+            m = types.ModuleType(pkg)
+            m.__path__ = []
+            sys.modules[pkg] = m
+    sys.modules["src.cpp.lib.libmatchers"] = libmatchers
+    sys.modules["src.cpp.lib.libfeatextract"] = libfeatextract
+    sys.modules["src.cpp.lib"].libmatchers = libmatchers
+    sys.modules["src.cpp.lib"].libfeatextract = libfeatextract
+    return libmatchers, libfeatextract

@@ -1,0 +1,325 @@
+// fte.cu -- libfeatextract drop-in kernels and the confidence pass.
+//
+//   swap_axes / swap_axes_back   featextract.cpp:49-105   (tiled transpose)
+//   get_right_cost/get_left_cost featextract.cpp:136-172, :464-499
+//   extract_likelihood (AML)     featextract.cpp:415-462  (warp per [D] row)
+//   extract_ratio (PKRN)         featextract.cpp:320-356
+//   WTA / second-min / peak-ratio / left-right check  (main_msnet.py:444-448 is
+//   the only reference consumer: np.argmin over D; the rest has no reference code)
+//
+// Row kernels ([n][D], D innermost -- the reference's flattened [H][W][D]) use one
+// warp per row with shuffle reductions over D; plane kernels ([D][n], the feature
+// layout) use one thread per pixel, coalesced across the warp.
+#include "common.cuh"
+#include "feature_math.cuh"
+
+namespace msn {
+
+// ---------------------------------------------------------------- transposes --
+// in[A][B] -> out[B][A] through a 32x33 shared tile; both sides coalesced.
+__global__ void transpose2d_kernel(const float* __restrict__ in, long long A, long long B,
+                                   float* __restrict__ out) {
+  __shared__ float tile[32][33];
+  const long long b0 = (long long)blockIdx.x * 32, a0 = (long long)blockIdx.y * 32;
+  for (int r = threadIdx.y; r < 32; r += blockDim.y) {
+    const long long a = a0 + r, b = b0 + threadIdx.x;
+    if (a < A && b < B) tile[r][threadIdx.x] = in[a * B + b];
+  }
+  __syncthreads();
+  for (int r = threadIdx.y; r < 32; r += blockDim.y) {
+    const long long b = b0 + r, a = a0 + threadIdx.x;
+    if (a < A && b < B) st_stream(out + b * A + a, tile[threadIdx.x][r]);
+  }
+}
+
+int launch_transpose2d(const float* in, long long A, long long B, float* out, cudaStream_t s) {
+  if (A == 0 || B == 0) return 0;
+  dim3 block(32, 8);
+  const long long gx = (B + 31) / 32, gy = (A + 31) / 32;
+  MSN_REQUIRE(gy <= 65535, "transpose: leading extent %lld too large", A);
+  dim3 grid((unsigned)gx, (unsigned)gy);
+  transpose2d_kernel<<<grid, block, 0, s>>>(in, A, B, out);
+  MSN_LAUNCH_OK();
+  return 0;
+}
+
+// ------------------------------------------------------- right / left re-index --
+// right: out[y][x][d] = c[y][x+d][d] if x < W-d else c[0]   (featextract.cpp:151,159-161)
+// left : out[y][x][d] = c[y][x-d][d] if x >= d  else c[0]   (featextract.cpp:479,487-489)
+template <bool kRight>
+__global__ void reindex_cost_kernel(const float* __restrict__ c, int H, int W, int D,
+                                    float* __restrict__ out) {
+  const long long total = (long long)H * W * D;
+  const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= total) return;
+  const int d = (int)(idx % D);
+  const long long p = idx / D;
+  const int x = (int)(p % W);
+  float v;
+  if (kRight)
+    v = (x < W - d) ? c[idx + (long long)d * D] : c[0];
+  else
+    v = (x >= d) ? c[idx - (long long)d * D] : c[0];
+  st_stream(out + idx, v);
+}
+
+int launch_reindex_cost(const float* c, int H, int W, int D, bool right, float* out, cudaStream_t s) {
+  const long long total = (long long)H * W * D;
+  if (total == 0) return 0;
+  if (right)
+    reindex_cost_kernel<true><<<div_up(total, 256), 256, 0, s>>>(c, H, W, D, out);
+  else
+    reindex_cost_kernel<false><<<div_up(total, 256), 256, 0, s>>>(c, H, W, D, out);
+  MSN_LAUNCH_OK();
+  return 0;
+}
+
+// ------------------------------------------------------------ warp reductions --
+__device__ __forceinline__ float warp_min(float v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v = fminf(v, __shfl_xor_sync(0xffffffffu, v, o));
+  return v;
+}
+__device__ __forceinline__ float warp_sum(float v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+
+// One warp per row of D costs.  min (strict <, start fill) -> sum of e -> e/den;
+// the whole row is 0 when the minimum is still fill (featextract.cpp:435-453).
+__global__ void aml_rows_kernel(const float* __restrict__ cost, long long n, int D, float k,
+                                float* __restrict__ out) {
+  const long long row = (long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  const int lane = threadIdx.x & 31;
+  if (row >= n) return;
+  const float* c = cost + row * D;
+  float* o = out + row * D;
+  float m = kFill;
+  for (int d = lane; d < D; d += 32) m = fminf(m, c[d]);
+  m = warp_min(m);
+  if (m == kFill) {
+    for (int d = lane; d < D; d += 32) st_stream(o + d, 0.f);
+    return;
+  }
+  float den = 0.f;
+  for (int d = lane; d < D; d += 32) den += aml_e(c[d], m, k);
+  den = warp_sum(den);
+  const float inv = 1.0f / den;
+  for (int d = lane; d < D; d += 32) st_stream(o + d, aml_e(c[d], m, k) * inv);
+}
+
+int launch_aml_rows(const float* cost, long long n, int D, float sigma, float* out, cudaStream_t s) {
+  if (n == 0 || D == 0) return 0;
+  const float k = aml_scale(sigma);
+  aml_rows_kernel<<<div_up(n, 8), 256, 0, s>>>(cost, n, D, k, out);
+  MSN_LAUNCH_OK();
+  return 0;
+}
+
+// out = (m + e) / (c + e) with IEEE fp32 add and division -> bit-exact
+// (featextract.cpp:349); 0 for the whole row when m is fill.
+__global__ void pkrn_rows_kernel(const float* __restrict__ cost, long long n, int D, float e,
+                                 float* __restrict__ out) {
+  const long long row = (long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  const int lane = threadIdx.x & 31;
+  if (row >= n) return;
+  const float* c = cost + row * D;
+  float* o = out + row * D;
+  float m = kFill;
+  for (int d = lane; d < D; d += 32) m = fminf(m, c[d]);
+  m = warp_min(m);
+  const bool dead = (m == kFill);
+  const float num = __fadd_rn(m, e);
+  for (int d = lane; d < D; d += 32)
+    st_stream(o + d, dead ? 0.f : __fdiv_rn(num, __fadd_rn(c[d], e)));
+}
+
+int launch_pkrn_rows(const float* cost, long long n, int D, float e, float* out, cudaStream_t s) {
+  if (n == 0 || D == 0) return 0;
+  pkrn_rows_kernel<<<div_up(n, 8), 256, 0, s>>>(cost, n, D, e, out);
+  MSN_LAUNCH_OK();
+  return 0;
+}
+
+// ---------------------------------------------------------------------- WTA --
+// (min1, argmin, min2) with np.argmin tie-breaking (first minimal index wins);
+// min2 is the second smallest entry counting duplicates.
+struct Best {
+  float m1, m2;
+  int i1;
+};
+__device__ __forceinline__ Best best_init() { return Best{INFINITY, INFINITY, 0x7fffffff}; }
+__device__ __forceinline__ void best_push(Best& b, float v, int i) {
+  if (v < b.m1 || (v == b.m1 && i < b.i1)) {
+    b.m2 = b.m1;
+    b.m1 = v;
+    b.i1 = i;
+  } else {
+    b.m2 = fminf(b.m2, v);
+  }
+}
+__device__ __forceinline__ Best best_merge(const Best& a, const Best& b) {
+  Best r;
+  const bool a_first = (a.m1 < b.m1) || (a.m1 == b.m1 && a.i1 <= b.i1);
+  if (a_first) {
+    r.m1 = a.m1; r.i1 = a.i1; r.m2 = fminf(a.m2, b.m1);
+  } else {
+    r.m1 = b.m1; r.i1 = b.i1; r.m2 = fminf(b.m2, a.m1);
+  }
+  return r;
+}
+__device__ __forceinline__ Best warp_best(Best b) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    Best other;
+    other.m1 = __shfl_xor_sync(0xffffffffu, b.m1, o);
+    other.m2 = __shfl_xor_sync(0xffffffffu, b.m2, o);
+    other.i1 = __shfl_xor_sync(0xffffffffu, b.i1, o);
+    b = best_merge(b, other);
+  }
+  return b;
+}
+
+// order-preserving map float -> uint32 (negative NCC costs sort below positive)
+__device__ __forceinline__ uint32_t float_key(float v) {
+  const uint32_t u = __float_as_uint(v);
+  return (u & 0x80000000u) ? ~u : (u | 0x80000000u);
+}
+__device__ __forceinline__ float key_float(uint32_t k) {
+  return __uint_as_float((k & 0x80000000u) ? (k & 0x7fffffffu) : ~k);
+}
+
+// 64-bit merge key: (monotonic float bits << 32 | d) with the top bit flipped so
+// that a SIGNED int64 all-reduce(min) across ranks orders like the unsigned key;
+// equal costs resolve to the lowest disparity, as np.argmin does.
+__device__ __forceinline__ long long pack_key(float m1, int d) {
+  const unsigned long long u = ((unsigned long long)float_key(m1) << 32) | (uint32_t)d;
+  return (long long)(u ^ 0x8000000000000000ull);
+}
+
+// layout 0: rows [n][D]; one warp per row.
+__global__ void wta_rows_kernel(const float* __restrict__ cost, long long n, int D, int d_begin,
+                                int32_t* __restrict__ amin, float* __restrict__ m1, float* __restrict__ m2,
+                                long long* __restrict__ keys) {
+  const long long row = (long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  const int lane = threadIdx.x & 31;
+  if (row >= n) return;
+  const float* c = cost + row * D;
+  Best b = best_init();
+  for (int d = lane; d < D; d += 32) best_push(b, c[d], d);
+  b = warp_best(b);
+  if (lane == 0) {
+    if (amin) amin[row] = b.i1;
+    if (m1) m1[row] = b.m1;
+    if (m2) m2[row] = b.m2;
+    if (keys) keys[row] = pack_key(b.m1, d_begin + b.i1);
+  }
+}
+// layout 1: planes [D][n]; one thread per pixel, coalesced across the warp.
+__global__ void wta_planes_kernel(const float* __restrict__ cost, long long n, int D, int d_begin,
+                                  int32_t* __restrict__ amin, float* __restrict__ m1,
+                                  float* __restrict__ m2, long long* __restrict__ keys) {
+  const long long p = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (p >= n) return;
+  Best b = best_init();
+#pragma unroll 4
+  for (int d = 0; d < D; ++d) best_push(b, cost[(long long)d * n + p], d);
+  if (amin) amin[p] = b.i1;
+  if (m1) m1[p] = b.m1;
+  if (m2) m2[p] = b.m2;
+  if (keys) keys[p] = pack_key(b.m1, d_begin + b.i1);
+}
+
+int launch_wta(const float* cost, long long n, int D, int layout, int d_begin, int32_t* amin, float* m1,
+               float* m2, long long* keys, cudaStream_t s) {
+  MSN_REQUIRE(D >= 1, "wta: D must be >= 1");
+  MSN_REQUIRE(layout == 0 || layout == 1, "wta: layout must be 0 ([n][D]) or 1 ([D][n])");
+  if (n == 0) return 0;
+  if (layout == 0)
+    wta_rows_kernel<<<div_up(n, 8), 256, 0, s>>>(cost, n, D, d_begin, amin, m1, m2, keys);
+  else
+    wta_planes_kernel<<<div_up(n, 256), 256, 0, s>>>(cost, n, D, d_begin, amin, m1, m2, keys);
+  MSN_LAUNCH_OK();
+  return 0;
+}
+
+__global__ void wta_unpack_kernel(const long long* __restrict__ keys, long long n, int32_t* __restrict__ amin,
+                                  float* __restrict__ m1) {
+  const long long p = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (p >= n) return;
+  const unsigned long long k = (unsigned long long)keys[p] ^ 0x8000000000000000ull;
+  if (amin) amin[p] = (int32_t)(uint32_t)(k & 0xffffffffull);
+  if (m1) m1[p] = key_float((uint32_t)(k >> 32));
+}
+
+int launch_wta_unpack(const long long* keys, long long n, int32_t* amin, float* m1, cudaStream_t s) {
+  if (n == 0) return 0;
+  wta_unpack_kernel<<<div_up(n, 256), 256, 0, s>>>(keys, n, amin, m1);
+  MSN_LAUNCH_OK();
+  return 0;
+}
+
+__global__ void pkrn_conf_kernel(const float* __restrict__ m1, const float* __restrict__ m2, long long n,
+                                 float e, float* __restrict__ conf) {
+  const long long p = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (p >= n) return;
+  const float a = m1[p];
+  conf[p] = (a == kFill) ? 0.f : __fdiv_rn(__fadd_rn(a, e), __fadd_rn(m2[p], e));
+}
+
+int launch_pkrn_conf(const float* m1, const float* m2, long long n, float e, float* conf, cudaStream_t s) {
+  if (n == 0) return 0;
+  pkrn_conf_kernel<<<div_up(n, 256), 256, 0, s>>>(m1, m2, n, e, conf);
+  MSN_LAUNCH_OK();
+  return 0;
+}
+
+// ---------------------------------------------------------- left-right check --
+// dL = argmin_d c[y][x][d]; dR = argmin_d (x+d < W ? c[y][x+d][d] : c[0]);
+// one warp per pixel computes both with shuffle reductions.
+__global__ void lrc_disp_kernel(const float* __restrict__ c, int H, int W, int D, int32_t* __restrict__ dl,
+                                int32_t* __restrict__ dr) {
+  const long long p = (long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  const int lane = threadIdx.x & 31;
+  if (p >= (long long)H * W) return;
+  const int x = (int)(p % W);
+  const float c0 = c[0];
+  Best bl = best_init(), br = best_init();
+  for (int d = lane; d < D; d += 32) {
+    best_push(bl, c[p * D + d], d);
+    best_push(br, (x < W - d) ? c[(p + d) * D + d] : c0, d);
+  }
+  bl = warp_best(bl);
+  br = warp_best(br);
+  if (lane == 0) {
+    dl[p] = bl.i1;
+    dr[p] = br.i1;
+  }
+}
+__global__ void lrc_mask_kernel(const int32_t* __restrict__ dl, const int32_t* __restrict__ dr, int H, int W,
+                                int thresh, uint8_t* __restrict__ mask) {
+  const long long p = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (p >= (long long)H * W) return;
+  const int x = (int)(p % W);
+  const int d = dl[p];
+  uint8_t ok = 0;
+  if (x - d >= 0) {
+    const int diff = d - dr[p - d];
+    ok = (diff <= thresh && -diff <= thresh) ? 1 : 0;
+  }
+  mask[p] = ok;
+}
+
+int launch_lrc(const float* c, int H, int W, int D, int thresh, int32_t* dl, int32_t* dr, uint8_t* mask,
+               cudaStream_t s) {
+  const long long n = (long long)H * W;
+  if (n == 0) return 0;
+  lrc_disp_kernel<<<div_up(n, 8), 256, 0, s>>>(c, H, W, D, dl, dr);
+  MSN_LAUNCH_OK();
+  lrc_mask_kernel<<<div_up(n, 256), 256, 0, s>>>(dl, dr, H, W, thresh, mask);
+  MSN_LAUNCH_OK();
+  return 0;
+}
+
+}  // namespace msn

@@ -1,0 +1,14 @@
+// ms_fused.cuh -- interface of the fused MS-volume kernel (ms_fused.cu).
+#pragma once
+#include "common.cuh"
+
+namespace msn {
+
+// true when (windows, disparity count) match what the fused kernel is specialised for
+bool fused_supported(const msn_ms_params* p, int Dn);
+size_t fused_workspace_bytes(int N, int H, int W, int Dn, const msn_ms_params* p);
+// d_left/d_right: [N][H][W] uint8; out: [N][C][D][h][w]; workspace 256-byte aligned
+int launch_ms_fused(const uint8_t* d_left, const uint8_t* d_right, int N, int H, int W, const msn_ms_params* p,
+                    float* d_out, char* workspace, cudaStream_t s);
+
+}  // namespace msn

@@ -1,0 +1,171 @@
+// sadsob.cu -- SAD over Sobel images through an fp32 summed-area table whose
+// ROUNDING IS PART OF THE RESULT (matchers.cpp:356-438).
+//
+// The reference builds, for every disparity, S = horizontal-prefix(vertical-
+// prefix(|L(i,j) - R(i,j-d)|)) with sequential fp32 adds and evaluates the box as
+// ((br - bl) - tr) + tl.  On a 560x980 pair the running sums pass 2^24, so S is
+// NOT the exact integer sum: a bit-exact result needs the same
+// add order.  Both prefix passes are therefore replayed as sequential chains --
+// there are D*(W+1) independent vertical chains and D*(H+1) independent
+// horizontal chains, plenty of parallelism -- organised so that every global
+// access is coalesced:
+//
+//   1. vband kernel: one thread per (d, column) walks down the image and records
+//      the vertical prefix at the first row of every 32-row band  -> Vb[d][band][j].
+//   2. scan kernel: one warp per (d, band) sweeps left to right in 32x32 tiles.
+//      Lanes first own COLUMNS (finish the vertical prefix inside the band from
+//      Vb, coalesced image reads), the tile is transposed through shared memory,
+//      lanes then own ROWS (continue the horizontal chain, carry in a register),
+//      and finally own columns again to evaluate the boxes and store one
+//      coalesced 128-byte row segment per output row.
+//
+// A band holds 32 table rows, i.e. 32 - wsize output rows (the box needs rows i
+// and i + wsize), so bands overlap by wsize rows.
+#include "common.cuh"
+
+namespace msn {
+
+constexpr int kSadTile = 32;
+constexpr int kSadMaxW = 16;                       // wsize <= 16
+constexpr int kSadVStride = kSadTile + 1;          // tV[32][33]
+constexpr int kSadSStride = kSadTile + kSadMaxW + 1;  // tS[32][49]: halo(wsize) + 32 columns
+constexpr int kSadWarps = 4;
+
+__device__ __forceinline__ float absdiff_rn(float a, float b) { return fabsf(__fsub_rn(a, b)); }
+
+// grid: (ceil(IW/128), Dn, N); thread = table column j in [0, W].
+__global__ void sadsob_vband_kernel(const float* __restrict__ L, const float* __restrict__ R, int H, int W,
+                                    int d_begin, int RB, int NB, size_t img_stride,
+                                    float* __restrict__ Vb) {
+  const int IW = W + 1;
+  const int j = blockIdx.x * blockDim.x + threadIdx.x;
+  const int dd = blockIdx.y, d = d_begin + dd, n = blockIdx.z;
+  if (j >= IW) return;
+  const int jc = j - 1;
+  const bool active = (jc >= d);  // implies jc >= 0; jc < W because j <= W
+  const float* l = L + n * img_stride + jc;
+  const float* r = R + n * img_stride + (jc - d);
+  float* vb = Vb + (((size_t)n * gridDim.y + dd) * NB) * IW + j;
+  float v = 0.f;
+  int band = 0;
+  for (int row = 0; row < H; ++row) {
+    if (band < NB && row == band * RB) {
+      vb[(size_t)band * IW] = v;
+      ++band;
+    }
+    if (active) v = __fadd_rn(v, absdiff_rn(l[(size_t)row * W], r[(size_t)row * W]));
+  }
+}
+
+// grid: (ceil(Dn*NB / kSadWarps), 1, N); one warp per (dd, band).
+__global__ void __launch_bounds__(kSadWarps * 32)
+sadsob_scan_kernel(const float* __restrict__ L, const float* __restrict__ R, int H, int W, int Dn,
+                   int d_begin, int wsize, int RB, int NB, size_t img_stride,
+                   const float* __restrict__ Vb, float* __restrict__ out, size_t out_stride) {
+  __shared__ float sV[kSadWarps][kSadTile * kSadVStride];
+  __shared__ float sS[kSadWarps][kSadTile * kSadSStride];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int job = blockIdx.x * kSadWarps + warp;
+  if (job >= Dn * NB) return;  // whole warp exits together
+  const int dd = job / NB, b = job % NB, n = blockIdx.z;
+  const int d = d_begin + dd;
+  const int IW = W + 1, wc = wsize / 2;
+  const int i0 = b * RB;
+  float* tV = sV[warp];
+  float* tS = sS[warp];
+  const float* Ln = L + n * img_stride;
+  const float* Rn = R + n * img_stride;
+  const float* vb = Vb + (((size_t)n * Dn + dd) * NB + b) * IW;
+  float* o = out + n * out_stride + (size_t)dd * H * W;
+
+  // table columns <= d are zero, so the sweep starts at the tile holding column d
+  const int t0 = d / kSadTile, t1 = (W - 1) / kSadTile;
+  float s = 0.f;  // horizontal carry of table row i0 + lane
+#pragma unroll 1
+  for (int k = 0; k < wsize; ++k) tS[lane * kSadSStride + kSadTile + k] = 0.f;
+  for (int t = t0; t <= t1; ++t) {
+    // (a) lanes own table columns: finish the vertical prefix inside the band
+    const int j = t * kSadTile + lane;
+    const int jc = j - 1;
+    const bool active = (j < IW) && (jc >= d);
+    float v = (j < IW) ? vb[j] : 0.f;
+    tV[lane] = v;
+    const float* lp = Ln + (size_t)i0 * W + jc;
+    const float* rp = Rn + (size_t)i0 * W + (jc - d);
+#pragma unroll 8
+    for (int r = 1; r < kSadTile; ++r) {
+      if (active && (i0 + r - 1) < H)
+        v = __fadd_rn(v, absdiff_rn(lp[(size_t)(r - 1) * W], rp[(size_t)(r - 1) * W]));
+      tV[r * kSadVStride + lane] = v;
+    }
+    __syncwarp();
+    // (b) lanes own table rows: slide the halo, continue the horizontal chain
+    for (int k = 0; k < wsize; ++k)
+      tS[lane * kSadSStride + k] = tS[lane * kSadSStride + kSadTile + k];
+#pragma unroll 8
+    for (int c = 0; c < kSadTile; ++c) {
+      s = __fadd_rn(s, tV[lane * kSadVStride + c]);
+      tS[lane * kSadSStride + wsize + c] = s;
+    }
+    __syncwarp();
+    // (c) lanes own origin columns again: boxes ((br - bl) - tr) + tl
+    const int jo = t * kSadTile - wsize + lane;  // window origin column
+    if (jo >= d && jo < W - wsize) {
+      for (int r = 0; r < RB; ++r) {
+        const int i = i0 + r;
+        if (i >= H - wsize) break;
+        const float br = tS[(r + wsize) * kSadSStride + lane + wsize];
+        const float bl = tS[(r + wsize) * kSadSStride + lane];
+        const float tr = tS[r * kSadSStride + lane + wsize];
+        const float tl = tS[r * kSadSStride + lane];
+        const float val = __fadd_rn(__fsub_rn(__fsub_rn(br, bl), tr), tl);
+        st_stream(o + (size_t)(i + wc) * W + (jo + wc), val);
+      }
+    }
+    __syncwarp();
+  }
+}
+
+static inline void sadsob_geom(int H, int wsize, int* RB, int* NB) {
+  *RB = kSadTile - wsize;
+  const int rows = H - wsize;  // origin rows i in [0, H - wsize)
+  *NB = rows > 0 ? (rows + *RB - 1) / *RB : 0;
+}
+
+size_t sadsob_workspace_bytes_n(int N, int H, int W, int Dn, int wsize) {
+  int RB, NB;
+  sadsob_geom(H, wsize, &RB, &NB);
+  return (size_t)N * Dn * (NB > 0 ? NB : 1) * (W + 1) * sizeof(float);
+}
+size_t sadsob_workspace_bytes(int H, int W, int D, int wsize) {
+  return sadsob_workspace_bytes_n(1, H, W, D, wsize);
+}
+
+// N pairs; L/R are float [N][H][W]; out is [N][Dn][H][W] with stride out_stride floats per pair.
+int launch_sadsob_n(const float* L, const float* R, int N, int H, int W, int Dn, int d_begin, int wsize,
+                    float* out, size_t out_stride, bool write_fill, void* workspace, cudaStream_t s) {
+  MSN_REQUIRE(wsize >= 1 && wsize <= kSadMaxW, "sadsob: wsize %d unsupported (1..%d)", wsize, kSadMaxW);
+  if (write_fill) {
+    for (int n = 0; n < N; ++n)
+      if (launch_fill(out + n * out_stride, (size_t)Dn * H * W, kFill, s)) return 1;
+  }
+  int RB, NB;
+  sadsob_geom(H, wsize, &RB, &NB);
+  if (NB <= 0 || W - wsize <= 0 || Dn <= 0) return 0;
+  float* Vb = static_cast<float*>(workspace);
+  dim3 g1(div_up(W + 1, 128), Dn, N);
+  sadsob_vband_kernel<<<g1, 128, 0, s>>>(L, R, H, W, d_begin, RB, NB, (size_t)H * W, Vb);
+  MSN_LAUNCH_OK();
+  dim3 g2(div_up((long long)Dn * NB, kSadWarps), 1, N);
+  sadsob_scan_kernel<<<g2, kSadWarps * 32, 0, s>>>(L, R, H, W, Dn, d_begin, wsize, RB, NB, (size_t)H * W, Vb,
+                                                   out, out_stride);
+  MSN_LAUNCH_OK();
+  return 0;
+}
+
+int launch_sadsob(const float* L, const float* R, int H, int W, int D, int d_begin, int wsize, float* out,
+                  bool write_fill, void* workspace, cudaStream_t s) {
+  return launch_sadsob_n(L, R, 1, H, W, D, d_begin, wsize, out, (size_t)D * H * W, write_fill, workspace, s);
+}
+
+}  // namespace msn

@@ -1,0 +1,102 @@
+"""Soft-argmin disparity regression: drop-in for `F.softmax(out, 1)` followed by
+`disparityregression` (src/models/gcnet_3dcnn.py:127-141; duplicate modules at
+gcnet_3dcnn.py:46-54, psmnet_3dcnn.py:28-37, basic_convs.py:279-287).
+
+The reference splits the op in two (softmax, then sum(prob * arange)); both halves
+are kept so either call site can be swapped:
+
+    soft_argmin(logits)                  fused softmax + expectation, one pass
+    disparityregression(maxdisp)(prob)   module with the reference's signature; fed
+                                         probabilities it returns sum_d d * prob_d
+    patch_gcnet(model)                   swaps model.disparityregression and makes
+                                         the final softmax+regression one kernel
+"""
+import numpy as np
+
+from . import _lib
+
+
+def _torch():
+    import torch
+    return torch
+
+
+def soft_argmin(logits, out=None):
+    """logits: float32 [N,D,H,W] (CUDA tensor or NumPy array) -> disp float32 [N,H,W]."""
+    if isinstance(logits, np.ndarray):
+        x = np.ascontiguousarray(logits, dtype=np.float32)
+        if x.ndim != 4:
+            raise ValueError("soft_argmin: expected [N,D,H,W]")
+        N, D, H, W = x.shape
+        res = np.empty((N, H, W), np.float32)
+        _lib.check(_lib.lib().msn_soft_argmin_host(x.ctypes.data, N, D, H, W, res.ctypes.data))
+        return res
+    torch = _torch()
+    if logits.dim() != 4 or logits.dtype != torch.float32:
+        raise ValueError("soft_argmin: expected a float32 [N,D,H,W] tensor")
+    if not logits.is_cuda:
+        raise _lib.MsnetsError("soft_argmin: tensor must live on a CUDA device (no CPU fallback)")
+    x = logits.contiguous()
+    N, D, H, W = x.shape
+    if out is None:
+        out = torch.empty((N, H, W), dtype=torch.float32, device=x.device)
+    with torch.cuda.device(x.device):
+        _lib.check(_lib.lib().msn_soft_argmin_dev(x.data_ptr(), N, D, H, W, out.data_ptr(),
+                                                  torch.cuda.current_stream().cuda_stream))
+    return out
+
+
+def expected_disparity(prob, out=None):
+    """sum_d d * prob_d for probabilities [N,D,H,W]: the body of the reference's
+    disparityregression (gcnet_3dcnn.py:136-139) without materialising
+    arange(D).repeat(N,1,H,W) or the product tensor."""
+    torch = _torch()
+    if prob.dim() != 4 or prob.dtype != torch.float32:
+        raise ValueError("disparityregression: expected a float32 [N,D,H,W] tensor")
+    if not prob.is_cuda:
+        raise _lib.MsnetsError("disparityregression: tensor must live on a CUDA device (no CPU fallback)")
+    x = prob.contiguous()
+    N, D, H, W = x.shape
+    if out is None:
+        out = torch.empty((N, H, W), dtype=torch.float32, device=x.device)
+    with torch.cuda.device(x.device):
+        _lib.check(_lib.lib().msn_expect_disp_dev(x.data_ptr(), N, D, H, W, out.data_ptr(),
+                                                  torch.cuda.current_stream().cuda_stream))
+    return out
+
+
+def _module_base():
+    import torch.nn as nn
+    return nn.Module
+
+
+class disparityregression(_module_base()):
+    """Same constructor/forward signature as the reference module (gcnet_3dcnn.py:46-54)."""
+
+    def __init__(self, maxdisp, sumKeepDim=False):
+        super(disparityregression, self).__init__()
+        self.maxdisp = int(maxdisp)
+        self.sumKeepDim = sumKeepDim
+
+    def forward(self, x):
+        if x.size(1) != self.maxdisp:
+            raise AssertionError("%d != %d" % (x.size(1), self.maxdisp))  # gcnet_3dcnn.py:135
+        out = expected_disparity(x)
+        return out.unsqueeze(1) if self.sumKeepDim else out
+
+
+def patch_gcnet(model):
+    """Swaps the `disparityregression` method of a reference GCNet_CostVolumeAggre
+    (gcnet_3dcnn.py:132-141) for the expectation kernel.  The model's forward keeps
+    its own `F.softmax(out,1)` (:127); to fuse both halves replace lines :127-128 with
+    `disp = msnets_b200.regression.soft_argmin(out)`.
+    Inference only: the kernels carry no autograd."""
+    import types
+
+    def _regress(self, x):
+        N, D, H, W = x.size()[:]
+        assert D == self.maxdisp, "%d != %d" % (D, self.maxdisp)  # gcnet_3dcnn.py:135
+        return expected_disparity(x)
+
+    model.disparityregression = types.MethodType(_regress, model)
+    return model

@@ -1,0 +1,269 @@
+"""GPU parity tests proper: every function on the hot path, called THROUGH THE C ABI
+(ctypes -> libmsnets_b200.so), against the CPU oracle on the same seeded inputs and
+against the committed reference golden vectors.
+
+Parity classes (stated here as the bar):
+  bit-exact (np.array_equal): census, sobel, zsad, sadsob, nccNister, swap_axes,
+      get_right_cost / get_left_cost, extract_ratio, feature channels 0-3, WTA argmin,
+      LR mask, concat / diff volume
+  tolerance: AML (extract_likelihood, channels 4-7)  <= 2e-6 abs on [0,1] outputs
+             soft-argmin                             <= 1e-3 px
+"""
+import os
+
+import numpy as np
+import pytest
+
+from tests._synth import bordered_pair, synth_pair
+
+pytestmark = pytest.mark.gpu
+
+AML_ATOL = 2e-6
+SOFTARGMIN_ATOL = 1e-3
+
+
+@pytest.fixture(scope="module")
+def ms():
+    import msnets_b200
+    assert msnets_b200.device_count() >= 1
+    return msnets_b200
+
+
+SHAPES = [(40, 56, 12, 11), (37, 53, 64, 12), (64, 97, 33, 13), (30, 130, 128, 14)]
+
+
+@pytest.mark.parametrize("H,W,D,seed", SHAPES)
+def test_matchers_default_windows_bit_exact(ms, oracle, H, W, D, seed):
+    L, R = synth_pair(H, W, seed, shift=5)
+    mtc = ms.libmatchers
+    assert np.array_equal(mtc.census(L, R, D, 11), oracle.census(L, R, D, 11))
+    assert np.array_equal(mtc.nccNister(L, R, D, 3), oracle.nccNister(L, R, D, 3))
+    assert np.array_equal(mtc.zsad(L, R, D, 5), oracle.zsad(L, R, D, 5))
+    sl, sr = mtc.sobel(L), mtc.sobel(R)
+    assert np.array_equal(sl, oracle.sobel(L)) and np.array_equal(sr, oracle.sobel(R))
+    assert np.array_equal(mtc.sadsob(sl, sr, D, 5), oracle.sadsob(sl, sr, D, 5))
+
+
+@pytest.mark.parametrize("censw,nccw,sadw,sobelw", [(7, 5, 3, 3), (9, 7, 7, 7), (5, 1, 1, 9), (16, 4, 6, 16)])
+def test_matchers_other_windows_bit_exact(ms, oracle, censw, nccw, sadw, sobelw):
+    H, W, D = 48, 75, 20
+    L, R = synth_pair(H, W, 99 + censw, shift=4)
+    mtc = ms.libmatchers
+    assert np.array_equal(mtc.census(L, R, D, censw), oracle.census(L, R, D, censw))
+    assert np.array_equal(mtc.nccNister(L, R, D, nccw), oracle.nccNister(L, R, D, nccw))
+    assert np.array_equal(mtc.zsad(L, R, D, sadw), oracle.zsad(L, R, D, sadw))
+    sl, sr = oracle.sobel(L), oracle.sobel(R)
+    assert np.array_equal(mtc.sadsob(sl, sr, D, sobelw), oracle.sadsob(sl, sr, D, sobelw))
+
+
+def test_sadsob_generic_float_inputs_and_big_sums(ms, oracle):
+    """sadsob takes any float32 images; large values push the running sums far past 2^24,
+    where only the replayed add order stays bit-exact."""
+    rng = np.random.default_rng(5)
+    H, W, D = 70, 150, 40
+    a = (rng.standard_normal((H, W)) * 3000).astype(np.float32)
+    b = (rng.standard_normal((H, W)) * 3000).astype(np.float32)
+    assert np.array_equal(ms.libmatchers.sadsob(a, b, D, 5), oracle.sadsob(a, b, D, 5))
+
+
+def test_edge_images_smaller_than_window(ms, oracle):
+    L, R = synth_pair(9, 14, 3, shift=2, patches=False)
+    mtc = ms.libmatchers
+    c = mtc.census(L, R, 6, 11)
+    assert np.all(c == oracle.FILL) and np.array_equal(c, oracle.census(L, R, 6, 11))
+    assert np.array_equal(mtc.zsad(L, R, 6, 5), oracle.zsad(L, R, 6, 5))
+    assert np.array_equal(mtc.nccNister(L, R, 1, 3), oracle.nccNister(L, R, 1, 3))
+    sl, sr = mtc.sobel(L), mtc.sobel(R)
+    assert np.array_equal(mtc.sadsob(sl, sr, 6, 5), oracle.sadsob(sl, sr, 6, 5))
+    tiny = np.zeros((2, 3), np.uint8)
+    assert np.array_equal(mtc.sobel(tiny), oracle.sobel(tiny))
+
+
+def test_saturated_and_flat_images(ms, oracle):
+    """all-255 / all-0 pairs: every NCC window is degenerate (cost +1), census all zero."""
+    for val in (0, 255):
+        L = np.full((30, 44), val, np.uint8)
+        R = L.copy()
+        mtc = ms.libmatchers
+        assert np.array_equal(mtc.nccNister(L, R, 8, 3), oracle.nccNister(L, R, 8, 3))
+        assert np.array_equal(mtc.census(L, R, 8, 11), oracle.census(L, R, 8, 11))
+        assert np.array_equal(mtc.zsad(L, R, 8, 5), oracle.zsad(L, R, 8, 5))
+
+
+def test_featextract_functions(ms, oracle):
+    H, W, D = 33, 47, 24
+    L, R = synth_pair(H, W, 21, shift=3)
+    fte = ms.libfeatextract
+    dhw = oracle.zsad(L, R, D, 5)
+    hwd = oracle.census(L, R, D, 11)
+    assert np.array_equal(fte.swap_axes(dhw), oracle.swap_axes(dhw))
+    assert np.array_equal(fte.swap_axes_back(hwd), oracle.swap_axes_back(hwd))
+    assert np.array_equal(fte.get_right_cost(hwd), oracle.get_right_cost(hwd))
+    assert np.array_equal(fte.get_left_cost(hwd), oracle.get_left_cost(hwd))
+    rows = hwd.reshape(-1, D)
+    assert np.array_equal(fte.extract_ratio(rows, 0.01), oracle.extract_ratio(rows, 0.01))
+    for sigma, vol in ((128.0, hwd), (0.02, oracle.swap_axes(oracle.nccNister(L, R, D, 3))),
+                       (20000.0, oracle.swap_axes(dhw))):
+        rows = np.ascontiguousarray(vol.reshape(-1, D))
+        got, want = fte.extract_likelihood(rows, sigma), oracle.extract_likelihood(rows, sigma)
+        assert np.abs(got - want).max() <= AML_ATOL
+        assert np.array_equal(got == 0, want == 0) or np.abs(got - want).max() <= AML_ATOL
+    with pytest.raises(NotImplementedError):
+        fte.extract_likelihood(rows, rows, 1.0)
+    with pytest.raises(NotImplementedError):
+        fte.get_samples(rows, rows)
+
+
+def _check_features(got, want, lr=False):
+    assert got.shape == want.shape and got.dtype == np.float32
+    nviews = 2 if lr else 1
+    for v in range(nviews):
+        b = 8 * v
+        assert np.array_equal(got[b:b + 4], want[b:b + 4]), "normalised channels must be bit-exact"
+        assert np.abs(got[b + 4:b + 8] - want[b + 4:b + 8]).max() <= AML_ATOL
+
+
+@pytest.mark.parametrize("H,W,D,border", [(44, 60, 16, 10), (52, 71, 40, 12), (36, 90, 100, 10)])
+def test_get_costs_and_extract_features_mirror(ms, oracle, H, W, D, border):
+    L, R = synth_pair(H, W, 300 + D, shift=6)
+    costs = ms.cbmv.get_costs(L, R, D, 11, 3, 5, 5, border, border, border)
+    want = oracle.get_costs(L, R, D, 11, 3, 5, 5, border, border, border)
+    for a, b in zip(costs, want):
+        assert a.flags["C_CONTIGUOUS"] and np.array_equal(a, b)
+    _check_features(ms.cbmv.extract_features_left(*costs), oracle.extract_features_left(*want))
+    _check_features(ms.cbmv.extract_features_lr(*costs), oracle.extract_features_lr(*want), lr=True)
+
+
+@pytest.mark.parametrize("left_only", [True, False])
+@pytest.mark.parametrize("H,W,D,bh,bl,br", [(44, 60, 16, 10, 10, 10), (50, 83, 48, 12, 20, 0), (40, 70, 96, 10, 10, 10)])
+def test_ms_features_one_call(ms, oracle, H, W, D, bh, bl, br, left_only):
+    L, R = synth_pair(H, W, 500 + W, shift=5)
+    got = ms.cbmv.ms_features(L, R, D, left_only=left_only, board_h=bh, board_w_left=bl, board_w_right=br)
+    want = oracle.ms_features(L, R, D, board_h=bh, board_w_left=bl, board_w_right=br, left_only=left_only)
+    _check_features(got, want, lr=not left_only)
+
+
+def test_ms_features_generic_path_matches(ms, oracle, monkeypatch):
+    """the three-phase global-memory path (used for slabs and non-default windows)."""
+    monkeypatch.setenv("MSNETS_FORCE_GENERIC", "1")
+    L, R = synth_pair(48, 66, 77, shift=4)
+    got = ms.cbmv.ms_features(L, R, 24, board_h=10, board_w_left=10, board_w_right=10)
+    want = oracle.ms_features(L, R, 24)
+    _check_features(got, want)
+    got = ms.cbmv.ms_features(L, R, 24, censw=9, nccw=5, sadw=3, sobelw=7, board_h=8, board_w_left=8,
+                              board_w_right=8)
+    costs = oracle.get_costs(L, R, 24, 9, 5, 3, 7, 8, 8, 8)
+    _check_features(got, oracle.extract_features_left(*costs))
+
+
+def test_ms_features_batch_is_independent(ms):
+    pairs = [synth_pair(44, 64, s, shift=3) for s in (1, 2, 3)]
+    L = np.stack([p[0] for p in pairs])
+    R = np.stack([p[1] for p in pairs])
+    both = ms.cbmv.ms_features(L, R, 16)
+    for i in range(3):
+        assert np.array_equal(both[i], ms.cbmv.ms_features(L[i], R[i], 16))
+
+
+def test_against_reference_golden(ms, golden_dir):
+    """the committed outputs of the unmodified reference (tests/golden/make_golden.py)."""
+    for case in ("small_a", "small_b", "small_c"):
+        g = np.load(os.path.join(golden_dir, case + ".npz"))
+        H, W, D, seed, shift, border = (int(v) for v in g["meta"])
+        L, R = g["L"], g["R"]
+        mtc = ms.libmatchers
+        assert np.array_equal(mtc.census(L, R, D, 11), g["census"])
+        assert np.array_equal(mtc.nccNister(L, R, D, 3), g["ncc"])
+        assert np.array_equal(mtc.zsad(L, R, D, 5), g["zsad"])
+        assert np.array_equal(mtc.sobel(L), g["sobel_l"])
+        assert np.array_equal(mtc.sadsob(mtc.sobel(L), mtc.sobel(R), D, 5), g["sadsob"])
+        f = ms.cbmv.ms_features(L, R, D, board_h=border, board_w_left=border, board_w_right=border)
+        _check_features(f, g["features_left"])
+
+
+def test_soft_argmin(ms, oracle, golden_dir):
+    import torch
+    g = np.load(os.path.join(golden_dir, "soft_argmin.npz"))
+    for name in ("sa_small", "sa_peaky", "sa_flat"):
+        x = g[name + "_x"]
+        assert np.abs(ms.regression.soft_argmin(x) - g[name + "_y"]).max() <= SOFTARGMIN_ATOL
+    rng = np.random.default_rng(8)
+    for shape in ((2, 192, 20, 32), (1, 48, 7, 9), (3, 5, 4, 4)):
+        x = (rng.standard_normal(shape) * 4).astype(np.float32)
+        want = oracle.soft_argmin(x)
+        got = ms.regression.soft_argmin(torch.from_numpy(x).cuda()).cpu().numpy()
+        assert np.abs(got - want).max() <= SOFTARGMIN_ATOL
+        prob = torch.softmax(torch.from_numpy(x).cuda(), 1)
+        mod = ms.regression.disparityregression(shape[1])
+        assert np.abs(mod(prob).cpu().numpy() - want).max() <= SOFTARGMIN_ATOL
+    onehot = np.full((1, 32, 4, 8), -1e4, np.float32)
+    onehot[0, 17] = 50.0
+    assert np.allclose(ms.regression.soft_argmin(onehot), 17.0, atol=1e-4)
+
+
+def test_wta_confidence_lrc(ms, oracle):
+    import torch
+    L, R = synth_pair(40, 70, 17, shift=6)
+    D = 32
+    hwd = oracle.census(L, R, D, 11)
+    am, m1, m2 = ms.confidence.wta(hwd, "hwd")
+    oam, om1, om2 = oracle.wta(hwd)
+    assert np.array_equal(am, oam) and np.array_equal(m1, om1) and np.array_equal(m2, om2)
+    ncc = oracle.nccNister(L, R, D, 3)  # negative costs, [D,H,W] plane layout
+    am, m1, m2 = ms.confidence.wta(torch.from_numpy(ncc).cuda(), "dhw")
+    oam, om1, om2 = oracle.wta(np.ascontiguousarray(ncc.transpose(1, 2, 0)))
+    assert np.array_equal(am.cpu().numpy(), oam) and np.array_equal(m1.cpu().numpy(), om1)
+    assert np.array_equal(m2.cpu().numpy(), om2)
+    conf = ms.confidence.pkrn_confidence(m1, m2, 0.01).cpu().numpy()
+    assert np.array_equal(conf, oracle.pkrn_confidence(om1, om2, 0.01))
+    dl, dr, mask = ms.confidence.lr_consistency(hwd, 1)
+    odl, odr, omask = oracle.lr_consistency(hwd, 1)
+    assert np.array_equal(dl, odl) and np.array_equal(dr, odr) and np.array_equal(mask, omask)
+
+
+def test_volume_builders(ms, oracle):
+    import torch
+    rng = np.random.default_rng(1234)
+    for (N, C, H, W, D) in ((2, 4, 6, 20, 8), (1, 3, 5, 13, 16)):
+        fl = rng.standard_normal((N, C, H, W)).astype(np.float32)
+        fr = rng.standard_normal((N, C, H, W)).astype(np.float32)
+        tl, tr = torch.from_numpy(fl).cuda(), torch.from_numpy(fr).cuda()
+        assert np.array_equal(ms.volume.concat_volume(tl, tr, D).cpu().numpy(), oracle.concat_volume(fl, fr, D))
+        assert np.array_equal(ms.volume.diff_volume(tl, tr, D).cpu().numpy(), oracle.diff_volume(fl, fr, D))
+
+
+def test_device_resident_extractor_matches_host_api(ms):
+    import torch
+    L, R = bordered_pair(32, 48, 9, border=10)
+    H, W = L.shape
+    ex = ms.cbmv.MSFeatureExtractor(2, H, W, maxdisp=24, board_h=10, board_w_left=10, board_w_right=10)
+    l = torch.from_numpy(np.stack([L, L])).cuda()
+    r = torch.from_numpy(np.stack([R, R])).cuda()
+    out = ex(l, r)
+    torch.cuda.synchronize()
+    want = ms.cbmv.ms_features(L, R, 24, board_h=10, board_w_left=10, board_w_right=10)
+    assert np.array_equal(out[0].cpu().numpy(), want) and np.array_equal(out[1].cpu().numpy(), want)
+
+
+def test_full_size_properties(ms):
+    """Config B of BASELINE.json (540x960, D=192, 10 px border) through size-independent
+    properties: channels in [0,1]; valid AML columns sum to 1; channel 0 holds k/120;
+    the run is deterministic; WTA over channel 0 equals WTA over its AML channel's argmax."""
+    import torch
+    L, R = bordered_pair(540, 960, 1234, border=10)
+    H, W = L.shape
+    ex = ms.cbmv.MSFeatureExtractor(1, H, W, maxdisp=192, board_h=10, board_w_left=10, board_w_right=10)
+    l, r = torch.from_numpy(L[None]).cuda(), torch.from_numpy(R[None]).cuda()
+    f = ex(l, r)
+    assert tuple(f.shape) == (1, 8, 192, 540, 960)
+    assert float(f.min()) >= 0.0 and float(f.max()) <= 1.0
+    s = f[0, 4:8].sum(1)
+    assert float((s - 1).abs().max()) <= 2e-5
+    k = f[0, 0] * 120.0
+    assert float((k - k.round()).abs().max()) <= 1e-4
+    f2 = ex(l, r)
+    assert torch.equal(f, f2)
+    am0 = ms.confidence.wta(f[0, 0].contiguous(), "dhw")[0]
+    assert torch.equal(am0.long(), f[0, 0].argmin(0))
+    # the true shift (7 px) wins the census WTA on the bulk of the image
+    assert float((am0[:, 200:] == 7).float().mean()) > 0.99
