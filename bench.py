@@ -1,0 +1,383 @@
+#!/usr/bin/env python
+"""bench.py -- BASELINE.json's metric on BASELINE.json's config.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference]
+
+metric : stereo pairs/sec for "MS features + cost volume + soft-argmin" at 540x960,
+         D=192 (BASELINE.json configs[1]: SceneFlow-shaped batch of 8 pairs per GPU).
+         In MS-GCNet the cost volume IS the 8-channel MS feature tensor
+         [N,8,D,h,w], so one step = that tensor for 8 pairs + the
+         soft-argmin over a [8,192,540,960] logit volume.
+step   : ours      -> prep + sadsob scan + fused volume kernel + soft-argmin kernel on
+                      cuda:<local rank>, inputs resident in HBM (value), and the same
+                      through the public API with pinned host buffers, H2D of the pairs
+                      and D2H of the disparities inside the timed region (e2e).
+         reference -> the reference's own CPU implementation (oracle/_ref = unmodified
+                      matchers.cpp / featextract.cpp compiled in the build container,
+                      driven by the NumPy glue restated in oracle/ms_oracle.py) on a
+                      bounded sample of the same workload, host cores only.
+Multi-GPU: one process per GPU (torchrun), pairs are independent -> weak scaling, no
+data-path collective; time = max over ranks.
+Prints ONE JSON line on rank 0.
+"""
+import argparse
+import ctypes
+import json
+import os
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+METRIC = "stereo pairs/sec (MS features+cost volume+soft-argmin, 540x960 D=192)"
+H_IMG, W_IMG, D_MAX, BORDER, BATCH = 540, 960, 192, 10, 8
+
+
+def peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.isfile(p):
+        try:
+            return float(json.load(open(p))["hbm_gbs"]), "MEASURED_PEAKS.json hbm_gbs (of measured)"
+        except Exception:
+            pass
+    return 6650.0, "B200_PROFILING.md fallback 6.65 TB/s (of fallback)"
+
+
+def algorithmic_bytes():
+    """compulsory traffic per pair."""
+    Hp, Wp = H_IMG + 2 * BORDER, W_IMG + 2 * BORDER
+    b_ms = 2 * Hp * Wp + 8 * D_MAX * H_IMG * W_IMG * 4
+    b_sa = 4 * D_MAX * H_IMG * W_IMG + 4 * H_IMG * W_IMG
+    return b_ms, b_sa
+
+
+class ClockSampler(threading.Thread):
+    """Samples SM clock / throttle reasons during the timed region (pynvml)."""
+
+    def __init__(self, index):
+        super().__init__(daemon=True)
+        self.index, self.stop_flag, self.samples, self.reasons, self.max_mhz = index, False, [], set(), None
+
+    def run(self):
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            h = pynvml.nvmlDeviceGetHandleByIndex(self.index)
+            self.max_mhz = pynvml.nvmlDeviceGetMaxClockInfo(h, pynvml.NVML_CLOCK_SM)
+            names = {0x2: "applications_clocks_setting", 0x4: "sw_power_cap", 0x8: "hw_slowdown",
+                     0x20: "sw_thermal_slowdown", 0x40: "hw_thermal_slowdown",
+                     0x80: "hw_power_brake_slowdown", 0x100: "display_clock_setting"}
+            while not self.stop_flag:
+                self.samples.append(pynvml.nvmlDeviceGetClockInfo(h, pynvml.NVML_CLOCK_SM))
+                try:
+                    r = pynvml.nvmlDeviceGetCurrentClocksEventReasons(h)
+                except Exception:
+                    r = pynvml.nvmlDeviceGetCurrentClocksThrottleReasons(h)
+                for bit, n in names.items():
+                    if r & bit:
+                        self.reasons.add(n)
+                time.sleep(0.05)
+        except Exception as e:  # never let the sampler kill the bench
+            self.reasons.add("sampler_error:%s" % type(e).__name__)
+
+    def summary(self):
+        s = sorted(self.samples)
+        return {"sm_mhz": s[len(s) // 2] if s else None, "sm_max_mhz": self.max_mhz,
+                "reasons": sorted(self.reasons), "samples": len(s)}
+
+
+def physical_index(local_rank):
+    vis = os.environ.get("CUDA_VISIBLE_DEVICES")
+    if vis:
+        try:
+            return int(vis.split(",")[local_rank])
+        except Exception:
+            return local_rank
+    return local_rank
+
+
+# --------------------------------------------------------------------- ours --
+def run_ours(args):
+    import numpy as np
+    import torch
+    import torch.distributed as dist
+
+    from tests._synth import bordered_pair
+
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device (the product has no CPU fallback)")
+    torch.cuda.set_device(local_rank)
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl")
+    import __graft_entry__
+    if rank == 0:
+        __graft_entry__.build()
+    if world > 1:
+        dist.barrier()
+    import msnets_b200
+    from msnets_b200 import _lib, cbmv, regression
+
+    dev = torch.device("cuda", local_rank)
+    Hb, Wb = H_IMG + 2 * BORDER, W_IMG + 2 * BORDER
+    # synthetic SceneFlow-shaped batch: seeded uniform pairs, 7 px shift,
+    # 10 px zero border; every rank gets its own pairs
+    NSETS = 2
+    host_l = torch.empty((NSETS, BATCH, Hb, Wb), dtype=torch.uint8).pin_memory()
+    host_r = torch.empty((NSETS, BATCH, Hb, Wb), dtype=torch.uint8).pin_memory()
+    for s in range(NSETS):
+        for i in range(BATCH):
+            L, R = bordered_pair(H_IMG, W_IMG, 1234 + 1000 * rank + 10 * s + i, border=BORDER)
+            host_l[s, i] = torch.from_numpy(L)
+            host_r[s, i] = torch.from_numpy(R)
+    dev_l, dev_r = host_l.to(dev), host_r.to(dev)
+    gen = torch.Generator(device=dev)
+    gen.manual_seed(1234 + rank)
+    logits = torch.randn((BATCH, D_MAX, H_IMG, W_IMG), generator=gen, device=dev, dtype=torch.float32)
+    ex = cbmv.MSFeatureExtractor(BATCH, Hb, Wb, maxdisp=D_MAX, board_h=BORDER, board_w_left=BORDER,
+                                 board_w_right=BORDER, device=dev)
+    feats = ex.empty_output()
+    disp = torch.empty((BATCH, H_IMG, W_IMG), dtype=torch.float32, device=dev)
+    host_disp = torch.empty((BATCH, H_IMG, W_IMG), dtype=torch.float32).pin_memory()
+
+    def step_resident(i):
+        s = i % NSETS
+        ex(dev_l[s], dev_r[s], out=feats)
+        regression.soft_argmin(logits, out=disp)
+
+    stage_l, stage_r = torch.empty_like(dev_l[0]), torch.empty_like(dev_r[0])
+
+    def step_e2e(i):
+        s = i % NSETS
+        stage_l.copy_(host_l[s], non_blocking=True)
+        stage_r.copy_(host_r[s], non_blocking=True)
+        ex(stage_l, stage_r, out=feats)
+        regression.soft_argmin(logits, out=disp)
+        host_disp.copy_(disp, non_blocking=True)
+        torch.cuda.current_stream().synchronize()   # the caller consumes the disparities
+
+    def timed(fn, steps, warmup, profile=False):
+        for i in range(warmup):
+            fn(i)
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+        if profile:
+            _lib.check(_lib.lib().msn_profile_enable(1))
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for i in range(steps):
+            fn(i)
+        e1.record()
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+        ms = e0.elapsed_time(e1)
+        prof = None
+        if profile:
+            a, b, c, n = ctypes.c_double(), ctypes.c_double(), ctypes.c_double(), ctypes.c_int()
+            _lib.check(_lib.lib().msn_profile_read(ctypes.byref(a), ctypes.byref(b), ctypes.byref(c), ctypes.byref(n)))
+            _lib.check(_lib.lib().msn_profile_enable(0))
+            prof = {"prep_ms": a.value, "sadsob_ms": b.value, "fused_ms": c.value, "calls": n.value}
+        if world > 1:
+            t = torch.tensor([ms], device=dev, dtype=torch.float64)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            ms = float(t.item())
+        return ms, prof
+
+    sampler = ClockSampler(physical_index(local_rank))
+    sampler.start()
+    ms_res, prof = timed(step_resident, args.steps, args.warmup, profile=True)
+    sampler.stop_flag = True
+    sampler.join(timeout=2)
+    ms_e2e, _ = timed(step_e2e, args.steps, min(args.warmup, 3))
+
+    # soft-argmin kernel alone (for the per-kernel breakdown)
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(args.steps):
+        regression.soft_argmin(logits, out=disp)
+    e1.record()
+    torch.cuda.synchronize()
+    sa_ms = e0.elapsed_time(e1) / args.steps
+
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return
+
+    pairs = BATCH * world * args.steps
+    value = pairs / (ms_res / 1e3)
+    e2e_value = pairs / (ms_e2e / 1e3)
+    b_ms, b_sa = algorithmic_bytes()
+    peak, peak_src = peaks()
+    fused_ms = prof["fused_ms"] / max(prof["calls"], 1)
+    achieved = BATCH * b_ms / (fused_ms / 1e3) / 1e9
+    traffic = None
+    tp = os.path.join(ROOT, "profiles", "roofline_traffic.json")
+    if os.path.isfile(tp):
+        try:
+            traffic = json.load(open(tp)).get("ms_fused_kernel_dram_bytes_per_launch")
+        except Exception:
+            traffic = None
+    step_ms = ms_res / args.steps
+    roofline = {
+        "bound": "hbm", "kernel": "ms_fused_kernel", "achieved": round(achieved, 1), "peak": peak,
+        "unit": "GB/s", "frac": round(achieved / peak, 4), "traffic": traffic,
+        "peak_source": peak_src,
+        "algorithmic_bytes_per_launch": BATCH * b_ms,
+        "kernel_ms_per_launch": round(fused_ms, 4),
+        "step_frac": round(BATCH * (b_ms + b_sa) / (step_ms / 1e3) / 1e9 / peak, 4),
+        "breakdown_ms_per_step": {"prep": round(prof["prep_ms"] / prof["calls"], 4),
+                                  "sadsob_scan": round(prof["sadsob_ms"] / prof["calls"], 4),
+                                  "ms_fused": round(fused_ms, 4), "soft_argmin": round(sa_ms, 4)},
+    }
+    cpu, dropin = None, None
+    if world == 1:
+        cpu = cpu_baseline_sample(budget_s=20.0)
+        # drop-in NumPy API, one pair, full 3.2 GB volume copied back to the host
+        t0 = time.time()
+        vol = cbmv.ms_features(host_l[0, 0].numpy(), host_r[0, 0].numpy(), D_MAX, board_h=BORDER,
+                               board_w_left=BORDER, board_w_right=BORDER)
+        dropin_s = time.time() - t0
+        dropin = {"pairs_per_s": round(1.0 / dropin_s, 3), "d2h_bytes": int(vol.nbytes),
+                  "note": "msn_ms_features_host, 1 pair, whole volume returned to pageable host memory"}
+        del vol
+    line = {
+        "metric": METRIC, "value": round(value, 2), "unit": "pairs/s", "n_gpus": world, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": round(step_ms, 4), "higher_is_better": True,
+        "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": "configs[1]: SceneFlow-shaped 540x960 D=192, batch 8 pairs per GPU: MS features "
+                               "[8,8,192,540,960] + soft-argmin over [8,192,540,960]",
+                   "pairs_per_step_per_gpu": BATCH, "border_px": BORDER, "windows": [11, 3, 5, 5],
+                   "parallelism": "batch-sharded x%d (no collective)" % world,
+                   "l2": "per-step working set 28.7 GB (25.5 GB written + 3.2 GB read) >> 126 MB L2; "
+                         "two input sets alternate; no flush needed"},
+        "clocks": sampler.summary(),
+        "e2e": {"value": round(e2e_value, 2), "unit": "pairs/s", "h2d_bytes_per_step": 2 * BATCH * Hb * Wb,
+                "d2h_bytes_per_step": BATCH * H_IMG * W_IMG * 4, "ms_per_step": round(ms_e2e / args.steps, 4),
+                "api": "MSFeatureExtractor(pinned uint8 pairs) -> soft_argmin -> pinned disparities"},
+        "gpu_launches": 5 * args.steps,
+        "roofline": roofline,
+        "cpu_baseline": cpu,
+        "numpy_dropin": dropin,
+    }
+    print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+# ---------------------------------------------------------------- reference --
+def _reference_modules():
+    from oracle import ms_oracle as O
+    ref = O.load_ref()
+    if ref is not None:
+        return O, ref[0], ref[1], "reference", "oracle/_ref (%s build of the unmodified matchers.cpp/featextract.cpp)" % ref[2]
+    O.lib()
+    return O, O.MTC, O.FTE, "port", "oracle/libms_oracle.so (C restatement)"
+
+
+def _cpu_step(O, mtc, fte, L, R, logits):
+    import torch
+    import torch.nn.functional as F
+    f = O.ms_features(L, R, D_MAX, board_h=BORDER, board_w_left=BORDER, board_w_right=BORDER, mtc=mtc, fte=fte)
+    x = torch.from_numpy(logits)
+    prob = F.softmax(x, 1)                                    # gcnet_3dcnn.py:127
+    d = torch.arange(D_MAX, dtype=torch.float32).view(1, D_MAX, 1, 1)
+    disp = torch.sum(prob * d, 1)                             # gcnet_3dcnn.py:136-139
+    return f, disp
+
+
+def _sample_inputs(rows):
+    import numpy as np
+
+    from tests._synth import bordered_pair
+    L, R = bordered_pair(rows, W_IMG, 1234, border=BORDER)
+    logits = np.random.default_rng(1234).standard_normal((1, D_MAX, rows, W_IMG)).astype(np.float32)
+    return L, R, logits
+
+
+def cpu_baseline_sample(budget_s=20.0):
+    """Times the CPU path on a bounded sample: a horizontal band of one 540x960 pair,
+    rows chosen from a 32-row calibration so the sample costs about budget_s."""
+    O, mtc, fte, kind, what = _reference_modules()
+    cores = int(mtc.initthreads()) if hasattr(mtc, "initthreads") else 1
+    L, R, lg = _sample_inputs(32)
+    t0 = time.time()
+    _cpu_step(O, mtc, fte, L, R, lg)
+    t32 = max(time.time() - t0, 1e-3)
+    rows = int(max(32, min(H_IMG, 32 * budget_s / t32)))
+    L, R, lg = _sample_inputs(rows)
+    t0 = time.time()
+    _cpu_step(O, mtc, fte, L, R, lg)
+    dt = time.time() - t0
+    frac = rows / float(H_IMG)
+    return {"value": round(frac / dt, 4), "unit": "pairs/s", "cores": cores, "kind": kind,
+            "sample": "%d of 540 rows (x960, D=192) of one pair: get_costs + extract_features_left + "
+                      "softmax/regression via %s; %d OpenMP threads (THREADS_NUM_USED, paramSetting.hpp:11); "
+                      "%d host cpus" % (rows, what, cores, os.cpu_count() or 0),
+            "seconds": round(dt, 2)}
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    O, mtc, fte, kind, what = _reference_modules()
+    cores = int(mtc.initthreads()) if hasattr(mtc, "initthreads") else 1
+    total = args.steps + args.warmup
+    L, R, lg = _sample_inputs(32)
+    t0 = time.time()
+    _cpu_step(O, mtc, fte, L, R, lg)
+    t32 = max(time.time() - t0, 1e-3)
+    per_step = 150.0 / max(total, 1)
+    rows = int(max(32, min(H_IMG, 32 * per_step / t32)))
+    L, R, lg = _sample_inputs(rows)
+    for _ in range(args.warmup):
+        _cpu_step(O, mtc, fte, L, R, lg)
+    t0 = time.time()
+    for _ in range(args.steps):
+        _cpu_step(O, mtc, fte, L, R, lg)
+    dt = time.time() - t0
+    frac = rows / float(H_IMG)
+    value = args.steps * frac / dt
+    sample = ("each step = %d of 540 rows (x960, D=192) of one pair through get_costs + extract_features_left "
+              "+ softmax/regression; %s; %d OpenMP threads; %d host cpus" % (rows, what, cores, os.cpu_count() or 0))
+    line = {
+        "impl": "reference", "metric": METRIC, "value": round(value, 4), "unit": "pairs/s",
+        "n_gpus": int(os.environ.get("WORLD_SIZE", "1")), "steps": args.steps, "warmup": args.warmup,
+        "ms_per_step": round(1e3 * dt / args.steps, 2), "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": "configs[1]: SceneFlow-shaped 540x960 D=192 MS features + soft-argmin, CPU reference",
+                   "sample_rows": rows},
+        "cpu_baseline": {"value": round(value, 4), "unit": "pairs/s", "cores": cores, "kind": kind, "sample": sample},
+        "e2e": {"value": round(value, 4), "unit": "pairs/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line))
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_ours(args)
+
+
+if __name__ == "__main__":
+    main()

@@ -116,6 +116,13 @@ MSN_API int msn_ms_features_dev(const uint8_t* d_left, const uint8_t* d_right, i
                         const msn_ms_params* p, float* d_out_ncdhw, void* d_workspace,
                         size_t workspace_bytes, void* stream);
 
+/* Measurement aid for bench.py: when enabled, msn_ms_features_dev brackets the kernels of
+ * the fused sequence (prep | sadsob scan | fused volume) with CUDA events on the launch
+ * stream; msn_profile_read synchronises, returns the summed milliseconds and the number
+ * of calls since the last read, and clears the records. */
+MSN_API int msn_profile_enable(int on);
+MSN_API int msn_profile_read(double* prep_ms, double* sadsob_ms, double* fused_ms, int* calls);
+
 /* Disparity-slab sharding: the AML of a pixel needs min and
  * sum over ALL disparities.  Phase A writes channels 0-3 for the slab, parks
  * the raw costs in channels 4-7 and emits per-pixel slab minima [N][4][h][w];

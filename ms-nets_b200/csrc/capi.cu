@@ -531,6 +531,11 @@ int msn_ms_features_host(const uint8_t* left, const uint8_t* right, int N, int H
   return ctx.finish();
 }
 
+int msn_profile_enable(int on) { return profile_enable(on); }
+int msn_profile_read(double* prep_ms, double* sadsob_ms, double* fused_ms, int* calls) {
+  return profile_read(prep_ms, sadsob_ms, fused_ms, calls);
+}
+
 // slab phases (multi-GPU disparity sharding); workspace sized by
 // msn_ms_slab_workspace_bytes for the slab in p.
 size_t msn_ms_slab_workspace_bytes(int N, int H, int W, const msn_ms_params* p) {

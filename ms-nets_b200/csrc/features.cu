@@ -22,7 +22,7 @@ features_from_costs_kernel(const float* __restrict__ c0, const float* __restrict
                            float k0, float k1, float k2, float k3, float* __restrict__ out) {
   extern __shared__ float tile[];  // [D][33]
   __shared__ float s_min[kFeatPix];
-  __shared__ float s_den[kFeatWarps][kFeatPix];
+  __shared__ float s_inv[kFeatPix];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int m = blockIdx.y & 3;          // matcher 0..3
   const bool right = (blockIdx.y >> 2);  // right-view channels 8..15
@@ -56,23 +56,30 @@ features_from_costs_kernel(const float* __restrict__ c0, const float* __restrict
   const long long p = p0 + lane;
   const bool live = p < n;
   const float mn = s_min[lane];
-  float den = 0.f;
-  if (live)
-    for (int d = warp; d < D; d += kFeatWarps) den += aml_e(tile[d * 33 + lane], mn, k);
-  s_den[warp][lane] = den;
-  __syncthreads();
-  den = 0.f;
-#pragma unroll
-  for (int i = 0; i < kFeatWarps; ++i) den += s_den[i][lane];
-  const float inv = (mn == kFill) ? 0.f : 1.0f / den;
-  if (!live) return;
-  float* o_norm = out + ((size_t)((right ? 8 : 0) + m) * D) * n + p;
-  float* o_aml = out + ((size_t)((right ? 8 : 0) + 4 + m) * D) * n + p;
-  for (int d = warp; d < D; d += kFeatWarps) {
-    const float v = tile[d * 33 + lane];
-    st_stream(o_norm + (size_t)d * n, normalise_cost(v, m));
-    st_stream(o_aml + (size_t)d * n, aml_e(v, mn, k) * inv);
+  // normalised plane out, exponentials into the tile
+  if (live) {
+    float* o_norm = out + ((size_t)((right ? 8 : 0) + m) * D) * n + p;
+    for (int d = warp; d < D; d += kFeatWarps) {
+      const float v = tile[d * 33 + lane];
+      st_stream(o_norm + (size_t)d * n, normalise_cost(v, m));
+      tile[d * 33 + lane] = aml_e(v, mn, k);
+    }
   }
+  __syncthreads();
+  // denominator in the reference's order: sequential fp32 over d (featextract.cpp:444-447)
+  if (warp == 0) {
+    float den = 0.f;
+    if (live) {
+#pragma unroll 8
+      for (int d = 0; d < D; ++d) den = __fadd_rn(den, tile[d * 33 + lane]);
+    }
+    s_inv[lane] = (mn == kFill) ? 0.f : 1.0f / den;
+  }
+  __syncthreads();
+  if (!live) return;
+  const float inv = s_inv[lane];
+  float* o_aml = out + ((size_t)((right ? 8 : 0) + 4 + m) * D) * n + p;
+  for (int d = warp; d < D; d += kFeatWarps) st_stream(o_aml + (size_t)d * n, tile[d * 33 + lane] * inv);
 }
 
 int launch_features_from_costs(const float* census, const float* ncc, const float* sobel, const float* sad,

@@ -86,33 +86,64 @@ __device__ __forceinline__ float warp_sum(float v) {
   return v;
 }
 
-// One warp per row of D costs.  min (strict <, start fill) -> sum of e -> e/den;
-// the whole row is 0 when the minimum is still fill (featextract.cpp:435-453).
-__global__ void aml_rows_kernel(const float* __restrict__ cost, long long n, int D, float k,
-                                float* __restrict__ out) {
-  const long long row = (long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
-  const int lane = threadIdx.x & 31;
-  if (row >= n) return;
-  const float* c = cost + row * D;
-  float* o = out + row * D;
-  float m = kFill;
-  for (int d = lane; d < D; d += 32) m = fminf(m, c[d]);
-  m = warp_min(m);
-  if (m == kFill) {
-    for (int d = lane; d < D; d += 32) st_stream(o + d, 0.f);
-    return;
+// AML over rows of D costs (featextract.cpp:415-462).  The reference sums the
+// denominator SEQUENTIALLY in fp32 (:444-447): terms below half an ulp of the running
+// sum are dropped, which moves the result by up to D * 2^-24 relative.  To stay inside
+// the 2e-6 tolerance the same order is replayed: a CTA stages 32 rows through shared
+// memory ([D][33], coalesced both ways), all warps compute the exponentials, then one
+// thread per row adds them in order d = 0..D-1.
+constexpr int kAmlRows = 32;
+constexpr int kAmlWarps = 8;
+__global__ void __launch_bounds__(kAmlWarps * 32)
+aml_rows_kernel(const float* __restrict__ cost, long long n, int D, float k, float* __restrict__ out) {
+  extern __shared__ float tile[];  // [D][33]
+  __shared__ float s_min[kAmlRows];
+  __shared__ float s_inv[kAmlRows];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const long long r0 = (long long)blockIdx.x * kAmlRows;
+  for (int r = warp; r < kAmlRows; r += kAmlWarps) {
+    float m = kFill;
+    if (r0 + r < n) {
+      const float* c = cost + (r0 + r) * D;
+      for (int d = lane; d < D; d += 32) {
+        const float v = c[d];
+        tile[d * 33 + r] = v;
+        m = fminf(m, v);
+      }
+    }
+    m = warp_min(m);
+    if (lane == 0) s_min[r] = m;
   }
-  float den = 0.f;
-  for (int d = lane; d < D; d += 32) den += aml_e(c[d], m, k);
-  den = warp_sum(den);
-  const float inv = 1.0f / den;
-  for (int d = lane; d < D; d += 32) st_stream(o + d, aml_e(c[d], m, k) * inv);
+  __syncthreads();
+  {
+    const float m = s_min[lane];
+    if (r0 + lane < n)
+      for (int d = warp; d < D; d += kAmlWarps) tile[d * 33 + lane] = aml_e(tile[d * 33 + lane], m, k);
+  }
+  __syncthreads();
+  if (warp == 0) {
+    float den = 0.f;
+    if (r0 + lane < n) {
+#pragma unroll 8
+      for (int d = 0; d < D; ++d) den = __fadd_rn(den, tile[d * 33 + lane]);
+    }
+    s_inv[lane] = (s_min[lane] == kFill) ? 0.f : 1.0f / den;
+  }
+  __syncthreads();
+  for (int r = warp; r < kAmlRows; r += kAmlWarps) {
+    if (r0 + r >= n) break;
+    const float inv = s_inv[r];
+    float* o = out + (r0 + r) * D;
+    for (int d = lane; d < D; d += 32) st_stream(o + d, tile[d * 33 + r] * inv);
+  }
 }
 
 int launch_aml_rows(const float* cost, long long n, int D, float sigma, float* out, cudaStream_t s) {
   if (n == 0 || D == 0) return 0;
-  const float k = aml_scale(sigma);
-  aml_rows_kernel<<<div_up(n, 8), 256, 0, s>>>(cost, n, D, k, out);
+  const size_t smem = (size_t)D * 33 * sizeof(float);
+  MSN_REQUIRE(smem <= 200 * 1024, "extract_likelihood: D=%d needs %zu B of shared memory (max 200 KiB)", D, smem);
+  MSN_CUDA_OK(cudaFuncSetAttribute(aml_rows_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  aml_rows_kernel<<<div_up(n, kAmlRows), kAmlWarps * 32, smem, s>>>(cost, n, D, aml_scale(sigma), out);
   MSN_LAUNCH_OK();
   return 0;
 }

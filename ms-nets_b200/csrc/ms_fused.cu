@@ -1,9 +1,529 @@
-// ms_fused.cu -- placeholder until the fused kernel lands (generic path is used).
+// ms_fused.cu -- the throughput path: MS feature volume [N][8][D][h][w] straight from
+// the uint8 pair, no intermediate cost volumes except the sadsob scratch.
+//
+// Replaces, in one pass, get_costs (census + nccNister + zsad + sobel/sadsob +
+// 3x swap_axes + border crop, cbmv_generator.py:27-79) and extract_features_left
+// (clip/normalise, 4x extract_likelihood, float64 scratch, transpose + cast,
+// cbmv_generator.py:258-308) for the default windows 11/3/5/5.
+//
+// Launch sequence (all on one stream):
+//   1. ms_prep_kernel    per padded pixel of every image: census code (4x u32), ZSAD
+//                        window mean, NCC window sum A and fp64 C = 1/sqrt(9B - A^2),
+//                        float copy of the pixel, Sobel response.
+//   2. sadsob vband+scan (sadsob.cu) -> raw SAD-of-Sobel volume [N][D][H][W]; its fp32
+//                        summed-area table needs whole-row sequential scans, so it
+//                        cannot live inside an x-tile.
+//   3. ms_fused_kernel   one CTA = one output row y x 32 pixels x ALL D:
+//        phase 1  8 warps split D; lane = pixel.  Per (pixel, d): census popcount,
+//                 NCC (9 fp32 products of exact integers, fp64 scaling), ZSAD (75
+//                 ordered fp32 adds over a register-resident 5x5 window that slides
+//                 with d), sadsob load; channels 0-3 are normalised and stored as four
+//                 128-byte row segments per warp; raw costs are parked in shared
+//                 memory (13 B/voxel: three floats + census byte); per-pixel minima.
+//        phase 2  exponentials exp(-(c-m)^2/sigma) written over the parked costs.
+//        phase 3  one thread per (pixel, matcher) adds the denominator in d order
+//                 (the reference's sequential fp32 sum, featextract.cpp:444-447).
+//        phase 4  channels 4-7 = e / den, again 128-byte segments per warp.
+//
+// Bounding resource: HBM writes (32 B per voxel) co-limited by issue slots -- ZSAD
+// alone is 75 dependent-order FADDs per voxel (DESIGN.md has the arithmetic).
 #include "ms_fused.cuh"
+
+#include <mutex>
+#include <vector>
+
+#include "feature_math.cuh"
+
 namespace msn {
-bool fused_supported(const msn_ms_params*, int) { return false; }
-size_t fused_workspace_bytes(int, int, int, int, const msn_ms_params*) { return 0; }
-int launch_ms_fused(const uint8_t*, const uint8_t*, int, int, int, const msn_ms_params*, float*, char*, cudaStream_t) {
-  return fail("fused kernel not built");
+
+namespace {
+
+constexpr int kWarps = 8;
+constexpr int kTile = 32;     // pixels per CTA
+constexpr int kPadT = 2;      // padded rows above/below (ZSAD halo)
+constexpr int kPadR = 40;     // padded columns to the right (tile overhang + halo)
+constexpr int kCensW = 11, kNccW = 3, kSadW = 5;
+constexpr int kMaxFusedD = 448;
+
+struct __align__(16) RStat {
+  float mean;  // ZSAD window mean (matchers.cpp:482)
+  float A;     // NCC window sum, exact integer <= 2295 (matchers.cpp:140)
+  double C;    // 1/sqrt(9*B - A*A) in fp64 (matchers.cpp:146)
+};
+
+struct FusedGeom {
+  int N, H, W, h, w, D, bh, bwl;
+  int Hp, Wp, padL;
+  __host__ __device__ size_t img_px() const { return (size_t)Hp * Wp; }
+};
+
+FusedGeom make_geom(int N, int H, int W, const msn_ms_params* p) {
+  FusedGeom g;
+  g.N = N; g.H = H; g.W = W; g.D = p->ndisp;
+  g.bh = p->board_h; g.bwl = p->board_w_left;
+  g.h = H - 2 * p->board_h;
+  g.w = W - p->board_w_left - p->board_w_right;
+  g.padL = (g.D + 1 + 7) & ~7;
+  g.Hp = H + 2 * kPadT;
+  g.Wp = (W + g.padL + kPadR + 3) & ~3;
+  return g;
 }
+
+struct FusedWs {
+  uint4* desc[2];
+  RStat* stat[2];
+  float* fimg[2];
+  float* sob[2];
+  float* sadsob;   // [N][D][H][W]
+  void* sad_ws;
+  size_t total;
+  void carve(char* base, const FusedGeom& g) {
+    size_t off = 0;
+    auto take = [&](size_t bytes) { char* q = base ? base + off : nullptr; off += (bytes + 255) & ~(size_t)255; return q; };
+    const size_t np = (size_t)g.N * g.img_px(), n = (size_t)g.N * g.H * g.W;
+    for (int i = 0; i < 2; ++i) desc[i] = (uint4*)take(np * sizeof(uint4));
+    for (int i = 0; i < 2; ++i) stat[i] = (RStat*)take(np * sizeof(RStat));
+    for (int i = 0; i < 2; ++i) fimg[i] = (float*)take(np * sizeof(float));
+    for (int i = 0; i < 2; ++i) sob[i] = (float*)take(n * sizeof(float));
+    sadsob = (float*)take(n * g.D * sizeof(float));
+    sad_ws = take(sadsob_workspace_bytes_n(g.N, g.H, g.W, g.D, kSadW));
+    total = off;
+  }
+};
+
+// ------------------------------------------------------------------ prep --
+// grid (ceil(Wp/128), Hp, 2N); blockIdx.z = 2*n + side.
+__global__ void __launch_bounds__(128)
+ms_prep_kernel(const uint8_t* __restrict__ left, const uint8_t* __restrict__ right, FusedGeom g,
+               uint4* __restrict__ descL, uint4* __restrict__ descR, RStat* __restrict__ statL,
+               RStat* __restrict__ statR, float* __restrict__ fL, float* __restrict__ fR,
+               float* __restrict__ sobL, float* __restrict__ sobR) {
+  const int xp = blockIdx.x * blockDim.x + threadIdx.x;
+  const int yp = blockIdx.y;
+  const int n = blockIdx.z >> 1, side = blockIdx.z & 1;
+  if (xp >= g.Wp) return;
+  const int H = g.H, W = g.W;
+  const uint8_t* img = (side ? right : left) + (size_t)n * H * W;
+  const int X = xp - g.padL, Y = yp - kPadT;
+  const bool inside = (X >= 0 && X < W && Y >= 0 && Y < H);
+  const size_t po = (size_t)n * g.img_px() + (size_t)yp * g.Wp + xp;
+
+  uint32_t w0 = 0, w1 = 0, w2 = 0, w3 = 0;
+  RStat st;
+  st.mean = 0.f; st.A = 0.f; st.C = 0.0;
+  float pix = 0.f;
+  if (inside) {
+    const int c = img[(size_t)Y * W + X];
+    pix = (float)c;
+    // census 11x11: bit k = a*11+b set iff centre < tap (matchers.cpp:290-297)
+    if (Y >= 5 && Y < H - 6 && X >= 5 && X < W - 6) {
+      const uint8_t* org = img + (size_t)(Y - 5) * W + (X - 5);
+      uint32_t words[4] = {0u, 0u, 0u, 0u};
+#pragma unroll
+      for (int a = 0; a < kCensW; ++a) {
+#pragma unroll
+        for (int b = 0; b < kCensW; ++b) {
+          const int bit = a * kCensW + b;
+          const uint32_t v = (c < (int)__ldg(org + (size_t)a * W + b)) ? 1u : 0u;
+          words[bit >> 5] |= v << (bit & 31);
+        }
+      }
+      w0 = words[0]; w1 = words[1]; w2 = words[2]; w3 = words[3];
+    }
+    // ZSAD 5x5 mean: exact integer sum, one IEEE division (matchers.cpp:472-485)
+    if (Y >= 2 && Y < H - 3 && X >= 2 && X < W - 3) {
+      const uint8_t* org = img + (size_t)(Y - 2) * W + (X - 2);
+      int sum = 0;
+#pragma unroll
+      for (int a = 0; a < kSadW; ++a)
+#pragma unroll
+        for (int b = 0; b < kSadW; ++b) sum += __ldg(org + (size_t)a * W + b);
+      st.mean = __fdiv_rn((float)sum, 25.0f);
+    }
+    // NCC 3x3: A, and C in fp64 exactly as matchers.cpp:146
+    if (Y >= 1 && Y < H - 2 && X >= 1 && X < W - 2) {
+      const uint8_t* org = img + (size_t)(Y - 1) * W + (X - 1);
+      unsigned a_sum = 0, b_sum = 0;
+#pragma unroll
+      for (int a = 0; a < kNccW; ++a)
+#pragma unroll
+        for (int b = 0; b < kNccW; ++b) {
+          const unsigned v = __ldg(org + (size_t)a * W + b);
+          a_sum += v;
+          b_sum += v * v;
+        }
+      st.A = (float)a_sum;
+      const double var = __dsub_rn((double)(9u * b_sum), __dmul_rn((double)a_sum, (double)a_sum));
+      st.C = __ddiv_rn(1.0, __dsqrt_rn(var));
+    }
+    // Sobel Gx (matchers.cpp:538-547); unpadded array feeds the sadsob scan
+    float sv = 0.f;
+    if (Y >= 1 && Y < H - 2 && X >= 1 && X < W - 2) {
+      const uint8_t* p = img + (size_t)(Y - 1) * W + (X - 1);
+      sv = (float)(((int)p[2] - (int)p[0]) + 2 * ((int)p[W + 2] - (int)p[W]) +
+                   ((int)p[2 * W + 2] - (int)p[2 * W]));
+    }
+    (side ? sobR : sobL)[(size_t)n * H * W + (size_t)Y * W + X] = sv;
+  }
+  (side ? descR : descL)[po] = make_uint4(w0, w1, w2, w3);
+  (side ? statR : statL)[po] = st;
+  (side ? fR : fL)[po] = pix;
+}
+
+// ----------------------------------------------------------------- fused --
+struct FusedArgs {
+  FusedGeom g;
+  const uint4 *descL, *descR;
+  const RStat *statL, *statR;
+  const float *fL, *fR;
+  const float* sadsob;  // [N][D][H][W]
+  float* out;           // [N][8][D][h][w]
+  float k_cen, k_ncc, k_sad;
+  int DC;               // disparities per warp
+  int RWa, RWFa;        // padded shared-row lengths
+  int tiles_x;
+};
+
+__device__ __forceinline__ float int_to_float_small(int c) {  // exact for 0 <= c < 2^23
+  return __uint_as_float(0x4B000000u | (uint32_t)c) - 8388608.0f;
+}
+// c / 120 correctly rounded for integer c in [0,120] (exhaustively checked in
+// tests/test_host_math.py): reciprocal multiply + one FMA residual correction.
+__device__ __forceinline__ float div120_exact(float cf) {
+  const float r = 1.0f / 120.0f;
+  float q = __fmul_rn(cf, r);
+  const float rem = __fmaf_rn(-120.0f, q, cf);
+  return __fmaf_rn(rem, r, q);
+}
+
+__global__ void __launch_bounds__(kWarps * 32, 2) ms_fused_kernel(const FusedArgs a) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  const FusedGeom& g = a.g;
+  const int D = g.D;
+  uint4* s_desc = reinterpret_cast<uint4*>(smem_raw);                    // [RWa]
+  RStat* s_stat = reinterpret_cast<RStat*>(s_desc + a.RWa);              // [RWa]
+  float* s_rf = reinterpret_cast<float*>(s_stat + a.RWa);                // [5][RWFa]
+  float* s_red = s_rf + 5 * a.RWFa;                                      // [8][4][32]
+  float* s_lut = s_red + kWarps * 4 * 32;                                // [128]
+  float* s_inv = s_lut + 128;                                            // [4][32]
+  float* s_par = s_inv + 4 * 32;                                         // [3][D][32] ncc, sadsob, zsad
+  uint8_t* s_cen = reinterpret_cast<uint8_t*>(s_par + (size_t)3 * D * 32);  // [D][32]
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  int tile = blockIdx.x;
+  const int xt = tile % a.tiles_x; tile /= a.tiles_x;
+  const int y = tile % g.h;
+  const int n = tile / g.h;
+  const int x0 = xt * kTile;
+  const int Y = y + g.bh;                 // bordered image row
+  const int Yp = Y + kPadT;               // padded row
+  const int X = x0 + lane + g.bwl;        // bordered image column of this lane
+  const int Xp = X + g.padL;
+  const int RW = D + kTile - 1;           // right-image columns this tile can touch
+  const int XbaseP = x0 + g.bwl - (D - 1) + g.padL;  // padded column of shared index 0
+  const size_t img_off = (size_t)n * g.img_px();
+
+  // ---- stage the right-image row data in shared memory -------------------
+  {
+    const uint4* gd = a.descR + img_off + (size_t)Yp * g.Wp + XbaseP;
+    const RStat* gs = a.statR + img_off + (size_t)Yp * g.Wp + XbaseP;
+    for (int i = threadIdx.x; i < RW; i += kWarps * 32) {
+      s_desc[i] = __ldg(gd + i);
+      const uint4 raw = __ldg(reinterpret_cast<const uint4*>(gs + i));
+      *reinterpret_cast<uint4*>(s_stat + i) = raw;
+    }
+    for (int r = 0; r < 5; ++r) {
+      const float* gf = a.fR + img_off + (size_t)(Yp - 2 + r) * g.Wp + (XbaseP - 2);
+      for (int i = threadIdx.x; i < RW + 4; i += kWarps * 32) s_rf[r * a.RWFa + i] = __ldg(gf + i);
+    }
+    if (threadIdx.x < 128) {
+      const int kk = threadIdx.x;
+      s_lut[kk] = (kk <= 120) ? ex2_approx(-(float)(kk * kk) * a.k_cen) : 0.f;
+    }
+  }
+
+  // ---- per-lane left-image data in registers -----------------------------
+  const uint4 ld = __ldg(a.descL + img_off + (size_t)Yp * g.Wp + Xp);
+  RStat ls;
+  {
+    const uint4 raw = __ldg(reinterpret_cast<const uint4*>(a.statL + img_off + (size_t)Yp * g.Wp + Xp));
+    ls = *reinterpret_cast<const RStat*>(&raw);
+  }
+  float at[5][5];   // (L - mL), hoisted over all d   (matchers.cpp:503)
+  float l3[3][3];   // centre 3x3 of L as float for NCC
+#pragma unroll
+  for (int r = 0; r < 5; ++r) {
+    const float* gf = a.fL + img_off + (size_t)(Yp - 2 + r) * g.Wp + (Xp - 2);
+#pragma unroll
+    for (int c = 0; c < 5; ++c) {
+      const float v = __ldg(gf + c);
+      at[r][c] = __fsub_rn(v, ls.mean);
+      if (r >= 1 && r <= 3 && c >= 1 && c <= 3) l3[r - 1][c - 1] = v;
+    }
+  }
+  // validity: cost(y,x,d) exists iff the window origin is inside and x - wc >= d
+  const int H = g.H, W = g.W;
+  const int dmax_cen = (Y >= 5 && Y < H - 6 && X >= 5 && X < W - 6) ? X - 5 : -1;
+  const int dmax_ncc = (Y >= 1 && Y < H - 2 && X >= 1 && X < W - 2) ? X - 1 : -1;
+  const int dmax_sad = (Y >= 2 && Y < H - 3 && X >= 2 && X < W - 3) ? X - 2 : -1;
+  const bool live = (x0 + lane) < g.w;
+
+  const size_t plane = (size_t)g.h * g.w;
+  const size_t chan = plane * D;
+  float* obase = a.out + (size_t)n * 8 * chan + (size_t)y * g.w + (x0 + lane);
+  const float* sbase = a.sadsob + ((size_t)n * D * H + Y) * W + X;
+  const size_t splane = (size_t)H * W;
+
+  __syncthreads();
+
+  // ---- phase 1: costs, channels 0-3, parking, minima ----------------------
+  const int d_lo = warp * a.DC;
+  const int d_hi = min(D, d_lo + a.DC);
+  float rw[5][5];  // sliding 5x5 right window; logical column c lives in rw[.][(c - s) mod 5]
+  if (d_lo < d_hi) {
+    const int ir = lane + (D - 1) - d_lo;
+#pragma unroll
+    for (int r = 0; r < 5; ++r)
+#pragma unroll
+      for (int c = 0; c < 5; ++c) rw[r][c] = s_rf[r * a.RWFa + ir + c];
+  }
+  int min_cen = 255;
+  float min_ncc = kFill, min_sob = kFill, min_sad = kFill;
+
+  for (int base = d_lo; base < d_hi; base += 5) {
+#pragma unroll
+    for (int k = 0; k < 5; ++k) {
+      const int d = base + k;
+      if (d < d_hi) {
+        const int ir = lane + (D - 1) - d;  // shared index of right column X - d
+        if (d > d_lo) {
+#pragma unroll
+          for (int r = 0; r < 5; ++r) rw[r][(5 - k) % 5] = s_rf[r * a.RWFa + ir];
+        }
+        const float sob_raw = (live && d <= dmax_sad) ? __ldcs(sbase + (size_t)d * splane) : kFill;
+        const uint4 rd = s_desc[ir];
+        const uint4 rs_raw = *reinterpret_cast<const uint4*>(s_stat + ir);
+        const RStat rs = *reinterpret_cast<const RStat*>(&rs_raw);
+
+        // census: Hamming distance of the packed codes (matchers.cpp:323-337)
+        const int cen = __popc(ld.x ^ rd.x) + __popc(ld.y ^ rd.y) + __popc(ld.z ^ rd.z) + __popc(ld.w ^ rd.w);
+        const bool ok_cen = d <= dmax_cen;
+        const int cen_b = ok_cen ? cen : 255;
+        const float f0 = ok_cen ? div120_exact(int_to_float_small(cen)) : 1.0f;
+
+        // NCC: P exact in fp32 (< 2^24); scaling in fp64 left to right (matchers.cpp:200-201)
+        float P = 0.f;
+#pragma unroll
+        for (int r = 0; r < 3; ++r)
+#pragma unroll
+          for (int c = 0; c < 3; ++c) P = __fmaf_rn(l3[r][c], rw[r + 1][(c + 1 - k + 5) % 5], P);
+        const float num = __fmaf_rn(9.0f, P, -__fmul_rn(ls.A, rs.A));
+        const double t = __dmul_rn(__dmul_rn(-(double)num, ls.C), rs.C);
+        float ncc = (float)t;
+        if (!(fabsf(ncc) <= 3.0e38f)) ncc = 1.0f;  // either C was inf (flat window), :196,204
+        if (d > dmax_ncc) ncc = kFill;
+
+        // ZSAD: 25 taps row-major, ((L - mL) - R) + mR, sequential fp32 (matchers.cpp:499-506)
+        float z = 0.f;
+#pragma unroll
+        for (int r = 0; r < 5; ++r)
+#pragma unroll
+          for (int c = 0; c < 5; ++c) {
+            const float u = __fadd_rn(__fsub_rn(at[r][c], rw[r][(c - k + 5) % 5]), rs.mean);
+            z = __fadd_rn(z, fabsf(u));
+          }
+        if (d > dmax_sad) z = kFill;
+
+        // channels 0-3 (cbmv_generator.py:283-287)
+        if (live) {
+          float* o = obase + (size_t)d * plane;
+          st_stream(o, f0);
+          st_stream(o + chan, normalise_cost(ncc, 1));
+          st_stream(o + 2 * chan, normalise_cost(sob_raw, 2));
+          st_stream(o + 3 * chan, normalise_cost(z, 3));
+        }
+        // park raw costs for the AML phases
+        s_cen[d * 32 + lane] = (uint8_t)cen_b;
+        s_par[(0 * D + d) * 32 + lane] = ncc;
+        s_par[(1 * D + d) * 32 + lane] = sob_raw;
+        s_par[(2 * D + d) * 32 + lane] = z;
+        min_cen = min(min_cen, cen_b);
+        min_ncc = fminf(min_ncc, ncc);
+        min_sob = fminf(min_sob, sob_raw);
+        min_sad = fminf(min_sad, z);
+      }
+    }
+  }
+  s_red[(warp * 4 + 0) * 32 + lane] = (min_cen == 255) ? kFill : (float)min_cen;
+  s_red[(warp * 4 + 1) * 32 + lane] = min_ncc;
+  s_red[(warp * 4 + 2) * 32 + lane] = min_sob;
+  s_red[(warp * 4 + 3) * 32 + lane] = min_sad;
+  __syncthreads();
+  float m[4];
+#pragma unroll
+  for (int q = 0; q < 4; ++q) {
+    float v = kFill;
+#pragma unroll
+    for (int wv = 0; wv < kWarps; ++wv) v = fminf(v, s_red[(wv * 4 + q) * 32 + lane]);
+    m[q] = v;
+  }
+
+  // ---- phase 2: exponentials over the parked float costs (own d range: no sync) ----
+  for (int d = d_lo; d < d_hi; ++d) {
+    s_par[(0 * D + d) * 32 + lane] = aml_e(s_par[(0 * D + d) * 32 + lane], m[1], a.k_ncc);
+    s_par[(1 * D + d) * 32 + lane] = aml_e(s_par[(1 * D + d) * 32 + lane], m[2], a.k_sad);
+    s_par[(2 * D + d) * 32 + lane] = aml_e(s_par[(2 * D + d) * 32 + lane], m[3], a.k_sad);
+  }
+  __syncthreads();
+
+  // ---- phase 3: denominators in the reference's order (sequential fp32 over d) ----
+  if (warp < 4) {
+    float den = 0.f;
+    if (warp == 0) {
+      const int mc = (m[0] == kFill) ? 0 : (int)m[0];
+#pragma unroll 8
+      for (int d = 0; d < D; ++d) den = __fadd_rn(den, s_lut[min((int)s_cen[d * 32 + lane] - mc, 127)]);
+    } else {
+      const float* e = s_par + (size_t)(warp - 1) * D * 32 + lane;
+#pragma unroll 8
+      for (int d = 0; d < D; ++d) den = __fadd_rn(den, e[d * 32]);
+    }
+    const float mm = (warp == 0) ? m[0] : (warp == 1) ? m[1] : (warp == 2) ? m[2] : m[3];
+    s_inv[warp * 32 + lane] = (mm == kFill) ? 0.f : 1.0f / den;
+  }
+  __syncthreads();
+
+  // ---- phase 4: channels 4-7 = e / den ------------------------------------
+  if (live) {
+    const float i0 = s_inv[lane], i1 = s_inv[32 + lane], i2 = s_inv[64 + lane], i3 = s_inv[96 + lane];
+    const int mc = (m[0] == kFill) ? 0 : (int)m[0];
+    for (int d = d_lo; d < d_hi; ++d) {
+      float* o = obase + 4 * chan + (size_t)d * plane;
+      st_stream(o, s_lut[min((int)s_cen[d * 32 + lane] - mc, 127)] * i0);
+      st_stream(o + chan, s_par[(0 * D + d) * 32 + lane] * i1);
+      st_stream(o + 2 * chan, s_par[(1 * D + d) * 32 + lane] * i2);
+      st_stream(o + 3 * chan, s_par[(2 * D + d) * 32 + lane] * i3);
+    }
+  }
+}
+
+size_t fused_smem_bytes(int D, int* RWa, int* RWFa) {
+  const int RW = D + kTile - 1;
+  *RWa = (RW + 3) & ~3;
+  *RWFa = (RW + 4 + 3) & ~3;
+  size_t b = 0;
+  b += (size_t)*RWa * sizeof(uint4);
+  b += (size_t)*RWa * sizeof(RStat);
+  b += (size_t)5 * *RWFa * sizeof(float);
+  b += (size_t)kWarps * 4 * 32 * sizeof(float);
+  b += 128 * sizeof(float);
+  b += 4 * 32 * sizeof(float);
+  b += (size_t)3 * D * 32 * sizeof(float);
+  b += (size_t)D * 32;
+  return b;
+}
+
+// Optional per-kernel timing (msn_profile_enable): CUDA events recorded on the launch
+// stream between the kernels of the fused sequence, read back by msn_profile_read.
+struct ProfRec { cudaEvent_t ev[4]; };
+std::mutex g_prof_mu;
+bool g_prof_on = false;
+std::vector<ProfRec> g_prof;
+
+}  // namespace
+
+int profile_enable(int on) {
+  std::lock_guard<std::mutex> lk(g_prof_mu);
+  g_prof_on = on != 0;
+  return 0;
+}
+
+int profile_read(double* prep_ms, double* sadsob_ms, double* fused_ms, int* calls) {
+  std::lock_guard<std::mutex> lk(g_prof_mu);
+  double t[3] = {0, 0, 0};
+  for (ProfRec& r : g_prof) {
+    MSN_CUDA_OK(cudaEventSynchronize(r.ev[3]));
+    for (int i = 0; i < 3; ++i) {
+      float ms = 0.f;
+      MSN_CUDA_OK(cudaEventElapsedTime(&ms, r.ev[i], r.ev[i + 1]));
+      t[i] += ms;
+    }
+    for (int i = 0; i < 4; ++i) cudaEventDestroy(r.ev[i]);
+  }
+  if (prep_ms) *prep_ms = t[0];
+  if (sadsob_ms) *sadsob_ms = t[1];
+  if (fused_ms) *fused_ms = t[2];
+  if (calls) *calls = (int)g_prof.size();
+  g_prof.clear();
+  return 0;
+}
+
+bool fused_supported(const msn_ms_params* p, int Dn) {
+  return p->censw == kCensW && p->nccw == kNccW && p->sadw == kSadW && p->sobelw == kSadW && p->lr == 0 &&
+         Dn == p->ndisp && p->ndisp <= kMaxFusedD;
+}
+
+size_t fused_workspace_bytes(int N, int H, int W, int Dn, const msn_ms_params* p) {
+  (void)Dn;
+  FusedGeom g = make_geom(N, H, W, p);
+  FusedWs ws;
+  ws.carve(nullptr, g);
+  return ws.total;
+}
+
+int launch_ms_fused(const uint8_t* d_left, const uint8_t* d_right, int N, int H, int W, const msn_ms_params* p,
+                    float* d_out, char* workspace, cudaStream_t s) {
+  if (N == 0) return 0;
+  FusedGeom g = make_geom(N, H, W, p);
+  FusedWs ws;
+  ws.carve(workspace, g);
+  MSN_REQUIRE(2 * N <= 65535 && g.Hp <= 65535, "ms_features: batch or image too large for one launch");
+
+  bool prof;
+  ProfRec rec;
+  {
+    std::lock_guard<std::mutex> lk(g_prof_mu);
+    prof = g_prof_on;
+  }
+  if (prof) {
+    for (int i = 0; i < 4; ++i) MSN_CUDA_OK(cudaEventCreate(&rec.ev[i]));
+    MSN_CUDA_OK(cudaEventRecord(rec.ev[0], s));
+  }
+  dim3 pgrid(div_up(g.Wp, 128), g.Hp, 2 * N);
+  ms_prep_kernel<<<pgrid, 128, 0, s>>>(d_left, d_right, g, ws.desc[0], ws.desc[1], ws.stat[0], ws.stat[1],
+                                       ws.fimg[0], ws.fimg[1], ws.sob[0], ws.sob[1]);
+  MSN_LAUNCH_OK();
+  if (prof) MSN_CUDA_OK(cudaEventRecord(rec.ev[1], s));
+  if (launch_sadsob_n(ws.sob[0], ws.sob[1], N, H, W, g.D, 0, kSadW, ws.sadsob, (size_t)g.D * H * W, false,
+                      ws.sad_ws, s))
+    return 1;
+  if (prof) MSN_CUDA_OK(cudaEventRecord(rec.ev[2], s));
+
+  FusedArgs a;
+  a.g = g;
+  a.descL = ws.desc[0]; a.descR = ws.desc[1];
+  a.statL = ws.stat[0]; a.statR = ws.stat[1];
+  a.fL = ws.fimg[0]; a.fR = ws.fimg[1];
+  a.sadsob = ws.sadsob;
+  a.out = d_out;
+  a.k_cen = aml_scale(p->cens_sigma);
+  a.k_ncc = aml_scale(p->ncc_sigma);
+  a.k_sad = aml_scale(p->sad_sigma);
+  a.DC = (g.D + kWarps - 1) / kWarps;
+  a.tiles_x = (g.w + kTile - 1) / kTile;
+  const size_t smem = fused_smem_bytes(g.D, &a.RWa, &a.RWFa);
+  MSN_REQUIRE(smem <= 227 * 1024, "ms_features: D=%d needs %zu B of shared memory", g.D, smem);
+  MSN_CUDA_OK(cudaFuncSetAttribute(ms_fused_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  const long long tiles = (long long)N * g.h * a.tiles_x;
+  MSN_REQUIRE(tiles <= 2147483647LL, "ms_features: too many tiles for one launch");
+  ms_fused_kernel<<<(unsigned)tiles, kWarps * 32, smem, s>>>(a);
+  MSN_LAUNCH_OK();
+  if (prof) {
+    MSN_CUDA_OK(cudaEventRecord(rec.ev[3], s));
+    std::lock_guard<std::mutex> lk(g_prof_mu);
+    g_prof.push_back(rec);
+  }
+  return 0;
+}
+
 }  // namespace msn

@@ -11,4 +11,7 @@ size_t fused_workspace_bytes(int N, int H, int W, int Dn, const msn_ms_params* p
 int launch_ms_fused(const uint8_t* d_left, const uint8_t* d_right, int N, int H, int W, const msn_ms_params* p,
                     float* d_out, char* workspace, cudaStream_t s);
 
+int profile_enable(int on);
+int profile_read(double* prep_ms, double* sadsob_ms, double* fused_ms, int* calls);
+
 }  // namespace msn

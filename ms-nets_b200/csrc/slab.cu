@@ -78,14 +78,11 @@ slab_phase_b_kernel(const float* __restrict__ out, const float* __restrict__ gmi
   const float m = gmin[(size_t)i * n + p];
   const float k = sc.k[i & 3];
   const float* c = out + (size_t)aml_channel(i) * Dn * n + p;
-  float s0 = 0.f, s1 = 0.f;
-  int dd = 0;
-  for (; dd + 1 < Dn; dd += 2) {
-    s0 += aml_e(c[(size_t)dd * n], m, k);
-    s1 += aml_e(c[(size_t)(dd + 1) * n], m, k);
-  }
-  if (dd < Dn) s0 += aml_e(c[(size_t)dd * n], m, k);
-  den[(size_t)i * n + p] = s0 + s1;
+  // sequential fp32 in d order, as the reference sums (featextract.cpp:444-447)
+  float s = 0.f;
+#pragma unroll 4
+  for (int dd = 0; dd < Dn; ++dd) s = __fadd_rn(s, aml_e(c[(size_t)dd * n], m, k));
+  den[(size_t)i * n + p] = s;
 }
 
 __global__ void __launch_bounds__(256)
