@@ -85,7 +85,7 @@ struct FusedWs {
     for (int i = 0; i < 2; ++i) stat[i] = (RStat*)take(np * sizeof(RStat));
     for (int i = 0; i < 2; ++i) fimg[i] = (float*)take(np * sizeof(float));
     for (int i = 0; i < 2; ++i) sob[i] = (float*)take(n * sizeof(float));
-    sadsob = (float*)take(n * g.D * sizeof(float));
+    sadsob = (float*)take(n * g.D * sizeof(float) + 256);  // + slack: dead lanes read past a row end
     sad_ws = take(sadsob_workspace_bytes_n(g.N, g.H, g.W, g.D, kSadW));
     total = off;
   }
@@ -176,12 +176,30 @@ struct FusedArgs {
   const uint4 *descL, *descR;
   const RStat *statL, *statR;
   const float *fL, *fR;
-  const float* sadsob;  // [N][D][H][W]
+  const float* sadsob;  // [N][D][H][W] (+ slack)
   float* out;           // [N][8][D][h][w]
   float k_cen, k_ncc, k_sad;
-  int DC;               // disparities per warp
-  int RWa, RWFa;        // padded shared-row lengths
+  int DC;               // disparity steps per warp (multiple of 5)
   int tiles_x;
+};
+
+// Shared-memory layout for disparity counts up to DMAX.  Row strides are compile-time
+// so every shared access in the hot loop is "pointer + immediate".
+constexpr int kSlack = 40;  // right-image entries below index 0 reached by dummy steps (d >= D)
+template <int DMAX>
+struct Lay {
+  static constexpr int RW = (DMAX + kTile - 1 + kSlack + 3) & ~3;  // desc / stat entries
+  static constexpr int RWF = RW + 8;                               // float row length (halo 2 each side)
+  static constexpr int DS = DMAX + 1;                              // parked planes + 1 scratch plane
+  static constexpr size_t off_desc = 0;
+  static constexpr size_t off_stat = off_desc + (size_t)RW * 16;
+  static constexpr size_t off_rf = off_stat + (size_t)RW * 16;
+  static constexpr size_t off_red = off_rf + (size_t)5 * RWF * 4;
+  static constexpr size_t off_lut = off_red + (size_t)kWarps * 4 * 32 * 4;
+  static constexpr size_t off_inv = off_lut + 128 * 4;
+  static constexpr size_t off_par = off_inv + 4 * 32 * 4;          // [3][DS][32] ncc, sadsob, zsad
+  static constexpr size_t off_cen = off_par + (size_t)3 * DS * 32 * 4;  // [DS][32] bytes
+  static constexpr size_t bytes = off_cen + (size_t)DS * 32;
 };
 
 __device__ __forceinline__ float int_to_float_small(int c) {  // exact for 0 <= c < 2^23
@@ -195,19 +213,27 @@ __device__ __forceinline__ float div120_exact(float cf) {
   const float rem = __fmaf_rn(-120.0f, q, cf);
   return __fmaf_rn(rem, r, q);
 }
+__device__ __forceinline__ void cp_async4(void* smem_dst, const void* gmem_src) {
+  const uint32_t d = (uint32_t)__cvta_generic_to_shared(smem_dst);
+  asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(d), "l"(gmem_src) : "memory");
+}
+__device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_all;" ::: "memory"); }
 
+template <int DMAX>
 __global__ void __launch_bounds__(kWarps * 32, 2) ms_fused_kernel(const FusedArgs a) {
+  using L = Lay<DMAX>;
   extern __shared__ __align__(16) unsigned char smem_raw[];
   const FusedGeom& g = a.g;
   const int D = g.D;
-  uint4* s_desc = reinterpret_cast<uint4*>(smem_raw);                    // [RWa]
-  RStat* s_stat = reinterpret_cast<RStat*>(s_desc + a.RWa);              // [RWa]
-  float* s_rf = reinterpret_cast<float*>(s_stat + a.RWa);                // [5][RWFa]
-  float* s_red = s_rf + 5 * a.RWFa;                                      // [8][4][32]
-  float* s_lut = s_red + kWarps * 4 * 32;                                // [128]
-  float* s_inv = s_lut + 128;                                            // [4][32]
-  float* s_par = s_inv + 4 * 32;                                         // [3][D][32] ncc, sadsob, zsad
-  uint8_t* s_cen = reinterpret_cast<uint8_t*>(s_par + (size_t)3 * D * 32);  // [D][32]
+  uint4* s_desc = reinterpret_cast<uint4*>(smem_raw + L::off_desc);
+  uint4* s_stat = reinterpret_cast<uint4*>(smem_raw + L::off_stat);  // RStat viewed as 16 bytes
+  float* s_rf = reinterpret_cast<float*>(smem_raw + L::off_rf);      // [5][RWF]
+  float* s_red = reinterpret_cast<float*>(smem_raw + L::off_red);    // [8][4][32]
+  float* s_lut = reinterpret_cast<float*>(smem_raw + L::off_lut);    // [128]
+  float* s_inv = reinterpret_cast<float*>(smem_raw + L::off_inv);    // [4][32]
+  float* s_par = reinterpret_cast<float*>(smem_raw + L::off_par);    // [3][DS][32]
+  uint8_t* s_cen = smem_raw + L::off_cen;                            // [DS][32]
+  constexpr int PS = L::DS * 32;                                     // floats per parked matcher
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   int tile = blockIdx.x;
@@ -215,26 +241,38 @@ __global__ void __launch_bounds__(kWarps * 32, 2) ms_fused_kernel(const FusedArg
   const int y = tile % g.h;
   const int n = tile / g.h;
   const int x0 = xt * kTile;
+  const int H = g.H, W = g.W;
   const int Y = y + g.bh;                 // bordered image row
   const int Yp = Y + kPadT;               // padded row
   const int X = x0 + lane + g.bwl;        // bordered image column of this lane
   const int Xp = X + g.padL;
-  const int RW = D + kTile - 1;           // right-image columns this tile can touch
-  const int XbaseP = x0 + g.bwl - (D - 1) + g.padL;  // padded column of shared index 0
+  const int RWn = D + kTile - 1 + kSlack;  // entries staged: shared index i <-> padded col XbaseP + i
+  const int XbaseP = x0 + g.bwl - (D - 1) - kSlack + g.padL;
   const size_t img_off = (size_t)n * g.img_px();
+  const bool live = (x0 + lane) < g.w;
+  const int d_lo = warp * a.DC;
+  const int d_end = min(D, d_lo + a.DC);  // real disparities of this warp: [d_lo, d_end)
+
+  // ---- sadsob costs of this lane's own disparities: async global -> parked plane 1 ----
+  {
+    const float* src = a.sadsob + ((size_t)n * D * H + Y) * W + X + (size_t)d_lo * H * W;
+    float* dst = s_par + PS + d_lo * 32 + lane;
+    const size_t splane = (size_t)H * W;
+    for (int d = d_lo; d < d_end; ++d, src += splane, dst += 32) cp_async4(dst, src);
+  }
 
   // ---- stage the right-image row data in shared memory -------------------
   {
     const uint4* gd = a.descR + img_off + (size_t)Yp * g.Wp + XbaseP;
-    const RStat* gs = a.statR + img_off + (size_t)Yp * g.Wp + XbaseP;
-    for (int i = threadIdx.x; i < RW; i += kWarps * 32) {
+    const uint4* gs = reinterpret_cast<const uint4*>(a.statR + img_off + (size_t)Yp * g.Wp + XbaseP);
+    for (int i = threadIdx.x; i < RWn; i += kWarps * 32) {
       s_desc[i] = __ldg(gd + i);
-      const uint4 raw = __ldg(reinterpret_cast<const uint4*>(gs + i));
-      *reinterpret_cast<uint4*>(s_stat + i) = raw;
+      s_stat[i] = __ldg(gs + i);
     }
+#pragma unroll
     for (int r = 0; r < 5; ++r) {
       const float* gf = a.fR + img_off + (size_t)(Yp - 2 + r) * g.Wp + (XbaseP - 2);
-      for (int i = threadIdx.x; i < RW + 4; i += kWarps * 32) s_rf[r * a.RWFa + i] = __ldg(gf + i);
+      for (int i = threadIdx.x; i < RWn + 4; i += kWarps * 32) s_rf[r * L::RWF + i] = __ldg(gf + i);
     }
     if (threadIdx.x < 128) {
       const int kk = threadIdx.x;
@@ -261,97 +299,99 @@ __global__ void __launch_bounds__(kWarps * 32, 2) ms_fused_kernel(const FusedArg
       if (r >= 1 && r <= 3 && c >= 1 && c <= 3) l3[r - 1][c - 1] = v;
     }
   }
-  // validity: cost(y,x,d) exists iff the window origin is inside and x - wc >= d
-  const int H = g.H, W = g.W;
-  const int dmax_cen = (Y >= 5 && Y < H - 6 && X >= 5 && X < W - 6) ? X - 5 : -1;
-  const int dmax_ncc = (Y >= 1 && Y < H - 2 && X >= 1 && X < W - 2) ? X - 1 : -1;
-  const int dmax_sad = (Y >= 2 && Y < H - 3 && X >= 2 && X < W - 3) ? X - 2 : -1;
-  const bool live = (x0 + lane) < g.w;
+  // validity: cost(y,x,d) exists iff the window origin is inside and x - wc >= d (and d < D)
+  const int dmax_cen = min(D - 1, (Y >= 5 && Y < H - 6 && X >= 5 && X < W - 6) ? X - 5 : -1);
+  const int dmax_ncc = min(D - 1, (Y >= 1 && Y < H - 2 && X >= 1 && X < W - 2) ? X - 1 : -1);
+  const int dmax_sad = min(D - 1, (Y >= 2 && Y < H - 3 && X >= 2 && X < W - 3) ? X - 2 : -1);
+  const int dmax_live = live ? D - 1 : -1;
 
   const size_t plane = (size_t)g.h * g.w;
   const size_t chan = plane * D;
-  float* obase = a.out + (size_t)n * 8 * chan + (size_t)y * g.w + (x0 + lane);
-  const float* sbase = a.sadsob + ((size_t)n * D * H + Y) * W + X;
-  const size_t splane = (size_t)H * W;
+  float* o0 = a.out + (size_t)n * 8 * chan + (size_t)y * g.w + (x0 + lane) + (size_t)d_lo * plane;
+  float* o1 = o0 + chan;
+  float* o2 = o1 + chan;
+  float* o3 = o2 + chan;
 
+  cp_async_wait_all();
   __syncthreads();
 
   // ---- phase 1: costs, channels 0-3, parking, minima ----------------------
-  const int d_lo = warp * a.DC;
-  const int d_hi = min(D, d_lo + a.DC);
+  // shared index of right column X - d is ir = lane + kSlack + (D-1) - d; it falls by one per step
+  const int ir0 = lane + kSlack + (D - 1) - d_lo;
+  const float* rfp = s_rf + ir0;
+  const uint4* dscp = s_desc + ir0;
+  const uint4* sttp = s_stat + ir0;
   float rw[5][5];  // sliding 5x5 right window; logical column c lives in rw[.][(c - s) mod 5]
-  if (d_lo < d_hi) {
-    const int ir = lane + (D - 1) - d_lo;
 #pragma unroll
-    for (int r = 0; r < 5; ++r)
+  for (int r = 0; r < 5; ++r)
 #pragma unroll
-      for (int c = 0; c < 5; ++c) rw[r][c] = s_rf[r * a.RWFa + ir + c];
-  }
+    for (int c = 0; c < 5; ++c) rw[r][c] = rfp[r * L::RWF + c];
   int min_cen = 255;
   float min_ncc = kFill, min_sob = kFill, min_sad = kFill;
 
-  for (int base = d_lo; base < d_hi; base += 5) {
+  for (int base = 0; base < a.DC; base += 5) {
 #pragma unroll
     for (int k = 0; k < 5; ++k) {
-      const int d = base + k;
-      if (d < d_hi) {
-        const int ir = lane + (D - 1) - d;  // shared index of right column X - d
-        if (d > d_lo) {
+      const int d = d_lo + base + k;
+      const int ds = min(d, D);  // dummy steps (d >= D) park into the scratch plane
+      float* park = s_par + ds * 32 + lane;
+      const uint4 rd = *dscp;
+      const uint4 rs_raw = *sttp;
+      const RStat rs = *reinterpret_cast<const RStat*>(&rs_raw);
+      float sob = park[PS];
+
+      // census: Hamming distance of the packed codes (matchers.cpp:323-337)
+      const int cen = __popc(ld.x ^ rd.x) + __popc(ld.y ^ rd.y) + __popc(ld.z ^ rd.z) + __popc(ld.w ^ rd.w);
+      const bool ok_cen = d <= dmax_cen;
+      const int cen_b = ok_cen ? cen : 255;
+      const float f0 = ok_cen ? div120_exact(int_to_float_small(cen)) : 1.0f;
+
+      // NCC: P exact in fp32 (< 2^24); scaling in fp64 left to right (matchers.cpp:200-201)
+      float P = 0.f;
 #pragma unroll
-          for (int r = 0; r < 5; ++r) rw[r][(5 - k) % 5] = s_rf[r * a.RWFa + ir];
+      for (int r = 0; r < 3; ++r)
+#pragma unroll
+        for (int c = 0; c < 3; ++c) P = __fmaf_rn(l3[r][c], rw[r + 1][(c + 1 - k + 5) % 5], P);
+      const float num = __fmaf_rn(9.0f, P, -__fmul_rn(ls.A, rs.A));
+      const double t = __dmul_rn(__dmul_rn(-(double)num, ls.C), rs.C);
+      float ncc = (float)t;
+      ncc = (fabsf(ncc) <= 3.0e38f) ? ncc : 1.0f;  // either C was inf (flat window), :196,204
+      ncc = (d <= dmax_ncc) ? ncc : kFill;
+
+      // ZSAD: 25 taps row-major, ((L - mL) - R) + mR, sequential fp32 (matchers.cpp:499-506)
+      float z = 0.f;
+#pragma unroll
+      for (int r = 0; r < 5; ++r)
+#pragma unroll
+        for (int c = 0; c < 5; ++c) {
+          const float u = __fadd_rn(__fsub_rn(at[r][c], rw[r][(c - k + 5) % 5]), rs.mean);
+          z = __fadd_rn(z, fabsf(u));
         }
-        const float sob_raw = (live && d <= dmax_sad) ? __ldcs(sbase + (size_t)d * splane) : kFill;
-        const uint4 rd = s_desc[ir];
-        const uint4 rs_raw = *reinterpret_cast<const uint4*>(s_stat + ir);
-        const RStat rs = *reinterpret_cast<const RStat*>(&rs_raw);
+      const bool ok_sad = d <= dmax_sad;
+      z = ok_sad ? z : kFill;
+      sob = ok_sad ? sob : kFill;
 
-        // census: Hamming distance of the packed codes (matchers.cpp:323-337)
-        const int cen = __popc(ld.x ^ rd.x) + __popc(ld.y ^ rd.y) + __popc(ld.z ^ rd.z) + __popc(ld.w ^ rd.w);
-        const bool ok_cen = d <= dmax_cen;
-        const int cen_b = ok_cen ? cen : 255;
-        const float f0 = ok_cen ? div120_exact(int_to_float_small(cen)) : 1.0f;
-
-        // NCC: P exact in fp32 (< 2^24); scaling in fp64 left to right (matchers.cpp:200-201)
-        float P = 0.f;
-#pragma unroll
-        for (int r = 0; r < 3; ++r)
-#pragma unroll
-          for (int c = 0; c < 3; ++c) P = __fmaf_rn(l3[r][c], rw[r + 1][(c + 1 - k + 5) % 5], P);
-        const float num = __fmaf_rn(9.0f, P, -__fmul_rn(ls.A, rs.A));
-        const double t = __dmul_rn(__dmul_rn(-(double)num, ls.C), rs.C);
-        float ncc = (float)t;
-        if (!(fabsf(ncc) <= 3.0e38f)) ncc = 1.0f;  // either C was inf (flat window), :196,204
-        if (d > dmax_ncc) ncc = kFill;
-
-        // ZSAD: 25 taps row-major, ((L - mL) - R) + mR, sequential fp32 (matchers.cpp:499-506)
-        float z = 0.f;
-#pragma unroll
-        for (int r = 0; r < 5; ++r)
-#pragma unroll
-          for (int c = 0; c < 5; ++c) {
-            const float u = __fadd_rn(__fsub_rn(at[r][c], rw[r][(c - k + 5) % 5]), rs.mean);
-            z = __fadd_rn(z, fabsf(u));
-          }
-        if (d > dmax_sad) z = kFill;
-
-        // channels 0-3 (cbmv_generator.py:283-287)
-        if (live) {
-          float* o = obase + (size_t)d * plane;
-          st_stream(o, f0);
-          st_stream(o + chan, normalise_cost(ncc, 1));
-          st_stream(o + 2 * chan, normalise_cost(sob_raw, 2));
-          st_stream(o + 3 * chan, normalise_cost(z, 3));
-        }
-        // park raw costs for the AML phases
-        s_cen[d * 32 + lane] = (uint8_t)cen_b;
-        s_par[(0 * D + d) * 32 + lane] = ncc;
-        s_par[(1 * D + d) * 32 + lane] = sob_raw;
-        s_par[(2 * D + d) * 32 + lane] = z;
-        min_cen = min(min_cen, cen_b);
-        min_ncc = fminf(min_ncc, ncc);
-        min_sob = fminf(min_sob, sob_raw);
-        min_sad = fminf(min_sad, z);
+      // channels 0-3 (cbmv_generator.py:283-287)
+      if (d <= dmax_live) {
+        st_stream(o0, f0);
+        st_stream(o1, normalise_cost(ncc, 1));
+        st_stream(o2, normalise_cost(sob, 2));
+        st_stream(o3, normalise_cost(z, 3));
       }
+      o0 += plane; o1 += plane; o2 += plane; o3 += plane;
+      // park raw costs for the AML phases
+      s_cen[ds * 32 + lane] = (uint8_t)cen_b;
+      park[0] = ncc;
+      park[PS] = sob;
+      park[2 * PS] = z;
+      min_cen = min(min_cen, cen_b);
+      min_ncc = fminf(min_ncc, ncc);
+      min_sob = fminf(min_sob, sob);
+      min_sad = fminf(min_sad, z);
+      // slide the window: next step's new left column
+      --rfp; --dscp; --sttp;
+#pragma unroll
+      for (int r = 0; r < 5; ++r) rw[r][(4 - k) % 5] = rfp[r * L::RWF];
     }
   }
   s_red[(warp * 4 + 0) * 32 + lane] = (min_cen == 255) ? kFill : (float)min_cen;
@@ -369,24 +409,29 @@ __global__ void __launch_bounds__(kWarps * 32, 2) ms_fused_kernel(const FusedArg
   }
 
   // ---- phase 2: exponentials over the parked float costs (own d range: no sync) ----
-  for (int d = d_lo; d < d_hi; ++d) {
-    s_par[(0 * D + d) * 32 + lane] = aml_e(s_par[(0 * D + d) * 32 + lane], m[1], a.k_ncc);
-    s_par[(1 * D + d) * 32 + lane] = aml_e(s_par[(1 * D + d) * 32 + lane], m[2], a.k_sad);
-    s_par[(2 * D + d) * 32 + lane] = aml_e(s_par[(2 * D + d) * 32 + lane], m[3], a.k_sad);
+  {
+    float* e = s_par + d_lo * 32 + lane;
+#pragma unroll 4
+    for (int d = d_lo; d < d_end; ++d, e += 32) {
+      e[0] = aml_e(e[0], m[1], a.k_ncc);
+      e[PS] = aml_e(e[PS], m[2], a.k_sad);
+      e[2 * PS] = aml_e(e[2 * PS], m[3], a.k_sad);
+    }
   }
   __syncthreads();
 
   // ---- phase 3: denominators in the reference's order (sequential fp32 over d) ----
+  const int mc = (m[0] == kFill) ? 0 : (int)m[0];
   if (warp < 4) {
     float den = 0.f;
     if (warp == 0) {
-      const int mc = (m[0] == kFill) ? 0 : (int)m[0];
+      const uint8_t* c = s_cen + lane;
 #pragma unroll 8
-      for (int d = 0; d < D; ++d) den = __fadd_rn(den, s_lut[min((int)s_cen[d * 32 + lane] - mc, 127)]);
+      for (int d = 0; d < D; ++d, c += 32) den = __fadd_rn(den, s_lut[min((int)c[0] - mc, 127)]);
     } else {
-      const float* e = s_par + (size_t)(warp - 1) * D * 32 + lane;
+      const float* e = s_par + (warp - 1) * PS + lane;
 #pragma unroll 8
-      for (int d = 0; d < D; ++d) den = __fadd_rn(den, e[d * 32]);
+      for (int d = 0; d < D; ++d, e += 32) den = __fadd_rn(den, e[0]);
     }
     const float mm = (warp == 0) ? m[0] : (warp == 1) ? m[1] : (warp == 2) ? m[2] : m[3];
     s_inv[warp * 32 + lane] = (mm == kFill) ? 0.f : 1.0f / den;
@@ -396,31 +441,21 @@ __global__ void __launch_bounds__(kWarps * 32, 2) ms_fused_kernel(const FusedArg
   // ---- phase 4: channels 4-7 = e / den ------------------------------------
   if (live) {
     const float i0 = s_inv[lane], i1 = s_inv[32 + lane], i2 = s_inv[64 + lane], i3 = s_inv[96 + lane];
-    const int mc = (m[0] == kFill) ? 0 : (int)m[0];
-    for (int d = d_lo; d < d_hi; ++d) {
-      float* o = obase + 4 * chan + (size_t)d * plane;
-      st_stream(o, s_lut[min((int)s_cen[d * 32 + lane] - mc, 127)] * i0);
-      st_stream(o + chan, s_par[(0 * D + d) * 32 + lane] * i1);
-      st_stream(o + 2 * chan, s_par[(1 * D + d) * 32 + lane] * i2);
-      st_stream(o + 3 * chan, s_par[(2 * D + d) * 32 + lane] * i3);
+    const float* e = s_par + d_lo * 32 + lane;
+    const uint8_t* c = s_cen + d_lo * 32 + lane;
+    float* p0 = a.out + (size_t)n * 8 * chan + 4 * chan + (size_t)y * g.w + (x0 + lane) + (size_t)d_lo * plane;
+    float* p1 = p0 + chan;
+    float* p2 = p1 + chan;
+    float* p3 = p2 + chan;
+#pragma unroll 4
+    for (int d = d_lo; d < d_end; ++d, e += 32, c += 32) {
+      st_stream(p0, s_lut[min((int)c[0] - mc, 127)] * i0);
+      st_stream(p1, e[0] * i1);
+      st_stream(p2, e[PS] * i2);
+      st_stream(p3, e[2 * PS] * i3);
+      p0 += plane; p1 += plane; p2 += plane; p3 += plane;
     }
   }
-}
-
-size_t fused_smem_bytes(int D, int* RWa, int* RWFa) {
-  const int RW = D + kTile - 1;
-  *RWa = (RW + 3) & ~3;
-  *RWFa = (RW + 4 + 3) & ~3;
-  size_t b = 0;
-  b += (size_t)*RWa * sizeof(uint4);
-  b += (size_t)*RWa * sizeof(RStat);
-  b += (size_t)5 * *RWFa * sizeof(float);
-  b += (size_t)kWarps * 4 * 32 * sizeof(float);
-  b += 128 * sizeof(float);
-  b += 4 * 32 * sizeof(float);
-  b += (size_t)3 * D * 32 * sizeof(float);
-  b += (size_t)D * 32;
-  return b;
 }
 
 // Optional per-kernel timing (msn_profile_enable): CUDA events recorded on the launch
@@ -509,14 +544,24 @@ int launch_ms_fused(const uint8_t* d_left, const uint8_t* d_right, int N, int H,
   a.k_cen = aml_scale(p->cens_sigma);
   a.k_ncc = aml_scale(p->ncc_sigma);
   a.k_sad = aml_scale(p->sad_sigma);
-  a.DC = (g.D + kWarps - 1) / kWarps;
+  a.DC = 5 * (((g.D + kWarps - 1) / kWarps + 4) / 5);
   a.tiles_x = (g.w + kTile - 1) / kTile;
-  const size_t smem = fused_smem_bytes(g.D, &a.RWa, &a.RWFa);
-  MSN_REQUIRE(smem <= 227 * 1024, "ms_features: D=%d needs %zu B of shared memory", g.D, smem);
-  MSN_CUDA_OK(cudaFuncSetAttribute(ms_fused_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   const long long tiles = (long long)N * g.h * a.tiles_x;
   MSN_REQUIRE(tiles <= 2147483647LL, "ms_features: too many tiles for one launch");
-  ms_fused_kernel<<<(unsigned)tiles, kWarps * 32, smem, s>>>(a);
+#define MSN_FUSED_CASE(DMAX)                                                                          \
+  if (g.D <= DMAX) {                                                                                  \
+    const size_t smem = Lay<DMAX>::bytes;                                                             \
+    MSN_CUDA_OK(cudaFuncSetAttribute(ms_fused_kernel<DMAX>, cudaFuncAttributeMaxDynamicSharedMemorySize, \
+                                     (int)smem));                                                     \
+    ms_fused_kernel<DMAX><<<(unsigned)tiles, kWarps * 32, smem, s>>>(a);                              \
+  } else
+  MSN_FUSED_CASE(64)
+  MSN_FUSED_CASE(128)
+  MSN_FUSED_CASE(192)
+  MSN_FUSED_CASE(256)
+  MSN_FUSED_CASE(384)
+  MSN_FUSED_CASE(448) { return fail("ms_features: D=%d exceeds the fused kernel's limit", g.D); }
+#undef MSN_FUSED_CASE
   MSN_LAUNCH_OK();
   if (prof) {
     MSN_CUDA_OK(cudaEventRecord(rec.ev[3], s));

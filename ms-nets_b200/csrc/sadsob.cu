@@ -48,12 +48,24 @@ __global__ void sadsob_vband_kernel(const float* __restrict__ L, const float* __
   float* vb = Vb + (((size_t)n * gridDim.y + dd) * NB) * IW + j;
   float v = 0.f;
   int band = 0;
-  for (int row = 0; row < H; ++row) {
-    if (band < NB && row == band * RB) {
-      vb[(size_t)band * IW] = v;
-      ++band;
+  // rows are taken 8 at a time so 16 independent loads are in flight per thread; the adds
+  // stay strictly sequential (adding the 0.0f of an inactive column is exact)
+  for (int row0 = 0; row0 < H; row0 += 8) {
+    float av[8];
+#pragma unroll
+    for (int q = 0; q < 8; ++q) {
+      const int row = row0 + q;
+      av[q] = (active && row < H) ? absdiff_rn(__ldg(l + (size_t)row * W), __ldg(r + (size_t)row * W)) : 0.f;
     }
-    if (active) v = __fadd_rn(v, absdiff_rn(l[(size_t)row * W], r[(size_t)row * W]));
+#pragma unroll
+    for (int q = 0; q < 8; ++q) {
+      const int row = row0 + q;
+      if (band < NB && row == band * RB) {
+        vb[(size_t)band * IW] = v;
+        ++band;
+      }
+      v = __fadd_rn(v, av[q]);
+    }
   }
 }
 
@@ -92,10 +104,14 @@ sadsob_scan_kernel(const float* __restrict__ L, const float* __restrict__ R, int
     tV[lane] = v;
     const float* lp = Ln + (size_t)i0 * W + jc;
     const float* rp = Rn + (size_t)i0 * W + (jc - d);
-#pragma unroll 8
+    // all 2x31 loads of the tile column are issued before the dependent add chain starts
+    float av[kSadTile - 1];
+#pragma unroll
+    for (int r = 0; r < kSadTile - 1; ++r)
+      av[r] = (active && (i0 + r) < H) ? absdiff_rn(__ldg(lp + (size_t)r * W), __ldg(rp + (size_t)r * W)) : 0.f;
+#pragma unroll
     for (int r = 1; r < kSadTile; ++r) {
-      if (active && (i0 + r - 1) < H)
-        v = __fadd_rn(v, absdiff_rn(lp[(size_t)(r - 1) * W], rp[(size_t)(r - 1) * W]));
+      v = __fadd_rn(v, av[r - 1]);  // + 0.0f on inactive entries is exact
       tV[r * kSadVStride + lane] = v;
     }
     __syncwarp();
