@@ -70,12 +70,18 @@ __global__ void sadsob_vband_kernel(const float* __restrict__ L, const float* __
 }
 
 // grid: (ceil(Dn*NB / kSadWarps), 1, N); one warp per (dd, band).
+// WS > 0: window size known at compile time (shared strides and box offsets become
+// immediates); WS == 0: runtime wsize (any 1..16).
+template <int WS>
 __global__ void __launch_bounds__(kSadWarps * 32)
 sadsob_scan_kernel(const float* __restrict__ L, const float* __restrict__ R, int H, int W, int Dn,
-                   int d_begin, int wsize, int RB, int NB, size_t img_stride,
+                   int d_begin, int wsize_rt, int NB, size_t img_stride,
                    const float* __restrict__ Vb, float* __restrict__ out, size_t out_stride) {
+  constexpr int SS = (WS > 0) ? (kSadTile + WS + ((WS & 1) ? 0 : 1)) : kSadSStride;  // odd stride
   __shared__ float sV[kSadWarps][kSadTile * kSadVStride];
-  __shared__ float sS[kSadWarps][kSadTile * kSadSStride];
+  __shared__ float sS[kSadWarps][kSadTile * SS];
+  const int wsize = (WS > 0) ? WS : wsize_rt;
+  const int RB = kSadTile - wsize;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int job = blockIdx.x * kSadWarps + warp;
   if (job >= Dn * NB) return;  // whole warp exits together
@@ -89,26 +95,33 @@ sadsob_scan_kernel(const float* __restrict__ L, const float* __restrict__ R, int
   const float* Rn = R + n * img_stride;
   const float* vb = Vb + (((size_t)n * Dn + dd) * NB + b) * IW;
   float* o = out + n * out_stride + (size_t)dd * H * W;
+  const int rows_live = min(kSadTile - 1, H - i0);      // image rows i0 .. i0+rows_live-1 exist
+  const int rmax = min(RB, H - wsize - i0);             // origin rows produced by this band
 
   // table columns <= d are zero, so the sweep starts at the tile holding column d
   const int t0 = d / kSadTile, t1 = (W - 1) / kSadTile;
   float s = 0.f;  // horizontal carry of table row i0 + lane
+  float* srow = tS + lane * SS;
 #pragma unroll 1
-  for (int k = 0; k < wsize; ++k) tS[lane * kSadSStride + kSadTile + k] = 0.f;
+  for (int k = 0; k < wsize; ++k) srow[kSadTile + k] = 0.f;
   for (int t = t0; t <= t1; ++t) {
-    // (a) lanes own table columns: finish the vertical prefix inside the band
+    // (a) lanes own table columns: finish the vertical prefix inside the band.
+    // All loads of the tile column are issued before the dependent add chain starts.
     const int j = t * kSadTile + lane;
     const int jc = j - 1;
     const bool active = (j < IW) && (jc >= d);
-    float v = (j < IW) ? vb[j] : 0.f;
-    tV[lane] = v;
-    const float* lp = Ln + (size_t)i0 * W + jc;
-    const float* rp = Rn + (size_t)i0 * W + (jc - d);
-    // all 2x31 loads of the tile column are issued before the dependent add chain starts
+    float v = (j < IW) ? __ldg(vb + j) : 0.f;
     float av[kSadTile - 1];
+    {
+      const float* lp = Ln + (size_t)i0 * W + jc;
+      const float* rp = lp + (Rn - Ln) - d;
 #pragma unroll
-    for (int r = 0; r < kSadTile - 1; ++r)
-      av[r] = (active && (i0 + r) < H) ? absdiff_rn(__ldg(lp + (size_t)r * W), __ldg(rp + (size_t)r * W)) : 0.f;
+      for (int r = 0; r < kSadTile - 1; ++r) {
+        av[r] = (active && r < rows_live) ? absdiff_rn(__ldg(lp), __ldg(rp)) : 0.f;
+        lp += W; rp += W;
+      }
+    }
+    tV[lane] = v;
 #pragma unroll
     for (int r = 1; r < kSadTile; ++r) {
       v = __fadd_rn(v, av[r - 1]);  // + 0.0f on inactive entries is exact
@@ -116,26 +129,30 @@ sadsob_scan_kernel(const float* __restrict__ L, const float* __restrict__ R, int
     }
     __syncwarp();
     // (b) lanes own table rows: slide the halo, continue the horizontal chain
-    for (int k = 0; k < wsize; ++k)
-      tS[lane * kSadSStride + k] = tS[lane * kSadSStride + kSadTile + k];
-#pragma unroll 8
-    for (int c = 0; c < kSadTile; ++c) {
-      s = __fadd_rn(s, tV[lane * kSadVStride + c]);
-      tS[lane * kSadSStride + wsize + c] = s;
+#pragma unroll
+    for (int k = 0; k < (WS > 0 ? WS : kSadMaxW); ++k)
+      if (k < wsize) srow[k] = srow[kSadTile + k];
+    {
+      const float* vrow = tV + lane * kSadVStride;
+      float* dst = srow + wsize;
+#pragma unroll
+      for (int c = 0; c < kSadTile; ++c) {
+        s = __fadd_rn(s, vrow[c]);
+        dst[c] = s;
+      }
     }
     __syncwarp();
     // (c) lanes own origin columns again: boxes ((br - bl) - tr) + tl
     const int jo = t * kSadTile - wsize + lane;  // window origin column
     if (jo >= d && jo < W - wsize) {
-      for (int r = 0; r < RB; ++r) {
-        const int i = i0 + r;
-        if (i >= H - wsize) break;
-        const float br = tS[(r + wsize) * kSadSStride + lane + wsize];
-        const float bl = tS[(r + wsize) * kSadSStride + lane];
-        const float tr = tS[r * kSadSStride + lane + wsize];
-        const float tl = tS[r * kSadSStride + lane];
-        const float val = __fadd_rn(__fsub_rn(__fsub_rn(br, bl), tr), tl);
-        st_stream(o + (size_t)(i + wc) * W + (jo + wc), val);
+      const float* top = tS + lane;
+      const float* bot = top + wsize * SS;
+      float* op = o + (size_t)(i0 + wc) * W + (jo + wc);
+#pragma unroll 9
+      for (int r = 0; r < rmax; ++r) {
+        const float val = __fadd_rn(__fsub_rn(__fsub_rn(bot[wsize], bot[0]), top[wsize]), top[0]);
+        st_stream(op, val);
+        top += SS; bot += SS; op += W;
       }
     }
     __syncwarp();
@@ -173,8 +190,12 @@ int launch_sadsob_n(const float* L, const float* R, int N, int H, int W, int Dn,
   sadsob_vband_kernel<<<g1, 128, 0, s>>>(L, R, H, W, d_begin, RB, NB, (size_t)H * W, Vb);
   MSN_LAUNCH_OK();
   dim3 g2(div_up((long long)Dn * NB, kSadWarps), 1, N);
-  sadsob_scan_kernel<<<g2, kSadWarps * 32, 0, s>>>(L, R, H, W, Dn, d_begin, wsize, RB, NB, (size_t)H * W, Vb,
-                                                   out, out_stride);
+  if (wsize == 5)  // the reference's default sobelw (cbmv_generator.py:440)
+    sadsob_scan_kernel<5><<<g2, kSadWarps * 32, 0, s>>>(L, R, H, W, Dn, d_begin, wsize, NB, (size_t)H * W, Vb, out,
+                                                        out_stride);
+  else
+    sadsob_scan_kernel<0><<<g2, kSadWarps * 32, 0, s>>>(L, R, H, W, Dn, d_begin, wsize, NB, (size_t)H * W, Vb, out,
+                                                        out_stride);
   MSN_LAUNCH_OK();
   return 0;
 }

@@ -1,0 +1,216 @@
+"""Multi-GPU sharding of the MS hot path over torch.distributed (one process per GPU).
+
+Two modes:
+
+* batch sharding -- stereo pairs are independent end to end: pair i goes to rank
+  i % world, no collective on the data path (optionally an all_gather of the
+  [N,H,W] disparities for reporting).  This is what bench.py scales.
+
+* disparity-slab sharding -- for frames whose 32*D*H*W-byte volume does not fit one
+  GPU (BASELINE config M: 1984x2880, D=640 -> 117 GB): rank r owns disparities
+  [r*D/G, (r+1)*D/G) of the SAME pair.  Raw matcher costs at disparity d depend only on
+  the two images, so each rank computes its slab alone; the AML channels need the
+  per-pixel minimum and denominator over ALL disparities, which costs two small
+  all-reduces ([4,h,w] floats each: min, then sum) between the three kernels phases.
+  WTA merges through an order-preserving int64 key all-reduce(min); soft-argmin
+  through an all_gather of per-pixel (max, sum e, sum d*e) partials.  The output stays
+  sharded along D.  Cross-slab denominators are summed in a different order than the
+  reference's sequential loop, so AML stays in its tolerance class (2e-6 abs), as
+  SURVEY.md section 7 anticipates.
+
+The collectives are torch.distributed calls (NCCL over NVLink on the GPU box, gloo in
+the CPU tests of the host logic); the volumes never cross the links.
+"""
+import ctypes
+
+from . import _lib
+
+
+def shard_range(total, rank, world):
+    """Contiguous block partition: (begin, count) of `total` items for `rank`."""
+    if world < 1 or not (0 <= rank < world):
+        raise ValueError("bad rank/world %r/%r" % (rank, world))
+    base, rem = divmod(int(total), world)
+    begin = rank * base + min(rank, rem)
+    return begin, base + (1 if rank < rem else 0)
+
+
+def shard_batch(n_pairs, rank, world):
+    """Round-robin pair -> rank assignment (pair i -> rank i % world)."""
+    return list(range(rank, int(n_pairs), world))
+
+
+def _dist():
+    import torch.distributed as dist
+    return dist
+
+
+# ------------------------------------------------------------------ merges --
+def merge_min(t, group=None):
+    """in-place all-reduce(min) of the per-pixel slab minima [.., 4, h, w]."""
+    dist = _dist()
+    if dist.is_initialized() and dist.get_world_size(group) > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MIN, group=group)
+    return t
+
+
+def merge_sum(t, group=None):
+    """in-place all-reduce(sum) of the partial AML denominators [.., 4, h, w]."""
+    dist = _dist()
+    if dist.is_initialized() and dist.get_world_size(group) > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.SUM, group=group)
+    return t
+
+
+def merge_wta_keys(keys, group=None):
+    """in-place all-reduce(min) of int64 WTA keys (cost bits made monotonic << 32 | d,
+    top bit flipped so the signed order equals the unsigned one): the global winner and,
+    on ties, the lowest disparity -- np.argmin's rule (main_msnet.py:444-448)."""
+    dist = _dist()
+    if dist.is_initialized() and dist.get_world_size(group) > 1:
+        dist.all_reduce(keys, op=dist.ReduceOp.MIN, group=group)
+    return keys
+
+
+def gather_parts(part, group=None):
+    """all_gather of per-rank soft-argmin partials [N,3,H,W] -> [world,N,3,H,W]."""
+    import torch
+    dist = _dist()
+    if not (dist.is_initialized() and dist.get_world_size(group) > 1):
+        return part.unsqueeze(0)
+    world = dist.get_world_size(group)
+    part = part.contiguous()
+    out = torch.empty((world * part.shape[0],) + tuple(part.shape[1:]), dtype=part.dtype, device=part.device)
+    dist.all_gather_into_tensor(out, part, group=group)   # concatenates along dim 0
+    return out.view((world,) + tuple(part.shape))
+
+
+def wta_key_pack(cost_min, d_index):
+    """Host/torch restatement of the device key (fte.cu: pack_key) for CPU tests and for
+    callers that already hold (min, argmin): int64 tensor."""
+    import torch
+    bits = cost_min.contiguous().view(torch.int32).to(torch.int64) & 0xFFFFFFFF
+    neg = (bits & 0x80000000) != 0
+    mono = torch.where(neg, (~bits) & 0xFFFFFFFF, bits | 0x80000000)
+    u = (mono << 32) | (d_index.to(torch.int64) & 0xFFFFFFFF)
+    return u ^ (-0x8000000000000000)
+
+
+def wta_key_unpack(keys):
+    """-> (argmin int32, min float32)."""
+    import torch
+    u = keys ^ (-0x8000000000000000)
+    d = (u & 0xFFFFFFFF).to(torch.int32)
+    mono = (u >> 32) & 0xFFFFFFFF
+    pos = (mono & 0x80000000) != 0
+    bits = torch.where(pos, mono & 0x7FFFFFFF, (~mono) & 0xFFFFFFFF)
+    bits = torch.where(bits >= 0x80000000, bits - 0x100000000, bits).to(torch.int32)
+    return d, bits.view(torch.float32)
+
+
+def softargmin_merge_reference(parts):
+    """torch restatement of msn_soft_argmin_merge_dev for CPU tests: parts [P,N,3,H,W]."""
+    import torch
+    m, s, t = parts[:, :, 0], parts[:, :, 1], parts[:, :, 2]
+    M = m.max(dim=0).values
+    sc = torch.exp(m - M.unsqueeze(0))
+    return (t * sc).sum(0) / (s * sc).sum(0)
+
+
+# ---------------------------------------------------------- slab extractor --
+class SlabShardedMSFeatures(object):
+    """Disparity-slab sharded MS volume: every rank calls this with the SAME pair(s) and
+    receives its [N,8,D/G,h,w] slab.  Three kernel phases with two all-reduces between
+    them (see module docstring)."""
+
+    def __init__(self, N, H, W, maxdisp=192, rank=None, world=None, group=None, device=None, **kw):
+        import torch
+
+        from . import cbmv
+        dist = _dist()
+        if not torch.cuda.is_available():
+            raise _lib.MsnetsError("SlabShardedMSFeatures needs a CUDA device (no CPU fallback)")
+        if rank is None:
+            rank = dist.get_rank(group) if dist.is_initialized() else 0
+        if world is None:
+            world = dist.get_world_size(group) if dist.is_initialized() else 1
+        self.torch, self.group, self.rank, self.world = torch, group, rank, world
+        self.device = torch.device("cuda", torch.cuda.current_device()) if device is None else torch.device(device)
+        self.N, self.H, self.W = int(N), int(H), int(W)
+        self.d_begin, self.d_count = shard_range(maxdisp, rank, world)
+        if self.d_count < 1:
+            raise ValueError("more ranks than disparities")
+        if not kw.get("left_only", True):
+            raise NotImplementedError("slab sharding provides the 8-channel (left) volume")
+        self.params = cbmv.make_params(maxdisp, d_begin=self.d_begin, d_count=self.d_count, **kw)
+        self.shape = cbmv.output_shape(self.N, self.H, self.W, self.params)
+        self.h, self.w = self.shape[3], self.shape[4]
+        with torch.cuda.device(self.device):
+            nbytes = _lib.lib().msn_ms_slab_workspace_bytes(self.N, self.H, self.W, ctypes.byref(self.params))
+            if nbytes == 0:
+                raise _lib.MsnetsError(_lib.lib().msn_last_error().decode())
+            self.workspace = torch.empty(nbytes, dtype=torch.uint8, device=self.device)
+            self.mins = torch.empty((self.N, 4, self.h, self.w), dtype=torch.float32, device=self.device)
+            self.den = torch.empty((self.N, 4, self.h, self.w), dtype=torch.float32, device=self.device)
+
+    def __call__(self, left, right, out=None):
+        torch, L = self.torch, _lib.lib()
+        for t in (left, right):
+            if t.dtype != torch.uint8 or tuple(t.shape) != (self.N, self.H, self.W) or not t.is_cuda \
+                    or not t.is_contiguous():
+                raise ValueError("expected contiguous uint8 CUDA tensors of shape %s" % ((self.N, self.H, self.W),))
+        if out is None:
+            out = torch.empty(self.shape, dtype=torch.float32, device=self.device)
+        p = ctypes.byref(self.params)
+        with torch.cuda.device(self.device):
+            st = torch.cuda.current_stream().cuda_stream
+            _lib.check(L.msn_ms_slab_phase_a_dev(left.data_ptr(), right.data_ptr(), self.N, self.H, self.W, p, None,
+                                                 out.data_ptr(), self.mins.data_ptr(), self.workspace.data_ptr(),
+                                                 self.workspace.numel(), st))
+            merge_min(self.mins, self.group)
+            _lib.check(L.msn_ms_slab_phase_b_dev(out.data_ptr(), self.mins.data_ptr(), self.N, self.h, self.w, p,
+                                                 self.den.data_ptr(), st))
+            merge_sum(self.den, self.group)
+            _lib.check(L.msn_ms_slab_phase_c_dev(out.data_ptr(), self.mins.data_ptr(), self.den.data_ptr(), self.N,
+                                                 self.h, self.w, p, st))
+        return out
+
+
+def slab_soft_argmin(logits_slab, d_begin, group=None):
+    """Soft-argmin over a D-sharded logit volume: logits_slab [N,D/G,H,W] on each rank,
+    d_begin = first disparity of the slab -> full-range disparity [N,H,W] on every rank."""
+    import torch
+    x = logits_slab.contiguous()
+    N, Dn, H, W = x.shape
+    part = torch.empty((N, 3, H, W), dtype=torch.float32, device=x.device)
+    L = _lib.lib()
+    with torch.cuda.device(x.device):
+        st = torch.cuda.current_stream().cuda_stream
+        _lib.check(L.msn_soft_argmin_partial_dev(x.data_ptr(), N, Dn, H, W, int(d_begin), part.data_ptr(), st))
+        parts = gather_parts(part, group)
+        disp = torch.empty((N, H, W), dtype=torch.float32, device=x.device)
+        _lib.check(L.msn_soft_argmin_merge_dev(parts.data_ptr(), parts.shape[0], N, H, W, disp.data_ptr(), st))
+    return disp
+
+
+def slab_wta(cost_slab, d_begin, layout="dhw", group=None):
+    """Winner-take-all over a D-sharded cost volume -> (argmin int32, min float32) of the
+    full disparity range on every rank."""
+    import torch
+    c = cost_slab.contiguous()
+    lay = 0 if layout == "hwd" else 1
+    D = c.shape[-1] if lay == 0 else c.shape[0]
+    shp = tuple(c.shape[:-1]) if lay == 0 else tuple(c.shape[1:])
+    n = 1
+    for v in shp:
+        n *= v
+    keys = torch.empty(shp, dtype=torch.int64, device=c.device)
+    L = _lib.lib()
+    with torch.cuda.device(c.device):
+        st = torch.cuda.current_stream().cuda_stream
+        _lib.check(L.msn_wta_keys_dev(c.data_ptr(), n, D, lay, int(d_begin), keys.data_ptr(), st))
+        merge_wta_keys(keys, group)
+        am = torch.empty(shp, dtype=torch.int32, device=c.device)
+        m1 = torch.empty(shp, dtype=torch.float32, device=c.device)
+        _lib.check(L.msn_wta_unpack_dev(keys.data_ptr(), n, am.data_ptr(), m1.data_ptr(), st))
+    return am, m1
