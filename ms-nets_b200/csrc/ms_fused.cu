@@ -14,20 +14,25 @@
 //                        summed-area table needs whole-row sequential scans, so it
 //                        cannot live inside an x-tile.
 //   3. ms_fused_kernel   one CTA = one output row y x 32 pixels x ALL D:
+//        stage    right-image row data (census codes, stats, 5 float rows) and the
+//                 tile's SAD-of-Sobel costs stream into shared memory with cp.async.
 //        phase 1  8 warps split D; lane = pixel.  Per (pixel, d): census popcount,
 //                 NCC (9 fp32 products of exact integers, fp64 scaling), ZSAD (75
 //                 ordered fp32 adds over a register-resident 5x5 window that slides
-//                 with d), sadsob load; channels 0-3 are normalised and stored as four
-//                 128-byte row segments per warp; raw costs are parked in shared
-//                 memory (13 B/voxel: three floats + census byte); per-pixel minima.
-//        phase 2  exponentials exp(-(c-m)^2/sigma) written over the parked costs.
+//                 with d); raw costs are parked in shared memory (13 B/voxel: three
+//                 floats + census byte); per-pixel minima.
+//        phase 2  thread = (pixel quad, d): channels 0-3 normalised and stored as
+//                 128-bit row segments; exponentials exp(-(c-m)^2/sigma) written over
+//                 the parked costs.
 //        phase 3  one thread per (pixel, matcher) adds the denominator in d order
 //                 (the reference's sequential fp32 sum, featextract.cpp:444-447).
-//        phase 4  channels 4-7 = e / den, again 128-byte segments per warp.
+//        phase 4  channels 4-7 = e / den, 128-bit row segments.
 //
 // Bounding resource: HBM writes (32 B per voxel) co-limited by issue slots -- ZSAD
 // alone is 75 dependent-order FADDs per voxel (DESIGN.md has the arithmetic).
 #include "ms_fused.cuh"
+
+#include <stdlib.h>
 
 #include <mutex>
 #include <vector>
@@ -63,7 +68,7 @@ FusedGeom make_geom(int N, int H, int W, const msn_ms_params* p) {
   g.bh = p->board_h; g.bwl = p->board_w_left;
   g.h = H - 2 * p->board_h;
   g.w = W - p->board_w_left - p->board_w_right;
-  g.padL = (g.D + 1 + 7) & ~7;
+  g.padL = (g.D + 1 + 40 + 8 + 7) & ~7;  // D-1 columns of disparity + dummy-step slack (kSlack) + halo/alignment
   g.Hp = H + 2 * kPadT;
   g.Wp = (W + g.padL + kPadR + 3) & ~3;
   return g;
@@ -181,24 +186,29 @@ struct FusedArgs {
   float k_cen, k_ncc, k_sad;
   int DC;               // disparity steps per warp (multiple of 5)
   int tiles_x;
+  int num_tiles;
 };
 
 // Shared-memory layout for disparity counts up to DMAX.  Row strides are compile-time
 // so every shared access in the hot loop is "pointer + immediate".
-constexpr int kSlack = 40;  // right-image entries below index 0 reached by dummy steps (d >= D)
+constexpr int kSlack = 40;  // right-image entries below index 0 reached by dummy steps (d >= D); see make_geom
 template <int DMAX>
 struct Lay {
   static constexpr int RW = (DMAX + kTile - 1 + kSlack + 3) & ~3;  // desc / stat entries
-  static constexpr int RWF = RW + 8;                               // float row length (halo 2 each side)
+  static constexpr int RWF = RW + 8;                               // float row: halo 2+2, align shift <= 3
   static constexpr int DS = DMAX + 1;                              // parked planes + 1 scratch plane
-  static constexpr size_t off_desc = 0;
-  static constexpr size_t off_stat = off_desc + (size_t)RW * 16;
-  static constexpr size_t off_rf = off_stat + (size_t)RW * 16;
-  static constexpr size_t off_red = off_rf + (size_t)5 * RWF * 4;
-  static constexpr size_t off_lut = off_red + (size_t)kWarps * 4 * 32 * 4;
-  static constexpr size_t off_inv = off_lut + 128 * 4;
-  static constexpr size_t off_par = off_inv + 4 * 32 * 4;          // [3][DS][32] ncc, sadsob, zsad
-  static constexpr size_t off_cen = off_par + (size_t)3 * DS * 32 * 4;  // [DS][32] bytes
+  // staging buffer: right-image row data of the tile
+  static constexpr size_t st_desc = 0;
+  static constexpr size_t st_stat = st_desc + (size_t)RW * 16;
+  static constexpr size_t st_rf = st_stat + (size_t)RW * 16;
+  static constexpr size_t st_bytes = st_rf + (size_t)5 * RWF * 4;
+  static constexpr size_t off_stage = 0;
+  static constexpr size_t off_red = off_stage + st_bytes;                     // [8][4][32]
+  static constexpr size_t off_min = off_red + (size_t)kWarps * 4 * 32 * 4;   // [4][32]
+  static constexpr size_t off_inv = off_min + 4 * 32 * 4;                    // [4][32]
+  static constexpr size_t off_lut = off_inv + 4 * 32 * 4;                    // [128]
+  static constexpr size_t off_par = off_lut + 128 * 4;                       // [3][DS][32] ncc, sadsob, zsad
+  static constexpr size_t off_cen = off_par + (size_t)3 * DS * 32 * 4;       // [DS][32] bytes
   static constexpr size_t bytes = off_cen + (size_t)DS * 32;
 };
 
@@ -217,243 +227,368 @@ __device__ __forceinline__ void cp_async4(void* smem_dst, const void* gmem_src) 
   const uint32_t d = (uint32_t)__cvta_generic_to_shared(smem_dst);
   asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(d), "l"(gmem_src) : "memory");
 }
+__device__ __forceinline__ void cp_async16(void* smem_dst, const void* gmem_src) {
+  const uint32_t d = (uint32_t)__cvta_generic_to_shared(smem_dst);
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(d), "l"(gmem_src) : "memory");
+}
 __device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_all;" ::: "memory"); }
 
+struct TileId {
+  int n, y, x0;
+};
+__device__ __forceinline__ TileId decode_tile(int tile, const FusedArgs& a) {
+  TileId t;
+  const int xt = tile % a.tiles_x;
+  tile /= a.tiles_x;
+  t.y = tile % a.g.h;
+  t.n = tile / a.g.h;
+  t.x0 = xt * kTile;
+  return t;
+}
+
+// Asynchronously copies the right-image row data of `t` into one staging buffer:
+// census codes and stats of the D+31(+slack) columns the tile can touch and the five
+// float rows of the ZSAD/NCC windows (16-byte cp.async; the float rows start at a
+// 4-float aligned column, the 0..3 float shift is returned through *shift).
+template <int DMAX>
+__device__ __forceinline__ void stage_right(const FusedArgs& a, const TileId& t, unsigned char* buf) {
+  using L = Lay<DMAX>;
+  const FusedGeom& g = a.g;
+  const int D = g.D;
+  const int RWn = D + kTile - 1 + kSlack;
+  const int XbaseP = t.x0 + g.bwl - (D - 1) - kSlack + g.padL;
+  const int Yp = t.y + g.bh + kPadT;
+  const size_t img_off = (size_t)t.n * g.img_px();
+  const uint4* gd = a.descR + img_off + (size_t)Yp * g.Wp + XbaseP;
+  const uint4* gs = reinterpret_cast<const uint4*>(a.statR + img_off + (size_t)Yp * g.Wp + XbaseP);
+  uint4* s_desc = reinterpret_cast<uint4*>(buf + L::st_desc);
+  uint4* s_stat = reinterpret_cast<uint4*>(buf + L::st_stat);
+  float* s_rf = reinterpret_cast<float*>(buf + L::st_rf);
+  for (int i = threadIdx.x; i < RWn; i += kWarps * 32) {
+    cp_async16(s_desc + i, gd + i);
+    cp_async16(s_stat + i, gs + i);
+  }
+  const int fstart = (XbaseP - 2) & ~3;                 // aligned first float column
+  const int nvec = (RWn + 4 + 3 + 3) >> 2;              // 16-byte groups per row (covers any shift)
+  for (int i = threadIdx.x; i < 5 * nvec; i += kWarps * 32) {
+    const int r = i / nvec, v = i - r * nvec;
+    cp_async16(s_rf + r * L::RWF + 4 * v, a.fR + img_off + (size_t)(Yp - 2 + r) * g.Wp + fstart + 4 * v);
+  }
+}
+
+// The lane's own left-image data: census code, stats, 5x5 float window.
+struct LeftRegs {
+  uint4 desc;
+  uint4 stat;
+  float px[5][5];
+};
+__device__ __forceinline__ void load_left(const FusedArgs& a, const TileId& t, int lane, LeftRegs& lr) {
+  const FusedGeom& g = a.g;
+  const int Yp = t.y + g.bh + kPadT;
+  const int Xp = t.x0 + lane + g.bwl + g.padL;
+  const size_t img_off = (size_t)t.n * g.img_px();
+  lr.desc = __ldg(a.descL + img_off + (size_t)Yp * g.Wp + Xp);
+  lr.stat = __ldg(reinterpret_cast<const uint4*>(a.statL + img_off + (size_t)Yp * g.Wp + Xp));
+#pragma unroll
+  for (int r = 0; r < 5; ++r) {
+    const float* gf = a.fL + img_off + (size_t)(Yp - 2 + r) * g.Wp + (Xp - 2);
+#pragma unroll
+    for (int c = 0; c < 5; ++c) lr.px[r][c] = __ldg(gf + c);
+  }
+}
+
+// One CTA per tile.  (A persistent variant with double-buffered staging and left-image
+// register prefetch was measured 13 % SLOWER on B200: resident CTAs fall into lockstep and
+// the hardware CTA scheduler balances the cheaper border tiles better; see DESIGN.md.)
 template <int DMAX>
 __global__ void __launch_bounds__(kWarps * 32, 2) ms_fused_kernel(const FusedArgs a) {
   using L = Lay<DMAX>;
   extern __shared__ __align__(16) unsigned char smem_raw[];
   const FusedGeom& g = a.g;
   const int D = g.D;
-  uint4* s_desc = reinterpret_cast<uint4*>(smem_raw + L::off_desc);
-  uint4* s_stat = reinterpret_cast<uint4*>(smem_raw + L::off_stat);  // RStat viewed as 16 bytes
-  float* s_rf = reinterpret_cast<float*>(smem_raw + L::off_rf);      // [5][RWF]
   float* s_red = reinterpret_cast<float*>(smem_raw + L::off_red);    // [8][4][32]
-  float* s_lut = reinterpret_cast<float*>(smem_raw + L::off_lut);    // [128]
+  float* s_min = reinterpret_cast<float*>(smem_raw + L::off_min);    // [4][32]
   float* s_inv = reinterpret_cast<float*>(smem_raw + L::off_inv);    // [4][32]
+  float* s_lut = reinterpret_cast<float*>(smem_raw + L::off_lut);    // [128]
   float* s_par = reinterpret_cast<float*>(smem_raw + L::off_par);    // [3][DS][32]
   uint8_t* s_cen = smem_raw + L::off_cen;                            // [DS][32]
   constexpr int PS = L::DS * 32;                                     // floats per parked matcher
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  int tile = blockIdx.x;
-  const int xt = tile % a.tiles_x; tile /= a.tiles_x;
-  const int y = tile % g.h;
-  const int n = tile / g.h;
-  const int x0 = xt * kTile;
   const int H = g.H, W = g.W;
-  const int Y = y + g.bh;                 // bordered image row
-  const int Yp = Y + kPadT;               // padded row
-  const int X = x0 + lane + g.bwl;        // bordered image column of this lane
-  const int Xp = X + g.padL;
-  const int RWn = D + kTile - 1 + kSlack;  // entries staged: shared index i <-> padded col XbaseP + i
-  const int XbaseP = x0 + g.bwl - (D - 1) - kSlack + g.padL;
-  const size_t img_off = (size_t)n * g.img_px();
-  const bool live = (x0 + lane) < g.w;
   const int d_lo = warp * a.DC;
   const int d_end = min(D, d_lo + a.DC);  // real disparities of this warp: [d_lo, d_end)
+  const size_t plane = (size_t)g.h * g.w;
+  const size_t chan = plane * D;
+  const size_t splane = (size_t)H * W;
+  // 128-bit stores need 16-byte aligned rows
+  const bool vec_ok = ((g.w & 3) == 0) && ((reinterpret_cast<uintptr_t>(a.out) & 15) == 0);
+  // AML-phase mapping: thread = (pixel quad q, disparity lane dl); d = dl, dl+32, ...
+  const int q4 = (threadIdx.x & 7) * 4;
+  const int dl = threadIdx.x >> 3;
 
-  // ---- sadsob costs of this lane's own disparities: async global -> parked plane 1 ----
+  const TileId t = decode_tile(blockIdx.x, a);
+  unsigned char* buf = smem_raw + L::off_stage;
   {
-    const float* src = a.sadsob + ((size_t)n * D * H + Y) * W + X + (size_t)d_lo * H * W;
-    float* dst = s_par + PS + d_lo * 32 + lane;
-    const size_t splane = (size_t)H * W;
-    for (int d = d_lo; d < d_end; ++d, src += splane, dst += 32) cp_async4(dst, src);
-  }
+    const int X = t.x0 + lane + g.bwl;      // bordered image column of this lane
+    const int Y = t.y + g.bh;               // bordered image row
 
-  // ---- stage the right-image row data in shared memory -------------------
-  {
-    const uint4* gd = a.descR + img_off + (size_t)Yp * g.Wp + XbaseP;
-    const uint4* gs = reinterpret_cast<const uint4*>(a.statR + img_off + (size_t)Yp * g.Wp + XbaseP);
-    for (int i = threadIdx.x; i < RWn; i += kWarps * 32) {
-      s_desc[i] = __ldg(gd + i);
-      s_stat[i] = __ldg(gs + i);
+    // sadsob costs of this lane's own disparities: async global -> parked plane 1
+    {
+      const float* src = a.sadsob + ((size_t)t.n * D * H + Y) * W + X + (size_t)d_lo * splane;
+      float* dst = s_par + PS + d_lo * 32 + lane;
+      for (int d = d_lo; d < d_end; ++d, src += splane, dst += 32) cp_async4(dst, src);
     }
-#pragma unroll
-    for (int r = 0; r < 5; ++r) {
-      const float* gf = a.fR + img_off + (size_t)(Yp - 2 + r) * g.Wp + (XbaseP - 2);
-      for (int i = threadIdx.x; i < RWn + 4; i += kWarps * 32) s_rf[r * L::RWF + i] = __ldg(gf + i);
-    }
+    stage_right<DMAX>(a, t, buf);
     if (threadIdx.x < 128) {
       const int kk = threadIdx.x;
       s_lut[kk] = (kk <= 120) ? ex2_approx(-(float)(kk * kk) * a.k_cen) : 0.f;
     }
-  }
-
-  // ---- per-lane left-image data in registers -----------------------------
-  const uint4 ld = __ldg(a.descL + img_off + (size_t)Yp * g.Wp + Xp);
-  RStat ls;
-  {
-    const uint4 raw = __ldg(reinterpret_cast<const uint4*>(a.statL + img_off + (size_t)Yp * g.Wp + Xp));
-    ls = *reinterpret_cast<const RStat*>(&raw);
-  }
-  float at[5][5];   // (L - mL), hoisted over all d   (matchers.cpp:503)
-  float l3[3][3];   // centre 3x3 of L as float for NCC
+    LeftRegs lr;
+    load_left(a, t, lane, lr);
+    const uint4 ld = lr.desc;
+    const RStat ls = *reinterpret_cast<const RStat*>(&lr.stat);
+    float at[5][5];   // (L - mL), hoisted over all d   (matchers.cpp:503)
+    float l3[3][3];   // centre 3x3 of L as float for NCC
 #pragma unroll
-  for (int r = 0; r < 5; ++r) {
-    const float* gf = a.fL + img_off + (size_t)(Yp - 2 + r) * g.Wp + (Xp - 2);
+    for (int r = 0; r < 5; ++r)
 #pragma unroll
-    for (int c = 0; c < 5; ++c) {
-      const float v = __ldg(gf + c);
-      at[r][c] = __fsub_rn(v, ls.mean);
-      if (r >= 1 && r <= 3 && c >= 1 && c <= 3) l3[r - 1][c - 1] = v;
-    }
-  }
-  // validity: cost(y,x,d) exists iff the window origin is inside and x - wc >= d (and d < D)
-  const int dmax_cen = min(D - 1, (Y >= 5 && Y < H - 6 && X >= 5 && X < W - 6) ? X - 5 : -1);
-  const int dmax_ncc = min(D - 1, (Y >= 1 && Y < H - 2 && X >= 1 && X < W - 2) ? X - 1 : -1);
-  const int dmax_sad = min(D - 1, (Y >= 2 && Y < H - 3 && X >= 2 && X < W - 3) ? X - 2 : -1);
-  const int dmax_live = live ? D - 1 : -1;
+      for (int c = 0; c < 5; ++c) {
+        at[r][c] = __fsub_rn(lr.px[r][c], ls.mean);
+        if (r >= 1 && r <= 3 && c >= 1 && c <= 3) l3[r - 1][c - 1] = lr.px[r][c];
+      }
+    // validity: cost(y,x,d) exists iff the window origin is inside and x - wc >= d (and d < D)
+    const int dmax_cen = min(D - 1, (Y >= 5 && Y < H - 6 && X >= 5 && X < W - 6) ? X - 5 : -1);
+    const int dmax_ncc = min(D - 1, (Y >= 1 && Y < H - 2 && X >= 1 && X < W - 2) ? X - 1 : -1);
+    const int dmax_sad = min(D - 1, (Y >= 2 && Y < H - 3 && X >= 2 && X < W - 3) ? X - 2 : -1);
 
-  const size_t plane = (size_t)g.h * g.w;
-  const size_t chan = plane * D;
-  float* o0 = a.out + (size_t)n * 8 * chan + (size_t)y * g.w + (x0 + lane) + (size_t)d_lo * plane;
-  float* o1 = o0 + chan;
-  float* o2 = o1 + chan;
-  float* o3 = o2 + chan;
-
-  cp_async_wait_all();
-  __syncthreads();
-
-  // ---- phase 1: costs, channels 0-3, parking, minima ----------------------
-  // shared index of right column X - d is ir = lane + kSlack + (D-1) - d; it falls by one per step
-  const int ir0 = lane + kSlack + (D - 1) - d_lo;
-  const float* rfp = s_rf + ir0;
-  const uint4* dscp = s_desc + ir0;
-  const uint4* sttp = s_stat + ir0;
-  float rw[5][5];  // sliding 5x5 right window; logical column c lives in rw[.][(c - s) mod 5]
-#pragma unroll
-  for (int r = 0; r < 5; ++r)
-#pragma unroll
-    for (int c = 0; c < 5; ++c) rw[r][c] = rfp[r * L::RWF + c];
-  int min_cen = 255;
-  float min_ncc = kFill, min_sob = kFill, min_sad = kFill;
-
-  for (int base = 0; base < a.DC; base += 5) {
-#pragma unroll
-    for (int k = 0; k < 5; ++k) {
-      const int d = d_lo + base + k;
-      const int ds = min(d, D);  // dummy steps (d >= D) park into the scratch plane
-      float* park = s_par + ds * 32 + lane;
-      const uint4 rd = *dscp;
-      const uint4 rs_raw = *sttp;
-      const RStat rs = *reinterpret_cast<const RStat*>(&rs_raw);
-      float sob = park[PS];
-
-      // census: Hamming distance of the packed codes (matchers.cpp:323-337)
-      const int cen = __popc(ld.x ^ rd.x) + __popc(ld.y ^ rd.y) + __popc(ld.z ^ rd.z) + __popc(ld.w ^ rd.w);
-      const bool ok_cen = d <= dmax_cen;
-      const int cen_b = ok_cen ? cen : 255;
-      const float f0 = ok_cen ? div120_exact(int_to_float_small(cen)) : 1.0f;
-
-      // NCC: P exact in fp32 (< 2^24); scaling in fp64 left to right (matchers.cpp:200-201)
-      float P = 0.f;
-#pragma unroll
-      for (int r = 0; r < 3; ++r)
-#pragma unroll
-        for (int c = 0; c < 3; ++c) P = __fmaf_rn(l3[r][c], rw[r + 1][(c + 1 - k + 5) % 5], P);
-      const float num = __fmaf_rn(9.0f, P, -__fmul_rn(ls.A, rs.A));
-      const double t = __dmul_rn(__dmul_rn(-(double)num, ls.C), rs.C);
-      float ncc = (float)t;
-      ncc = (fabsf(ncc) <= 3.0e38f) ? ncc : 1.0f;  // either C was inf (flat window), :196,204
-      ncc = (d <= dmax_ncc) ? ncc : kFill;
-
-      // ZSAD: 25 taps row-major, ((L - mL) - R) + mR, sequential fp32 (matchers.cpp:499-506)
-      float z = 0.f;
+    cp_async_wait_all();
+    __syncthreads();
+    // ---- phase 1: raw costs into the parking planes, per-pixel minima ----------------
+    {
+      const uint4* s_desc = reinterpret_cast<const uint4*>(buf + L::st_desc);
+      const uint4* s_stat = reinterpret_cast<const uint4*>(buf + L::st_stat);
+      const float* s_rf = reinterpret_cast<const float*>(buf + L::st_rf);
+      // shared index of right column X - d is ir = lane + kSlack + (D-1) - d; falls by one per step
+      const int XbaseP = t.x0 + g.bwl - (D - 1) - kSlack + g.padL;
+      const int shift = (XbaseP - 2) & 3;
+      const int ir0 = lane + kSlack + (D - 1) - d_lo;
+      const float* rfp = s_rf + shift + ir0;
+      const uint4* dscp = s_desc + ir0;
+      const uint4* sttp = s_stat + ir0;
+      float rw[5][5];  // sliding 5x5 right window; logical column c lives in rw[.][(c - s) mod 5]
 #pragma unroll
       for (int r = 0; r < 5; ++r)
 #pragma unroll
-        for (int c = 0; c < 5; ++c) {
-          const float u = __fadd_rn(__fsub_rn(at[r][c], rw[r][(c - k + 5) % 5]), rs.mean);
-          z = __fadd_rn(z, fabsf(u));
+        for (int c = 0; c < 5; ++c) rw[r][c] = rfp[r * L::RWF + c];
+      int min_cen = 255;
+      float min_ncc = kFill, min_sob = kFill, min_sad = kFill;
+
+      for (int base = 0; base < a.DC; base += 5) {
+#pragma unroll
+        for (int k = 0; k < 5; ++k) {
+          const int d = d_lo + base + k;
+          const int ds = min(d, D);  // dummy steps (d >= D) park into the scratch plane
+          float* park = s_par + ds * 32 + lane;
+          const uint4 rd = *dscp;
+          const uint4 rs_raw = *sttp;
+          const RStat rs = *reinterpret_cast<const RStat*>(&rs_raw);
+          float sob = park[PS];
+
+          // census: Hamming distance of the packed codes (matchers.cpp:323-337)
+          const int cen = __popc(ld.x ^ rd.x) + __popc(ld.y ^ rd.y) + __popc(ld.z ^ rd.z) + __popc(ld.w ^ rd.w);
+          const int cen_b = (d <= dmax_cen) ? cen : 255;
+
+          // NCC: P exact in fp32 (< 2^24); scaling in fp64 left to right (matchers.cpp:200-201)
+          float P = 0.f;
+#pragma unroll
+          for (int r = 0; r < 3; ++r)
+#pragma unroll
+            for (int c = 0; c < 3; ++c) P = __fmaf_rn(l3[r][c], rw[r + 1][(c + 1 - k + 5) % 5], P);
+          const float num = __fmaf_rn(9.0f, P, -__fmul_rn(ls.A, rs.A));
+          const double tt = __dmul_rn(__dmul_rn(-(double)num, ls.C), rs.C);
+          float ncc = (float)tt;
+          ncc = (fabsf(ncc) <= 3.0e38f) ? ncc : 1.0f;  // either C was inf (flat window), :196,204
+          ncc = (d <= dmax_ncc) ? ncc : kFill;
+
+          // ZSAD: 25 taps row-major, ((L - mL) - R) + mR, sequential fp32 (matchers.cpp:499-506)
+          float z = 0.f;
+#pragma unroll
+          for (int r = 0; r < 5; ++r)
+#pragma unroll
+            for (int c = 0; c < 5; ++c) {
+              const float u = __fadd_rn(__fsub_rn(at[r][c], rw[r][(c - k + 5) % 5]), rs.mean);
+              z = __fadd_rn(z, fabsf(u));
+            }
+          const bool ok_sad = d <= dmax_sad;
+          z = ok_sad ? z : kFill;
+          sob = ok_sad ? sob : kFill;
+
+          s_cen[ds * 32 + lane] = (uint8_t)cen_b;
+          park[0] = ncc;
+          park[PS] = sob;
+          park[2 * PS] = z;
+          min_cen = min(min_cen, cen_b);
+          min_ncc = fminf(min_ncc, ncc);
+          min_sob = fminf(min_sob, sob);
+          min_sad = fminf(min_sad, z);
+          // slide the window: next step's new left column
+          --rfp; --dscp; --sttp;
+#pragma unroll
+          for (int r = 0; r < 5; ++r) rw[r][(4 - k) % 5] = rfp[r * L::RWF];
         }
-      const bool ok_sad = d <= dmax_sad;
-      z = ok_sad ? z : kFill;
-      sob = ok_sad ? sob : kFill;
-
-      // channels 0-3 (cbmv_generator.py:283-287)
-      if (d <= dmax_live) {
-        st_stream(o0, f0);
-        st_stream(o1, normalise_cost(ncc, 1));
-        st_stream(o2, normalise_cost(sob, 2));
-        st_stream(o3, normalise_cost(z, 3));
       }
-      o0 += plane; o1 += plane; o2 += plane; o3 += plane;
-      // park raw costs for the AML phases
-      s_cen[ds * 32 + lane] = (uint8_t)cen_b;
-      park[0] = ncc;
-      park[PS] = sob;
-      park[2 * PS] = z;
-      min_cen = min(min_cen, cen_b);
-      min_ncc = fminf(min_ncc, ncc);
-      min_sob = fminf(min_sob, sob);
-      min_sad = fminf(min_sad, z);
-      // slide the window: next step's new left column
-      --rfp; --dscp; --sttp;
-#pragma unroll
-      for (int r = 0; r < 5; ++r) rw[r][(4 - k) % 5] = rfp[r * L::RWF];
+      s_red[(warp * 4 + 0) * 32 + lane] = (min_cen == 255) ? kFill : (float)min_cen;
+      s_red[(warp * 4 + 1) * 32 + lane] = min_ncc;
+      s_red[(warp * 4 + 2) * 32 + lane] = min_sob;
+      s_red[(warp * 4 + 3) * 32 + lane] = min_sad;
     }
-  }
-  s_red[(warp * 4 + 0) * 32 + lane] = (min_cen == 255) ? kFill : (float)min_cen;
-  s_red[(warp * 4 + 1) * 32 + lane] = min_ncc;
-  s_red[(warp * 4 + 2) * 32 + lane] = min_sob;
-  s_red[(warp * 4 + 3) * 32 + lane] = min_sad;
-  __syncthreads();
-  float m[4];
+    __syncthreads();
+    if (threadIdx.x < 128) {  // minima across the 8 warps
+      float v = kFill;
 #pragma unroll
-  for (int q = 0; q < 4; ++q) {
-    float v = kFill;
+      for (int wv = 0; wv < kWarps; ++wv) v = fminf(v, s_red[wv * 128 + threadIdx.x]);
+      s_min[threadIdx.x] = v;
+    }
+    __syncthreads();
+
+    // ---- phase 2: channels 0-3 (cbmv_generator.py:283-287) out as 128-bit rows, and the
+    //      exponentials exp(-(c-m)^2/sigma) written over the parked float costs ----------
+    const float4 m_cen4 = *reinterpret_cast<const float4*>(s_min + q4);
+    const float4 m_ncc4 = *reinterpret_cast<const float4*>(s_min + 32 + q4);
+    const float4 m_sob4 = *reinterpret_cast<const float4*>(s_min + 64 + q4);
+    const float4 m_sad4 = *reinterpret_cast<const float4*>(s_min + 96 + q4);
+    float* orow = a.out + (size_t)t.n * 8 * chan + (size_t)t.y * g.w + (t.x0 + q4);
+    const int nlive = min(4, g.w - (t.x0 + q4));  // live pixels of this quad (<= 0: none)
+    for (int d = dl; d < D; d += 32) {
+      float* e0 = s_par + d * 32 + q4;
+      const uchar4 cb = *reinterpret_cast<const uchar4*>(s_cen + d * 32 + q4);
+      float4 c0;
+      c0.x = (cb.x == 255) ? 1.0f : div120_exact(int_to_float_small(cb.x));
+      c0.y = (cb.y == 255) ? 1.0f : div120_exact(int_to_float_small(cb.y));
+      c0.z = (cb.z == 255) ? 1.0f : div120_exact(int_to_float_small(cb.z));
+      c0.w = (cb.w == 255) ? 1.0f : div120_exact(int_to_float_small(cb.w));
+      float4 v1 = *reinterpret_cast<float4*>(e0);
+      float4 v2 = *reinterpret_cast<float4*>(e0 + PS);
+      float4 v3 = *reinterpret_cast<float4*>(e0 + 2 * PS);
+      float4 c1 = make_float4(normalise_cost(v1.x, 1), normalise_cost(v1.y, 1), normalise_cost(v1.z, 1),
+                              normalise_cost(v1.w, 1));
+      float4 c2 = make_float4(normalise_cost(v2.x, 2), normalise_cost(v2.y, 2), normalise_cost(v2.z, 2),
+                              normalise_cost(v2.w, 2));
+      float4 c3 = make_float4(normalise_cost(v3.x, 3), normalise_cost(v3.y, 3), normalise_cost(v3.z, 3),
+                              normalise_cost(v3.w, 3));
+      float* o = orow + (size_t)d * plane;
+      if (vec_ok && nlive == 4) {
+        st_stream4(o, c0);
+        st_stream4(o + chan, c1);
+        st_stream4(o + 2 * chan, c2);
+        st_stream4(o + 3 * chan, c3);
+      } else {
+        const float cc[4][4] = {{c0.x, c0.y, c0.z, c0.w}, {c1.x, c1.y, c1.z, c1.w}, {c2.x, c2.y, c2.z, c2.w},
+                                {c3.x, c3.y, c3.z, c3.w}};
 #pragma unroll
-    for (int wv = 0; wv < kWarps; ++wv) v = fminf(v, s_red[(wv * 4 + q) * 32 + lane]);
-    m[q] = v;
-  }
-
-  // ---- phase 2: exponentials over the parked float costs (own d range: no sync) ----
-  {
-    float* e = s_par + d_lo * 32 + lane;
-#pragma unroll 4
-    for (int d = d_lo; d < d_end; ++d, e += 32) {
-      e[0] = aml_e(e[0], m[1], a.k_ncc);
-      e[PS] = aml_e(e[PS], m[2], a.k_sad);
-      e[2 * PS] = aml_e(e[2 * PS], m[3], a.k_sad);
+        for (int ch = 0; ch < 4; ++ch)
+#pragma unroll
+          for (int i = 0; i < 4; ++i)
+            if (i < nlive) st_stream(o + ch * chan + i, cc[ch][i]);
+      }
+      v1 = make_float4(aml_e(v1.x, m_ncc4.x, a.k_ncc), aml_e(v1.y, m_ncc4.y, a.k_ncc),
+                       aml_e(v1.z, m_ncc4.z, a.k_ncc), aml_e(v1.w, m_ncc4.w, a.k_ncc));
+      v2 = make_float4(aml_e(v2.x, m_sob4.x, a.k_sad), aml_e(v2.y, m_sob4.y, a.k_sad),
+                       aml_e(v2.z, m_sob4.z, a.k_sad), aml_e(v2.w, m_sob4.w, a.k_sad));
+      v3 = make_float4(aml_e(v3.x, m_sad4.x, a.k_sad), aml_e(v3.y, m_sad4.y, a.k_sad),
+                       aml_e(v3.z, m_sad4.z, a.k_sad), aml_e(v3.w, m_sad4.w, a.k_sad));
+      *reinterpret_cast<float4*>(e0) = v1;
+      *reinterpret_cast<float4*>(e0 + PS) = v2;
+      *reinterpret_cast<float4*>(e0 + 2 * PS) = v3;
     }
-  }
-  __syncthreads();
+    __syncthreads();
 
-  // ---- phase 3: denominators in the reference's order (sequential fp32 over d) ----
-  const int mc = (m[0] == kFill) ? 0 : (int)m[0];
-  if (warp < 4) {
-    float den = 0.f;
-    if (warp == 0) {
-      const uint8_t* c = s_cen + lane;
-#pragma unroll 8
-      for (int d = 0; d < D; ++d, c += 32) den = __fadd_rn(den, s_lut[min((int)c[0] - mc, 127)]);
-    } else {
-      const float* e = s_par + (warp - 1) * PS + lane;
-#pragma unroll 8
-      for (int d = 0; d < D; ++d, e += 32) den = __fadd_rn(den, e[0]);
+    // ---- phase 3: denominators in the reference's order (sequential fp32 over d) ------
+    // One thread per (pixel, matcher); the loads run one group of 8 ahead of the dependent
+    // add chain (values past D are +0.0f, which is exact to add).
+    if (warp < 4) {
+      const float mm = s_min[warp * 32 + lane];
+      float den = 0.f;
+      float nxt[8];
+      if (warp == 0) {
+        const int mc = (mm == kFill) ? 0 : (int)mm;
+        const uint8_t* c = s_cen + lane;
+        int idx[8];
+#pragma unroll
+        for (int j = 0; j < 8; ++j) idx[j] = (j < D) ? min((int)c[j * 32] - mc, 127) : 127;
+#pragma unroll
+        for (int j = 0; j < 8; ++j) nxt[j] = s_lut[idx[j]];
+        for (int d0 = 0; d0 < D; d0 += 8) {
+          float cur[8];
+#pragma unroll
+          for (int j = 0; j < 8; ++j) cur[j] = nxt[j];
+          c += 8 * 32;
+#pragma unroll
+          for (int j = 0; j < 8; ++j) idx[j] = (d0 + 8 + j < D) ? min((int)c[j * 32] - mc, 127) : 127;
+#pragma unroll
+          for (int j = 0; j < 8; ++j) nxt[j] = s_lut[idx[j]];
+#pragma unroll
+          for (int j = 0; j < 8; ++j) den = __fadd_rn(den, cur[j]);
+        }
+      } else {
+        const float* e = s_par + (warp - 1) * PS + lane;
+#pragma unroll
+        for (int j = 0; j < 8; ++j) nxt[j] = (j < D) ? e[j * 32] : 0.f;
+        for (int d0 = 0; d0 < D; d0 += 8) {
+          float cur[8];
+#pragma unroll
+          for (int j = 0; j < 8; ++j) cur[j] = nxt[j];
+          e += 8 * 32;
+#pragma unroll
+          for (int j = 0; j < 8; ++j) nxt[j] = (d0 + 8 + j < D) ? e[j * 32] : 0.f;
+#pragma unroll
+          for (int j = 0; j < 8; ++j) den = __fadd_rn(den, cur[j]);
+        }
+      }
+      s_inv[warp * 32 + lane] = (mm == kFill) ? 0.f : 1.0f / den;
     }
-    const float mm = (warp == 0) ? m[0] : (warp == 1) ? m[1] : (warp == 2) ? m[2] : m[3];
-    s_inv[warp * 32 + lane] = (mm == kFill) ? 0.f : 1.0f / den;
-  }
-  __syncthreads();
+    __syncthreads();
 
-  // ---- phase 4: channels 4-7 = e / den ------------------------------------
-  if (live) {
-    const float i0 = s_inv[lane], i1 = s_inv[32 + lane], i2 = s_inv[64 + lane], i3 = s_inv[96 + lane];
-    const float* e = s_par + d_lo * 32 + lane;
-    const uint8_t* c = s_cen + d_lo * 32 + lane;
-    float* p0 = a.out + (size_t)n * 8 * chan + 4 * chan + (size_t)y * g.w + (x0 + lane) + (size_t)d_lo * plane;
-    float* p1 = p0 + chan;
-    float* p2 = p1 + chan;
-    float* p3 = p2 + chan;
-#pragma unroll 4
-    for (int d = d_lo; d < d_end; ++d, e += 32, c += 32) {
-      st_stream(p0, s_lut[min((int)c[0] - mc, 127)] * i0);
-      st_stream(p1, e[0] * i1);
-      st_stream(p2, e[PS] * i2);
-      st_stream(p3, e[2 * PS] * i3);
-      p0 += plane; p1 += plane; p2 += plane; p3 += plane;
+    // ---- phase 4: channels 4-7 = e / den, 128-bit rows ---------------------------------
+    {
+      const float4 i0 = *reinterpret_cast<const float4*>(s_inv + q4);
+      const float4 i1 = *reinterpret_cast<const float4*>(s_inv + 32 + q4);
+      const float4 i2 = *reinterpret_cast<const float4*>(s_inv + 64 + q4);
+      const float4 i3 = *reinterpret_cast<const float4*>(s_inv + 96 + q4);
+      const int mcx = (m_cen4.x == kFill) ? 0 : (int)m_cen4.x, mcy = (m_cen4.y == kFill) ? 0 : (int)m_cen4.y;
+      const int mcz = (m_cen4.z == kFill) ? 0 : (int)m_cen4.z, mcw = (m_cen4.w == kFill) ? 0 : (int)m_cen4.w;
+      float* arow = orow + 4 * chan;
+      for (int d = dl; d < D; d += 32) {
+        const float* e0 = s_par + d * 32 + q4;
+        const uchar4 cb = *reinterpret_cast<const uchar4*>(s_cen + d * 32 + q4);
+        float4 a0;
+        a0.x = s_lut[min((int)cb.x - mcx, 127)] * i0.x;
+        a0.y = s_lut[min((int)cb.y - mcy, 127)] * i0.y;
+        a0.z = s_lut[min((int)cb.z - mcz, 127)] * i0.z;
+        a0.w = s_lut[min((int)cb.w - mcw, 127)] * i0.w;
+        const float4 v1 = *reinterpret_cast<const float4*>(e0);
+        const float4 v2 = *reinterpret_cast<const float4*>(e0 + PS);
+        const float4 v3 = *reinterpret_cast<const float4*>(e0 + 2 * PS);
+        const float4 a1 = make_float4(v1.x * i1.x, v1.y * i1.y, v1.z * i1.z, v1.w * i1.w);
+        const float4 a2 = make_float4(v2.x * i2.x, v2.y * i2.y, v2.z * i2.z, v2.w * i2.w);
+        const float4 a3 = make_float4(v3.x * i3.x, v3.y * i3.y, v3.z * i3.z, v3.w * i3.w);
+        float* o = arow + (size_t)d * plane;
+        if (vec_ok && nlive == 4) {
+          st_stream4(o, a0);
+          st_stream4(o + chan, a1);
+          st_stream4(o + 2 * chan, a2);
+          st_stream4(o + 3 * chan, a3);
+        } else {
+          const float cc[4][4] = {{a0.x, a0.y, a0.z, a0.w}, {a1.x, a1.y, a1.z, a1.w}, {a2.x, a2.y, a2.z, a2.w},
+                                  {a3.x, a3.y, a3.z, a3.w}};
+#pragma unroll
+          for (int ch = 0; ch < 4; ++ch)
+#pragma unroll
+            for (int i = 0; i < 4; ++i)
+              if (i < nlive) st_stream(o + ch * chan + i, cc[ch][i]);
+        }
+      }
     }
   }
 }
@@ -548,6 +683,7 @@ int launch_ms_fused(const uint8_t* d_left, const uint8_t* d_right, int N, int H,
   a.tiles_x = (g.w + kTile - 1) / kTile;
   const long long tiles = (long long)N * g.h * a.tiles_x;
   MSN_REQUIRE(tiles <= 2147483647LL, "ms_features: too many tiles for one launch");
+  a.num_tiles = (int)tiles;
 #define MSN_FUSED_CASE(DMAX)                                                                          \
   if (g.D <= DMAX) {                                                                                  \
     const size_t smem = Lay<DMAX>::bytes;                                                             \
