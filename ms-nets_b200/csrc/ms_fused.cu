@@ -21,12 +21,12 @@
 //                 ordered fp32 adds over a register-resident 5x5 window that slides
 //                 with d); raw costs are parked in shared memory (13 B/voxel: three
 //                 floats + census byte); per-pixel minima.
-//        phase 2  thread = (pixel quad, d): channels 0-3 normalised and stored as
-//                 128-bit row segments; exponentials exp(-(c-m)^2/sigma) written over
-//                 the parked costs.
-//        phase 3  one thread per (pixel, matcher) adds the denominator in d order
-//                 (the reference's sequential fp32 sum, featextract.cpp:444-447).
-//        phase 4  channels 4-7 = e / den, 128-bit row segments.
+//        phase 2  warp-specialised, both halves only READ the parked costs:
+//                 warps 0-3: one thread per (pixel, matcher) adds the AML denominator in
+//                 d order (the reference's sequential fp32 sum, featextract.cpp:444-447);
+//                 warps 4-7: thread = (pixel quad, d): channels 0-3 normalised and stored
+//                 as 128-bit row segments.
+//        phase 3  channels 4-7 = exp(-(c-m)^2/sigma) / den, 128-bit row segments.
 //
 // Bounding resource: HBM writes (32 B per voxel) co-limited by issue slots -- ZSAD
 // alone is 75 dependent-order FADDs per voxel (DESIGN.md has the arithmetic).
@@ -452,106 +452,85 @@ __global__ void __launch_bounds__(kWarps * 32, 2) ms_fused_kernel(const FusedArg
     }
     __syncthreads();
 
-    // ---- phase 2: channels 0-3 (cbmv_generator.py:283-287) out as 128-bit rows, and the
-    //      exponentials exp(-(c-m)^2/sigma) written over the parked float costs ----------
-    const float4 m_cen4 = *reinterpret_cast<const float4*>(s_min + q4);
-    const float4 m_ncc4 = *reinterpret_cast<const float4*>(s_min + 32 + q4);
-    const float4 m_sob4 = *reinterpret_cast<const float4*>(s_min + 64 + q4);
-    const float4 m_sad4 = *reinterpret_cast<const float4*>(s_min + 96 + q4);
+    // ---- phase 2 (warp-specialised, the two halves run concurrently and never write the
+    //      parking planes, so there is no hazard between them):
+    //      warps 0-3  one thread per (pixel, matcher): AML denominator, exponentials
+    //                 evaluated on the fly and added in the reference's order -- sequential
+    //                 fp32 over d (featextract.cpp:444-447);
+    //      warps 4-7  thread = (pixel quad, d): channels 0-3 (cbmv_generator.py:283-287)
+    //                 normalised and stored as 128-bit row segments. -----------------------
     float* orow = a.out + (size_t)t.n * 8 * chan + (size_t)t.y * g.w + (t.x0 + q4);
     const int nlive = min(4, g.w - (t.x0 + q4));  // live pixels of this quad (<= 0: none)
-    for (int d = dl; d < D; d += 32) {
-      float* e0 = s_par + d * 32 + q4;
-      const uchar4 cb = *reinterpret_cast<const uchar4*>(s_cen + d * 32 + q4);
-      float4 c0;
-      c0.x = (cb.x == 255) ? 1.0f : div120_exact(int_to_float_small(cb.x));
-      c0.y = (cb.y == 255) ? 1.0f : div120_exact(int_to_float_small(cb.y));
-      c0.z = (cb.z == 255) ? 1.0f : div120_exact(int_to_float_small(cb.z));
-      c0.w = (cb.w == 255) ? 1.0f : div120_exact(int_to_float_small(cb.w));
-      float4 v1 = *reinterpret_cast<float4*>(e0);
-      float4 v2 = *reinterpret_cast<float4*>(e0 + PS);
-      float4 v3 = *reinterpret_cast<float4*>(e0 + 2 * PS);
-      float4 c1 = make_float4(normalise_cost(v1.x, 1), normalise_cost(v1.y, 1), normalise_cost(v1.z, 1),
-                              normalise_cost(v1.w, 1));
-      float4 c2 = make_float4(normalise_cost(v2.x, 2), normalise_cost(v2.y, 2), normalise_cost(v2.z, 2),
-                              normalise_cost(v2.w, 2));
-      float4 c3 = make_float4(normalise_cost(v3.x, 3), normalise_cost(v3.y, 3), normalise_cost(v3.z, 3),
-                              normalise_cost(v3.w, 3));
-      float* o = orow + (size_t)d * plane;
-      if (vec_ok && nlive == 4) {
-        st_stream4(o, c0);
-        st_stream4(o + chan, c1);
-        st_stream4(o + 2 * chan, c2);
-        st_stream4(o + 3 * chan, c3);
-      } else {
-        const float cc[4][4] = {{c0.x, c0.y, c0.z, c0.w}, {c1.x, c1.y, c1.z, c1.w}, {c2.x, c2.y, c2.z, c2.w},
-                                {c3.x, c3.y, c3.z, c3.w}};
-#pragma unroll
-        for (int ch = 0; ch < 4; ++ch)
-#pragma unroll
-          for (int i = 0; i < 4; ++i)
-            if (i < nlive) st_stream(o + ch * chan + i, cc[ch][i]);
-      }
-      v1 = make_float4(aml_e(v1.x, m_ncc4.x, a.k_ncc), aml_e(v1.y, m_ncc4.y, a.k_ncc),
-                       aml_e(v1.z, m_ncc4.z, a.k_ncc), aml_e(v1.w, m_ncc4.w, a.k_ncc));
-      v2 = make_float4(aml_e(v2.x, m_sob4.x, a.k_sad), aml_e(v2.y, m_sob4.y, a.k_sad),
-                       aml_e(v2.z, m_sob4.z, a.k_sad), aml_e(v2.w, m_sob4.w, a.k_sad));
-      v3 = make_float4(aml_e(v3.x, m_sad4.x, a.k_sad), aml_e(v3.y, m_sad4.y, a.k_sad),
-                       aml_e(v3.z, m_sad4.z, a.k_sad), aml_e(v3.w, m_sad4.w, a.k_sad));
-      *reinterpret_cast<float4*>(e0) = v1;
-      *reinterpret_cast<float4*>(e0 + PS) = v2;
-      *reinterpret_cast<float4*>(e0 + 2 * PS) = v3;
-    }
-    __syncthreads();
-
-    // ---- phase 3: denominators in the reference's order (sequential fp32 over d) ------
-    // One thread per (pixel, matcher); the loads run one group of 8 ahead of the dependent
-    // add chain (values past D are +0.0f, which is exact to add).
     if (warp < 4) {
       const float mm = s_min[warp * 32 + lane];
       float den = 0.f;
-      float nxt[8];
       if (warp == 0) {
         const int mc = (mm == kFill) ? 0 : (int)mm;
         const uint8_t* c = s_cen + lane;
-        int idx[8];
-#pragma unroll
-        for (int j = 0; j < 8; ++j) idx[j] = (j < D) ? min((int)c[j * 32] - mc, 127) : 127;
-#pragma unroll
-        for (int j = 0; j < 8; ++j) nxt[j] = s_lut[idx[j]];
         for (int d0 = 0; d0 < D; d0 += 8) {
-          float cur[8];
+          float ev[8];
 #pragma unroll
-          for (int j = 0; j < 8; ++j) cur[j] = nxt[j];
+          for (int j = 0; j < 8; ++j) ev[j] = (d0 + j < D) ? s_lut[min((int)c[j * 32] - mc, 127)] : 0.f;
+#pragma unroll
+          for (int j = 0; j < 8; ++j) den = __fadd_rn(den, ev[j]);  // + 0.0f past D is exact
           c += 8 * 32;
-#pragma unroll
-          for (int j = 0; j < 8; ++j) idx[j] = (d0 + 8 + j < D) ? min((int)c[j * 32] - mc, 127) : 127;
-#pragma unroll
-          for (int j = 0; j < 8; ++j) nxt[j] = s_lut[idx[j]];
-#pragma unroll
-          for (int j = 0; j < 8; ++j) den = __fadd_rn(den, cur[j]);
         }
       } else {
+        const float kq = (warp == 1) ? a.k_ncc : a.k_sad;
         const float* e = s_par + (warp - 1) * PS + lane;
-#pragma unroll
-        for (int j = 0; j < 8; ++j) nxt[j] = (j < D) ? e[j * 32] : 0.f;
         for (int d0 = 0; d0 < D; d0 += 8) {
-          float cur[8];
+          float ev[8];
 #pragma unroll
-          for (int j = 0; j < 8; ++j) cur[j] = nxt[j];
+          for (int j = 0; j < 8; ++j) ev[j] = (d0 + j < D) ? aml_e(e[j * 32], mm, kq) : 0.f;
+#pragma unroll
+          for (int j = 0; j < 8; ++j) den = __fadd_rn(den, ev[j]);
           e += 8 * 32;
-#pragma unroll
-          for (int j = 0; j < 8; ++j) nxt[j] = (d0 + 8 + j < D) ? e[j * 32] : 0.f;
-#pragma unroll
-          for (int j = 0; j < 8; ++j) den = __fadd_rn(den, cur[j]);
         }
       }
       s_inv[warp * 32 + lane] = (mm == kFill) ? 0.f : 1.0f / den;
+    } else {
+      for (int d = dl - 16; d < D; d += 16) {   // dl in [16,32) for warps 4-7
+        const float* e0 = s_par + d * 32 + q4;
+        const uchar4 cb = *reinterpret_cast<const uchar4*>(s_cen + d * 32 + q4);
+        float4 c0;
+        c0.x = (cb.x == 255) ? 1.0f : div120_exact(int_to_float_small(cb.x));
+        c0.y = (cb.y == 255) ? 1.0f : div120_exact(int_to_float_small(cb.y));
+        c0.z = (cb.z == 255) ? 1.0f : div120_exact(int_to_float_small(cb.z));
+        c0.w = (cb.w == 255) ? 1.0f : div120_exact(int_to_float_small(cb.w));
+        const float4 v1 = *reinterpret_cast<const float4*>(e0);
+        const float4 v2 = *reinterpret_cast<const float4*>(e0 + PS);
+        const float4 v3 = *reinterpret_cast<const float4*>(e0 + 2 * PS);
+        const float4 c1 = make_float4(normalise_cost(v1.x, 1), normalise_cost(v1.y, 1), normalise_cost(v1.z, 1),
+                                      normalise_cost(v1.w, 1));
+        const float4 c2 = make_float4(normalise_cost(v2.x, 2), normalise_cost(v2.y, 2), normalise_cost(v2.z, 2),
+                                      normalise_cost(v2.w, 2));
+        const float4 c3 = make_float4(normalise_cost(v3.x, 3), normalise_cost(v3.y, 3), normalise_cost(v3.z, 3),
+                                      normalise_cost(v3.w, 3));
+        float* o = orow + (size_t)d * plane;
+        if (vec_ok && nlive == 4) {
+          st_stream4(o, c0);
+          st_stream4(o + chan, c1);
+          st_stream4(o + 2 * chan, c2);
+          st_stream4(o + 3 * chan, c3);
+        } else {
+          const float cc[4][4] = {{c0.x, c0.y, c0.z, c0.w}, {c1.x, c1.y, c1.z, c1.w}, {c2.x, c2.y, c2.z, c2.w},
+                                  {c3.x, c3.y, c3.z, c3.w}};
+#pragma unroll
+          for (int ch = 0; ch < 4; ++ch)
+#pragma unroll
+            for (int i = 0; i < 4; ++i)
+              if (i < nlive) st_stream(o + ch * chan + i, cc[ch][i]);
+        }
+      }
     }
     __syncthreads();
 
-    // ---- phase 4: channels 4-7 = e / den, 128-bit rows ---------------------------------
+    // ---- phase 3: channels 4-7 = exp(-(c-m)^2/sigma) / den, 128-bit row segments --------
     {
+      const float4 m_cen4 = *reinterpret_cast<const float4*>(s_min + q4);
+      const float4 m_ncc4 = *reinterpret_cast<const float4*>(s_min + 32 + q4);
+      const float4 m_sob4 = *reinterpret_cast<const float4*>(s_min + 64 + q4);
+      const float4 m_sad4 = *reinterpret_cast<const float4*>(s_min + 96 + q4);
       const float4 i0 = *reinterpret_cast<const float4*>(s_inv + q4);
       const float4 i1 = *reinterpret_cast<const float4*>(s_inv + 32 + q4);
       const float4 i2 = *reinterpret_cast<const float4*>(s_inv + 64 + q4);
@@ -570,9 +549,12 @@ __global__ void __launch_bounds__(kWarps * 32, 2) ms_fused_kernel(const FusedArg
         const float4 v1 = *reinterpret_cast<const float4*>(e0);
         const float4 v2 = *reinterpret_cast<const float4*>(e0 + PS);
         const float4 v3 = *reinterpret_cast<const float4*>(e0 + 2 * PS);
-        const float4 a1 = make_float4(v1.x * i1.x, v1.y * i1.y, v1.z * i1.z, v1.w * i1.w);
-        const float4 a2 = make_float4(v2.x * i2.x, v2.y * i2.y, v2.z * i2.z, v2.w * i2.w);
-        const float4 a3 = make_float4(v3.x * i3.x, v3.y * i3.y, v3.z * i3.z, v3.w * i3.w);
+        const float4 a1 = make_float4(aml_e(v1.x, m_ncc4.x, a.k_ncc) * i1.x, aml_e(v1.y, m_ncc4.y, a.k_ncc) * i1.y,
+                                      aml_e(v1.z, m_ncc4.z, a.k_ncc) * i1.z, aml_e(v1.w, m_ncc4.w, a.k_ncc) * i1.w);
+        const float4 a2 = make_float4(aml_e(v2.x, m_sob4.x, a.k_sad) * i2.x, aml_e(v2.y, m_sob4.y, a.k_sad) * i2.y,
+                                      aml_e(v2.z, m_sob4.z, a.k_sad) * i2.z, aml_e(v2.w, m_sob4.w, a.k_sad) * i2.w);
+        const float4 a3 = make_float4(aml_e(v3.x, m_sad4.x, a.k_sad) * i3.x, aml_e(v3.y, m_sad4.y, a.k_sad) * i3.y,
+                                      aml_e(v3.z, m_sad4.z, a.k_sad) * i3.z, aml_e(v3.w, m_sad4.w, a.k_sad) * i3.w);
         float* o = arow + (size_t)d * plane;
         if (vec_ok && nlive == 4) {
           st_stream4(o, a0);
