@@ -83,7 +83,8 @@ size_t sadsob_workspace_bytes_n(int N, int H, int W, int Dn, int wsize);
 int launch_sadsob(const float* L, const float* R, int H, int W, int D, int d_begin, int wsize, float* out,
                   bool write_fill, void* workspace, cudaStream_t s);
 int launch_sadsob_n(const float* L, const float* R, int N, int H, int W, int Dn, int d_begin, int wsize,
-                    float* out, size_t out_stride, bool write_fill, void* workspace, cudaStream_t s);
+                    float* out, size_t out_stride, int out_pitch, bool write_fill, void* workspace,
+                    cudaStream_t s);
 // fte.cu
 int launch_transpose2d(const float* in, long long A, long long B, float* out, cudaStream_t s);
 int launch_reindex_cost(const float* c, int H, int W, int D, bool right, float* out, cudaStream_t s);

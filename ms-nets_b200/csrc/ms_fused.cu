@@ -32,6 +32,7 @@
 // alone is 75 dependent-order FADDs per voxel (DESIGN.md has the arithmetic).
 #include "ms_fused.cuh"
 
+#include <cuda.h>
 #include <stdlib.h>
 
 #include <mutex>
@@ -59,6 +60,7 @@ struct __align__(16) RStat {
 struct FusedGeom {
   int N, H, W, h, w, D, bh, bwl;
   int Hp, Wp, padL;
+  int sxo, Ws;   // SAD-of-Sobel scratch: column offset and row pitch (tile starts land on 16 B)
   __host__ __device__ size_t img_px() const { return (size_t)Hp * Wp; }
 };
 
@@ -71,6 +73,8 @@ FusedGeom make_geom(int N, int H, int W, const msn_ms_params* p) {
   g.padL = (g.D + 1 + 40 + 8 + 7) & ~7;  // D-1 columns of disparity + dummy-step slack (kSlack) + halo/alignment
   g.Hp = H + 2 * kPadT;
   g.Wp = (W + g.padL + kPadR + 3) & ~3;
+  g.sxo = (4 - (g.bwl & 3)) & 3;            // x0 + bwl + sxo is a multiple of 4 for every tile
+  g.Ws = (W + g.sxo + kTile + 3) & ~3;      // room for the last tile's overhang
   return g;
 }
 
@@ -90,7 +94,7 @@ struct FusedWs {
     for (int i = 0; i < 2; ++i) stat[i] = (RStat*)take(np * sizeof(RStat));
     for (int i = 0; i < 2; ++i) fimg[i] = (float*)take(np * sizeof(float));
     for (int i = 0; i < 2; ++i) sob[i] = (float*)take(n * sizeof(float));
-    sadsob = (float*)take(n * g.D * sizeof(float) + 256);  // + slack: dead lanes read past a row end
+    sadsob = (float*)take((size_t)g.N * g.D * g.H * g.Ws * sizeof(float) + 256);
     sad_ws = take(sadsob_workspace_bytes_n(g.N, g.H, g.W, g.D, kSadW));
     total = off;
   }
@@ -207,9 +211,10 @@ struct Lay {
   static constexpr size_t off_min = off_red + (size_t)kWarps * 4 * 32 * 4;   // [4][32]
   static constexpr size_t off_inv = off_min + 4 * 32 * 4;                    // [4][32]
   static constexpr size_t off_lut = off_inv + 4 * 32 * 4;                    // [128]
-  static constexpr size_t off_par = off_lut + 128 * 4;                       // [3][DS][32] ncc, sadsob, zsad
+  static constexpr size_t off_par = (off_lut + 128 * 4 + 127) & ~(size_t)127;  // [3][DS][32] ncc, sadsob, zsad (128 B aligned: TMA destination)
   static constexpr size_t off_cen = off_par + (size_t)3 * DS * 32 * 4;       // [DS][32] bytes
-  static constexpr size_t bytes = off_cen + (size_t)DS * 32;
+  static constexpr size_t off_bar = (off_cen + (size_t)DS * 32 + 15) & ~(size_t)15;  // mbarrier (8 B)
+  static constexpr size_t bytes = off_bar + 16;
 };
 
 __device__ __forceinline__ float int_to_float_small(int c) {  // exact for 0 <= c < 2^23
@@ -231,6 +236,39 @@ __device__ __forceinline__ void cp_async16(void* smem_dst, const void* gmem_src)
   const uint32_t d = (uint32_t)__cvta_generic_to_shared(smem_dst);
   asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(d), "l"(gmem_src) : "memory");
 }
+// ---- TMA / bulk-copy helpers (cp.async.bulk*, completion through an mbarrier) ----------
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(unsigned long long* bar, unsigned count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+  asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(unsigned long long* bar, unsigned bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(unsigned long long* bar, unsigned parity) {
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      "MSN_WAIT_%=:\n"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+      "@p bra MSN_DONE_%=;\n"
+      "bra MSN_WAIT_%=;\n"
+      "MSN_DONE_%=:\n"
+      "}\n" ::"r"(smem_u32(bar)), "r"(parity) : "memory");
+}
+// 1-D bulk copy global -> shared (bytes multiple of 16, both sides 16 B aligned)
+__device__ __forceinline__ void bulk_load(void* dst, const void* src, unsigned bytes, unsigned long long* bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+                   smem_u32(dst)), "l"(src), "r"(bytes), "r"(smem_u32(bar)) : "memory");
+}
+// 3-D tiled tensor copy global -> shared through a CUtensorMap (out-of-range elements read as 0)
+__device__ __forceinline__ void tma_load_3d(void* dst, const CUtensorMap* map, int c0, int c1, int c2,
+                                            unsigned long long* bar) {
+  asm volatile(
+      "cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3, %4}], [%5];" ::"r"(
+          smem_u32(dst)), "l"(reinterpret_cast<uint64_t>(map)), "r"(c0), "r"(c1), "r"(c2), "r"(smem_u32(bar)) : "memory");
+}
+
 __device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_all;" ::: "memory"); }
 
 struct TileId {
@@ -276,6 +314,32 @@ __device__ __forceinline__ void stage_right(const FusedArgs& a, const TileId& t,
   }
 }
 
+// Same data through the TMA engine: seven 1-D bulk copies plus ONE 3-D tensor copy that
+// drops the tile's D x 32 SAD-of-Sobel costs straight into parking plane 1; issued by a
+// single thread, completion counted in bytes on `bar`.
+template <int DMAX>
+__device__ __forceinline__ void stage_tma(const FusedArgs& a, const CUtensorMap* sad_map, const TileId& t,
+                                          unsigned char* buf, float* park_plane1, unsigned long long* bar) {
+  using L = Lay<DMAX>;
+  const FusedGeom& g = a.g;
+  const int D = g.D;
+  const int RWn = D + kTile - 1 + kSlack;
+  const int XbaseP = t.x0 + g.bwl - (D - 1) - kSlack + g.padL;
+  const int Yp = t.y + g.bh + kPadT;
+  const size_t img_off = (size_t)t.n * g.img_px();
+  const int fstart = (XbaseP - 2) & ~3;
+  const int nvec = (RWn + 4 + 3 + 3) >> 2;
+  const unsigned row_bytes = (unsigned)RWn * 16u, frow_bytes = (unsigned)nvec * 16u;
+  mbar_expect_tx(bar, 2u * row_bytes + 5u * frow_bytes + (unsigned)D * kTile * 4u);
+  tma_load_3d(park_plane1, sad_map, t.x0 + g.bwl + g.sxo, t.y + g.bh, t.n * D, bar);  // inner coordinate % 4 == 0
+  bulk_load(buf + L::st_desc, a.descR + img_off + (size_t)Yp * g.Wp + XbaseP, row_bytes, bar);
+  bulk_load(buf + L::st_stat, a.statR + img_off + (size_t)Yp * g.Wp + XbaseP, row_bytes, bar);
+  float* s_rf = reinterpret_cast<float*>(buf + L::st_rf);
+#pragma unroll
+  for (int r = 0; r < 5; ++r)
+    bulk_load(s_rf + r * L::RWF, a.fR + img_off + (size_t)(Yp - 2 + r) * g.Wp + fstart, frow_bytes, bar);
+}
+
 // The lane's own left-image data: census code, stats, 5x5 float window.
 struct LeftRegs {
   uint4 desc;
@@ -300,12 +364,18 @@ __device__ __forceinline__ void load_left(const FusedArgs& a, const TileId& t, i
 // One CTA per tile.  (A persistent variant with double-buffered staging and left-image
 // register prefetch was measured 13 % SLOWER on B200: resident CTAs fall into lockstep and
 // the hardware CTA scheduler balances the cheaper border tiles better; see DESIGN.md.)
-template <int DMAX>
-__global__ void __launch_bounds__(kWarps * 32, 2) ms_fused_kernel(const FusedArgs a) {
+// kTma: right-image rows and the SAD-of-Sobel tile arrive through cp.async.bulk /
+// cp.async.bulk.tensor (D <= 256: box limit); otherwise through LDGSTS.  The tensor copy's
+// inner coordinate must be a multiple of 16 bytes (measured: anything else raises an
+// illegal-instruction fault), which is why the scratch is stored with column offset sxo.
+template <int DMAX, bool kTma>
+__global__ void __launch_bounds__(kWarps * 32, 2)
+ms_fused_kernel(const FusedArgs a, const __grid_constant__ CUtensorMap sad_map) {
   using L = Lay<DMAX>;
-  extern __shared__ __align__(16) unsigned char smem_raw[];
+  extern __shared__ __align__(128) unsigned char smem_raw[];  // TMA destinations need 128 B
   const FusedGeom& g = a.g;
   const int D = g.D;
+  unsigned long long& s_bar = *reinterpret_cast<unsigned long long*>(smem_raw + L::off_bar);
   float* s_red = reinterpret_cast<float*>(smem_raw + L::off_red);    // [8][4][32]
   float* s_min = reinterpret_cast<float*>(smem_raw + L::off_min);    // [4][32]
   float* s_inv = reinterpret_cast<float*>(smem_raw + L::off_inv);    // [4][32]
@@ -320,7 +390,7 @@ __global__ void __launch_bounds__(kWarps * 32, 2) ms_fused_kernel(const FusedArg
   const int d_end = min(D, d_lo + a.DC);  // real disparities of this warp: [d_lo, d_end)
   const size_t plane = (size_t)g.h * g.w;
   const size_t chan = plane * D;
-  const size_t splane = (size_t)H * W;
+  const size_t splane = (size_t)H * g.Ws;
   // 128-bit stores need 16-byte aligned rows
   const bool vec_ok = ((g.w & 3) == 0) && ((reinterpret_cast<uintptr_t>(a.out) & 15) == 0);
   // AML-phase mapping: thread = (pixel quad q, disparity lane dl); d = dl, dl+32, ...
@@ -333,13 +403,17 @@ __global__ void __launch_bounds__(kWarps * 32, 2) ms_fused_kernel(const FusedArg
     const int X = t.x0 + lane + g.bwl;      // bordered image column of this lane
     const int Y = t.y + g.bh;               // bordered image row
 
-    // sadsob costs of this lane's own disparities: async global -> parked plane 1
-    {
-      const float* src = a.sadsob + ((size_t)t.n * D * H + Y) * W + X + (size_t)d_lo * splane;
+    if (kTma) {
+      if (threadIdx.x == 0) mbar_init(&s_bar, 1);
+      __syncthreads();
+      if (threadIdx.x == 0) stage_tma<DMAX>(a, &sad_map, t, buf, s_par + PS, &s_bar);
+    } else {
+      // sadsob costs of this lane's own disparities: async global -> parked plane 1
+      const float* src = a.sadsob + ((size_t)t.n * D * H + Y) * g.Ws + (X + g.sxo) + (size_t)d_lo * splane;
       float* dst = s_par + PS + d_lo * 32 + lane;
       for (int d = d_lo; d < d_end; ++d, src += splane, dst += 32) cp_async4(dst, src);
+      stage_right<DMAX>(a, t, buf);
     }
-    stage_right<DMAX>(a, t, buf);
     if (threadIdx.x < 128) {
       const int kk = threadIdx.x;
       s_lut[kk] = (kk <= 120) ? ex2_approx(-(float)(kk * kk) * a.k_cen) : 0.f;
@@ -362,7 +436,8 @@ __global__ void __launch_bounds__(kWarps * 32, 2) ms_fused_kernel(const FusedArg
     const int dmax_ncc = min(D - 1, (Y >= 1 && Y < H - 2 && X >= 1 && X < W - 2) ? X - 1 : -1);
     const int dmax_sad = min(D - 1, (Y >= 2 && Y < H - 3 && X >= 2 && X < W - 3) ? X - 2 : -1);
 
-    cp_async_wait_all();
+    if (kTma) mbar_wait(&s_bar, 0);
+    else cp_async_wait_all();
     __syncthreads();
     // ---- phase 1: raw costs into the parking planes, per-pixel minima ----------------
     {
@@ -584,6 +659,26 @@ std::vector<ProfRec> g_prof;
 
 }  // namespace
 
+typedef CUresult (*PFN_encodeTiled)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                    const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                    CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+// cuTensorMapEncodeTiled through the runtime's driver entry-point lookup (no libcuda link)
+static PFN_encodeTiled get_encode_fn() {
+  static PFN_encodeTiled fn = [] {
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) != cudaSuccess ||
+        q != cudaDriverEntryPointSuccess)
+      p = nullptr;
+    return (PFN_encodeTiled)p;
+  }();
+  return fn;
+}
+static bool tma_disabled() {
+  const char* e = getenv("MSNETS_NO_TMA");
+  return e && e[0] == '1';
+}
+
 int profile_enable(int on) {
   std::lock_guard<std::mutex> lk(g_prof_mu);
   g_prof_on = on != 0;
@@ -646,8 +741,8 @@ int launch_ms_fused(const uint8_t* d_left, const uint8_t* d_right, int N, int H,
                                        ws.fimg[0], ws.fimg[1], ws.sob[0], ws.sob[1]);
   MSN_LAUNCH_OK();
   if (prof) MSN_CUDA_OK(cudaEventRecord(rec.ev[1], s));
-  if (launch_sadsob_n(ws.sob[0], ws.sob[1], N, H, W, g.D, 0, kSadW, ws.sadsob, (size_t)g.D * H * W, false,
-                      ws.sad_ws, s))
+  if (launch_sadsob_n(ws.sob[0], ws.sob[1], N, H, W, g.D, 0, kSadW, ws.sadsob + g.sxo, (size_t)g.D * H * g.Ws, g.Ws,
+                      false, ws.sad_ws, s))
     return 1;
   if (prof) MSN_CUDA_OK(cudaEventRecord(rec.ev[2], s));
 
@@ -666,12 +761,36 @@ int launch_ms_fused(const uint8_t* d_left, const uint8_t* d_right, int N, int H,
   const long long tiles = (long long)N * g.h * a.tiles_x;
   MSN_REQUIRE(tiles <= 2147483647LL, "ms_features: too many tiles for one launch");
   a.num_tiles = (int)tiles;
+  // TMA path: 3-D tensor map over the SAD-of-Sobel scratch [N*D][H][W], box 32 x 1 x D
+  CUtensorMap sad_map;
+  memset(&sad_map, 0, sizeof(sad_map));
+  bool use_tma = g.D <= 256 && !tma_disabled();
+  if (use_tma) {
+    PFN_encodeTiled enc = get_encode_fn();
+    if (!enc) {
+      use_tma = false;
+    } else {
+      const cuuint64_t gdim[3] = {(cuuint64_t)g.Ws, (cuuint64_t)H, (cuuint64_t)N * g.D};
+      const cuuint64_t gstr[2] = {(cuuint64_t)g.Ws * 4, (cuuint64_t)H * g.Ws * 4};
+      const cuuint32_t box[3] = {(cuuint32_t)kTile, 1u, (cuuint32_t)g.D};
+      const cuuint32_t estr[3] = {1u, 1u, 1u};
+      const CUresult rc = enc(&sad_map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3, ws.sadsob, gdim, gstr, box, estr,
+                              CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE,
+                              CU_TENSOR_MAP_L2_PROMOTION_NONE, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+      if (rc != CUDA_SUCCESS) use_tma = false;
+    }
+  }
+#define MSN_FUSED_LAUNCH(DMAX, TMA)                                                                   \
+  {                                                                                                   \
+    const size_t smem = Lay<DMAX>::bytes;                                                             \
+    MSN_CUDA_OK(cudaFuncSetAttribute(ms_fused_kernel<DMAX, TMA>,                                      \
+                                     cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));        \
+    ms_fused_kernel<DMAX, TMA><<<(unsigned)tiles, kWarps * 32, smem, s>>>(a, sad_map);                \
+  }
 #define MSN_FUSED_CASE(DMAX)                                                                          \
   if (g.D <= DMAX) {                                                                                  \
-    const size_t smem = Lay<DMAX>::bytes;                                                             \
-    MSN_CUDA_OK(cudaFuncSetAttribute(ms_fused_kernel<DMAX>, cudaFuncAttributeMaxDynamicSharedMemorySize, \
-                                     (int)smem));                                                     \
-    ms_fused_kernel<DMAX><<<(unsigned)tiles, kWarps * 32, smem, s>>>(a);                              \
+    if (use_tma && DMAX <= 256) MSN_FUSED_LAUNCH(DMAX <= 256 ? DMAX : 256, true)                      \
+    else MSN_FUSED_LAUNCH(DMAX, false)                                                                \
   } else
   MSN_FUSED_CASE(64)
   MSN_FUSED_CASE(128)
@@ -680,6 +799,7 @@ int launch_ms_fused(const uint8_t* d_left, const uint8_t* d_right, int N, int H,
   MSN_FUSED_CASE(384)
   MSN_FUSED_CASE(448) { return fail("ms_features: D=%d exceeds the fused kernel's limit", g.D); }
 #undef MSN_FUSED_CASE
+#undef MSN_FUSED_LAUNCH
   MSN_LAUNCH_OK();
   if (prof) {
     MSN_CUDA_OK(cudaEventRecord(rec.ev[3], s));

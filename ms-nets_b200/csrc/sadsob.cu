@@ -76,7 +76,7 @@ template <int WS>
 __global__ void __launch_bounds__(kSadWarps * 32)
 sadsob_scan_kernel(const float* __restrict__ L, const float* __restrict__ R, int H, int W, int Dn,
                    int d_begin, int wsize_rt, int NB, size_t img_stride,
-                   const float* __restrict__ Vb, float* __restrict__ out, size_t out_stride) {
+                   const float* __restrict__ Vb, float* __restrict__ out, size_t out_stride, int out_pitch) {
   constexpr int SS = (WS > 0) ? (kSadTile + WS + ((WS & 1) ? 0 : 1)) : kSadSStride;  // odd stride
   __shared__ float sV[kSadWarps][kSadTile * kSadVStride];
   __shared__ float sS[kSadWarps][kSadTile * SS];
@@ -94,7 +94,7 @@ sadsob_scan_kernel(const float* __restrict__ L, const float* __restrict__ R, int
   const float* Ln = L + n * img_stride;
   const float* Rn = R + n * img_stride;
   const float* vb = Vb + (((size_t)n * Dn + dd) * NB + b) * IW;
-  float* o = out + n * out_stride + (size_t)dd * H * W;
+  float* o = out + n * out_stride + (size_t)dd * H * out_pitch;  // rows of out_pitch floats
   const int rows_live = min(kSadTile - 1, H - i0);      // image rows i0 .. i0+rows_live-1 exist
   const int rmax = min(RB, H - wsize - i0);             // origin rows produced by this band
 
@@ -147,12 +147,12 @@ sadsob_scan_kernel(const float* __restrict__ L, const float* __restrict__ R, int
     if (jo >= d && jo < W - wsize) {
       const float* top = tS + lane;
       const float* bot = top + wsize * SS;
-      float* op = o + (size_t)(i0 + wc) * W + (jo + wc);
+      float* op = o + (size_t)(i0 + wc) * out_pitch + (jo + wc);
 #pragma unroll 9
       for (int r = 0; r < rmax; ++r) {
         const float val = __fadd_rn(__fsub_rn(__fsub_rn(bot[wsize], bot[0]), top[wsize]), top[0]);
         st_stream(op, val);
-        top += SS; bot += SS; op += W;
+        top += SS; bot += SS; op += out_pitch;
       }
     }
     __syncwarp();
@@ -174,13 +174,15 @@ size_t sadsob_workspace_bytes(int H, int W, int D, int wsize) {
   return sadsob_workspace_bytes_n(1, H, W, D, wsize);
 }
 
-// N pairs; L/R are float [N][H][W]; out is [N][Dn][H][W] with stride out_stride floats per pair.
+// N pairs; L/R are float [N][H][W]; out is [N][Dn][H][out_pitch] (out_pitch >= W; the caller may
+// pre-offset `out` by a few columns) with stride out_stride floats per pair.
 int launch_sadsob_n(const float* L, const float* R, int N, int H, int W, int Dn, int d_begin, int wsize,
-                    float* out, size_t out_stride, bool write_fill, void* workspace, cudaStream_t s) {
+                    float* out, size_t out_stride, int out_pitch, bool write_fill, void* workspace,
+                    cudaStream_t s) {
   MSN_REQUIRE(wsize >= 1 && wsize <= kSadMaxW, "sadsob: wsize %d unsupported (1..%d)", wsize, kSadMaxW);
   if (write_fill) {
     for (int n = 0; n < N; ++n)
-      if (launch_fill(out + n * out_stride, (size_t)Dn * H * W, kFill, s)) return 1;
+      if (launch_fill(out + n * out_stride, (size_t)Dn * H * out_pitch, kFill, s)) return 1;
   }
   int RB, NB;
   sadsob_geom(H, wsize, &RB, &NB);
@@ -192,17 +194,17 @@ int launch_sadsob_n(const float* L, const float* R, int N, int H, int W, int Dn,
   dim3 g2(div_up((long long)Dn * NB, kSadWarps), 1, N);
   if (wsize == 5)  // the reference's default sobelw (cbmv_generator.py:440)
     sadsob_scan_kernel<5><<<g2, kSadWarps * 32, 0, s>>>(L, R, H, W, Dn, d_begin, wsize, NB, (size_t)H * W, Vb, out,
-                                                        out_stride);
+                                                        out_stride, out_pitch);
   else
     sadsob_scan_kernel<0><<<g2, kSadWarps * 32, 0, s>>>(L, R, H, W, Dn, d_begin, wsize, NB, (size_t)H * W, Vb, out,
-                                                        out_stride);
+                                                        out_stride, out_pitch);
   MSN_LAUNCH_OK();
   return 0;
 }
 
 int launch_sadsob(const float* L, const float* R, int H, int W, int D, int d_begin, int wsize, float* out,
                   bool write_fill, void* workspace, cudaStream_t s) {
-  return launch_sadsob_n(L, R, 1, H, W, D, d_begin, wsize, out, (size_t)D * H * W, write_fill, workspace, s);
+  return launch_sadsob_n(L, R, 1, H, W, D, d_begin, wsize, out, (size_t)D * H * W, W, write_fill, workspace, s);
 }
 
 }  // namespace msn
