@@ -477,7 +477,7 @@ size_t msn_ms_features_workspace_bytes(int N, int H, int W, const msn_ms_params*
   GenericWs ws;
   ws.carve(nullptr, g, p);
   size_t need = ws.total;
-  if (fused_supported(p, g.Dn) && !force_generic()) {
+  if (fused_supported(p, g.Dn) && sadsob_fast_pitch(W + 35) > 0 && !force_generic()) {
     const size_t f = fused_workspace_bytes(N, H, W, g.Dn, p);
     need = f;
   }
@@ -496,7 +496,7 @@ int msn_ms_features_dev(const uint8_t* d_left, const uint8_t* d_right, int N, in
   MSN_REQUIRE(g.d_begin == 0 && g.Dn == g.D, "ms_features: slabs go through msn_ms_slab_phase_*_dev");
   cudaStream_t s = as_stream(stream);
   char* base = (char*)(((uintptr_t)d_workspace + 255) & ~(uintptr_t)255);
-  if (fused_supported(p, g.Dn) && !force_generic())
+  if (fused_supported(p, g.Dn) && sadsob_fast_pitch(W + 35) > 0 && !force_generic())
     return launch_ms_fused(d_left, d_right, N, H, W, p, d_out, base, s);
   GenericWs ws;
   ws.carve(base, g, p);

@@ -74,7 +74,7 @@ FusedGeom make_geom(int N, int H, int W, const msn_ms_params* p) {
   g.Hp = H + 2 * kPadT;
   g.Wp = (W + g.padL + kPadR + 3) & ~3;
   g.sxo = (4 - (g.bwl & 3)) & 3;            // x0 + bwl + sxo is a multiple of 4 for every tile
-  g.Ws = (W + g.sxo + kTile + 3) & ~3;      // room for the last tile's overhang
+  g.Ws = sadsob_fast_pitch(W + g.sxo + kTile);  // compile-time pitch of the scan kernels (0: too wide)
   return g;
 }
 
@@ -93,7 +93,7 @@ struct FusedWs {
     for (int i = 0; i < 2; ++i) desc[i] = (uint4*)take(np * sizeof(uint4));
     for (int i = 0; i < 2; ++i) stat[i] = (RStat*)take(np * sizeof(RStat));
     for (int i = 0; i < 2; ++i) fimg[i] = (float*)take(np * sizeof(float));
-    for (int i = 0; i < 2; ++i) sob[i] = (float*)take(n * sizeof(float));
+    for (int i = 0; i < 2; ++i) sob[i] = (float*)take((size_t)g.N * (g.H + kSadRowPad) * g.Ws * sizeof(float));  // zero padded
     sadsob = (float*)take((size_t)g.N * g.D * g.H * g.Ws * sizeof(float) + 256);
     sad_ws = take(sadsob_workspace_bytes_n(g.N, g.H, g.W, g.D, kSadW));
     total = off;
@@ -172,7 +172,7 @@ ms_prep_kernel(const uint8_t* __restrict__ left, const uint8_t* __restrict__ rig
       sv = (float)(((int)p[2] - (int)p[0]) + 2 * ((int)p[W + 2] - (int)p[W]) +
                    ((int)p[2 * W + 2] - (int)p[2 * W]));
     }
-    (side ? sobR : sobL)[(size_t)n * H * W + (size_t)Y * W + X] = sv;
+    (side ? sobR : sobL)[(size_t)n * (H + kSadRowPad) * g.Ws + (size_t)Y * g.Ws + X] = sv;
   }
   (side ? descR : descL)[po] = make_uint4(w0, w1, w2, w3);
   (side ? statR : statL)[po] = st;
@@ -707,7 +707,7 @@ int profile_read(double* prep_ms, double* sadsob_ms, double* fused_ms, int* call
 
 bool fused_supported(const msn_ms_params* p, int Dn) {
   return p->censw == kCensW && p->nccw == kNccW && p->sadw == kSadW && p->sobelw == kSadW && p->lr == 0 &&
-         Dn == p->ndisp && p->ndisp <= kMaxFusedD;
+         Dn == p->ndisp && p->ndisp <= kMaxFusedD;  // (image width is checked at launch)
 }
 
 size_t fused_workspace_bytes(int N, int H, int W, int Dn, const msn_ms_params* p) {
@@ -736,14 +736,15 @@ int launch_ms_fused(const uint8_t* d_left, const uint8_t* d_right, int N, int H,
     for (int i = 0; i < 4; ++i) MSN_CUDA_OK(cudaEventCreate(&rec.ev[i]));
     MSN_CUDA_OK(cudaEventRecord(rec.ev[0], s));
   }
+  // zero the row padding of the Sobel images (the scan reads up to 31 rows past H)
+  for (int i = 0; i < 2; ++i)
+    MSN_CUDA_OK(cudaMemsetAsync(ws.sob[i], 0, (size_t)N * (H + kSadRowPad) * g.Ws * sizeof(float), s));
   dim3 pgrid(div_up(g.Wp, 128), g.Hp, 2 * N);
   ms_prep_kernel<<<pgrid, 128, 0, s>>>(d_left, d_right, g, ws.desc[0], ws.desc[1], ws.stat[0], ws.stat[1],
                                        ws.fimg[0], ws.fimg[1], ws.sob[0], ws.sob[1]);
   MSN_LAUNCH_OK();
   if (prof) MSN_CUDA_OK(cudaEventRecord(rec.ev[1], s));
-  if (launch_sadsob_n(ws.sob[0], ws.sob[1], N, H, W, g.D, 0, kSadW, ws.sadsob + g.sxo, (size_t)g.D * H * g.Ws, g.Ws,
-                      false, ws.sad_ws, s))
-    return 1;
+  if (launch_sadsob5_padded(ws.sob[0], ws.sob[1], N, H, W, g.D, 0, ws.sadsob + g.sxo, ws.sad_ws, s)) return 1;
   if (prof) MSN_CUDA_OK(cudaEventRecord(rec.ev[2], s));
 
   FusedArgs a;

@@ -34,8 +34,9 @@ constexpr int kSadWarps = 4;
 __device__ __forceinline__ float absdiff_rn(float a, float b) { return fabsf(__fsub_rn(a, b)); }
 
 // grid: (ceil(IW/128), Dn, N); thread = table column j in [0, W].
+// pitch: row pitch of L/R in floats (>= W).
 __global__ void sadsob_vband_kernel(const float* __restrict__ L, const float* __restrict__ R, int H, int W,
-                                    int d_begin, int RB, int NB, size_t img_stride,
+                                    int pitch, int d_begin, int RB, int NB, size_t img_stride,
                                     float* __restrict__ Vb) {
   const int IW = W + 1;
   const int j = blockIdx.x * blockDim.x + threadIdx.x;
@@ -55,7 +56,7 @@ __global__ void sadsob_vband_kernel(const float* __restrict__ L, const float* __
 #pragma unroll
     for (int q = 0; q < 8; ++q) {
       const int row = row0 + q;
-      av[q] = (active && row < H) ? absdiff_rn(__ldg(l + (size_t)row * W), __ldg(r + (size_t)row * W)) : 0.f;
+      av[q] = (active && row < H) ? absdiff_rn(__ldg(l + (size_t)row * pitch), __ldg(r + (size_t)row * pitch)) : 0.f;
     }
 #pragma unroll
     for (int q = 0; q < 8; ++q) {
@@ -159,6 +160,112 @@ sadsob_scan_kernel(const float* __restrict__ L, const float* __restrict__ R, int
   }
 }
 
+// ---------------------------------------------------------------------------
+// Specialised sweep for the reference's default window (sobelw = 5) used by the fused
+// path, whose Sobel images carry >= 31 ZERO rows below row H-1 (kSadRowPad), so the 62
+// loads of a tile column need no row guards (|0 - 0| adds an exact 0).  One shared tile
+// T[32][37] per warp serves in turn the vertical prefixes (written column-wise, read
+// row-wise), the horizontal prefixes (in place) and the boxes (read column-wise); the five
+// halo columns travel in registers between tiles, and the box stage reads every table
+// element once, keeping the five rows a window spans in registers.
+constexpr int kS5W = 5;
+constexpr int kS5Stride = kSadTile + kS5W;  // 37: odd, conflict-free both ways
+constexpr int kS5Warps = 4;
+
+template <bool kMask, int SP>
+__device__ __forceinline__ void s5_vertical(const float* __restrict__ lp, const float* __restrict__ rp,
+                                            bool active, float v, float* __restrict__ T, int lane) {
+  float av[kSadTile - 1];
+#pragma unroll
+  for (int r = 0; r < kSadTile - 1; ++r) {   // row offsets r*SP are immediates: no address math
+    const float x = absdiff_rn(__ldg(lp + r * SP), __ldg(rp + r * SP));
+    av[r] = (!kMask || active) ? x : 0.f;
+  }
+  T[kS5W + lane] = v;
+#pragma unroll
+  for (int r = 1; r < kSadTile; ++r) {
+    v = __fadd_rn(v, av[r - 1]);  // + 0.0f on masked / padded entries is exact
+    T[r * kS5Stride + kS5W + lane] = v;
+  }
+}
+
+// SP: row pitch in floats of BOTH the Sobel images and the output volume (compile-time so
+// that every row offset is an immediate); W <= SP.
+template <int SP>
+__global__ void __launch_bounds__(kS5Warps * 32, 6)
+sadsob_scan5_kernel(const float* __restrict__ L, const float* __restrict__ R, int H, int W, int Dn, int d_begin,
+                    int NB, size_t img_stride, const float* __restrict__ Vb, float* __restrict__ out,
+                    size_t out_stride) {
+  __shared__ float sT[kS5Warps][kSadTile * kS5Stride];
+  constexpr int RB = kSadTile - kS5W;  // 27 origin rows per band
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int job = blockIdx.x * kS5Warps + warp;
+  if (job >= Dn * NB) return;  // whole warp exits together
+  const int dd = job / NB, b = job % NB, n = blockIdx.z;
+  const int d = d_begin + dd;
+  const int IW = W + 1;
+  const int i0 = b * RB;
+  float* T = sT[warp];
+  const float* Ln = L + n * img_stride + (size_t)i0 * SP;
+  const float* Rn = R + n * img_stride + (size_t)i0 * SP - d;
+  const float* vb = Vb + (((size_t)n * Dn + dd) * NB + b) * IW;
+  float* o = out + n * out_stride + (size_t)dd * H * SP + (size_t)(i0 + 2) * SP + 2;
+  const int rmax = min(RB, H - kS5W - i0);          // origin rows produced by this band
+
+  const int t0 = d / kSadTile, t1 = (W - 1) / kSadTile;
+  float s = 0.f;                                  // horizontal carry of table row i0 + lane
+  float h0 = 0.f, h1 = 0.f, h2 = 0.f, h3 = 0.f, h4 = 0.f;  // this row's last five S values
+  float* trow = T + lane * kS5Stride;
+  for (int t = t0; t <= t1; ++t) {
+    // (a) lanes own table columns: vertical prefix inside the band (loads first, then chain)
+    const int j = t * kSadTile + lane;
+    const int jc = j - 1;
+    const float v = (j < IW) ? __ldg(vb + j) : 0.f;
+    if (t == t0 || t == t1) {
+      const bool active = (j < IW) && (jc >= d);
+      const int jsafe = min(max(jc, d), W - 1);      // masked lanes load a valid address
+      s5_vertical<true, SP>(Ln + jsafe, Rn + jsafe, active, v, T, lane);
+    } else {
+      s5_vertical<false, SP>(Ln + jc, Rn + jc, true, v, T, lane);
+    }
+    __syncwarp();
+    // (b) lanes own table rows: halo from registers, horizontal chain in place
+    trow[0] = h0; trow[1] = h1; trow[2] = h2; trow[3] = h3; trow[4] = h4;
+#pragma unroll
+    for (int c = 0; c < kSadTile; ++c) {
+      s = __fadd_rn(s, trow[kS5W + c]);
+      trow[kS5W + c] = s;
+      if (c == kSadTile - 5) h0 = s;
+      if (c == kSadTile - 4) h1 = s;
+      if (c == kSadTile - 3) h2 = s;
+      if (c == kSadTile - 2) h3 = s;
+      if (c == kSadTile - 1) h4 = s;
+    }
+    __syncwarp();
+    // (c) lanes own origin columns: out(r) = ((S[r+5][j+5] - S[r+5][j]) - S[r][j+5]) + S[r][j]
+    const int jo = t * kSadTile - kS5W + lane;  // window origin column
+    if (jo >= d && jo < W - kS5W) {
+      float lo[kS5W], hi[kS5W];  // table rows r .. r+4 at columns jo and jo+5
+#pragma unroll
+      for (int r = 0; r < kS5W; ++r) {
+        lo[r] = T[r * kS5Stride + lane];
+        hi[r] = T[r * kS5Stride + lane + kS5W];
+      }
+      float* op = o + jo;
+#pragma unroll
+      for (int r = 0; r < RB; ++r) {
+        const float bl = T[(r + kS5W) * kS5Stride + lane];
+        const float br = T[(r + kS5W) * kS5Stride + lane + kS5W];
+        const float val = __fadd_rn(__fsub_rn(__fsub_rn(br, bl), hi[r % kS5W]), lo[r % kS5W]);
+        if (r < rmax) st_stream(op + r * SP, val);
+        lo[r % kS5W] = bl;
+        hi[r % kS5W] = br;
+      }
+    }
+    __syncwarp();
+  }
+}
+
 static inline void sadsob_geom(int H, int wsize, int* RB, int* NB) {
   *RB = kSadTile - wsize;
   const int rows = H - wsize;  // origin rows i in [0, H - wsize)
@@ -176,6 +283,8 @@ size_t sadsob_workspace_bytes(int H, int W, int D, int wsize) {
 
 // N pairs; L/R are float [N][H][W]; out is [N][Dn][H][out_pitch] (out_pitch >= W; the caller may
 // pre-offset `out` by a few columns) with stride out_stride floats per pair.
+// Generic form: L/R are [N][H][W] (pitch W); out is [N][Dn][H][out_pitch] (out_pitch >= W) with
+// stride out_stride floats per pair.
 int launch_sadsob_n(const float* L, const float* R, int N, int H, int W, int Dn, int d_begin, int wsize,
                     float* out, size_t out_stride, int out_pitch, bool write_fill, void* workspace,
                     cudaStream_t s) {
@@ -188,16 +297,45 @@ int launch_sadsob_n(const float* L, const float* R, int N, int H, int W, int Dn,
   sadsob_geom(H, wsize, &RB, &NB);
   if (NB <= 0 || W - wsize <= 0 || Dn <= 0) return 0;
   float* Vb = static_cast<float*>(workspace);
+  const size_t img_stride = (size_t)H * W;
   dim3 g1(div_up(W + 1, 128), Dn, N);
-  sadsob_vband_kernel<<<g1, 128, 0, s>>>(L, R, H, W, d_begin, RB, NB, (size_t)H * W, Vb);
+  sadsob_vband_kernel<<<g1, 128, 0, s>>>(L, R, H, W, W, d_begin, RB, NB, img_stride, Vb);
   MSN_LAUNCH_OK();
   dim3 g2(div_up((long long)Dn * NB, kSadWarps), 1, N);
   if (wsize == 5)  // the reference's default sobelw (cbmv_generator.py:440)
-    sadsob_scan_kernel<5><<<g2, kSadWarps * 32, 0, s>>>(L, R, H, W, Dn, d_begin, wsize, NB, (size_t)H * W, Vb, out,
+    sadsob_scan_kernel<5><<<g2, kSadWarps * 32, 0, s>>>(L, R, H, W, Dn, d_begin, wsize, NB, img_stride, Vb, out,
                                                         out_stride, out_pitch);
   else
-    sadsob_scan_kernel<0><<<g2, kSadWarps * 32, 0, s>>>(L, R, H, W, Dn, d_begin, wsize, NB, (size_t)H * W, Vb, out,
+    sadsob_scan_kernel<0><<<g2, kSadWarps * 32, 0, s>>>(L, R, H, W, Dn, d_begin, wsize, NB, img_stride, Vb, out,
                                                         out_stride, out_pitch);
+  MSN_LAUNCH_OK();
+  return 0;
+}
+
+// Fast form for the fused path (window 5): L/R are [N][H + kSadRowPad][SP] with ZERO padding
+// rows/columns, out is [N][Dn][H][SP]; SP = sadsob_fast_pitch(W) is one of 1024/2048/4096.
+int sadsob_fast_pitch(int W) { return W <= 1024 ? 1024 : W <= 2048 ? 2048 : W <= 4096 ? 4096 : 0; }
+
+int launch_sadsob5_padded(const float* L, const float* R, int N, int H, int W, int Dn, int d_begin, float* out,
+                          void* workspace, cudaStream_t s) {
+  const int SP = sadsob_fast_pitch(W);
+  MSN_REQUIRE(SP > 0, "sadsob: W=%d too wide for the padded window-5 scan", W);
+  int RB, NB;
+  sadsob_geom(H, kS5W, &RB, &NB);
+  if (NB <= 0 || W - kS5W <= 0 || Dn <= 0) return 0;
+  float* Vb = static_cast<float*>(workspace);
+  const size_t img_stride = (size_t)(H + kSadRowPad) * SP;
+  const size_t out_stride = (size_t)Dn * H * SP;
+  dim3 g1(div_up(W + 1, 128), Dn, N);
+  sadsob_vband_kernel<<<g1, 128, 0, s>>>(L, R, H, W, SP, d_begin, RB, NB, img_stride, Vb);
+  MSN_LAUNCH_OK();
+  dim3 g5(div_up((long long)Dn * NB, kS5Warps), 1, N);
+  if (SP == 1024)
+    sadsob_scan5_kernel<1024><<<g5, kS5Warps * 32, 0, s>>>(L, R, H, W, Dn, d_begin, NB, img_stride, Vb, out, out_stride);
+  else if (SP == 2048)
+    sadsob_scan5_kernel<2048><<<g5, kS5Warps * 32, 0, s>>>(L, R, H, W, Dn, d_begin, NB, img_stride, Vb, out, out_stride);
+  else
+    sadsob_scan5_kernel<4096><<<g5, kS5Warps * 32, 0, s>>>(L, R, H, W, Dn, d_begin, NB, img_stride, Vb, out, out_stride);
   MSN_LAUNCH_OK();
   return 0;
 }
