@@ -213,7 +213,7 @@ struct Lay {
   static constexpr size_t off_lut = off_inv + 4 * 32 * 4;                    // [128]
   static constexpr size_t off_par = (off_lut + 128 * 4 + 127) & ~(size_t)127;  // [3][DS][32] ncc, sadsob, zsad (128 B aligned: TMA destination)
   static constexpr size_t off_cen = off_par + (size_t)3 * DS * 32 * 4;       // [DS][32] bytes
-  static constexpr size_t off_bar = (off_cen + (size_t)DS * 32 + 15) & ~(size_t)15;  // mbarrier (8 B)
+  static constexpr size_t off_bar = (off_cen + (size_t)DS * 32 + 15) & ~(size_t)15;  // 2 mbarriers (8 B each)
   static constexpr size_t bytes = off_bar + 16;
 };
 
@@ -319,7 +319,8 @@ __device__ __forceinline__ void stage_right(const FusedArgs& a, const TileId& t,
 // single thread, completion counted in bytes on `bar`.
 template <int DMAX>
 __device__ __forceinline__ void stage_tma(const FusedArgs& a, const CUtensorMap* sad_map, const TileId& t,
-                                          unsigned char* buf, float* park_plane1, unsigned long long* bar) {
+                                          unsigned char* buf, float* park_plane1, unsigned long long* bar,
+                                          unsigned long long* bar_sad) {
   using L = Lay<DMAX>;
   const FusedGeom& g = a.g;
   const int D = g.D;
@@ -330,8 +331,10 @@ __device__ __forceinline__ void stage_tma(const FusedArgs& a, const CUtensorMap*
   const int fstart = (XbaseP - 2) & ~3;
   const int nvec = (RWn + 4 + 3 + 3) >> 2;
   const unsigned row_bytes = (unsigned)RWn * 16u, frow_bytes = (unsigned)nvec * 16u;
-  mbar_expect_tx(bar, 2u * row_bytes + 5u * frow_bytes + (unsigned)D * kTile * 4u);
-  tma_load_3d(park_plane1, sad_map, t.x0 + g.bwl + g.sxo, t.y + g.bh, t.n * D, bar);  // inner coordinate % 4 == 0
+  // the SAD-of-Sobel tile comes from DRAM and is only needed after phase 1: own barrier
+  mbar_expect_tx(bar_sad, (unsigned)D * kTile * 4u);
+  tma_load_3d(park_plane1, sad_map, t.x0 + g.bwl + g.sxo, t.y + g.bh, t.n * D, bar_sad);  // inner coordinate % 4 == 0
+  mbar_expect_tx(bar, 2u * row_bytes + 5u * frow_bytes);
   bulk_load(buf + L::st_desc, a.descR + img_off + (size_t)Yp * g.Wp + XbaseP, row_bytes, bar);
   bulk_load(buf + L::st_stat, a.statR + img_off + (size_t)Yp * g.Wp + XbaseP, row_bytes, bar);
   float* s_rf = reinterpret_cast<float*>(buf + L::st_rf);
@@ -375,7 +378,7 @@ ms_fused_kernel(const FusedArgs a, const __grid_constant__ CUtensorMap sad_map) 
   extern __shared__ __align__(128) unsigned char smem_raw[];  // TMA destinations need 128 B
   const FusedGeom& g = a.g;
   const int D = g.D;
-  unsigned long long& s_bar = *reinterpret_cast<unsigned long long*>(smem_raw + L::off_bar);
+  unsigned long long* s_bar = reinterpret_cast<unsigned long long*>(smem_raw + L::off_bar);  // [0] rows, [1] sadsob tile
   float* s_red = reinterpret_cast<float*>(smem_raw + L::off_red);    // [8][4][32]
   float* s_min = reinterpret_cast<float*>(smem_raw + L::off_min);    // [4][32]
   float* s_inv = reinterpret_cast<float*>(smem_raw + L::off_inv);    // [4][32]
@@ -404,9 +407,12 @@ ms_fused_kernel(const FusedArgs a, const __grid_constant__ CUtensorMap sad_map) 
     const int Y = t.y + g.bh;               // bordered image row
 
     if (kTma) {
-      if (threadIdx.x == 0) mbar_init(&s_bar, 1);
+      if (threadIdx.x == 0) {
+        mbar_init(&s_bar[0], 1);
+        mbar_init(&s_bar[1], 1);
+      }
       __syncthreads();
-      if (threadIdx.x == 0) stage_tma<DMAX>(a, &sad_map, t, buf, s_par + PS, &s_bar);
+      if (threadIdx.x == 0) stage_tma<DMAX>(a, &sad_map, t, buf, s_par + PS, &s_bar[0], &s_bar[1]);
     } else {
       // sadsob costs of this lane's own disparities: async global -> parked plane 1
       const float* src = a.sadsob + ((size_t)t.n * D * H + Y) * g.Ws + (X + g.sxo) + (size_t)d_lo * splane;
@@ -436,7 +442,7 @@ ms_fused_kernel(const FusedArgs a, const __grid_constant__ CUtensorMap sad_map) 
     const int dmax_ncc = min(D - 1, (Y >= 1 && Y < H - 2 && X >= 1 && X < W - 2) ? X - 1 : -1);
     const int dmax_sad = min(D - 1, (Y >= 2 && Y < H - 3 && X >= 2 && X < W - 3) ? X - 2 : -1);
 
-    if (kTma) mbar_wait(&s_bar, 0);
+    if (kTma) mbar_wait(&s_bar[0], 0);
     else cp_async_wait_all();
     __syncthreads();
     // ---- phase 1: raw costs into the parking planes, per-pixel minima ----------------
@@ -468,7 +474,6 @@ ms_fused_kernel(const FusedArgs a, const __grid_constant__ CUtensorMap sad_map) 
           const uint4 rd = *dscp;
           const uint4 rs_raw = *sttp;
           const RStat rs = *reinterpret_cast<const RStat*>(&rs_raw);
-          float sob = park[PS];
 
           // census: Hamming distance of the packed codes (matchers.cpp:323-337)
           const int cen = __popc(ld.x ^ rd.x) + __popc(ld.y ^ rd.y) + __popc(ld.z ^ rd.z) + __popc(ld.w ^ rd.w);
@@ -495,22 +500,33 @@ ms_fused_kernel(const FusedArgs a, const __grid_constant__ CUtensorMap sad_map) 
               const float u = __fadd_rn(__fsub_rn(at[r][c], rw[r][(c - k + 5) % 5]), rs.mean);
               z = __fadd_rn(z, fabsf(u));
             }
-          const bool ok_sad = d <= dmax_sad;
-          z = ok_sad ? z : kFill;
-          sob = ok_sad ? sob : kFill;
+          z = (d <= dmax_sad) ? z : kFill;
 
           s_cen[ds * 32 + lane] = (uint8_t)cen_b;
           park[0] = ncc;
-          park[PS] = sob;
           park[2 * PS] = z;
           min_cen = min(min_cen, cen_b);
           min_ncc = fminf(min_ncc, ncc);
-          min_sob = fminf(min_sob, sob);
           min_sad = fminf(min_sad, z);
           // slide the window: next step's new left column
           --rfp; --dscp; --sttp;
 #pragma unroll
           for (int r = 0; r < 5; ++r) rw[r][(4 - k) % 5] = rfp[r * L::RWF];
+        }
+      }
+      // SAD-of-Sobel costs of this warp's disparities (delivered by TMA / cp.async while the loop
+      // above ran): replace what lies outside the valid region by fill, take the minimum
+      if (kTma) mbar_wait(&s_bar[1], 0);
+      {
+        float* sp = s_par + PS + d_lo * 32 + lane;
+#pragma unroll 4
+        for (int d = d_lo; d < d_end; ++d, sp += 32) {
+          float v = *sp;
+          if (d > dmax_sad) {
+            v = kFill;
+            *sp = v;
+          }
+          min_sob = fminf(min_sob, v);
         }
       }
       s_red[(warp * 4 + 0) * 32 + lane] = (min_cen == 255) ? kFill : (float)min_cen;
