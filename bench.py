@@ -225,7 +225,7 @@ def run_ours(args):
     tp = os.path.join(ROOT, "profiles", "roofline_traffic.json")
     if os.path.isfile(tp):
         try:
-            traffic = json.load(open(tp)).get("ms_fused_kernel_dram_bytes_per_launch")
+            traffic = int(json.load(open(tp)).get("ms_fused_kernel_dram_bytes_per_pair") * BATCH)
         except Exception:
             traffic = None
     step_ms = ms_res / args.steps
