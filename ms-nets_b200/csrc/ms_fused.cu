@@ -191,30 +191,39 @@ struct FusedArgs {
   int DC;               // disparity steps per warp (multiple of 5)
   int tiles_x;
   int num_tiles;
+  float stagger_ns;     // persistent kernel: CTA start offsets are drawn from [0, stagger_ns)
 };
 
 // Shared-memory layout for disparity counts up to DMAX.  Row strides are compile-time
 // so every shared access in the hot loop is "pointer + immediate".
-constexpr int kSlack = 40;  // right-image entries below index 0 reached by dummy steps (d >= D); see make_geom
-template <int DMAX>
+//   SLACK : right-image entries below index 0 reached by dummy steps (d >= D); 8*DC - D of them
+//   NBUF  : staging buffers (1: one tile per CTA; 2: persistent CTA, next tile prefetched)
+constexpr int kSlack = 40;  // enough for every D (see make_geom: padL covers it)
+template <int DMAX, int SLACK = kSlack, int NBUF = 1>
 struct Lay {
-  static constexpr int RW = (DMAX + kTile - 1 + kSlack + 3) & ~3;  // desc / stat entries
+  static constexpr int kSl = SLACK;
+  static constexpr int RW = (DMAX + kTile - 1 + SLACK + 3) & ~3;   // desc / stat entries
   static constexpr int RWF = RW + 8;                               // float row: halo 2+2, align shift <= 3
+  static constexpr int LF = 40;                                    // left float row: 32 + halo 4, shift <= 3
   static constexpr int DS = DMAX + 1;                              // parked planes + 1 scratch plane
-  // staging buffer: right-image row data of the tile
+  // one staging buffer: right-image row data of a tile (+ the 32 left pixels' data when the
+  // persistent kernel prefetches them through TMA as well)
   static constexpr size_t st_desc = 0;
   static constexpr size_t st_stat = st_desc + (size_t)RW * 16;
   static constexpr size_t st_rf = st_stat + (size_t)RW * 16;
-  static constexpr size_t st_bytes = st_rf + (size_t)5 * RWF * 4;
+  static constexpr size_t st_ldesc = st_rf + (size_t)5 * RWF * 4;
+  static constexpr size_t st_lstat = st_ldesc + (NBUF > 1 ? kTile * 16 : 0);
+  static constexpr size_t st_lf = st_lstat + (NBUF > 1 ? kTile * 16 : 0);
+  static constexpr size_t st_bytes = st_lf + (NBUF > 1 ? 5 * LF * 4 : 0);
   static constexpr size_t off_stage = 0;
-  static constexpr size_t off_red = off_stage + st_bytes;                     // [8][4][32]
+  static constexpr size_t off_red = off_stage + NBUF * st_bytes;              // [8][4][32]
   static constexpr size_t off_min = off_red + (size_t)kWarps * 4 * 32 * 4;   // [4][32]
   static constexpr size_t off_inv = off_min + 4 * 32 * 4;                    // [4][32]
   static constexpr size_t off_lut = off_inv + 4 * 32 * 4;                    // [128]
   static constexpr size_t off_par = (off_lut + 128 * 4 + 127) & ~(size_t)127;  // [3][DS][32] ncc, sadsob, zsad (128 B aligned: TMA destination)
   static constexpr size_t off_cen = off_par + (size_t)3 * DS * 32 * 4;       // [DS][32] bytes
-  static constexpr size_t off_bar = (off_cen + (size_t)DS * 32 + 15) & ~(size_t)15;  // 2 mbarriers (8 B each)
-  static constexpr size_t bytes = off_bar + 16;
+  static constexpr size_t off_bar = (off_cen + (size_t)DS * 32 + 15) & ~(size_t)15;  // mbarriers (8 B each)
+  static constexpr size_t bytes = off_bar + 32;
 };
 
 __device__ __forceinline__ float int_to_float_small(int c) {  // exact for 0 <= c < 2^23
@@ -288,13 +297,12 @@ __device__ __forceinline__ TileId decode_tile(int tile, const FusedArgs& a) {
 // census codes and stats of the D+31(+slack) columns the tile can touch and the five
 // float rows of the ZSAD/NCC windows (16-byte cp.async; the float rows start at a
 // 4-float aligned column, the 0..3 float shift is returned through *shift).
-template <int DMAX>
+template <class L>
 __device__ __forceinline__ void stage_right(const FusedArgs& a, const TileId& t, unsigned char* buf) {
-  using L = Lay<DMAX>;
   const FusedGeom& g = a.g;
   const int D = g.D;
-  const int RWn = D + kTile - 1 + kSlack;
-  const int XbaseP = t.x0 + g.bwl - (D - 1) - kSlack + g.padL;
+  const int RWn = D + kTile - 1 + L::kSl;
+  const int XbaseP = t.x0 + g.bwl - (D - 1) - L::kSl + g.padL;
   const int Yp = t.y + g.bh + kPadT;
   const size_t img_off = (size_t)t.n * g.img_px();
   const uint4* gd = a.descR + img_off + (size_t)Yp * g.Wp + XbaseP;
@@ -314,33 +322,46 @@ __device__ __forceinline__ void stage_right(const FusedArgs& a, const TileId& t,
   }
 }
 
-// Same data through the TMA engine: seven 1-D bulk copies plus ONE 3-D tensor copy that
-// drops the tile's D x 32 SAD-of-Sobel costs straight into parking plane 1; issued by a
-// single thread, completion counted in bytes on `bar`.
-template <int DMAX>
-__device__ __forceinline__ void stage_tma(const FusedArgs& a, const CUtensorMap* sad_map, const TileId& t,
-                                          unsigned char* buf, float* park_plane1, unsigned long long* bar,
-                                          unsigned long long* bar_sad) {
-  using L = Lay<DMAX>;
+// Same data through the TMA engine: seven 1-D bulk copies (plus seven tiny ones for the 32
+// left pixels when with_left), issued by a single thread, completion counted in bytes on `bar`.
+template <class L>
+__device__ __forceinline__ void stage_rows_tma(const FusedArgs& a, const TileId& t, unsigned char* buf,
+                                               unsigned long long* bar, bool with_left) {
   const FusedGeom& g = a.g;
   const int D = g.D;
-  const int RWn = D + kTile - 1 + kSlack;
-  const int XbaseP = t.x0 + g.bwl - (D - 1) - kSlack + g.padL;
+  const int RWn = D + kTile - 1 + L::kSl;
+  const int XbaseP = t.x0 + g.bwl - (D - 1) - L::kSl + g.padL;
   const int Yp = t.y + g.bh + kPadT;
   const size_t img_off = (size_t)t.n * g.img_px();
   const int fstart = (XbaseP - 2) & ~3;
   const int nvec = (RWn + 4 + 3 + 3) >> 2;
   const unsigned row_bytes = (unsigned)RWn * 16u, frow_bytes = (unsigned)nvec * 16u;
-  // the SAD-of-Sobel tile comes from DRAM and is only needed after phase 1: own barrier
-  mbar_expect_tx(bar_sad, (unsigned)D * kTile * 4u);
-  tma_load_3d(park_plane1, sad_map, t.x0 + g.bwl + g.sxo, t.y + g.bh, t.n * D, bar_sad);  // inner coordinate % 4 == 0
-  mbar_expect_tx(bar, 2u * row_bytes + 5u * frow_bytes);
+  const int XpL = t.x0 + g.bwl + g.padL;                 // padded column of the tile's first left pixel
+  const int lstart = (XpL - 2) & ~3;
+  mbar_expect_tx(bar, 2u * row_bytes + 5u * frow_bytes + (with_left ? (2u * kTile * 16u + 5u * L::LF * 4u) : 0u));
   bulk_load(buf + L::st_desc, a.descR + img_off + (size_t)Yp * g.Wp + XbaseP, row_bytes, bar);
   bulk_load(buf + L::st_stat, a.statR + img_off + (size_t)Yp * g.Wp + XbaseP, row_bytes, bar);
   float* s_rf = reinterpret_cast<float*>(buf + L::st_rf);
 #pragma unroll
   for (int r = 0; r < 5; ++r)
     bulk_load(s_rf + r * L::RWF, a.fR + img_off + (size_t)(Yp - 2 + r) * g.Wp + fstart, frow_bytes, bar);
+  if (with_left) {
+    bulk_load(buf + L::st_ldesc, a.descL + img_off + (size_t)Yp * g.Wp + XpL, kTile * 16u, bar);
+    bulk_load(buf + L::st_lstat, a.statL + img_off + (size_t)Yp * g.Wp + XpL, kTile * 16u, bar);
+    float* s_lf = reinterpret_cast<float*>(buf + L::st_lf);
+#pragma unroll
+    for (int r = 0; r < 5; ++r)
+      bulk_load(s_lf + r * L::LF, a.fL + img_off + (size_t)(Yp - 2 + r) * g.Wp + lstart, L::LF * 4u, bar);
+  }
+}
+
+// The tile's D x 32 SAD-of-Sobel costs: ONE 3-D tensor copy straight into parking plane 1.
+// They come from DRAM and are only needed after phase 1, hence their own barrier.
+__device__ __forceinline__ void stage_sad_tma(const FusedArgs& a, const CUtensorMap* sad_map, const TileId& t,
+                                              float* park_plane1, unsigned long long* bar_sad) {
+  const FusedGeom& g = a.g;
+  mbar_expect_tx(bar_sad, (unsigned)g.D * kTile * 4u);
+  tma_load_3d(park_plane1, sad_map, t.x0 + g.bwl + g.sxo, t.y + g.bh, t.n * g.D, bar_sad);  // inner coordinate % 4 == 0
 }
 
 // The lane's own left-image data: census code, stats, 5x5 float window.
@@ -364,21 +385,29 @@ __device__ __forceinline__ void load_left(const FusedArgs& a, const TileId& t, i
   }
 }
 
-// One CTA per tile.  (A persistent variant with double-buffered staging and left-image
-// register prefetch was measured 13 % SLOWER on B200: resident CTAs fall into lockstep and
-// the hardware CTA scheduler balances the cheaper border tiles better; see DESIGN.md.)
-// kTma: right-image rows and the SAD-of-Sobel tile arrive through cp.async.bulk /
-// cp.async.bulk.tensor (D <= 256: box limit); otherwise through LDGSTS.  The tensor copy's
-// inner coordinate must be a multiple of 16 bytes (measured: anything else raises an
-// illegal-instruction fault), which is why the scratch is stored with column offset sxo.
-template <int DMAX, bool kTma>
-__global__ void __launch_bounds__(kWarps * 32, 2)
-ms_fused_kernel(const FusedArgs a, const __grid_constant__ CUtensorMap sad_map) {
-  using L = Lay<DMAX>;
-  extern __shared__ __align__(128) unsigned char smem_raw[];  // TMA destinations need 128 B
+// Left data from the persistent kernel's staging buffer (delivered by TMA).
+template <class L>
+__device__ __forceinline__ void load_left_smem(const FusedArgs& a, const TileId& t, const unsigned char* buf, int lane,
+                                               LeftRegs& lr) {
+  const int shift = (t.x0 + a.g.bwl + a.g.padL - 2) & 3;
+  lr.desc = reinterpret_cast<const uint4*>(buf + L::st_ldesc)[lane];
+  lr.stat = reinterpret_cast<const uint4*>(buf + L::st_lstat)[lane];
+  const float* s_lf = reinterpret_cast<const float*>(buf + L::st_lf) + shift + lane;
+#pragma unroll
+  for (int r = 0; r < 5; ++r)
+#pragma unroll
+    for (int c = 0; c < 5; ++c) lr.px[r][c] = s_lf[r * L::LF + c];
+}
+
+// Everything a tile does once its right-image rows are staged in `buf` (and every thread has
+// passed the barrier that made them visible): phases 1-3 described at the top of the file.
+// `lr` holds the lane's left-image data; the SAD-of-Sobel tile is awaited on bar_sad (TMA).
+template <class L, bool kTma>
+__device__ __forceinline__ void tile_compute(const FusedArgs& a, unsigned char* smem_raw, const TileId& t,
+                                             const unsigned char* buf, const LeftRegs& lr,
+                                             unsigned long long* bar_sad, unsigned sad_parity) {
   const FusedGeom& g = a.g;
   const int D = g.D;
-  unsigned long long* s_bar = reinterpret_cast<unsigned long long*>(smem_raw + L::off_bar);  // [0] rows, [1] sadsob tile
   float* s_red = reinterpret_cast<float*>(smem_raw + L::off_red);    // [8][4][32]
   float* s_min = reinterpret_cast<float*>(smem_raw + L::off_min);    // [4][32]
   float* s_inv = reinterpret_cast<float*>(smem_raw + L::off_inv);    // [4][32]
@@ -386,74 +415,45 @@ ms_fused_kernel(const FusedArgs a, const __grid_constant__ CUtensorMap sad_map) 
   float* s_par = reinterpret_cast<float*>(smem_raw + L::off_par);    // [3][DS][32]
   uint8_t* s_cen = smem_raw + L::off_cen;                            // [DS][32]
   constexpr int PS = L::DS * 32;                                     // floats per parked matcher
-
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int H = g.H, W = g.W;
   const int d_lo = warp * a.DC;
   const int d_end = min(D, d_lo + a.DC);  // real disparities of this warp: [d_lo, d_end)
   const size_t plane = (size_t)g.h * g.w;
   const size_t chan = plane * D;
-  const size_t splane = (size_t)H * g.Ws;
   // 128-bit stores need 16-byte aligned rows
   const bool vec_ok = ((g.w & 3) == 0) && ((reinterpret_cast<uintptr_t>(a.out) & 15) == 0);
   // AML-phase mapping: thread = (pixel quad q, disparity lane dl); d = dl, dl+32, ...
   const int q4 = (threadIdx.x & 7) * 4;
   const int dl = threadIdx.x >> 3;
-
-  const TileId t = decode_tile(blockIdx.x, a);
-  unsigned char* buf = smem_raw + L::off_stage;
+  const int X = t.x0 + lane + g.bwl;      // bordered image column of this lane
+  const int Y = t.y + g.bh;               // bordered image row
+  const uint4 ld = lr.desc;
+  const RStat ls = *reinterpret_cast<const RStat*>(&lr.stat);
+  float at[5][5];   // (L - mL), hoisted over all d   (matchers.cpp:503)
+  float l3[3][3];   // centre 3x3 of L as float for NCC
+#pragma unroll
+  for (int r = 0; r < 5; ++r)
+#pragma unroll
+    for (int c = 0; c < 5; ++c) {
+      at[r][c] = __fsub_rn(lr.px[r][c], ls.mean);
+      if (r >= 1 && r <= 3 && c >= 1 && c <= 3) l3[r - 1][c - 1] = lr.px[r][c];
+    }
   {
-    const int X = t.x0 + lane + g.bwl;      // bordered image column of this lane
-    const int Y = t.y + g.bh;               // bordered image row
-
-    if (kTma) {
-      if (threadIdx.x == 0) {
-        mbar_init(&s_bar[0], 1);
-        mbar_init(&s_bar[1], 1);
-      }
-      __syncthreads();
-      if (threadIdx.x == 0) stage_tma<DMAX>(a, &sad_map, t, buf, s_par + PS, &s_bar[0], &s_bar[1]);
-    } else {
-      // sadsob costs of this lane's own disparities: async global -> parked plane 1
-      const float* src = a.sadsob + ((size_t)t.n * D * H + Y) * g.Ws + (X + g.sxo) + (size_t)d_lo * splane;
-      float* dst = s_par + PS + d_lo * 32 + lane;
-      for (int d = d_lo; d < d_end; ++d, src += splane, dst += 32) cp_async4(dst, src);
-      stage_right<DMAX>(a, t, buf);
-    }
-    if (threadIdx.x < 128) {
-      const int kk = threadIdx.x;
-      s_lut[kk] = (kk <= 120) ? ex2_approx(-(float)(kk * kk) * a.k_cen) : 0.f;
-    }
-    LeftRegs lr;
-    load_left(a, t, lane, lr);
-    const uint4 ld = lr.desc;
-    const RStat ls = *reinterpret_cast<const RStat*>(&lr.stat);
-    float at[5][5];   // (L - mL), hoisted over all d   (matchers.cpp:503)
-    float l3[3][3];   // centre 3x3 of L as float for NCC
-#pragma unroll
-    for (int r = 0; r < 5; ++r)
-#pragma unroll
-      for (int c = 0; c < 5; ++c) {
-        at[r][c] = __fsub_rn(lr.px[r][c], ls.mean);
-        if (r >= 1 && r <= 3 && c >= 1 && c <= 3) l3[r - 1][c - 1] = lr.px[r][c];
-      }
     // validity: cost(y,x,d) exists iff the window origin is inside and x - wc >= d (and d < D)
     const int dmax_cen = min(D - 1, (Y >= 5 && Y < H - 6 && X >= 5 && X < W - 6) ? X - 5 : -1);
     const int dmax_ncc = min(D - 1, (Y >= 1 && Y < H - 2 && X >= 1 && X < W - 2) ? X - 1 : -1);
     const int dmax_sad = min(D - 1, (Y >= 2 && Y < H - 3 && X >= 2 && X < W - 3) ? X - 2 : -1);
 
-    if (kTma) mbar_wait(&s_bar[0], 0);
-    else cp_async_wait_all();
-    __syncthreads();
     // ---- phase 1: raw costs into the parking planes, per-pixel minima ----------------
     {
       const uint4* s_desc = reinterpret_cast<const uint4*>(buf + L::st_desc);
       const uint4* s_stat = reinterpret_cast<const uint4*>(buf + L::st_stat);
       const float* s_rf = reinterpret_cast<const float*>(buf + L::st_rf);
-      // shared index of right column X - d is ir = lane + kSlack + (D-1) - d; falls by one per step
-      const int XbaseP = t.x0 + g.bwl - (D - 1) - kSlack + g.padL;
+      // shared index of right column X - d is ir = lane + L::kSl + (D-1) - d; falls by one per step
+      const int XbaseP = t.x0 + g.bwl - (D - 1) - L::kSl + g.padL;
       const int shift = (XbaseP - 2) & 3;
-      const int ir0 = lane + kSlack + (D - 1) - d_lo;
+      const int ir0 = lane + L::kSl + (D - 1) - d_lo;
       const float* rfp = s_rf + shift + ir0;
       const uint4* dscp = s_desc + ir0;
       const uint4* sttp = s_stat + ir0;
@@ -516,7 +516,7 @@ ms_fused_kernel(const FusedArgs a, const __grid_constant__ CUtensorMap sad_map) 
       }
       // SAD-of-Sobel costs of this warp's disparities (delivered by TMA / cp.async while the loop
       // above ran): replace what lies outside the valid region by fill, take the minimum
-      if (kTma) mbar_wait(&s_bar[1], 0);
+      if (kTma) mbar_wait(bar_sad, sad_parity);
       {
         float* sp = s_par + PS + d_lo * 32 + lane;
 #pragma unroll 4
@@ -555,28 +555,29 @@ ms_fused_kernel(const FusedArgs a, const __grid_constant__ CUtensorMap sad_map) 
     if (warp < 4) {
       const float mm = s_min[warp * 32 + lane];
       float den = 0.f;
+      const int Dfull = D & ~7;   // groups of 8 without guards, then a guarded tail
       if (warp == 0) {
         const int mc = (mm == kFill) ? 0 : (int)mm;
         const uint8_t* c = s_cen + lane;
-        for (int d0 = 0; d0 < D; d0 += 8) {
+        for (int d0 = 0; d0 < Dfull; d0 += 8, c += 8 * 32) {
           float ev[8];
 #pragma unroll
-          for (int j = 0; j < 8; ++j) ev[j] = (d0 + j < D) ? s_lut[min((int)c[j * 32] - mc, 127)] : 0.f;
+          for (int j = 0; j < 8; ++j) ev[j] = s_lut[min((int)c[j * 32] - mc, 127)];
 #pragma unroll
-          for (int j = 0; j < 8; ++j) den = __fadd_rn(den, ev[j]);  // + 0.0f past D is exact
-          c += 8 * 32;
+          for (int j = 0; j < 8; ++j) den = __fadd_rn(den, ev[j]);
         }
+        for (int d = Dfull; d < D; ++d, c += 32) den = __fadd_rn(den, s_lut[min((int)c[0] - mc, 127)]);
       } else {
         const float kq = (warp == 1) ? a.k_ncc : a.k_sad;
         const float* e = s_par + (warp - 1) * PS + lane;
-        for (int d0 = 0; d0 < D; d0 += 8) {
+        for (int d0 = 0; d0 < Dfull; d0 += 8, e += 8 * 32) {
           float ev[8];
 #pragma unroll
-          for (int j = 0; j < 8; ++j) ev[j] = (d0 + j < D) ? aml_e(e[j * 32], mm, kq) : 0.f;
+          for (int j = 0; j < 8; ++j) ev[j] = aml_e(e[j * 32], mm, kq);
 #pragma unroll
           for (int j = 0; j < 8; ++j) den = __fadd_rn(den, ev[j]);
-          e += 8 * 32;
         }
+        for (int d = Dfull; d < D; ++d, e += 32) den = __fadd_rn(den, aml_e(e[0], mm, kq));
       }
       s_inv[warp * 32 + lane] = (mm == kFill) ? 0.f : 1.0f / den;
     } else {
@@ -663,6 +664,118 @@ ms_fused_kernel(const FusedArgs a, const __grid_constant__ CUtensorMap sad_map) 
         }
       }
     }
+
+  }
+}
+
+// One CTA per tile.
+// kTma: right-image rows and the SAD-of-Sobel tile arrive through cp.async.bulk /
+// cp.async.bulk.tensor (D <= 256: box limit); otherwise through LDGSTS.  The tensor copy's
+// inner coordinate must be a multiple of 16 bytes (measured: anything else raises an
+// illegal-instruction fault), which is why the scratch is stored with column offset sxo.
+template <int DMAX, bool kTma>
+__global__ void __launch_bounds__(kWarps * 32, 2)
+ms_fused_kernel(const FusedArgs a, const __grid_constant__ CUtensorMap sad_map) {
+  using L = Lay<DMAX>;
+  extern __shared__ __align__(128) unsigned char smem_raw[];  // TMA destinations need 128 B
+  const FusedGeom& g = a.g;
+  const int D = g.D;
+  unsigned long long* s_bar = reinterpret_cast<unsigned long long*>(smem_raw + L::off_bar);  // [0] rows, [1] sadsob tile
+  float* s_lut = reinterpret_cast<float*>(smem_raw + L::off_lut);
+  float* s_par = reinterpret_cast<float*>(smem_raw + L::off_par);
+  constexpr int PS = L::DS * 32;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const TileId t = decode_tile(blockIdx.x, a);
+  unsigned char* buf = smem_raw + L::off_stage;
+  if (kTma) {
+    if (threadIdx.x == 0) {
+      mbar_init(&s_bar[0], 1);
+      mbar_init(&s_bar[1], 1);
+      stage_sad_tma(a, &sad_map, t, s_par + PS, &s_bar[1]);
+      stage_rows_tma<L>(a, t, buf, &s_bar[0], false);
+    }
+  } else {
+    // sadsob costs of this lane's own disparities: async global -> parked plane 1
+    const int d_lo = warp * a.DC, d_end = min(D, d_lo + a.DC);
+    const size_t splane = (size_t)g.H * g.Ws;
+    const float* src = a.sadsob + ((size_t)t.n * D * g.H + (t.y + g.bh)) * g.Ws + (t.x0 + lane + g.bwl + g.sxo) +
+                       (size_t)d_lo * splane;
+    float* dst = s_par + PS + d_lo * 32 + lane;
+    for (int d = d_lo; d < d_end; ++d, src += splane, dst += 32) cp_async4(dst, src);
+    stage_right<L>(a, t, buf);
+  }
+  if (threadIdx.x < 128) {
+    const int kk = threadIdx.x;
+    s_lut[kk] = (kk <= 120) ? ex2_approx(-(float)(kk * kk) * a.k_cen) : 0.f;
+  }
+  LeftRegs lr;
+  load_left(a, t, lane, lr);
+  __syncthreads();                       // barrier init + LUT visible to everyone
+  if (kTma) mbar_wait(&s_bar[0], 0);
+  else {
+    cp_async_wait_all();
+    __syncthreads();
+  }
+  tile_compute<L, kTma>(a, smem_raw, t, buf, lr, &s_bar[1], 0);
+}
+
+// Persistent variant (TMA only): gridDim.x resident CTAs walk the tiles with stride gridDim.x;
+// while a tile is in phase 1 the TMA engine already fetches the next tile's right-image rows
+// and left-pixel data into the other staging buffer.  Selected with MSNETS_FUSED_PERSISTENT=1.
+template <int DMAX, int SLACK>
+__global__ void __launch_bounds__(kWarps * 32, 2)
+ms_fused_persistent_kernel(const FusedArgs a, const __grid_constant__ CUtensorMap sad_map) {
+  using L = Lay<DMAX, SLACK, 2>;
+  extern __shared__ __align__(128) unsigned char smem_raw[];
+  unsigned long long* s_bar = reinterpret_cast<unsigned long long*>(smem_raw + L::off_bar);  // [0],[1] rows per buffer, [2] sadsob
+  float* s_lut = reinterpret_cast<float*>(smem_raw + L::off_lut);
+  float* s_par = reinterpret_cast<float*>(smem_raw + L::off_par);
+  constexpr int PS = L::DS * 32;
+  const int lane = threadIdx.x & 31;
+  int tile = blockIdx.x;
+  if (tile >= a.num_tiles) return;
+  TileId t = decode_tile(tile, a);
+  if (a.stagger_ns > 0.f) {
+    // desynchronise the resident CTAs: pseudo-random start offset within one tile period
+    const unsigned frac = (blockIdx.x * 2654435761u) >> 26;            // 0..63
+    unsigned ns = (unsigned)(a.stagger_ns * (frac / 64.0f));
+    while (ns > 0) {
+      const unsigned step = ns > 50000u ? 50000u : ns;
+      __nanosleep(step);
+      ns -= step;
+    }
+  }
+  if (threadIdx.x == 0) {
+    mbar_init(&s_bar[0], 1);
+    mbar_init(&s_bar[1], 1);
+    mbar_init(&s_bar[2], 1);
+    stage_rows_tma<L>(a, t, smem_raw + L::off_stage, &s_bar[0], true);
+  }
+  if (threadIdx.x < 128) {
+    const int kk = threadIdx.x;
+    s_lut[kk] = (kk <= 120) ? ex2_approx(-(float)(kk * kk) * a.k_cen) : 0.f;
+  }
+  __syncthreads();
+  for (int it = 0; tile < a.num_tiles; ++it, tile += gridDim.x) {
+    const int b = it & 1;
+    unsigned char* buf = smem_raw + L::off_stage + (size_t)b * L::st_bytes;
+    const int next = tile + gridDim.x;
+    TileId tn = t;
+    if (threadIdx.x == 0) {
+      // this tile's SAD-of-Sobel costs (the parking planes are free: end-of-tile barrier below)
+      stage_sad_tma(a, &sad_map, t, s_par + PS, &s_bar[2]);
+      // next tile's rows into the other buffer (last read during the previous tile's phase 1)
+      if (next < a.num_tiles) {
+        tn = decode_tile(next, a);
+        stage_rows_tma<L>(a, tn, smem_raw + L::off_stage + (size_t)(b ^ 1) * L::st_bytes, &s_bar[b ^ 1], true);
+      }
+    }
+    mbar_wait(&s_bar[b], (it >> 1) & 1);
+    LeftRegs lr;
+    load_left_smem<L>(a, t, buf, lane, lr);
+    tile_compute<L, true>(a, smem_raw, t, buf, lr, &s_bar[2], it & 1);
+    __syncthreads();  // parking planes, minima and staging buffer b are free again
+    if (next < a.num_tiles) t = decode_tile(next, a);
   }
 }
 
@@ -689,6 +802,10 @@ static PFN_encodeTiled get_encode_fn() {
     return (PFN_encodeTiled)p;
   }();
   return fn;
+}
+static bool persistent_enabled() {
+  const char* e = getenv("MSNETS_FUSED_PERSISTENT");
+  return e && e[0] == '1';
 }
 static bool tma_disabled() {
   const char* e = getenv("MSNETS_NO_TMA");
@@ -778,6 +895,10 @@ int launch_ms_fused(const uint8_t* d_left, const uint8_t* d_right, int N, int H,
   const long long tiles = (long long)N * g.h * a.tiles_x;
   MSN_REQUIRE(tiles <= 2147483647LL, "ms_features: too many tiles for one launch");
   a.num_tiles = (int)tiles;
+  {
+    const char* e = getenv("MSNETS_FUSED_STAGGER_NS");
+    a.stagger_ns = e ? (float)atof(e) : 0.f;
+  }
   // TMA path: 3-D tensor map over the SAD-of-Sobel scratch [N*D][H][W], box 32 x 1 x D
   CUtensorMap sad_map;
   memset(&sad_map, 0, sizeof(sad_map));
@@ -796,6 +917,35 @@ int launch_ms_fused(const uint8_t* d_left, const uint8_t* d_right, int N, int H,
                               CU_TENSOR_MAP_L2_PROMOTION_NONE, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
       if (rc != CUDA_SUCCESS) use_tma = false;
     }
+  }
+  // experimental persistent variant (MSNETS_FUSED_PERSISTENT=1): needs TMA and at most 8 dummy steps
+  if (use_tma && persistent_enabled() && 8 * a.DC - g.D <= 8 && g.D <= 192) {
+    int dev = 0, sms = 0;
+    MSN_CUDA_OK(cudaGetDevice(&dev));
+    MSN_CUDA_OK(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
+#define MSN_PERSIST_CASE(DMAX)                                                                        \
+  if (g.D <= DMAX) {                                                                                  \
+    const size_t smem = Lay<DMAX, 8, 2>::bytes;                                                       \
+    MSN_CUDA_OK(cudaFuncSetAttribute(ms_fused_persistent_kernel<DMAX, 8>,                             \
+                                     cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));        \
+    int per_sm = 0;                                                                                   \
+    MSN_CUDA_OK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, ms_fused_persistent_kernel<DMAX, 8>, \
+                                                              kWarps * 32, smem));                    \
+    MSN_REQUIRE(per_sm >= 1, "ms_features: persistent kernel does not fit");                          \
+    const long long grid = (long long)per_sm * sms < tiles ? (long long)per_sm * sms : tiles;         \
+    ms_fused_persistent_kernel<DMAX, 8><<<(unsigned)grid, kWarps * 32, smem, s>>>(a, sad_map);        \
+  } else
+    MSN_PERSIST_CASE(64)
+    MSN_PERSIST_CASE(128)
+    MSN_PERSIST_CASE(192) {}
+#undef MSN_PERSIST_CASE
+    MSN_LAUNCH_OK();
+    if (prof) {
+      MSN_CUDA_OK(cudaEventRecord(rec.ev[3], s));
+      std::lock_guard<std::mutex> lk(g_prof_mu);
+      g_prof.push_back(rec);
+    }
+    return 0;
   }
 #define MSN_FUSED_LAUNCH(DMAX, TMA)                                                                   \
   {                                                                                                   \
