@@ -44,8 +44,9 @@ namespace msn {
 
 namespace {
 
-constexpr int kWarps = 8;
-constexpr int kTile = 32;     // pixels per CTA
+constexpr int kTileMax = 32;  // widest tile (pixels per CTA) the geometry allows for
+constexpr int kGroups = 8;    // d-groups per tile: every thread of phase 1 owns (pixel, d-group)
+constexpr int kSlack = 56;    // right-image columns left of X-(D-1) that dummy steps (d >= D) may read: 8*DC - D <= 47, + pair halo
 constexpr int kPadT = 2;      // padded rows above/below (ZSAD halo)
 constexpr int kPadR = 40;     // padded columns to the right (tile overhang + halo)
 constexpr int kCensW = 11, kNccW = 3, kSadW = 5;
@@ -70,11 +71,11 @@ FusedGeom make_geom(int N, int H, int W, const msn_ms_params* p) {
   g.bh = p->board_h; g.bwl = p->board_w_left;
   g.h = H - 2 * p->board_h;
   g.w = W - p->board_w_left - p->board_w_right;
-  g.padL = (g.D + 1 + 40 + 8 + 7) & ~7;  // D-1 columns of disparity + dummy-step slack (kSlack) + halo/alignment
+  g.padL = (g.D + 1 + kSlack + 8 + 7) & ~7;  // D-1 columns of disparity + dummy-step slack + halo/alignment
   g.Hp = H + 2 * kPadT;
   g.Wp = (W + g.padL + kPadR + 3) & ~3;
   g.sxo = (4 - (g.bwl & 3)) & 3;            // x0 + bwl + sxo is a multiple of 4 for every tile
-  g.Ws = sadsob_fast_pitch(W + g.sxo + kTile);  // compile-time pitch of the scan kernels (0: too wide)
+  g.Ws = sadsob_fast_pitch(W + g.sxo + kTileMax);  // compile-time pitch of the scan kernels (0: too wide)
   return g;
 }
 
@@ -185,58 +186,46 @@ struct FusedArgs {
   const uint4 *descL, *descR;
   const RStat *statL, *statR;
   const float *fL, *fR;
-  const float* sadsob;  // [N][D][H][W] (+ slack)
+  const float* sadsob;  // [N][D][H][Ws] (+ slack)
   float* out;           // [N][8][D][h][w]
   float k_cen, k_ncc, k_sad;
-  int DC;               // disparity steps per warp (multiple of 5)
+  int DC;               // disparity steps per d-group (multiple of 6)
   int tiles_x;
-  int num_tiles;
-  float stagger_ns;     // persistent kernel: CTA start offsets are drawn from [0, stagger_ns)
 };
 
-// Shared-memory layout for disparity counts up to DMAX.  Row strides are compile-time
-// so every shared access in the hot loop is "pointer + immediate".
-//   SLACK : right-image entries below index 0 reached by dummy steps (d >= D); 8*DC - D of them
-//   NBUF  : staging buffers (1: one tile per CTA; 2: persistent CTA, next tile prefetched)
-constexpr int kSlack = 40;  // enough for every D (see make_geom: padL covers it)
-template <int DMAX, int SLACK = kSlack, int NBUF = 1>
+
+// Shared-memory layout of one tile of TILE pixels x all disparities (up to DMAX).  Row strides
+// are compile-time so every shared access in the hot loops is "pointer + immediate".
+//   region 0 : staging (right-image census codes, stats, 5 float rows) + per-group minima during
+//              phase 1; afterwards the SAME bytes hold the census AML exponentials [DS][TILE]
+//   parking  : [3][DS][TILE] floats (ncc, sadsob, zsad) + [DS][TILE] census bytes
+template <int DMAX, int TILE, int SLACK>
 struct Lay {
   static constexpr int kSl = SLACK;
-  static constexpr int RW = (DMAX + kTile - 1 + SLACK + 3) & ~3;   // desc / stat entries
-  static constexpr int RWF = RW + 8;                               // float row: halo 2+2, align shift <= 3
-  static constexpr int LF = 40;                                    // left float row: 32 + halo 4, shift <= 3
-  static constexpr int DS = DMAX + 1;                              // parked planes + 1 scratch plane
-  // one staging buffer: right-image row data of a tile (+ the 32 left pixels' data when the
-  // persistent kernel prefetches them through TMA as well)
+  static constexpr int RW = (DMAX + TILE - 1 + SLACK + 3) & ~3;   // desc / stat entries
+  static constexpr int RWF = RW + 8;                              // float row: halo 2+2, align shift <= 3
+  // parked planes + 1 scratch plane (dummy steps); even for 16-pixel tiles so that every plane
+  // starts on a 128-byte boundary (plane 1 is a TMA destination)
+  static constexpr int DS = (TILE >= 32) ? DMAX + 1 : ((DMAX + 2) & ~1);
   static constexpr size_t st_desc = 0;
   static constexpr size_t st_stat = st_desc + (size_t)RW * 16;
   static constexpr size_t st_rf = st_stat + (size_t)RW * 16;
-  static constexpr size_t st_ldesc = st_rf + (size_t)5 * RWF * 4;
-  static constexpr size_t st_lstat = st_ldesc + (NBUF > 1 ? kTile * 16 : 0);
-  static constexpr size_t st_lf = st_lstat + (NBUF > 1 ? kTile * 16 : 0);
-  static constexpr size_t st_bytes = st_lf + (NBUF > 1 ? 5 * LF * 4 : 0);
-  static constexpr size_t off_stage = 0;
-  static constexpr size_t off_red = off_stage + NBUF * st_bytes;              // [8][4][32]
-  static constexpr size_t off_min = off_red + (size_t)kWarps * 4 * 32 * 4;   // [4][32]
-  static constexpr size_t off_inv = off_min + 4 * 32 * 4;                    // [4][32]
-  static constexpr size_t off_lut = off_inv + 4 * 32 * 4;                    // [128]
-  static constexpr size_t off_par = (off_lut + 128 * 4 + 127) & ~(size_t)127;  // [3][DS][32] ncc, sadsob, zsad (128 B aligned: TMA destination)
-  static constexpr size_t off_cen = off_par + (size_t)3 * DS * 32 * 4;       // [DS][32] bytes
-  static constexpr size_t off_bar = (off_cen + (size_t)DS * 32 + 15) & ~(size_t)15;  // mbarriers (8 B each)
+  static constexpr size_t st_mean = st_rf + (size_t)5 * RWF * 4;       // [2][RW + 4] ZSAD means, copy 1 shifted by one
+  static constexpr size_t st_bytes = st_mean + (size_t)2 * (RW + 4) * 4;
+  static constexpr size_t off_red = st_bytes;                                     // [kGroups][4][TILE]
+  static constexpr size_t r0_a = off_red + (size_t)kGroups * 4 * TILE * 4;
+  static constexpr size_t r0_b = (size_t)DS * TILE * 4;                            // census exponentials
+  static constexpr size_t off_cene = 0;
+  static constexpr size_t off_min = ((r0_a > r0_b ? r0_a : r0_b) + 15) & ~(size_t)15;  // [4][TILE]
+  static constexpr size_t off_inv = off_min + 4 * TILE * 4;                       // [4][TILE]
+  static constexpr size_t off_lut = off_inv + 4 * TILE * 4;                       // [128] census AML exponentials
+  static constexpr size_t off_lutn = off_lut + 128 * 4;                           // [256] census byte -> channel 0
+  static constexpr size_t off_par = (off_lutn + 256 * 4 + 127) & ~(size_t)127;    // 128 B aligned: TMA destination
+  static constexpr size_t off_cen = off_par + (size_t)3 * DS * TILE * 4;          // [DS][TILE] bytes
+  static constexpr size_t off_bar = (off_cen + (size_t)DS * TILE + 15) & ~(size_t)15;  // mbarriers (8 B each)
   static constexpr size_t bytes = off_bar + 32;
 };
 
-__device__ __forceinline__ float int_to_float_small(int c) {  // exact for 0 <= c < 2^23
-  return __uint_as_float(0x4B000000u | (uint32_t)c) - 8388608.0f;
-}
-// c / 120 correctly rounded for integer c in [0,120] (exhaustively checked in
-// tests/test_host_math.py): reciprocal multiply + one FMA residual correction.
-__device__ __forceinline__ float div120_exact(float cf) {
-  const float r = 1.0f / 120.0f;
-  float q = __fmul_rn(cf, r);
-  const float rem = __fmaf_rn(-120.0f, q, cf);
-  return __fmaf_rn(rem, r, q);
-}
 __device__ __forceinline__ void cp_async4(void* smem_dst, const void* gmem_src) {
   const uint32_t d = (uint32_t)__cvta_generic_to_shared(smem_dst);
   asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(d), "l"(gmem_src) : "memory");
@@ -280,28 +269,55 @@ __device__ __forceinline__ void tma_load_3d(void* dst, const CUtensorMap* map, i
 
 __device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_all;" ::: "memory"); }
 
+// ---- packed fp32x2 arithmetic (Blackwell FADD2: two IEEE round-to-nearest adds per issue slot;
+//      operand B may be a scalar register broadcast to both halves, |x| is an operand modifier)
+typedef unsigned long long f32x2;
+__device__ __forceinline__ f32x2 pk2(float lo, float hi) {
+  f32x2 r;
+  asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(lo), "f"(hi));
+  return r;
+}
+__device__ __forceinline__ void upk2(f32x2 v, float& lo, float& hi) {
+  asm("mov.b64 {%0, %1}, %2;" : "=f"(lo), "=f"(hi) : "l"(v));
+}
+__device__ __forceinline__ f32x2 add2(f32x2 a, f32x2 b) {
+  f32x2 r;
+  asm("add.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b));
+  return r;
+}
+__device__ __forceinline__ f32x2 sub2(f32x2 a, f32x2 b) {
+  f32x2 r;
+  asm("sub.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b));
+  return r;
+}
+__device__ __forceinline__ f32x2 abs2(f32x2 v) {
+  float lo, hi;
+  upk2(v, lo, hi);
+  return pk2(fabsf(lo), fabsf(hi));
+}
+
 struct TileId {
   int n, y, x0;
 };
+template <int TILE>
 __device__ __forceinline__ TileId decode_tile(int tile, const FusedArgs& a) {
   TileId t;
   const int xt = tile % a.tiles_x;
   tile /= a.tiles_x;
   t.y = tile % a.g.h;
   t.n = tile / a.g.h;
-  t.x0 = xt * kTile;
+  t.x0 = xt * TILE;
   return t;
 }
 
-// Asynchronously copies the right-image row data of `t` into one staging buffer:
-// census codes and stats of the D+31(+slack) columns the tile can touch and the five
-// float rows of the ZSAD/NCC windows (16-byte cp.async; the float rows start at a
-// 4-float aligned column, the 0..3 float shift is returned through *shift).
-template <class L>
+// Asynchronously copies the right-image row data of `t` into the staging buffer with LDGSTS:
+// census codes and stats of the D+TILE-1(+slack) columns the tile can touch and the five float
+// rows of the ZSAD/NCC windows (the float rows start at a 4-float aligned column).
+template <class L, int TILE, int NT>
 __device__ __forceinline__ void stage_right(const FusedArgs& a, const TileId& t, unsigned char* buf) {
   const FusedGeom& g = a.g;
   const int D = g.D;
-  const int RWn = D + kTile - 1 + L::kSl;
+  const int RWn = D + TILE - 1 + L::kSl;
   const int XbaseP = t.x0 + g.bwl - (D - 1) - L::kSl + g.padL;
   const int Yp = t.y + g.bh + kPadT;
   const size_t img_off = (size_t)t.n * g.img_px();
@@ -310,70 +326,61 @@ __device__ __forceinline__ void stage_right(const FusedArgs& a, const TileId& t,
   uint4* s_desc = reinterpret_cast<uint4*>(buf + L::st_desc);
   uint4* s_stat = reinterpret_cast<uint4*>(buf + L::st_stat);
   float* s_rf = reinterpret_cast<float*>(buf + L::st_rf);
-  for (int i = threadIdx.x; i < RWn; i += kWarps * 32) {
+  for (int i = threadIdx.x; i < RWn; i += NT) {
     cp_async16(s_desc + i, gd + i);
     cp_async16(s_stat + i, gs + i);
   }
   const int fstart = (XbaseP - 2) & ~3;                 // aligned first float column
   const int nvec = (RWn + 4 + 3 + 3) >> 2;              // 16-byte groups per row (covers any shift)
-  for (int i = threadIdx.x; i < 5 * nvec; i += kWarps * 32) {
+  for (int i = threadIdx.x; i < 5 * nvec; i += NT) {
     const int r = i / nvec, v = i - r * nvec;
     cp_async16(s_rf + r * L::RWF + 4 * v, a.fR + img_off + (size_t)(Yp - 2 + r) * g.Wp + fstart + 4 * v);
   }
 }
 
-// Same data through the TMA engine: seven 1-D bulk copies (plus seven tiny ones for the 32
-// left pixels when with_left), issued by a single thread, completion counted in bytes on `bar`.
-template <class L>
+// Same data through the TMA engine: seven 1-D bulk copies issued by a single thread,
+// completion counted in bytes on `bar`.
+template <class L, int TILE>
 __device__ __forceinline__ void stage_rows_tma(const FusedArgs& a, const TileId& t, unsigned char* buf,
-                                               unsigned long long* bar, bool with_left) {
+                                               unsigned long long* bar) {
   const FusedGeom& g = a.g;
   const int D = g.D;
-  const int RWn = D + kTile - 1 + L::kSl;
+  const int RWn = D + TILE - 1 + L::kSl;
   const int XbaseP = t.x0 + g.bwl - (D - 1) - L::kSl + g.padL;
   const int Yp = t.y + g.bh + kPadT;
   const size_t img_off = (size_t)t.n * g.img_px();
   const int fstart = (XbaseP - 2) & ~3;
   const int nvec = (RWn + 4 + 3 + 3) >> 2;
   const unsigned row_bytes = (unsigned)RWn * 16u, frow_bytes = (unsigned)nvec * 16u;
-  const int XpL = t.x0 + g.bwl + g.padL;                 // padded column of the tile's first left pixel
-  const int lstart = (XpL - 2) & ~3;
-  mbar_expect_tx(bar, 2u * row_bytes + 5u * frow_bytes + (with_left ? (2u * kTile * 16u + 5u * L::LF * 4u) : 0u));
+  mbar_expect_tx(bar, 2u * row_bytes + 5u * frow_bytes);
   bulk_load(buf + L::st_desc, a.descR + img_off + (size_t)Yp * g.Wp + XbaseP, row_bytes, bar);
   bulk_load(buf + L::st_stat, a.statR + img_off + (size_t)Yp * g.Wp + XbaseP, row_bytes, bar);
   float* s_rf = reinterpret_cast<float*>(buf + L::st_rf);
 #pragma unroll
   for (int r = 0; r < 5; ++r)
     bulk_load(s_rf + r * L::RWF, a.fR + img_off + (size_t)(Yp - 2 + r) * g.Wp + fstart, frow_bytes, bar);
-  if (with_left) {
-    bulk_load(buf + L::st_ldesc, a.descL + img_off + (size_t)Yp * g.Wp + XpL, kTile * 16u, bar);
-    bulk_load(buf + L::st_lstat, a.statL + img_off + (size_t)Yp * g.Wp + XpL, kTile * 16u, bar);
-    float* s_lf = reinterpret_cast<float*>(buf + L::st_lf);
-#pragma unroll
-    for (int r = 0; r < 5; ++r)
-      bulk_load(s_lf + r * L::LF, a.fL + img_off + (size_t)(Yp - 2 + r) * g.Wp + lstart, L::LF * 4u, bar);
-  }
 }
 
-// The tile's D x 32 SAD-of-Sobel costs: ONE 3-D tensor copy straight into parking plane 1.
+// The tile's D x TILE SAD-of-Sobel costs: ONE 3-D tensor copy straight into parking plane 1.
 // They come from DRAM and are only needed after phase 1, hence their own barrier.
+template <int TILE>
 __device__ __forceinline__ void stage_sad_tma(const FusedArgs& a, const CUtensorMap* sad_map, const TileId& t,
                                               float* park_plane1, unsigned long long* bar_sad) {
   const FusedGeom& g = a.g;
-  mbar_expect_tx(bar_sad, (unsigned)g.D * kTile * 4u);
+  mbar_expect_tx(bar_sad, (unsigned)g.D * TILE * 4u);
   tma_load_3d(park_plane1, sad_map, t.x0 + g.bwl + g.sxo, t.y + g.bh, t.n * g.D, bar_sad);  // inner coordinate % 4 == 0
 }
 
-// The lane's own left-image data: census code, stats, 5x5 float window.
+// A pixel's own left-image data: census code, stats, 5x5 float window.
 struct LeftRegs {
   uint4 desc;
   uint4 stat;
   float px[5][5];
 };
-__device__ __forceinline__ void load_left(const FusedArgs& a, const TileId& t, int lane, LeftRegs& lr) {
+__device__ __forceinline__ void load_left(const FusedArgs& a, const TileId& t, int px, LeftRegs& lr) {
   const FusedGeom& g = a.g;
   const int Yp = t.y + g.bh + kPadT;
-  const int Xp = t.x0 + lane + g.bwl + g.padL;
+  const int Xp = t.x0 + px + g.bwl + g.padL;
   const size_t img_off = (size_t)t.n * g.img_px();
   lr.desc = __ldg(a.descL + img_off + (size_t)Yp * g.Wp + Xp);
   lr.stat = __ldg(reinterpret_cast<const uint4*>(a.statL + img_off + (size_t)Yp * g.Wp + Xp));
@@ -385,398 +392,384 @@ __device__ __forceinline__ void load_left(const FusedArgs& a, const TileId& t, i
   }
 }
 
-// Left data from the persistent kernel's staging buffer (delivered by TMA).
-template <class L>
-__device__ __forceinline__ void load_left_smem(const FusedArgs& a, const TileId& t, const unsigned char* buf, int lane,
-                                               LeftRegs& lr) {
-  const int shift = (t.x0 + a.g.bwl + a.g.padL - 2) & 3;
-  lr.desc = reinterpret_cast<const uint4*>(buf + L::st_ldesc)[lane];
-  lr.stat = reinterpret_cast<const uint4*>(buf + L::st_lstat)[lane];
-  const float* s_lf = reinterpret_cast<const float*>(buf + L::st_lf) + shift + lane;
+// Stores four channel planes' 4-pixel row segments: 128-bit streaming stores when the rows are
+// 16 B aligned and the quad is fully inside the image (kVec), guarded scalars otherwise.
+template <bool kVec>
+__device__ __forceinline__ void store_quads(float* o, size_t chan, int nlive, const float4& c0, const float4& c1,
+                                            const float4& c2, const float4& c3) {
+  if (kVec) {
+    st_stream4(o, c0);
+    st_stream4(o + chan, c1);
+    st_stream4(o + 2 * chan, c2);
+    st_stream4(o + 3 * chan, c3);
+  } else {
+    const float cc[4][4] = {{c0.x, c0.y, c0.z, c0.w}, {c1.x, c1.y, c1.z, c1.w}, {c2.x, c2.y, c2.z, c2.w},
+                            {c3.x, c3.y, c3.z, c3.w}};
 #pragma unroll
-  for (int r = 0; r < 5; ++r)
+    for (int ch = 0; ch < 4; ++ch)
 #pragma unroll
-    for (int c = 0; c < 5; ++c) lr.px[r][c] = s_lf[r * L::LF + c];
+      for (int i = 0; i < 4; ++i)
+        if (i < nlive) st_stream(o + ch * chan + i, cc[ch][i]);
+  }
 }
 
-// Everything a tile does once its right-image rows are staged in `buf` (and every thread has
-// passed the barrier that made them visible): phases 1-3 described at the top of the file.
-// `lr` holds the lane's left-image data; the SAD-of-Sobel tile is awaited on bar_sad (TMA).
-template <class L, bool kTma>
-__device__ __forceinline__ void tile_compute(const FusedArgs& a, unsigned char* smem_raw, const TileId& t,
-                                             const unsigned char* buf, const LeftRegs& lr,
-                                             unsigned long long* bar_sad, unsigned sad_parity) {
+// Phase 2 for one thread = (pixel quad q4, disparities dl, dl+DSTEP, ...): channels 0-3
+// (cbmv_generator.py:283-287) normalised and stored; every parked cost replaced IN PLACE by its
+// AML exponential exp(-(c-m)^2/sigma) (census: looked up in s_lut and written to s_cene), so each
+// exponential is evaluated once.  fill: (fill-m)^2*k is huge -> ex2 of minus it is 0.
+template <bool kVec, int TILE, int DSTEP>
+__device__ __forceinline__ void phase2_quads(float* s_par, const uint8_t* s_cen, float* s_cene, const float* s_lut,
+                                             const float* s_lutn, const float* s_min, int PS, int q4, int dl, int D,
+                                             float* orow, size_t plane, size_t chan, int nlive, float k1, float k2) {
+  const float4 m_cen4 = *reinterpret_cast<const float4*>(s_min + q4);
+  const float4 m1 = *reinterpret_cast<const float4*>(s_min + TILE + q4);
+  const float4 m2 = *reinterpret_cast<const float4*>(s_min + 2 * TILE + q4);
+  const float4 m3 = *reinterpret_cast<const float4*>(s_min + 3 * TILE + q4);
+  const int mcx = (m_cen4.x == kFill) ? 0 : (int)m_cen4.x, mcy = (m_cen4.y == kFill) ? 0 : (int)m_cen4.y;
+  const int mcz = (m_cen4.z == kFill) ? 0 : (int)m_cen4.z, mcw = (m_cen4.w == kFill) ? 0 : (int)m_cen4.w;
+#pragma unroll 2
+  for (int d = dl; d < D; d += DSTEP) {
+    float* e0 = s_par + d * TILE + q4;
+    const uchar4 cb = *reinterpret_cast<const uchar4*>(s_cen + d * TILE + q4);
+    const float4 v1 = *reinterpret_cast<const float4*>(e0);
+    const float4 v2 = *reinterpret_cast<const float4*>(e0 + PS);
+    const float4 v3 = *reinterpret_cast<const float4*>(e0 + 2 * PS);
+    const float4 c0 = make_float4(s_lutn[cb.x], s_lutn[cb.y], s_lutn[cb.z], s_lutn[cb.w]);
+    const float4 c1 = make_float4(normalise_cost(v1.x, 1), normalise_cost(v1.y, 1), normalise_cost(v1.z, 1),
+                                  normalise_cost(v1.w, 1));
+    const float4 c2 = make_float4(normalise_cost(v2.x, 2), normalise_cost(v2.y, 2), normalise_cost(v2.z, 2),
+                                  normalise_cost(v2.w, 2));
+    const float4 c3 = make_float4(normalise_cost(v3.x, 3), normalise_cost(v3.y, 3), normalise_cost(v3.z, 3),
+                                  normalise_cost(v3.w, 3));
+    store_quads<kVec>(orow + (size_t)d * plane, chan, nlive, c0, c1, c2, c3);
+    *reinterpret_cast<float4*>(s_cene + d * TILE + q4) =
+        make_float4(s_lut[min((int)cb.x - mcx, 127)], s_lut[min((int)cb.y - mcy, 127)],
+                    s_lut[min((int)cb.z - mcz, 127)], s_lut[min((int)cb.w - mcw, 127)]);
+    *reinterpret_cast<float4*>(e0) =
+        make_float4(aml_e(v1.x, m1.x, k1), aml_e(v1.y, m1.y, k1), aml_e(v1.z, m1.z, k1), aml_e(v1.w, m1.w, k1));
+    *reinterpret_cast<float4*>(e0 + PS) =
+        make_float4(aml_e(v2.x, m2.x, k2), aml_e(v2.y, m2.y, k2), aml_e(v2.z, m2.z, k2), aml_e(v2.w, m2.w, k2));
+    *reinterpret_cast<float4*>(e0 + 2 * PS) =
+        make_float4(aml_e(v3.x, m3.x, k2), aml_e(v3.y, m3.y, k2), aml_e(v3.z, m3.z, k2), aml_e(v3.w, m3.w, k2));
+  }
+}
+
+// Phase 3: channels 4-7 = parked exponential * (1/den), 128-bit row segments.
+template <bool kVec, int TILE, int DSTEP>
+__device__ __forceinline__ void phase3_quads(const float* s_par, const float* s_cene, const float* s_inv, int PS, int q4,
+                                             int dl, int D, float* arow, size_t plane, size_t chan, int nlive) {
+  const float4 i0 = *reinterpret_cast<const float4*>(s_inv + q4);
+  const float4 i1 = *reinterpret_cast<const float4*>(s_inv + TILE + q4);
+  const float4 i2 = *reinterpret_cast<const float4*>(s_inv + 2 * TILE + q4);
+  const float4 i3 = *reinterpret_cast<const float4*>(s_inv + 3 * TILE + q4);
+#pragma unroll 2
+  for (int d = dl; d < D; d += DSTEP) {
+    const float* e0 = s_par + d * TILE + q4;
+    const float4 v0 = *reinterpret_cast<const float4*>(s_cene + d * TILE + q4);
+    const float4 v1 = *reinterpret_cast<const float4*>(e0);
+    const float4 v2 = *reinterpret_cast<const float4*>(e0 + PS);
+    const float4 v3 = *reinterpret_cast<const float4*>(e0 + 2 * PS);
+    const float4 a0 = make_float4(v0.x * i0.x, v0.y * i0.y, v0.z * i0.z, v0.w * i0.w);
+    const float4 a1 = make_float4(v1.x * i1.x, v1.y * i1.y, v1.z * i1.z, v1.w * i1.w);
+    const float4 a2 = make_float4(v2.x * i2.x, v2.y * i2.y, v2.z * i2.z, v2.w * i2.w);
+    const float4 a3 = make_float4(v3.x * i3.x, v3.y * i3.y, v3.z * i3.z, v3.w * i3.w);
+    store_quads<kVec>(arow + (size_t)d * plane, chan, nlive, a0, a1, a2, a3);
+  }
+}
+
+// One CTA per tile = (pair n, output row y, TILE consecutive x) x all D; 32*WARPS threads.
+//   phase 1  thread = (pixel, d-group): 32*WARPS/TILE = 8 d-groups split D.  Per (pixel, d):
+//            census popcount, NCC, ZSAD over a register-resident 5x5 window that slides with d;
+//            raw costs parked in shared memory (13 B/voxel); per-pixel minima.
+//   phase 2  thread = (pixel quad, d): channels 0-3 stored, costs -> AML exponentials in place.
+//   phase 2b one thread per (pixel, matcher): denominator = sequential fp32 sum over d of the
+//            parked exponentials, the reference's order (featextract.cpp:444-447; a tree sum is
+//            measurably outside the 2e-6 bound).
+//   phase 3  thread = (pixel quad, d): channels 4-7 = exponential / den.
+// kTma: right-image rows and the SAD-of-Sobel tile arrive through cp.async.bulk /
+// cp.async.bulk.tensor (D <= 256: box limit); otherwise through LDGSTS.  The tensor copy's
+// inner coordinate must be a multiple of 16 bytes (measured: anything else raises an
+// illegal-instruction fault), which is why the scratch is stored with column offset sxo.
+template <int DMAX, bool kTma, int TILE, int WARPS, int SLACK, int MINB>
+__global__ void __launch_bounds__(WARPS * 32, MINB)
+ms_fused_kernel(const FusedArgs a, const __grid_constant__ CUtensorMap sad_map) {
+  using L = Lay<DMAX, TILE, SLACK>;
+  constexpr int NT = WARPS * 32;
+  static_assert(NT / TILE == kGroups, "phase 1 needs 8 d-groups");
+  constexpr int QPR = TILE / 4;          // pixel quads per row
+  constexpr int DSTEP = NT / QPR;        // disparity stride of the quad sweeps
+  constexpr int PS = L::DS * TILE;       // floats per parked matcher
+  extern __shared__ __align__(128) unsigned char smem_raw[];  // TMA destinations need 128 B
   const FusedGeom& g = a.g;
   const int D = g.D;
-  float* s_red = reinterpret_cast<float*>(smem_raw + L::off_red);    // [8][4][32]
-  float* s_min = reinterpret_cast<float*>(smem_raw + L::off_min);    // [4][32]
-  float* s_inv = reinterpret_cast<float*>(smem_raw + L::off_inv);    // [4][32]
+  unsigned long long* s_bar = reinterpret_cast<unsigned long long*>(smem_raw + L::off_bar);  // [0] rows, [1] sadsob tile
+  float* s_red = reinterpret_cast<float*>(smem_raw + L::off_red);    // [8][4][TILE]
+  float* s_cene = reinterpret_cast<float*>(smem_raw + L::off_cene);  // [DS][TILE] (aliases staging + s_red)
+  float* s_min = reinterpret_cast<float*>(smem_raw + L::off_min);    // [4][TILE]
+  float* s_inv = reinterpret_cast<float*>(smem_raw + L::off_inv);    // [4][TILE]
   float* s_lut = reinterpret_cast<float*>(smem_raw + L::off_lut);    // [128]
-  float* s_par = reinterpret_cast<float*>(smem_raw + L::off_par);    // [3][DS][32]
-  uint8_t* s_cen = smem_raw + L::off_cen;                            // [DS][32]
-  constexpr int PS = L::DS * 32;                                     // floats per parked matcher
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  float* s_lutn = reinterpret_cast<float*>(smem_raw + L::off_lutn);  // [256]
+  float* s_par = reinterpret_cast<float*>(smem_raw + L::off_par);    // [3][DS][TILE]
+  uint8_t* s_cen = smem_raw + L::off_cen;                            // [DS][TILE]
+  const unsigned char* buf = smem_raw;
+  const int tid = threadIdx.x;
+  const int px = tid % TILE;             // phase 1: this thread's pixel ...
+  const int grp = tid / TILE;            // ... and d-group
+  const TileId t = decode_tile<TILE>(blockIdx.x, a);
+  const int d_lo = grp * a.DC;
+  const int d_end = min(D, d_lo + a.DC);  // real disparities of this thread: [d_lo, d_end)
+
+  if (kTma) {
+    if (tid == 0) {
+      mbar_init(&s_bar[0], 1);
+      mbar_init(&s_bar[1], 1);
+      stage_sad_tma<TILE>(a, &sad_map, t, s_par + PS, &s_bar[1]);
+      stage_rows_tma<L, TILE>(a, t, smem_raw, &s_bar[0]);
+    }
+  } else {
+    // sadsob costs of this thread's own disparities: async global -> parked plane 1
+    const size_t splane = (size_t)g.H * g.Ws;
+    const float* src = a.sadsob + ((size_t)t.n * D * g.H + (t.y + g.bh)) * g.Ws + (t.x0 + px + g.bwl + g.sxo) +
+                       (size_t)d_lo * splane;
+    float* dst = s_par + PS + d_lo * TILE + px;
+    for (int d = d_lo; d < d_end; ++d, src += splane, dst += TILE) cp_async4(dst, src);
+    stage_right<L, TILE, NT>(a, t, smem_raw);
+  }
+  for (int kk = tid; kk < 256; kk += NT) {
+    if (kk < 128) s_lut[kk] = (kk <= 120) ? ex2_approx(-(float)(kk * kk) * a.k_cen) : 0.f;
+    // channel 0 of a parked census byte: k/120 as a true IEEE division; 255 (no cost) -> clip(fill)/120 = 1
+    s_lutn[kk] = (kk <= 120) ? __fdiv_rn((float)kk, 120.0f) : 1.0f;
+  }
+  LeftRegs lr;
+  load_left(a, t, px, lr);
+  __syncthreads();                       // barrier init + LUTs visible to everyone
+  if (kTma) mbar_wait(&s_bar[0], 0);
+  else {
+    cp_async_wait_all();
+    __syncthreads();
+  }
+  // ZSAD means of the right image as two float arrays, the second shifted by one entry, so that
+  // the means of a disparity pair (columns X-d-1, X-d) are ONE aligned 64-bit shared load
+  {
+    const RStat* st = reinterpret_cast<const RStat*>(smem_raw + L::st_stat);
+    float* mA = reinterpret_cast<float*>(smem_raw + L::st_mean);
+    float* mB = mA + (L::RW + 4);
+    for (int i = tid; i < D + TILE - 1 + L::kSl; i += NT) {
+      const float m = st[i].mean;
+      mA[i] = m;
+      mB[i + 1] = m;
+    }
+  }
+  __syncthreads();
+
   const int H = g.H, W = g.W;
-  const int d_lo = warp * a.DC;
-  const int d_end = min(D, d_lo + a.DC);  // real disparities of this warp: [d_lo, d_end)
   const size_t plane = (size_t)g.h * g.w;
   const size_t chan = plane * D;
-  // 128-bit stores need 16-byte aligned rows
-  const bool vec_ok = ((g.w & 3) == 0) && ((reinterpret_cast<uintptr_t>(a.out) & 15) == 0);
-  // AML-phase mapping: thread = (pixel quad q, disparity lane dl); d = dl, dl+32, ...
-  const int q4 = (threadIdx.x & 7) * 4;
-  const int dl = threadIdx.x >> 3;
-  const int X = t.x0 + lane + g.bwl;      // bordered image column of this lane
+  const int X = t.x0 + px + g.bwl;        // bordered image column of this thread's pixel
   const int Y = t.y + g.bh;               // bordered image row
-  const uint4 ld = lr.desc;
-  const RStat ls = *reinterpret_cast<const RStat*>(&lr.stat);
-  float at[5][5];   // (L - mL), hoisted over all d   (matchers.cpp:503)
-  float l3[3][3];   // centre 3x3 of L as float for NCC
-#pragma unroll
-  for (int r = 0; r < 5; ++r)
-#pragma unroll
-    for (int c = 0; c < 5; ++c) {
-      at[r][c] = __fsub_rn(lr.px[r][c], ls.mean);
-      if (r >= 1 && r <= 3 && c >= 1 && c <= 3) l3[r - 1][c - 1] = lr.px[r][c];
-    }
   {
+    const uint4 ld = lr.desc;
+    const RStat ls = *reinterpret_cast<const RStat*>(&lr.stat);
+    // ZSAD evaluates disparities in pairs (dA = d, dB = d + 1) with packed FADD2, dB in the low
+    // half.  The right windows of the pair overlap: dB's is dA's shifted one column left, so with
+    // wv[r][j] = right pixel at column (X - dB - 2) + j, j = 0..5, tap c of dA reads wv[c+1] and
+    // tap c of dB reads wv[c].  Pairing tap j of dB with tap j-1 of dA gives both halves the SAME
+    // right pixel (a broadcast operand) and a constant left operand ap[r][j-1] =
+    // (L[r][j] - mL, L[r][j-1] - mL), hoisted over all d (matchers.cpp:503).  Per window row:
+    // one scalar step (dB tap 0), four packed steps, one scalar step (dA tap 4) -- each half
+    // still adds its 25 taps in row-major order, every operation an IEEE fp32 add.
+    f32x2 ap[5][4];   // ap[r][j-1] for j = 1..4
+    float l3[3][3];   // centre 3x3 of L as float for NCC
+#pragma unroll
+    for (int r = 0; r < 5; ++r) {
+      float av[5];
+#pragma unroll
+      for (int c = 0; c < 5; ++c) {
+        av[c] = __fsub_rn(lr.px[r][c], ls.mean);
+        if (r >= 1 && r <= 3 && c >= 1 && c <= 3) l3[r - 1][c - 1] = lr.px[r][c];
+      }
+#pragma unroll
+      for (int j = 1; j <= 4; ++j) ap[r][j - 1] = pk2(av[j], av[j - 1]);
+    }
     // validity: cost(y,x,d) exists iff the window origin is inside and x - wc >= d (and d < D)
     const int dmax_cen = min(D - 1, (Y >= 5 && Y < H - 6 && X >= 5 && X < W - 6) ? X - 5 : -1);
     const int dmax_ncc = min(D - 1, (Y >= 1 && Y < H - 2 && X >= 1 && X < W - 2) ? X - 1 : -1);
     const int dmax_sad = min(D - 1, (Y >= 2 && Y < H - 3 && X >= 2 && X < W - 3) ? X - 2 : -1);
 
     // ---- phase 1: raw costs into the parking planes, per-pixel minima ----------------
-    {
-      const uint4* s_desc = reinterpret_cast<const uint4*>(buf + L::st_desc);
-      const uint4* s_stat = reinterpret_cast<const uint4*>(buf + L::st_stat);
-      const float* s_rf = reinterpret_cast<const float*>(buf + L::st_rf);
-      // shared index of right column X - d is ir = lane + L::kSl + (D-1) - d; falls by one per step
-      const int XbaseP = t.x0 + g.bwl - (D - 1) - L::kSl + g.padL;
-      const int shift = (XbaseP - 2) & 3;
-      const int ir0 = lane + L::kSl + (D - 1) - d_lo;
-      const float* rfp = s_rf + shift + ir0;
-      const uint4* dscp = s_desc + ir0;
-      const uint4* sttp = s_stat + ir0;
-      float rw[5][5];  // sliding 5x5 right window; logical column c lives in rw[.][(c - s) mod 5]
+    const uint4* s_desc = reinterpret_cast<const uint4*>(buf + L::st_desc);
+    const uint4* s_stat = reinterpret_cast<const uint4*>(buf + L::st_stat);
+    const float* s_rf = reinterpret_cast<const float*>(buf + L::st_rf);
+    // shared index of right column X - d is ir = px + L::kSl + (D-1) - d; falls by one per step
+    const int XbaseP = t.x0 + g.bwl - (D - 1) - L::kSl + g.padL;
+    const int shift = (XbaseP - 2) & 3;
+    const int ir0 = px + L::kSl + (D - 1) - d_lo;
+    const float* rfp = s_rf + shift + ir0 - 1;   // column (X - dB - 2) of the pair's second disparity
+    const uint4* dscp = s_desc + ir0;
+    const uint4* sttp = s_stat + ir0;
+    // (mean[ir-1], mean[ir]) as one 8-byte aligned load: copy 0 when ir-1 is even, else copy 1 (shifted)
+    const float2* mnp = reinterpret_cast<const float2*>(
+        reinterpret_cast<const float*>(buf + L::st_mean) + (((ir0 - 1) & 1) ? (L::RW + 4) + ir0 : ir0 - 1));
+    float wv[5][6];  // sliding 5x6 right window; logical column j lives in wv[.][(j - 2*s) mod 6]
 #pragma unroll
-      for (int r = 0; r < 5; ++r)
+    for (int r = 0; r < 5; ++r)
 #pragma unroll
-        for (int c = 0; c < 5; ++c) rw[r][c] = rfp[r * L::RWF + c];
-      int min_cen = 255;
-      float min_ncc = kFill, min_sob = kFill, min_sad = kFill;
+      for (int j = 0; j < 6; ++j) wv[r][j] = rfp[r * L::RWF + j];
+    int min_cen = 255;
+    float min_ncc = kFill, min_sob = kFill, min_sad = kFill;
 
-      for (int base = 0; base < a.DC; base += 5) {
+    for (int base = 0; base < a.DC; base += 6) {
 #pragma unroll
-        for (int k = 0; k < 5; ++k) {
-          const int d = d_lo + base + k;
-          const int ds = min(d, D);  // dummy steps (d >= D) park into the scratch plane
-          float* park = s_par + ds * 32 + lane;
-          const uint4 rd = *dscp;
-          const uint4 rs_raw = *sttp;
-          const RStat rs = *reinterpret_cast<const RStat*>(&rs_raw);
+      for (int sI = 0; sI < 3; ++sI) {
+#define WV(r, j) wv[r][((j) + 12 - 2 * sI) % 6]
+        const int dA = d_lo + base + 2 * sI, dB = dA + 1;
+        const uint4 rdA = dscp[0], rdB = dscp[-1];
+        const uint4 rsA_raw = sttp[0], rsB_raw = sttp[-1];
+        const RStat rsA = *reinterpret_cast<const RStat*>(&rsA_raw);
+        const RStat rsB = *reinterpret_cast<const RStat*>(&rsB_raw);
+        const float2 mBA = *mnp;   // (mean at X - dB, mean at X - dA)
 
-          // census: Hamming distance of the packed codes (matchers.cpp:323-337)
-          const int cen = __popc(ld.x ^ rd.x) + __popc(ld.y ^ rd.y) + __popc(ld.z ^ rd.z) + __popc(ld.w ^ rd.w);
-          const int cen_b = (d <= dmax_cen) ? cen : 255;
+        // census: Hamming distance of the packed codes (matchers.cpp:323-337)
+        const int cenA = __popc(ld.x ^ rdA.x) + __popc(ld.y ^ rdA.y) + __popc(ld.z ^ rdA.z) + __popc(ld.w ^ rdA.w);
+        const int cenB = __popc(ld.x ^ rdB.x) + __popc(ld.y ^ rdB.y) + __popc(ld.z ^ rdB.z) + __popc(ld.w ^ rdB.w);
+        const int cen_bA = (dA <= dmax_cen) ? cenA : 255;
+        const int cen_bB = (dB <= dmax_cen) ? cenB : 255;
 
-          // NCC: P exact in fp32 (< 2^24); scaling in fp64 left to right (matchers.cpp:200-201)
-          float P = 0.f;
+        // NCC: P exact in fp32 (< 2^24); scaling in fp64 left to right (matchers.cpp:200-201)
+        float PA = 0.f, PB = 0.f;
 #pragma unroll
-          for (int r = 0; r < 3; ++r)
+        for (int r = 0; r < 3; ++r)
 #pragma unroll
-            for (int c = 0; c < 3; ++c) P = __fmaf_rn(l3[r][c], rw[r + 1][(c + 1 - k + 5) % 5], P);
-          const float num = __fmaf_rn(9.0f, P, -__fmul_rn(ls.A, rs.A));
-          const double tt = __dmul_rn(__dmul_rn(-(double)num, ls.C), rs.C);
-          float ncc = (float)tt;
-          ncc = (fabsf(ncc) <= 3.0e38f) ? ncc : 1.0f;  // either C was inf (flat window), :196,204
-          ncc = (d <= dmax_ncc) ? ncc : kFill;
-
-          // ZSAD: 25 taps row-major, ((L - mL) - R) + mR, sequential fp32 (matchers.cpp:499-506)
-          float z = 0.f;
-#pragma unroll
-          for (int r = 0; r < 5; ++r)
-#pragma unroll
-            for (int c = 0; c < 5; ++c) {
-              const float u = __fadd_rn(__fsub_rn(at[r][c], rw[r][(c - k + 5) % 5]), rs.mean);
-              z = __fadd_rn(z, fabsf(u));
-            }
-          z = (d <= dmax_sad) ? z : kFill;
-
-          s_cen[ds * 32 + lane] = (uint8_t)cen_b;
-          park[0] = ncc;
-          park[2 * PS] = z;
-          min_cen = min(min_cen, cen_b);
-          min_ncc = fminf(min_ncc, ncc);
-          min_sad = fminf(min_sad, z);
-          // slide the window: next step's new left column
-          --rfp; --dscp; --sttp;
-#pragma unroll
-          for (int r = 0; r < 5; ++r) rw[r][(4 - k) % 5] = rfp[r * L::RWF];
-        }
-      }
-      // SAD-of-Sobel costs of this warp's disparities (delivered by TMA / cp.async while the loop
-      // above ran): replace what lies outside the valid region by fill, take the minimum
-      if (kTma) mbar_wait(bar_sad, sad_parity);
-      {
-        float* sp = s_par + PS + d_lo * 32 + lane;
-#pragma unroll 4
-        for (int d = d_lo; d < d_end; ++d, sp += 32) {
-          float v = *sp;
-          if (d > dmax_sad) {
-            v = kFill;
-            *sp = v;
+          for (int c = 0; c < 3; ++c) {
+            PA = __fmaf_rn(l3[r][c], WV(r + 1, c + 2), PA);
+            PB = __fmaf_rn(l3[r][c], WV(r + 1, c + 1), PB);
           }
-          min_sob = fminf(min_sob, v);
-        }
-      }
-      s_red[(warp * 4 + 0) * 32 + lane] = (min_cen == 255) ? kFill : (float)min_cen;
-      s_red[(warp * 4 + 1) * 32 + lane] = min_ncc;
-      s_red[(warp * 4 + 2) * 32 + lane] = min_sob;
-      s_red[(warp * 4 + 3) * 32 + lane] = min_sad;
-    }
-    __syncthreads();
-    if (threadIdx.x < 128) {  // minima across the 8 warps
-      float v = kFill;
-#pragma unroll
-      for (int wv = 0; wv < kWarps; ++wv) v = fminf(v, s_red[wv * 128 + threadIdx.x]);
-      s_min[threadIdx.x] = v;
-    }
-    __syncthreads();
+        const float numA = __fmaf_rn(9.0f, PA, -__fmul_rn(ls.A, rsA.A));
+        const float numB = __fmaf_rn(9.0f, PB, -__fmul_rn(ls.A, rsB.A));
+        float nccA = (float)__dmul_rn(__dmul_rn(-(double)numA, ls.C), rsA.C);
+        float nccB = (float)__dmul_rn(__dmul_rn(-(double)numB, ls.C), rsB.C);
+        nccA = (fabsf(nccA) <= 3.0e38f) ? nccA : 1.0f;  // either C was inf (flat window), :196,204
+        nccB = (fabsf(nccB) <= 3.0e38f) ? nccB : 1.0f;
+        nccA = (dA <= dmax_ncc) ? nccA : kFill;
+        nccB = (dB <= dmax_ncc) ? nccB : kFill;
 
-    // ---- phase 2 (warp-specialised, the two halves run concurrently and never write the
-    //      parking planes, so there is no hazard between them):
-    //      warps 0-3  one thread per (pixel, matcher): AML denominator, exponentials
-    //                 evaluated on the fly and added in the reference's order -- sequential
-    //                 fp32 over d (featextract.cpp:444-447);
-    //      warps 4-7  thread = (pixel quad, d): channels 0-3 (cbmv_generator.py:283-287)
-    //                 normalised and stored as 128-bit row segments. -----------------------
-    float* orow = a.out + (size_t)t.n * 8 * chan + (size_t)t.y * g.w + (t.x0 + q4);
-    const int nlive = min(4, g.w - (t.x0 + q4));  // live pixels of this quad (<= 0: none)
-    if (warp < 4) {
-      const float mm = s_min[warp * 32 + lane];
-      float den = 0.f;
-      const int Dfull = D & ~7;   // groups of 8 without guards, then a guarded tail
-      if (warp == 0) {
-        const int mc = (mm == kFill) ? 0 : (int)mm;
-        const uint8_t* c = s_cen + lane;
-        for (int d0 = 0; d0 < Dfull; d0 += 8, c += 8 * 32) {
-          float ev[8];
+        // ZSAD: 25 taps row-major, ((L - mL) - R) + mR, sequential fp32 (matchers.cpp:499-506)
+        const f32x2 m2 = pk2(mBA.x, mBA.y);
+        f32x2 acc = pk2(0.f, 0.f);   // (dB, dA)
 #pragma unroll
-          for (int j = 0; j < 8; ++j) ev[j] = s_lut[min((int)c[j * 32] - mc, 127)];
+        for (int r = 0; r < 5; ++r) {
+          float a_first, a_last, dum, accA, accB;
+          upk2(ap[r][0], dum, a_first);   // L[r][0] - mL
+          upk2(ap[r][3], a_last, dum);    // L[r][4] - mL
+          upk2(acc, accB, accA);
+          accB = __fadd_rn(accB, fabsf(__fadd_rn(__fsub_rn(a_first, WV(r, 0)), mBA.x)));   // dB tap 0
+          acc = pk2(accB, accA);
 #pragma unroll
-          for (int j = 0; j < 8; ++j) den = __fadd_rn(den, ev[j]);
+          for (int j = 1; j <= 4; ++j) {
+            const float wj = WV(r, j);
+            const f32x2 u = add2(sub2(ap[r][j - 1], pk2(wj, wj)), m2);                    // dB tap j, dA tap j-1
+            acc = add2(acc, abs2(u));
+          }
+          upk2(acc, accB, accA);
+          accA = __fadd_rn(accA, fabsf(__fadd_rn(__fsub_rn(a_last, WV(r, 5)), mBA.y)));    // dA tap 4
+          acc = pk2(accB, accA);
         }
-        for (int d = Dfull; d < D; ++d, c += 32) den = __fadd_rn(den, s_lut[min((int)c[0] - mc, 127)]);
-      } else {
-        const float kq = (warp == 1) ? a.k_ncc : a.k_sad;
-        const float* e = s_par + (warp - 1) * PS + lane;
-        for (int d0 = 0; d0 < Dfull; d0 += 8, e += 8 * 32) {
-          float ev[8];
+        float zA, zB;
+        upk2(acc, zB, zA);
+        zA = (dA <= dmax_sad) ? zA : kFill;
+        zB = (dB <= dmax_sad) ? zB : kFill;
+
+        const int dsA = min(dA, D), dsB = min(dB, D);  // dummy steps (d >= D) park into the scratch plane
+        s_cen[dsA * TILE + px] = (uint8_t)cen_bA;
+        s_cen[dsB * TILE + px] = (uint8_t)cen_bB;
+        s_par[dsA * TILE + px] = nccA;
+        s_par[dsB * TILE + px] = nccB;
+        s_par[2 * PS + dsA * TILE + px] = zA;
+        s_par[2 * PS + dsB * TILE + px] = zB;
+        min_cen = min(min_cen, min(cen_bA, cen_bB));
+        min_ncc = fminf(min_ncc, fminf(nccA, nccB));
+        min_sad = fminf(min_sad, fminf(zA, zB));
+        // slide the window two columns left: the next pair's new columns 0 and 1
+        rfp -= 2; dscp -= 2; sttp -= 2; mnp -= 1;
 #pragma unroll
-          for (int j = 0; j < 8; ++j) ev[j] = aml_e(e[j * 32], mm, kq);
-#pragma unroll
-          for (int j = 0; j < 8; ++j) den = __fadd_rn(den, ev[j]);
+        for (int r = 0; r < 5; ++r) {
+          wv[r][(0 + 12 - 2 * (sI + 1)) % 6] = rfp[r * L::RWF];
+          wv[r][(1 + 12 - 2 * (sI + 1)) % 6] = rfp[r * L::RWF + 1];
         }
-        for (int d = Dfull; d < D; ++d, e += 32) den = __fadd_rn(den, aml_e(e[0], mm, kq));
-      }
-      s_inv[warp * 32 + lane] = (mm == kFill) ? 0.f : 1.0f / den;
-    } else {
-      for (int d = dl - 16; d < D; d += 16) {   // dl in [16,32) for warps 4-7
-        const float* e0 = s_par + d * 32 + q4;
-        const uchar4 cb = *reinterpret_cast<const uchar4*>(s_cen + d * 32 + q4);
-        float4 c0;
-        c0.x = (cb.x == 255) ? 1.0f : div120_exact(int_to_float_small(cb.x));
-        c0.y = (cb.y == 255) ? 1.0f : div120_exact(int_to_float_small(cb.y));
-        c0.z = (cb.z == 255) ? 1.0f : div120_exact(int_to_float_small(cb.z));
-        c0.w = (cb.w == 255) ? 1.0f : div120_exact(int_to_float_small(cb.w));
-        const float4 v1 = *reinterpret_cast<const float4*>(e0);
-        const float4 v2 = *reinterpret_cast<const float4*>(e0 + PS);
-        const float4 v3 = *reinterpret_cast<const float4*>(e0 + 2 * PS);
-        const float4 c1 = make_float4(normalise_cost(v1.x, 1), normalise_cost(v1.y, 1), normalise_cost(v1.z, 1),
-                                      normalise_cost(v1.w, 1));
-        const float4 c2 = make_float4(normalise_cost(v2.x, 2), normalise_cost(v2.y, 2), normalise_cost(v2.z, 2),
-                                      normalise_cost(v2.w, 2));
-        const float4 c3 = make_float4(normalise_cost(v3.x, 3), normalise_cost(v3.y, 3), normalise_cost(v3.z, 3),
-                                      normalise_cost(v3.w, 3));
-        float* o = orow + (size_t)d * plane;
-        if (vec_ok && nlive == 4) {
-          st_stream4(o, c0);
-          st_stream4(o + chan, c1);
-          st_stream4(o + 2 * chan, c2);
-          st_stream4(o + 3 * chan, c3);
-        } else {
-          const float cc[4][4] = {{c0.x, c0.y, c0.z, c0.w}, {c1.x, c1.y, c1.z, c1.w}, {c2.x, c2.y, c2.z, c2.w},
-                                  {c3.x, c3.y, c3.z, c3.w}};
-#pragma unroll
-          for (int ch = 0; ch < 4; ++ch)
-#pragma unroll
-            for (int i = 0; i < 4; ++i)
-              if (i < nlive) st_stream(o + ch * chan + i, cc[ch][i]);
-        }
+#undef WV
       }
     }
-    __syncthreads();
-
-    // ---- phase 3: channels 4-7 = exp(-(c-m)^2/sigma) / den, 128-bit row segments --------
+    // SAD-of-Sobel costs of this thread's disparities (delivered by TMA / cp.async while the loop
+    // above ran): replace what lies outside the valid region by fill, take the minimum
+    if (kTma) mbar_wait(&s_bar[1], 0);
     {
-      const float4 m_cen4 = *reinterpret_cast<const float4*>(s_min + q4);
-      const float4 m_ncc4 = *reinterpret_cast<const float4*>(s_min + 32 + q4);
-      const float4 m_sob4 = *reinterpret_cast<const float4*>(s_min + 64 + q4);
-      const float4 m_sad4 = *reinterpret_cast<const float4*>(s_min + 96 + q4);
-      const float4 i0 = *reinterpret_cast<const float4*>(s_inv + q4);
-      const float4 i1 = *reinterpret_cast<const float4*>(s_inv + 32 + q4);
-      const float4 i2 = *reinterpret_cast<const float4*>(s_inv + 64 + q4);
-      const float4 i3 = *reinterpret_cast<const float4*>(s_inv + 96 + q4);
-      const int mcx = (m_cen4.x == kFill) ? 0 : (int)m_cen4.x, mcy = (m_cen4.y == kFill) ? 0 : (int)m_cen4.y;
-      const int mcz = (m_cen4.z == kFill) ? 0 : (int)m_cen4.z, mcw = (m_cen4.w == kFill) ? 0 : (int)m_cen4.w;
-      float* arow = orow + 4 * chan;
-      for (int d = dl; d < D; d += 32) {
-        const float* e0 = s_par + d * 32 + q4;
-        const uchar4 cb = *reinterpret_cast<const uchar4*>(s_cen + d * 32 + q4);
-        float4 a0;
-        a0.x = s_lut[min((int)cb.x - mcx, 127)] * i0.x;
-        a0.y = s_lut[min((int)cb.y - mcy, 127)] * i0.y;
-        a0.z = s_lut[min((int)cb.z - mcz, 127)] * i0.z;
-        a0.w = s_lut[min((int)cb.w - mcw, 127)] * i0.w;
-        const float4 v1 = *reinterpret_cast<const float4*>(e0);
-        const float4 v2 = *reinterpret_cast<const float4*>(e0 + PS);
-        const float4 v3 = *reinterpret_cast<const float4*>(e0 + 2 * PS);
-        const float4 a1 = make_float4(aml_e(v1.x, m_ncc4.x, a.k_ncc) * i1.x, aml_e(v1.y, m_ncc4.y, a.k_ncc) * i1.y,
-                                      aml_e(v1.z, m_ncc4.z, a.k_ncc) * i1.z, aml_e(v1.w, m_ncc4.w, a.k_ncc) * i1.w);
-        const float4 a2 = make_float4(aml_e(v2.x, m_sob4.x, a.k_sad) * i2.x, aml_e(v2.y, m_sob4.y, a.k_sad) * i2.y,
-                                      aml_e(v2.z, m_sob4.z, a.k_sad) * i2.z, aml_e(v2.w, m_sob4.w, a.k_sad) * i2.w);
-        const float4 a3 = make_float4(aml_e(v3.x, m_sad4.x, a.k_sad) * i3.x, aml_e(v3.y, m_sad4.y, a.k_sad) * i3.y,
-                                      aml_e(v3.z, m_sad4.z, a.k_sad) * i3.z, aml_e(v3.w, m_sad4.w, a.k_sad) * i3.w);
-        float* o = arow + (size_t)d * plane;
-        if (vec_ok && nlive == 4) {
-          st_stream4(o, a0);
-          st_stream4(o + chan, a1);
-          st_stream4(o + 2 * chan, a2);
-          st_stream4(o + 3 * chan, a3);
-        } else {
-          const float cc[4][4] = {{a0.x, a0.y, a0.z, a0.w}, {a1.x, a1.y, a1.z, a1.w}, {a2.x, a2.y, a2.z, a2.w},
-                                  {a3.x, a3.y, a3.z, a3.w}};
-#pragma unroll
-          for (int ch = 0; ch < 4; ++ch)
-#pragma unroll
-            for (int i = 0; i < 4; ++i)
-              if (i < nlive) st_stream(o + ch * chan + i, cc[ch][i]);
+      float* sp = s_par + PS + d_lo * TILE + px;
+#pragma unroll 4
+      for (int d = d_lo; d < d_end; ++d, sp += TILE) {
+        float v = *sp;
+        if (d > dmax_sad) {
+          v = kFill;
+          *sp = v;
         }
+        min_sob = fminf(min_sob, v);
       }
     }
-
-  }
-}
-
-// One CTA per tile.
-// kTma: right-image rows and the SAD-of-Sobel tile arrive through cp.async.bulk /
-// cp.async.bulk.tensor (D <= 256: box limit); otherwise through LDGSTS.  The tensor copy's
-// inner coordinate must be a multiple of 16 bytes (measured: anything else raises an
-// illegal-instruction fault), which is why the scratch is stored with column offset sxo.
-template <int DMAX, bool kTma>
-__global__ void __launch_bounds__(kWarps * 32, 2)
-ms_fused_kernel(const FusedArgs a, const __grid_constant__ CUtensorMap sad_map) {
-  using L = Lay<DMAX>;
-  extern __shared__ __align__(128) unsigned char smem_raw[];  // TMA destinations need 128 B
-  const FusedGeom& g = a.g;
-  const int D = g.D;
-  unsigned long long* s_bar = reinterpret_cast<unsigned long long*>(smem_raw + L::off_bar);  // [0] rows, [1] sadsob tile
-  float* s_lut = reinterpret_cast<float*>(smem_raw + L::off_lut);
-  float* s_par = reinterpret_cast<float*>(smem_raw + L::off_par);
-  constexpr int PS = L::DS * 32;
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const TileId t = decode_tile(blockIdx.x, a);
-  unsigned char* buf = smem_raw + L::off_stage;
-  if (kTma) {
-    if (threadIdx.x == 0) {
-      mbar_init(&s_bar[0], 1);
-      mbar_init(&s_bar[1], 1);
-      stage_sad_tma(a, &sad_map, t, s_par + PS, &s_bar[1]);
-      stage_rows_tma<L>(a, t, buf, &s_bar[0], false);
-    }
-  } else {
-    // sadsob costs of this lane's own disparities: async global -> parked plane 1
-    const int d_lo = warp * a.DC, d_end = min(D, d_lo + a.DC);
-    const size_t splane = (size_t)g.H * g.Ws;
-    const float* src = a.sadsob + ((size_t)t.n * D * g.H + (t.y + g.bh)) * g.Ws + (t.x0 + lane + g.bwl + g.sxo) +
-                       (size_t)d_lo * splane;
-    float* dst = s_par + PS + d_lo * 32 + lane;
-    for (int d = d_lo; d < d_end; ++d, src += splane, dst += 32) cp_async4(dst, src);
-    stage_right<L>(a, t, buf);
-  }
-  if (threadIdx.x < 128) {
-    const int kk = threadIdx.x;
-    s_lut[kk] = (kk <= 120) ? ex2_approx(-(float)(kk * kk) * a.k_cen) : 0.f;
-  }
-  LeftRegs lr;
-  load_left(a, t, lane, lr);
-  __syncthreads();                       // barrier init + LUT visible to everyone
-  if (kTma) mbar_wait(&s_bar[0], 0);
-  else {
-    cp_async_wait_all();
-    __syncthreads();
-  }
-  tile_compute<L, kTma>(a, smem_raw, t, buf, lr, &s_bar[1], 0);
-}
-
-// Persistent variant (TMA only): gridDim.x resident CTAs walk the tiles with stride gridDim.x;
-// while a tile is in phase 1 the TMA engine already fetches the next tile's right-image rows
-// and left-pixel data into the other staging buffer.  Selected with MSNETS_FUSED_PERSISTENT=1.
-template <int DMAX, int SLACK>
-__global__ void __launch_bounds__(kWarps * 32, 2)
-ms_fused_persistent_kernel(const FusedArgs a, const __grid_constant__ CUtensorMap sad_map) {
-  using L = Lay<DMAX, SLACK, 2>;
-  extern __shared__ __align__(128) unsigned char smem_raw[];
-  unsigned long long* s_bar = reinterpret_cast<unsigned long long*>(smem_raw + L::off_bar);  // [0],[1] rows per buffer, [2] sadsob
-  float* s_lut = reinterpret_cast<float*>(smem_raw + L::off_lut);
-  float* s_par = reinterpret_cast<float*>(smem_raw + L::off_par);
-  constexpr int PS = L::DS * 32;
-  const int lane = threadIdx.x & 31;
-  int tile = blockIdx.x;
-  if (tile >= a.num_tiles) return;
-  TileId t = decode_tile(tile, a);
-  if (a.stagger_ns > 0.f) {
-    // desynchronise the resident CTAs: pseudo-random start offset within one tile period
-    const unsigned frac = (blockIdx.x * 2654435761u) >> 26;            // 0..63
-    unsigned ns = (unsigned)(a.stagger_ns * (frac / 64.0f));
-    while (ns > 0) {
-      const unsigned step = ns > 50000u ? 50000u : ns;
-      __nanosleep(step);
-      ns -= step;
-    }
-  }
-  if (threadIdx.x == 0) {
-    mbar_init(&s_bar[0], 1);
-    mbar_init(&s_bar[1], 1);
-    mbar_init(&s_bar[2], 1);
-    stage_rows_tma<L>(a, t, smem_raw + L::off_stage, &s_bar[0], true);
-  }
-  if (threadIdx.x < 128) {
-    const int kk = threadIdx.x;
-    s_lut[kk] = (kk <= 120) ? ex2_approx(-(float)(kk * kk) * a.k_cen) : 0.f;
+    s_red[(grp * 4 + 0) * TILE + px] = (min_cen == 255) ? kFill : (float)min_cen;
+    s_red[(grp * 4 + 1) * TILE + px] = min_ncc;
+    s_red[(grp * 4 + 2) * TILE + px] = min_sob;
+    s_red[(grp * 4 + 3) * TILE + px] = min_sad;
   }
   __syncthreads();
-  for (int it = 0; tile < a.num_tiles; ++it, tile += gridDim.x) {
-    const int b = it & 1;
-    unsigned char* buf = smem_raw + L::off_stage + (size_t)b * L::st_bytes;
-    const int next = tile + gridDim.x;
-    TileId tn = t;
-    if (threadIdx.x == 0) {
-      // this tile's SAD-of-Sobel costs (the parking planes are free: end-of-tile barrier below)
-      stage_sad_tma(a, &sad_map, t, s_par + PS, &s_bar[2]);
-      // next tile's rows into the other buffer (last read during the previous tile's phase 1)
-      if (next < a.num_tiles) {
-        tn = decode_tile(next, a);
-        stage_rows_tma<L>(a, tn, smem_raw + L::off_stage + (size_t)(b ^ 1) * L::st_bytes, &s_bar[b ^ 1], true);
-      }
-    }
-    mbar_wait(&s_bar[b], (it >> 1) & 1);
-    LeftRegs lr;
-    load_left_smem<L>(a, t, buf, lane, lr);
-    tile_compute<L, true>(a, smem_raw, t, buf, lr, &s_bar[2], it & 1);
-    __syncthreads();  // parking planes, minima and staging buffer b are free again
-    if (next < a.num_tiles) t = decode_tile(next, a);
+  if (tid < 4 * TILE) {  // minima across the 8 d-groups
+    float v = kFill;
+#pragma unroll
+    for (int gq = 0; gq < kGroups; ++gq) v = fminf(v, s_red[gq * 4 * TILE + tid]);
+    s_min[tid] = v;
   }
+  __syncthreads();   // from here on the staging buffer and s_red are dead: s_cene may overwrite them
+
+  // ---- phase 2 ----------------------------------------------------------------------------
+  const int q4 = (tid % QPR) * 4;
+  const int dl = tid / QPR;
+  // 128-bit stores need 16-byte aligned rows
+  const bool vec_ok = ((g.w & 3) == 0) && ((reinterpret_cast<uintptr_t>(a.out) & 15) == 0);
+  float* orow = a.out + (size_t)t.n * 8 * chan + (size_t)t.y * g.w + (t.x0 + q4);
+  const int nlive = min(4, g.w - (t.x0 + q4));  // live pixels of this quad (<= 0: none)
+  const bool vec = vec_ok && nlive == 4;
+  if (vec) phase2_quads<true, TILE, DSTEP>(s_par, s_cen, s_cene, s_lut, s_lutn, s_min, PS, q4, dl, D, orow, plane, chan, nlive, a.k_ncc, a.k_sad);
+  else phase2_quads<false, TILE, DSTEP>(s_par, s_cen, s_cene, s_lut, s_lutn, s_min, PS, q4, dl, D, orow, plane, chan, nlive, a.k_ncc, a.k_sad);
+  __syncthreads();
+
+  // ---- phase 2b: AML denominators, one thread per (matcher, pixel); the next eight
+  //      exponentials are loaded before the current eight are added ----------------------
+  if (tid < 4 * TILE) {
+    const int m = tid / TILE, p = tid % TILE;
+    const float mm = s_min[tid];
+    const float* e = (m == 0 ? s_cene : s_par + (m - 1) * PS) + p;
+    float den = 0.f;
+    const int Dfull = D & ~7;
+    float cur[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) cur[j] = (j < Dfull) ? e[j * TILE] : 0.f;
+    for (int d0 = 0; d0 < Dfull; d0 += 8) {
+      e += 8 * TILE;
+      const bool more = d0 + 8 < Dfull;
+      float nxt[8];
+#pragma unroll
+      for (int j = 0; j < 8; ++j) nxt[j] = more ? e[j * TILE] : 0.f;
+#pragma unroll
+      for (int j = 0; j < 8; ++j) den = __fadd_rn(den, cur[j]);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) cur[j] = nxt[j];
+    }
+    for (int d = Dfull; d < D; ++d, e += TILE) den = __fadd_rn(den, e[0]);
+    s_inv[tid] = (mm == kFill) ? 0.f : 1.0f / den;
+  }
+  __syncthreads();
+
+  // ---- phase 3 ----------------------------------------------------------------------------
+  if (vec) phase3_quads<true, TILE, DSTEP>(s_par, s_cene, s_inv, PS, q4, dl, D, orow + 4 * chan, plane, chan, nlive);
+  else phase3_quads<false, TILE, DSTEP>(s_par, s_cene, s_inv, PS, q4, dl, D, orow + 4 * chan, plane, chan, nlive);
 }
 
 // Optional per-kernel timing (msn_profile_enable): CUDA events recorded on the launch
@@ -802,10 +795,6 @@ static PFN_encodeTiled get_encode_fn() {
     return (PFN_encodeTiled)p;
   }();
   return fn;
-}
-static bool persistent_enabled() {
-  const char* e = getenv("MSNETS_FUSED_PERSISTENT");
-  return e && e[0] == '1';
 }
 static bool tma_disabled() {
   const char* e = getenv("MSNETS_NO_TMA");
@@ -890,16 +879,12 @@ int launch_ms_fused(const uint8_t* d_left, const uint8_t* d_right, int N, int H,
   a.k_cen = aml_scale(p->cens_sigma);
   a.k_ncc = aml_scale(p->ncc_sigma);
   a.k_sad = aml_scale(p->sad_sigma);
-  a.DC = 5 * (((g.D + kWarps - 1) / kWarps + 4) / 5);
-  a.tiles_x = (g.w + kTile - 1) / kTile;
+  a.DC = 6 * (((g.D + kGroups - 1) / kGroups + 5) / 6);   // phase 1 walks d in unrolled groups of 3 pairs
+  const int tile = 32;
+  a.tiles_x = (g.w + tile - 1) / tile;
   const long long tiles = (long long)N * g.h * a.tiles_x;
   MSN_REQUIRE(tiles <= 2147483647LL, "ms_features: too many tiles for one launch");
-  a.num_tiles = (int)tiles;
-  {
-    const char* e = getenv("MSNETS_FUSED_STAGGER_NS");
-    a.stagger_ns = e ? (float)atof(e) : 0.f;
-  }
-  // TMA path: 3-D tensor map over the SAD-of-Sobel scratch [N*D][H][W], box 32 x 1 x D
+  // TMA path: 3-D tensor map over the SAD-of-Sobel scratch [N*D][H][Ws], box tile x 1 x D
   CUtensorMap sad_map;
   memset(&sad_map, 0, sizeof(sad_map));
   bool use_tma = g.D <= 256 && !tma_disabled();
@@ -910,7 +895,7 @@ int launch_ms_fused(const uint8_t* d_left, const uint8_t* d_right, int N, int H,
     } else {
       const cuuint64_t gdim[3] = {(cuuint64_t)g.Ws, (cuuint64_t)H, (cuuint64_t)N * g.D};
       const cuuint64_t gstr[2] = {(cuuint64_t)g.Ws * 4, (cuuint64_t)H * g.Ws * 4};
-      const cuuint32_t box[3] = {(cuuint32_t)kTile, 1u, (cuuint32_t)g.D};
+      const cuuint32_t box[3] = {(cuuint32_t)tile, 1u, (cuuint32_t)g.D};
       const cuuint32_t estr[3] = {1u, 1u, 1u};
       const CUresult rc = enc(&sad_map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3, ws.sadsob, gdim, gstr, box, estr,
                               CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE,
@@ -918,46 +903,20 @@ int launch_ms_fused(const uint8_t* d_left, const uint8_t* d_right, int N, int H,
       if (rc != CUDA_SUCCESS) use_tma = false;
     }
   }
-  // experimental persistent variant (MSNETS_FUSED_PERSISTENT=1): needs TMA and at most 8 dummy steps
-  if (use_tma && persistent_enabled() && 8 * a.DC - g.D <= 8 && g.D <= 192) {
-    int dev = 0, sms = 0;
-    MSN_CUDA_OK(cudaGetDevice(&dev));
-    MSN_CUDA_OK(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
-#define MSN_PERSIST_CASE(DMAX)                                                                        \
-  if (g.D <= DMAX) {                                                                                  \
-    const size_t smem = Lay<DMAX, 8, 2>::bytes;                                                       \
-    MSN_CUDA_OK(cudaFuncSetAttribute(ms_fused_persistent_kernel<DMAX, 8>,                             \
-                                     cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));        \
-    int per_sm = 0;                                                                                   \
-    MSN_CUDA_OK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, ms_fused_persistent_kernel<DMAX, 8>, \
-                                                              kWarps * 32, smem));                    \
-    MSN_REQUIRE(per_sm >= 1, "ms_features: persistent kernel does not fit");                          \
-    const long long grid = (long long)per_sm * sms < tiles ? (long long)per_sm * sms : tiles;         \
-    ms_fused_persistent_kernel<DMAX, 8><<<(unsigned)grid, kWarps * 32, smem, s>>>(a, sad_map);        \
-  } else
-    MSN_PERSIST_CASE(64)
-    MSN_PERSIST_CASE(128)
-    MSN_PERSIST_CASE(192) {}
-#undef MSN_PERSIST_CASE
-    MSN_LAUNCH_OK();
-    if (prof) {
-      MSN_CUDA_OK(cudaEventRecord(rec.ev[3], s));
-      std::lock_guard<std::mutex> lk(g_prof_mu);
-      g_prof.push_back(rec);
-    }
-    return 0;
-  }
-#define MSN_FUSED_LAUNCH(DMAX, TMA)                                                                   \
+#define MSN_FUSED_LAUNCH(DMAX, TMA, TILE, WARPS, SLACK, MINB)                                         \
   {                                                                                                   \
-    const size_t smem = Lay<DMAX>::bytes;                                                             \
-    MSN_CUDA_OK(cudaFuncSetAttribute(ms_fused_kernel<DMAX, TMA>,                                      \
-                                     cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));        \
-    ms_fused_kernel<DMAX, TMA><<<(unsigned)tiles, kWarps * 32, smem, s>>>(a, sad_map);                \
+    auto kern = ms_fused_kernel<DMAX, TMA, TILE, WARPS, SLACK, MINB>;                                 \
+    const size_t smem = Lay<DMAX, TILE, SLACK>::bytes;                                                \
+    MSN_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));  \
+    MSN_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout,            \
+                                     (int)cudaSharedmemCarveoutMaxShared));                           \
+    kern<<<(unsigned)tiles, WARPS * 32, smem, s>>>(a, sad_map);                                       \
   }
+#define MSN_FUSED_TILE(DMAX, TMA) MSN_FUSED_LAUNCH(DMAX, TMA, 32, 8, kSlack, 2)
 #define MSN_FUSED_CASE(DMAX)                                                                          \
   if (g.D <= DMAX) {                                                                                  \
-    if (use_tma && DMAX <= 256) MSN_FUSED_LAUNCH(DMAX <= 256 ? DMAX : 256, true)                      \
-    else MSN_FUSED_LAUNCH(DMAX, false)                                                                \
+    if (use_tma && DMAX <= 256) MSN_FUSED_TILE(DMAX <= 256 ? DMAX : 256, true)                        \
+    else MSN_FUSED_TILE(DMAX, false)                                                                  \
   } else
   MSN_FUSED_CASE(64)
   MSN_FUSED_CASE(128)
@@ -966,6 +925,7 @@ int launch_ms_fused(const uint8_t* d_left, const uint8_t* d_right, int N, int H,
   MSN_FUSED_CASE(384)
   MSN_FUSED_CASE(448) { return fail("ms_features: D=%d exceeds the fused kernel's limit", g.D); }
 #undef MSN_FUSED_CASE
+#undef MSN_FUSED_TILE
 #undef MSN_FUSED_LAUNCH
   MSN_LAUNCH_OK();
   if (prof) {

@@ -24,18 +24,15 @@ def _round_f32(x):
     return sign * fl * q
 
 
-def test_div120_fma_refinement_is_exact():
-    """ms_fused.cu:div120_exact -- q = c*r; q += fma(-120,q,c)*r equals the IEEE quotient
-    c/120 for every census cost c in [0,120] (cbmv_generator.py:283 divides by 120.)."""
-    r = _round_f32(Fraction(1, 120))
+def test_census_channel0_lut_is_the_ieee_quotient():
+    """ms_fused.cu fills a 256-entry shared-memory table with __fdiv_rn(k, 120) (k <= 120) and
+    1.0 elsewhere; channel 0 is a table look-up of the parked census byte.  The exact
+    quotient rounded to nearest-even equals NumPy's float32 division (cbmv_generator.py:283
+    divides by 120.), and clip(fill, 0, 120)/120 == 1."""
     for c in range(121):
-        cf = Fraction(c)
-        q = _round_f32(cf * r)
-        rem = _round_f32(-120 * q + cf)
-        q2 = _round_f32(rem * r + q)
-        want = _round_f32(cf / 120)
-        assert q2 == want, c
+        want = _round_f32(Fraction(c, 120))
         assert float(want) == float(np.float32(c) / np.float32(120.0))
+    assert float(np.clip(np.float32(2147483648.0), 0, 120) / np.float32(120.0)) == 1.0
 
 
 def test_ncc_numerator_is_exact_in_fp32():
