@@ -45,8 +45,9 @@ namespace msn {
 namespace {
 
 constexpr int kTileMax = 32;  // widest tile (pixels per CTA) the geometry allows for
-constexpr int kGroups = 8;    // d-groups per tile: every thread of phase 1 owns (pixel, d-group)
-constexpr int kSlack = 56;    // right-image columns left of X-(D-1) that dummy steps (d >= D) may read: 8*DC - D <= 47, + pair halo
+constexpr int kGroups = 8;    // d-groups per tile in the one-tile-per-CTA kernel: a phase-1 thread owns (pixel, d-group)
+constexpr int kGroupsWS = 12; // d-groups (= producer warps) in the warp-specialised kernel
+constexpr int kSlack = 24;    // right-image columns left of X-(D-1) that dummy steps (d >= D) may read: groups*DC - D < 2*groups
 constexpr int kPadT = 2;      // padded rows above/below (ZSAD halo)
 constexpr int kPadR = 40;     // padded columns to the right (tile overhang + halo)
 constexpr int kCensW = 11, kNccW = 3, kSadW = 5;
@@ -189,41 +190,74 @@ struct FusedArgs {
   const float* sadsob;  // [N][D][H][Ws] (+ slack)
   float* out;           // [N][8][D][h][w]
   float k_cen, k_ncc, k_sad;
-  int DC;               // disparity steps per d-group (multiple of 6)
+  int DC;               // disparity steps per d-group (even: phase 1 walks disparity pairs)
   int tiles_x;
+  int num_tiles;
+  int dbg;              // timing experiments only (MSNETS_FUSED_DBG): 1 skips phase 1, 2 skips phases 2-3, 4 skips stores
 };
 
+constexpr int kTile = 32;   // pixels per tile: one output row segment of 128 bytes
 
-// Shared-memory layout of one tile of TILE pixels x all disparities (up to DMAX).  Row strides
-// are compile-time so every shared access in the hot loops is "pointer + immediate".
-//   region 0 : staging (right-image census codes, stats, 5 float rows) + per-group minima during
-//              phase 1; afterwards the SAME bytes hold the census AML exponentials [DS][TILE]
-//   parking  : [3][DS][TILE] floats (ncc, sadsob, zsad) + [DS][TILE] census bytes
-template <int DMAX, int TILE, int SLACK>
-struct Lay {
+// Staging buffer of one tile: right-image row data for the D + 31 (+ slack) columns the tile
+// can touch.  Row strides are compile-time so every shared access in the hot loop is
+// "pointer + immediate".
+template <int DMAX, int SLACK>
+struct StageLay {
   static constexpr int kSl = SLACK;
-  static constexpr int RW = (DMAX + TILE - 1 + SLACK + 3) & ~3;   // desc / stat entries
-  static constexpr int RWF = RW + 8;                              // float row: halo 2+2, align shift <= 3
-  // parked planes + 1 scratch plane (dummy steps); even for 16-pixel tiles so that every plane
-  // starts on a 128-byte boundary (plane 1 is a TMA destination)
-  static constexpr int DS = (TILE >= 32) ? DMAX + 1 : ((DMAX + 2) & ~1);
-  static constexpr size_t st_desc = 0;
-  static constexpr size_t st_stat = st_desc + (size_t)RW * 16;
-  static constexpr size_t st_rf = st_stat + (size_t)RW * 16;
-  static constexpr size_t st_mean = st_rf + (size_t)5 * RWF * 4;       // [2][RW + 4] ZSAD means, copy 1 shifted by one
-  static constexpr size_t st_bytes = st_mean + (size_t)2 * (RW + 4) * 4;
-  static constexpr size_t off_red = st_bytes;                                     // [kGroups][4][TILE]
-  static constexpr size_t r0_a = off_red + (size_t)kGroups * 4 * TILE * 4;
-  static constexpr size_t r0_b = (size_t)DS * TILE * 4;                            // census exponentials
+  static constexpr int RW = (DMAX + kTile - 1 + SLACK + 3) & ~3;   // desc / stat entries
+  static constexpr int RWF = RW + 8;                               // float row: halo 2+2, align shift <= 3
+  static constexpr size_t st_desc = 0;                                   // [RW] uint4 census codes
+  static constexpr size_t st_stat = st_desc + (size_t)RW * 16;           // [RW] RStat
+  static constexpr size_t st_rf = st_stat + (size_t)RW * 16;             // [5][RWF] float pixel rows
+  static constexpr size_t st_mean = st_rf + (size_t)5 * RWF * 4;         // [2][RW + 4] ZSAD means, copy 1 shifted by one
+  static constexpr size_t st_bytes = (st_mean + (size_t)2 * (RW + 4) * 4 + 127) & ~(size_t)127;
+};
+
+// Parking buffer of one tile: raw costs (later: AML exponentials) for every (d, pixel).
+//   [3][DS][32] floats (ncc, sadsob, zsad) + [DS][32] census bytes; plane DMAX is scratch for
+//   dummy steps.  Plane 1 is a TMA destination: DS * 128 bytes keeps it 128-byte aligned.
+template <int DMAX>
+struct ParkLay {
+  static constexpr int DS = DMAX + 1;
+  static constexpr int PS = DS * kTile;                                  // floats per parked matcher
+  static constexpr size_t pk_cen = (size_t)3 * PS * 4;
+  static constexpr size_t pk_bytes = (pk_cen + (size_t)DS * kTile + 127) & ~(size_t)127;
+};
+
+// One-tile-per-CTA kernel (2 CTAs per SM).  Region 0 holds the staging buffer and the per-group
+// minima during phase 1; afterwards the SAME bytes hold the census AML exponentials [DS][32].
+template <int DMAX, int SLACK>
+struct Lay : StageLay<DMAX, SLACK>, ParkLay<DMAX> {
+  using S = StageLay<DMAX, SLACK>;
+  using P = ParkLay<DMAX>;
+  static constexpr size_t off_red = S::st_bytes;                                  // [kGroups][4][32]
+  static constexpr size_t r0_a = off_red + (size_t)kGroups * 4 * kTile * 4;
+  static constexpr size_t r0_b = (size_t)P::DS * kTile * 4;                        // census exponentials
   static constexpr size_t off_cene = 0;
-  static constexpr size_t off_min = ((r0_a > r0_b ? r0_a : r0_b) + 15) & ~(size_t)15;  // [4][TILE]
-  static constexpr size_t off_inv = off_min + 4 * TILE * 4;                       // [4][TILE]
-  static constexpr size_t off_lut = off_inv + 4 * TILE * 4;                       // [128] census AML exponentials
+  static constexpr size_t off_min = ((r0_a > r0_b ? r0_a : r0_b) + 15) & ~(size_t)15;  // [4][32]
+  static constexpr size_t off_inv = off_min + 4 * kTile * 4;                      // [4][32]
+  static constexpr size_t off_lut = off_inv + 4 * kTile * 4;                      // [128] census AML exponentials
   static constexpr size_t off_lutn = off_lut + 128 * 4;                           // [256] census byte -> channel 0
   static constexpr size_t off_par = (off_lutn + 256 * 4 + 127) & ~(size_t)127;    // 128 B aligned: TMA destination
-  static constexpr size_t off_cen = off_par + (size_t)3 * DS * TILE * 4;          // [DS][TILE] bytes
-  static constexpr size_t off_bar = (off_cen + (size_t)DS * TILE + 15) & ~(size_t)15;  // mbarriers (8 B each)
+  static constexpr size_t off_bar = off_par + P::pk_bytes;                        // mbarriers (8 B each)
   static constexpr size_t bytes = off_bar + 32;
+};
+
+// Warp-specialised persistent kernel (1 CTA per SM): two staging and two parking buffers.
+template <int DMAX, int SLACK>
+struct LayWS : StageLay<DMAX, SLACK>, ParkLay<DMAX> {
+  using S = StageLay<DMAX, SLACK>;
+  using P = ParkLay<DMAX>;
+  static constexpr size_t off_stage = 0;                                          // [2] staging
+  static constexpr size_t off_park = off_stage + 2 * S::st_bytes;                 // [2] parking (128 B aligned)
+  static constexpr size_t off_cene = off_park + 2 * P::pk_bytes;                  // [DS][32] census exponentials
+  static constexpr size_t off_red = off_cene + (size_t)P::DS * kTile * 4;         // [2][kGroupsWS][4][32]
+  static constexpr size_t off_min = off_red + (size_t)2 * kGroupsWS * 4 * kTile * 4;  // [4][32]
+  static constexpr size_t off_inv = off_min + 4 * kTile * 4;                      // [4][32]
+  static constexpr size_t off_lut = off_inv + 4 * kTile * 4;                      // [128]
+  static constexpr size_t off_lutn = off_lut + 128 * 4;                           // [256]
+  static constexpr size_t off_bar = off_lutn + 256 * 4;                           // 8 mbarriers
+  static constexpr size_t bytes = off_bar + 64;
 };
 
 __device__ __forceinline__ void cp_async4(void* smem_dst, const void* gmem_src) {
@@ -234,25 +268,51 @@ __device__ __forceinline__ void cp_async16(void* smem_dst, const void* gmem_src)
   const uint32_t d = (uint32_t)__cvta_generic_to_shared(smem_dst);
   asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(d), "l"(gmem_src) : "memory");
 }
+__device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_all;" ::: "memory"); }
+
 // ---- TMA / bulk-copy helpers (cp.async.bulk*, completion through an mbarrier) ----------
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
 __device__ __forceinline__ void mbar_init(unsigned long long* bar, unsigned count) {
   asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_init_fence() {
   asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
 }
 __device__ __forceinline__ void mbar_expect_tx(unsigned long long* bar, unsigned bytes) {
   asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
 }
+__device__ __forceinline__ void mbar_arrive(unsigned long long* bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+// Waits for the phase with the given parity.  try_wait suspends the warp in hardware (up to the
+// hint, in ns) instead of polling, so waiting warps leave the issue slots to the working ones.
+// (No __trap() escape here: an exit path inside the wait makes ptxas ignore the register
+// budget that setmaxnreg.inc raised for the producer warps -- measured: 216 B of spills.)
 __device__ __forceinline__ void mbar_wait(unsigned long long* bar, unsigned parity) {
-  asm volatile(
-      "{\n"
-      ".reg .pred p;\n"
-      "MSN_WAIT_%=:\n"
-      "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
-      "@p bra MSN_DONE_%=;\n"
-      "bra MSN_WAIT_%=;\n"
-      "MSN_DONE_%=:\n"
-      "}\n" ::"r"(smem_u32(bar)), "r"(parity) : "memory");
+  const uint32_t addr = smem_u32(bar);
+  unsigned done;
+  do {
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2, %3;\n"
+        "selp.u32 %0, 1, 0, p;\n"
+        "}\n"
+        : "=r"(done)
+        : "r"(addr), "r"(parity), "r"(1000000u)
+        : "memory");
+  } while (!done);
+}
+// orders this thread's earlier generic-proxy shared accesses before later async-proxy (TMA) ones
+__device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+// named barrier among `count` threads (ids 1..15; 0 is __syncthreads)
+__device__ __forceinline__ void named_bar_sync(int id, int count) {
+  asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(count) : "memory");
+}
+// producer/consumer hand-off on a named barrier: arrive does not block, sync waits for `count`
+// arrivals (arrive + sync together); the waiting warps sleep in hardware -- no polling
+__device__ __forceinline__ void named_bar_arrive(int id, int count) {
+  asm volatile("bar.arrive %0, %1;" ::"r"(id), "r"(count) : "memory");
 }
 // 1-D bulk copy global -> shared (bytes multiple of 16, both sides 16 B aligned)
 __device__ __forceinline__ void bulk_load(void* dst, const void* src, unsigned bytes, unsigned long long* bar) {
@@ -266,8 +326,6 @@ __device__ __forceinline__ void tma_load_3d(void* dst, const CUtensorMap* map, i
       "cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3, %4}], [%5];" ::"r"(
           smem_u32(dst)), "l"(reinterpret_cast<uint64_t>(map)), "r"(c0), "r"(c1), "r"(c2), "r"(smem_u32(bar)) : "memory");
 }
-
-__device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_all;" ::: "memory"); }
 
 // ---- packed fp32x2 arithmetic (Blackwell FADD2: two IEEE round-to-nearest adds per issue slot;
 //      operand B may be a scalar register broadcast to both halves, |x| is an operand modifier)
@@ -299,25 +357,24 @@ __device__ __forceinline__ f32x2 abs2(f32x2 v) {
 struct TileId {
   int n, y, x0;
 };
-template <int TILE>
 __device__ __forceinline__ TileId decode_tile(int tile, const FusedArgs& a) {
   TileId t;
   const int xt = tile % a.tiles_x;
   tile /= a.tiles_x;
   t.y = tile % a.g.h;
   t.n = tile / a.g.h;
-  t.x0 = xt * TILE;
+  t.x0 = xt * kTile;
   return t;
 }
 
-// Asynchronously copies the right-image row data of `t` into the staging buffer with LDGSTS:
-// census codes and stats of the D+TILE-1(+slack) columns the tile can touch and the five float
+// Asynchronously copies the right-image row data of `t` into a staging buffer with LDGSTS:
+// census codes and stats of the D+31(+slack) columns the tile can touch and the five float
 // rows of the ZSAD/NCC windows (the float rows start at a 4-float aligned column).
-template <class L, int TILE, int NT>
+template <class L, int NT>
 __device__ __forceinline__ void stage_right(const FusedArgs& a, const TileId& t, unsigned char* buf) {
   const FusedGeom& g = a.g;
   const int D = g.D;
-  const int RWn = D + TILE - 1 + L::kSl;
+  const int RWn = D + kTile - 1 + L::kSl;
   const int XbaseP = t.x0 + g.bwl - (D - 1) - L::kSl + g.padL;
   const int Yp = t.y + g.bh + kPadT;
   const size_t img_off = (size_t)t.n * g.img_px();
@@ -340,12 +397,12 @@ __device__ __forceinline__ void stage_right(const FusedArgs& a, const TileId& t,
 
 // Same data through the TMA engine: seven 1-D bulk copies issued by a single thread,
 // completion counted in bytes on `bar`.
-template <class L, int TILE>
+template <class L>
 __device__ __forceinline__ void stage_rows_tma(const FusedArgs& a, const TileId& t, unsigned char* buf,
                                                unsigned long long* bar) {
   const FusedGeom& g = a.g;
   const int D = g.D;
-  const int RWn = D + TILE - 1 + L::kSl;
+  const int RWn = D + kTile - 1 + L::kSl;
   const int XbaseP = t.x0 + g.bwl - (D - 1) - L::kSl + g.padL;
   const int Yp = t.y + g.bh + kPadT;
   const size_t img_off = (size_t)t.n * g.img_px();
@@ -361,14 +418,28 @@ __device__ __forceinline__ void stage_rows_tma(const FusedArgs& a, const TileId&
     bulk_load(s_rf + r * L::RWF, a.fR + img_off + (size_t)(Yp - 2 + r) * g.Wp + fstart, frow_bytes, bar);
 }
 
-// The tile's D x TILE SAD-of-Sobel costs: ONE 3-D tensor copy straight into parking plane 1.
+// The tile's D x 32 SAD-of-Sobel costs: ONE 3-D tensor copy straight into parking plane 1.
 // They come from DRAM and are only needed after phase 1, hence their own barrier.
-template <int TILE>
 __device__ __forceinline__ void stage_sad_tma(const FusedArgs& a, const CUtensorMap* sad_map, const TileId& t,
                                               float* park_plane1, unsigned long long* bar_sad) {
   const FusedGeom& g = a.g;
-  mbar_expect_tx(bar_sad, (unsigned)g.D * TILE * 4u);
+  mbar_expect_tx(bar_sad, (unsigned)g.D * kTile * 4u);
   tma_load_3d(park_plane1, sad_map, t.x0 + g.bwl + g.sxo, t.y + g.bh, t.n * g.D, bar_sad);  // inner coordinate % 4 == 0
+}
+
+// ZSAD means of the staged right-image row as two float arrays, the second shifted by one
+// entry, so that the means of a disparity pair (columns X-d-1, X-d) are ONE aligned 64-bit
+// shared load.  Called by NT threads with ids tid; a barrier among them must follow.
+template <class L>
+__device__ __forceinline__ void build_mean_arrays(unsigned char* stage, int D, int tid, int NT) {
+  const RStat* st = reinterpret_cast<const RStat*>(stage + L::st_stat);
+  float* mA = reinterpret_cast<float*>(stage + L::st_mean);
+  float* mB = mA + (L::RW + 4);
+  for (int i = tid; i < D + kTile - 1 + L::kSl; i += NT) {
+    const float m = st[i].mean;
+    mA[i] = m;
+    mB[i + 1] = m;
+  }
 }
 
 // A pixel's own left-image data: census code, stats, 5x5 float window.
@@ -392,6 +463,195 @@ __device__ __forceinline__ void load_left(const FusedArgs& a, const TileId& t, i
   }
 }
 
+// Census AML exponentials exp(-(k^2)/sigma) for k = 0..120 and the channel-0 table k/120 (a
+// true IEEE division; 255 = no cost -> clip(fill, 0, 120)/120 = 1).
+__device__ __forceinline__ void fill_luts(float* s_lut, float* s_lutn, float k_cen, int tid, int NT) {
+  for (int kk = tid; kk < 256; kk += NT) {
+    if (kk < 128) s_lut[kk] = (kk <= 120) ? ex2_approx(-(float)(kk * kk) * k_cen) : 0.f;
+    s_lutn[kk] = (kk <= 120) ? __fdiv_rn((float)kk, 120.0f) : 1.0f;
+  }
+}
+
+// ---- phase 1 of a tile for one thread = (pixel px, d-group [d_lo, d_lo + DC)) ---------------
+// Per (pixel, d): census popcount, NCC (9 fp32 products of exact integers, fp64 scaling), ZSAD
+// over a register-resident right window that slides with d; raw costs are parked in shared
+// memory (ncc -> plane 0, zsad -> plane 2, census byte); running minima are returned.
+//
+// ZSAD evaluates disparities in pairs (dA = d, dB = d + 1) with packed FADD2, dB in the low
+// half.  The right windows of the pair overlap: dB's is dA's shifted one column left, so with
+// wv[r][j] = right pixel at column (X - dB - 2) + j, j = 0..5, tap c of dA reads wv[c+1] and
+// tap c of dB reads wv[c].  Pairing tap j of dB with tap j-1 of dA gives both halves the SAME
+// right pixel (a broadcast operand) and a constant left operand ap[r][j-1] =
+// (L[r][j] - mL, L[r][j-1] - mL), hoisted over all d (matchers.cpp:503).  Per window row: one
+// scalar step (dB tap 0), four packed steps, one scalar step (dA tap 4) -- each half still adds
+// its 25 taps in row-major order, every operation an IEEE fp32 add: bit-exact.
+struct Phase1Out {
+  int min_cen;
+  float min_ncc, min_sad;
+  int dmax_sad;
+};
+template <class L, bool kMult6>
+__device__ __forceinline__ Phase1Out phase1_tile(const FusedArgs& a, const TileId& t, const unsigned char* stage,
+                                                 float* s_par, uint8_t* s_cen, const LeftRegs& lr, int px,
+                                                 int d_lo) {
+  constexpr int PS = L::PS;
+  const FusedGeom& g = a.g;
+  const int D = g.D, H = g.H, W = g.W;
+  const int X = t.x0 + px + g.bwl;        // bordered image column of this thread's pixel
+  const int Y = t.y + g.bh;               // bordered image row
+  const uint4 ld = lr.desc;
+  const RStat ls = *reinterpret_cast<const RStat*>(&lr.stat);
+  f32x2 ap[5][4];   // ap[r][j-1] for j = 1..4
+  float l3[3][3];   // centre 3x3 of L as float for NCC
+#pragma unroll
+  for (int r = 0; r < 5; ++r) {
+    float av[5];
+#pragma unroll
+    for (int c = 0; c < 5; ++c) {
+      av[c] = __fsub_rn(lr.px[r][c], ls.mean);
+      if (r >= 1 && r <= 3 && c >= 1 && c <= 3) l3[r - 1][c - 1] = lr.px[r][c];
+    }
+#pragma unroll
+    for (int j = 1; j <= 4; ++j) ap[r][j - 1] = pk2(av[j], av[j - 1]);
+  }
+  // validity: cost(y,x,d) exists iff the window origin is inside and x - wc >= d (and d < D)
+  const int dmax_cen = min(D - 1, (Y >= 5 && Y < H - 6 && X >= 5 && X < W - 6) ? X - 5 : -1);
+  const int dmax_ncc = min(D - 1, (Y >= 1 && Y < H - 2 && X >= 1 && X < W - 2) ? X - 1 : -1);
+  const int dmax_sad = min(D - 1, (Y >= 2 && Y < H - 3 && X >= 2 && X < W - 3) ? X - 2 : -1);
+
+  const uint4* s_desc = reinterpret_cast<const uint4*>(stage + L::st_desc);
+  const uint4* s_stat = reinterpret_cast<const uint4*>(stage + L::st_stat);
+  const float* s_rf = reinterpret_cast<const float*>(stage + L::st_rf);
+  // shared index of right column X - d is ir = px + L::kSl + (D-1) - d; falls by one per step
+  const int XbaseP = t.x0 + g.bwl - (D - 1) - L::kSl + g.padL;
+  const int shift = (XbaseP - 2) & 3;
+  const int ir0 = px + L::kSl + (D - 1) - d_lo;
+  const float* rfp = s_rf + shift + ir0 - 1;   // column (X - dB - 2) of the pair's second disparity
+  const uint4* dscp = s_desc + ir0;
+  const uint4* sttp = s_stat + ir0;
+  // (mean[ir-1], mean[ir]) as one 8-byte aligned load: copy 0 when ir-1 is even, else copy 1 (shifted)
+  const float2* mnp = reinterpret_cast<const float2*>(
+      reinterpret_cast<const float*>(stage + L::st_mean) + (((ir0 - 1) & 1) ? (L::RW + 4) + ir0 : ir0 - 1));
+  float wv[5][6];  // sliding 5x6 right window; logical column j lives in wv[.][(j - 2*s) mod 6]
+#pragma unroll
+  for (int r = 0; r < 5; ++r)
+#pragma unroll
+    for (int j = 0; j < 6; ++j) wv[r][j] = rfp[r * L::RWF + j];
+  int min_cen = 255;
+  float min_ncc = kFill, min_sad = kFill;
+
+  for (int base = 0; base < a.DC; base += 6) {
+#pragma unroll
+    for (int sI = 0; sI < 3; ++sI) {
+#define WV(r, j) wv[r][((j) + 12 - 2 * sI) % 6]
+      if (!kMult6 && sI > 0 && base + 2 * sI >= a.DC) break;   // DC is even; kMult6: a multiple of 6 (no check, one basic block)
+      const int dA = d_lo + base + 2 * sI, dB = dA + 1;
+      const uint4 rdA = dscp[0], rdB = dscp[-1];
+      const uint4 rsA_raw = sttp[0], rsB_raw = sttp[-1];
+      const RStat rsA = *reinterpret_cast<const RStat*>(&rsA_raw);
+      const RStat rsB = *reinterpret_cast<const RStat*>(&rsB_raw);
+      const float2 mBA = *mnp;   // (mean at X - dB, mean at X - dA)
+
+      // census: Hamming distance of the packed codes (matchers.cpp:323-337)
+      const int cenA = __popc(ld.x ^ rdA.x) + __popc(ld.y ^ rdA.y) + __popc(ld.z ^ rdA.z) + __popc(ld.w ^ rdA.w);
+      const int cenB = __popc(ld.x ^ rdB.x) + __popc(ld.y ^ rdB.y) + __popc(ld.z ^ rdB.z) + __popc(ld.w ^ rdB.w);
+      const int cen_bA = (dA <= dmax_cen) ? cenA : 255;
+      const int cen_bB = (dB <= dmax_cen) ? cenB : 255;
+
+      // NCC: P exact in fp32 (< 2^24); scaling in fp64 left to right (matchers.cpp:200-201)
+      float PA = 0.f, PB = 0.f;
+#pragma unroll
+      for (int r = 0; r < 3; ++r)
+#pragma unroll
+        for (int c = 0; c < 3; ++c) {
+          PA = __fmaf_rn(l3[r][c], WV(r + 1, c + 2), PA);
+          PB = __fmaf_rn(l3[r][c], WV(r + 1, c + 1), PB);
+        }
+      const float numA = __fmaf_rn(9.0f, PA, -__fmul_rn(ls.A, rsA.A));
+      const float numB = __fmaf_rn(9.0f, PB, -__fmul_rn(ls.A, rsB.A));
+      float nccA = (float)__dmul_rn(__dmul_rn(-(double)numA, ls.C), rsA.C);
+      float nccB = (float)__dmul_rn(__dmul_rn(-(double)numB, ls.C), rsB.C);
+      nccA = (fabsf(nccA) <= 3.0e38f) ? nccA : 1.0f;  // either C was inf (flat window), :196,204
+      nccB = (fabsf(nccB) <= 3.0e38f) ? nccB : 1.0f;
+      nccA = (dA <= dmax_ncc) ? nccA : kFill;
+      nccB = (dB <= dmax_ncc) ? nccB : kFill;
+
+      // ZSAD: 25 taps row-major, ((L - mL) - R) + mR, sequential fp32 (matchers.cpp:499-506)
+      const f32x2 m2 = pk2(mBA.x, mBA.y);
+      f32x2 acc = pk2(0.f, 0.f);   // (dB, dA)
+#pragma unroll
+      for (int r = 0; r < 5; ++r) {
+        float a_first, a_last, dum, accA, accB;
+        upk2(ap[r][0], dum, a_first);   // L[r][0] - mL
+        upk2(ap[r][3], a_last, dum);    // L[r][4] - mL
+        upk2(acc, accB, accA);
+        accB = __fadd_rn(accB, fabsf(__fadd_rn(__fsub_rn(a_first, WV(r, 0)), mBA.x)));   // dB tap 0
+        acc = pk2(accB, accA);
+#pragma unroll
+        for (int j = 1; j <= 4; ++j) {
+          const float wj = WV(r, j);
+          const f32x2 u = add2(sub2(ap[r][j - 1], pk2(wj, wj)), m2);                    // dB tap j, dA tap j-1
+          acc = add2(acc, abs2(u));
+        }
+        upk2(acc, accB, accA);
+        accA = __fadd_rn(accA, fabsf(__fadd_rn(__fsub_rn(a_last, WV(r, 5)), mBA.y)));    // dA tap 4
+        acc = pk2(accB, accA);
+      }
+      float zA, zB;
+      upk2(acc, zB, zA);
+      zA = (dA <= dmax_sad) ? zA : kFill;
+      zB = (dB <= dmax_sad) ? zB : kFill;
+
+      const int dsA = min(dA, D), dsB = min(dB, D);  // dummy steps (d >= D) park into the scratch plane
+      s_cen[dsA * kTile + px] = (uint8_t)cen_bA;
+      s_cen[dsB * kTile + px] = (uint8_t)cen_bB;
+      s_par[dsA * kTile + px] = nccA;
+      s_par[dsB * kTile + px] = nccB;
+      s_par[2 * PS + dsA * kTile + px] = zA;
+      s_par[2 * PS + dsB * kTile + px] = zB;
+      min_cen = min(min_cen, min(cen_bA, cen_bB));
+      min_ncc = fminf(min_ncc, fminf(nccA, nccB));
+      min_sad = fminf(min_sad, fminf(zA, zB));
+      // slide the window two columns left: the next pair's new columns 0 and 1
+      rfp -= 2; dscp -= 2; sttp -= 2; mnp -= 1;
+#pragma unroll
+      for (int r = 0; r < 5; ++r) {
+        wv[r][(0 + 12 - 2 * (sI + 1)) % 6] = rfp[r * L::RWF];
+        wv[r][(1 + 12 - 2 * (sI + 1)) % 6] = rfp[r * L::RWF + 1];
+      }
+#undef WV
+    }
+  }
+  Phase1Out o;
+  o.min_cen = min_cen;
+  o.min_ncc = min_ncc;
+  o.min_sad = min_sad;
+  o.dmax_sad = dmax_sad;
+  return o;
+}
+
+// After phase 1 and once the tile's SAD-of-Sobel costs have landed in plane 1: this thread's
+// disparities outside the valid region become fill; per-group minima go to s_red[grp][4][32].
+template <class L>
+__device__ __forceinline__ void finish_phase1(float* s_par, float* s_red, const Phase1Out& o, int px, int grp,
+                                              int d_lo, int d_end) {
+  float min_sob = kFill;
+  float* sp = s_par + L::PS + d_lo * kTile + px;
+#pragma unroll 4
+  for (int d = d_lo; d < d_end; ++d, sp += kTile) {
+    float v = *sp;
+    if (d > o.dmax_sad) {
+      v = kFill;
+      *sp = v;
+    }
+    min_sob = fminf(min_sob, v);
+  }
+  s_red[(grp * 4 + 0) * kTile + px] = (o.min_cen == 255) ? kFill : (float)o.min_cen;
+  s_red[(grp * 4 + 1) * kTile + px] = o.min_ncc;
+  s_red[(grp * 4 + 2) * kTile + px] = min_sob;
+  s_red[(grp * 4 + 3) * kTile + px] = o.min_sad;
+}
+
 // Stores four channel planes' 4-pixel row segments: 128-bit streaming stores when the rows are
 // 16 B aligned and the quad is fully inside the image (kVec), guarded scalars otherwise.
 template <bool kVec>
@@ -413,24 +673,24 @@ __device__ __forceinline__ void store_quads(float* o, size_t chan, int nlive, co
   }
 }
 
-// Phase 2 for one thread = (pixel quad q4, disparities dl, dl+DSTEP, ...): channels 0-3
+// Phase 2 for one thread = (pixel quad q4, disparities dl, dl+32, ...): channels 0-3
 // (cbmv_generator.py:283-287) normalised and stored; every parked cost replaced IN PLACE by its
 // AML exponential exp(-(c-m)^2/sigma) (census: looked up in s_lut and written to s_cene), so each
 // exponential is evaluated once.  fill: (fill-m)^2*k is huge -> ex2 of minus it is 0.
-template <bool kVec, int TILE, int DSTEP>
+template <bool kVec>
 __device__ __forceinline__ void phase2_quads(float* s_par, const uint8_t* s_cen, float* s_cene, const float* s_lut,
                                              const float* s_lutn, const float* s_min, int PS, int q4, int dl, int D,
                                              float* orow, size_t plane, size_t chan, int nlive, float k1, float k2) {
   const float4 m_cen4 = *reinterpret_cast<const float4*>(s_min + q4);
-  const float4 m1 = *reinterpret_cast<const float4*>(s_min + TILE + q4);
-  const float4 m2 = *reinterpret_cast<const float4*>(s_min + 2 * TILE + q4);
-  const float4 m3 = *reinterpret_cast<const float4*>(s_min + 3 * TILE + q4);
+  const float4 m1 = *reinterpret_cast<const float4*>(s_min + kTile + q4);
+  const float4 m2 = *reinterpret_cast<const float4*>(s_min + 2 * kTile + q4);
+  const float4 m3 = *reinterpret_cast<const float4*>(s_min + 3 * kTile + q4);
   const int mcx = (m_cen4.x == kFill) ? 0 : (int)m_cen4.x, mcy = (m_cen4.y == kFill) ? 0 : (int)m_cen4.y;
   const int mcz = (m_cen4.z == kFill) ? 0 : (int)m_cen4.z, mcw = (m_cen4.w == kFill) ? 0 : (int)m_cen4.w;
 #pragma unroll 2
-  for (int d = dl; d < D; d += DSTEP) {
-    float* e0 = s_par + d * TILE + q4;
-    const uchar4 cb = *reinterpret_cast<const uchar4*>(s_cen + d * TILE + q4);
+  for (int d = dl; d < D; d += 32) {
+    float* e0 = s_par + d * kTile + q4;
+    const uchar4 cb = *reinterpret_cast<const uchar4*>(s_cen + d * kTile + q4);
     const float4 v1 = *reinterpret_cast<const float4*>(e0);
     const float4 v2 = *reinterpret_cast<const float4*>(e0 + PS);
     const float4 v3 = *reinterpret_cast<const float4*>(e0 + 2 * PS);
@@ -442,7 +702,7 @@ __device__ __forceinline__ void phase2_quads(float* s_par, const uint8_t* s_cen,
     const float4 c3 = make_float4(normalise_cost(v3.x, 3), normalise_cost(v3.y, 3), normalise_cost(v3.z, 3),
                                   normalise_cost(v3.w, 3));
     store_quads<kVec>(orow + (size_t)d * plane, chan, nlive, c0, c1, c2, c3);
-    *reinterpret_cast<float4*>(s_cene + d * TILE + q4) =
+    *reinterpret_cast<float4*>(s_cene + d * kTile + q4) =
         make_float4(s_lut[min((int)cb.x - mcx, 127)], s_lut[min((int)cb.y - mcy, 127)],
                     s_lut[min((int)cb.z - mcz, 127)], s_lut[min((int)cb.w - mcw, 127)]);
     *reinterpret_cast<float4*>(e0) =
@@ -454,18 +714,43 @@ __device__ __forceinline__ void phase2_quads(float* s_par, const uint8_t* s_cen,
   }
 }
 
+// Phase 2b for one thread = (matcher m, pixel p): AML denominator = sequential fp32 sum over d of
+// the parked exponentials, the reference's order (featextract.cpp:444-447; a tree sum is
+// measurably outside the 2e-6 bound).  The next eight terms are loaded before the current
+// eight are added.  Returns 1/den (0 when the pixel has no valid cost: min == fill).
+__device__ __forceinline__ float aml_inverse_den(const float* e, int D, float mm) {
+  float den = 0.f;
+  const int Dfull = D & ~7;
+  float cur[8];
+#pragma unroll
+  for (int j = 0; j < 8; ++j) cur[j] = (j < Dfull) ? e[j * kTile] : 0.f;
+  for (int d0 = 0; d0 < Dfull; d0 += 8) {
+    e += 8 * kTile;
+    const bool more = d0 + 8 < Dfull;
+    float nxt[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) nxt[j] = more ? e[j * kTile] : 0.f;
+#pragma unroll
+    for (int j = 0; j < 8; ++j) den = __fadd_rn(den, cur[j]);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) cur[j] = nxt[j];
+  }
+  for (int d = Dfull; d < D; ++d, e += kTile) den = __fadd_rn(den, e[0]);
+  return (mm == kFill) ? 0.f : 1.0f / den;
+}
+
 // Phase 3: channels 4-7 = parked exponential * (1/den), 128-bit row segments.
-template <bool kVec, int TILE, int DSTEP>
+template <bool kVec>
 __device__ __forceinline__ void phase3_quads(const float* s_par, const float* s_cene, const float* s_inv, int PS, int q4,
                                              int dl, int D, float* arow, size_t plane, size_t chan, int nlive) {
   const float4 i0 = *reinterpret_cast<const float4*>(s_inv + q4);
-  const float4 i1 = *reinterpret_cast<const float4*>(s_inv + TILE + q4);
-  const float4 i2 = *reinterpret_cast<const float4*>(s_inv + 2 * TILE + q4);
-  const float4 i3 = *reinterpret_cast<const float4*>(s_inv + 3 * TILE + q4);
+  const float4 i1 = *reinterpret_cast<const float4*>(s_inv + kTile + q4);
+  const float4 i2 = *reinterpret_cast<const float4*>(s_inv + 2 * kTile + q4);
+  const float4 i3 = *reinterpret_cast<const float4*>(s_inv + 3 * kTile + q4);
 #pragma unroll 2
-  for (int d = dl; d < D; d += DSTEP) {
-    const float* e0 = s_par + d * TILE + q4;
-    const float4 v0 = *reinterpret_cast<const float4*>(s_cene + d * TILE + q4);
+  for (int d = dl; d < D; d += 32) {
+    const float* e0 = s_par + d * kTile + q4;
+    const float4 v0 = *reinterpret_cast<const float4*>(s_cene + d * kTile + q4);
     const float4 v1 = *reinterpret_cast<const float4*>(e0);
     const float4 v2 = *reinterpret_cast<const float4*>(e0 + PS);
     const float4 v3 = *reinterpret_cast<const float4*>(e0 + 2 * PS);
@@ -477,45 +762,85 @@ __device__ __forceinline__ void phase3_quads(const float* s_par, const float* s_
   }
 }
 
-// One CTA per tile = (pair n, output row y, TILE consecutive x) x all D; 32*WARPS threads.
-//   phase 1  thread = (pixel, d-group): 32*WARPS/TILE = 8 d-groups split D.  Per (pixel, d):
-//            census popcount, NCC, ZSAD over a register-resident 5x5 window that slides with d;
-//            raw costs parked in shared memory (13 B/voxel); per-pixel minima.
-//   phase 2  thread = (pixel quad, d): channels 0-3 stored, costs -> AML exponentials in place.
-//   phase 2b one thread per (pixel, matcher): denominator = sequential fp32 sum over d of the
-//            parked exponentials, the reference's order (featextract.cpp:444-447; a tree sum is
-//            measurably outside the 2e-6 bound).
-//   phase 3  thread = (pixel quad, d): channels 4-7 = exponential / den.
+// Phases 2, 2b, 3 of a tile, executed by the 256 threads ctid = 0..255 that synchronise through
+// `sync()` (the CTA barrier or a named barrier).  s_red holds the per-group minima of phase 1.
+template <class L, int NG, class Sync>
+__device__ __forceinline__ void tile_back_half(const FusedArgs& a, const TileId& t, int ctid, float* s_par,
+                                               uint8_t* s_cen, float* s_cene, const float* s_red, float* s_min,
+                                               float* s_inv, const float* s_lut, const float* s_lutn, Sync sync) {
+  constexpr int PS = L::PS;
+  const FusedGeom& g = a.g;
+  const int D = g.D;
+  const size_t plane = (size_t)g.h * g.w;
+  const size_t chan = plane * D;
+  if (ctid < 4 * kTile) {  // minima across the d-groups
+    float v = kFill;
+#pragma unroll
+    for (int gq = 0; gq < NG; ++gq) v = fminf(v, s_red[gq * 4 * kTile + ctid]);
+    s_min[ctid] = v;
+  }
+  sync();
+  // ---- phase 2 ----
+  const int q4 = (ctid & 7) * 4;
+  const int dl = ctid >> 3;
+  // 128-bit stores need 16-byte aligned rows
+  const bool vec_ok = ((g.w & 3) == 0) && ((reinterpret_cast<uintptr_t>(a.out) & 15) == 0);
+  float* orow = a.out + (size_t)t.n * 8 * chan + (size_t)t.y * g.w + (t.x0 + q4);
+  const int nlive = (a.dbg & 4) ? 0 : min(4, g.w - (t.x0 + q4));  // live pixels of this quad (<= 0: none)
+  const bool vec = vec_ok && nlive == 4;
+  if (vec) phase2_quads<true>(s_par, s_cen, s_cene, s_lut, s_lutn, s_min, PS, q4, dl, D, orow, plane, chan, nlive, a.k_ncc, a.k_sad);
+  else phase2_quads<false>(s_par, s_cen, s_cene, s_lut, s_lutn, s_min, PS, q4, dl, D, orow, plane, chan, nlive, a.k_ncc, a.k_sad);
+  sync();
+  // ---- phase 2b ----
+  if (ctid < 4 * kTile) {
+    const int m = ctid / kTile, p = ctid % kTile;
+    s_inv[ctid] = aml_inverse_den((m == 0 ? s_cene : s_par + (m - 1) * PS) + p, D, s_min[ctid]);
+  }
+  sync();
+  // ---- phase 3 ----
+  if (vec) phase3_quads<true>(s_par, s_cene, s_inv, PS, q4, dl, D, orow + 4 * chan, plane, chan, nlive);
+  else phase3_quads<false>(s_par, s_cene, s_inv, PS, q4, dl, D, orow + 4 * chan, plane, chan, nlive);
+}
+
+struct CtaSync {
+  __device__ __forceinline__ void operator()() const { __syncthreads(); }
+};
+struct NamedSync {
+  int id, count;
+  __device__ __forceinline__ void operator()() const { named_bar_sync(id, count); }
+};
+
+// ---- one CTA per tile (fallback: any D up to 448, with or without TMA) ----------------------
+//   phase 1  thread = (pixel, d-group): 8 warps split D (phase1_tile)
+//   phase 2  thread = (pixel quad, d): channels 0-3 stored, costs -> AML exponentials in place
+//   phase 2b one thread per (pixel, matcher): sequential denominator
+//   phase 3  thread = (pixel quad, d): channels 4-7 = exponential / den
 // kTma: right-image rows and the SAD-of-Sobel tile arrive through cp.async.bulk /
 // cp.async.bulk.tensor (D <= 256: box limit); otherwise through LDGSTS.  The tensor copy's
 // inner coordinate must be a multiple of 16 bytes (measured: anything else raises an
 // illegal-instruction fault), which is why the scratch is stored with column offset sxo.
-template <int DMAX, bool kTma, int TILE, int WARPS, int SLACK, int MINB>
-__global__ void __launch_bounds__(WARPS * 32, MINB)
+template <int DMAX, bool kTma>
+__global__ void __launch_bounds__(256, 2)
 ms_fused_kernel(const FusedArgs a, const __grid_constant__ CUtensorMap sad_map) {
-  using L = Lay<DMAX, TILE, SLACK>;
-  constexpr int NT = WARPS * 32;
-  static_assert(NT / TILE == kGroups, "phase 1 needs 8 d-groups");
-  constexpr int QPR = TILE / 4;          // pixel quads per row
-  constexpr int DSTEP = NT / QPR;        // disparity stride of the quad sweeps
-  constexpr int PS = L::DS * TILE;       // floats per parked matcher
+  using L = Lay<DMAX, kSlack>;
+  constexpr int NT = 256;
+  constexpr int PS = L::PS;
   extern __shared__ __align__(128) unsigned char smem_raw[];  // TMA destinations need 128 B
   const FusedGeom& g = a.g;
   const int D = g.D;
   unsigned long long* s_bar = reinterpret_cast<unsigned long long*>(smem_raw + L::off_bar);  // [0] rows, [1] sadsob tile
-  float* s_red = reinterpret_cast<float*>(smem_raw + L::off_red);    // [8][4][TILE]
-  float* s_cene = reinterpret_cast<float*>(smem_raw + L::off_cene);  // [DS][TILE] (aliases staging + s_red)
-  float* s_min = reinterpret_cast<float*>(smem_raw + L::off_min);    // [4][TILE]
-  float* s_inv = reinterpret_cast<float*>(smem_raw + L::off_inv);    // [4][TILE]
-  float* s_lut = reinterpret_cast<float*>(smem_raw + L::off_lut);    // [128]
-  float* s_lutn = reinterpret_cast<float*>(smem_raw + L::off_lutn);  // [256]
-  float* s_par = reinterpret_cast<float*>(smem_raw + L::off_par);    // [3][DS][TILE]
-  uint8_t* s_cen = smem_raw + L::off_cen;                            // [DS][TILE]
-  const unsigned char* buf = smem_raw;
+  float* s_red = reinterpret_cast<float*>(smem_raw + L::off_red);    // [8][4][32]
+  float* s_cene = reinterpret_cast<float*>(smem_raw + L::off_cene);  // [DS][32] (aliases staging + s_red)
+  float* s_min = reinterpret_cast<float*>(smem_raw + L::off_min);
+  float* s_inv = reinterpret_cast<float*>(smem_raw + L::off_inv);
+  float* s_lut = reinterpret_cast<float*>(smem_raw + L::off_lut);
+  float* s_lutn = reinterpret_cast<float*>(smem_raw + L::off_lutn);
+  float* s_par = reinterpret_cast<float*>(smem_raw + L::off_par);    // [3][DS][32]
+  uint8_t* s_cen = smem_raw + L::off_par + L::pk_cen;                // [DS][32]
   const int tid = threadIdx.x;
-  const int px = tid % TILE;             // phase 1: this thread's pixel ...
-  const int grp = tid / TILE;            // ... and d-group
-  const TileId t = decode_tile<TILE>(blockIdx.x, a);
+  const int px = tid % kTile;             // phase 1: this thread's pixel ...
+  const int grp = tid / kTile;            // ... and d-group
+  const TileId t = decode_tile(blockIdx.x, a);
   const int d_lo = grp * a.DC;
   const int d_end = min(D, d_lo + a.DC);  // real disparities of this thread: [d_lo, d_end)
 
@@ -523,23 +848,21 @@ ms_fused_kernel(const FusedArgs a, const __grid_constant__ CUtensorMap sad_map) 
     if (tid == 0) {
       mbar_init(&s_bar[0], 1);
       mbar_init(&s_bar[1], 1);
-      stage_sad_tma<TILE>(a, &sad_map, t, s_par + PS, &s_bar[1]);
-      stage_rows_tma<L, TILE>(a, t, smem_raw, &s_bar[0]);
+      mbar_init_fence();
+      // rows first: phase 1 waits for them; the SAD-of-Sobel box is only needed after phase 1
+      stage_rows_tma<L>(a, t, smem_raw, &s_bar[0]);
+      stage_sad_tma(a, &sad_map, t, s_par + PS, &s_bar[1]);
     }
   } else {
     // sadsob costs of this thread's own disparities: async global -> parked plane 1
     const size_t splane = (size_t)g.H * g.Ws;
     const float* src = a.sadsob + ((size_t)t.n * D * g.H + (t.y + g.bh)) * g.Ws + (t.x0 + px + g.bwl + g.sxo) +
                        (size_t)d_lo * splane;
-    float* dst = s_par + PS + d_lo * TILE + px;
-    for (int d = d_lo; d < d_end; ++d, src += splane, dst += TILE) cp_async4(dst, src);
-    stage_right<L, TILE, NT>(a, t, smem_raw);
+    float* dst = s_par + PS + d_lo * kTile + px;
+    for (int d = d_lo; d < d_end; ++d, src += splane, dst += kTile) cp_async4(dst, src);
+    stage_right<L, NT>(a, t, smem_raw);
   }
-  for (int kk = tid; kk < 256; kk += NT) {
-    if (kk < 128) s_lut[kk] = (kk <= 120) ? ex2_approx(-(float)(kk * kk) * a.k_cen) : 0.f;
-    // channel 0 of a parked census byte: k/120 as a true IEEE division; 255 (no cost) -> clip(fill)/120 = 1
-    s_lutn[kk] = (kk <= 120) ? __fdiv_rn((float)kk, 120.0f) : 1.0f;
-  }
+  fill_luts(s_lut, s_lutn, a.k_cen, tid, NT);
   LeftRegs lr;
   load_left(a, t, px, lr);
   __syncthreads();                       // barrier init + LUTs visible to everyone
@@ -548,228 +871,125 @@ ms_fused_kernel(const FusedArgs a, const __grid_constant__ CUtensorMap sad_map) 
     cp_async_wait_all();
     __syncthreads();
   }
-  // ZSAD means of the right image as two float arrays, the second shifted by one entry, so that
-  // the means of a disparity pair (columns X-d-1, X-d) are ONE aligned 64-bit shared load
-  {
-    const RStat* st = reinterpret_cast<const RStat*>(smem_raw + L::st_stat);
-    float* mA = reinterpret_cast<float*>(smem_raw + L::st_mean);
-    float* mB = mA + (L::RW + 4);
-    for (int i = tid; i < D + TILE - 1 + L::kSl; i += NT) {
-      const float m = st[i].mean;
-      mA[i] = m;
-      mB[i + 1] = m;
-    }
-  }
+  build_mean_arrays<L>(smem_raw, D, tid, NT);
   __syncthreads();
 
-  const int H = g.H, W = g.W;
-  const size_t plane = (size_t)g.h * g.w;
-  const size_t chan = plane * D;
-  const int X = t.x0 + px + g.bwl;        // bordered image column of this thread's pixel
-  const int Y = t.y + g.bh;               // bordered image row
-  {
-    const uint4 ld = lr.desc;
-    const RStat ls = *reinterpret_cast<const RStat*>(&lr.stat);
-    // ZSAD evaluates disparities in pairs (dA = d, dB = d + 1) with packed FADD2, dB in the low
-    // half.  The right windows of the pair overlap: dB's is dA's shifted one column left, so with
-    // wv[r][j] = right pixel at column (X - dB - 2) + j, j = 0..5, tap c of dA reads wv[c+1] and
-    // tap c of dB reads wv[c].  Pairing tap j of dB with tap j-1 of dA gives both halves the SAME
-    // right pixel (a broadcast operand) and a constant left operand ap[r][j-1] =
-    // (L[r][j] - mL, L[r][j-1] - mL), hoisted over all d (matchers.cpp:503).  Per window row:
-    // one scalar step (dB tap 0), four packed steps, one scalar step (dA tap 4) -- each half
-    // still adds its 25 taps in row-major order, every operation an IEEE fp32 add.
-    f32x2 ap[5][4];   // ap[r][j-1] for j = 1..4
-    float l3[3][3];   // centre 3x3 of L as float for NCC
-#pragma unroll
-    for (int r = 0; r < 5; ++r) {
-      float av[5];
-#pragma unroll
-      for (int c = 0; c < 5; ++c) {
-        av[c] = __fsub_rn(lr.px[r][c], ls.mean);
-        if (r >= 1 && r <= 3 && c >= 1 && c <= 3) l3[r - 1][c - 1] = lr.px[r][c];
+  const Phase1Out o = (a.DC % 6 == 0) ? phase1_tile<L, true>(a, t, smem_raw, s_par, s_cen, lr, px, d_lo)
+                                       : phase1_tile<L, false>(a, t, smem_raw, s_par, s_cen, lr, px, d_lo);
+  if (kTma) mbar_wait(&s_bar[1], 0);
+  finish_phase1<L>(s_par, s_red, o, px, grp, d_lo, d_end);
+  __syncthreads();   // phase 1 is over everywhere: from the first sweep on, s_cene overwrites the staging
+                     // buffer (and s_red, which tile_back_half reads before its first barrier)
+  tile_back_half<L, kGroups>(a, t, tid, s_par, s_cen, s_cene, s_red, s_min, s_inv, s_lut, s_lutn, CtaSync());
+}
+
+// ---- warp-specialised persistent kernel (D <= 192; 1 CTA of 20 warps per SM) ----------------
+// Warps 0-11 (producers, one d-group each) run phase 1 of tile i+1 while warps 12-19
+// (consumers) run phases 2, 2b, 3 of tile i: the FADD2-bound cost loop overlaps the
+// MUFU/store-bound back half instead of alternating with it.  The CTA is launched with 96
+// registers per thread (640 * 96 = 61440) and redistributes them with setmaxnreg: producers
+// 120 (the two 5x5 windows of phase 1 live in registers), consumers 56 -- 384*120 + 256*56 =
+// 60416 <= 61440 (setmaxnreg.inc can only draw on what the CTA's own warps released).
+// Two parking buffers and two staging buffers;
+// hand-offs:
+//   rows_full[s]   mbarrier, TMA -> producers     right-image rows of a tile are in stage[s]
+//   sad_full[b]    mbarrier, TMA -> producers     the tile's SAD-of-Sobel box is in park[b] plane 1
+//   park_full[b]   named barrier 3+b, producers arrive / consumers sync: costs + minima are parked
+//   park_empty[b]  named barrier 5+b, consumers arrive / producers sync: phase 3 has read park[b]
+// (named barriers: the waiting side sleeps in hardware; an mbarrier try_wait loop was measured
+// to burn a third of the issued instructions)
+// Tiles are walked with stride gridDim.x; the TMA for tile i+2 is issued as soon as phase 1 of
+// tile i has released its staging buffer, the left-image registers of tile i+1 are prefetched
+// while tile i waits for its SAD-of-Sobel box.
+constexpr int kWsProducers = kGroupsWS * 32;   // 384 threads
+constexpr int kWsConsumers = 256;
+template <int DMAX, int SLACK>
+__global__ void __launch_bounds__(kWsProducers + kWsConsumers, 1)
+ms_fused_ws_kernel(const FusedArgs a, const __grid_constant__ CUtensorMap sad_map) {
+  using L = LayWS<DMAX, SLACK>;
+  constexpr int PS = L::PS;
+  extern __shared__ __align__(128) unsigned char smem_raw[];
+  const FusedGeom& g = a.g;
+  const int D = g.D;
+  unsigned long long* s_bar = reinterpret_cast<unsigned long long*>(smem_raw + L::off_bar);
+  unsigned long long* rows_full = s_bar;        // [2]
+  unsigned long long* sad_full = s_bar + 2;     // [2]
+  float* s_lut = reinterpret_cast<float*>(smem_raw + L::off_lut);
+  float* s_lutn = reinterpret_cast<float*>(smem_raw + L::off_lutn);
+  const int tid = threadIdx.x;
+  if (tid == 0) {
+    for (int i = 0; i < 4; ++i) mbar_init(&s_bar[i], 1);
+    mbar_init_fence();
+  }
+  fill_luts(s_lut, s_lutn, a.k_cen, tid, kWsProducers + kWsConsumers);
+  __syncthreads();
+  const int stride = gridDim.x;
+
+  if (tid < kWsProducers) {
+    // ------------------------------ producers ------------------------------
+    asm volatile("setmaxnreg.inc.sync.aligned.u32 120;");
+    const int px = tid % kTile, grp = tid / kTile;
+    const int d_lo = grp * a.DC;
+    const int d_end = min(D, d_lo + a.DC);
+    int tile = blockIdx.x;
+    if (tid == 0) {
+      stage_rows_tma<L>(a, decode_tile(tile, a), smem_raw + L::off_stage, &rows_full[0]);
+      if (tile + stride < a.num_tiles)
+        stage_rows_tma<L>(a, decode_tile(tile + stride, a), smem_raw + L::off_stage + L::st_bytes, &rows_full[1]);
+    }
+    LeftRegs lr;
+    load_left(a, decode_tile(tile, a), px, lr);
+    for (int it = 0; tile < a.num_tiles; ++it, tile += stride) {
+      const int b = it & 1, k = it >> 1;
+      const TileId t = decode_tile(tile, a);
+      unsigned char* stage = smem_raw + L::off_stage + (size_t)b * L::st_bytes;
+      unsigned char* park = smem_raw + L::off_park + (size_t)b * L::pk_bytes;
+      float* s_par = reinterpret_cast<float*>(park);
+      uint8_t* s_cen = park + L::pk_cen;
+      float* s_red = reinterpret_cast<float*>(smem_raw + L::off_red) + (size_t)b * kGroupsWS * 4 * kTile;
+      if (it >= 2) named_bar_sync(5 + b, kWsProducers + kWsConsumers);   // consumers have finished with park[b]
+      if (tid == 0 && !(a.dbg & 8)) {
+        fence_proxy_async();
+        stage_sad_tma(a, &sad_map, t, s_par + PS, &sad_full[b]);
       }
-#pragma unroll
-      for (int j = 1; j <= 4; ++j) ap[r][j - 1] = pk2(av[j], av[j - 1]);
-    }
-    // validity: cost(y,x,d) exists iff the window origin is inside and x - wc >= d (and d < D)
-    const int dmax_cen = min(D - 1, (Y >= 5 && Y < H - 6 && X >= 5 && X < W - 6) ? X - 5 : -1);
-    const int dmax_ncc = min(D - 1, (Y >= 1 && Y < H - 2 && X >= 1 && X < W - 2) ? X - 1 : -1);
-    const int dmax_sad = min(D - 1, (Y >= 2 && Y < H - 3 && X >= 2 && X < W - 3) ? X - 2 : -1);
-
-    // ---- phase 1: raw costs into the parking planes, per-pixel minima ----------------
-    const uint4* s_desc = reinterpret_cast<const uint4*>(buf + L::st_desc);
-    const uint4* s_stat = reinterpret_cast<const uint4*>(buf + L::st_stat);
-    const float* s_rf = reinterpret_cast<const float*>(buf + L::st_rf);
-    // shared index of right column X - d is ir = px + L::kSl + (D-1) - d; falls by one per step
-    const int XbaseP = t.x0 + g.bwl - (D - 1) - L::kSl + g.padL;
-    const int shift = (XbaseP - 2) & 3;
-    const int ir0 = px + L::kSl + (D - 1) - d_lo;
-    const float* rfp = s_rf + shift + ir0 - 1;   // column (X - dB - 2) of the pair's second disparity
-    const uint4* dscp = s_desc + ir0;
-    const uint4* sttp = s_stat + ir0;
-    // (mean[ir-1], mean[ir]) as one 8-byte aligned load: copy 0 when ir-1 is even, else copy 1 (shifted)
-    const float2* mnp = reinterpret_cast<const float2*>(
-        reinterpret_cast<const float*>(buf + L::st_mean) + (((ir0 - 1) & 1) ? (L::RW + 4) + ir0 : ir0 - 1));
-    float wv[5][6];  // sliding 5x6 right window; logical column j lives in wv[.][(j - 2*s) mod 6]
-#pragma unroll
-    for (int r = 0; r < 5; ++r)
-#pragma unroll
-      for (int j = 0; j < 6; ++j) wv[r][j] = rfp[r * L::RWF + j];
-    int min_cen = 255;
-    float min_ncc = kFill, min_sob = kFill, min_sad = kFill;
-
-    for (int base = 0; base < a.DC; base += 6) {
-#pragma unroll
-      for (int sI = 0; sI < 3; ++sI) {
-#define WV(r, j) wv[r][((j) + 12 - 2 * sI) % 6]
-        const int dA = d_lo + base + 2 * sI, dB = dA + 1;
-        const uint4 rdA = dscp[0], rdB = dscp[-1];
-        const uint4 rsA_raw = sttp[0], rsB_raw = sttp[-1];
-        const RStat rsA = *reinterpret_cast<const RStat*>(&rsA_raw);
-        const RStat rsB = *reinterpret_cast<const RStat*>(&rsB_raw);
-        const float2 mBA = *mnp;   // (mean at X - dB, mean at X - dA)
-
-        // census: Hamming distance of the packed codes (matchers.cpp:323-337)
-        const int cenA = __popc(ld.x ^ rdA.x) + __popc(ld.y ^ rdA.y) + __popc(ld.z ^ rdA.z) + __popc(ld.w ^ rdA.w);
-        const int cenB = __popc(ld.x ^ rdB.x) + __popc(ld.y ^ rdB.y) + __popc(ld.z ^ rdB.z) + __popc(ld.w ^ rdB.w);
-        const int cen_bA = (dA <= dmax_cen) ? cenA : 255;
-        const int cen_bB = (dB <= dmax_cen) ? cenB : 255;
-
-        // NCC: P exact in fp32 (< 2^24); scaling in fp64 left to right (matchers.cpp:200-201)
-        float PA = 0.f, PB = 0.f;
-#pragma unroll
-        for (int r = 0; r < 3; ++r)
-#pragma unroll
-          for (int c = 0; c < 3; ++c) {
-            PA = __fmaf_rn(l3[r][c], WV(r + 1, c + 2), PA);
-            PB = __fmaf_rn(l3[r][c], WV(r + 1, c + 1), PB);
-          }
-        const float numA = __fmaf_rn(9.0f, PA, -__fmul_rn(ls.A, rsA.A));
-        const float numB = __fmaf_rn(9.0f, PB, -__fmul_rn(ls.A, rsB.A));
-        float nccA = (float)__dmul_rn(__dmul_rn(-(double)numA, ls.C), rsA.C);
-        float nccB = (float)__dmul_rn(__dmul_rn(-(double)numB, ls.C), rsB.C);
-        nccA = (fabsf(nccA) <= 3.0e38f) ? nccA : 1.0f;  // either C was inf (flat window), :196,204
-        nccB = (fabsf(nccB) <= 3.0e38f) ? nccB : 1.0f;
-        nccA = (dA <= dmax_ncc) ? nccA : kFill;
-        nccB = (dB <= dmax_ncc) ? nccB : kFill;
-
-        // ZSAD: 25 taps row-major, ((L - mL) - R) + mR, sequential fp32 (matchers.cpp:499-506)
-        const f32x2 m2 = pk2(mBA.x, mBA.y);
-        f32x2 acc = pk2(0.f, 0.f);   // (dB, dA)
-#pragma unroll
-        for (int r = 0; r < 5; ++r) {
-          float a_first, a_last, dum, accA, accB;
-          upk2(ap[r][0], dum, a_first);   // L[r][0] - mL
-          upk2(ap[r][3], a_last, dum);    // L[r][4] - mL
-          upk2(acc, accB, accA);
-          accB = __fadd_rn(accB, fabsf(__fadd_rn(__fsub_rn(a_first, WV(r, 0)), mBA.x)));   // dB tap 0
-          acc = pk2(accB, accA);
-#pragma unroll
-          for (int j = 1; j <= 4; ++j) {
-            const float wj = WV(r, j);
-            const f32x2 u = add2(sub2(ap[r][j - 1], pk2(wj, wj)), m2);                    // dB tap j, dA tap j-1
-            acc = add2(acc, abs2(u));
-          }
-          upk2(acc, accB, accA);
-          accA = __fadd_rn(accA, fabsf(__fadd_rn(__fsub_rn(a_last, WV(r, 5)), mBA.y)));    // dA tap 4
-          acc = pk2(accB, accA);
-        }
-        float zA, zB;
-        upk2(acc, zB, zA);
-        zA = (dA <= dmax_sad) ? zA : kFill;
-        zB = (dB <= dmax_sad) ? zB : kFill;
-
-        const int dsA = min(dA, D), dsB = min(dB, D);  // dummy steps (d >= D) park into the scratch plane
-        s_cen[dsA * TILE + px] = (uint8_t)cen_bA;
-        s_cen[dsB * TILE + px] = (uint8_t)cen_bB;
-        s_par[dsA * TILE + px] = nccA;
-        s_par[dsB * TILE + px] = nccB;
-        s_par[2 * PS + dsA * TILE + px] = zA;
-        s_par[2 * PS + dsB * TILE + px] = zB;
-        min_cen = min(min_cen, min(cen_bA, cen_bB));
-        min_ncc = fminf(min_ncc, fminf(nccA, nccB));
-        min_sad = fminf(min_sad, fminf(zA, zB));
-        // slide the window two columns left: the next pair's new columns 0 and 1
-        rfp -= 2; dscp -= 2; sttp -= 2; mnp -= 1;
-#pragma unroll
-        for (int r = 0; r < 5; ++r) {
-          wv[r][(0 + 12 - 2 * (sI + 1)) % 6] = rfp[r * L::RWF];
-          wv[r][(1 + 12 - 2 * (sI + 1)) % 6] = rfp[r * L::RWF + 1];
-        }
-#undef WV
+      mbar_wait(&rows_full[b], k & 1);
+      build_mean_arrays<L>(stage, D, tid, kWsProducers);
+      named_bar_sync(1, kWsProducers);
+      Phase1Out o;
+      o.min_cen = 0; o.min_ncc = 0.f; o.min_sad = 0.f; o.dmax_sad = D - 1;
+      if (!(a.dbg & 1)) o = phase1_tile<L, false>(a, t, stage, s_par, s_cen, lr, px, d_lo);
+      named_bar_sync(1, kWsProducers);                       // every producer is done with stage[b]
+      if (tid == 0 && tile + 2 * stride < a.num_tiles) {
+        fence_proxy_async();
+        stage_rows_tma<L>(a, decode_tile(tile + 2 * stride, a), stage, &rows_full[b]);
       }
+      if (tile + stride < a.num_tiles) load_left(a, decode_tile(tile + stride, a), px, lr);   // next tile's left data
+      if (!(a.dbg & 8)) mbar_wait(&sad_full[b], k & 1);
+      finish_phase1<L>(s_par, s_red, o, px, grp, d_lo, d_end);
+      named_bar_arrive(3 + b, kWsProducers + kWsConsumers);
     }
-    // SAD-of-Sobel costs of this thread's disparities (delivered by TMA / cp.async while the loop
-    // above ran): replace what lies outside the valid region by fill, take the minimum
-    if (kTma) mbar_wait(&s_bar[1], 0);
-    {
-      float* sp = s_par + PS + d_lo * TILE + px;
-#pragma unroll 4
-      for (int d = d_lo; d < d_end; ++d, sp += TILE) {
-        float v = *sp;
-        if (d > dmax_sad) {
-          v = kFill;
-          *sp = v;
-        }
-        min_sob = fminf(min_sob, v);
-      }
+  } else {
+    // ------------------------------ consumers ------------------------------
+    asm volatile("setmaxnreg.dec.sync.aligned.u32 56;");
+    const int ctid = tid - kWsProducers;
+    float* s_cene = reinterpret_cast<float*>(smem_raw + L::off_cene);
+    float* s_min = reinterpret_cast<float*>(smem_raw + L::off_min);
+    float* s_inv = reinterpret_cast<float*>(smem_raw + L::off_inv);
+    int tile = blockIdx.x;
+    for (int it = 0; tile < a.num_tiles; ++it, tile += stride) {
+      const int b = it & 1, k = it >> 1;
+      const TileId t = decode_tile(tile, a);
+      unsigned char* park = smem_raw + L::off_park + (size_t)b * L::pk_bytes;
+      float* s_par = reinterpret_cast<float*>(park);
+      uint8_t* s_cen = park + L::pk_cen;
+      const float* s_red = reinterpret_cast<const float*>(smem_raw + L::off_red) + (size_t)b * kGroupsWS * 4 * kTile;
+      named_bar_sync(3 + b, kWsProducers + kWsConsumers);
+      if (!(a.dbg & 2))
+        tile_back_half<L, kGroupsWS>(a, t, ctid, s_par, s_cen, s_cene, s_red, s_min, s_inv, s_lut, s_lutn,
+                                     NamedSync{2, kWsConsumers});
+      if (tile + 2 * stride < a.num_tiles) named_bar_arrive(5 + b, kWsProducers + kWsConsumers);
     }
-    s_red[(grp * 4 + 0) * TILE + px] = (min_cen == 255) ? kFill : (float)min_cen;
-    s_red[(grp * 4 + 1) * TILE + px] = min_ncc;
-    s_red[(grp * 4 + 2) * TILE + px] = min_sob;
-    s_red[(grp * 4 + 3) * TILE + px] = min_sad;
   }
-  __syncthreads();
-  if (tid < 4 * TILE) {  // minima across the 8 d-groups
-    float v = kFill;
-#pragma unroll
-    for (int gq = 0; gq < kGroups; ++gq) v = fminf(v, s_red[gq * 4 * TILE + tid]);
-    s_min[tid] = v;
-  }
-  __syncthreads();   // from here on the staging buffer and s_red are dead: s_cene may overwrite them
-
-  // ---- phase 2 ----------------------------------------------------------------------------
-  const int q4 = (tid % QPR) * 4;
-  const int dl = tid / QPR;
-  // 128-bit stores need 16-byte aligned rows
-  const bool vec_ok = ((g.w & 3) == 0) && ((reinterpret_cast<uintptr_t>(a.out) & 15) == 0);
-  float* orow = a.out + (size_t)t.n * 8 * chan + (size_t)t.y * g.w + (t.x0 + q4);
-  const int nlive = min(4, g.w - (t.x0 + q4));  // live pixels of this quad (<= 0: none)
-  const bool vec = vec_ok && nlive == 4;
-  if (vec) phase2_quads<true, TILE, DSTEP>(s_par, s_cen, s_cene, s_lut, s_lutn, s_min, PS, q4, dl, D, orow, plane, chan, nlive, a.k_ncc, a.k_sad);
-  else phase2_quads<false, TILE, DSTEP>(s_par, s_cen, s_cene, s_lut, s_lutn, s_min, PS, q4, dl, D, orow, plane, chan, nlive, a.k_ncc, a.k_sad);
-  __syncthreads();
-
-  // ---- phase 2b: AML denominators, one thread per (matcher, pixel); the next eight
-  //      exponentials are loaded before the current eight are added ----------------------
-  if (tid < 4 * TILE) {
-    const int m = tid / TILE, p = tid % TILE;
-    const float mm = s_min[tid];
-    const float* e = (m == 0 ? s_cene : s_par + (m - 1) * PS) + p;
-    float den = 0.f;
-    const int Dfull = D & ~7;
-    float cur[8];
-#pragma unroll
-    for (int j = 0; j < 8; ++j) cur[j] = (j < Dfull) ? e[j * TILE] : 0.f;
-    for (int d0 = 0; d0 < Dfull; d0 += 8) {
-      e += 8 * TILE;
-      const bool more = d0 + 8 < Dfull;
-      float nxt[8];
-#pragma unroll
-      for (int j = 0; j < 8; ++j) nxt[j] = more ? e[j * TILE] : 0.f;
-#pragma unroll
-      for (int j = 0; j < 8; ++j) den = __fadd_rn(den, cur[j]);
-#pragma unroll
-      for (int j = 0; j < 8; ++j) cur[j] = nxt[j];
-    }
-    for (int d = Dfull; d < D; ++d, e += TILE) den = __fadd_rn(den, e[0]);
-    s_inv[tid] = (mm == kFill) ? 0.f : 1.0f / den;
-  }
-  __syncthreads();
-
-  // ---- phase 3 ----------------------------------------------------------------------------
-  if (vec) phase3_quads<true, TILE, DSTEP>(s_par, s_cene, s_inv, PS, q4, dl, D, orow + 4 * chan, plane, chan, nlive);
-  else phase3_quads<false, TILE, DSTEP>(s_par, s_cene, s_inv, PS, q4, dl, D, orow + 4 * chan, plane, chan, nlive);
 }
 
 // Optional per-kernel timing (msn_profile_enable): CUDA events recorded on the launch
@@ -795,6 +1015,14 @@ static PFN_encodeTiled get_encode_fn() {
     return (PFN_encodeTiled)p;
   }();
   return fn;
+}
+// MSNETS_FUSED_WS=1 selects the warp-specialised persistent kernel where it fits (D <= 192).
+// Measured at 540x960x192: 1.04 ms/pair against 0.90 for the one-tile-per-CTA kernel (its
+// producer and consumer halves each take 0.70 ms alone: both are bound by the shared-memory /
+// LSU pipe and by per-warp dependency latency, so running them side by side does not overlap).
+static bool ws_disabled() {
+  const char* e = getenv("MSNETS_FUSED_WS");
+  return !(e && e[0] == '1');
 }
 static bool tma_disabled() {
   const char* e = getenv("MSNETS_NO_TMA");
@@ -879,12 +1107,15 @@ int launch_ms_fused(const uint8_t* d_left, const uint8_t* d_right, int N, int H,
   a.k_cen = aml_scale(p->cens_sigma);
   a.k_ncc = aml_scale(p->ncc_sigma);
   a.k_sad = aml_scale(p->sad_sigma);
-  a.DC = 6 * (((g.D + kGroups - 1) / kGroups + 5) / 6);   // phase 1 walks d in unrolled groups of 3 pairs
-  const int tile = 32;
-  a.tiles_x = (g.w + tile - 1) / tile;
+  a.tiles_x = (g.w + kTile - 1) / kTile;
   const long long tiles = (long long)N * g.h * a.tiles_x;
   MSN_REQUIRE(tiles <= 2147483647LL, "ms_features: too many tiles for one launch");
-  // TMA path: 3-D tensor map over the SAD-of-Sobel scratch [N*D][H][Ws], box tile x 1 x D
+  a.num_tiles = (int)tiles;
+  {
+    const char* e = getenv("MSNETS_FUSED_DBG");
+    a.dbg = e ? atoi(e) : 0;
+  }
+  // TMA path: 3-D tensor map over the SAD-of-Sobel scratch [N*D][H][Ws], box 32 x 1 x D
   CUtensorMap sad_map;
   memset(&sad_map, 0, sizeof(sad_map));
   bool use_tma = g.D <= 256 && !tma_disabled();
@@ -895,7 +1126,7 @@ int launch_ms_fused(const uint8_t* d_left, const uint8_t* d_right, int N, int H,
     } else {
       const cuuint64_t gdim[3] = {(cuuint64_t)g.Ws, (cuuint64_t)H, (cuuint64_t)N * g.D};
       const cuuint64_t gstr[2] = {(cuuint64_t)g.Ws * 4, (cuuint64_t)H * g.Ws * 4};
-      const cuuint32_t box[3] = {(cuuint32_t)tile, 1u, (cuuint32_t)g.D};
+      const cuuint32_t box[3] = {(cuuint32_t)kTile, 1u, (cuuint32_t)g.D};
       const cuuint32_t estr[3] = {1u, 1u, 1u};
       const CUresult rc = enc(&sad_map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3, ws.sadsob, gdim, gstr, box, estr,
                               CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE,
@@ -903,30 +1134,47 @@ int launch_ms_fused(const uint8_t* d_left, const uint8_t* d_right, int N, int H,
       if (rc != CUDA_SUCCESS) use_tma = false;
     }
   }
-#define MSN_FUSED_LAUNCH(DMAX, TMA, TILE, WARPS, SLACK, MINB)                                         \
-  {                                                                                                   \
-    auto kern = ms_fused_kernel<DMAX, TMA, TILE, WARPS, SLACK, MINB>;                                 \
-    const size_t smem = Lay<DMAX, TILE, SLACK>::bytes;                                                \
+  // warp-specialised persistent kernel: needs TMA and two parking buffers in one SM (D <= 192)
+  if (use_tma && g.D <= 192 && !ws_disabled()) {
+    a.DC = 2 * (((g.D + kGroupsWS - 1) / kGroupsWS + 1) / 2);
+    int dev = 0, sms = 0;
+    MSN_CUDA_OK(cudaGetDevice(&dev));
+    MSN_CUDA_OK(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
+    const unsigned grid = (unsigned)(tiles < sms ? tiles : sms);
+#define MSN_WS_CASE(DMAX)                                                                             \
+  if (g.D <= DMAX) {                                                                                  \
+    auto kern = ms_fused_ws_kernel<DMAX, kSlack>;                                                     \
+    const size_t smem = LayWS<DMAX, kSlack>::bytes;                                                   \
     MSN_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));  \
-    MSN_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout,            \
-                                     (int)cudaSharedmemCarveoutMaxShared));                           \
-    kern<<<(unsigned)tiles, WARPS * 32, smem, s>>>(a, sad_map);                                       \
+    kern<<<grid, kWsProducers + kWsConsumers, smem, s>>>(a, sad_map);                                                         \
+  } else
+    MSN_WS_CASE(64)
+    MSN_WS_CASE(128)
+    MSN_WS_CASE(192) {}
+#undef MSN_WS_CASE
+  } else {
+    a.DC = 2 * (((g.D + kGroups - 1) / kGroups + 1) / 2);
+#define MSN_FUSED_LAUNCH(DMAX, TMA)                                                                   \
+  {                                                                                                   \
+    auto kern = ms_fused_kernel<DMAX, TMA>;                                                           \
+    const size_t smem = Lay<DMAX, kSlack>::bytes;                                                     \
+    MSN_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));  \
+    kern<<<(unsigned)tiles, 256, smem, s>>>(a, sad_map);                                              \
   }
-#define MSN_FUSED_TILE(DMAX, TMA) MSN_FUSED_LAUNCH(DMAX, TMA, 32, 8, kSlack, 2)
 #define MSN_FUSED_CASE(DMAX)                                                                          \
   if (g.D <= DMAX) {                                                                                  \
-    if (use_tma && DMAX <= 256) MSN_FUSED_TILE(DMAX <= 256 ? DMAX : 256, true)                        \
-    else MSN_FUSED_TILE(DMAX, false)                                                                  \
+    if (use_tma && DMAX <= 256) MSN_FUSED_LAUNCH(DMAX <= 256 ? DMAX : 256, true)                      \
+    else MSN_FUSED_LAUNCH(DMAX, false)                                                                \
   } else
-  MSN_FUSED_CASE(64)
-  MSN_FUSED_CASE(128)
-  MSN_FUSED_CASE(192)
-  MSN_FUSED_CASE(256)
-  MSN_FUSED_CASE(384)
-  MSN_FUSED_CASE(448) { return fail("ms_features: D=%d exceeds the fused kernel's limit", g.D); }
+    MSN_FUSED_CASE(64)
+    MSN_FUSED_CASE(128)
+    MSN_FUSED_CASE(192)
+    MSN_FUSED_CASE(256)
+    MSN_FUSED_CASE(384)
+    MSN_FUSED_CASE(448) { return fail("ms_features: D=%d exceeds the fused kernel's limit", g.D); }
 #undef MSN_FUSED_CASE
-#undef MSN_FUSED_TILE
 #undef MSN_FUSED_LAUNCH
+  }
   MSN_LAUNCH_OK();
   if (prof) {
     MSN_CUDA_OK(cudaEventRecord(rec.ev[3], s));
