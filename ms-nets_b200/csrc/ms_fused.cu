@@ -14,13 +14,15 @@
 //                        summed-area table needs whole-row sequential scans, so it
 //                        cannot live inside an x-tile.
 //   3. ms_fused_kernel   one CTA = one output row y x 32 pixels x ALL D:
-//        stage    right-image row data (census codes, stats, 5 float rows) and the
-//                 tile's SAD-of-Sobel costs stream into shared memory with cp.async.
-//        phase 1  8 warps split D; lane = pixel.  Per (pixel, d): census popcount,
-//                 NCC (9 fp32 products of exact integers, fp64 scaling), ZSAD (75
-//                 ordered fp32 adds over a register-resident 5x5 window that slides
-//                 with d); raw costs are parked in shared memory (13 B/voxel: three
-//                 floats + census byte); per-pixel minima.
+//        stage    right-image row data (census codes, stats, 5 float rows) and the tile's
+//                 SAD-of-Sobel costs stream into shared memory through TMA (cp.async.bulk /
+//                 cp.async.bulk.tensor; LDGSTS fallback for D > 256).
+//        phase 1  8 warps split D; lane = pixel.  Per (pixel, d): census popcount, NCC (9 fp32
+//                 products of exact integers, fp64 scaling), ZSAD over a register-resident
+//                 right window that slides with d -- two disparities at a time with packed
+//                 FADD2, every add still an IEEE fp32 add in the reference's order; raw costs
+//                 are parked in shared memory (13 B/voxel: three floats + census byte);
+//                 per-pixel minima.
 //        phase 2  warp-specialised, both halves only READ the parked costs:
 //                 warps 0-3: one thread per (pixel, matcher) adds the AML denominator in
 //                 d order (the reference's sequential fp32 sum, featextract.cpp:444-447);
@@ -28,8 +30,8 @@
 //                 as 128-bit row segments.
 //        phase 3  channels 4-7 = exp(-(c-m)^2/sigma) / den, 128-bit row segments.
 //
-// Bounding resource: HBM writes (32 B per voxel) co-limited by issue slots -- ZSAD
-// alone is 75 dependent-order FADDs per voxel (DESIGN.md has the arithmetic).
+// Bounding resource: HBM writes (32 B per voxel), co-limited by the FP32 pipe -- ZSAD alone is
+// 75 ordered adds per voxel -- and by shared-memory/LSU traffic (DESIGN.md has the arithmetic).
 #include "ms_fused.cuh"
 
 #include <cuda.h>
@@ -45,8 +47,7 @@ namespace msn {
 namespace {
 
 constexpr int kTileMax = 32;  // widest tile (pixels per CTA) the geometry allows for
-constexpr int kGroups = 8;    // d-groups per tile in the one-tile-per-CTA kernel: a phase-1 thread owns (pixel, d-group)
-constexpr int kGroupsWS = 12; // d-groups (= producer warps) in the warp-specialised kernel
+constexpr int kGroups = 8;    // d-groups per tile: a phase-1 thread owns (pixel, d-group)
 constexpr int kSlack = 24;    // right-image columns left of X-(D-1) that dummy steps (d >= D) may read: groups*DC - D < 2*groups
 constexpr int kPadT = 2;      // padded rows above/below (ZSAD halo)
 constexpr int kPadR = 40;     // padded columns to the right (tile overhang + halo)
@@ -91,7 +92,7 @@ struct FusedWs {
   void carve(char* base, const FusedGeom& g) {
     size_t off = 0;
     auto take = [&](size_t bytes) { char* q = base ? base + off : nullptr; off += (bytes + 255) & ~(size_t)255; return q; };
-    const size_t np = (size_t)g.N * g.img_px(), n = (size_t)g.N * g.H * g.W;
+    const size_t np = (size_t)g.N * g.img_px();
     for (int i = 0; i < 2; ++i) desc[i] = (uint4*)take(np * sizeof(uint4));
     for (int i = 0; i < 2; ++i) stat[i] = (RStat*)take(np * sizeof(RStat));
     for (int i = 0; i < 2; ++i) fimg[i] = (float*)take(np * sizeof(float));
@@ -192,8 +193,6 @@ struct FusedArgs {
   float k_cen, k_ncc, k_sad;
   int DC;               // disparity steps per d-group (even: phase 1 walks disparity pairs)
   int tiles_x;
-  int num_tiles;
-  int dbg;              // timing experiments only (MSNETS_FUSED_DBG): 1 skips phase 1, 2 skips phases 2-3, 4 skips stores
 };
 
 constexpr int kTile = 32;   // pixels per tile: one output row segment of 128 bytes
@@ -224,40 +223,19 @@ struct ParkLay {
   static constexpr size_t pk_bytes = (pk_cen + (size_t)DS * kTile + 127) & ~(size_t)127;
 };
 
-// One-tile-per-CTA kernel (2 CTAs per SM).  Region 0 holds the staging buffer and the per-group
-// minima during phase 1; afterwards the SAME bytes hold the census AML exponentials [DS][32].
+// Shared memory of one CTA = one tile (2 CTAs per SM).
 template <int DMAX, int SLACK>
 struct Lay : StageLay<DMAX, SLACK>, ParkLay<DMAX> {
   using S = StageLay<DMAX, SLACK>;
   using P = ParkLay<DMAX>;
-  static constexpr size_t off_red = S::st_bytes;                                  // [kGroups][4][32]
-  static constexpr size_t r0_a = off_red + (size_t)kGroups * 4 * kTile * 4;
-  static constexpr size_t r0_b = (size_t)P::DS * kTile * 4;                        // census exponentials
-  static constexpr size_t off_cene = 0;
-  static constexpr size_t off_min = ((r0_a > r0_b ? r0_a : r0_b) + 15) & ~(size_t)15;  // [4][32]
+  static constexpr size_t off_red = S::st_bytes;                                  // [kGroups][4][32] per-group minima
+  static constexpr size_t off_min = off_red + (size_t)kGroups * 4 * kTile * 4;    // [4][32]
   static constexpr size_t off_inv = off_min + 4 * kTile * 4;                      // [4][32]
   static constexpr size_t off_lut = off_inv + 4 * kTile * 4;                      // [128] census AML exponentials
   static constexpr size_t off_lutn = off_lut + 128 * 4;                           // [256] census byte -> channel 0
   static constexpr size_t off_par = (off_lutn + 256 * 4 + 127) & ~(size_t)127;    // 128 B aligned: TMA destination
-  static constexpr size_t off_bar = off_par + P::pk_bytes;                        // mbarriers (8 B each)
+  static constexpr size_t off_bar = off_par + P::pk_bytes;                        // 2 mbarriers
   static constexpr size_t bytes = off_bar + 32;
-};
-
-// Warp-specialised persistent kernel (1 CTA per SM): two staging and two parking buffers.
-template <int DMAX, int SLACK>
-struct LayWS : StageLay<DMAX, SLACK>, ParkLay<DMAX> {
-  using S = StageLay<DMAX, SLACK>;
-  using P = ParkLay<DMAX>;
-  static constexpr size_t off_stage = 0;                                          // [2] staging
-  static constexpr size_t off_park = off_stage + 2 * S::st_bytes;                 // [2] parking (128 B aligned)
-  static constexpr size_t off_cene = off_park + 2 * P::pk_bytes;                  // [DS][32] census exponentials
-  static constexpr size_t off_red = off_cene + (size_t)P::DS * kTile * 4;         // [2][kGroupsWS][4][32]
-  static constexpr size_t off_min = off_red + (size_t)2 * kGroupsWS * 4 * kTile * 4;  // [4][32]
-  static constexpr size_t off_inv = off_min + 4 * kTile * 4;                      // [4][32]
-  static constexpr size_t off_lut = off_inv + 4 * kTile * 4;                      // [128]
-  static constexpr size_t off_lutn = off_lut + 128 * 4;                           // [256]
-  static constexpr size_t off_bar = off_lutn + 256 * 4;                           // 8 mbarriers
-  static constexpr size_t bytes = off_bar + 64;
 };
 
 __device__ __forceinline__ void cp_async4(void* smem_dst, const void* gmem_src) {
@@ -281,13 +259,8 @@ __device__ __forceinline__ void mbar_init_fence() {
 __device__ __forceinline__ void mbar_expect_tx(unsigned long long* bar, unsigned bytes) {
   asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
 }
-__device__ __forceinline__ void mbar_arrive(unsigned long long* bar) {
-  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
-}
 // Waits for the phase with the given parity.  try_wait suspends the warp in hardware (up to the
 // hint, in ns) instead of polling, so waiting warps leave the issue slots to the working ones.
-// (No __trap() escape here: an exit path inside the wait makes ptxas ignore the register
-// budget that setmaxnreg.inc raised for the producer warps -- measured: 216 B of spills.)
 __device__ __forceinline__ void mbar_wait(unsigned long long* bar, unsigned parity) {
   const uint32_t addr = smem_u32(bar);
   unsigned done;
@@ -302,17 +275,6 @@ __device__ __forceinline__ void mbar_wait(unsigned long long* bar, unsigned pari
         : "r"(addr), "r"(parity), "r"(1000000u)
         : "memory");
   } while (!done);
-}
-// orders this thread's earlier generic-proxy shared accesses before later async-proxy (TMA) ones
-__device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
-// named barrier among `count` threads (ids 1..15; 0 is __syncthreads)
-__device__ __forceinline__ void named_bar_sync(int id, int count) {
-  asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(count) : "memory");
-}
-// producer/consumer hand-off on a named barrier: arrive does not block, sync waits for `count`
-// arrivals (arrive + sync together); the waiting warps sleep in hardware -- no polling
-__device__ __forceinline__ void named_bar_arrive(int id, int count) {
-  asm volatile("bar.arrive %0, %1;" ::"r"(id), "r"(count) : "memory");
 }
 // 1-D bulk copy global -> shared (bytes multiple of 16, both sides 16 B aligned)
 __device__ __forceinline__ void bulk_load(void* dst, const void* src, unsigned bytes, unsigned long long* bar) {
@@ -673,23 +635,16 @@ __device__ __forceinline__ void store_quads(float* o, size_t chan, int nlive, co
   }
 }
 
-// Phase 2 for one thread = (pixel quad q4, disparities dl, dl+32, ...): channels 0-3
-// (cbmv_generator.py:283-287) normalised and stored; every parked cost replaced IN PLACE by its
-// AML exponential exp(-(c-m)^2/sigma) (census: looked up in s_lut and written to s_cene), so each
-// exponential is evaluated once.  fill: (fill-m)^2*k is huge -> ex2 of minus it is 0.
+// ---- back half of a tile: channels 0-3, AML denominators, channels 4-7 --------------------
+// Channels 0-3 (cbmv_generator.py:283-287) for thread = (pixel quad q4, disparities d0, d0+16, ... < d1):
+// normalised costs stored as 128-bit row segments.
 template <bool kVec>
-__device__ __forceinline__ void phase2_quads(float* s_par, const uint8_t* s_cen, float* s_cene, const float* s_lut,
-                                             const float* s_lutn, const float* s_min, int PS, int q4, int dl, int D,
-                                             float* orow, size_t plane, size_t chan, int nlive, float k1, float k2) {
-  const float4 m_cen4 = *reinterpret_cast<const float4*>(s_min + q4);
-  const float4 m1 = *reinterpret_cast<const float4*>(s_min + kTile + q4);
-  const float4 m2 = *reinterpret_cast<const float4*>(s_min + 2 * kTile + q4);
-  const float4 m3 = *reinterpret_cast<const float4*>(s_min + 3 * kTile + q4);
-  const int mcx = (m_cen4.x == kFill) ? 0 : (int)m_cen4.x, mcy = (m_cen4.y == kFill) ? 0 : (int)m_cen4.y;
-  const int mcz = (m_cen4.z == kFill) ? 0 : (int)m_cen4.z, mcw = (m_cen4.w == kFill) ? 0 : (int)m_cen4.w;
+__device__ __forceinline__ void store_ch03(const float* s_par, const uint8_t* s_cen, const float* s_lutn, int PS,
+                                           int q4, int d0, int d1, float* orow, size_t plane, size_t chan,
+                                           int nlive) {
 #pragma unroll 2
-  for (int d = dl; d < D; d += 32) {
-    float* e0 = s_par + d * kTile + q4;
+  for (int d = d0; d < d1; d += 16) {
+    const float* e0 = s_par + d * kTile + q4;
     const uchar4 cb = *reinterpret_cast<const uchar4*>(s_cen + d * kTile + q4);
     const float4 v1 = *reinterpret_cast<const float4*>(e0);
     const float4 v2 = *reinterpret_cast<const float4*>(e0 + PS);
@@ -702,113 +657,120 @@ __device__ __forceinline__ void phase2_quads(float* s_par, const uint8_t* s_cen,
     const float4 c3 = make_float4(normalise_cost(v3.x, 3), normalise_cost(v3.y, 3), normalise_cost(v3.z, 3),
                                   normalise_cost(v3.w, 3));
     store_quads<kVec>(orow + (size_t)d * plane, chan, nlive, c0, c1, c2, c3);
-    *reinterpret_cast<float4*>(s_cene + d * kTile + q4) =
-        make_float4(s_lut[min((int)cb.x - mcx, 127)], s_lut[min((int)cb.y - mcy, 127)],
-                    s_lut[min((int)cb.z - mcz, 127)], s_lut[min((int)cb.w - mcw, 127)]);
-    *reinterpret_cast<float4*>(e0) =
-        make_float4(aml_e(v1.x, m1.x, k1), aml_e(v1.y, m1.y, k1), aml_e(v1.z, m1.z, k1), aml_e(v1.w, m1.w, k1));
-    *reinterpret_cast<float4*>(e0 + PS) =
-        make_float4(aml_e(v2.x, m2.x, k2), aml_e(v2.y, m2.y, k2), aml_e(v2.z, m2.z, k2), aml_e(v2.w, m2.w, k2));
-    *reinterpret_cast<float4*>(e0 + 2 * PS) =
-        make_float4(aml_e(v3.x, m3.x, k2), aml_e(v3.y, m3.y, k2), aml_e(v3.z, m3.z, k2), aml_e(v3.w, m3.w, k2));
   }
 }
 
-// Phase 2b for one thread = (matcher m, pixel p): AML denominator = sequential fp32 sum over d of
-// the parked exponentials, the reference's order (featextract.cpp:444-447; a tree sum is
-// measurably outside the 2e-6 bound).  The next eight terms are loaded before the current
-// eight are added.  Returns 1/den (0 when the pixel has no valid cost: min == fill).
-__device__ __forceinline__ float aml_inverse_den(const float* e, int D, float mm) {
-  float den = 0.f;
-  const int Dfull = D & ~7;
-  float cur[8];
-#pragma unroll
-  for (int j = 0; j < 8; ++j) cur[j] = (j < Dfull) ? e[j * kTile] : 0.f;
-  for (int d0 = 0; d0 < Dfull; d0 += 8) {
-    e += 8 * kTile;
-    const bool more = d0 + 8 < Dfull;
-    float nxt[8];
-#pragma unroll
-    for (int j = 0; j < 8; ++j) nxt[j] = more ? e[j * kTile] : 0.f;
-#pragma unroll
-    for (int j = 0; j < 8; ++j) den = __fadd_rn(den, cur[j]);
-#pragma unroll
-    for (int j = 0; j < 8; ++j) cur[j] = nxt[j];
-  }
-  for (int d = Dfull; d < D; ++d, e += kTile) den = __fadd_rn(den, e[0]);
-  return (mm == kFill) ? 0.f : 1.0f / den;
-}
-
-// Phase 3: channels 4-7 = parked exponential * (1/den), 128-bit row segments.
+// Channels 4-7 = exp(-(c-m)^2/sigma) / den for thread = (pixel quad q4, disparities dl, dl+32, ...),
+// exponentials recomputed from the parked costs, 128-bit row segments.
 template <bool kVec>
-__device__ __forceinline__ void phase3_quads(const float* s_par, const float* s_cene, const float* s_inv, int PS, int q4,
-                                             int dl, int D, float* arow, size_t plane, size_t chan, int nlive) {
+__device__ __forceinline__ void phase3_quads(const float* s_par, const uint8_t* s_cen, const float* s_lut,
+                                             const float* s_min, const float* s_inv, int PS, int q4, int dl, int D,
+                                             float* arow, size_t plane, size_t chan, int nlive, float k1, float k2) {
+  const float4 m_cen4 = *reinterpret_cast<const float4*>(s_min + q4);
+  const float4 m1 = *reinterpret_cast<const float4*>(s_min + kTile + q4);
+  const float4 m2 = *reinterpret_cast<const float4*>(s_min + 2 * kTile + q4);
+  const float4 m3 = *reinterpret_cast<const float4*>(s_min + 3 * kTile + q4);
   const float4 i0 = *reinterpret_cast<const float4*>(s_inv + q4);
   const float4 i1 = *reinterpret_cast<const float4*>(s_inv + kTile + q4);
   const float4 i2 = *reinterpret_cast<const float4*>(s_inv + 2 * kTile + q4);
   const float4 i3 = *reinterpret_cast<const float4*>(s_inv + 3 * kTile + q4);
+  const int mcx = (m_cen4.x == kFill) ? 0 : (int)m_cen4.x, mcy = (m_cen4.y == kFill) ? 0 : (int)m_cen4.y;
+  const int mcz = (m_cen4.z == kFill) ? 0 : (int)m_cen4.z, mcw = (m_cen4.w == kFill) ? 0 : (int)m_cen4.w;
 #pragma unroll 2
   for (int d = dl; d < D; d += 32) {
     const float* e0 = s_par + d * kTile + q4;
-    const float4 v0 = *reinterpret_cast<const float4*>(s_cene + d * kTile + q4);
+    const uchar4 cb = *reinterpret_cast<const uchar4*>(s_cen + d * kTile + q4);
     const float4 v1 = *reinterpret_cast<const float4*>(e0);
     const float4 v2 = *reinterpret_cast<const float4*>(e0 + PS);
     const float4 v3 = *reinterpret_cast<const float4*>(e0 + 2 * PS);
-    const float4 a0 = make_float4(v0.x * i0.x, v0.y * i0.y, v0.z * i0.z, v0.w * i0.w);
-    const float4 a1 = make_float4(v1.x * i1.x, v1.y * i1.y, v1.z * i1.z, v1.w * i1.w);
-    const float4 a2 = make_float4(v2.x * i2.x, v2.y * i2.y, v2.z * i2.z, v2.w * i2.w);
-    const float4 a3 = make_float4(v3.x * i3.x, v3.y * i3.y, v3.z * i3.z, v3.w * i3.w);
+    const float4 a0 = make_float4(s_lut[min((int)cb.x - mcx, 127)] * i0.x, s_lut[min((int)cb.y - mcy, 127)] * i0.y,
+                                  s_lut[min((int)cb.z - mcz, 127)] * i0.z, s_lut[min((int)cb.w - mcw, 127)] * i0.w);
+    const float4 a1 = make_float4(aml_e(v1.x, m1.x, k1) * i1.x, aml_e(v1.y, m1.y, k1) * i1.y,
+                                  aml_e(v1.z, m1.z, k1) * i1.z, aml_e(v1.w, m1.w, k1) * i1.w);
+    const float4 a2 = make_float4(aml_e(v2.x, m2.x, k2) * i2.x, aml_e(v2.y, m2.y, k2) * i2.y,
+                                  aml_e(v2.z, m2.z, k2) * i2.z, aml_e(v2.w, m2.w, k2) * i2.w);
+    const float4 a3 = make_float4(aml_e(v3.x, m3.x, k2) * i3.x, aml_e(v3.y, m3.y, k2) * i3.y,
+                                  aml_e(v3.z, m3.z, k2) * i3.z, aml_e(v3.w, m3.w, k2) * i3.w);
     store_quads<kVec>(arow + (size_t)d * plane, chan, nlive, a0, a1, a2, a3);
   }
 }
 
-// Phases 2, 2b, 3 of a tile, executed by the 256 threads ctid = 0..255 that synchronise through
-// `sync()` (the CTA barrier or a named barrier).  s_red holds the per-group minima of phase 1.
-template <class L, int NG, class Sync>
-__device__ __forceinline__ void tile_back_half(const FusedArgs& a, const TileId& t, int ctid, float* s_par,
-                                               uint8_t* s_cen, float* s_cene, const float* s_red, float* s_min,
-                                               float* s_inv, const float* s_lut, const float* s_lutn, Sync sync) {
+// Phases 2 and 3 for the 256 threads of a CTA.  s_red holds the per-group minima of phase 1.
+//   phase 2 (warp-specialised; both halves only READ the parked costs, so they overlap without
+//            hazards):
+//     warps 0-3  one thread per (pixel, matcher): AML denominator, exponentials evaluated on
+//                the fly and added in the reference's order -- sequential fp32 over d
+//                (featextract.cpp:444-447; a tree sum is measurably outside the 2e-6 bound);
+//     warps 4-7  thread = (pixel quad, d): channels 0-3 normalised and stored.
+//   phase 3      all warps: channels 4-7.
+// Measured alternatives: writing each exponential back in place and adding
+// the denominators in a phase of their own (fewer instructions, 6 % slower: the chain is
+// exposed), the same behind a progress counter (slower still: the chain warps spin), handing
+// part of the channel 0-3 stores to the chain warps statically or through a work counter (no
+// gain: the halves are already balanced), a warp-specialised persistent producer/consumer
+// kernel (15 % slower).
+template <class L>
+__device__ __forceinline__ void tile_back_half(const FusedArgs& a, const TileId& t, int tid, const float* s_par,
+                                               const uint8_t* s_cen, const float* s_red, float* s_min,
+                                               float* s_inv, const float* s_lut, const float* s_lutn) {
   constexpr int PS = L::PS;
   const FusedGeom& g = a.g;
   const int D = g.D;
   const size_t plane = (size_t)g.h * g.w;
   const size_t chan = plane * D;
-  if (ctid < 4 * kTile) {  // minima across the d-groups
+  if (tid < 4 * kTile) {  // minima across the d-groups
     float v = kFill;
 #pragma unroll
-    for (int gq = 0; gq < NG; ++gq) v = fminf(v, s_red[gq * 4 * kTile + ctid]);
-    s_min[ctid] = v;
+    for (int gq = 0; gq < kGroups; ++gq) v = fminf(v, s_red[gq * 4 * kTile + tid]);
+    s_min[tid] = v;
   }
-  sync();
-  // ---- phase 2 ----
-  const int q4 = (ctid & 7) * 4;
-  const int dl = ctid >> 3;
+  __syncthreads();
+  const int warp = tid >> 5, lane = tid & 31;
+  const int q4 = (tid & 7) * 4;
   // 128-bit stores need 16-byte aligned rows
   const bool vec_ok = ((g.w & 3) == 0) && ((reinterpret_cast<uintptr_t>(a.out) & 15) == 0);
   float* orow = a.out + (size_t)t.n * 8 * chan + (size_t)t.y * g.w + (t.x0 + q4);
-  const int nlive = (a.dbg & 4) ? 0 : min(4, g.w - (t.x0 + q4));  // live pixels of this quad (<= 0: none)
+  const int nlive = min(4, g.w - (t.x0 + q4));  // live pixels of this quad (<= 0: none)
   const bool vec = vec_ok && nlive == 4;
-  if (vec) phase2_quads<true>(s_par, s_cen, s_cene, s_lut, s_lutn, s_min, PS, q4, dl, D, orow, plane, chan, nlive, a.k_ncc, a.k_sad);
-  else phase2_quads<false>(s_par, s_cen, s_cene, s_lut, s_lutn, s_min, PS, q4, dl, D, orow, plane, chan, nlive, a.k_ncc, a.k_sad);
-  sync();
-  // ---- phase 2b ----
-  if (ctid < 4 * kTile) {
-    const int m = ctid / kTile, p = ctid % kTile;
-    s_inv[ctid] = aml_inverse_den((m == 0 ? s_cene : s_par + (m - 1) * PS) + p, D, s_min[ctid]);
+  if (warp < 4) {
+    const float mm = s_min[warp * kTile + lane];
+    float den = 0.f;
+    const int Dfull = D & ~7;   // groups of 8 without guards, then a guarded tail
+    if (warp == 0) {
+      const int mc = (mm == kFill) ? 0 : (int)mm;
+      const uint8_t* c = s_cen + lane;
+      for (int d0 = 0; d0 < Dfull; d0 += 8, c += 8 * kTile) {
+        float ev[8];
+#pragma unroll
+        for (int j = 0; j < 8; ++j) ev[j] = s_lut[min((int)c[j * kTile] - mc, 127)];
+#pragma unroll
+        for (int j = 0; j < 8; ++j) den = __fadd_rn(den, ev[j]);
+      }
+      for (int d = Dfull; d < D; ++d, c += kTile) den = __fadd_rn(den, s_lut[min((int)c[0] - mc, 127)]);
+    } else {
+      const float kq = (warp == 1) ? a.k_ncc : a.k_sad;
+      const float* e = s_par + (warp - 1) * PS + lane;
+      for (int d0 = 0; d0 < Dfull; d0 += 8, e += 8 * kTile) {
+        float ev[8];
+#pragma unroll
+        for (int j = 0; j < 8; ++j) ev[j] = aml_e(e[j * kTile], mm, kq);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) den = __fadd_rn(den, ev[j]);
+      }
+      for (int d = Dfull; d < D; ++d, e += kTile) den = __fadd_rn(den, aml_e(e[0], mm, kq));
+    }
+    s_inv[warp * kTile + lane] = (mm == kFill) ? 0.f : 1.0f / den;
   }
-  sync();
-  // ---- phase 3 ----
-  if (vec) phase3_quads<true>(s_par, s_cene, s_inv, PS, q4, dl, D, orow + 4 * chan, plane, chan, nlive);
-  else phase3_quads<false>(s_par, s_cene, s_inv, PS, q4, dl, D, orow + 4 * chan, plane, chan, nlive);
+  else {
+    // channels 0-3: thread = (pixel quad, d), 16 disparities per sweep of the four warps
+    if (vec) store_ch03<true>(s_par, s_cen, s_lutn, PS, q4, (tid >> 3) - 16, D, orow, plane, chan, nlive);
+    else store_ch03<false>(s_par, s_cen, s_lutn, PS, q4, (tid >> 3) - 16, D, orow, plane, chan, nlive);
+  }
+  __syncthreads();
+  const int dl = tid >> 3;
+  if (vec) phase3_quads<true>(s_par, s_cen, s_lut, s_min, s_inv, PS, q4, dl, D, orow + 4 * chan, plane, chan, nlive, a.k_ncc, a.k_sad);
+  else phase3_quads<false>(s_par, s_cen, s_lut, s_min, s_inv, PS, q4, dl, D, orow + 4 * chan, plane, chan, nlive, a.k_ncc, a.k_sad);
 }
-
-struct CtaSync {
-  __device__ __forceinline__ void operator()() const { __syncthreads(); }
-};
-struct NamedSync {
-  int id, count;
-  __device__ __forceinline__ void operator()() const { named_bar_sync(id, count); }
-};
 
 // ---- one CTA per tile (fallback: any D up to 448, with or without TMA) ----------------------
 //   phase 1  thread = (pixel, d-group): 8 warps split D (phase1_tile)
@@ -830,7 +792,6 @@ ms_fused_kernel(const FusedArgs a, const __grid_constant__ CUtensorMap sad_map) 
   const int D = g.D;
   unsigned long long* s_bar = reinterpret_cast<unsigned long long*>(smem_raw + L::off_bar);  // [0] rows, [1] sadsob tile
   float* s_red = reinterpret_cast<float*>(smem_raw + L::off_red);    // [8][4][32]
-  float* s_cene = reinterpret_cast<float*>(smem_raw + L::off_cene);  // [DS][32] (aliases staging + s_red)
   float* s_min = reinterpret_cast<float*>(smem_raw + L::off_min);
   float* s_inv = reinterpret_cast<float*>(smem_raw + L::off_inv);
   float* s_lut = reinterpret_cast<float*>(smem_raw + L::off_lut);
@@ -843,7 +804,6 @@ ms_fused_kernel(const FusedArgs a, const __grid_constant__ CUtensorMap sad_map) 
   const TileId t = decode_tile(blockIdx.x, a);
   const int d_lo = grp * a.DC;
   const int d_end = min(D, d_lo + a.DC);  // real disparities of this thread: [d_lo, d_end)
-
   if (kTma) {
     if (tid == 0) {
       mbar_init(&s_bar[0], 1);
@@ -878,118 +838,8 @@ ms_fused_kernel(const FusedArgs a, const __grid_constant__ CUtensorMap sad_map) 
                                        : phase1_tile<L, false>(a, t, smem_raw, s_par, s_cen, lr, px, d_lo);
   if (kTma) mbar_wait(&s_bar[1], 0);
   finish_phase1<L>(s_par, s_red, o, px, grp, d_lo, d_end);
-  __syncthreads();   // phase 1 is over everywhere: from the first sweep on, s_cene overwrites the staging
-                     // buffer (and s_red, which tile_back_half reads before its first barrier)
-  tile_back_half<L, kGroups>(a, t, tid, s_par, s_cen, s_cene, s_red, s_min, s_inv, s_lut, s_lutn, CtaSync());
-}
-
-// ---- warp-specialised persistent kernel (D <= 192; 1 CTA of 20 warps per SM) ----------------
-// Warps 0-11 (producers, one d-group each) run phase 1 of tile i+1 while warps 12-19
-// (consumers) run phases 2, 2b, 3 of tile i: the FADD2-bound cost loop overlaps the
-// MUFU/store-bound back half instead of alternating with it.  The CTA is launched with 96
-// registers per thread (640 * 96 = 61440) and redistributes them with setmaxnreg: producers
-// 120 (the two 5x5 windows of phase 1 live in registers), consumers 56 -- 384*120 + 256*56 =
-// 60416 <= 61440 (setmaxnreg.inc can only draw on what the CTA's own warps released).
-// Two parking buffers and two staging buffers;
-// hand-offs:
-//   rows_full[s]   mbarrier, TMA -> producers     right-image rows of a tile are in stage[s]
-//   sad_full[b]    mbarrier, TMA -> producers     the tile's SAD-of-Sobel box is in park[b] plane 1
-//   park_full[b]   named barrier 3+b, producers arrive / consumers sync: costs + minima are parked
-//   park_empty[b]  named barrier 5+b, consumers arrive / producers sync: phase 3 has read park[b]
-// (named barriers: the waiting side sleeps in hardware; an mbarrier try_wait loop was measured
-// to burn a third of the issued instructions)
-// Tiles are walked with stride gridDim.x; the TMA for tile i+2 is issued as soon as phase 1 of
-// tile i has released its staging buffer, the left-image registers of tile i+1 are prefetched
-// while tile i waits for its SAD-of-Sobel box.
-constexpr int kWsProducers = kGroupsWS * 32;   // 384 threads
-constexpr int kWsConsumers = 256;
-template <int DMAX, int SLACK>
-__global__ void __launch_bounds__(kWsProducers + kWsConsumers, 1)
-ms_fused_ws_kernel(const FusedArgs a, const __grid_constant__ CUtensorMap sad_map) {
-  using L = LayWS<DMAX, SLACK>;
-  constexpr int PS = L::PS;
-  extern __shared__ __align__(128) unsigned char smem_raw[];
-  const FusedGeom& g = a.g;
-  const int D = g.D;
-  unsigned long long* s_bar = reinterpret_cast<unsigned long long*>(smem_raw + L::off_bar);
-  unsigned long long* rows_full = s_bar;        // [2]
-  unsigned long long* sad_full = s_bar + 2;     // [2]
-  float* s_lut = reinterpret_cast<float*>(smem_raw + L::off_lut);
-  float* s_lutn = reinterpret_cast<float*>(smem_raw + L::off_lutn);
-  const int tid = threadIdx.x;
-  if (tid == 0) {
-    for (int i = 0; i < 4; ++i) mbar_init(&s_bar[i], 1);
-    mbar_init_fence();
-  }
-  fill_luts(s_lut, s_lutn, a.k_cen, tid, kWsProducers + kWsConsumers);
   __syncthreads();
-  const int stride = gridDim.x;
-
-  if (tid < kWsProducers) {
-    // ------------------------------ producers ------------------------------
-    asm volatile("setmaxnreg.inc.sync.aligned.u32 120;");
-    const int px = tid % kTile, grp = tid / kTile;
-    const int d_lo = grp * a.DC;
-    const int d_end = min(D, d_lo + a.DC);
-    int tile = blockIdx.x;
-    if (tid == 0) {
-      stage_rows_tma<L>(a, decode_tile(tile, a), smem_raw + L::off_stage, &rows_full[0]);
-      if (tile + stride < a.num_tiles)
-        stage_rows_tma<L>(a, decode_tile(tile + stride, a), smem_raw + L::off_stage + L::st_bytes, &rows_full[1]);
-    }
-    LeftRegs lr;
-    load_left(a, decode_tile(tile, a), px, lr);
-    for (int it = 0; tile < a.num_tiles; ++it, tile += stride) {
-      const int b = it & 1, k = it >> 1;
-      const TileId t = decode_tile(tile, a);
-      unsigned char* stage = smem_raw + L::off_stage + (size_t)b * L::st_bytes;
-      unsigned char* park = smem_raw + L::off_park + (size_t)b * L::pk_bytes;
-      float* s_par = reinterpret_cast<float*>(park);
-      uint8_t* s_cen = park + L::pk_cen;
-      float* s_red = reinterpret_cast<float*>(smem_raw + L::off_red) + (size_t)b * kGroupsWS * 4 * kTile;
-      if (it >= 2) named_bar_sync(5 + b, kWsProducers + kWsConsumers);   // consumers have finished with park[b]
-      if (tid == 0 && !(a.dbg & 8)) {
-        fence_proxy_async();
-        stage_sad_tma(a, &sad_map, t, s_par + PS, &sad_full[b]);
-      }
-      mbar_wait(&rows_full[b], k & 1);
-      build_mean_arrays<L>(stage, D, tid, kWsProducers);
-      named_bar_sync(1, kWsProducers);
-      Phase1Out o;
-      o.min_cen = 0; o.min_ncc = 0.f; o.min_sad = 0.f; o.dmax_sad = D - 1;
-      if (!(a.dbg & 1)) o = phase1_tile<L, false>(a, t, stage, s_par, s_cen, lr, px, d_lo);
-      named_bar_sync(1, kWsProducers);                       // every producer is done with stage[b]
-      if (tid == 0 && tile + 2 * stride < a.num_tiles) {
-        fence_proxy_async();
-        stage_rows_tma<L>(a, decode_tile(tile + 2 * stride, a), stage, &rows_full[b]);
-      }
-      if (tile + stride < a.num_tiles) load_left(a, decode_tile(tile + stride, a), px, lr);   // next tile's left data
-      if (!(a.dbg & 8)) mbar_wait(&sad_full[b], k & 1);
-      finish_phase1<L>(s_par, s_red, o, px, grp, d_lo, d_end);
-      named_bar_arrive(3 + b, kWsProducers + kWsConsumers);
-    }
-  } else {
-    // ------------------------------ consumers ------------------------------
-    asm volatile("setmaxnreg.dec.sync.aligned.u32 56;");
-    const int ctid = tid - kWsProducers;
-    float* s_cene = reinterpret_cast<float*>(smem_raw + L::off_cene);
-    float* s_min = reinterpret_cast<float*>(smem_raw + L::off_min);
-    float* s_inv = reinterpret_cast<float*>(smem_raw + L::off_inv);
-    int tile = blockIdx.x;
-    for (int it = 0; tile < a.num_tiles; ++it, tile += stride) {
-      const int b = it & 1, k = it >> 1;
-      const TileId t = decode_tile(tile, a);
-      unsigned char* park = smem_raw + L::off_park + (size_t)b * L::pk_bytes;
-      float* s_par = reinterpret_cast<float*>(park);
-      uint8_t* s_cen = park + L::pk_cen;
-      const float* s_red = reinterpret_cast<const float*>(smem_raw + L::off_red) + (size_t)b * kGroupsWS * 4 * kTile;
-      named_bar_sync(3 + b, kWsProducers + kWsConsumers);
-      if (!(a.dbg & 2))
-        tile_back_half<L, kGroupsWS>(a, t, ctid, s_par, s_cen, s_cene, s_red, s_min, s_inv, s_lut, s_lutn,
-                                     NamedSync{2, kWsConsumers});
-      if (tile + 2 * stride < a.num_tiles) named_bar_arrive(5 + b, kWsProducers + kWsConsumers);
-    }
-  }
+  tile_back_half<L>(a, t, tid, s_par, s_cen, s_red, s_min, s_inv, s_lut, s_lutn);
 }
 
 // Optional per-kernel timing (msn_profile_enable): CUDA events recorded on the launch
@@ -1015,14 +865,6 @@ static PFN_encodeTiled get_encode_fn() {
     return (PFN_encodeTiled)p;
   }();
   return fn;
-}
-// MSNETS_FUSED_WS=1 selects the warp-specialised persistent kernel where it fits (D <= 192).
-// Measured at 540x960x192: 1.04 ms/pair against 0.90 for the one-tile-per-CTA kernel (its
-// producer and consumer halves each take 0.70 ms alone: both are bound by the shared-memory /
-// LSU pipe and by per-warp dependency latency, so running them side by side does not overlap).
-static bool ws_disabled() {
-  const char* e = getenv("MSNETS_FUSED_WS");
-  return !(e && e[0] == '1');
 }
 static bool tma_disabled() {
   const char* e = getenv("MSNETS_NO_TMA");
@@ -1110,11 +952,6 @@ int launch_ms_fused(const uint8_t* d_left, const uint8_t* d_right, int N, int H,
   a.tiles_x = (g.w + kTile - 1) / kTile;
   const long long tiles = (long long)N * g.h * a.tiles_x;
   MSN_REQUIRE(tiles <= 2147483647LL, "ms_features: too many tiles for one launch");
-  a.num_tiles = (int)tiles;
-  {
-    const char* e = getenv("MSNETS_FUSED_DBG");
-    a.dbg = e ? atoi(e) : 0;
-  }
   // TMA path: 3-D tensor map over the SAD-of-Sobel scratch [N*D][H][Ws], box 32 x 1 x D
   CUtensorMap sad_map;
   memset(&sad_map, 0, sizeof(sad_map));
@@ -1134,26 +971,7 @@ int launch_ms_fused(const uint8_t* d_left, const uint8_t* d_right, int N, int H,
       if (rc != CUDA_SUCCESS) use_tma = false;
     }
   }
-  // warp-specialised persistent kernel: needs TMA and two parking buffers in one SM (D <= 192)
-  if (use_tma && g.D <= 192 && !ws_disabled()) {
-    a.DC = 2 * (((g.D + kGroupsWS - 1) / kGroupsWS + 1) / 2);
-    int dev = 0, sms = 0;
-    MSN_CUDA_OK(cudaGetDevice(&dev));
-    MSN_CUDA_OK(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
-    const unsigned grid = (unsigned)(tiles < sms ? tiles : sms);
-#define MSN_WS_CASE(DMAX)                                                                             \
-  if (g.D <= DMAX) {                                                                                  \
-    auto kern = ms_fused_ws_kernel<DMAX, kSlack>;                                                     \
-    const size_t smem = LayWS<DMAX, kSlack>::bytes;                                                   \
-    MSN_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));  \
-    kern<<<grid, kWsProducers + kWsConsumers, smem, s>>>(a, sad_map);                                                         \
-  } else
-    MSN_WS_CASE(64)
-    MSN_WS_CASE(128)
-    MSN_WS_CASE(192) {}
-#undef MSN_WS_CASE
-  } else {
-    a.DC = 2 * (((g.D + kGroups - 1) / kGroups + 1) / 2);
+  a.DC = 2 * (((g.D + kGroups - 1) / kGroups + 1) / 2);   // phase 1 walks disparity pairs
 #define MSN_FUSED_LAUNCH(DMAX, TMA)                                                                   \
   {                                                                                                   \
     auto kern = ms_fused_kernel<DMAX, TMA>;                                                           \
@@ -1166,15 +984,14 @@ int launch_ms_fused(const uint8_t* d_left, const uint8_t* d_right, int N, int H,
     if (use_tma && DMAX <= 256) MSN_FUSED_LAUNCH(DMAX <= 256 ? DMAX : 256, true)                      \
     else MSN_FUSED_LAUNCH(DMAX, false)                                                                \
   } else
-    MSN_FUSED_CASE(64)
-    MSN_FUSED_CASE(128)
-    MSN_FUSED_CASE(192)
-    MSN_FUSED_CASE(256)
-    MSN_FUSED_CASE(384)
-    MSN_FUSED_CASE(448) { return fail("ms_features: D=%d exceeds the fused kernel's limit", g.D); }
+  MSN_FUSED_CASE(64)
+  MSN_FUSED_CASE(128)
+  MSN_FUSED_CASE(192)
+  MSN_FUSED_CASE(256)
+  MSN_FUSED_CASE(384)
+  MSN_FUSED_CASE(448) { return fail("ms_features: D=%d exceeds the fused kernel's limit", g.D); }
 #undef MSN_FUSED_CASE
 #undef MSN_FUSED_LAUNCH
-  }
   MSN_LAUNCH_OK();
   if (prof) {
     MSN_CUDA_OK(cudaEventRecord(rec.ev[3], s));
