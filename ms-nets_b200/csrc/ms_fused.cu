@@ -86,6 +86,8 @@ struct FusedWs {
   RStat* stat[2];
   float* fimg[2];
   float* sob[2];
+  float* meanR[2]; // ZSAD means of the right image as plain floats; copy 1 is shifted by one column
+  float* luts;     // [128] census AML exponentials + [256] census byte -> channel 0
   float* sadsob;   // [N][D][H][W]
   void* sad_ws;
   size_t total;
@@ -97,6 +99,8 @@ struct FusedWs {
     for (int i = 0; i < 2; ++i) stat[i] = (RStat*)take(np * sizeof(RStat));
     for (int i = 0; i < 2; ++i) fimg[i] = (float*)take(np * sizeof(float));
     for (int i = 0; i < 2; ++i) sob[i] = (float*)take((size_t)g.N * (g.H + kSadRowPad) * g.Ws * sizeof(float));  // zero padded
+    for (int i = 0; i < 2; ++i) meanR[i] = (float*)take((np + 16) * sizeof(float));
+    luts = (float*)take(384 * sizeof(float));
     sadsob = (float*)take((size_t)g.N * g.D * g.H * g.Ws * sizeof(float) + 256);
     sad_ws = take(sadsob_workspace_bytes_n(g.N, g.H, g.W, g.D, kSadW));
     total = off;
@@ -109,7 +113,17 @@ __global__ void __launch_bounds__(128)
 ms_prep_kernel(const uint8_t* __restrict__ left, const uint8_t* __restrict__ right, FusedGeom g,
                uint4* __restrict__ descL, uint4* __restrict__ descR, RStat* __restrict__ statL,
                RStat* __restrict__ statR, float* __restrict__ fL, float* __restrict__ fR,
-               float* __restrict__ sobL, float* __restrict__ sobR) {
+               float* __restrict__ sobL, float* __restrict__ sobR, float* __restrict__ meanR0,
+               float* __restrict__ meanR1, float* __restrict__ luts, float k_cen) {
+  if (blockIdx.x == 0 && blockIdx.y == 0 && blockIdx.z == 0) {
+    // tables for the fused kernel: census AML exponentials exp(-(k^2)/sigma), k = 0..120, and the
+    // channel-0 value k/120 of a parked census byte (a true IEEE division; 255 = no cost ->
+    // clip(fill, 0, 120)/120 = 1)
+    for (int kk = threadIdx.x; kk < 256; kk += blockDim.x) {
+      if (kk < 128) luts[kk] = (kk <= 120) ? ex2_approx(-(float)(kk * kk) * k_cen) : 0.f;
+      luts[128 + kk] = (kk <= 120) ? __fdiv_rn((float)kk, 120.0f) : 1.0f;
+    }
+  }
   const int xp = blockIdx.x * blockDim.x + threadIdx.x;
   const int yp = blockIdx.y;
   const int n = blockIdx.z >> 1, side = blockIdx.z & 1;
@@ -180,6 +194,12 @@ ms_prep_kernel(const uint8_t* __restrict__ left, const uint8_t* __restrict__ rig
   (side ? descR : descL)[po] = make_uint4(w0, w1, w2, w3);
   (side ? statR : statL)[po] = st;
   (side ? fR : fL)[po] = pix;
+  if (side) {
+    // (mean[x-1], mean[x]) must be ONE aligned 64-bit shared load in the fused kernel whatever
+    // the parity of x: the second copy holds the same row shifted right by one element
+    meanR0[po] = st.mean;
+    meanR1[po + 1] = st.mean;
+  }
 }
 
 // ----------------------------------------------------------------- fused --
@@ -188,6 +208,8 @@ struct FusedArgs {
   const uint4 *descL, *descR;
   const RStat *statL, *statR;
   const float *fL, *fR;
+  const float *meanR0, *meanR1;  // right-image ZSAD means; meanR1[x] = mean[x-1]
+  const float* luts;    // [128] + [256], see ms_prep_kernel
   const float* sadsob;  // [N][D][H][Ws] (+ slack)
   float* out;           // [N][8][D][h][w]
   float k_cen, k_ncc, k_sad;
@@ -208,8 +230,8 @@ struct StageLay {
   static constexpr size_t st_desc = 0;                                   // [RW] uint4 census codes
   static constexpr size_t st_stat = st_desc + (size_t)RW * 16;           // [RW] RStat
   static constexpr size_t st_rf = st_stat + (size_t)RW * 16;             // [5][RWF] float pixel rows
-  static constexpr size_t st_mean = st_rf + (size_t)5 * RWF * 4;         // [2][RW + 4] ZSAD means, copy 1 shifted by one
-  static constexpr size_t st_bytes = (st_mean + (size_t)2 * (RW + 4) * 4 + 127) & ~(size_t)127;
+  static constexpr size_t st_mean = st_rf + (size_t)5 * RWF * 4;         // [2][RWF] ZSAD means, copy 1 shifted by one
+  static constexpr size_t st_bytes = (st_mean + (size_t)2 * RWF * 4 + 127) & ~(size_t)127;
 };
 
 // Parking buffer of one tile: raw costs (later: AML exponentials) for every (d, pixel).
@@ -355,9 +377,16 @@ __device__ __forceinline__ void stage_right(const FusedArgs& a, const TileId& t,
     const int r = i / nvec, v = i - r * nvec;
     cp_async16(s_rf + r * L::RWF + 4 * v, a.fR + img_off + (size_t)(Yp - 2 + r) * g.Wp + fstart + 4 * v);
   }
+  float* s_mean = reinterpret_cast<float*>(buf + L::st_mean);
+  const int mstart = XbaseP & ~3;
+  const int nvm = (RWn + 3 + 3) >> 2;
+  for (int i = threadIdx.x; i < 2 * nvm; i += NT) {
+    const int c = i / nvm, v = i - c * nvm;
+    cp_async16(s_mean + c * L::RWF + 4 * v, (c ? a.meanR1 : a.meanR0) + img_off + (size_t)Yp * g.Wp + mstart + 4 * v);
+  }
 }
 
-// Same data through the TMA engine: seven 1-D bulk copies issued by a single thread,
+// Same data through the TMA engine: nine 1-D bulk copies issued by a single thread,
 // completion counted in bytes on `bar`.
 template <class L>
 __device__ __forceinline__ void stage_rows_tma(const FusedArgs& a, const TileId& t, unsigned char* buf,
@@ -371,13 +400,18 @@ __device__ __forceinline__ void stage_rows_tma(const FusedArgs& a, const TileId&
   const int fstart = (XbaseP - 2) & ~3;
   const int nvec = (RWn + 4 + 3 + 3) >> 2;
   const unsigned row_bytes = (unsigned)RWn * 16u, frow_bytes = (unsigned)nvec * 16u;
-  mbar_expect_tx(bar, 2u * row_bytes + 5u * frow_bytes);
+  const int mstart = XbaseP & ~3;
+  const unsigned mrow_bytes = (unsigned)((RWn + 3 + 3) >> 2) * 16u;
+  mbar_expect_tx(bar, 2u * row_bytes + 5u * frow_bytes + 2u * mrow_bytes);
   bulk_load(buf + L::st_desc, a.descR + img_off + (size_t)Yp * g.Wp + XbaseP, row_bytes, bar);
   bulk_load(buf + L::st_stat, a.statR + img_off + (size_t)Yp * g.Wp + XbaseP, row_bytes, bar);
   float* s_rf = reinterpret_cast<float*>(buf + L::st_rf);
 #pragma unroll
   for (int r = 0; r < 5; ++r)
     bulk_load(s_rf + r * L::RWF, a.fR + img_off + (size_t)(Yp - 2 + r) * g.Wp + fstart, frow_bytes, bar);
+  float* s_mean = reinterpret_cast<float*>(buf + L::st_mean);
+  bulk_load(s_mean, a.meanR0 + img_off + (size_t)Yp * g.Wp + mstart, mrow_bytes, bar);
+  bulk_load(s_mean + L::RWF, a.meanR1 + img_off + (size_t)Yp * g.Wp + mstart, mrow_bytes, bar);
 }
 
 // The tile's D x 32 SAD-of-Sobel costs: ONE 3-D tensor copy straight into parking plane 1.
@@ -389,22 +423,9 @@ __device__ __forceinline__ void stage_sad_tma(const FusedArgs& a, const CUtensor
   tma_load_3d(park_plane1, sad_map, t.x0 + g.bwl + g.sxo, t.y + g.bh, t.n * g.D, bar_sad);  // inner coordinate % 4 == 0
 }
 
-// ZSAD means of the staged right-image row as two float arrays, the second shifted by one
-// entry, so that the means of a disparity pair (columns X-d-1, X-d) are ONE aligned 64-bit
-// shared load.  Called by NT threads with ids tid; a barrier among them must follow.
-template <class L>
-__device__ __forceinline__ void build_mean_arrays(unsigned char* stage, int D, int tid, int NT) {
-  const RStat* st = reinterpret_cast<const RStat*>(stage + L::st_stat);
-  float* mA = reinterpret_cast<float*>(stage + L::st_mean);
-  float* mB = mA + (L::RW + 4);
-  for (int i = tid; i < D + kTile - 1 + L::kSl; i += NT) {
-    const float m = st[i].mean;
-    mA[i] = m;
-    mB[i + 1] = m;
-  }
-}
-
-// A pixel's own left-image data: census code, stats, 5x5 float window.
+// A pixel's own left-image data: census code, stats, 5x5 float window.  Loaded straight from
+// global memory before the staging barrier, so the latency overlaps the TMA round trip
+// (staging it through TMA as well was measured 1.5 % slower).
 struct LeftRegs {
   uint4 desc;
   uint4 stat;
@@ -422,15 +443,6 @@ __device__ __forceinline__ void load_left(const FusedArgs& a, const TileId& t, i
     const float* gf = a.fL + img_off + (size_t)(Yp - 2 + r) * g.Wp + (Xp - 2);
 #pragma unroll
     for (int c = 0; c < 5; ++c) lr.px[r][c] = __ldg(gf + c);
-  }
-}
-
-// Census AML exponentials exp(-(k^2)/sigma) for k = 0..120 and the channel-0 table k/120 (a
-// true IEEE division; 255 = no cost -> clip(fill, 0, 120)/120 = 1).
-__device__ __forceinline__ void fill_luts(float* s_lut, float* s_lutn, float k_cen, int tid, int NT) {
-  for (int kk = tid; kk < 256; kk += NT) {
-    if (kk < 128) s_lut[kk] = (kk <= 120) ? ex2_approx(-(float)(kk * kk) * k_cen) : 0.f;
-    s_lutn[kk] = (kk <= 120) ? __fdiv_rn((float)kk, 120.0f) : 1.0f;
   }
 }
 
@@ -491,9 +503,11 @@ __device__ __forceinline__ Phase1Out phase1_tile(const FusedArgs& a, const TileI
   const float* rfp = s_rf + shift + ir0 - 1;   // column (X - dB - 2) of the pair's second disparity
   const uint4* dscp = s_desc + ir0;
   const uint4* sttp = s_stat + ir0;
-  // (mean[ir-1], mean[ir]) as one 8-byte aligned load: copy 0 when ir-1 is even, else copy 1 (shifted)
+  // (mean[ir-1], mean[ir]) as one 8-byte aligned load: the plain copy when its float index is
+  // even, else the copy shifted by one (staged from the aligned column XbaseP & ~3)
+  const int im = (XbaseP & 3) + ir0 - 1;
   const float2* mnp = reinterpret_cast<const float2*>(
-      reinterpret_cast<const float*>(stage + L::st_mean) + (((ir0 - 1) & 1) ? (L::RW + 4) + ir0 : ir0 - 1));
+      reinterpret_cast<const float*>(stage + L::st_mean) + ((im & 1) ? L::RWF + im + 1 : im));
   float wv[5][6];  // sliding 5x6 right window; logical column j lives in wv[.][(j - 2*s) mod 6]
 #pragma unroll
   for (int r = 0; r < 5; ++r)
@@ -822,17 +836,13 @@ ms_fused_kernel(const FusedArgs a, const __grid_constant__ CUtensorMap sad_map) 
     for (int d = d_lo; d < d_end; ++d, src += splane, dst += kTile) cp_async4(dst, src);
     stage_right<L, NT>(a, t, smem_raw);
   }
-  fill_luts(s_lut, s_lutn, a.k_cen, tid, NT);
+  if (tid < 128) s_lut[tid] = __ldg(a.luts + tid);
+  s_lutn[tid] = __ldg(a.luts + 128 + tid);
   LeftRegs lr;
   load_left(a, t, px, lr);
-  __syncthreads();                       // barrier init + LUTs visible to everyone
+  if (!kTma) cp_async_wait_all();
+  __syncthreads();                       // barrier init, LUTs (and LDGSTS data) visible to everyone
   if (kTma) mbar_wait(&s_bar[0], 0);
-  else {
-    cp_async_wait_all();
-    __syncthreads();
-  }
-  build_mean_arrays<L>(smem_raw, D, tid, NT);
-  __syncthreads();
 
   const Phase1Out o = (a.DC % 6 == 0) ? phase1_tile<L, true>(a, t, smem_raw, s_par, s_cen, lr, px, d_lo)
                                        : phase1_tile<L, false>(a, t, smem_raw, s_par, s_cen, lr, px, d_lo);
@@ -933,7 +943,8 @@ int launch_ms_fused(const uint8_t* d_left, const uint8_t* d_right, int N, int H,
     MSN_CUDA_OK(cudaMemsetAsync(ws.sob[i], 0, (size_t)N * (H + kSadRowPad) * g.Ws * sizeof(float), s));
   dim3 pgrid(div_up(g.Wp, 128), g.Hp, 2 * N);
   ms_prep_kernel<<<pgrid, 128, 0, s>>>(d_left, d_right, g, ws.desc[0], ws.desc[1], ws.stat[0], ws.stat[1],
-                                       ws.fimg[0], ws.fimg[1], ws.sob[0], ws.sob[1]);
+                                       ws.fimg[0], ws.fimg[1], ws.sob[0], ws.sob[1], ws.meanR[0], ws.meanR[1],
+                                       ws.luts, aml_scale(p->cens_sigma));
   MSN_LAUNCH_OK();
   if (prof) MSN_CUDA_OK(cudaEventRecord(rec.ev[1], s));
   if (launch_sadsob5_padded(ws.sob[0], ws.sob[1], N, H, W, g.D, 0, ws.sadsob + g.sxo, ws.sad_ws, s)) return 1;
@@ -944,6 +955,8 @@ int launch_ms_fused(const uint8_t* d_left, const uint8_t* d_right, int N, int H,
   a.descL = ws.desc[0]; a.descR = ws.desc[1];
   a.statL = ws.stat[0]; a.statR = ws.stat[1];
   a.fL = ws.fimg[0]; a.fR = ws.fimg[1];
+  a.meanR0 = ws.meanR[0]; a.meanR1 = ws.meanR[1];
+  a.luts = ws.luts;
   a.sadsob = ws.sadsob;
   a.out = d_out;
   a.k_cen = aml_scale(p->cens_sigma);
