@@ -464,7 +464,9 @@ struct Phase1Out {
   float min_ncc, min_sad;
   int dmax_sad;
 };
-template <class L, bool kMult6>
+// kAllValid: every (pixel, d) of the tile has all three costs and there are no dummy steps (a
+// CTA-uniform property of interior tiles), so the validity selects drop out of the loop.
+template <class L, bool kMult6, bool kAllValid>
 __device__ __forceinline__ Phase1Out phase1_tile(const FusedArgs& a, const TileId& t, const unsigned char* stage,
                                                  float* s_par, uint8_t* s_cen, const LeftRegs& lr, int px,
                                                  int d_lo) {
@@ -531,8 +533,8 @@ __device__ __forceinline__ Phase1Out phase1_tile(const FusedArgs& a, const TileI
       // census: Hamming distance of the packed codes (matchers.cpp:323-337)
       const int cenA = __popc(ld.x ^ rdA.x) + __popc(ld.y ^ rdA.y) + __popc(ld.z ^ rdA.z) + __popc(ld.w ^ rdA.w);
       const int cenB = __popc(ld.x ^ rdB.x) + __popc(ld.y ^ rdB.y) + __popc(ld.z ^ rdB.z) + __popc(ld.w ^ rdB.w);
-      const int cen_bA = (dA <= dmax_cen) ? cenA : 255;
-      const int cen_bB = (dB <= dmax_cen) ? cenB : 255;
+      const int cen_bA = (kAllValid || dA <= dmax_cen) ? cenA : 255;
+      const int cen_bB = (kAllValid || dB <= dmax_cen) ? cenB : 255;
 
       // NCC: P exact in fp32 (< 2^24); scaling in fp64 left to right (matchers.cpp:200-201)
       float PA = 0.f, PB = 0.f;
@@ -549,8 +551,8 @@ __device__ __forceinline__ Phase1Out phase1_tile(const FusedArgs& a, const TileI
       float nccB = (float)__dmul_rn(__dmul_rn(-(double)numB, ls.C), rsB.C);
       nccA = (fabsf(nccA) <= 3.0e38f) ? nccA : 1.0f;  // either C was inf (flat window), :196,204
       nccB = (fabsf(nccB) <= 3.0e38f) ? nccB : 1.0f;
-      nccA = (dA <= dmax_ncc) ? nccA : kFill;
-      nccB = (dB <= dmax_ncc) ? nccB : kFill;
+      nccA = (kAllValid || dA <= dmax_ncc) ? nccA : kFill;
+      nccB = (kAllValid || dB <= dmax_ncc) ? nccB : kFill;
 
       // ZSAD: 25 taps row-major, ((L - mL) - R) + mR, sequential fp32 (matchers.cpp:499-506)
       const f32x2 m2 = pk2(mBA.x, mBA.y);
@@ -575,10 +577,11 @@ __device__ __forceinline__ Phase1Out phase1_tile(const FusedArgs& a, const TileI
       }
       float zA, zB;
       upk2(acc, zB, zA);
-      zA = (dA <= dmax_sad) ? zA : kFill;
-      zB = (dB <= dmax_sad) ? zB : kFill;
+      zA = (kAllValid || dA <= dmax_sad) ? zA : kFill;
+      zB = (kAllValid || dB <= dmax_sad) ? zB : kFill;
 
-      const int dsA = min(dA, D), dsB = min(dB, D);  // dummy steps (d >= D) park into the scratch plane
+      const int dsA = kAllValid ? dA : min(dA, D);   // dummy steps (d >= D) park into the scratch plane
+      const int dsB = kAllValid ? dB : min(dB, D);
       s_cen[dsA * kTile + px] = (uint8_t)cen_bA;
       s_cen[dsB * kTile + px] = (uint8_t)cen_bB;
       s_par[dsA * kTile + px] = nccA;
@@ -844,8 +847,17 @@ ms_fused_kernel(const FusedArgs a, const __grid_constant__ CUtensorMap sad_map) 
   __syncthreads();                       // barrier init, LUTs (and LDGSTS data) visible to everyone
   if (kTma) mbar_wait(&s_bar[0], 0);
 
-  const Phase1Out o = (a.DC % 6 == 0) ? phase1_tile<L, true>(a, t, smem_raw, s_par, s_cen, lr, px, d_lo)
-                                       : phase1_tile<L, false>(a, t, smem_raw, s_par, s_cen, lr, px, d_lo);
+  // interior tile: all 32 pixels have every cost at every disparity, and the d-groups cover D exactly
+  const int Xl = t.x0 + g.bwl, Yr = t.y + g.bh;
+  const bool all_valid = (kGroups * a.DC == D) && (Xl - 5 >= D - 1) && (Xl + kTile - 1 < g.W - 6) && (Yr >= 5) &&
+                         (Yr < g.H - 6);
+  Phase1Out o;
+  if (a.DC % 6 == 0) {
+    if (all_valid) o = phase1_tile<L, true, true>(a, t, smem_raw, s_par, s_cen, lr, px, d_lo);
+    else o = phase1_tile<L, true, false>(a, t, smem_raw, s_par, s_cen, lr, px, d_lo);
+  } else {
+    o = phase1_tile<L, false, false>(a, t, smem_raw, s_par, s_cen, lr, px, d_lo);
+  }
   if (kTma) mbar_wait(&s_bar[1], 0);
   finish_phase1<L>(s_par, s_red, o, px, grp, d_lo, d_end);
   __syncthreads();
