@@ -143,6 +143,25 @@ def test_ms_features_one_call(ms, oracle, H, W, D, bh, bl, br, left_only):
     _check_features(got, want, lr=not left_only)
 
 
+@pytest.mark.parametrize("H,W,D", [(34, 300, 200), (32, 352, 300), (32, 470, 448)])
+def test_ms_features_fused_large_d(ms, oracle, H, W, D):
+    """D above 192 selects the 256 / 384 / 448 instantiations of the fused kernel (TMA box up to
+    256 disparities, LDGSTS staging above); interior tiles exist (W > D + 37 + border)."""
+    L, R = synth_pair(H, W, 900 + D, shift=9)
+    got = ms.cbmv.ms_features(L, R, D, board_h=10, board_w_left=10, board_w_right=10)
+    want = oracle.ms_features(L, R, D, board_h=10, board_w_left=10, board_w_right=10)
+    _check_features(got, want)
+
+
+def test_ms_features_fused_interior_tiles(ms, oracle):
+    """D = 8 * 6: the d-groups cover D exactly, so tiles right of column D + 5 take the
+    instantiation without validity selects; the image is wide enough to have several."""
+    L, R = synth_pair(40, 260, 77, shift=11)
+    got = ms.cbmv.ms_features(L, R, 48, board_h=10, board_w_left=10, board_w_right=10)
+    want = oracle.ms_features(L, R, 48, board_h=10, board_w_left=10, board_w_right=10)
+    _check_features(got, want)
+
+
 def test_ms_features_generic_path_matches(ms, oracle, monkeypatch):
     """the three-phase global-memory path (used for slabs and non-default windows)."""
     monkeypatch.setenv("MSNETS_FORCE_GENERIC", "1")
