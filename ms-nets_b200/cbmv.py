@@ -5,6 +5,7 @@
     extract_features_left  cbmv_generator.py:258-308
     extract_features_lr    cbmv_generator.py:84-254
     get_default_args_dict  cbmv_generator.py:434-462
+    generate_test_cbmv     cbmv_generator.py:727-861 (device-resident: returns a CUDA tensor)
 
 plus the B200-native entry points that skip the reference's intermediate layouts:
 
@@ -156,3 +157,67 @@ class MSFeatureExtractor(object):
                                                       ctypes.byref(self.params), out.data_ptr(),
                                                       self.workspace.data_ptr(), self.workspace.numel(), stream))
         return out
+
+
+_extractors = {}
+
+
+def generate_test_cbmv(limg_name, rimg_name, crop_height=384, crop_width=1248, encoder_ds=64, maxdisp=192,
+                       args_dict=None, is_left_only=True, device=None):
+    """cbmv_generator.py:727-861, device-resident: same arguments and return
+    tuple `(features, h, w, crop_height, crop_width)`, but `features` is a float32 CUDA tensor
+    [C, D, crop_height, crop_width] produced where the 3D CNN consumes it -- the caller's
+    `features.cuda()` (main_msnet.py:571-572) becomes a no-op.
+
+    limg_name / rimg_name: file names (read with cv2.imread(name, 0) as the reference does) or
+    uint8 gray images.  As in the reference, crop_height / crop_width are recomputed from the
+    image size: zero padding on top and on the right up to a multiple of encoder_ds (:780-788),
+    then a 10-pixel zero border on all sides so the matchers' border fill lands outside the crop
+    (:819-834).  ds_scale (args_dict) must be 1: the reference's default 2 goes through
+    skimage.transform.rescale, which is not ported yet."""
+    import torch
+    ad = get_default_args_dict()
+    ad["ds_scale"] = 1
+    if args_dict is not None:
+        ad.update(args_dict)
+    if int(ad["ds_scale"]) != 1:
+        raise NotImplementedError("generate_test_cbmv: ds_scale=%r needs the anti-aliased rescale "
+                                  "(skimage.transform.rescale), not ported yet" % (ad["ds_scale"],))
+    imgs = []
+    for src in (limg_name, rimg_name):
+        if isinstance(src, str):
+            import cv2
+            im = cv2.imread(src, 0)
+            if im is None:
+                raise ValueError("generate_test_cbmv: cannot read %r" % (src,))
+            src = im
+        a = np.ascontiguousarray(src)
+        if a.dtype != np.uint8 or a.ndim != 2:
+            raise ValueError("generate_test_cbmv: expected uint8 gray images [H,W]")
+        imgs.append(a)
+    if imgs[0].shape != imgs[1].shape:
+        raise ValueError("generate_test_cbmv: left and right image sizes differ")
+    h, w = imgs[0].shape
+    crop_width = w + (encoder_ds - w % encoder_ds) % encoder_ds
+    crop_height = h + (encoder_ds - h % encoder_ds) % encoder_ds
+    if not torch.cuda.is_available():
+        raise _lib.MsnetsError("generate_test_cbmv needs a CUDA device (no CPU fallback)")
+    dev = torch.device("cuda", torch.cuda.current_device()) if device is None else torch.device(device)
+    board = 10
+    Hb, Wb = crop_height + 2 * board, crop_width + 2 * board
+    pair = torch.zeros((2, 1, Hb, Wb), dtype=torch.uint8, device=dev)
+    for i, a in enumerate(imgs):   # top/right padding and the border are the zeros already there
+        pair[i, 0, board + crop_height - h:board + crop_height, board:board + w] = torch.from_numpy(a).to(dev)
+    key = (dev.index, Hb, Wb, int(maxdisp), bool(is_left_only), ad["censw"], ad["nccw"], ad["sadw"], ad["sobelw"],
+           float(ad["cens_sigma"]), float(ad["ncc_sigma"]), float(ad["sad_sigma"]))
+    ex = _extractors.get(key)
+    if ex is None:
+        _extractors.clear()        # one cached workspace: test images usually share a size
+        ex = MSFeatureExtractor(1, Hb, Wb, maxdisp=int(maxdisp) // int(ad["ds_scale"]), left_only=is_left_only,
+                                device=dev, censw=ad["censw"], nccw=ad["nccw"], sadw=ad["sadw"],
+                                sobelw=ad["sobelw"], board_h=board, board_w_left=board, board_w_right=board,
+                                cens_sigma=ad["cens_sigma"], ncc_sigma=ad["ncc_sigma"], sad_sigma=ad["sad_sigma"])
+        _extractors[key] = ex
+    with torch.cuda.device(dev):
+        features = ex(pair[0], pair[1])[0]
+    return features, h, w, crop_height, crop_width

@@ -5,6 +5,7 @@
     get_costs             -> src/dataloader/cbmv_generator.py:27-79
     extract_features_left -> src/dataloader/cbmv_generator.py:258-308
     extract_features_lr   -> src/dataloader/cbmv_generator.py:84-254
+    generate_test_cbmv    -> src/dataloader/cbmv_generator.py:727-861 (ds_scale = 1 branch)
     WTA pictures          -> main_msnet.py:444-448 (np.argmin over D)
     soft-argmin           -> src/models/gcnet_3dcnn.py:127-141
 * definitions for the north-star items that have NO reference code (SURVEY.md
@@ -267,6 +268,37 @@ def ms_features(iml, imr, maxdisp=192, board_h=10, board_w_left=10, board_w_righ
 
 
 # --------------------------------------------------------------- soft-argmin
+def pad_test_pair(imgl, imgr, encoder_ds):
+    """cbmv_generator.py:780-788 + :819-823: zero-pad top/right to a multiple of encoder_ds,
+    then a 10-pixel zero border on all four sides.  Returns (L, R, h, w, crop_h, crop_w)."""
+    h, w = imgl.shape[:2]
+    crop_w = w + (encoder_ds - w % encoder_ds) % encoder_ds
+    crop_h = h + (encoder_ds - h % encoder_ds) % encoder_ds
+    out = []
+    for im in (imgl, imgr):
+        a = np.pad(im, ((crop_h - h, 0), (0, crop_w - w)), "constant").astype(np.uint8)
+        out.append(np.ascontiguousarray(np.pad(a, ((10, 10), (10, 10)), "constant").astype(np.uint8)))
+    return out[0], out[1], h, w, crop_h, crop_w
+
+
+def generate_test_cbmv(imgl, imgr, encoder_ds=64, maxdisp=192, args_dict=None, is_left_only=True):
+    """cbmv_generator.py:727-861 on two uint8 gray images (the reference reads them with
+    cv2.imread(name, 0)); only the ds_scale == 1 branch (skimage's rescale is not restated).
+    Returns (features float32 [C, D, crop_h, crop_w], h, w, crop_h, crop_w)."""
+    ad = dict(censw=11, nccw=3, sadw=5, sobelw=5, cens_sigma=128.0, ncc_sigma=0.02, sad_sigma=20000.0,
+              sobel_sigma=20000.0, ds_scale=1)
+    if args_dict:
+        ad.update(args_dict)
+    if int(ad["ds_scale"]) != 1:
+        raise NotImplementedError("oracle: ds_scale != 1 needs skimage.transform.rescale")
+    L, R, h, w, crop_h, crop_w = pad_test_pair(imgl, imgr, encoder_ds)
+    costs = get_costs(L, R, maxdisp // int(ad["ds_scale"]), ad["censw"], ad["nccw"], ad["sadw"], ad["sobelw"],
+                      10, 10, 10)
+    fn = extract_features_left if is_left_only else extract_features_lr
+    f = fn(*costs, cens_sigma=ad["cens_sigma"], ncc_sigma=ad["ncc_sigma"], sad_sigma=ad["sad_sigma"])
+    return f, h, w, crop_h, crop_w
+
+
 def soft_argmin(logits):
     """gcnet_3dcnn.py:127-141: softmax over dim 1 of [N,D,H,W], expectation of d."""
     x = _f32(logits)

@@ -116,8 +116,35 @@ def soft_argmin_vectors():
     return out
 
 
+def test_cbmv_vectors(gen):
+    """generate_test_cbmv (cbmv_generator.py:727-861) run on two PNG files written here, with
+    ds_scale = 1 (the reference's ds_scale = 2 branch needs skimage, absent in this container).
+    Stores the inputs, the returned sizes, the SHA-256 of the feature tensors and every 5th
+    value of them."""
+    import tempfile
+    import cv2
+    L, R = synth_pair(27, 45, 777, 4)
+    out = {"L": L, "R": R}
+    with tempfile.TemporaryDirectory() as td:
+        fl, fr = os.path.join(td, "l.png"), os.path.join(td, "r.png")
+        cv2.imwrite(fl, L)
+        cv2.imwrite(fr, R)
+        for tag, left_only in (("left", True), ("lr", False)):
+            ad = gen.get_default_args_dict()
+            ad["ds_scale"] = 1
+            f, h, w, ch, cw = gen.generate_test_cbmv(fl, fr, encoder_ds=16, maxdisp=24, args_dict=ad,
+                                                     is_left_only=left_only)
+            f = f.numpy()
+            assert f.dtype == np.float32
+            out["meta_" + tag] = np.array([h, w, ch, cw] + list(f.shape), np.int64)
+            out["sha_" + tag] = np.array(digest(f))
+            out["sub_" + tag] = f.reshape(-1)[::5].copy()
+    return out
+
+
 def main():
     mtc, fte, gen = import_reference_glue()
+    np.savez_compressed(os.path.join(HERE, "test_cbmv.npz"), **test_cbmv_vectors(gen))
     for name, cfg in SMALL.items():
         np.savez_compressed(os.path.join(HERE, name + ".npz"), **run_case(mtc, fte, gen, *cfg, full=True))
     for name, cfg in MEDIUM.items():

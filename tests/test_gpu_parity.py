@@ -286,3 +286,28 @@ def test_full_size_properties(ms):
     assert torch.equal(am0.long(), f[0, 0].argmin(0))
     # the true shift (7 px) wins the census WTA on the bulk of the image
     assert float((am0[:, 200:] == 7).float().mean()) > 0.99
+
+
+@pytest.mark.parametrize("left_only", [True, False])
+def test_generate_test_cbmv_device_resident(ms, oracle, golden_dir, left_only):
+    """cbmv.generate_test_cbmv mirrors cbmv_generator.py:727-861 but hands back a CUDA tensor."""
+    import torch
+    g = np.load(os.path.join(golden_dir, "test_cbmv.npz"))
+    tag = "left" if left_only else "lr"
+    f, h, w, ch, cw = ms.cbmv.generate_test_cbmv(g["L"], g["R"], encoder_ds=16, maxdisp=24, is_left_only=left_only)
+    assert isinstance(f, torch.Tensor) and f.is_cuda and f.dtype == torch.float32
+    want, h2, w2, ch2, cw2 = oracle.generate_test_cbmv(g["L"], g["R"], encoder_ds=16, maxdisp=24,
+                                                       is_left_only=left_only)
+    assert (h, w, ch, cw) == (h2, w2, ch2, cw2)
+    assert [h, w, ch, cw] + list(f.shape) == g["meta_" + tag].tolist()
+    got = f.cpu().numpy()
+    _check_features(got, want, lr=not left_only)
+    # and against the reference's own output (every 5th value is stored)
+    ref = g["sub_" + tag]
+    sub = got.reshape(-1)[::5]
+    C = got.shape[0]
+    chan = (np.arange(got.size)[::5] // (got.size // C)) % 8
+    assert np.array_equal(sub[chan < 4], ref[chan < 4])
+    assert np.abs(sub - ref).max() <= AML_ATOL
+    with pytest.raises(NotImplementedError):
+        ms.cbmv.generate_test_cbmv(g["L"], g["R"], args_dict={"ds_scale": 2})

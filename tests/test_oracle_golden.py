@@ -11,7 +11,7 @@ from tests._synth import digest, synth_pair
 
 CASES = sorted(os.path.basename(p)[:-4] for p in
                glob.glob(os.path.join(os.path.dirname(__file__), "golden", "*.npz"))
-               if not p.endswith("soft_argmin.npz"))
+               if not p.endswith("soft_argmin.npz") and not p.endswith("test_cbmv.npz"))
 
 
 def _oracle_outputs(O, L, R, D, border):
@@ -89,3 +89,14 @@ def test_aml_properties(oracle):
     s = a.sum(1)
     assert np.allclose(np.delete(s, 5), 1.0, atol=1e-5)
     assert np.all(a[6, 10:] == 0)
+
+
+@pytest.mark.parametrize("tag,left_only", [("left", True), ("lr", False)])
+def test_oracle_generate_test_cbmv_matches_reference(oracle, golden_dir, tag, left_only):
+    """generate_test_cbmv (cbmv_generator.py:727-861): pad-to-multiple policy, 10 px border and
+    feature assembly, against the reference function run on PNG files (ds_scale = 1)."""
+    g = np.load(os.path.join(golden_dir, "test_cbmv.npz"))
+    f, h, w, ch, cw = oracle.generate_test_cbmv(g["L"], g["R"], encoder_ds=16, maxdisp=24, is_left_only=left_only)
+    assert [h, w, ch, cw] + list(f.shape) == g["meta_" + tag].tolist()
+    assert digest(f) == str(g["sha_" + tag])
+    assert np.array_equal(f.reshape(-1)[::5], g["sub_" + tag])
