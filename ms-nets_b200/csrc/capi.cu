@@ -497,7 +497,7 @@ int msn_ms_features_dev(const uint8_t* d_left, const uint8_t* d_right, int N, in
   cudaStream_t s = as_stream(stream);
   char* base = (char*)(((uintptr_t)d_workspace + 255) & ~(uintptr_t)255);
   if (fused_supported(p, g.Dn) && sadsob_fast_pitch(W + 35) > 0 && !force_generic())
-    return launch_ms_fused(d_left, d_right, N, H, W, p, d_out, base, s);
+    return launch_ms_fused(d_left, d_right, N, H, W, p, d_out, nullptr, base, s);
   GenericWs ws;
   ws.carve(base, g, p);
   const size_t n = (size_t)g.h * g.w;
@@ -538,9 +538,14 @@ int msn_profile_read(double* prep_ms, double* sadsob_ms, double* fused_ms, int* 
 
 // slab phases (multi-GPU disparity sharding); workspace sized by
 // msn_ms_slab_workspace_bytes for the slab in p.
+static bool slab_fused(const msn_ms_params* p, const Geometry& g, int W) {
+  return fused_supported(p, g.Dn) && sadsob_fast_pitch(W + 35) > 0 && !force_generic();
+}
+
 size_t msn_ms_slab_workspace_bytes(int N, int H, int W, const msn_ms_params* p) {
   Geometry g;
   if (resolve(p, N, H, W, &g, "ms_slab_workspace_bytes")) return 0;
+  if (slab_fused(p, g, W)) return fused_workspace_bytes(N, H, W, g.Dn, p) + 256;
   GenericWs ws;
   ws.carve(nullptr, g, p);
   return ws.total + 256;
@@ -554,8 +559,11 @@ int msn_ms_slab_phase_a_dev(const uint8_t* d_left, const uint8_t* d_right, int N
   MSN_REQUIRE(d_left && d_right && d_out && d_min && d_workspace, "ms_slab_phase_a: null pointer argument");
   MSN_REQUIRE(workspace_bytes >= msn_ms_slab_workspace_bytes(N, H, W, p), "ms_slab_phase_a: workspace too small");
   cudaStream_t s = as_stream(stream);
+  char* base = (char*)(((uintptr_t)d_workspace + 255) & ~(uintptr_t)255);
+  // default windows, left view: phase 1 of the fused kernel computes the slab's costs on chip
+  if (slab_fused(p, g, W)) return launch_ms_fused(d_left, d_right, N, H, W, p, d_out, d_min, base, s);
   GenericWs ws;
-  ws.carve((char*)(((uintptr_t)d_workspace + 255) & ~(uintptr_t)255), g, p);
+  ws.carve(base, g, p);
   const size_t n = (size_t)g.h * g.w;
   const int nm = p->lr ? 8 : 4;
   for (int i = 0; i < N; ++i)

@@ -61,7 +61,9 @@ struct __align__(16) RStat {
 };
 
 struct FusedGeom {
-  int N, H, W, h, w, D, bh, bwl;
+  int N, H, W, h, w, bh, bwl;
+  int D;    // disparities handled by this launch: [d0, d0 + D)
+  int d0;   // first disparity (> 0 only for a disparity slab)
   int Hp, Wp, padL;
   int sxo, Ws;   // SAD-of-Sobel scratch: column offset and row pitch (tile starts land on 16 B)
   __host__ __device__ size_t img_px() const { return (size_t)Hp * Wp; }
@@ -69,11 +71,13 @@ struct FusedGeom {
 
 FusedGeom make_geom(int N, int H, int W, const msn_ms_params* p) {
   FusedGeom g;
-  g.N = N; g.H = H; g.W = W; g.D = p->ndisp;
+  g.N = N; g.H = H; g.W = W;
+  g.d0 = p->d_count > 0 ? p->d_begin : 0;
+  g.D = p->d_count > 0 ? p->d_count : p->ndisp;
   g.bh = p->board_h; g.bwl = p->board_w_left;
   g.h = H - 2 * p->board_h;
   g.w = W - p->board_w_left - p->board_w_right;
-  g.padL = (g.D + 1 + kSlack + 8 + 7) & ~7;  // D-1 columns of disparity + dummy-step slack + halo/alignment
+  g.padL = (g.d0 + g.D + 1 + kSlack + 8 + 7) & ~7;  // d0+D-1 columns of disparity + dummy-step slack + halo/alignment
   g.Hp = H + 2 * kPadT;
   g.Wp = (W + g.padL + kPadR + 3) & ~3;
   g.sxo = (4 - (g.bwl & 3)) & 3;            // x0 + bwl + sxo is a multiple of 4 for every tile
@@ -212,6 +216,7 @@ struct FusedArgs {
   const float* luts;    // [128] + [256], see ms_prep_kernel
   const float* sadsob;  // [N][D][H][Ws] (+ slack)
   float* out;           // [N][8][D][h][w]
+  float* mins;          // slab phase A only: [N][4][h][w] per-pixel minima of this launch's disparities
   float k_cen, k_ncc, k_sad;
   int DC;               // disparity steps per d-group (even: phase 1 walks disparity pairs)
   int tiles_x;
@@ -359,7 +364,7 @@ __device__ __forceinline__ void stage_right(const FusedArgs& a, const TileId& t,
   const FusedGeom& g = a.g;
   const int D = g.D;
   const int RWn = D + kTile - 1 + L::kSl;
-  const int XbaseP = t.x0 + g.bwl - (D - 1) - L::kSl + g.padL;
+  const int XbaseP = t.x0 + g.bwl - (g.d0 + D - 1) - L::kSl + g.padL;
   const int Yp = t.y + g.bh + kPadT;
   const size_t img_off = (size_t)t.n * g.img_px();
   const uint4* gd = a.descR + img_off + (size_t)Yp * g.Wp + XbaseP;
@@ -394,7 +399,7 @@ __device__ __forceinline__ void stage_rows_tma(const FusedArgs& a, const TileId&
   const FusedGeom& g = a.g;
   const int D = g.D;
   const int RWn = D + kTile - 1 + L::kSl;
-  const int XbaseP = t.x0 + g.bwl - (D - 1) - L::kSl + g.padL;
+  const int XbaseP = t.x0 + g.bwl - (g.d0 + D - 1) - L::kSl + g.padL;
   const int Yp = t.y + g.bh + kPadT;
   const size_t img_off = (size_t)t.n * g.img_px();
   const int fstart = (XbaseP - 2) & ~3;
@@ -491,15 +496,16 @@ __device__ __forceinline__ Phase1Out phase1_tile(const FusedArgs& a, const TileI
     for (int j = 1; j <= 4; ++j) ap[r][j - 1] = pk2(av[j], av[j - 1]);
   }
   // validity: cost(y,x,d) exists iff the window origin is inside and x - wc >= d (and d < D)
-  const int dmax_cen = min(D - 1, (Y >= 5 && Y < H - 6 && X >= 5 && X < W - 6) ? X - 5 : -1);
-  const int dmax_ncc = min(D - 1, (Y >= 1 && Y < H - 2 && X >= 1 && X < W - 2) ? X - 1 : -1);
-  const int dmax_sad = min(D - 1, (Y >= 2 && Y < H - 3 && X >= 2 && X < W - 3) ? X - 2 : -1);
+  // (dmax_* are local to the launch: disparity d0 + d of the image is step d here)
+  const int dmax_cen = min(D - 1, ((Y >= 5 && Y < H - 6 && X >= 5 && X < W - 6) ? X - 5 : -1) - g.d0);
+  const int dmax_ncc = min(D - 1, ((Y >= 1 && Y < H - 2 && X >= 1 && X < W - 2) ? X - 1 : -1) - g.d0);
+  const int dmax_sad = min(D - 1, ((Y >= 2 && Y < H - 3 && X >= 2 && X < W - 3) ? X - 2 : -1) - g.d0);
 
   const uint4* s_desc = reinterpret_cast<const uint4*>(stage + L::st_desc);
   const uint4* s_stat = reinterpret_cast<const uint4*>(stage + L::st_stat);
   const float* s_rf = reinterpret_cast<const float*>(stage + L::st_rf);
   // shared index of right column X - d is ir = px + L::kSl + (D-1) - d; falls by one per step
-  const int XbaseP = t.x0 + g.bwl - (D - 1) - L::kSl + g.padL;
+  const int XbaseP = t.x0 + g.bwl - (g.d0 + D - 1) - L::kSl + g.padL;
   const int shift = (XbaseP - 2) & 3;
   const int ir0 = px + L::kSl + (D - 1) - d_lo;
   const float* rfp = s_rf + shift + ir0 - 1;   // column (X - dB - 2) of the pair's second disparity
@@ -789,6 +795,68 @@ __device__ __forceinline__ void tile_back_half(const FusedArgs& a, const TileId&
   else phase3_quads<false>(s_par, s_cen, s_lut, s_min, s_inv, PS, q4, dl, D, orow + 4 * chan, plane, chan, nlive, a.k_ncc, a.k_sad);
 }
 
+// Back half of a tile for DISPARITY-SLAB SHARDING (phase A of slab.cu): the AML
+// minimum and denominator need the other ranks' disparities, so the tile only stores channels
+// 0-3, parks the RAW costs in channels 4-7 (census as float; fill where there is no cost) and
+// writes the slab's per-pixel minima; slab_phase_b/c finish the job after the all-reduces.
+template <class L>
+__device__ __forceinline__ void tile_slab_a(const FusedArgs& a, const TileId& t, int tid, const float* s_par,
+                                            const uint8_t* s_cen, const float* s_red, const float* s_lutn) {
+  constexpr int PS = L::PS;
+  const FusedGeom& g = a.g;
+  const int D = g.D;
+  const size_t plane = (size_t)g.h * g.w;
+  const size_t chan = plane * D;
+  if (tid < 4 * kTile) {  // minima across the d-groups -> global
+    float v = kFill;
+#pragma unroll
+    for (int gq = 0; gq < kGroups; ++gq) v = fminf(v, s_red[gq * 4 * kTile + tid]);
+    const int m = tid / kTile, x = t.x0 + tid % kTile;
+    if (x < g.w) a.mins[(((size_t)t.n * 4 + m) * g.h + t.y) * g.w + x] = v;
+  }
+  const int q4 = (tid & 7) * 4;
+  const int dl = tid >> 3;
+  const bool vec_ok = ((g.w & 3) == 0) && ((reinterpret_cast<uintptr_t>(a.out) & 15) == 0);
+  float* orow = a.out + (size_t)t.n * 8 * chan + (size_t)t.y * g.w + (t.x0 + q4);
+  const int nlive = min(4, g.w - (t.x0 + q4));
+  const bool vec = vec_ok && nlive == 4;
+#pragma unroll 2
+  for (int d = dl; d < D; d += 32) {
+    const float* e0 = s_par + d * kTile + q4;
+    const uchar4 cb = *reinterpret_cast<const uchar4*>(s_cen + d * kTile + q4);
+    const float4 v1 = *reinterpret_cast<const float4*>(e0);
+    const float4 v2 = *reinterpret_cast<const float4*>(e0 + PS);
+    const float4 v3 = *reinterpret_cast<const float4*>(e0 + 2 * PS);
+    const float4 v0 = make_float4(cb.x == 255 ? kFill : (float)cb.x, cb.y == 255 ? kFill : (float)cb.y,
+                                  cb.z == 255 ? kFill : (float)cb.z, cb.w == 255 ? kFill : (float)cb.w);
+    const float4 c0 = make_float4(s_lutn[cb.x], s_lutn[cb.y], s_lutn[cb.z], s_lutn[cb.w]);
+    const float4 c1 = make_float4(normalise_cost(v1.x, 1), normalise_cost(v1.y, 1), normalise_cost(v1.z, 1),
+                                  normalise_cost(v1.w, 1));
+    const float4 c2 = make_float4(normalise_cost(v2.x, 2), normalise_cost(v2.y, 2), normalise_cost(v2.z, 2),
+                                  normalise_cost(v2.w, 2));
+    const float4 c3 = make_float4(normalise_cost(v3.x, 3), normalise_cost(v3.y, 3), normalise_cost(v3.z, 3),
+                                  normalise_cost(v3.w, 3));
+    float* o = orow + (size_t)d * plane;
+    if (vec) {
+      store_quads<true>(o, chan, nlive, c0, c1, c2, c3);
+      // parked raw costs are read again by slab_phase_b/c: plain (cached) stores
+      *reinterpret_cast<float4*>(o + 4 * chan) = v0;
+      *reinterpret_cast<float4*>(o + 5 * chan) = v1;
+      *reinterpret_cast<float4*>(o + 6 * chan) = v2;
+      *reinterpret_cast<float4*>(o + 7 * chan) = v3;
+    } else {
+      store_quads<false>(o, chan, nlive, c0, c1, c2, c3);
+      const float rr[4][4] = {{v0.x, v0.y, v0.z, v0.w}, {v1.x, v1.y, v1.z, v1.w}, {v2.x, v2.y, v2.z, v2.w},
+                              {v3.x, v3.y, v3.z, v3.w}};
+#pragma unroll
+      for (int ch = 0; ch < 4; ++ch)
+#pragma unroll
+        for (int i = 0; i < 4; ++i)
+          if (i < nlive) o[(4 + ch) * chan + i] = rr[ch][i];
+    }
+  }
+}
+
 // ---- one CTA per tile (fallback: any D up to 448, with or without TMA) ----------------------
 //   phase 1  thread = (pixel, d-group): 8 warps split D (phase1_tile)
 //   phase 2  thread = (pixel quad, d): channels 0-3 stored, costs -> AML exponentials in place
@@ -798,7 +866,8 @@ __device__ __forceinline__ void tile_back_half(const FusedArgs& a, const TileId&
 // cp.async.bulk.tensor (D <= 256: box limit); otherwise through LDGSTS.  The tensor copy's
 // inner coordinate must be a multiple of 16 bytes (measured: anything else raises an
 // illegal-instruction fault), which is why the scratch is stored with column offset sxo.
-template <int DMAX, bool kTma>
+// kSlabA: stop after phase 1 and emit what slab.cu's phase A emits (tile_slab_a).
+template <int DMAX, bool kTma, bool kSlabA>
 __global__ void __launch_bounds__(256, 2)
 ms_fused_kernel(const FusedArgs a, const __grid_constant__ CUtensorMap sad_map) {
   using L = Lay<DMAX, kSlack>;
@@ -849,7 +918,7 @@ ms_fused_kernel(const FusedArgs a, const __grid_constant__ CUtensorMap sad_map) 
 
   // interior tile: all 32 pixels have every cost at every disparity, and the d-groups cover D exactly
   const int Xl = t.x0 + g.bwl, Yr = t.y + g.bh;
-  const bool all_valid = (kGroups * a.DC == D) && (Xl - 5 >= D - 1) && (Xl + kTile - 1 < g.W - 6) && (Yr >= 5) &&
+  const bool all_valid = (kGroups * a.DC == D) && (Xl - 5 >= g.d0 + D - 1) && (Xl + kTile - 1 < g.W - 6) && (Yr >= 5) &&
                          (Yr < g.H - 6);
   Phase1Out o;
   if (a.DC % 6 == 0) {
@@ -861,7 +930,8 @@ ms_fused_kernel(const FusedArgs a, const __grid_constant__ CUtensorMap sad_map) 
   if (kTma) mbar_wait(&s_bar[1], 0);
   finish_phase1<L>(s_par, s_red, o, px, grp, d_lo, d_end);
   __syncthreads();
-  tile_back_half<L>(a, t, tid, s_par, s_cen, s_red, s_min, s_inv, s_lut, s_lutn);
+  if (kSlabA) tile_slab_a<L>(a, t, tid, s_par, s_cen, s_red, s_lutn);
+  else tile_back_half<L>(a, t, tid, s_par, s_cen, s_red, s_min, s_inv, s_lut, s_lutn);
 }
 
 // Optional per-kernel timing (msn_profile_enable): CUDA events recorded on the launch
@@ -921,7 +991,7 @@ int profile_read(double* prep_ms, double* sadsob_ms, double* fused_ms, int* call
 
 bool fused_supported(const msn_ms_params* p, int Dn) {
   return p->censw == kCensW && p->nccw == kNccW && p->sadw == kSadW && p->sobelw == kSadW && p->lr == 0 &&
-         Dn == p->ndisp && p->ndisp <= kMaxFusedD;  // (image width is checked at launch)
+         Dn <= kMaxFusedD;  // (image width is checked at launch)
 }
 
 size_t fused_workspace_bytes(int N, int H, int W, int Dn, const msn_ms_params* p) {
@@ -932,8 +1002,10 @@ size_t fused_workspace_bytes(int N, int H, int W, int Dn, const msn_ms_params* p
   return ws.total;
 }
 
+// d_mins == nullptr: the whole feature volume (p describes all disparities).  Otherwise phase A of
+// the slab path for disparities [p->d_begin, p->d_begin + p->d_count).
 int launch_ms_fused(const uint8_t* d_left, const uint8_t* d_right, int N, int H, int W, const msn_ms_params* p,
-                    float* d_out, char* workspace, cudaStream_t s) {
+                    float* d_out, float* d_mins, char* workspace, cudaStream_t s) {
   if (N == 0) return 0;
   FusedGeom g = make_geom(N, H, W, p);
   FusedWs ws;
@@ -959,7 +1031,7 @@ int launch_ms_fused(const uint8_t* d_left, const uint8_t* d_right, int N, int H,
                                        ws.luts, aml_scale(p->cens_sigma));
   MSN_LAUNCH_OK();
   if (prof) MSN_CUDA_OK(cudaEventRecord(rec.ev[1], s));
-  if (launch_sadsob5_padded(ws.sob[0], ws.sob[1], N, H, W, g.D, 0, ws.sadsob + g.sxo, ws.sad_ws, s)) return 1;
+  if (launch_sadsob5_padded(ws.sob[0], ws.sob[1], N, H, W, g.D, g.d0, ws.sadsob + g.sxo, ws.sad_ws, s)) return 1;
   if (prof) MSN_CUDA_OK(cudaEventRecord(rec.ev[2], s));
 
   FusedArgs a;
@@ -971,6 +1043,7 @@ int launch_ms_fused(const uint8_t* d_left, const uint8_t* d_right, int N, int H,
   a.luts = ws.luts;
   a.sadsob = ws.sadsob;
   a.out = d_out;
+  a.mins = d_mins;
   a.k_cen = aml_scale(p->cens_sigma);
   a.k_ncc = aml_scale(p->ncc_sigma);
   a.k_sad = aml_scale(p->sad_sigma);
@@ -997,12 +1070,17 @@ int launch_ms_fused(const uint8_t* d_left, const uint8_t* d_right, int N, int H,
     }
   }
   a.DC = 2 * (((g.D + kGroups - 1) / kGroups + 1) / 2);   // phase 1 walks disparity pairs
-#define MSN_FUSED_LAUNCH(DMAX, TMA)                                                                   \
+#define MSN_FUSED_LAUNCH1(DMAX, TMA, SLAB)                                                            \
   {                                                                                                   \
-    auto kern = ms_fused_kernel<DMAX, TMA>;                                                           \
+    auto kern = ms_fused_kernel<DMAX, TMA, SLAB>;                                                     \
     const size_t smem = Lay<DMAX, kSlack>::bytes;                                                     \
     MSN_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));  \
     kern<<<(unsigned)tiles, 256, smem, s>>>(a, sad_map);                                              \
+  }
+#define MSN_FUSED_LAUNCH(DMAX, TMA)                                                                   \
+  {                                                                                                   \
+    if (d_mins) MSN_FUSED_LAUNCH1(DMAX, TMA, true)                                                    \
+    else MSN_FUSED_LAUNCH1(DMAX, TMA, false)                                                          \
   }
 #define MSN_FUSED_CASE(DMAX)                                                                          \
   if (g.D <= DMAX) {                                                                                  \
@@ -1017,6 +1095,7 @@ int launch_ms_fused(const uint8_t* d_left, const uint8_t* d_right, int N, int H,
   MSN_FUSED_CASE(448) { return fail("ms_features: D=%d exceeds the fused kernel's limit", g.D); }
 #undef MSN_FUSED_CASE
 #undef MSN_FUSED_LAUNCH
+#undef MSN_FUSED_LAUNCH1
   MSN_LAUNCH_OK();
   if (prof) {
     MSN_CUDA_OK(cudaEventRecord(rec.ev[3], s));
