@@ -471,17 +471,26 @@ bool force_generic() {
 
 }  // namespace
 
+// The fused kernel serves the default windows.  Left view only (lr = 0): one launch writes the
+// final volume.  Both views (lr = 1): the fused kernel runs in its phase-A form (channels 0-3
+// final, raw costs parked in 4-7, minima), slab.cu derives channels 8-15 from the parked costs and
+// phases B/C finish all eight AML channels; mins/den [N][8][h][w] follow the fused workspace.
+static bool use_fused(const msn_ms_params* p, const Geometry& g, int W) {
+  return fused_supported(p, g.Dn) && sadsob_fast_pitch(W + 35) > 0 && !force_generic();
+}
+
+
 size_t msn_ms_features_workspace_bytes(int N, int H, int W, const msn_ms_params* p) {
   Geometry g;
   if (resolve(p, N, H, W, &g, "ms_features_workspace_bytes")) return 0;
+  if (use_fused(p, g, W)) {
+    size_t need = align256(fused_workspace_bytes(N, H, W, g.Dn, p));
+    if (p->lr) need += 2 * align256((size_t)N * 8 * g.h * g.w * sizeof(float));
+    return need + 256;
+  }
   GenericWs ws;
   ws.carve(nullptr, g, p);
-  size_t need = ws.total;
-  if (fused_supported(p, g.Dn) && sadsob_fast_pitch(W + 35) > 0 && !force_generic()) {
-    const size_t f = fused_workspace_bytes(N, H, W, g.Dn, p);
-    need = f;
-  }
-  return need + 256;
+  return ws.total + 256;
 }
 
 int msn_ms_features_dev(const uint8_t* d_left, const uint8_t* d_right, int N, int H, int W,
@@ -496,11 +505,25 @@ int msn_ms_features_dev(const uint8_t* d_left, const uint8_t* d_right, int N, in
   MSN_REQUIRE(g.d_begin == 0 && g.Dn == g.D, "ms_features: slabs go through msn_ms_slab_phase_*_dev");
   cudaStream_t s = as_stream(stream);
   char* base = (char*)(((uintptr_t)d_workspace + 255) & ~(uintptr_t)255);
-  if (fused_supported(p, g.Dn) && sadsob_fast_pitch(W + 35) > 0 && !force_generic())
-    return launch_ms_fused(d_left, d_right, N, H, W, p, d_out, nullptr, base, s);
+  const size_t n = (size_t)g.h * g.w;
+  if (use_fused(p, g, W)) {
+    if (!p->lr) return launch_ms_fused(d_left, d_right, N, H, W, p, d_out, nullptr, base, s);
+    const size_t stat_bytes = align256((size_t)N * 8 * n * sizeof(float));
+    float* mins = reinterpret_cast<float*>(base + align256(fused_workspace_bytes(N, H, W, g.Dn, p)));
+    float* den = reinterpret_cast<float*>(reinterpret_cast<char*>(mins) + stat_bytes);
+    TRY(launch_ms_fused(d_left, d_right, N, H, W, p, d_out, mins, base, s));
+    for (int i = 0; i < N; ++i) {
+      float* out = d_out + (size_t)i * 16 * g.Dn * n;
+      TRY(launch_slab_right_view(out, g.h, g.w, g.Dn, 0, nullptr, mins + (size_t)i * 8 * n, s));
+      TRY(launch_slab_phase_b(out, mins + (size_t)i * 8 * n, (long long)n, g.Dn, 1, p->cens_sigma, p->ncc_sigma,
+                              p->sad_sigma, den + (size_t)i * 8 * n, s));
+      TRY(launch_slab_phase_c(out, mins + (size_t)i * 8 * n, den + (size_t)i * 8 * n, (long long)n, g.Dn, 1,
+                              p->cens_sigma, p->ncc_sigma, p->sad_sigma, s));
+    }
+    return 0;
+  }
   GenericWs ws;
   ws.carve(base, g, p);
-  const size_t n = (size_t)g.h * g.w;
   for (int i = 0; i < N; ++i) {
     float* out = d_out + (size_t)i * g.C * g.Dn * n;
     TRY(generic_phase_a(d_left + (size_t)i * H * W, d_right + (size_t)i * H * W, g, p, ws, nullptr, out, ws.mins, s));
@@ -539,7 +562,7 @@ int msn_profile_read(double* prep_ms, double* sadsob_ms, double* fused_ms, int* 
 // slab phases (multi-GPU disparity sharding); workspace sized by
 // msn_ms_slab_workspace_bytes for the slab in p.
 static bool slab_fused(const msn_ms_params* p, const Geometry& g, int W) {
-  return fused_supported(p, g.Dn) && sadsob_fast_pitch(W + 35) > 0 && !force_generic();
+  return !p->lr && use_fused(p, g, W);   // (the slab path provides the left view only)
 }
 
 size_t msn_ms_slab_workspace_bytes(int N, int H, int W, const msn_ms_params* p) {

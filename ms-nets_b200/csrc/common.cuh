@@ -108,6 +108,8 @@ int launch_features_from_costs(const float* census, const float* ncc, const floa
 int launch_slab_phase_a(const float* census, const float* ncc, const float* sob, const float* sad, int H, int W,
                         int y0, int x0, int h, int w, int Dn, int d_begin, int lr, const float* d_first4,
                         float* out, float* mins, cudaStream_t s);
+int launch_slab_right_view(float* out, int h, int w, int Dn, int d_begin, const float* d_first4, float* mins,
+                           cudaStream_t s);
 int launch_slab_phase_b(const float* out, const float* gmin, long long n, int Dn, int lr, float cens_sigma,
                         float ncc_sigma, float sad_sigma, float* den, cudaStream_t s);
 int launch_slab_phase_c(float* out, const float* gmin, const float* gden, long long n, int Dn, int lr,

@@ -216,7 +216,9 @@ struct FusedArgs {
   const float* luts;    // [128] + [256], see ms_prep_kernel
   const float* sadsob;  // [N][D][H][Ws] (+ slack)
   float* out;           // [N][8][D][h][w]
-  float* mins;          // slab phase A only: [N][4][h][w] per-pixel minima of this launch's disparities
+  float* mins;          // slab phase A only: [N][mins_planes][h][w], planes 0-3 = per-pixel minima of this launch's disparities
+  int out_channels;     // channel count of the output tensor (pair stride): 8, or 16 when the caller adds the right view
+  int mins_planes;      // 4, or 8 when the caller adds the right view
   float k_cen, k_ncc, k_sad;
   int DC;               // disparity steps per d-group (even: phase 1 walks disparity pairs)
   int tiles_x;
@@ -752,7 +754,7 @@ __device__ __forceinline__ void tile_back_half(const FusedArgs& a, const TileId&
   const int q4 = (tid & 7) * 4;
   // 128-bit stores need 16-byte aligned rows
   const bool vec_ok = ((g.w & 3) == 0) && ((reinterpret_cast<uintptr_t>(a.out) & 15) == 0);
-  float* orow = a.out + (size_t)t.n * 8 * chan + (size_t)t.y * g.w + (t.x0 + q4);
+  float* orow = a.out + (size_t)t.n * a.out_channels * chan + (size_t)t.y * g.w + (t.x0 + q4);
   const int nlive = min(4, g.w - (t.x0 + q4));  // live pixels of this quad (<= 0: none)
   const bool vec = vec_ok && nlive == 4;
   if (warp < 4) {
@@ -812,12 +814,12 @@ __device__ __forceinline__ void tile_slab_a(const FusedArgs& a, const TileId& t,
 #pragma unroll
     for (int gq = 0; gq < kGroups; ++gq) v = fminf(v, s_red[gq * 4 * kTile + tid]);
     const int m = tid / kTile, x = t.x0 + tid % kTile;
-    if (x < g.w) a.mins[(((size_t)t.n * 4 + m) * g.h + t.y) * g.w + x] = v;
+    if (x < g.w) a.mins[(((size_t)t.n * a.mins_planes + m) * g.h + t.y) * g.w + x] = v;
   }
   const int q4 = (tid & 7) * 4;
   const int dl = tid >> 3;
   const bool vec_ok = ((g.w & 3) == 0) && ((reinterpret_cast<uintptr_t>(a.out) & 15) == 0);
-  float* orow = a.out + (size_t)t.n * 8 * chan + (size_t)t.y * g.w + (t.x0 + q4);
+  float* orow = a.out + (size_t)t.n * a.out_channels * chan + (size_t)t.y * g.w + (t.x0 + q4);
   const int nlive = min(4, g.w - (t.x0 + q4));
   const bool vec = vec_ok && nlive == 4;
 #pragma unroll 2
@@ -990,8 +992,8 @@ int profile_read(double* prep_ms, double* sadsob_ms, double* fused_ms, int* call
 }
 
 bool fused_supported(const msn_ms_params* p, int Dn) {
-  return p->censw == kCensW && p->nccw == kNccW && p->sadw == kSadW && p->sobelw == kSadW && p->lr == 0 &&
-         Dn <= kMaxFusedD;  // (image width is checked at launch)
+  return p->censw == kCensW && p->nccw == kNccW && p->sadw == kSadW && p->sobelw == kSadW &&
+         Dn <= kMaxFusedD;  // (image width is checked at launch; p->lr: the caller adds the right view)
 }
 
 size_t fused_workspace_bytes(int N, int H, int W, int Dn, const msn_ms_params* p) {
@@ -1044,6 +1046,8 @@ int launch_ms_fused(const uint8_t* d_left, const uint8_t* d_right, int N, int H,
   a.sadsob = ws.sadsob;
   a.out = d_out;
   a.mins = d_mins;
+  a.out_channels = p->lr ? 16 : 8;
+  a.mins_planes = p->lr ? 8 : 4;
   a.k_cen = aml_scale(p->cens_sigma);
   a.k_ncc = aml_scale(p->ncc_sigma);
   a.k_sad = aml_scale(p->sad_sigma);

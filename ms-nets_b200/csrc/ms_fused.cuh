@@ -4,12 +4,15 @@
 
 namespace msn {
 
-// true when (windows, disparity count) match what the fused kernel is specialised for
+// true when (windows, disparity count) match what the fused kernel is specialised for.  With
+// p->lr the kernel still produces the LEFT view only, laid out for a 16-channel tensor (phase A
+// form); slab.cu's launch_slab_right_view derives channels 8-15 from the parked costs.
 bool fused_supported(const msn_ms_params* p, int Dn);
 size_t fused_workspace_bytes(int N, int H, int W, int Dn, const msn_ms_params* p);
 // d_left/d_right: [N][H][W] uint8; out: [N][C][D][h][w]; workspace 256-byte aligned.
 // d_mins == nullptr: the whole volume.  d_mins != nullptr: phase A of the disparity-slab path
-// (channels 0-3 final, raw costs parked in channels 4-7, per-pixel slab minima in d_mins).
+// (channels 0-3 final, raw costs parked in channels 4-7, per-pixel slab minima in d_mins
+// [N][4 or 8][h][w]).
 int launch_ms_fused(const uint8_t* d_left, const uint8_t* d_right, int N, int H, int W, const msn_ms_params* p,
                     float* d_out, float* d_mins, char* workspace, cudaStream_t s);
 

@@ -66,6 +66,47 @@ slab_phase_a_kernel(RawViews raw, int H, int W, int y0, int x0, int h, int w, in
   for (int i = 0; i < nm; ++i) mins[(size_t)i * n + p] = mn[i];
 }
 
+// Right-view channels from the PARKED left-view raw costs of a 16-channel tensor (phase A form:
+// channels 4-7 = raw [Dn][h][w]): right(y,x,d) = left(y,x+d,d) for x < w-d, else c.flat[0]
+// (featextract.cpp:136-172).  Writes channels 8-11 (normalised), 12-15 (raw, parked) and the
+// right-view minima (planes 4-7 of mins).
+__global__ void __launch_bounds__(256)
+slab_right_view_kernel(float* __restrict__ out, int h, int w, int Dn, int d_begin, const float* __restrict__ first4,
+                       float* __restrict__ mins) {
+  const long long n = (long long)h * w;
+  const long long p = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (p >= n) return;
+  const int x = (int)(p % w);
+  float firsts[4], mn[4];
+#pragma unroll
+  for (int m = 0; m < 4; ++m) {
+    firsts[m] = first4 ? first4[m] : out[(size_t)(4 + m) * Dn * n];   // voxel (d=0, y=0, x=0) of the cropped volume
+    mn[m] = kFill;
+  }
+  for (int dd = 0; dd < Dn; ++dd) {
+    const int d = d_begin + dd;
+#pragma unroll
+    for (int m = 0; m < 4; ++m) {
+      const float v = (x < w - d) ? out[((size_t)(4 + m) * Dn + dd) * n + p + d] : firsts[m];
+      st_stream(out + ((size_t)(8 + m) * Dn + dd) * n + p, normalise_cost(v, m));
+      out[((size_t)(12 + m) * Dn + dd) * n + p] = v;
+      mn[m] = fminf(mn[m], v);
+    }
+  }
+#pragma unroll
+  for (int m = 0; m < 4; ++m) mins[(size_t)(4 + m) * n + p] = mn[m];
+}
+
+int launch_slab_right_view(float* out, int h, int w, int Dn, int d_begin, const float* d_first4, float* mins,
+                           cudaStream_t s) {
+  const long long n = (long long)h * w;
+  if (n <= 0 || Dn <= 0) return 0;
+  MSN_REQUIRE(d_first4 || d_begin == 0, "slab right view: d_begin > 0 needs the four c[0] values of slab 0");
+  slab_right_view_kernel<<<div_up(n, 256), 256, 0, s>>>(out, h, w, Dn, d_begin, d_first4, mins);
+  MSN_LAUNCH_OK();
+  return 0;
+}
+
 // channel that parks / receives the AML of (view, matcher)
 __device__ __forceinline__ int aml_channel(int i) { return (i >> 2) * 8 + 4 + (i & 3); }
 
