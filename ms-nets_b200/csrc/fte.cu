@@ -229,37 +229,95 @@ __device__ __forceinline__ long long pack_key(float m1, int d) {
   return (long long)(u ^ 0x8000000000000000ull);
 }
 
-// layout 0: rows [n][D]; one warp per row.
-__global__ void wta_rows_kernel(const float* __restrict__ cost, long long n, int D, int d_begin,
-                                int32_t* __restrict__ amin, float* __restrict__ m1, float* __restrict__ m2,
-                                long long* __restrict__ keys) {
-  const long long row = (long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
-  const int lane = threadIdx.x & 31;
-  if (row >= n) return;
-  const float* c = cost + row * D;
+// layout 0: rows [n][D].  kLanes lanes share a row (32 / kLanes rows per warp): each lane reads
+// 128-bit vectors when D is a multiple of 4, the (min, argmin, second-min) triples are merged
+// with log2(kLanes) shuffle steps.  Index order decides ties, so the strided split is harmless.
+template <int kLanes>
+__global__ void __launch_bounds__(256)
+wta_rows_kernel(const float* __restrict__ cost, long long n, int D, int d_begin, int32_t* __restrict__ amin,
+                float* __restrict__ m1, float* __restrict__ m2, long long* __restrict__ keys) {
+  constexpr int kRows = 32 / kLanes;
+  const int lane = threadIdx.x & 31, sub = lane % kLanes;
+  const long long row = ((long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5)) * kRows + lane / kLanes;
   Best b = best_init();
-  for (int d = lane; d < D; d += 32) best_push(b, c[d], d);
-  b = warp_best(b);
-  if (lane == 0) {
+  if (row < n) {
+    const float* c = cost + row * D;
+    if ((D & 3) == 0 && ((reinterpret_cast<uintptr_t>(cost) & 15) == 0)) {
+      const float4* c4 = reinterpret_cast<const float4*>(c);
+      const int D4 = D >> 2;
+#pragma unroll 4
+      for (int q = sub; q < D4; q += kLanes) {
+        const float4 v = __ldg(c4 + q);
+        best_push(b, v.x, 4 * q);
+        best_push(b, v.y, 4 * q + 1);
+        best_push(b, v.z, 4 * q + 2);
+        best_push(b, v.w, 4 * q + 3);
+      }
+    } else {
+      for (int d = sub; d < D; d += kLanes) best_push(b, c[d], d);
+    }
+  }
+#pragma unroll
+  for (int o = kLanes >> 1; o > 0; o >>= 1) {
+    Best other;
+    other.m1 = __shfl_xor_sync(0xffffffffu, b.m1, o);
+    other.m2 = __shfl_xor_sync(0xffffffffu, b.m2, o);
+    other.i1 = __shfl_xor_sync(0xffffffffu, b.i1, o);
+    b = best_merge(b, other);
+  }
+  if (sub == 0 && row < n) {
     if (amin) amin[row] = b.i1;
     if (m1) m1[row] = b.m1;
     if (m2) m2[row] = b.m2;
     if (keys) keys[row] = pack_key(b.m1, d_begin + b.i1);
   }
 }
-// layout 1: planes [D][n]; one thread per pixel, coalesced across the warp.
-__global__ void wta_planes_kernel(const float* __restrict__ cost, long long n, int D, int d_begin,
-                                  int32_t* __restrict__ amin, float* __restrict__ m1,
-                                  float* __restrict__ m2, long long* __restrict__ keys) {
-  const long long p = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-  if (p >= n) return;
-  Best b = best_init();
+// layout 1: planes [D][n]; a thread owns 4 consecutive pixels (128-bit loads, coalesced across
+// the warp) and one of kSplit interleaved slices of D; the slices meet in shared memory.
+constexpr int kWtaSplit = 4;
+__global__ void __launch_bounds__(64 * kWtaSplit)
+wta_planes_kernel(const float* __restrict__ cost, long long n, int D, int d_begin, int32_t* __restrict__ amin,
+                  float* __restrict__ m1, float* __restrict__ m2, long long* __restrict__ keys) {
+  __shared__ Best sb[kWtaSplit][64][4];
+  const int tx = threadIdx.x & 63, ty = threadIdx.x >> 6;
+  const long long p0 = ((long long)blockIdx.x * 64 + tx) * 4;
+  const bool vec = ((n & 3) == 0) && ((reinterpret_cast<uintptr_t>(cost) & 15) == 0);
+  Best b[4] = {best_init(), best_init(), best_init(), best_init()};
+  if (p0 < n) {
+    if (vec) {
 #pragma unroll 4
-  for (int d = 0; d < D; ++d) best_push(b, cost[(long long)d * n + p], d);
-  if (amin) amin[p] = b.i1;
-  if (m1) m1[p] = b.m1;
-  if (m2) m2[p] = b.m2;
-  if (keys) keys[p] = pack_key(b.m1, d_begin + b.i1);
+      for (int d = ty; d < D; d += kWtaSplit) {
+        const float4 v = __ldg(reinterpret_cast<const float4*>(cost + (long long)d * n + p0));
+        best_push(b[0], v.x, d);
+        best_push(b[1], v.y, d);
+        best_push(b[2], v.z, d);
+        best_push(b[3], v.w, d);
+      }
+    } else {
+      for (int d = ty; d < D; d += kWtaSplit)
+#pragma unroll
+        for (int i = 0; i < 4; ++i)
+          if (p0 + i < n) best_push(b[i], cost[(long long)d * n + p0 + i], d);
+    }
+  }
+#pragma unroll
+  for (int i = 0; i < 4; ++i) sb[ty][tx][i] = b[i];
+  __syncthreads();
+  if (ty == 0 && p0 < n) {
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      Best r = b[i];
+#pragma unroll
+      for (int k = 1; k < kWtaSplit; ++k) r = best_merge(r, sb[k][tx][i]);
+      const long long p = p0 + i;
+      if (p < n) {
+        if (amin) amin[p] = r.i1;
+        if (m1) m1[p] = r.m1;
+        if (m2) m2[p] = r.m2;
+        if (keys) keys[p] = pack_key(r.m1, d_begin + r.i1);
+      }
+    }
+  }
 }
 
 int launch_wta(const float* cost, long long n, int D, int layout, int d_begin, int32_t* amin, float* m1,
@@ -267,10 +325,12 @@ int launch_wta(const float* cost, long long n, int D, int layout, int d_begin, i
   MSN_REQUIRE(D >= 1, "wta: D must be >= 1");
   MSN_REQUIRE(layout == 0 || layout == 1, "wta: layout must be 0 ([n][D]) or 1 ([D][n])");
   if (n == 0) return 0;
-  if (layout == 0)
-    wta_rows_kernel<<<div_up(n, 8), 256, 0, s>>>(cost, n, D, d_begin, amin, m1, m2, keys);
-  else
-    wta_planes_kernel<<<div_up(n, 256), 256, 0, s>>>(cost, n, D, d_begin, amin, m1, m2, keys);
+  if (layout == 0) {
+    if (D >= 128) wta_rows_kernel<8><<<div_up(n, 8 * 4), 256, 0, s>>>(cost, n, D, d_begin, amin, m1, m2, keys);
+    else wta_rows_kernel<4><<<div_up(n, 8 * 8), 256, 0, s>>>(cost, n, D, d_begin, amin, m1, m2, keys);
+  } else {
+    wta_planes_kernel<<<div_up(n, 256), 64 * kWtaSplit, 0, s>>>(cost, n, D, d_begin, amin, m1, m2, keys);
+  }
   MSN_LAUNCH_OK();
   return 0;
 }

@@ -144,56 +144,82 @@ int launch_soft_argmin_merge(const float* parts, int P, int N, int H, int W, flo
 // concat: vol[n][c][d][y][x]   = x >= d ? fl[n][c][y][x]   : 0      (c <  C)
 //         vol[n][C+c][d][y][x] = x >= d ? fr[n][c][y][x-d] : 0
 // diff  : vol[n][c][d][y][x]   = x >= d ? fl[n][c][y][x] - fr[n][c][y][x-d] : 0
-// Pure data movement, D-fold write amplification: HBM-write bound.  One thread
-// writes 4 consecutive x with one 128-bit streaming store; the inputs (D times
-// smaller) are re-read through L1/L2.
+// Pure data movement, D-fold write amplification: HBM-write bound.  One thread owns 4
+// consecutive x of one input channel row and walks ALL disparities: the left quad stays in
+// registers, the right quad slides one column per disparity (one scalar load per step), and
+// every step emits one (diff) or two (concat) 128-bit streaming stores.  blockIdx.y splits D
+// into chunks so small inputs still fill the machine.
 template <bool kDiff>
 __global__ void __launch_bounds__(256)
 shift_volume_kernel(const float* __restrict__ fl, const float* __restrict__ fr, int C, int H, int W, int D,
-                    float* __restrict__ vol) {
+                    int d_chunk, float* __restrict__ vol) {
   const int Wq = (W + 3) >> 2;
   const long long row_groups = (long long)H * Wq;
   const long long g = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   if (g >= row_groups) return;
-  const int d = blockIdx.y;
-  const int nc = blockIdx.z;  // n * Cout + co
-  const int Cout = kDiff ? C : 2 * C;
-  const int n = nc / Cout, co = nc % Cout;
+  const int nc = blockIdx.z;  // n * C + ci
+  const int n = nc / C, ci = nc % C;
   const int y = (int)(g / Wq), x0 = (int)(g % Wq) * 4;
-  const bool from_right = !kDiff && co >= C;
-  const int ci = from_right ? co - C : co;
+  const int d_lo = blockIdx.y * d_chunk, d_hi = min(D, d_lo + d_chunk);
   const float* lrow = fl + (((size_t)n * C + ci) * H + y) * W;
   const float* rrow = fr + (((size_t)n * C + ci) * H + y) * W;
-  float v[4];
+  const int Cout = kDiff ? C : 2 * C;
+  const size_t plane = (size_t)H * W;
+  float* o_l = vol + ((((size_t)n * Cout + ci) * D + d_lo) * H + y) * W + x0;            // left copy / difference
+  float* o_r = kDiff ? nullptr : o_l + (size_t)C * D * plane;                            // shifted right copy
+  float l[4], r[4];
 #pragma unroll
   for (int i = 0; i < 4; ++i) {
     const int x = x0 + i;
-    float r = 0.f;
-    if (x < W && x >= d) {
-      if (kDiff) r = __fsub_rn(lrow[x], rrow[x - d]);
-      else r = from_right ? rrow[x - d] : lrow[x];
-    }
-    v[i] = r;
+    l[i] = (x < W) ? lrow[x] : 0.f;
+    const int xr = x - d_lo;
+    r[i] = (x < W && xr >= 0) ? rrow[xr] : 0.f;
   }
-  float* o = vol + ((((size_t)n * Cout + co) * D + d) * H + y) * W + x0;
-  if ((W & 3) == 0) {
-    st_stream4(o, make_float4(v[0], v[1], v[2], v[3]));
-  } else {
+  const bool vec = (W & 3) == 0;
+  for (int d = d_lo; d < d_hi; ++d) {
+    float a[4], b[4];
 #pragma unroll
-    for (int i = 0; i < 4; ++i)
-      if (x0 + i < W) st_stream(o + i, v[i]);
+    for (int i = 0; i < 4; ++i) {
+      const bool in = (x0 + i >= d) && (x0 + i < W);
+      if (kDiff) a[i] = in ? __fsub_rn(l[i], r[i]) : 0.f;
+      else {
+        a[i] = in ? l[i] : 0.f;
+        b[i] = in ? r[i] : 0.f;
+      }
+    }
+    if (vec) {
+      st_stream4(o_l, make_float4(a[0], a[1], a[2], a[3]));
+      if (!kDiff) st_stream4(o_r, make_float4(b[0], b[1], b[2], b[3]));
+    } else {
+#pragma unroll
+      for (int i = 0; i < 4; ++i)
+        if (x0 + i < W) {
+          st_stream(o_l + i, a[i]);
+          if (!kDiff) st_stream(o_r + i, b[i]);
+        }
+    }
+    o_l += plane;
+    if (!kDiff) o_r += plane;
+    // next disparity: the right quad moves one column to the left
+    r[3] = r[2]; r[2] = r[1]; r[1] = r[0];
+    const int xn = x0 - (d + 1);
+    r[0] = (xn >= 0 && x0 < W) ? rrow[xn] : 0.f;
   }
 }
 
 int launch_shift_volume(const float* fl, const float* fr, int N, int C, int H, int W, int D, bool diff,
                         float* vol, cudaStream_t s) {
   MSN_REQUIRE(N >= 0 && C >= 1 && H >= 0 && W >= 0 && D >= 1, "volume: bad shape");
-  const int Cout = diff ? C : 2 * C;
   if (N == 0 || H == 0 || W == 0) return 0;
-  MSN_REQUIRE(D <= 65535 && (long long)N * Cout <= 65535, "volume: D or N*C too large for one launch");
-  dim3 grid(div_up((long long)H * ((W + 3) / 4), 256), D, N * Cout);
-  if (diff) shift_volume_kernel<true><<<grid, 256, 0, s>>>(fl, fr, C, H, W, D, vol);
-  else shift_volume_kernel<false><<<grid, 256, 0, s>>>(fl, fr, C, H, W, D, vol);
+  MSN_REQUIRE((long long)N * C <= 65535, "volume: N*C too large for one launch");
+  const unsigned gx = div_up((long long)H * ((W + 3) / 4), 256);
+  // enough CTAs for a few waves of 148 SMs x 8 CTAs; otherwise one thread walks all of D
+  int chunks = 1;
+  while (chunks < D && (long long)gx * N * C * chunks < 4 * 148 * 8) chunks *= 2;
+  const int d_chunk = (D + chunks - 1) / chunks;
+  dim3 grid(gx, (D + d_chunk - 1) / d_chunk, N * C);
+  if (diff) shift_volume_kernel<true><<<grid, 256, 0, s>>>(fl, fr, C, H, W, D, d_chunk, vol);
+  else shift_volume_kernel<false><<<grid, 256, 0, s>>>(fl, fr, C, H, W, D, d_chunk, vol);
   MSN_LAUNCH_OK();
   return 0;
 }
