@@ -667,7 +667,7 @@ template <bool kVec>
 __device__ __forceinline__ void store_ch03(const float* s_par, const uint8_t* s_cen, const float* s_lutn, int PS,
                                            int q4, int d0, int d1, float* orow, size_t plane, size_t chan,
                                            int nlive) {
-#pragma unroll 2
+#pragma unroll 1
   for (int d = d0; d < d1; d += 16) {
     const float* e0 = s_par + d * kTile + q4;
     const uchar4 cb = *reinterpret_cast<const uchar4*>(s_cen + d * kTile + q4);
@@ -701,7 +701,7 @@ __device__ __forceinline__ void phase3_quads(const float* s_par, const uint8_t* 
   const float4 i3 = *reinterpret_cast<const float4*>(s_inv + 3 * kTile + q4);
   const int mcx = (m_cen4.x == kFill) ? 0 : (int)m_cen4.x, mcy = (m_cen4.y == kFill) ? 0 : (int)m_cen4.y;
   const int mcz = (m_cen4.z == kFill) ? 0 : (int)m_cen4.z, mcw = (m_cen4.w == kFill) ? 0 : (int)m_cen4.w;
-#pragma unroll 2
+#pragma unroll 1
   for (int d = dl; d < D; d += 32) {
     const float* e0 = s_par + d * kTile + q4;
     const uchar4 cb = *reinterpret_cast<const uchar4*>(s_cen + d * kTile + q4);
