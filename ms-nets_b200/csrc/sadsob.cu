@@ -192,7 +192,7 @@ __device__ __forceinline__ void s5_vertical(const float* __restrict__ lp, const 
 // SP: row pitch in floats of BOTH the Sobel images and the output volume (compile-time so
 // that every row offset is an immediate); W <= SP.
 template <int SP>
-__global__ void __launch_bounds__(kS5Warps * 32, 6)
+__global__ void __launch_bounds__(kS5Warps * 32, 4)
 sadsob_scan5_kernel(const float* __restrict__ L, const float* __restrict__ R, int H, int W, int Dn, int d_begin,
                     int NB, size_t img_stride, const float* __restrict__ Vb, float* __restrict__ out,
                     size_t out_stride) {
