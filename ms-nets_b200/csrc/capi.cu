@@ -478,6 +478,19 @@ bool force_generic() {
 static bool use_fused(const msn_ms_params* p, const Geometry& g, int W) {
   return fused_supported(p, g.Dn) && sadsob_fast_pitch(W + 35) > 0 && !force_generic();
 }
+// More disparities than one fused launch parks in shared memory (left view, default windows): the
+// volume is cut into slabs of kFusedSlabD disparities, each through the fused kernel's phase-A
+// form, then phases B/C over all disparities -- the slab-sharding scheme of SURVEY.md 8e on one GPU.
+static bool use_fused_slabs(const msn_ms_params* p, const Geometry& g, int W) {
+  return !p->lr && g.Dn == g.D && !fused_supported(p, g.Dn) && fused_supported(p, kFusedSlabD) &&
+         sadsob_fast_pitch(W + 35) > 0 && !force_generic();
+}
+static msn_ms_params slab_params(const msn_ms_params* p, int d0, int dn) {
+  msn_ms_params q = *p;
+  q.d_begin = d0;
+  q.d_count = dn;
+  return q;
+}
 
 
 size_t msn_ms_features_workspace_bytes(int N, int H, int W, const msn_ms_params* p) {
@@ -487,6 +500,12 @@ size_t msn_ms_features_workspace_bytes(int N, int H, int W, const msn_ms_params*
     size_t need = align256(fused_workspace_bytes(N, H, W, g.Dn, p));
     if (p->lr) need += 2 * align256((size_t)N * 8 * g.h * g.w * sizeof(float));
     return need + 256;
+  }
+  if (use_fused_slabs(p, g, W)) {
+    // sized for the slab with the largest disparity offset (widest left padding) and a full count
+    const msn_ms_params q = slab_params(p, g.D - kFusedSlabD, kFusedSlabD);
+    return align256(fused_workspace_bytes(N, H, W, kFusedSlabD, &q)) +
+           2 * align256((size_t)N * 4 * g.h * g.w * sizeof(float)) + 256;
   }
   GenericWs ws;
   ws.carve(nullptr, g, p);
@@ -518,6 +537,24 @@ int msn_ms_features_dev(const uint8_t* d_left, const uint8_t* d_right, int N, in
       TRY(launch_slab_phase_b(out, mins + (size_t)i * 8 * n, (long long)n, g.Dn, 1, p->cens_sigma, p->ncc_sigma,
                               p->sad_sigma, den + (size_t)i * 8 * n, s));
       TRY(launch_slab_phase_c(out, mins + (size_t)i * 8 * n, den + (size_t)i * 8 * n, (long long)n, g.Dn, 1,
+                              p->cens_sigma, p->ncc_sigma, p->sad_sigma, s));
+    }
+    return 0;
+  }
+  if (use_fused_slabs(p, g, W)) {
+    const msn_ms_params q0 = slab_params(p, g.D - kFusedSlabD, kFusedSlabD);
+    const size_t stat_bytes = align256((size_t)N * 4 * n * sizeof(float));
+    float* mins = reinterpret_cast<float*>(base + align256(fused_workspace_bytes(N, H, W, kFusedSlabD, &q0)));
+    float* den = reinterpret_cast<float*>(reinterpret_cast<char*>(mins) + stat_bytes);
+    for (int d0 = 0; d0 < g.D; d0 += kFusedSlabD) {
+      const msn_ms_params q = slab_params(p, d0, g.D - d0 < kFusedSlabD ? g.D - d0 : kFusedSlabD);
+      TRY(launch_ms_fused(d_left, d_right, N, H, W, &q, d_out, mins, base, s, g.D, d0, d0 > 0));
+    }
+    for (int i = 0; i < N; ++i) {
+      float* out = d_out + (size_t)i * 8 * g.D * n;
+      TRY(launch_slab_phase_b(out, mins + (size_t)i * 4 * n, (long long)n, g.D, 0, p->cens_sigma, p->ncc_sigma,
+                              p->sad_sigma, den + (size_t)i * 4 * n, s));
+      TRY(launch_slab_phase_c(out, mins + (size_t)i * 4 * n, den + (size_t)i * 4 * n, (long long)n, g.D, 0,
                               p->cens_sigma, p->ncc_sigma, p->sad_sigma, s));
     }
     return 0;
@@ -568,7 +605,12 @@ static bool slab_fused(const msn_ms_params* p, const Geometry& g, int W) {
 size_t msn_ms_slab_workspace_bytes(int N, int H, int W, const msn_ms_params* p) {
   Geometry g;
   if (resolve(p, N, H, W, &g, "ms_slab_workspace_bytes")) return 0;
-  if (slab_fused(p, g, W)) return fused_workspace_bytes(N, H, W, g.Dn, p) + 256;
+  if (slab_fused(p, g, W)) {
+    // sized for the sub-slab with the largest disparity offset and a full count (see phase A)
+    const int dn = g.Dn < kFusedSlabD ? g.Dn : kFusedSlabD;
+    const msn_ms_params q = slab_params(p, g.d_begin + g.Dn - dn, dn);
+    return fused_workspace_bytes(N, H, W, dn, &q) + 256;
+  }
   GenericWs ws;
   ws.carve(nullptr, g, p);
   return ws.total + 256;
@@ -584,7 +626,14 @@ int msn_ms_slab_phase_a_dev(const uint8_t* d_left, const uint8_t* d_right, int N
   cudaStream_t s = as_stream(stream);
   char* base = (char*)(((uintptr_t)d_workspace + 255) & ~(uintptr_t)255);
   // default windows, left view: phase 1 of the fused kernel computes the slab's costs on chip
-  if (slab_fused(p, g, W)) return launch_ms_fused(d_left, d_right, N, H, W, p, d_out, d_min, base, s);
+  if (slab_fused(p, g, W)) {
+    // sub-slabs of at most kFusedSlabD disparities keep the launch on the TMA instantiations
+    for (int o = 0; o < g.Dn; o += kFusedSlabD) {
+      const msn_ms_params q = slab_params(p, g.d_begin + o, g.Dn - o < kFusedSlabD ? g.Dn - o : kFusedSlabD);
+      TRY(launch_ms_fused(d_left, d_right, N, H, W, &q, d_out, d_min, base, s, g.Dn, o, o > 0));
+    }
+    return 0;
+  }
   GenericWs ws;
   ws.carve(base, g, p);
   const size_t n = (size_t)g.h * g.w;

@@ -219,6 +219,8 @@ struct FusedArgs {
   float* mins;          // slab phase A only: [N][mins_planes][h][w], planes 0-3 = per-pixel minima of this launch's disparities
   int out_channels;     // channel count of the output tensor (pair stride): 8, or 16 when the caller adds the right view
   int mins_planes;      // 4, or 8 when the caller adds the right view
+  int out_D, out_d0;    // slab phase A: disparity count of the output tensor and where this launch's slab sits in it
+  int mins_accumulate;  // slab phase A: fold into the minima already in `mins` (a later slab of the same volume)
   float k_cen, k_ncc, k_sad;
   int DC;               // disparity steps per d-group (even: phase 1 walks disparity pairs)
   int tiles_x;
@@ -808,13 +810,16 @@ __device__ __forceinline__ void tile_slab_a(const FusedArgs& a, const TileId& t,
   const FusedGeom& g = a.g;
   const int D = g.D;
   const size_t plane = (size_t)g.h * g.w;
-  const size_t chan = plane * D;
+  const size_t chan = plane * a.out_D;
   if (tid < 4 * kTile) {  // minima across the d-groups -> global
     float v = kFill;
 #pragma unroll
     for (int gq = 0; gq < kGroups; ++gq) v = fminf(v, s_red[gq * 4 * kTile + tid]);
     const int m = tid / kTile, x = t.x0 + tid % kTile;
-    if (x < g.w) a.mins[(((size_t)t.n * a.mins_planes + m) * g.h + t.y) * g.w + x] = v;
+    if (x < g.w) {
+      float* mp = a.mins + (((size_t)t.n * a.mins_planes + m) * g.h + t.y) * g.w + x;
+      *mp = a.mins_accumulate ? fminf(*mp, v) : v;
+    }
   }
   const int q4 = (tid & 7) * 4;
   const int dl = tid >> 3;
@@ -838,7 +843,7 @@ __device__ __forceinline__ void tile_slab_a(const FusedArgs& a, const TileId& t,
                                   normalise_cost(v2.w, 2));
     const float4 c3 = make_float4(normalise_cost(v3.x, 3), normalise_cost(v3.y, 3), normalise_cost(v3.z, 3),
                                   normalise_cost(v3.w, 3));
-    float* o = orow + (size_t)d * plane;
+    float* o = orow + (size_t)(a.out_d0 + d) * plane;
     if (vec) {
       store_quads<true>(o, chan, nlive, c0, c1, c2, c3);
       // parked raw costs are read again by slab_phase_b/c: plain (cached) stores
@@ -1005,9 +1010,13 @@ size_t fused_workspace_bytes(int N, int H, int W, int Dn, const msn_ms_params* p
 }
 
 // d_mins == nullptr: the whole feature volume (p describes all disparities).  Otherwise phase A of
-// the slab path for disparities [p->d_begin, p->d_begin + p->d_count).
+// the slab path for disparities [p->d_begin, p->d_begin + p->d_count): the output tensor holds
+// out_D disparities per channel and the slab starts at out_d0 in it (a rank's own slab tensor:
+// out_D = d_count, out_d0 = 0; slabs of one big volume on one GPU: out_D = ndisp, out_d0 = d_begin,
+// accumulate != 0 from the second slab on).
 int launch_ms_fused(const uint8_t* d_left, const uint8_t* d_right, int N, int H, int W, const msn_ms_params* p,
-                    float* d_out, float* d_mins, char* workspace, cudaStream_t s) {
+                    float* d_out, float* d_mins, char* workspace, cudaStream_t s, int out_D, int out_d0,
+                    int accumulate) {
   if (N == 0) return 0;
   FusedGeom g = make_geom(N, H, W, p);
   FusedWs ws;
@@ -1048,6 +1057,9 @@ int launch_ms_fused(const uint8_t* d_left, const uint8_t* d_right, int N, int H,
   a.mins = d_mins;
   a.out_channels = p->lr ? 16 : 8;
   a.mins_planes = p->lr ? 8 : 4;
+  a.out_D = out_D > 0 ? out_D : g.D;
+  a.out_d0 = out_d0;
+  a.mins_accumulate = accumulate;
   a.k_cen = aml_scale(p->cens_sigma);
   a.k_ncc = aml_scale(p->ncc_sigma);
   a.k_sad = aml_scale(p->sad_sigma);

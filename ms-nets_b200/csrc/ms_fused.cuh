@@ -13,8 +13,11 @@ size_t fused_workspace_bytes(int N, int H, int W, int Dn, const msn_ms_params* p
 // d_mins == nullptr: the whole volume.  d_mins != nullptr: phase A of the disparity-slab path
 // (channels 0-3 final, raw costs parked in channels 4-7, per-pixel slab minima in d_mins
 // [N][4 or 8][h][w]).
+// out_D / out_d0 / accumulate: see ms_fused.cu (slabs of one volume processed on one GPU).
 int launch_ms_fused(const uint8_t* d_left, const uint8_t* d_right, int N, int H, int W, const msn_ms_params* p,
-                    float* d_out, float* d_mins, char* workspace, cudaStream_t s);
+                    float* d_out, float* d_mins, char* workspace, cudaStream_t s, int out_D = 0, int out_d0 = 0,
+                    int accumulate = 0);
+constexpr int kFusedSlabD = 192;   // slab size when a volume above the fused kernel's limit is cut into slabs
 
 int profile_enable(int on);
 int profile_read(double* prep_ms, double* sadsob_ms, double* fused_ms, int* calls);

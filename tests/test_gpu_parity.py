@@ -153,6 +153,16 @@ def test_ms_features_fused_large_d(ms, oracle, H, W, D):
     _check_features(got, want)
 
 
+@pytest.mark.parametrize("D", [500, 640])
+def test_ms_features_above_fused_limit_uses_slabs(ms, oracle, D):
+    """More than 448 disparities: the volume is cut into slabs of 192 through the fused kernel's
+    phase-A form, minima folded across slabs, phases B/C over all D (one GPU)."""
+    L, R = synth_pair(31, 700, 1500 + D, shift=9)
+    got = ms.cbmv.ms_features(L, R, D, board_h=10, board_w_left=10, board_w_right=10)
+    want = oracle.ms_features(L, R, D, board_h=10, board_w_left=10, board_w_right=10)
+    _check_features(got, want)
+
+
 def test_ms_features_fused_interior_tiles(ms, oracle):
     """D = 8 * 6: the d-groups cover D exactly, so tiles right of column D + 5 take the
     instantiation without validity selects; the image is wide enough to have several."""
