@@ -23,7 +23,7 @@ __device__ __forceinline__ float ex2_approx(float x) {
 
 // AML term expf(-(c-m)^2 / sigma) = 2^(-(c-m)^2 * log2(e)/sigma)   (featextract.cpp:444-452).
 // Tolerance class: the reference calls glibc expf and sums sequentially; here the
-// SFU ex2 (rel. error ~2^-22) and tree sums are used.  Stated bound, checked in
+// SFU ex2 (rel. error ~2^-22) is used and the sum is replayed in the same order.  Stated bound, checked in
 // tests/: |AML - reference| <= 2e-6 on outputs in [0,1].
 __host__ __device__ __forceinline__ float aml_scale(float sigma) { return 1.4426950408889634f / sigma; }
 __device__ __forceinline__ float aml_e(float c, float m, float k) {
