@@ -39,9 +39,15 @@ __global__ void sadsob_vband_kernel(const float* __restrict__ L, const float* __
                                     int pitch, int d_begin, int RB, int NB, size_t img_stride,
                                     float* __restrict__ Vb) {
   const int IW = W + 1;
-  const int j = blockIdx.x * blockDim.x + threadIdx.x;
+  // thread i owns table column j = i + 1, i.e. image column i: the warp's loads of L start on a
+  // 128-byte line.  Table column 0 is identically zero; thread 0 writes it as well.
+  const int j = blockIdx.x * blockDim.x + threadIdx.x + 1;
   const int dd = blockIdx.y, d = d_begin + dd, n = blockIdx.z;
   if (j >= IW) return;
+  if (j == 1) {
+    float* z = Vb + (((size_t)n * gridDim.y + dd) * NB) * IW;
+    for (int b = 0; b < NB; ++b) z[(size_t)b * IW] = 0.f;
+  }
   const int jc = j - 1;
   const bool active = (jc >= d);  // implies jc >= 0; jc < W because j <= W
   const float* l = L + n * img_stride + jc;
@@ -219,7 +225,10 @@ sadsob_scan5_kernel(const float* __restrict__ L, const float* __restrict__ R, in
   float* trow = T + lane * kS5Stride;
   for (int t = t0; t <= t1; ++t) {
     // (a) lanes own table columns: vertical prefix inside the band (loads first, then chain)
-    const int j = t * kSadTile + lane;
+    // tile t holds table columns j = 32t+1 .. 32t+32, i.e. image columns jc = 32t .. 32t+31: the
+    // warp's loads of L start on a 128-byte line, and so do its stores of the 27 output rows when
+    // the caller's output pointer is offset by 2 columns modulo 32 (the fused path's scratch is)
+    const int j = t * kSadTile + lane + 1;
     const int jc = j - 1;
     const float v = (j < IW) ? __ldg(vb + j) : 0.f;
     if (t == t0 || t == t1) {
@@ -244,7 +253,7 @@ sadsob_scan5_kernel(const float* __restrict__ L, const float* __restrict__ R, in
     }
     __syncwarp();
     // (c) lanes own origin columns: out(r) = ((S[r+5][j+5] - S[r+5][j]) - S[r][j+5]) + S[r][j]
-    const int jo = t * kSadTile - kS5W + lane;  // window origin column
+    const int jo = t * kSadTile + 1 - kS5W + lane;  // window origin column
     if (jo >= d && jo < W - kS5W) {
       float lo[kS5W], hi[kS5W];  // table rows r .. r+4 at columns jo and jo+5
 #pragma unroll
@@ -299,7 +308,7 @@ int launch_sadsob_n(const float* L, const float* R, int N, int H, int W, int Dn,
   if (NB <= 0 || W - wsize <= 0 || Dn <= 0) return 0;
   float* Vb = static_cast<float*>(workspace);
   const size_t img_stride = (size_t)H * W;
-  dim3 g1(div_up(W + 1, 128), Dn, N);
+  dim3 g1(div_up(W, 128), Dn, N);
   sadsob_vband_kernel<<<g1, 128, 0, s>>>(L, R, H, W, W, d_begin, RB, NB, img_stride, Vb);
   MSN_LAUNCH_OK();
   dim3 g2(div_up((long long)Dn * NB, kSadWarps), 1, N);
@@ -327,7 +336,7 @@ int launch_sadsob5_padded(const float* L, const float* R, int N, int H, int W, i
   float* Vb = static_cast<float*>(workspace);
   const size_t img_stride = (size_t)(H + kSadRowPad) * SP;
   const size_t out_stride = (size_t)Dn * H * SP;
-  dim3 g1(div_up(W + 1, 128), Dn, N);
+  dim3 g1(div_up(W, 128), Dn, N);
   sadsob_vband_kernel<<<g1, 128, 0, s>>>(L, R, H, W, SP, d_begin, RB, NB, img_stride, Vb);
   MSN_LAUNCH_OK();
   dim3 g5(div_up((long long)Dn * NB, kS5Warps), 1, N);
