@@ -115,7 +115,7 @@ def run_ours(args):
     torch.cuda.set_device(local_rank)
     if world > 1:
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
-        dist.init_process_group("nccl")
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
     import __graft_entry__
     if rank == 0:
         __graft_entry__.build()
