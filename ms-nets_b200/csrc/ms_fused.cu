@@ -91,7 +91,7 @@ struct FusedWs {
   float* fimg[2];
   float* sob[2];
   float* meanR[2]; // ZSAD means of the right image as plain floats; copy 1 is shifted by one column
-  float* luts;     // [128] census AML exponentials + [256] census byte -> channel 0
+  float* luts;     // [256] census AML exponentials (0 from 121 on) + [256] census byte -> channel 0
   float* sadsob;   // [N][D][H][W]
   void* sad_ws;
   size_t total;
@@ -104,7 +104,7 @@ struct FusedWs {
     for (int i = 0; i < 2; ++i) fimg[i] = (float*)take(np * sizeof(float));
     for (int i = 0; i < 2; ++i) sob[i] = (float*)take((size_t)g.N * (g.H + kSadRowPad) * g.Ws * sizeof(float));  // zero padded
     for (int i = 0; i < 2; ++i) meanR[i] = (float*)take((np + 16) * sizeof(float));
-    luts = (float*)take(384 * sizeof(float));
+    luts = (float*)take(512 * sizeof(float));
     sadsob = (float*)take((size_t)g.N * g.D * g.H * g.Ws * sizeof(float) + 256);
     sad_ws = take(sadsob_workspace_bytes_n(g.N, g.H, g.W, g.D, kSadW));
     total = off;
@@ -124,8 +124,8 @@ ms_prep_kernel(const uint8_t* __restrict__ left, const uint8_t* __restrict__ rig
     // channel-0 value k/120 of a parked census byte (a true IEEE division; 255 = no cost ->
     // clip(fill, 0, 120)/120 = 1)
     for (int kk = threadIdx.x; kk < 256; kk += blockDim.x) {
-      if (kk < 128) luts[kk] = (kk <= 120) ? ex2_approx(-(float)(kk * kk) * k_cen) : 0.f;
-      luts[128 + kk] = (kk <= 120) ? __fdiv_rn((float)kk, 120.0f) : 1.0f;
+      luts[kk] = (kk <= 120) ? ex2_approx(-(float)(kk * kk) * k_cen) : 0.f;
+      luts[256 + kk] = (kk <= 120) ? __fdiv_rn((float)kk, 120.0f) : 1.0f;
     }
   }
   const int xp = blockIdx.x * blockDim.x + threadIdx.x;
@@ -213,7 +213,7 @@ struct FusedArgs {
   const RStat *statL, *statR;
   const float *fL, *fR;
   const float *meanR0, *meanR1;  // right-image ZSAD means; meanR1[x] = mean[x-1]
-  const float* luts;    // [128] + [256], see ms_prep_kernel
+  const float* luts;    // [256] + [256], see ms_prep_kernel
   const float* sadsob;  // [N][D][H][Ws] (+ slack)
   float* out;           // [N][8][D][h][w]
   float* mins;          // slab phase A only: [N][mins_planes][h][w], planes 0-3 = per-pixel minima of this launch's disparities
@@ -222,6 +222,7 @@ struct FusedArgs {
   int out_D, out_d0;    // slab phase A: disparity count of the output tensor and where this launch's slab sits in it
   int mins_accumulate;  // slab phase A: fold into the minima already in `mins` (a later slab of the same volume)
   float k_cen, k_ncc, k_sad;
+  float neg_zero;       // -0.0f (x + -0.0f == x exactly): an operand the compiler cannot fold
   int DC;               // disparity steps per d-group (even: phase 1 walks disparity pairs)
   int tiles_x;
 };
@@ -916,7 +917,7 @@ ms_fused_kernel(const FusedArgs a, const __grid_constant__ CUtensorMap sad_map) 
     stage_right<L, NT>(a, t, smem_raw);
   }
   if (tid < 128) s_lut[tid] = __ldg(a.luts + tid);
-  s_lutn[tid] = __ldg(a.luts + 128 + tid);
+  s_lutn[tid] = __ldg(a.luts + 256 + tid);
   LeftRegs lr;
   load_left(a, t, px, lr);
   if (!kTma) cp_async_wait_all();
@@ -939,6 +940,169 @@ ms_fused_kernel(const FusedArgs a, const __grid_constant__ CUtensorMap sad_map) 
   __syncthreads();
   if (kSlabA) tile_slab_a<L>(a, t, tid, s_par, s_cen, s_red, s_lutn);
   else tile_back_half<L>(a, t, tid, s_par, s_cen, s_red, s_min, s_inv, s_lut, s_lutn);
+}
+
+#include "ms_fused_v2.cuh"
+
+// Back half of a tile for DISPARITY-SLAB SHARDING, v2 thread layout (16 d-groups in s_red).
+template <class L>
+__device__ __forceinline__ void tile_slab_a2(const FusedArgs& a, const TileId& t, int tid, const float* s_par,
+                                             const uint8_t* s_cen, const float* s_red, const float* s_lutn) {
+  constexpr int PS = L::PS;
+  const FusedGeom& g = a.g;
+  const int D = g.D;
+  const size_t plane = (size_t)g.h * g.w;
+  const size_t chan = plane * a.out_D;
+  if (tid < 4 * kTile) {  // minima across the d-groups -> global
+    float v = kFill;
+#pragma unroll
+    for (int gq = 0; gq < kG2; ++gq) v = fminf(v, s_red[gq * 4 * kTile + tid]);
+    const int m = tid / kTile, x = t.x0 + tid % kTile;
+    if (x < g.w) {
+      float* mp = a.mins + (((size_t)t.n * a.mins_planes + m) * g.h + t.y) * g.w + x;
+      *mp = a.mins_accumulate ? fminf(*mp, v) : v;
+    }
+  }
+  const int q4 = (tid & 7) * 4;
+  const int dl = tid >> 3;
+  const bool vec_ok = ((g.w & 3) == 0) && ((reinterpret_cast<uintptr_t>(a.out) & 15) == 0);
+  float* orow = a.out + (size_t)t.n * a.out_channels * chan + (size_t)t.y * g.w + (t.x0 + q4);
+  const int nlive = min(4, g.w - (t.x0 + q4));
+  const bool vec = vec_ok && nlive == 4;
+#pragma unroll 2
+  for (int d = dl; d < D; d += 32) {
+    const float* e0 = s_par + d * kTile + q4;
+    const uchar4 cb = *reinterpret_cast<const uchar4*>(s_cen + d * kTile + q4);
+    const float4 v1 = *reinterpret_cast<const float4*>(e0);
+    const float4 v2 = *reinterpret_cast<const float4*>(e0 + PS);
+    const float4 v3 = *reinterpret_cast<const float4*>(e0 + 2 * PS);
+    const float4 v0 = make_float4(cb.x == 255 ? kFill : (float)cb.x, cb.y == 255 ? kFill : (float)cb.y,
+                                  cb.z == 255 ? kFill : (float)cb.z, cb.w == 255 ? kFill : (float)cb.w);
+    const float4 c0 = make_float4(s_lutn[cb.x], s_lutn[cb.y], s_lutn[cb.z], s_lutn[cb.w]);
+    const float4 c1 = make_float4(normalise_cost(v1.x, 1), normalise_cost(v1.y, 1), normalise_cost(v1.z, 1),
+                                  normalise_cost(v1.w, 1));
+    const float4 c2 = make_float4(normalise_cost(v2.x, 2), normalise_cost(v2.y, 2), normalise_cost(v2.z, 2),
+                                  normalise_cost(v2.w, 2));
+    const float4 c3 = make_float4(normalise_cost(v3.x, 3), normalise_cost(v3.y, 3), normalise_cost(v3.z, 3),
+                                  normalise_cost(v3.w, 3));
+    float* o = orow + (size_t)(a.out_d0 + d) * plane;
+    if (vec) {
+      store_quads<true>(o, chan, nlive, c0, c1, c2, c3);
+      *reinterpret_cast<float4*>(o + 4 * chan) = v0;
+      *reinterpret_cast<float4*>(o + 5 * chan) = v1;
+      *reinterpret_cast<float4*>(o + 6 * chan) = v2;
+      *reinterpret_cast<float4*>(o + 7 * chan) = v3;
+    } else {
+      store_quads<false>(o, chan, nlive, c0, c1, c2, c3);
+      const float rr[4][4] = {{v0.x, v0.y, v0.z, v0.w}, {v1.x, v1.y, v1.z, v1.w}, {v2.x, v2.y, v2.z, v2.w},
+                              {v3.x, v3.y, v3.z, v3.w}};
+#pragma unroll
+      for (int ch = 0; ch < 4; ++ch)
+#pragma unroll
+        for (int i = 0; i < 4; ++i)
+          if (i < nlive) o[(4 + ch) * chan + i] = rr[ch][i];
+    }
+  }
+}
+
+// ---- v2 kernel: one CTA per tile (see ms_fused_v2.cuh) ---------------------------------------
+template <int DMAX, bool kTma, bool kSlabA>
+__global__ void __launch_bounds__(256, 2)
+ms_fused2_kernel(const FusedArgs a, const __grid_constant__ CUtensorMap sad_map) {
+  using L = Lay2<DMAX>;
+  constexpr int NT = 256;
+  constexpr int PS = L::PS;
+  extern __shared__ __align__(128) unsigned char smem_raw[];  // TMA destinations need 128 B
+  const FusedGeom& g = a.g;
+  const int D = g.D;
+  unsigned long long* s_bar = reinterpret_cast<unsigned long long*>(smem_raw + L::off_bar);  // [0] rows, [1] sadsob tile
+  float* s_red = reinterpret_cast<float*>(smem_raw + L::off_red);    // [16][4][32]
+  float* s_min = reinterpret_cast<float*>(smem_raw + L::off_min);
+  float* s_inv = reinterpret_cast<float*>(smem_raw + L::off_inv);
+  float* s_lut = reinterpret_cast<float*>(smem_raw + L::off_lut);
+  float* s_lutn = reinterpret_cast<float*>(smem_raw + L::off_lutn);
+  float* s_par = reinterpret_cast<float*>(smem_raw + L::off_par);    // [3][DS][32]
+  uint8_t* s_cen = smem_raw + L::off_par + L::pk_cen;                // [DS][32]
+  const int tid = threadIdx.x;
+  const TileId t = decode_tile(blockIdx.x, a);
+  if (kTma) {
+    if (tid == 0) {
+      mbar_init(&s_bar[0], 1);
+      mbar_init(&s_bar[1], 1);
+      mbar_init_fence();
+      // rows first: phase 1 waits for them; the SAD-of-Sobel box is only needed after phase 1
+      stage2_rows_tma<L>(a, t, smem_raw, &s_bar[0]);
+      stage_sad_tma(a, &sad_map, t, s_par + PS, &s_bar[1]);
+    }
+  } else {
+    // the tile's SAD-of-Sobel costs: async global -> parked plane 1
+    const size_t splane = (size_t)g.H * g.Ws;
+    const float* src = a.sadsob + ((size_t)t.n * D * g.H + (t.y + g.bh)) * g.Ws + (t.x0 + g.bwl + g.sxo);
+    for (int i = tid; i < D * kTile; i += NT) cp_async4(s_par + PS + i, src + (size_t)(i >> 5) * splane + (i & 31));
+    stage2_rows_ldgsts<L, NT>(a, t, smem_raw);
+  }
+  s_lut[tid] = __ldg(a.luts + tid);
+  s_lutn[tid] = __ldg(a.luts + 256 + tid);
+
+  P1Ctx c;
+  c.pr = tid & 15;
+  const int grp = tid >> 4;
+  Left2 lr;
+  load_left2(a, t, c.pr, lr);
+  // interior tile: all 32 pixels have every cost at every disparity, the d-groups cover D exactly
+  // and walk whole blocks of 6 steps
+  const int Xl = t.x0 + g.bwl, Yr = t.y + g.bh;
+  const bool all_valid = (Xl - 5 >= g.d0 + D - 1) && (Xl + kTile - 1 < g.W - 6) && (Yr >= 5) && (Yr < g.H - 6);
+  const bool fast = all_valid && (kG2 * a.DC == D) && (a.DC % 6 == 0);
+  c.dA0 = grp * a.DC - ((!fast && grp == 0) ? 1 : 0);
+  c.nsteps = a.DC + ((!fast && grp == 0) ? 1 : 0);
+  c.ir0 = 2 * c.pr + L::SL + (D - 1) - c.dA0;
+  {
+    const int XbaseP = stage2_xbase<L>(a, t);
+    c.shift = (XbaseP - 2) & 3;
+    c.mofs = XbaseP & 3;
+  }
+  c.lastB_dummy = (grp == kG2 - 1);
+  {
+    const int H = g.H, W = g.W;
+    const int XA = t.x0 + 2 * c.pr + g.bwl, XB = XA + 1, Y = Yr;
+    const bool yc = (Y >= 5 && Y < H - 6), yn = (Y >= 1 && Y < H - 2), yz = (Y >= 2 && Y < H - 3);
+    c.dmaxA[0] = min(D - 1, ((yc && XA >= 5 && XA < W - 6) ? XA - 5 : -1) - g.d0);
+    c.dmaxB[0] = min(D - 1, ((yc && XB >= 5 && XB < W - 6) ? XB - 5 : -1) - g.d0);
+    c.dmaxA[1] = min(D - 1, ((yn && XA >= 1 && XA < W - 2) ? XA - 1 : -1) - g.d0);
+    c.dmaxB[1] = min(D - 1, ((yn && XB >= 1 && XB < W - 2) ? XB - 1 : -1) - g.d0);
+    c.dmaxA[2] = min(D - 1, ((yz && XA >= 2 && XA < W - 3) ? XA - 2 : -1) - g.d0);
+    c.dmaxB[2] = min(D - 1, ((yz && XB >= 2 && XB < W - 3) ? XB - 2 : -1) - g.d0);
+  }
+  if (!kTma) cp_async_wait_all();
+  __syncthreads();                       // barrier init, LUTs (and LDGSTS data) visible to everyone
+  if (kTma) mbar_wait(&s_bar[0], 0);
+
+  P1Min mn;
+  mn.cenA = 255; mn.cenB = 255;
+  mn.nccA = kFill; mn.nccB = kFill; mn.sadA = kFill; mn.sadB = kFill;
+  if (fast) {
+    if (grp == 0) p1_extra_b0<L>(a, smem_raw, s_par, s_cen, lr, c.pr, c.ir0 + 1, c.shift, c.mofs, mn);
+    p1_census_ncc<L, true>(a, smem_raw, s_par, s_cen, lr, c, mn);
+    p1_zsad<L, true>(a, smem_raw, s_par, lr, c, mn);
+  } else {
+    p1_census_ncc<L, false>(a, smem_raw, s_par, s_cen, lr, c, mn);
+    p1_zsad<L, false>(a, smem_raw, s_par, lr, c, mn);
+  }
+  {
+    float* r0 = s_red + grp * 4 * kTile + 2 * c.pr;
+    r0[0] = (mn.cenA == 255) ? kFill : (float)mn.cenA;
+    r0[1] = (mn.cenB == 255) ? kFill : (float)mn.cenB;
+    r0[kTile] = mn.nccA;
+    r0[kTile + 1] = mn.nccB;
+    r0[3 * kTile] = mn.sadA;
+    r0[3 * kTile + 1] = mn.sadB;
+  }
+  if (kTma) mbar_wait(&s_bar[1], 0);   // (LDGSTS: landed before the first barrier)
+  sob_finish<L>(a, t, s_par, s_red, tid, all_valid);
+  __syncthreads();
+  if (kSlabA) tile_slab_a2<L>(a, t, tid, s_par, s_cen, s_red, s_lutn);
+  else tile_back_half2<L>(a, t, tid, s_par, s_cen, s_red, s_min, s_inv, s_lut, s_lutn);
 }
 
 // Optional per-kernel timing (msn_profile_enable): CUDA events recorded on the launch
@@ -964,6 +1128,10 @@ static PFN_encodeTiled get_encode_fn() {
     return (PFN_encodeTiled)p;
   }();
   return fn;
+}
+static bool fused_v1() {
+  const char* e = getenv("MSNETS_FUSED_V2");   // v2 (diagonal pairs) is opt-in until it beats v1
+  return !(e && e[0] == '1');
 }
 static bool tma_disabled() {
   const char* e = getenv("MSNETS_NO_TMA");
@@ -1063,6 +1231,7 @@ int launch_ms_fused(const uint8_t* d_left, const uint8_t* d_right, int N, int H,
   a.k_cen = aml_scale(p->cens_sigma);
   a.k_ncc = aml_scale(p->ncc_sigma);
   a.k_sad = aml_scale(p->sad_sigma);
+  a.neg_zero = -0.0f;
   a.tiles_x = (g.w + kTile - 1) / kTile;
   const long long tiles = (long long)N * g.h * a.tiles_x;
   MSN_REQUIRE(tiles <= 2147483647LL, "ms_features: too many tiles for one launch");
@@ -1085,19 +1254,27 @@ int launch_ms_fused(const uint8_t* d_left, const uint8_t* d_right, int N, int H,
       if (rc != CUDA_SUCCESS) use_tma = false;
     }
   }
-  a.DC = 2 * (((g.D + kGroups - 1) / kGroups + 1) / 2);   // phase 1 walks disparity pairs
-#define MSN_FUSED_LAUNCH1(DMAX, TMA, SLAB)                                                            \
+  const bool v1 = fused_v1();
+  a.DC = v1 ? 2 * (((g.D + kGroups - 1) / kGroups + 1) / 2)   // v1 phase 1 walks disparity pairs
+            : (g.D + kG2 - 1) / kG2;                           // v2: steps per d-group
+#define MSN_FUSED_LAUNCH1(KERN, LAY, DMAX, TMA, SLAB)                                                 \
   {                                                                                                   \
-    auto kern = ms_fused_kernel<DMAX, TMA, SLAB>;                                                     \
-    const size_t smem = Lay<DMAX, kSlack>::bytes;                                                     \
+    auto kern = KERN<DMAX, TMA, SLAB>;                                                                \
+    const size_t smem = LAY::bytes;                                                                   \
     MSN_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));  \
     kern<<<(unsigned)tiles, 256, smem, s>>>(a, sad_map);                                              \
   }
 #define MSN_FUSED_LAUNCH(DMAX, TMA)                                                                   \
   {                                                                                                   \
-    if (d_mins) MSN_FUSED_LAUNCH1(DMAX, TMA, true)                                                    \
-    else MSN_FUSED_LAUNCH1(DMAX, TMA, false)                                                          \
+    if (v1) {                                                                                         \
+      if (d_mins) MSN_FUSED_LAUNCH1(ms_fused_kernel, Lay<DMAX MSN_COMMA kSlack>, DMAX, TMA, true)     \
+      else MSN_FUSED_LAUNCH1(ms_fused_kernel, Lay<DMAX MSN_COMMA kSlack>, DMAX, TMA, false)           \
+    } else {                                                                                          \
+      if (d_mins) MSN_FUSED_LAUNCH1(ms_fused2_kernel, Lay2<DMAX>, DMAX, TMA, true)                    \
+      else MSN_FUSED_LAUNCH1(ms_fused2_kernel, Lay2<DMAX>, DMAX, TMA, false)                          \
+    }                                                                                                 \
   }
+#define MSN_COMMA ,
 #define MSN_FUSED_CASE(DMAX)                                                                          \
   if (g.D <= DMAX) {                                                                                  \
     if (use_tma && DMAX <= 256) MSN_FUSED_LAUNCH(DMAX <= 256 ? DMAX : 256, true)                      \
@@ -1112,6 +1289,7 @@ int launch_ms_fused(const uint8_t* d_left, const uint8_t* d_right, int N, int H,
 #undef MSN_FUSED_CASE
 #undef MSN_FUSED_LAUNCH
 #undef MSN_FUSED_LAUNCH1
+#undef MSN_COMMA
   MSN_LAUNCH_OK();
   if (prof) {
     MSN_CUDA_OK(cudaEventRecord(rec.ev[3], s));
