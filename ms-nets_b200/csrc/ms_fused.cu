@@ -37,7 +37,7 @@ constexpr int kTile = 32;     // pixels per tile: one output row segment of 128 
 constexpr int kPadT = 2;      // padded rows above/below (ZSAD halo)
 constexpr int kPadR = 48;     // padded columns to the right (tile overhang + halo + copy granules)
 constexpr int kCensW = 11, kNccW = 3, kSadW = 5;
-constexpr int kMaxFusedD = 448;
+constexpr int kMaxFusedD = 384;   // more disparities: slabs of kFusedSlabD (capi.cu)
 
 struct __align__(16) RStat {
   float mean;  // ZSAD window mean (matchers.cpp:482)
@@ -359,25 +359,22 @@ ms_fused_kernel(const FusedArgs a, const __grid_constant__ CUtensorMap sad_map) 
   const int grp = tid >> 4;
   Left2 lr;
   load_left2(a, t, c.pr, lr);
-  // interior tile: all 32 pixels have every cost at every disparity, the d-groups cover D exactly
-  // and walk whole blocks of 6 steps
-  const int Xl = t.x0 + g.bwl, Yr = t.y + g.bh;
-  const bool all_valid = (Xl - 5 >= g.d0 + D - 1) && (Xl + kTile - 1 < g.W - 6) && (Yr >= 5) && (Yr < g.H - 6);
-  const bool fast = all_valid && (kG2 * a.DC == D) && (a.DC % 6 == 0);
-  c.dA0 = grp * a.DC - ((!fast && grp == 0) ? 1 : 0);
-  c.nsteps = a.DC + ((!fast && grp == 0) ? 1 : 0);
+  c.dA0 = grp * a.DC;
+  c.nsteps = a.DC;
   c.cx0 = t.x0 + 2 * c.pr + g.bwl + g.padL - (g.d0 + c.dA0);
-  c.lastB_dummy = (grp == kG2 - 1);
+  // largest local disparity with a cost, per pixel and matcher (-1 - d0 or less: none):
+  // cost(y,x,d) exists iff the window origin is inside the image and x - wc >= d (and d < D)
+  int dmaxCN[4], dmaxZA, dmaxZB;   // CN: census A, census B, ncc A, ncc B
   {
     const int H = g.H, W = g.W;
-    const int XA = t.x0 + 2 * c.pr + g.bwl, XB = XA + 1, Y = Yr;
+    const int XA = t.x0 + 2 * c.pr + g.bwl, XB = XA + 1, Y = t.y + g.bh;
     const bool yc = (Y >= 5 && Y < H - 6), yn = (Y >= 1 && Y < H - 2), yz = (Y >= 2 && Y < H - 3);
-    c.dmaxA[0] = min(D - 1, ((yc && XA >= 5 && XA < W - 6) ? XA - 5 : -1) - g.d0);
-    c.dmaxB[0] = min(D - 1, ((yc && XB >= 5 && XB < W - 6) ? XB - 5 : -1) - g.d0);
-    c.dmaxA[1] = min(D - 1, ((yn && XA >= 1 && XA < W - 2) ? XA - 1 : -1) - g.d0);
-    c.dmaxB[1] = min(D - 1, ((yn && XB >= 1 && XB < W - 2) ? XB - 1 : -1) - g.d0);
-    c.dmaxA[2] = min(D - 1, ((yz && XA >= 2 && XA < W - 3) ? XA - 2 : -1) - g.d0);
-    c.dmaxB[2] = min(D - 1, ((yz && XB >= 2 && XB < W - 3) ? XB - 2 : -1) - g.d0);
+    dmaxCN[0] = min(D - 1, ((yc && XA >= 5 && XA < W - 6) ? XA - 5 : -1) - g.d0);
+    dmaxCN[1] = min(D - 1, ((yc && XB >= 5 && XB < W - 6) ? XB - 5 : -1) - g.d0);
+    dmaxCN[2] = min(D - 1, ((yn && XA >= 1 && XA < W - 2) ? XA - 1 : -1) - g.d0);
+    dmaxCN[3] = min(D - 1, ((yn && XB >= 1 && XB < W - 2) ? XB - 1 : -1) - g.d0);
+    dmaxZA = min(D - 1, ((yz && XA >= 2 && XA < W - 3) ? XA - 2 : -1) - g.d0);
+    dmaxZB = min(D - 1, ((yz && XB >= 2 && XB < W - 3) ? XB - 2 : -1) - g.d0);
   }
   if (!kTma) cp_async_wait_all();
   __syncthreads();                       // barrier init (and LDGSTS data) visible to everyone
@@ -386,14 +383,9 @@ ms_fused_kernel(const FusedArgs a, const __grid_constant__ CUtensorMap sad_map) 
   P1Min mn;
   mn.cenA = 255; mn.cenB = 255;
   mn.nccA = kFill; mn.nccB = kFill; mn.sadA = kFill; mn.sadB = kFill;
-  if (fast) {
-    if (grp == 0) p1_extra_b0<L>(smem_raw, sg, s_par, s_cen, lr, c.pr, c.cx0 + 1, mn);
-    p1_census_ncc<L, true>(a, smem_raw, sg, s_par, s_cen, lr, c, mn);
-    p1_zsad<L, true>(a, smem_raw, sg, s_par, lr, c, mn);
-  } else {
-    p1_census_ncc<L, false>(a, smem_raw, sg, s_par, s_cen, lr, c, mn);
-    p1_zsad<L, false>(a, smem_raw, sg, s_par, lr, c, mn);
-  }
+  if (grp == 0) p1_extra_b0<L>(smem_raw, sg, s_par, s_cen, lr, c.pr, c.cx0 + 1, dmaxCN[1], dmaxCN[3], dmaxZB, mn);
+  p1_census_ncc<L>(a, smem_raw, sg, s_par, s_cen, lr, c, dmaxCN, mn);
+  p1_zsad<L>(a, smem_raw, sg, s_par, lr, c, dmaxZA, dmaxZB, mn);
   {
     float* r0 = s_red + grp * 4 * kTile + 2 * c.pr;
     r0[0] = (mn.cenA == 255) ? kFill : (float)mn.cenA;
@@ -404,10 +396,14 @@ ms_fused_kernel(const FusedArgs a, const __grid_constant__ CUtensorMap sad_map) 
     r0[3 * kTile + 1] = mn.sadB;
   }
   if (kTma) mbar_wait(&s_bar[1], 0);   // (LDGSTS: landed before the first barrier)
-  sob_finish<L>(a, t, s_par, s_red, tid, all_valid);
+  {
+    const int Xl = t.x0 + g.bwl, Yr = t.y + g.bh;   // every pixel of the tile has a SAD-of-Sobel cost at every disparity?
+    const bool sob_all = (Xl - 2 >= g.d0 + D - 1) && (Xl + kTile - 1 < g.W - 3) && (Yr >= 2) && (Yr < g.H - 3);
+    sob_finish<L>(a, t, s_par, s_red, tid, sob_all);
+  }
   __syncthreads();
   if (kSlabA) tile_slab_a<L>(a, t, tid, s_par, s_cen, s_red);
-  else tile_back_half<L>(a, t, tid, s_par, s_cen, s_red, s_min, s_inv);
+  else tile_back_half<L>(a, t, tid, s_par, s_cen, reinterpret_cast<float*>(smem_raw + L::off_cene), s_red, s_min, s_inv);
 }
 
 // Optional per-kernel timing (msn_profile_enable): CUDA events recorded on the launch
@@ -616,8 +612,7 @@ int launch_ms_fused(const uint8_t* d_left, const uint8_t* d_right, int N, int H,
   MSN_FUSED_CASE(128)
   MSN_FUSED_CASE(192)
   MSN_FUSED_CASE(256)
-  MSN_FUSED_CASE(384)
-  MSN_FUSED_CASE(448) { return fail("ms_features: D=%d exceeds the fused kernel's limit", g.D); }
+  MSN_FUSED_CASE(384) { return fail("ms_features: D=%d exceeds the fused kernel's limit", g.D); }
 #undef MSN_FUSED_CASE
 #undef MSN_FUSED_LAUNCH
   MSN_LAUNCH_OK();

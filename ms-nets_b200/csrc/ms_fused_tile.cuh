@@ -3,11 +3,11 @@
 //
 // Tile = (pair n, output row y, 32 consecutive x) x all D; one CTA of 256 threads per tile.
 //
-// What bounds this kernel (ncu, profiles/r2*): NOT instruction issue but the L1 / shared-memory
-// data pipe -- one 128-byte wavefront per cycle per SM (l1tex__data_pipe_lsu_wavefronts at 78-82 %
-// of peak in the round-1 kernel).  Everything below is organised to move fewer wavefronts per
-// voxel: no lookup tables (arithmetic is cheap here), no bank conflicts in the phase-1 loads
-// (de-interleaved staging), each parked cost read the minimum number of times.
+// What bounds this kernel (ncu, profiles/r2*): two resources at once -- the L1 / shared-memory data
+// pipe (one 128-byte wavefront per cycle per SM; the round-1 kernel ran it at 78 % of peak) and
+// instruction issue with only 16 resident warps per SM.  Hence: no lookup tables and no bank
+// conflicts in the phase-1 loads (de-interleaved staging) for the former, packed fp32 arithmetic,
+// exponentials evaluated once and no work on voxels without a cost for the latter.
 //
 //   phase 1   thread = (pixel PAIR (2k, 2k+1), d-group g of 16).  Per step the thread evaluates
 //             two voxels on a DIAGONAL of the volume: A = (x, d) and B = (x+1, d+1).  Both read
@@ -26,12 +26,16 @@
 //                        step (6 physical columns: the next column loads while this one computes)
 //             Raw costs are parked in shared memory [d][32] (ncc, zsad floats; census byte); the
 //             tile's SAD-of-Sobel costs arrive by TMA straight into their parking plane.
-//   phase 2   warp-specialised, both halves only READ the parked costs:
-//             warps 0-3  one thread per (pixel, matcher): AML denominator, exponentials evaluated
-//                        on the fly and added sequentially in d order as the reference does
-//                        (featextract.cpp:444-447);
-//             warps 4-7  thread = (pixel quad, d): channels 0-3 normalised, 128-bit row stores.
-//   phase 3   all warps: channels 4-7 = exp(-(c-m)^2/sigma) / den, 128-bit row stores.
+//             A thread walks its disparities in blocks of 6 steps; a block in which every voxel has
+//             its costs runs a body without validity selects, a block past the valid range only
+//             parks fill (no arithmetic at all), the rest a generic body -- chosen per warp.
+//   back half every AML exponential is evaluated ONCE:
+//     pass E  thread = (pixel quad, d): channels 0-3 normalised and stored (128-bit rows), the
+//             exponentials exp(-(c-m)^2/sigma) written over the parked costs (census: own plane
+//             in the dead staging area);
+//     pass S  one thread per (pixel, matcher): the AML denominator, added sequentially in d
+//             order as the reference does (featextract.cpp:444-447) -- loads and adds only;
+//     pass N  thread = (pixel quad, d): channels 4-7 = e * (1/den), 128-bit rows.
 #pragma once
 
 constexpr int kG2 = 16;       // d-groups per tile (16 pixel pairs x 16 groups = 256 threads)
@@ -40,6 +44,8 @@ constexpr int kG2 = 16;       // d-groups per tile (16 pixel pairs x 16 groups =
 //   cl = Xt - d0 - 16*DC - 2,  ch = Xt - d0 + 33,  Xt = x0 + board_w_left + padL,
 // every array as two halves (even columns / odd columns).  Column c lives in half (c & 1) at
 // element (c >> 1) - pstart, pstart = (cl >> 1) rounded down to the array's 16-byte granule.
+// The staging area and the per-group minima are dead once the back half starts: the same bytes
+// then hold the census AML exponentials as a fourth float plane [D][32].
 template <int DMAX>
 struct Lay3 {
   static constexpr int HE = DMAX / 2 + 28;                       // positions per half before alignment slack
@@ -55,7 +61,10 @@ struct Lay3 {
   static constexpr int DS = DMAX + 1;                            // parked rows; row D is scratch for dummy steps
   static constexpr int PS = DS * kTile;                          // floats per parked matcher
   static constexpr size_t off_red = st_bytes;                    // [kG2][4][32] per-group minima
-  static constexpr size_t off_min = off_red + (size_t)kG2 * 4 * kTile * 4;   // [4][32]
+  static constexpr size_t red_end = off_red + (size_t)kG2 * 4 * kTile * 4;
+  static constexpr size_t off_cene = 0;                          // back half: [DMAX][32] census exponentials (aliases the above)
+  static constexpr size_t cene_end = (size_t)DMAX * kTile * 4;
+  static constexpr size_t off_min = ((red_end > cene_end ? red_end : cene_end) + 127) & ~(size_t)127;   // [4][32]
   static constexpr size_t off_inv = off_min + 4 * kTile * 4;     // [4][32]
   static constexpr size_t off_par = (off_inv + 4 * kTile * 4 + 127) & ~(size_t)127;   // [3][DS][32] floats; plane 1 is a TMA destination
   static constexpr size_t pk_cen = (size_t)3 * PS * 4;           // then [DS][32] census bytes
@@ -149,22 +158,20 @@ __device__ __forceinline__ void load_left2(const FusedArgs& a, const TileId& t, 
   lr.descB = __ldg(dp + 1);
   lr.statA = __ldg(sp);
   lr.statB = __ldg(sp + 1);
+  const float* gf = a.fL + img_off + (size_t)(Yp - 2) * g.Wp + (Xp - 2);
 #pragma unroll
   for (int r = 0; r < 5; ++r) {
-    const float* gf = a.fL + img_off + (size_t)(Yp - 2 + r) * g.Wp + (Xp - 2);
 #pragma unroll
     for (int c = 0; c < 6; ++c) lr.px[r][c] = __ldg(gf + c);
+    gf += g.Wp;
   }
 }
 
-// per-thread description of its share of a tile
+// per-thread description of its share of a tile: pixel pair pr = tile pixels 2*pr (voxel A) and
+// 2*pr+1 (voxel B); nsteps steps from local disparity dA0 (voxel B: dA0 + 1); cx0 = padded
+// right-image column x_A - d_A at step 0 (falls by one per step).
 struct P1Ctx {
-  int pr;          // pixel pair: tile pixels 2*pr (voxel A) and 2*pr+1 (voxel B)
-  int dA0;         // local disparity of voxel A at step 0 (group 0 starts at -1: its B covers d = 0)
-  int nsteps;      // steps of this thread
-  int cx0;         // padded right-image column x_A - d_A at step 0 (falls by one per step)
-  int dmaxA[3], dmaxB[3];   // largest local d with a cost: census, ncc, zsad (-1: none)
-  bool lastB_dummy;         // the thread's last step has dB == D (fast path only: last group)
+  int pr, dA0, nsteps, cx0;
 };
 
 struct P1Min {
@@ -187,13 +194,95 @@ __device__ __forceinline__ float ncc_scale(float num, double cl, double cr) {
 // pointer of cb, odd steps through the pointer of cb - 1 (the other half), both with immediates.
 #define MSN_STEP_PTR(p0, p1, sI) (((sI) & 1) ? (p1) - ((sI) >> 1) : (p0) - ((sI) >> 1))
 
+// A thread walks its disparities in BLOCKS of 6 steps (the period of the register-resident sliding
+// windows).  Costs exist for d <= dmax (a per-pixel bound: the window must fit left of x - d), so a
+// block is one of: all 12 voxels have costs -> the clean body (no selects, one basic block); none has
+// (monotone in d: nothing after it has either) -> only fill is parked; mixed / partial -> the generic
+// body with validity selects.  The choice is made per WARP (ballot), so there is no divergence.
+enum { kBlkClean = 0, kBlkGeneric = 1, kBlkFill = 2 };
+__device__ __forceinline__ int block_kind(int dA, int steps_left, int dmaxA_tight, int dmaxB_tight, int dmaxA_loose,
+                                          int dmaxB_loose) {
+  const bool clean = (steps_left >= 6) && (dA + 5 <= dmaxA_tight) && (dA + 6 <= dmaxB_tight);
+  const bool none = (dA > dmaxA_loose) && (dA + 1 > dmaxB_loose);
+  if (__all_sync(0xffffffffu, clean)) return kBlkClean;
+  if (__all_sync(0xffffffffu, none)) return kBlkFill;
+  return kBlkGeneric;
+}
+
 // ---- loop CN: census + NCC ------------------------------------------------------------------
-// kFast: interior tile whose d-groups cover D exactly and whose step count is a multiple of 6 --
-// no validity selects, no row clamps, one basic block per 6 steps.
-template <class L, bool kFast>
+template <class L>
+struct CnState {
+  const uint4 *d0p, *d1p;
+  const double *c0p, *c1p;
+  const float *a0p, *a1p, *r0p, *r1p;
+  float w3[3][3];   // sliding 3x3 right window; logical column j lives in w3[.][(j + 12 - sI) % 3]
+  float* pn;        // ncc plane, column of voxel A
+  uint8_t* pc;      // census bytes, column of voxel A
+  int dA;
+};
+
+template <class L, bool kClean>
+__device__ __forceinline__ void cn_block(CnState<L>& s, int steps_left, int D, const uint4& ldA, const uint4& ldB,
+                                         const f32x2 (&l3)[3][3], f32x2 lA2, double lCA, double lCB,
+                                         const int (&dmax)[4], P1Min& mn) {
+  const f32x2 nine2 = pk2(9.0f, 9.0f);
+#pragma unroll
+  for (int sI = 0; sI < 6; ++sI) {
+    if (!kClean && sI > 0 && sI >= steps_left) break;
+#define W3(r, j) s.w3[r][((j) + 12 - sI) % 3]
+    const int dA = s.dA + sI, dB = dA + 1;
+    const uint4 rd = *MSN_STEP_PTR(s.d0p, s.d1p, sI);
+    const double rC = *MSN_STEP_PTR(s.c0p, s.c1p, sI);
+    const float rA = *MSN_STEP_PTR(s.a0p, s.a1p, sI);
+    // census: Hamming distance of the packed codes (matchers.cpp:323-337)
+    int cenA = popc128(ldA, rd);
+    int cenB = popc128(ldB, rd);
+    // NCC: P exact in fp32 (< 2^24); scaling in fp64 left to right (matchers.cpp:200-201)
+    f32x2 P = pk2(0.f, 0.f);
+#pragma unroll
+    for (int r = 0; r < 3; ++r)
+#pragma unroll
+      for (int j = 0; j < 3; ++j) {
+        const float w = W3(r, j);
+        P = fma2(l3[r][j], pk2(w, w), P);
+      }
+    const float nra = -rA;
+    const f32x2 num2 = fma2(nine2, P, mul2(lA2, pk2(nra, nra)));   // 9P - A_L*A_R, exact
+    float numA, numB;
+    upk2(num2, numA, numB);
+    float nccA = ncc_scale(numA, lCA, rC);
+    float nccB = ncc_scale(numB, lCB, rC);
+    int rowA = dA, rowB = dB;
+    if (!kClean) {
+      cenA = (dA <= dmax[0]) ? cenA : 255;
+      cenB = (dB <= dmax[1]) ? cenB : 255;
+      nccA = (dA <= dmax[2]) ? nccA : kFill;
+      nccB = (dB <= dmax[3]) ? nccB : kFill;
+      rowA = min(dA, D);     // dummy steps (d >= D) park into the scratch row
+      rowB = min(dB, D);
+    }
+    s.pc[rowA * kTile] = (uint8_t)cenA;
+    s.pc[rowB * kTile + 1] = (uint8_t)cenB;
+    s.pn[rowA * kTile] = nccA;
+    s.pn[rowB * kTile + 1] = nccB;
+    mn.cenA = min(mn.cenA, cenA);
+    mn.cenB = min(mn.cenB, cenB);
+    mn.nccA = fminf(mn.nccA, nccA);
+    mn.nccB = fminf(mn.nccB, nccB);
+    // slide the window one column left: the next step's logical column 0
+    {
+      const float* q = MSN_STEP_PTR(s.r0p, s.r1p, sI);
+#pragma unroll
+      for (int r = 0; r < 3; ++r) s.w3[r][(0 + 12 - (sI + 1)) % 3] = q[r * 2 * L::capF];
+    }
+#undef W3
+  }
+}
+
+template <class L>
 __device__ __forceinline__ void p1_census_ncc(const FusedArgs& a, const unsigned char* stage, const StageGeo& sg,
                                               float* s_par, uint8_t* s_cen, const Left2& lr, const P1Ctx& c,
-                                              P1Min& mn) {
+                                              const int (&dmax)[4], P1Min& mn) {
   const int D = a.g.D;
   const RStat lsA = *reinterpret_cast<const RStat*>(&lr.statA);
   const RStat lsB = *reinterpret_cast<const RStat*>(&lr.statB);
@@ -207,95 +296,113 @@ __device__ __forceinline__ void p1_census_ncc(const FusedArgs& a, const unsigned
       l3[r][j] = add2(pk2(lr.px[r + 1][1 + j], lr.px[r + 1][2 + j]), pk2(a.neg_zero, a.neg_zero));
     }
   const f32x2 lA2 = pk2(lsA.A, lsB.A);
-  const f32x2 nine2 = pk2(9.0f, 9.0f);
 
+  CnState<L> s;
   const int cx = c.cx0;
-  const uint4* d0p = colptr<uint4>(stage + L::st_desc, L::capD, sg.pD, cx);
-  const uint4* d1p = colptr<uint4>(stage + L::st_desc, L::capD, sg.pD, cx - 1);
-  const double* c0p = colptr<double>(stage + L::st_c, L::capC, sg.pC, cx);
-  const double* c1p = colptr<double>(stage + L::st_c, L::capC, sg.pC, cx - 1);
-  const float* a0p = colptr<float>(stage + L::st_a, L::capF, sg.pF, cx);
-  const float* a1p = colptr<float>(stage + L::st_a, L::capF, sg.pF, cx - 1);
+  s.d0p = colptr<uint4>(stage + L::st_desc, L::capD, sg.pD, cx);
+  s.d1p = colptr<uint4>(stage + L::st_desc, L::capD, sg.pD, cx - 1);
+  s.c0p = colptr<double>(stage + L::st_c, L::capC, sg.pC, cx);
+  s.c1p = colptr<double>(stage + L::st_c, L::capC, sg.pC, cx - 1);
+  s.a0p = colptr<float>(stage + L::st_a, L::capF, sg.pF, cx);
+  s.a1p = colptr<float>(stage + L::st_a, L::capF, sg.pF, cx - 1);
   // pixel rows y-1..y+1 are rows 1..3 of the staged five; the window's new column at step sI is cx-sI-2
   const unsigned char* rfb = stage + L::st_rf + (size_t)2 * L::capF * 4;
-  const float* r0p = colptr<float>(rfb, L::capF, sg.pF, cx - 2);
-  const float* r1p = colptr<float>(rfb, L::capF, sg.pF, cx - 3);
-  float w3[3][3];   // sliding 3x3 right window; logical column j lives in w3[.][(j + 12 - sI) % 3]
+  s.r0p = colptr<float>(rfb, L::capF, sg.pF, cx - 2);
+  s.r1p = colptr<float>(rfb, L::capF, sg.pF, cx - 3);
+  {
+    // initial window, columns cx-1, cx, cx+1: cx-1 = (cx-3)+2 and cx+1 = (cx-3)+4 share r1p's half
+    const float* qa = s.r1p + 1;   // cx - 1
+    const float* qb = s.r0p + 1;   // cx
+    const float* qc = s.r1p + 2;   // cx + 1
 #pragma unroll
-  for (int j = 0; j < 3; ++j) {
-    const float* q = colptr<float>(rfb, L::capF, sg.pF, cx - 1 + j);
-#pragma unroll
-    for (int r = 0; r < 3; ++r) w3[r][j] = q[r * 2 * L::capF];
+    for (int r = 0; r < 3; ++r) {
+      s.w3[r][0] = qa[r * 2 * L::capF];
+      s.w3[r][1] = qb[r * 2 * L::capF];
+      s.w3[r][2] = qc[r * 2 * L::capF];
+    }
   }
-  float* pn = s_par + 2 * c.pr;              // ncc plane
-  uint8_t* pc = s_cen + 2 * c.pr;
-  int dA = c.dA0;
+  s.pn = s_par + 2 * c.pr;
+  s.pc = s_cen + 2 * c.pr;
+  s.dA = c.dA0;
 
   for (int base = 0; base < c.nsteps; base += 6) {
+    const int kind = block_kind(s.dA, c.nsteps - base, dmax[0], dmax[1], dmax[2], dmax[3]);
+    if (kind == kBlkClean) {
+      cn_block<L, true>(s, 6, D, lr.descA, lr.descB, l3, lA2, lsA.C, lsB.C, dmax, mn);
+    } else if (kind == kBlkGeneric) {
+      cn_block<L, false>(s, c.nsteps - base, D, lr.descA, lr.descB, l3, lA2, lsA.C, lsB.C, dmax, mn);
+    } else {
 #pragma unroll
-    for (int sI = 0; sI < 6; ++sI) {
-      if (!kFast && sI > 0 && base + sI >= c.nsteps) break;
-#define W3(r, j) w3[r][((j) + 12 - sI) % 3]
-      const int dB = dA + 1;
-      const uint4 rd = *MSN_STEP_PTR(d0p, d1p, sI);
-      const double rC = *MSN_STEP_PTR(c0p, c1p, sI);
-      const float rA = *MSN_STEP_PTR(a0p, a1p, sI);
-      // census: Hamming distance of the packed codes (matchers.cpp:323-337)
-      int cenA = popc128(lr.descA, rd);
-      int cenB = popc128(lr.descB, rd);
-      // NCC: P exact in fp32 (< 2^24); scaling in fp64 left to right (matchers.cpp:200-201)
-      f32x2 P = pk2(0.f, 0.f);
-#pragma unroll
-      for (int r = 0; r < 3; ++r)
-#pragma unroll
-        for (int j = 0; j < 3; ++j) {
-          const float w = W3(r, j);
-          P = fma2(l3[r][j], pk2(w, w), P);
-        }
-      const float nra = -rA;
-      const f32x2 num2 = fma2(nine2, P, mul2(lA2, pk2(nra, nra)));   // 9P - A_L*A_R, exact
-      float numA, numB;
-      upk2(num2, numA, numB);
-      float nccA = ncc_scale(numA, lsA.C, rC);
-      float nccB = ncc_scale(numB, lsB.C, rC);
-      int rowA = dA, rowB = dB;
-      if (!kFast) {
-        cenA = (dA >= 0 && dA <= c.dmaxA[0]) ? cenA : 255;
-        cenB = (dB <= c.dmaxB[0]) ? cenB : 255;
-        nccA = (dA >= 0 && dA <= c.dmaxA[1]) ? nccA : kFill;
-        nccB = (dB <= c.dmaxB[1]) ? nccB : kFill;
-        rowA = (dA >= 0 && dA < D) ? dA : D;     // dummy steps park into the scratch row
-        rowB = (dB < D) ? dB : D;
+      for (int sI = 0; sI < 6; ++sI) {
+        if (sI >= c.nsteps - base) break;
+        const int rowA = min(s.dA + sI, D), rowB = min(s.dA + sI + 1, D);
+        s.pc[rowA * kTile] = 255;
+        s.pc[rowB * kTile + 1] = 255;
+        s.pn[rowA * kTile] = kFill;
+        s.pn[rowB * kTile + 1] = kFill;
       }
-      pc[rowA * kTile] = (uint8_t)cenA;
-      pc[rowB * kTile + 1] = (uint8_t)cenB;
-      pn[rowA * kTile] = nccA;
-      pn[rowB * kTile + 1] = nccB;
-      mn.cenA = min(mn.cenA, cenA);
-      mn.nccA = fminf(mn.nccA, nccA);
-      if (!(kFast && sI == 5 && c.lastB_dummy && base + 6 >= c.nsteps)) {
-        mn.cenB = min(mn.cenB, cenB);
-        mn.nccB = fminf(mn.nccB, nccB);
-      }
-      // slide the window one column left: the next step's logical column 0
-      {
-        const float* q = MSN_STEP_PTR(r0p, r1p, sI);
-#pragma unroll
-        for (int r = 0; r < 3; ++r) w3[r][(0 + 12 - (sI + 1)) % 3] = q[r * 2 * L::capF];
-      }
-      dA += 1;
-#undef W3
     }
-    d0p -= 3; d1p -= 3; c0p -= 3; c1p -= 3; a0p -= 3; a1p -= 3; r0p -= 3; r1p -= 3;
+    s.dA += 6;
+    s.d0p -= 3; s.d1p -= 3; s.c0p -= 3; s.c1p -= 3; s.a0p -= 3; s.a1p -= 3; s.r0p -= 3; s.r1p -= 3;
   }
 }
 
 // ---- loop Z: ZSAD ---------------------------------------------------------------------------
 // 25 taps row-major, ((L - mL) - R) + mR, sequential fp32 per voxel (matchers.cpp:499-506); the
 // two voxels of the pair occupy the two halves of every packed operation.
-template <class L, bool kFast>
+template <class L>
+struct ZState {
+  const float *q0p, *q1p, *m0p, *m1p;
+  float wv[5][6];   // sliding right window, 5 logical columns + the one being loaded for the next step
+  float* pz;        // zsad plane, column of voxel A
+  int dA;
+};
+
+template <class L, bool kClean>
+__device__ __forceinline__ void z_block(ZState<L>& s, int steps_left, int D, const f32x2 (&ap)[5][5], int dmaxA,
+                                        int dmaxB, P1Min& mn) {
+#pragma unroll
+  for (int sI = 0; sI < 6; ++sI) {
+    if (!kClean && sI > 0 && sI >= steps_left) break;
+#define WV(r, j) s.wv[r][((j) + 12 - sI) % 6]
+    const int dA = s.dA + sI, dB = dA + 1;
+    // next step's new left column into the spare slot (logical column -1 of this step)
+    {
+      const float* q = MSN_STEP_PTR(s.q0p, s.q1p, sI);
+#pragma unroll
+      for (int r = 0; r < 5; ++r) WV(r, 5) = q[r * 2 * L::capF];
+    }
+    const float mR = *MSN_STEP_PTR(s.m0p, s.m1p, sI);
+    const f32x2 mR2 = pk2(mR, mR);
+    f32x2 acc = pk2(0.f, 0.f);
+#pragma unroll
+    for (int r = 0; r < 5; ++r)
+#pragma unroll
+      for (int j = 0; j < 5; ++j) {
+        const float w = WV(r, j);
+        acc = add2(acc, abs2(add2(sub2(ap[r][j], pk2(w, w)), mR2)));
+      }
+    float zA, zB;
+    upk2(acc, zA, zB);
+    int rowA = dA, rowB = dB;
+    if (!kClean) {
+      zA = (dA <= dmaxA) ? zA : kFill;
+      zB = (dB <= dmaxB) ? zB : kFill;
+      rowA = min(dA, D);
+      rowB = min(dB, D);
+    }
+    s.pz[rowA * kTile] = zA;
+    s.pz[rowB * kTile + 1] = zB;
+    mn.sadA = fminf(mn.sadA, zA);
+    mn.sadB = fminf(mn.sadB, zB);
+#undef WV
+  }
+}
+
+template <class L>
 __device__ __forceinline__ void p1_zsad(const FusedArgs& a, const unsigned char* stage, const StageGeo& sg,
-                                        float* s_par, const Left2& lr, const P1Ctx& c, P1Min& mn) {
+                                        float* s_par, const Left2& lr, const P1Ctx& c, int dmaxA, int dmaxB,
+                                        P1Min& mn) {
   const int D = a.g.D;
   const float mLA = reinterpret_cast<const RStat*>(&lr.statA)->mean;
   const float mLB = reinterpret_cast<const RStat*>(&lr.statB)->mean;
@@ -304,76 +411,55 @@ __device__ __forceinline__ void p1_zsad(const FusedArgs& a, const unsigned char*
   for (int r = 0; r < 5; ++r)
 #pragma unroll
     for (int j = 0; j < 5; ++j) ap[r][j] = pk2(__fsub_rn(lr.px[r][j], mLA), __fsub_rn(lr.px[r][j + 1], mLB));
+  ZState<L> s;
   const int cx = c.cx0;
   const unsigned char* rfb = stage + L::st_rf;
   // the column loaded at step sI for step sI+1: cx - sI - 3
-  const float* q0p = colptr<float>(rfb, L::capF, sg.pF, cx - 3);
-  const float* q1p = colptr<float>(rfb, L::capF, sg.pF, cx - 4);
-  const float* m0p = colptr<float>(stage + L::st_mean, L::capF, sg.pF, cx);
-  const float* m1p = colptr<float>(stage + L::st_mean, L::capF, sg.pF, cx - 1);
-  float wv[5][6];   // sliding right window, 5 logical columns + the one being loaded for the next step
+  s.q0p = colptr<float>(rfb, L::capF, sg.pF, cx - 3);
+  s.q1p = colptr<float>(rfb, L::capF, sg.pF, cx - 4);
+  s.m0p = colptr<float>(stage + L::st_mean, L::capF, sg.pF, cx);
+  s.m1p = colptr<float>(stage + L::st_mean, L::capF, sg.pF, cx - 1);
+  // initial window, columns cx-2 .. cx+2: (cx-4)+2, (cx-3)+2, (cx-4)+4, (cx-3)+4, (cx-4)+6
 #pragma unroll
   for (int j = 0; j < 5; ++j) {
-    const float* q = colptr<float>(rfb, L::capF, sg.pF, cx - 2 + j);
+    const float* q = (j & 1) ? s.q0p + 1 + (j >> 1) : s.q1p + 1 + (j >> 1);
 #pragma unroll
-    for (int r = 0; r < 5; ++r) wv[r][j] = q[r * 2 * L::capF];
+    for (int r = 0; r < 5; ++r) s.wv[r][j] = q[r * 2 * L::capF];
   }
-  float* pz = s_par + 2 * L::PS + 2 * c.pr;   // zsad plane
-  int dA = c.dA0;
+  s.pz = s_par + 2 * L::PS + 2 * c.pr;
+  s.dA = c.dA0;
 
   for (int base = 0; base < c.nsteps; base += 6) {
+    const int kind = block_kind(s.dA, c.nsteps - base, dmaxA, dmaxB, dmaxA, dmaxB);
+    if (kind == kBlkClean) {
+      z_block<L, true>(s, 6, D, ap, dmaxA, dmaxB, mn);
+    } else if (kind == kBlkGeneric) {
+      z_block<L, false>(s, c.nsteps - base, D, ap, dmaxA, dmaxB, mn);
+    } else {
 #pragma unroll
-    for (int sI = 0; sI < 6; ++sI) {
-      if (!kFast && sI > 0 && base + sI >= c.nsteps) break;
-#define WV(r, j) wv[r][((j) + 12 - sI) % 6]
-      const int dB = dA + 1;
-      // next step's new left column into the spare slot (logical column -1 of this step)
-      {
-        const float* q = MSN_STEP_PTR(q0p, q1p, sI);
-#pragma unroll
-        for (int r = 0; r < 5; ++r) WV(r, 5) = q[r * 2 * L::capF];
+      for (int sI = 0; sI < 6; ++sI) {
+        if (sI >= c.nsteps - base) break;
+        s.pz[min(s.dA + sI, D) * kTile] = kFill;
+        s.pz[min(s.dA + sI + 1, D) * kTile + 1] = kFill;
       }
-      const float mR = *MSN_STEP_PTR(m0p, m1p, sI);
-      const f32x2 mR2 = pk2(mR, mR);
-      f32x2 acc = pk2(0.f, 0.f);
-#pragma unroll
-      for (int r = 0; r < 5; ++r)
-#pragma unroll
-        for (int j = 0; j < 5; ++j) {
-          const float w = WV(r, j);
-          acc = add2(acc, abs2(add2(sub2(ap[r][j], pk2(w, w)), mR2)));
-        }
-      float zA, zB;
-      upk2(acc, zA, zB);
-      int rowA = dA, rowB = dB;
-      if (!kFast) {
-        zA = (dA >= 0 && dA <= c.dmaxA[2]) ? zA : kFill;
-        zB = (dB <= c.dmaxB[2]) ? zB : kFill;
-        rowA = (dA >= 0 && dA < D) ? dA : D;
-        rowB = (dB < D) ? dB : D;
-      }
-      pz[rowA * kTile] = zA;
-      pz[rowB * kTile + 1] = zB;
-      mn.sadA = fminf(mn.sadA, zA);
-      if (!(kFast && sI == 5 && c.lastB_dummy && base + 6 >= c.nsteps)) mn.sadB = fminf(mn.sadB, zB);
-      dA += 1;
-#undef WV
     }
-    q0p -= 3; q1p -= 3; m0p -= 3; m1p -= 3;
+    s.dA += 6;
+    s.q0p -= 3; s.q1p -= 3; s.m0p -= 3; s.m1p -= 3;
   }
 }
 
-// Group 0's extra step (fast path): voxel B = (odd pixel, d = 0) alone; A would be d = -1.
-// cxB: padded right column of B at d = 0.
+// Group 0's extra voxel: B = (odd pixel, d = 0) alone (its diagonal partner would be d = -1).
+// cxB: padded right column of B at d = 0.  dmaxB*: validity bounds of pixel B (cost iff 0 <= dmax).
 template <class L>
 __device__ __forceinline__ void p1_extra_b0(const unsigned char* stage, const StageGeo& sg, float* s_par,
-                                            uint8_t* s_cen, const Left2& lr, int pr, int cxB, P1Min& mn) {
+                                            uint8_t* s_cen, const Left2& lr, int pr, int cxB, int dmaxB_cen,
+                                            int dmaxB_ncc, int dmaxB_sad, P1Min& mn) {
   const RStat lsB = *reinterpret_cast<const RStat*>(&lr.statB);
   const uint4 rd = *colptr<uint4>(stage + L::st_desc, L::capD, sg.pD, cxB);
   const double rC = *colptr<double>(stage + L::st_c, L::capC, sg.pC, cxB);
   const float rA = *colptr<float>(stage + L::st_a, L::capF, sg.pF, cxB);
   const float mR = *colptr<float>(stage + L::st_mean, L::capF, sg.pF, cxB);
-  const int cen = popc128(lr.descB, rd);
+  int cen = popc128(lr.descB, rd);
   float P = 0.f, z = 0.f;
 #pragma unroll
   for (int r = 0; r < 5; ++r)
@@ -384,7 +470,10 @@ __device__ __forceinline__ void p1_extra_b0(const unsigned char* stage, const St
       z = __fadd_rn(z, fabsf(__fadd_rn(__fsub_rn(__fsub_rn(lr.px[r][j + 1], lsB.mean), w), mR)));
     }
   const float num = __fmaf_rn(9.0f, P, -__fmul_rn(lsB.A, rA));
-  const float ncc = ncc_scale(num, lsB.C, rC);
+  float ncc = ncc_scale(num, lsB.C, rC);
+  cen = (dmaxB_cen >= 0) ? cen : 255;
+  ncc = (dmaxB_ncc >= 0) ? ncc : kFill;
+  z = (dmaxB_sad >= 0) ? z : kFill;
   s_cen[2 * pr + 1] = (uint8_t)cen;
   s_par[2 * pr + 1] = ncc;
   s_par[2 * L::PS + 2 * pr + 1] = z;
@@ -429,8 +518,8 @@ __device__ __forceinline__ void sob_finish(const FusedArgs& a, const TileId& t, 
 // ---- back half ------------------------------------------------------------------------------
 // Channel 0 = clip(census, 0, 120) / 120 as a TRUE division (cbmv_generator.py:283): q = k*r refined
 // by two FMAs is the correctly rounded quotient for every k in 0..120 (checked exhaustively in
-// tests/test_host_math.py); a parked 255 (no cost) clips to 120 -> 1.0.  No table: the kernel is
-// bound by shared-memory wavefronts, not by arithmetic.
+// tests/test_host_math.py); a parked 255 (no cost) clips to 120 -> 1.0.  No table: shared-memory
+// wavefronts are the scarcer resource here.
 __device__ __forceinline__ float census_ch0(unsigned k) {
   const float kf = (float)min(k, 120u);
   const float r = 1.0f / 120.0f;
@@ -466,13 +555,23 @@ __device__ __forceinline__ void store_quads(float* o, size_t chan, int nlive, co
   }
 }
 
-// Channels 0-3 (cbmv_generator.py:283-287) for thread = (pixel quad q4, disparities d0, d0+16, ... < d1)
+// Pass E for thread = (pixel quad q4, disparities dl, dl+32, ...): channels 0-3 normalised
+// (cbmv_generator.py:283-287) and stored as 128-bit row segments; every AML exponential
+// exp(-(c-m)^2/sigma) evaluated ONCE -- the three float planes are overwritten in place, the census
+// exponentials go to their own plane s_ce (the dead staging area).
 template <bool kVec>
-__device__ __forceinline__ void store_ch03(const float* s_par, const uint8_t* s_cen, int PS, int q4, int d0, int d1,
-                                           float* orow, size_t plane, size_t chan, int nlive) {
+__device__ __forceinline__ void pass_e(float* s_par, const uint8_t* s_cen, float* s_ce, const float* s_min, int PS,
+                                       int q4, int dl, int D, float* orow, size_t plane, size_t chan, int nlive,
+                                       float k0, float k1, float k2) {
+  const float4 m0 = *reinterpret_cast<const float4*>(s_min + q4);
+  const float4 m1 = *reinterpret_cast<const float4*>(s_min + kTile + q4);
+  const float4 m2 = *reinterpret_cast<const float4*>(s_min + 2 * kTile + q4);
+  const float4 m3 = *reinterpret_cast<const float4*>(s_min + 3 * kTile + q4);
+  const int mcx = (m0.x == kFill) ? 0 : (int)m0.x, mcy = (m0.y == kFill) ? 0 : (int)m0.y;
+  const int mcz = (m0.z == kFill) ? 0 : (int)m0.z, mcw = (m0.w == kFill) ? 0 : (int)m0.w;
 #pragma unroll 1
-  for (int d = d0; d < d1; d += 16) {
-    const float* e0 = s_par + d * kTile + q4;
+  for (int d = dl; d < D; d += 32) {
+    float* e0 = s_par + d * kTile + q4;
     const uchar4 cb = *reinterpret_cast<const uchar4*>(s_cen + d * kTile + q4);
     const float4 v1 = *reinterpret_cast<const float4*>(e0);
     const float4 v2 = *reinterpret_cast<const float4*>(e0 + PS);
@@ -485,47 +584,72 @@ __device__ __forceinline__ void store_ch03(const float* s_par, const uint8_t* s_
     const float4 c3 = make_float4(normalise_cost(v3.x, 3), normalise_cost(v3.y, 3), normalise_cost(v3.z, 3),
                                   normalise_cost(v3.w, 3));
     store_quads<kVec>(orow + (size_t)d * plane, chan, nlive, c0, c1, c2, c3);
+    *reinterpret_cast<float4*>(s_ce + d * kTile + q4) =
+        make_float4(census_e(cb.x, mcx, k0), census_e(cb.y, mcy, k0), census_e(cb.z, mcz, k0), census_e(cb.w, mcw, k0));
+    *reinterpret_cast<float4*>(e0) =
+        make_float4(aml_e(v1.x, m1.x, k1), aml_e(v1.y, m1.y, k1), aml_e(v1.z, m1.z, k1), aml_e(v1.w, m1.w, k1));
+    *reinterpret_cast<float4*>(e0 + PS) =
+        make_float4(aml_e(v2.x, m2.x, k2), aml_e(v2.y, m2.y, k2), aml_e(v2.z, m2.z, k2), aml_e(v2.w, m2.w, k2));
+    *reinterpret_cast<float4*>(e0 + 2 * PS) =
+        make_float4(aml_e(v3.x, m3.x, k2), aml_e(v3.y, m3.y, k2), aml_e(v3.z, m3.z, k2), aml_e(v3.w, m3.w, k2));
   }
 }
 
-// Channels 4-7 = exp(-(c-m)^2/sigma) / den for thread = (pixel quad q4, disparities dl, dl+32, ...),
-// exponentials recomputed from the parked costs, 128-bit row segments.
+// Pass N: channels 4-7 = e * (1/den), 128-bit row segments.
 template <bool kVec>
-__device__ __forceinline__ void phase3_quads(const float* s_par, const uint8_t* s_cen, const float* s_min,
-                                             const float* s_inv, int PS, int q4, int dl, int D, float* arow,
-                                             size_t plane, size_t chan, int nlive, float k0, float k1, float k2) {
-  const float4 m_cen4 = *reinterpret_cast<const float4*>(s_min + q4);
-  const float4 m1 = *reinterpret_cast<const float4*>(s_min + kTile + q4);
-  const float4 m2 = *reinterpret_cast<const float4*>(s_min + 2 * kTile + q4);
-  const float4 m3 = *reinterpret_cast<const float4*>(s_min + 3 * kTile + q4);
+__device__ __forceinline__ void pass_n(const float* s_par, const float* s_ce, const float* s_inv, int PS, int q4,
+                                       int dl, int D, float* arow, size_t plane, size_t chan, int nlive) {
   const float4 i0 = *reinterpret_cast<const float4*>(s_inv + q4);
   const float4 i1 = *reinterpret_cast<const float4*>(s_inv + kTile + q4);
   const float4 i2 = *reinterpret_cast<const float4*>(s_inv + 2 * kTile + q4);
   const float4 i3 = *reinterpret_cast<const float4*>(s_inv + 3 * kTile + q4);
-  const int mcx = (m_cen4.x == kFill) ? 0 : (int)m_cen4.x, mcy = (m_cen4.y == kFill) ? 0 : (int)m_cen4.y;
-  const int mcz = (m_cen4.z == kFill) ? 0 : (int)m_cen4.z, mcw = (m_cen4.w == kFill) ? 0 : (int)m_cen4.w;
-#pragma unroll 1
+#pragma unroll 2
   for (int d = dl; d < D; d += 32) {
     const float* e0 = s_par + d * kTile + q4;
-    const uchar4 cb = *reinterpret_cast<const uchar4*>(s_cen + d * kTile + q4);
+    const float4 v0 = *reinterpret_cast<const float4*>(s_ce + d * kTile + q4);
     const float4 v1 = *reinterpret_cast<const float4*>(e0);
     const float4 v2 = *reinterpret_cast<const float4*>(e0 + PS);
     const float4 v3 = *reinterpret_cast<const float4*>(e0 + 2 * PS);
-    const float4 a0 = make_float4(census_e(cb.x, mcx, k0) * i0.x, census_e(cb.y, mcy, k0) * i0.y,
-                                  census_e(cb.z, mcz, k0) * i0.z, census_e(cb.w, mcw, k0) * i0.w);
-    const float4 a1 = make_float4(aml_e(v1.x, m1.x, k1) * i1.x, aml_e(v1.y, m1.y, k1) * i1.y,
-                                  aml_e(v1.z, m1.z, k1) * i1.z, aml_e(v1.w, m1.w, k1) * i1.w);
-    const float4 a2 = make_float4(aml_e(v2.x, m2.x, k2) * i2.x, aml_e(v2.y, m2.y, k2) * i2.y,
-                                  aml_e(v2.z, m2.z, k2) * i2.z, aml_e(v2.w, m2.w, k2) * i2.w);
-    const float4 a3 = make_float4(aml_e(v3.x, m3.x, k2) * i3.x, aml_e(v3.y, m3.y, k2) * i3.y,
-                                  aml_e(v3.z, m3.z, k2) * i3.z, aml_e(v3.w, m3.w, k2) * i3.w);
+    const float4 a0 = make_float4(v0.x * i0.x, v0.y * i0.y, v0.z * i0.z, v0.w * i0.w);
+    const float4 a1 = make_float4(v1.x * i1.x, v1.y * i1.y, v1.z * i1.z, v1.w * i1.w);
+    const float4 a2 = make_float4(v2.x * i2.x, v2.y * i2.y, v2.z * i2.z, v2.w * i2.w);
+    const float4 a3 = make_float4(v3.x * i3.x, v3.y * i3.y, v3.z * i3.z, v3.w * i3.w);
     store_quads<kVec>(arow + (size_t)d * plane, chan, nlive, a0, a1, a2, a3);
   }
 }
 
+// Pass S for one thread = (pixel, matcher): den = sum over d of e, added SEQUENTIALLY in d order as the
+// reference does (featextract.cpp:444-447; a tree sum is measurably outside the 2e-6 bound).  Only
+// loads and adds; the loads run a batch of 16 ahead of the dependent adds.
+__device__ __forceinline__ float chain_sum(const float* e, int D) {
+  constexpr int B = 16;
+  float den = 0.f;
+  float bufA[B], bufB[B];
+  const int nb = D / (2 * B);   // double batches
+  if (nb > 0) {
+#pragma unroll
+    for (int j = 0; j < B; ++j) bufA[j] = e[j * kTile];
+  }
+  for (int b = 0; b < nb; ++b) {
+    const float* eb = e + (size_t)(2 * b + 1) * B * kTile;
+#pragma unroll
+    for (int j = 0; j < B; ++j) bufB[j] = eb[j * kTile];
+#pragma unroll
+    for (int j = 0; j < B; ++j) den = __fadd_rn(den, bufA[j]);
+    if (b + 1 < nb) {
+#pragma unroll
+      for (int j = 0; j < B; ++j) bufA[j] = eb[(B + j) * kTile];
+    }
+#pragma unroll
+    for (int j = 0; j < B; ++j) den = __fadd_rn(den, bufB[j]);
+  }
+  for (int d = nb * 2 * B; d < D; ++d) den = __fadd_rn(den, e[d * kTile]);
+  return den;
+}
+
 template <class L>
-__device__ __forceinline__ void tile_back_half(const FusedArgs& a, const TileId& t, int tid, const float* s_par,
-                                               const uint8_t* s_cen, const float* s_red, float* s_min,
+__device__ __forceinline__ void tile_back_half(const FusedArgs& a, const TileId& t, int tid, float* s_par,
+                                               const uint8_t* s_cen, float* s_ce, const float* s_red, float* s_min,
                                                float* s_inv) {
   constexpr int PS = L::PS;
   const FusedGeom& g = a.g;
@@ -538,52 +662,27 @@ __device__ __forceinline__ void tile_back_half(const FusedArgs& a, const TileId&
     for (int gq = 0; gq < kG2; ++gq) v = fminf(v, s_red[gq * 4 * kTile + tid]);
     s_min[tid] = v;
   }
-  __syncthreads();
+  __syncthreads();        // s_min visible; staging area and s_red are dead from here on (-> s_ce)
   const int warp = tid >> 5, lane = tid & 31;
   const int q4 = (tid & 7) * 4;
+  const int dl = tid >> 3;
   // 128-bit stores need 16-byte aligned rows
   const bool vec_ok = ((g.w & 3) == 0) && ((reinterpret_cast<uintptr_t>(a.out) & 15) == 0);
   float* orow = a.out + (size_t)t.n * a.out_channels * chan + (size_t)t.y * g.w + (t.x0 + q4);
   const int nlive = min(4, g.w - (t.x0 + q4));  // live pixels of this quad (<= 0: none)
   const bool vec = vec_ok && nlive == 4;
+  if (vec) pass_e<true>(s_par, s_cen, s_ce, s_min, PS, q4, dl, D, orow, plane, chan, nlive, a.k_cen, a.k_ncc, a.k_sad);
+  else pass_e<false>(s_par, s_cen, s_ce, s_min, PS, q4, dl, D, orow, plane, chan, nlive, a.k_cen, a.k_ncc, a.k_sad);
+  __syncthreads();
   if (warp < 4) {
-    // the reference's sequential fp32 sum over d (featextract.cpp:444-447), exponentials on the fly
     const float mm = s_min[warp * kTile + lane];
-    float den = 0.f;
-    const int Dfull = D & ~7;   // groups of 8 without guards, then a guarded tail
-    if (warp == 0) {
-      const int mc = (mm == kFill) ? 0 : (int)mm;
-      const uint8_t* c = s_cen + lane;
-      for (int d0 = 0; d0 < Dfull; d0 += 8, c += 8 * kTile) {
-        float ev[8];
-#pragma unroll
-        for (int j = 0; j < 8; ++j) ev[j] = census_e(c[j * kTile], mc, a.k_cen);
-#pragma unroll
-        for (int j = 0; j < 8; ++j) den = __fadd_rn(den, ev[j]);
-      }
-      for (int d = Dfull; d < D; ++d, c += kTile) den = __fadd_rn(den, census_e(c[0], mc, a.k_cen));
-    } else {
-      const float kq = (warp == 1) ? a.k_ncc : a.k_sad;
-      const float* e = s_par + (warp - 1) * PS + lane;
-      for (int d0 = 0; d0 < Dfull; d0 += 8, e += 8 * kTile) {
-        float ev[8];
-#pragma unroll
-        for (int j = 0; j < 8; ++j) ev[j] = aml_e(e[j * kTile], mm, kq);
-#pragma unroll
-        for (int j = 0; j < 8; ++j) den = __fadd_rn(den, ev[j]);
-      }
-      for (int d = Dfull; d < D; ++d, e += kTile) den = __fadd_rn(den, aml_e(e[0], mm, kq));
-    }
+    const float* e = (warp == 0 ? s_ce : s_par + (warp - 1) * PS) + lane;
+    const float den = chain_sum(e, D);
     s_inv[warp * kTile + lane] = (mm == kFill) ? 0.f : 1.0f / den;
-  } else {
-    // channels 0-3: thread = (pixel quad, d), 16 disparities per sweep of the four warps
-    if (vec) store_ch03<true>(s_par, s_cen, PS, q4, (tid >> 3) - 16, D, orow, plane, chan, nlive);
-    else store_ch03<false>(s_par, s_cen, PS, q4, (tid >> 3) - 16, D, orow, plane, chan, nlive);
   }
   __syncthreads();
-  const int dl = tid >> 3;
-  if (vec) phase3_quads<true>(s_par, s_cen, s_min, s_inv, PS, q4, dl, D, orow + 4 * chan, plane, chan, nlive, a.k_cen, a.k_ncc, a.k_sad);
-  else phase3_quads<false>(s_par, s_cen, s_min, s_inv, PS, q4, dl, D, orow + 4 * chan, plane, chan, nlive, a.k_cen, a.k_ncc, a.k_sad);
+  if (vec) pass_n<true>(s_par, s_ce, s_inv, PS, q4, dl, D, orow + 4 * chan, plane, chan, nlive);
+  else pass_n<false>(s_par, s_ce, s_inv, PS, q4, dl, D, orow + 4 * chan, plane, chan, nlive);
 }
 
 // Back half of a tile for DISPARITY-SLAB SHARDING (phase A of slab.cu): the AML
