@@ -208,6 +208,7 @@ struct FusedArgs {
   float neg_zero;       // -0.0f (x + -0.0f == x exactly): an operand the compiler cannot fold
   int DC;               // disparity steps per d-group
   int tiles_x;
+  int xflags;           // experiment switches (MSNETS_X)
 };
 
 __device__ __forceinline__ void cp_async4(void* smem_dst, const void* gmem_src) {
@@ -383,9 +384,10 @@ ms_fused_kernel(const FusedArgs a, const __grid_constant__ CUtensorMap sad_map) 
   P1Min mn;
   mn.cenA = 255; mn.cenB = 255;
   mn.nccA = kFill; mn.nccB = kFill; mn.sadA = kFill; mn.sadB = kFill;
-  if (grp == 0) p1_extra_b0<L>(smem_raw, sg, s_par, s_cen, lr, c.pr, c.cx0 + 1, dmaxCN[1], dmaxCN[3], dmaxZB, mn);
-  p1_census_ncc<L>(a, smem_raw, sg, s_par, s_cen, lr, c, dmaxCN, mn);
+  if (grp == 0)
+    p1_extra_b0<L>(a, t, smem_raw, sg, s_par, s_cen, lr, c.pr, c.cx0 + 1, dmaxCN[1], dmaxCN[3], dmaxZB, mn);
   p1_zsad<L>(a, smem_raw, sg, s_par, lr, c, dmaxZA, dmaxZB, mn);
+  p1_census_ncc<L>(a, t, smem_raw, sg, s_par, s_cen, c, dmaxCN, mn);
   {
     float* r0 = s_red + grp * 4 * kTile + 2 * c.pr;
     r0[0] = (mn.cenA == 255) ? kFill : (float)mn.cenA;
@@ -403,6 +405,7 @@ ms_fused_kernel(const FusedArgs a, const __grid_constant__ CUtensorMap sad_map) 
   }
   __syncthreads();
   if (kSlabA) tile_slab_a<L>(a, t, tid, s_par, s_cen, s_red);
+  else if (a.xflags & 2) tile_back_half_otf<L>(a, t, tid, s_par, s_cen, s_red, s_min, s_inv);
   else tile_back_half<L>(a, t, tid, s_par, s_cen, reinterpret_cast<float*>(smem_raw + L::off_cene), s_red, s_min, s_inv);
 }
 
@@ -590,6 +593,7 @@ int launch_ms_fused(const uint8_t* d_left, const uint8_t* d_right, int N, int H,
   a.k_ncc = aml_scale(p->ncc_sigma);
   a.k_sad = aml_scale(p->sad_sigma);
   a.neg_zero = -0.0f;
+  { const char* e = getenv("MSNETS_X"); a.xflags = e ? atoi(e) : 0; }
   a.tiles_x = (g.w + kTile - 1) / kTile;
   a.DC = (g.D + kG2 - 1) / kG2;
   const long long tiles = (long long)N * g.h * a.tiles_x;

@@ -21,9 +21,10 @@
 //             prep kernel writes them that way and the TMA copies fetch the two halves), so at any
 //             step the 16 lanes of a d-group read 16 consecutive words: conflict-free.
 //             Two loops so that neither outgrows the 128-register budget of 2 CTAs/SM:
-//               loop CN  census (xor + popc) and NCC (9 FFMA2 of exact integers, fp64 scaling)
 //               loop Z   ZSAD over a register-resident right window that slides one column per
 //                        step (6 physical columns: the next column loads while this one computes)
+//               loop CN  census (xor + popc) and NCC (9 FFMA2 of exact integers, fp64 scaling),
+//                        six steps side by side for instruction-level parallelism
 //             Raw costs are parked in shared memory [d][32] (ncc, zsad floats; census byte); the
 //             tile's SAD-of-Sobel costs arrive by TMA straight into their parking plane.
 //             A thread walks its disparities in blocks of 6 steps; a block in which every voxel has
@@ -143,8 +144,7 @@ __device__ __forceinline__ const T* colptr(const unsigned char* base, int cap, i
 
 // ---- left-image data of a pixel pair: straight from global memory (before the staging wait) ---
 struct Left2 {
-  uint4 descA, descB;
-  uint4 statA, statB;   // RStat bits
+  float meanA, meanB;   // ZSAD window means
   float px[5][6];       // rows y-2..y+2, columns xA-2 .. xA+3
 };
 __device__ __forceinline__ void load_left2(const FusedArgs& a, const TileId& t, int pr, Left2& lr) {
@@ -152,12 +152,9 @@ __device__ __forceinline__ void load_left2(const FusedArgs& a, const TileId& t, 
   const int Yp = t.y + g.bh + kPadT;
   const int Xp = t.x0 + 2 * pr + g.bwl + g.padL;
   const size_t img_off = (size_t)t.n * g.img_px();
-  const uint4* dp = a.descL + img_off + (size_t)Yp * g.Wp + Xp;
-  const uint4* sp = reinterpret_cast<const uint4*>(a.statL + img_off + (size_t)Yp * g.Wp + Xp);
-  lr.descA = __ldg(dp);
-  lr.descB = __ldg(dp + 1);
-  lr.statA = __ldg(sp);
-  lr.statB = __ldg(sp + 1);
+  const RStat* sp = a.statL + img_off + (size_t)Yp * g.Wp + Xp;
+  lr.meanA = __ldg(&sp[0].mean);
+  lr.meanB = __ldg(&sp[1].mean);
   const float* gf = a.fL + img_off + (size_t)(Yp - 2) * g.Wp + (Xp - 2);
 #pragma unroll
   for (int r = 0; r < 5; ++r) {
@@ -195,7 +192,7 @@ __device__ __forceinline__ float ncc_scale(float num, double cl, double cr) {
 #define MSN_STEP_PTR(p0, p1, sI) (((sI) & 1) ? (p1) - ((sI) >> 1) : (p0) - ((sI) >> 1))
 
 // A thread walks its disparities in BLOCKS of 6 steps (the period of the register-resident sliding
-// windows).  Costs exist for d <= dmax (a per-pixel bound: the window must fit left of x - d), so a
+// window).  Costs exist for d <= dmax (a per-pixel bound: the window must fit left of x - d), so a
 // block is one of: all 12 voxels have costs -> the clean body (no selects, one basic block); none has
 // (monotone in d: nothing after it has either) -> only fill is parked; mixed / partial -> the generic
 // body with validity selects.  The choice is made per WARP (ballot), so there is no divergence.
@@ -207,144 +204,6 @@ __device__ __forceinline__ int block_kind(int dA, int steps_left, int dmaxA_tigh
   if (__all_sync(0xffffffffu, clean)) return kBlkClean;
   if (__all_sync(0xffffffffu, none)) return kBlkFill;
   return kBlkGeneric;
-}
-
-// ---- loop CN: census + NCC ------------------------------------------------------------------
-template <class L>
-struct CnState {
-  const uint4 *d0p, *d1p;
-  const double *c0p, *c1p;
-  const float *a0p, *a1p, *r0p, *r1p;
-  float w3[3][3];   // sliding 3x3 right window; logical column j lives in w3[.][(j + 12 - sI) % 3]
-  float* pn;        // ncc plane, column of voxel A
-  uint8_t* pc;      // census bytes, column of voxel A
-  int dA;
-};
-
-template <class L, bool kClean>
-__device__ __forceinline__ void cn_block(CnState<L>& s, int steps_left, int D, const uint4& ldA, const uint4& ldB,
-                                         const f32x2 (&l3)[3][3], f32x2 lA2, double lCA, double lCB,
-                                         const int (&dmax)[4], P1Min& mn) {
-  const f32x2 nine2 = pk2(9.0f, 9.0f);
-#pragma unroll
-  for (int sI = 0; sI < 6; ++sI) {
-    if (!kClean && sI > 0 && sI >= steps_left) break;
-#define W3(r, j) s.w3[r][((j) + 12 - sI) % 3]
-    const int dA = s.dA + sI, dB = dA + 1;
-    const uint4 rd = *MSN_STEP_PTR(s.d0p, s.d1p, sI);
-    const double rC = *MSN_STEP_PTR(s.c0p, s.c1p, sI);
-    const float rA = *MSN_STEP_PTR(s.a0p, s.a1p, sI);
-    // census: Hamming distance of the packed codes (matchers.cpp:323-337)
-    int cenA = popc128(ldA, rd);
-    int cenB = popc128(ldB, rd);
-    // NCC: P exact in fp32 (< 2^24); scaling in fp64 left to right (matchers.cpp:200-201)
-    f32x2 P = pk2(0.f, 0.f);
-#pragma unroll
-    for (int r = 0; r < 3; ++r)
-#pragma unroll
-      for (int j = 0; j < 3; ++j) {
-        const float w = W3(r, j);
-        P = fma2(l3[r][j], pk2(w, w), P);
-      }
-    const float nra = -rA;
-    const f32x2 num2 = fma2(nine2, P, mul2(lA2, pk2(nra, nra)));   // 9P - A_L*A_R, exact
-    float numA, numB;
-    upk2(num2, numA, numB);
-    float nccA = ncc_scale(numA, lCA, rC);
-    float nccB = ncc_scale(numB, lCB, rC);
-    int rowA = dA, rowB = dB;
-    if (!kClean) {
-      cenA = (dA <= dmax[0]) ? cenA : 255;
-      cenB = (dB <= dmax[1]) ? cenB : 255;
-      nccA = (dA <= dmax[2]) ? nccA : kFill;
-      nccB = (dB <= dmax[3]) ? nccB : kFill;
-      rowA = min(dA, D);     // dummy steps (d >= D) park into the scratch row
-      rowB = min(dB, D);
-    }
-    s.pc[rowA * kTile] = (uint8_t)cenA;
-    s.pc[rowB * kTile + 1] = (uint8_t)cenB;
-    s.pn[rowA * kTile] = nccA;
-    s.pn[rowB * kTile + 1] = nccB;
-    mn.cenA = min(mn.cenA, cenA);
-    mn.cenB = min(mn.cenB, cenB);
-    mn.nccA = fminf(mn.nccA, nccA);
-    mn.nccB = fminf(mn.nccB, nccB);
-    // slide the window one column left: the next step's logical column 0
-    {
-      const float* q = MSN_STEP_PTR(s.r0p, s.r1p, sI);
-#pragma unroll
-      for (int r = 0; r < 3; ++r) s.w3[r][(0 + 12 - (sI + 1)) % 3] = q[r * 2 * L::capF];
-    }
-#undef W3
-  }
-}
-
-template <class L>
-__device__ __forceinline__ void p1_census_ncc(const FusedArgs& a, const unsigned char* stage, const StageGeo& sg,
-                                              float* s_par, uint8_t* s_cen, const Left2& lr, const P1Ctx& c,
-                                              const int (&dmax)[4], P1Min& mn) {
-  const int D = a.g.D;
-  const RStat lsA = *reinterpret_cast<const RStat*>(&lr.statA);
-  const RStat lsB = *reinterpret_cast<const RStat*>(&lr.statB);
-  f32x2 l3[3][3];   // (A, B) left pixels of the 3x3 NCC windows
-#pragma unroll
-  for (int r = 0; r < 3; ++r)
-#pragma unroll
-    for (int j = 0; j < 3; ++j) {
-      // + (-0.0) is exact; the run-time operand keeps each pair in registers of its own (ptxas would
-      // otherwise rebuild the overlapping pairs from the left window with MOVs at every step)
-      l3[r][j] = add2(pk2(lr.px[r + 1][1 + j], lr.px[r + 1][2 + j]), pk2(a.neg_zero, a.neg_zero));
-    }
-  const f32x2 lA2 = pk2(lsA.A, lsB.A);
-
-  CnState<L> s;
-  const int cx = c.cx0;
-  s.d0p = colptr<uint4>(stage + L::st_desc, L::capD, sg.pD, cx);
-  s.d1p = colptr<uint4>(stage + L::st_desc, L::capD, sg.pD, cx - 1);
-  s.c0p = colptr<double>(stage + L::st_c, L::capC, sg.pC, cx);
-  s.c1p = colptr<double>(stage + L::st_c, L::capC, sg.pC, cx - 1);
-  s.a0p = colptr<float>(stage + L::st_a, L::capF, sg.pF, cx);
-  s.a1p = colptr<float>(stage + L::st_a, L::capF, sg.pF, cx - 1);
-  // pixel rows y-1..y+1 are rows 1..3 of the staged five; the window's new column at step sI is cx-sI-2
-  const unsigned char* rfb = stage + L::st_rf + (size_t)2 * L::capF * 4;
-  s.r0p = colptr<float>(rfb, L::capF, sg.pF, cx - 2);
-  s.r1p = colptr<float>(rfb, L::capF, sg.pF, cx - 3);
-  {
-    // initial window, columns cx-1, cx, cx+1: cx-1 = (cx-3)+2 and cx+1 = (cx-3)+4 share r1p's half
-    const float* qa = s.r1p + 1;   // cx - 1
-    const float* qb = s.r0p + 1;   // cx
-    const float* qc = s.r1p + 2;   // cx + 1
-#pragma unroll
-    for (int r = 0; r < 3; ++r) {
-      s.w3[r][0] = qa[r * 2 * L::capF];
-      s.w3[r][1] = qb[r * 2 * L::capF];
-      s.w3[r][2] = qc[r * 2 * L::capF];
-    }
-  }
-  s.pn = s_par + 2 * c.pr;
-  s.pc = s_cen + 2 * c.pr;
-  s.dA = c.dA0;
-
-  for (int base = 0; base < c.nsteps; base += 6) {
-    const int kind = block_kind(s.dA, c.nsteps - base, dmax[0], dmax[1], dmax[2], dmax[3]);
-    if (kind == kBlkClean) {
-      cn_block<L, true>(s, 6, D, lr.descA, lr.descB, l3, lA2, lsA.C, lsB.C, dmax, mn);
-    } else if (kind == kBlkGeneric) {
-      cn_block<L, false>(s, c.nsteps - base, D, lr.descA, lr.descB, l3, lA2, lsA.C, lsB.C, dmax, mn);
-    } else {
-#pragma unroll
-      for (int sI = 0; sI < 6; ++sI) {
-        if (sI >= c.nsteps - base) break;
-        const int rowA = min(s.dA + sI, D), rowB = min(s.dA + sI + 1, D);
-        s.pc[rowA * kTile] = 255;
-        s.pc[rowB * kTile + 1] = 255;
-        s.pn[rowA * kTile] = kFill;
-        s.pn[rowB * kTile + 1] = kFill;
-      }
-    }
-    s.dA += 6;
-    s.d0p -= 3; s.d1p -= 3; s.c0p -= 3; s.c1p -= 3; s.a0p -= 3; s.a1p -= 3; s.r0p -= 3; s.r1p -= 3;
-  }
 }
 
 // ---- loop Z: ZSAD ---------------------------------------------------------------------------
@@ -388,7 +247,7 @@ __device__ __forceinline__ void z_block(ZState<L>& s, int steps_left, int D, con
     if (!kClean) {
       zA = (dA <= dmaxA) ? zA : kFill;
       zB = (dB <= dmaxB) ? zB : kFill;
-      rowA = min(dA, D);
+      rowA = min(dA, D);     // dummy steps (d >= D) park into the scratch row
       rowB = min(dB, D);
     }
     s.pz[rowA * kTile] = zA;
@@ -404,13 +263,12 @@ __device__ __forceinline__ void p1_zsad(const FusedArgs& a, const unsigned char*
                                         float* s_par, const Left2& lr, const P1Ctx& c, int dmaxA, int dmaxB,
                                         P1Min& mn) {
   const int D = a.g.D;
-  const float mLA = reinterpret_cast<const RStat*>(&lr.statA)->mean;
-  const float mLB = reinterpret_cast<const RStat*>(&lr.statB)->mean;
   f32x2 ap[5][5];   // (L_A[tap] - mL_A, L_B[tap] - mL_B), hoisted over all d
 #pragma unroll
   for (int r = 0; r < 5; ++r)
 #pragma unroll
-    for (int j = 0; j < 5; ++j) ap[r][j] = pk2(__fsub_rn(lr.px[r][j], mLA), __fsub_rn(lr.px[r][j + 1], mLB));
+    for (int j = 0; j < 5; ++j)
+      ap[r][j] = pk2(__fsub_rn(lr.px[r][j], lr.meanA), __fsub_rn(lr.px[r][j + 1], lr.meanB));
   ZState<L> s;
   const int cx = c.cx0;
   const unsigned char* rfb = stage + L::st_rf;
@@ -448,18 +306,157 @@ __device__ __forceinline__ void p1_zsad(const FusedArgs& a, const unsigned char*
   }
 }
 
+// ---- loop CN: census + NCC ------------------------------------------------------------------
+// Per voxel NCC is one long dependent chain (9 products -> fp64 scaling -> fp32) and census a burst
+// of XU work, so a block evaluates its six steps side by side: all right-image data of the block is
+// loaded up front (8 window columns x 3 rows, 6 codes, 6 A, 6 C; no state carried between blocks)
+// and the six steps are independent instruction streams for the scheduler to interleave.
+// dmax: census A, census B, ncc A, ncc B
+template <class L, bool kClean>
+__device__ __forceinline__ void cn_block(const unsigned char* stage, const StageGeo& sg, int cx, int dA0,
+                                         int steps_left, int D, const uint4& ldA, const uint4& ldB,
+                                         const f32x2 (&l3)[3][3], f32x2 lA2, double lCA, double lCB,
+                                         const int (&dmax)[4], float* pn, uint8_t* pc, P1Min& mn) {
+  // columns cx-6 .. cx+1 of pixel rows y-1 .. y+1 (rows 1..3 of the staged five)
+  const unsigned char* rfb = stage + L::st_rf + (size_t)2 * L::capF * 4;
+  const float* e0 = colptr<float>(rfb, L::capF, sg.pF, cx - 6);   // cx-6, cx-4, cx-2, cx
+  const float* e1 = colptr<float>(rfb, L::capF, sg.pF, cx - 5);   // cx-5, cx-3, cx-1, cx+1
+  float w[3][8];
+#pragma unroll
+  for (int r = 0; r < 3; ++r)
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      w[r][2 * k] = e0[r * 2 * L::capF + k];
+      w[r][2 * k + 1] = e1[r * 2 * L::capF + k];
+    }
+  const float* a0p = colptr<float>(stage + L::st_a, L::capF, sg.pF, cx);
+  const float* a1p = colptr<float>(stage + L::st_a, L::capF, sg.pF, cx - 1);
+  const double* c0p = colptr<double>(stage + L::st_c, L::capC, sg.pC, cx);
+  const double* c1p = colptr<double>(stage + L::st_c, L::capC, sg.pC, cx - 1);
+  const uint4* d0p = colptr<uint4>(stage + L::st_desc, L::capD, sg.pD, cx);
+  const uint4* d1p = colptr<uint4>(stage + L::st_desc, L::capD, sg.pD, cx - 1);
+  const f32x2 nine2 = pk2(9.0f, 9.0f);
+#pragma unroll
+  for (int sI = 0; sI < 6; ++sI) {
+    if (!kClean && sI > 0 && sI >= steps_left) break;
+    const int dA = dA0 + sI, dB = dA + 1;
+    const uint4 rd = *MSN_STEP_PTR(d0p, d1p, sI);
+    const double rC = *MSN_STEP_PTR(c0p, c1p, sI);
+    const float rA = *MSN_STEP_PTR(a0p, a1p, sI);
+    // census: Hamming distance of the packed codes (matchers.cpp:323-337)
+    int cenA = popc128(ldA, rd);
+    int cenB = popc128(ldB, rd);
+    // NCC: P exact in fp32 (< 2^24); scaling in fp64 left to right (matchers.cpp:200-201)
+    f32x2 P = pk2(0.f, 0.f);
+#pragma unroll
+    for (int r = 0; r < 3; ++r)
+#pragma unroll
+      for (int j = 0; j < 3; ++j) {
+        const float wj = w[r][5 - sI + j];   // column cx - sI - 1 + j
+        P = fma2(l3[r][j], pk2(wj, wj), P);
+      }
+    const float nra = -rA;
+    const f32x2 num2 = fma2(nine2, P, mul2(lA2, pk2(nra, nra)));   // 9P - A_L*A_R, exact
+    float numA, numB;
+    upk2(num2, numA, numB);
+    float nccA = ncc_scale(numA, lCA, rC);
+    float nccB = ncc_scale(numB, lCB, rC);
+    int rowA = dA, rowB = dB;
+    if (!kClean) {
+      cenA = (dA <= dmax[0]) ? cenA : 255;
+      cenB = (dB <= dmax[1]) ? cenB : 255;
+      nccA = (dA <= dmax[2]) ? nccA : kFill;
+      nccB = (dB <= dmax[3]) ? nccB : kFill;
+      rowA = min(dA, D);
+      rowB = min(dB, D);
+    }
+    pc[rowA * kTile] = (uint8_t)cenA;
+    pc[rowB * kTile + 1] = (uint8_t)cenB;
+    pn[rowA * kTile] = nccA;
+    pn[rowB * kTile + 1] = nccB;
+    mn.cenA = min(mn.cenA, cenA);
+    mn.cenB = min(mn.cenB, cenB);
+    mn.nccA = fminf(mn.nccA, nccA);
+    mn.nccB = fminf(mn.nccB, nccB);
+  }
+}
+
+template <class L>
+__device__ __forceinline__ void p1_census_ncc(const FusedArgs& a, const TileId& t, const unsigned char* stage,
+                                              const StageGeo& sg, float* s_par, uint8_t* s_cen, const P1Ctx& c,
+                                              const int (&dmax)[4], P1Min& mn) {
+  const FusedGeom& g = a.g;
+  const int D = g.D;
+  // the pair's left census codes, 3x4 patch and NCC statistics (read here, after loop Z, rather than
+  // kept live through it: they come from L1/L2)
+  uint4 ldA, ldB;
+  f32x2 l3[3][3];
+  f32x2 lA2;
+  double lCA, lCB;
+  {
+    const int Yp = t.y + g.bh + kPadT;
+    const int Xp = t.x0 + 2 * c.pr + g.bwl + g.padL;
+    const size_t img_off = (size_t)t.n * g.img_px();
+    const uint4* dp = a.descL + img_off + (size_t)Yp * g.Wp + Xp;
+    ldA = __ldg(dp);
+    ldB = __ldg(dp + 1);
+    const float* gf = a.fL + img_off + (size_t)(Yp - 1) * g.Wp + (Xp - 1);
+#pragma unroll
+    for (int r = 0; r < 3; ++r) {
+      float v[4];
+#pragma unroll
+      for (int k = 0; k < 4; ++k) v[k] = __ldg(gf + k);
+      // + (-0.0) is exact; the run-time operand keeps each pair in registers of its own (ptxas would
+      // otherwise rebuild the overlapping pairs with MOVs at every use)
+#pragma unroll
+      for (int j = 0; j < 3; ++j) l3[r][j] = add2(pk2(v[j], v[j + 1]), pk2(a.neg_zero, a.neg_zero));
+      gf += g.Wp;
+    }
+    const RStat* sp = a.statL + img_off + (size_t)Yp * g.Wp + Xp;
+    lA2 = pk2(__ldg(&sp[0].A), __ldg(&sp[1].A));
+    lCA = __ldg(&sp[0].C);
+    lCB = __ldg(&sp[1].C);
+  }
+  float* pn = s_par + 2 * c.pr;     // ncc plane, column of voxel A
+  uint8_t* pc = s_cen + 2 * c.pr;   // census bytes, column of voxel A
+  int dA = c.dA0, cx = c.cx0;
+  for (int base = 0; base < c.nsteps; base += 6, dA += 6, cx -= 6) {
+    const int kind = block_kind(dA, c.nsteps - base, dmax[0], dmax[1], dmax[2], dmax[3]);
+    if (kind == kBlkClean) {
+      cn_block<L, true>(stage, sg, cx, dA, 6, D, ldA, ldB, l3, lA2, lCA, lCB, dmax, pn, pc, mn);
+    } else if (kind == kBlkGeneric) {
+      cn_block<L, false>(stage, sg, cx, dA, c.nsteps - base, D, ldA, ldB, l3, lA2, lCA, lCB, dmax, pn, pc, mn);
+    } else {
+#pragma unroll
+      for (int sI = 0; sI < 6; ++sI) {
+        if (sI >= c.nsteps - base) break;
+        const int rowA = min(dA + sI, D), rowB = min(dA + sI + 1, D);
+        pc[rowA * kTile] = 255;
+        pc[rowB * kTile + 1] = 255;
+        pn[rowA * kTile] = kFill;
+        pn[rowB * kTile + 1] = kFill;
+      }
+    }
+  }
+}
+
 // Group 0's extra voxel: B = (odd pixel, d = 0) alone (its diagonal partner would be d = -1).
 // cxB: padded right column of B at d = 0.  dmaxB*: validity bounds of pixel B (cost iff 0 <= dmax).
 template <class L>
-__device__ __forceinline__ void p1_extra_b0(const unsigned char* stage, const StageGeo& sg, float* s_par,
-                                            uint8_t* s_cen, const Left2& lr, int pr, int cxB, int dmaxB_cen,
-                                            int dmaxB_ncc, int dmaxB_sad, P1Min& mn) {
-  const RStat lsB = *reinterpret_cast<const RStat*>(&lr.statB);
+__device__ __forceinline__ void p1_extra_b0(const FusedArgs& a, const TileId& t, const unsigned char* stage,
+                                            const StageGeo& sg, float* s_par, uint8_t* s_cen, const Left2& lr, int pr,
+                                            int cxB, int dmaxB_cen, int dmaxB_ncc, int dmaxB_sad, P1Min& mn) {
+  const FusedGeom& g = a.g;
+  const uint4 lsB_raw = __ldg(reinterpret_cast<const uint4*>(
+      a.statL + (size_t)t.n * g.img_px() + (size_t)(t.y + g.bh + kPadT) * g.Wp + (t.x0 + 2 * pr + 1 + g.bwl + g.padL)));
+  const RStat lsB = *reinterpret_cast<const RStat*>(&lsB_raw);
+  const uint4 ldB = __ldg(a.descL + (size_t)t.n * g.img_px() + (size_t)(t.y + g.bh + kPadT) * g.Wp +
+                          (t.x0 + 2 * pr + 1 + g.bwl + g.padL));
   const uint4 rd = *colptr<uint4>(stage + L::st_desc, L::capD, sg.pD, cxB);
   const double rC = *colptr<double>(stage + L::st_c, L::capC, sg.pC, cxB);
   const float rA = *colptr<float>(stage + L::st_a, L::capF, sg.pF, cxB);
   const float mR = *colptr<float>(stage + L::st_mean, L::capF, sg.pF, cxB);
-  int cen = popc128(lr.descB, rd);
+  int cen = popc128(ldB, rd);
   float P = 0.f, z = 0.f;
 #pragma unroll
   for (int r = 0; r < 5; ++r)
@@ -467,7 +464,7 @@ __device__ __forceinline__ void p1_extra_b0(const unsigned char* stage, const St
     for (int j = 0; j < 5; ++j) {
       const float w = colptr<float>(stage + L::st_rf, L::capF, sg.pF, cxB - 2 + j)[r * 2 * L::capF];
       if (r >= 1 && r <= 3 && j >= 1 && j <= 3) P = __fmaf_rn(lr.px[r][j + 1], w, P);
-      z = __fadd_rn(z, fabsf(__fadd_rn(__fsub_rn(__fsub_rn(lr.px[r][j + 1], lsB.mean), w), mR)));
+      z = __fadd_rn(z, fabsf(__fadd_rn(__fsub_rn(__fsub_rn(lr.px[r][j + 1], lr.meanB), w), mR)));
     }
   const float num = __fmaf_rn(9.0f, P, -__fmul_rn(lsB.A, rA));
   float ncc = ncc_scale(num, lsB.C, rC);
@@ -683,6 +680,127 @@ __device__ __forceinline__ void tile_back_half(const FusedArgs& a, const TileId&
   __syncthreads();
   if (vec) pass_n<true>(s_par, s_ce, s_inv, PS, q4, dl, D, orow + 4 * chan, plane, chan, nlive);
   else pass_n<false>(s_par, s_ce, s_inv, PS, q4, dl, D, orow + 4 * chan, plane, chan, nlive);
+}
+
+// ---- alternative back half: exponentials recomputed on the fly (no write-back) ----------------
+// Channels 0-3 (cbmv_generator.py:283-287) for thread = (pixel quad q4, disparities d0, d0+16, ... < d1)
+template <bool kVec>
+__device__ __forceinline__ void store_ch03(const float* s_par, const uint8_t* s_cen, int PS, int q4, int d0, int d1,
+                                           float* orow, size_t plane, size_t chan, int nlive) {
+#pragma unroll 1
+  for (int d = d0; d < d1; d += 16) {
+    const float* e0 = s_par + d * kTile + q4;
+    const uchar4 cb = *reinterpret_cast<const uchar4*>(s_cen + d * kTile + q4);
+    const float4 v1 = *reinterpret_cast<const float4*>(e0);
+    const float4 v2 = *reinterpret_cast<const float4*>(e0 + PS);
+    const float4 v3 = *reinterpret_cast<const float4*>(e0 + 2 * PS);
+    const float4 c0 = make_float4(census_ch0(cb.x), census_ch0(cb.y), census_ch0(cb.z), census_ch0(cb.w));
+    const float4 c1 = make_float4(normalise_cost(v1.x, 1), normalise_cost(v1.y, 1), normalise_cost(v1.z, 1),
+                                  normalise_cost(v1.w, 1));
+    const float4 c2 = make_float4(normalise_cost(v2.x, 2), normalise_cost(v2.y, 2), normalise_cost(v2.z, 2),
+                                  normalise_cost(v2.w, 2));
+    const float4 c3 = make_float4(normalise_cost(v3.x, 3), normalise_cost(v3.y, 3), normalise_cost(v3.z, 3),
+                                  normalise_cost(v3.w, 3));
+    store_quads<kVec>(orow + (size_t)d * plane, chan, nlive, c0, c1, c2, c3);
+  }
+}
+
+// Channels 4-7 = exp(-(c-m)^2/sigma) / den for thread = (pixel quad q4, disparities dl, dl+32, ...),
+// exponentials recomputed from the parked costs, 128-bit row segments.
+template <bool kVec>
+__device__ __forceinline__ void phase3_quads(const float* s_par, const uint8_t* s_cen, const float* s_min,
+                                             const float* s_inv, int PS, int q4, int dl, int D, float* arow,
+                                             size_t plane, size_t chan, int nlive, float k0, float k1, float k2) {
+  const float4 m_cen4 = *reinterpret_cast<const float4*>(s_min + q4);
+  const float4 m1 = *reinterpret_cast<const float4*>(s_min + kTile + q4);
+  const float4 m2 = *reinterpret_cast<const float4*>(s_min + 2 * kTile + q4);
+  const float4 m3 = *reinterpret_cast<const float4*>(s_min + 3 * kTile + q4);
+  const float4 i0 = *reinterpret_cast<const float4*>(s_inv + q4);
+  const float4 i1 = *reinterpret_cast<const float4*>(s_inv + kTile + q4);
+  const float4 i2 = *reinterpret_cast<const float4*>(s_inv + 2 * kTile + q4);
+  const float4 i3 = *reinterpret_cast<const float4*>(s_inv + 3 * kTile + q4);
+  const int mcx = (m_cen4.x == kFill) ? 0 : (int)m_cen4.x, mcy = (m_cen4.y == kFill) ? 0 : (int)m_cen4.y;
+  const int mcz = (m_cen4.z == kFill) ? 0 : (int)m_cen4.z, mcw = (m_cen4.w == kFill) ? 0 : (int)m_cen4.w;
+#pragma unroll 1
+  for (int d = dl; d < D; d += 32) {
+    const float* e0 = s_par + d * kTile + q4;
+    const uchar4 cb = *reinterpret_cast<const uchar4*>(s_cen + d * kTile + q4);
+    const float4 v1 = *reinterpret_cast<const float4*>(e0);
+    const float4 v2 = *reinterpret_cast<const float4*>(e0 + PS);
+    const float4 v3 = *reinterpret_cast<const float4*>(e0 + 2 * PS);
+    const float4 a0 = make_float4(census_e(cb.x, mcx, k0) * i0.x, census_e(cb.y, mcy, k0) * i0.y,
+                                  census_e(cb.z, mcz, k0) * i0.z, census_e(cb.w, mcw, k0) * i0.w);
+    const float4 a1 = make_float4(aml_e(v1.x, m1.x, k1) * i1.x, aml_e(v1.y, m1.y, k1) * i1.y,
+                                  aml_e(v1.z, m1.z, k1) * i1.z, aml_e(v1.w, m1.w, k1) * i1.w);
+    const float4 a2 = make_float4(aml_e(v2.x, m2.x, k2) * i2.x, aml_e(v2.y, m2.y, k2) * i2.y,
+                                  aml_e(v2.z, m2.z, k2) * i2.z, aml_e(v2.w, m2.w, k2) * i2.w);
+    const float4 a3 = make_float4(aml_e(v3.x, m3.x, k2) * i3.x, aml_e(v3.y, m3.y, k2) * i3.y,
+                                  aml_e(v3.z, m3.z, k2) * i3.z, aml_e(v3.w, m3.w, k2) * i3.w);
+    store_quads<kVec>(arow + (size_t)d * plane, chan, nlive, a0, a1, a2, a3);
+  }
+}
+
+template <class L>
+__device__ __forceinline__ void tile_back_half_otf(const FusedArgs& a, const TileId& t, int tid, const float* s_par,
+                                               const uint8_t* s_cen, const float* s_red, float* s_min,
+                                               float* s_inv) {
+  constexpr int PS = L::PS;
+  const FusedGeom& g = a.g;
+  const int D = g.D;
+  const size_t plane = (size_t)g.h * g.w;
+  const size_t chan = plane * D;
+  if (tid < 4 * kTile) {  // minima across the d-groups
+    float v = kFill;
+#pragma unroll
+    for (int gq = 0; gq < kG2; ++gq) v = fminf(v, s_red[gq * 4 * kTile + tid]);
+    s_min[tid] = v;
+  }
+  __syncthreads();
+  const int warp = tid >> 5, lane = tid & 31;
+  const int q4 = (tid & 7) * 4;
+  // 128-bit stores need 16-byte aligned rows
+  const bool vec_ok = ((g.w & 3) == 0) && ((reinterpret_cast<uintptr_t>(a.out) & 15) == 0);
+  float* orow = a.out + (size_t)t.n * a.out_channels * chan + (size_t)t.y * g.w + (t.x0 + q4);
+  const int nlive = min(4, g.w - (t.x0 + q4));  // live pixels of this quad (<= 0: none)
+  const bool vec = vec_ok && nlive == 4;
+  if (warp < 4) {
+    // the reference's sequential fp32 sum over d (featextract.cpp:444-447), exponentials on the fly
+    const float mm = s_min[warp * kTile + lane];
+    float den = 0.f;
+    const int Dfull = D & ~7;   // groups of 8 without guards, then a guarded tail
+    if (warp == 0) {
+      const int mc = (mm == kFill) ? 0 : (int)mm;
+      const uint8_t* c = s_cen + lane;
+      for (int d0 = 0; d0 < Dfull; d0 += 8, c += 8 * kTile) {
+        float ev[8];
+#pragma unroll
+        for (int j = 0; j < 8; ++j) ev[j] = census_e(c[j * kTile], mc, a.k_cen);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) den = __fadd_rn(den, ev[j]);
+      }
+      for (int d = Dfull; d < D; ++d, c += kTile) den = __fadd_rn(den, census_e(c[0], mc, a.k_cen));
+    } else {
+      const float kq = (warp == 1) ? a.k_ncc : a.k_sad;
+      const float* e = s_par + (warp - 1) * PS + lane;
+      for (int d0 = 0; d0 < Dfull; d0 += 8, e += 8 * kTile) {
+        float ev[8];
+#pragma unroll
+        for (int j = 0; j < 8; ++j) ev[j] = aml_e(e[j * kTile], mm, kq);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) den = __fadd_rn(den, ev[j]);
+      }
+      for (int d = Dfull; d < D; ++d, e += kTile) den = __fadd_rn(den, aml_e(e[0], mm, kq));
+    }
+    s_inv[warp * kTile + lane] = (mm == kFill) ? 0.f : 1.0f / den;
+  } else {
+    // channels 0-3: thread = (pixel quad, d), 16 disparities per sweep of the four warps
+    if (vec) store_ch03<true>(s_par, s_cen, PS, q4, (tid >> 3) - 16, D, orow, plane, chan, nlive);
+    else store_ch03<false>(s_par, s_cen, PS, q4, (tid >> 3) - 16, D, orow, plane, chan, nlive);
+  }
+  __syncthreads();
+  const int dl = tid >> 3;
+  if (vec) phase3_quads<true>(s_par, s_cen, s_min, s_inv, PS, q4, dl, D, orow + 4 * chan, plane, chan, nlive, a.k_cen, a.k_ncc, a.k_sad);
+  else phase3_quads<false>(s_par, s_cen, s_min, s_inv, PS, q4, dl, D, orow + 4 * chan, plane, chan, nlive, a.k_cen, a.k_ncc, a.k_sad);
 }
 
 // Back half of a tile for DISPARITY-SLAB SHARDING (phase A of slab.cu): the AML
