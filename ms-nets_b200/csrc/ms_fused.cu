@@ -9,16 +9,29 @@
 // Launch sequence (all on one stream):
 //   1. ms_prep_kernel    per padded pixel of every image: census code (4x u32), ZSAD
 //                        window mean, NCC window sum A and fp64 C = 1/sqrt(9B - A^2),
-//                        float copy of the pixel, Sobel response.  The right image's planes
-//                        are written DE-INTERLEAVED (even columns, then odd columns of a row).
-//   2. sadsob scan       (sadsob.cu) -> raw SAD-of-Sobel volume [N][D][H][W]; its fp32
+//                        float copy of the pixel, Sobel response.
+//   2. sadsob vband+scan (sadsob.cu) -> raw SAD-of-Sobel volume [N][D][H][W]; its fp32
 //                        summed-area table needs whole-row sequential scans, so it
 //                        cannot live inside an x-tile.
-//   3. ms_fused_kernel   one CTA = one output row y x 32 pixels x ALL D (ms_fused_tile.cuh).
+//   3. ms_fused_kernel   one CTA = one output row y x 32 pixels x ALL D:
+//        stage    right-image row data (census codes, stats, 5 float rows) and the tile's
+//                 SAD-of-Sobel costs stream into shared memory through TMA (cp.async.bulk /
+//                 cp.async.bulk.tensor; LDGSTS fallback for D > 256).
+//        phase 1  8 warps split D; lane = pixel.  Per (pixel, d): census popcount, NCC (9 fp32
+//                 products of exact integers, fp64 scaling), ZSAD over a register-resident
+//                 right window that slides with d -- two disparities at a time with packed
+//                 FADD2, every add still an IEEE fp32 add in the reference's order; raw costs
+//                 are parked in shared memory (13 B/voxel: three floats + census byte);
+//                 per-pixel minima.
+//        phase 2  warp-specialised, both halves only READ the parked costs:
+//                 warps 0-3: one thread per (pixel, matcher) adds the AML denominator in
+//                 d order (the reference's sequential fp32 sum, featextract.cpp:444-447);
+//                 warps 4-7: thread = (pixel quad, d): channels 0-3 normalised and stored
+//                 as 128-bit row segments.
+//        phase 3  channels 4-7 = exp(-(c-m)^2/sigma) / den, 128-bit row segments.
 //
-// Bounding resources, in the order they bite (ncu, profiles/): the L1 / shared-memory data pipe
-// (one 128-byte wavefront per cycle per SM), then HBM writes (32 B per voxel); the FP32 pipe
-// (ZSAD: 75 ordered adds per voxel, issued as packed FADD2) is third.
+// Bounding resource: HBM writes (32 B per voxel), co-limited by the FP32 pipe -- ZSAD alone is
+// 75 ordered adds per voxel -- and by shared-memory/LSU traffic (DESIGN.md has the arithmetic).
 #include "ms_fused.cuh"
 
 #include <cuda.h>
@@ -33,11 +46,13 @@ namespace msn {
 
 namespace {
 
-constexpr int kTile = 32;     // pixels per tile: one output row segment of 128 bytes
+constexpr int kTileMax = 32;  // widest tile (pixels per CTA) the geometry allows for
+constexpr int kGroups = 8;    // d-groups per tile: a phase-1 thread owns (pixel, d-group)
+constexpr int kSlack = 24;    // right-image columns left of X-(D-1) that dummy steps (d >= D) may read: groups*DC - D < 2*groups
 constexpr int kPadT = 2;      // padded rows above/below (ZSAD halo)
-constexpr int kPadR = 48;     // padded columns to the right (tile overhang + halo + copy granules)
+constexpr int kPadR = 40;     // padded columns to the right (tile overhang + halo)
 constexpr int kCensW = 11, kNccW = 3, kSadW = 5;
-constexpr int kMaxFusedD = 384;   // more disparities: slabs of kFusedSlabD (capi.cu)
+constexpr int kMaxFusedD = 448;
 
 struct __align__(16) RStat {
   float mean;  // ZSAD window mean (matchers.cpp:482)
@@ -62,36 +77,34 @@ FusedGeom make_geom(int N, int H, int W, const msn_ms_params* p) {
   g.bh = p->board_h; g.bwl = p->board_w_left;
   g.h = H - 2 * p->board_h;
   g.w = W - p->board_w_left - p->board_w_right;
-  g.padL = (g.d0 + g.D + 32 + 7) & ~7;      // the leftmost staged column (see stage_geo) stays >= 0
+  g.padL = (g.d0 + g.D + 1 + kSlack + 8 + 7) & ~7;  // d0+D-1 columns of disparity + dummy-step slack + halo/alignment
   g.Hp = H + 2 * kPadT;
-  g.Wp = (W + g.padL + kPadR + 7) & ~7;     // multiple of 8: both halves of a de-interleaved row start on 16 B
+  g.Wp = (W + g.padL + kPadR + 3) & ~3;
   g.sxo = (4 - (g.bwl & 3)) & 3;            // x0 + bwl + sxo is a multiple of 4 for every tile
-  g.Ws = sadsob_fast_pitch(W + g.sxo + kTile);  // compile-time pitch of the scan kernels (0: too wide)
+  g.Ws = sadsob_fast_pitch(W + g.sxo + kTileMax);  // compile-time pitch of the scan kernels (0: too wide)
   return g;
 }
 
 struct FusedWs {
-  uint4* desc[2];   // census codes; [1] (right image) de-interleaved like every right-image plane
-  RStat* statL;
-  float* aR;        // right image: NCC window sum A
-  double* cR;       // right image: NCC C
-  float* meanR;     // right image: ZSAD window mean
+  uint4* desc[2];
+  RStat* stat[2];
   float* fimg[2];
   float* sob[2];
-  float* sadsob;    // [N][D][H][Ws]
+  float* meanR[2]; // ZSAD means of the right image as plain floats; copy 1 is shifted by one column
+  float* luts;     // [128] census AML exponentials + [256] census byte -> channel 0
+  float* sadsob;   // [N][D][H][W]
   void* sad_ws;
   size_t total;
   void carve(char* base, const FusedGeom& g) {
     size_t off = 0;
     auto take = [&](size_t bytes) { char* q = base ? base + off : nullptr; off += (bytes + 255) & ~(size_t)255; return q; };
-    const size_t np = (size_t)g.N * g.img_px() + 64;   // (+ slack: a half-row copy may run a granule past the last row)
+    const size_t np = (size_t)g.N * g.img_px();
     for (int i = 0; i < 2; ++i) desc[i] = (uint4*)take(np * sizeof(uint4));
-    statL = (RStat*)take(np * sizeof(RStat));
-    aR = (float*)take(np * sizeof(float));
-    cR = (double*)take(np * sizeof(double));
-    meanR = (float*)take(np * sizeof(float));
+    for (int i = 0; i < 2; ++i) stat[i] = (RStat*)take(np * sizeof(RStat));
     for (int i = 0; i < 2; ++i) fimg[i] = (float*)take(np * sizeof(float));
     for (int i = 0; i < 2; ++i) sob[i] = (float*)take((size_t)g.N * (g.H + kSadRowPad) * g.Ws * sizeof(float));  // zero padded
+    for (int i = 0; i < 2; ++i) meanR[i] = (float*)take((np + 16) * sizeof(float));
+    luts = (float*)take(384 * sizeof(float));
     sadsob = (float*)take((size_t)g.N * g.D * g.H * g.Ws * sizeof(float) + 256);
     sad_ws = take(sadsob_workspace_bytes_n(g.N, g.H, g.W, g.D, kSadW));
     total = off;
@@ -103,8 +116,18 @@ struct FusedWs {
 __global__ void __launch_bounds__(128)
 ms_prep_kernel(const uint8_t* __restrict__ left, const uint8_t* __restrict__ right, FusedGeom g,
                uint4* __restrict__ descL, uint4* __restrict__ descR, RStat* __restrict__ statL,
-               float* __restrict__ aR, double* __restrict__ cR, float* __restrict__ meanR,
-               float* __restrict__ fL, float* __restrict__ fR, float* __restrict__ sobL, float* __restrict__ sobR) {
+               RStat* __restrict__ statR, float* __restrict__ fL, float* __restrict__ fR,
+               float* __restrict__ sobL, float* __restrict__ sobR, float* __restrict__ meanR0,
+               float* __restrict__ meanR1, float* __restrict__ luts, float k_cen) {
+  if (blockIdx.x == 0 && blockIdx.y == 0 && blockIdx.z == 0) {
+    // tables for the fused kernel: census AML exponentials exp(-(k^2)/sigma), k = 0..120, and the
+    // channel-0 value k/120 of a parked census byte (a true IEEE division; 255 = no cost ->
+    // clip(fill, 0, 120)/120 = 1)
+    for (int kk = threadIdx.x; kk < 256; kk += blockDim.x) {
+      if (kk < 128) luts[kk] = (kk <= 120) ? ex2_approx(-(float)(kk * kk) * k_cen) : 0.f;
+      luts[128 + kk] = (kk <= 120) ? __fdiv_rn((float)kk, 120.0f) : 1.0f;
+    }
+  }
   const int xp = blockIdx.x * blockDim.x + threadIdx.x;
   const int yp = blockIdx.y;
   const int n = blockIdx.z >> 1, side = blockIdx.z & 1;
@@ -113,7 +136,7 @@ ms_prep_kernel(const uint8_t* __restrict__ left, const uint8_t* __restrict__ rig
   const uint8_t* img = (side ? right : left) + (size_t)n * H * W;
   const int X = xp - g.padL, Y = yp - kPadT;
   const bool inside = (X >= 0 && X < W && Y >= 0 && Y < H);
-  const size_t rowo = (size_t)n * g.img_px() + (size_t)yp * g.Wp;
+  const size_t po = (size_t)n * g.img_px() + (size_t)yp * g.Wp + xp;
 
   uint32_t w0 = 0, w1 = 0, w2 = 0, w3 = 0;
   RStat st;
@@ -172,19 +195,14 @@ ms_prep_kernel(const uint8_t* __restrict__ left, const uint8_t* __restrict__ rig
     }
     (side ? sobR : sobL)[(size_t)n * (H + kSadRowPad) * g.Ws + (size_t)Y * g.Ws + X] = sv;
   }
+  (side ? descR : descL)[po] = make_uint4(w0, w1, w2, w3);
+  (side ? statR : statL)[po] = st;
+  (side ? fR : fL)[po] = pix;
   if (side) {
-    // right image: even columns first, then odd columns (ms_fused_tile.cuh: lanes own pixel pairs)
-    const size_t po = rowo + (size_t)(xp >> 1) + (size_t)(xp & 1) * (g.Wp >> 1);
-    descR[po] = make_uint4(w0, w1, w2, w3);
-    aR[po] = st.A;
-    cR[po] = st.C;
-    meanR[po] = st.mean;
-    fR[po] = pix;
-  } else {
-    const size_t po = rowo + xp;
-    descL[po] = make_uint4(w0, w1, w2, w3);
-    statL[po] = st;
-    fL[po] = pix;
+    // (mean[x-1], mean[x]) must be ONE aligned 64-bit shared load in the fused kernel whatever
+    // the parity of x: the second copy holds the same row shifted right by one element
+    meanR0[po] = st.mean;
+    meanR1[po + 1] = st.mean;
   }
 }
 
@@ -192,11 +210,10 @@ ms_prep_kernel(const uint8_t* __restrict__ left, const uint8_t* __restrict__ rig
 struct FusedArgs {
   FusedGeom g;
   const uint4 *descL, *descR;
-  const RStat* statL;
-  const float* aR;
-  const double* cR;
-  const float* meanR;
+  const RStat *statL, *statR;
   const float *fL, *fR;
+  const float *meanR0, *meanR1;  // right-image ZSAD means; meanR1[x] = mean[x-1]
+  const float* luts;    // [128] + [256], see ms_prep_kernel
   const float* sadsob;  // [N][D][H][Ws] (+ slack)
   float* out;           // [N][8][D][h][w]
   float* mins;          // slab phase A only: [N][mins_planes][h][w], planes 0-3 = per-pixel minima of this launch's disparities
@@ -205,10 +222,51 @@ struct FusedArgs {
   int out_D, out_d0;    // slab phase A: disparity count of the output tensor and where this launch's slab sits in it
   int mins_accumulate;  // slab phase A: fold into the minima already in `mins` (a later slab of the same volume)
   float k_cen, k_ncc, k_sad;
-  float neg_zero;       // -0.0f (x + -0.0f == x exactly): an operand the compiler cannot fold
-  int DC;               // disparity steps per d-group
+  int DC;               // disparity steps per d-group (even: phase 1 walks disparity pairs)
   int tiles_x;
-  int xflags;           // experiment switches (MSNETS_X)
+};
+
+constexpr int kTile = 32;   // pixels per tile: one output row segment of 128 bytes
+
+// Staging buffer of one tile: right-image row data for the D + 31 (+ slack) columns the tile
+// can touch.  Row strides are compile-time so every shared access in the hot loop is
+// "pointer + immediate".
+template <int DMAX, int SLACK>
+struct StageLay {
+  static constexpr int kSl = SLACK;
+  static constexpr int RW = (DMAX + kTile - 1 + SLACK + 3) & ~3;   // desc / stat entries
+  static constexpr int RWF = RW + 8;                               // float row: halo 2+2, align shift <= 3
+  static constexpr size_t st_desc = 0;                                   // [RW] uint4 census codes
+  static constexpr size_t st_stat = st_desc + (size_t)RW * 16;           // [RW] RStat
+  static constexpr size_t st_rf = st_stat + (size_t)RW * 16;             // [5][RWF] float pixel rows
+  static constexpr size_t st_mean = st_rf + (size_t)5 * RWF * 4;         // [2][RWF] ZSAD means, copy 1 shifted by one
+  static constexpr size_t st_bytes = (st_mean + (size_t)2 * RWF * 4 + 127) & ~(size_t)127;
+};
+
+// Parking buffer of one tile: raw costs (later: AML exponentials) for every (d, pixel).
+//   [3][DS][32] floats (ncc, sadsob, zsad) + [DS][32] census bytes; plane DMAX is scratch for
+//   dummy steps.  Plane 1 is a TMA destination: DS * 128 bytes keeps it 128-byte aligned.
+template <int DMAX>
+struct ParkLay {
+  static constexpr int DS = DMAX + 1;
+  static constexpr int PS = DS * kTile;                                  // floats per parked matcher
+  static constexpr size_t pk_cen = (size_t)3 * PS * 4;
+  static constexpr size_t pk_bytes = (pk_cen + (size_t)DS * kTile + 127) & ~(size_t)127;
+};
+
+// Shared memory of one CTA = one tile (2 CTAs per SM).
+template <int DMAX, int SLACK>
+struct Lay : StageLay<DMAX, SLACK>, ParkLay<DMAX> {
+  using S = StageLay<DMAX, SLACK>;
+  using P = ParkLay<DMAX>;
+  static constexpr size_t off_red = S::st_bytes;                                  // [kGroups][4][32] per-group minima
+  static constexpr size_t off_min = off_red + (size_t)kGroups * 4 * kTile * 4;    // [4][32]
+  static constexpr size_t off_inv = off_min + 4 * kTile * 4;                      // [4][32]
+  static constexpr size_t off_lut = off_inv + 4 * kTile * 4;                      // [128] census AML exponentials
+  static constexpr size_t off_lutn = off_lut + 128 * 4;                           // [256] census byte -> channel 0
+  static constexpr size_t off_par = (off_lutn + 256 * 4 + 127) & ~(size_t)127;    // 128 B aligned: TMA destination
+  static constexpr size_t off_bar = off_par + P::pk_bytes;                        // 2 mbarriers
+  static constexpr size_t bytes = off_bar + 32;
 };
 
 __device__ __forceinline__ void cp_async4(void* smem_dst, const void* gmem_src) {
@@ -302,6 +360,69 @@ __device__ __forceinline__ TileId decode_tile(int tile, const FusedArgs& a) {
   return t;
 }
 
+// Asynchronously copies the right-image row data of `t` into a staging buffer with LDGSTS:
+// census codes and stats of the D+31(+slack) columns the tile can touch and the five float
+// rows of the ZSAD/NCC windows (the float rows start at a 4-float aligned column).
+template <class L, int NT>
+__device__ __forceinline__ void stage_right(const FusedArgs& a, const TileId& t, unsigned char* buf) {
+  const FusedGeom& g = a.g;
+  const int D = g.D;
+  const int RWn = D + kTile - 1 + L::kSl;
+  const int XbaseP = t.x0 + g.bwl - (g.d0 + D - 1) - L::kSl + g.padL;
+  const int Yp = t.y + g.bh + kPadT;
+  const size_t img_off = (size_t)t.n * g.img_px();
+  const uint4* gd = a.descR + img_off + (size_t)Yp * g.Wp + XbaseP;
+  const uint4* gs = reinterpret_cast<const uint4*>(a.statR + img_off + (size_t)Yp * g.Wp + XbaseP);
+  uint4* s_desc = reinterpret_cast<uint4*>(buf + L::st_desc);
+  uint4* s_stat = reinterpret_cast<uint4*>(buf + L::st_stat);
+  float* s_rf = reinterpret_cast<float*>(buf + L::st_rf);
+  for (int i = threadIdx.x; i < RWn; i += NT) {
+    cp_async16(s_desc + i, gd + i);
+    cp_async16(s_stat + i, gs + i);
+  }
+  const int fstart = (XbaseP - 2) & ~3;                 // aligned first float column
+  const int nvec = (RWn + 4 + 3 + 3) >> 2;              // 16-byte groups per row (covers any shift)
+  for (int i = threadIdx.x; i < 5 * nvec; i += NT) {
+    const int r = i / nvec, v = i - r * nvec;
+    cp_async16(s_rf + r * L::RWF + 4 * v, a.fR + img_off + (size_t)(Yp - 2 + r) * g.Wp + fstart + 4 * v);
+  }
+  float* s_mean = reinterpret_cast<float*>(buf + L::st_mean);
+  const int mstart = XbaseP & ~3;
+  const int nvm = (RWn + 3 + 3) >> 2;
+  for (int i = threadIdx.x; i < 2 * nvm; i += NT) {
+    const int c = i / nvm, v = i - c * nvm;
+    cp_async16(s_mean + c * L::RWF + 4 * v, (c ? a.meanR1 : a.meanR0) + img_off + (size_t)Yp * g.Wp + mstart + 4 * v);
+  }
+}
+
+// Same data through the TMA engine: nine 1-D bulk copies issued by a single thread,
+// completion counted in bytes on `bar`.
+template <class L>
+__device__ __forceinline__ void stage_rows_tma(const FusedArgs& a, const TileId& t, unsigned char* buf,
+                                               unsigned long long* bar) {
+  const FusedGeom& g = a.g;
+  const int D = g.D;
+  const int RWn = D + kTile - 1 + L::kSl;
+  const int XbaseP = t.x0 + g.bwl - (g.d0 + D - 1) - L::kSl + g.padL;
+  const int Yp = t.y + g.bh + kPadT;
+  const size_t img_off = (size_t)t.n * g.img_px();
+  const int fstart = (XbaseP - 2) & ~3;
+  const int nvec = (RWn + 4 + 3 + 3) >> 2;
+  const unsigned row_bytes = (unsigned)RWn * 16u, frow_bytes = (unsigned)nvec * 16u;
+  const int mstart = XbaseP & ~3;
+  const unsigned mrow_bytes = (unsigned)((RWn + 3 + 3) >> 2) * 16u;
+  mbar_expect_tx(bar, 2u * row_bytes + 5u * frow_bytes + 2u * mrow_bytes);
+  bulk_load(buf + L::st_desc, a.descR + img_off + (size_t)Yp * g.Wp + XbaseP, row_bytes, bar);
+  bulk_load(buf + L::st_stat, a.statR + img_off + (size_t)Yp * g.Wp + XbaseP, row_bytes, bar);
+  float* s_rf = reinterpret_cast<float*>(buf + L::st_rf);
+#pragma unroll
+  for (int r = 0; r < 5; ++r)
+    bulk_load(s_rf + r * L::RWF, a.fR + img_off + (size_t)(Yp - 2 + r) * g.Wp + fstart, frow_bytes, bar);
+  float* s_mean = reinterpret_cast<float*>(buf + L::st_mean);
+  bulk_load(s_mean, a.meanR0 + img_off + (size_t)Yp * g.Wp + mstart, mrow_bytes, bar);
+  bulk_load(s_mean + L::RWF, a.meanR1 + img_off + (size_t)Yp * g.Wp + mstart, mrow_bytes, bar);
+}
+
 // The tile's D x 32 SAD-of-Sobel costs: ONE 3-D tensor copy straight into parking plane 1.
 // They come from DRAM and are only needed after phase 1, hence their own barrier.
 __device__ __forceinline__ void stage_sad_tma(const FusedArgs& a, const CUtensorMap* sad_map, const TileId& t,
@@ -311,10 +432,506 @@ __device__ __forceinline__ void stage_sad_tma(const FusedArgs& a, const CUtensor
   tma_load_3d(park_plane1, sad_map, t.x0 + g.bwl + g.sxo, t.y + g.bh, t.n * g.D, bar_sad);  // inner coordinate % 4 == 0
 }
 
+// A pixel's own left-image data: census code, stats, 5x5 float window.  Loaded straight from
+// global memory before the staging barrier, so the latency overlaps the TMA round trip
+// (staging it through TMA as well was measured 1.5 % slower).
+struct LeftRegs {
+  uint4 desc;
+  uint4 stat;
+  float px[5][5];
+};
+__device__ __forceinline__ void load_left(const FusedArgs& a, const TileId& t, int px, LeftRegs& lr) {
+  const FusedGeom& g = a.g;
+  const int Yp = t.y + g.bh + kPadT;
+  const int Xp = t.x0 + px + g.bwl + g.padL;
+  const size_t img_off = (size_t)t.n * g.img_px();
+  lr.desc = __ldg(a.descL + img_off + (size_t)Yp * g.Wp + Xp);
+  lr.stat = __ldg(reinterpret_cast<const uint4*>(a.statL + img_off + (size_t)Yp * g.Wp + Xp));
+#pragma unroll
+  for (int r = 0; r < 5; ++r) {
+    const float* gf = a.fL + img_off + (size_t)(Yp - 2 + r) * g.Wp + (Xp - 2);
+#pragma unroll
+    for (int c = 0; c < 5; ++c) lr.px[r][c] = __ldg(gf + c);
+  }
+}
 
-#include "ms_fused_tile.cuh"
+// ---- phase 1 of a tile for one thread = (pixel px, d-group [d_lo, d_lo + DC)) ---------------
+// Per (pixel, d): census popcount, NCC (9 fp32 products of exact integers, fp64 scaling), ZSAD
+// over a register-resident right window that slides with d; raw costs are parked in shared
+// memory (ncc -> plane 0, zsad -> plane 2, census byte); running minima are returned.
+//
+// ZSAD evaluates disparities in pairs (dA = d, dB = d + 1) with packed FADD2, dB in the low
+// half.  The right windows of the pair overlap: dB's is dA's shifted one column left, so with
+// wv[r][j] = right pixel at column (X - dB - 2) + j, j = 0..5, tap c of dA reads wv[c+1] and
+// tap c of dB reads wv[c].  Pairing tap j of dB with tap j-1 of dA gives both halves the SAME
+// right pixel (a broadcast operand) and a constant left operand ap[r][j-1] =
+// (L[r][j] - mL, L[r][j-1] - mL), hoisted over all d (matchers.cpp:503).  Per window row: one
+// scalar step (dB tap 0), four packed steps, one scalar step (dA tap 4) -- each half still adds
+// its 25 taps in row-major order, every operation an IEEE fp32 add: bit-exact.
+struct Phase1Out {
+  int min_cen;
+  float min_ncc, min_sad;
+  int dmax_sad;
+};
 
-// ---- one CTA per tile ------------------------------------------------------------------------
+// Per-thread state of the phase-1 loop: staging pointers (they fall by two columns per disparity
+// pair), the register-resident right window and the running minima.
+template <class L>
+struct P1State {
+  const float* rfp;    // column (X - dB - 2) of the pair's second disparity
+  const uint4* dscp;
+  const uint4* sttp;
+  const float2* mnp;
+  float wv[5][6];      // sliding 5x6 right window; logical column j lives in wv[.][(j - 2*s) mod 6]
+  int min_cen;
+  float min_ncc, min_sad;
+};
+
+// One BLOCK of phase 1 = three disparity pairs (the rotation period of the window registers).
+// kClean: every disparity of the block has all three costs for this thread's pixel and the block is
+// whole (no dummy steps): no validity selects, one basic block.  Otherwise validity is checked per
+// voxel and `steps` (<= 3) pairs are walked.
+template <class L, bool kClean>
+__device__ __forceinline__ void p1_block(P1State<L>& st, int dblk, int steps, int D, const f32x2 (&ap)[5][4],
+                                         const float (&l3)[3][3], const uint4& ld, const RStat& ls, int dmax_cen,
+                                         int dmax_ncc, int dmax_sad, float* s_par, uint8_t* s_cen, int px) {
+  constexpr int PS = L::PS;
+#pragma unroll
+  for (int sI = 0; sI < 3; ++sI) {
+#define WV(r, j) st.wv[r][((j) + 12 - 2 * sI) % 6]
+    if (!kClean && sI > 0 && sI >= steps) break;
+    const int dA = dblk + 2 * sI, dB = dA + 1;
+    const uint4 rdA = st.dscp[0], rdB = st.dscp[-1];
+    const uint4 rsA_raw = st.sttp[0], rsB_raw = st.sttp[-1];
+    const RStat rsA = *reinterpret_cast<const RStat*>(&rsA_raw);
+    const RStat rsB = *reinterpret_cast<const RStat*>(&rsB_raw);
+    const float2 mBA = *st.mnp;   // (mean at X - dB, mean at X - dA)
+
+    // census: Hamming distance of the packed codes (matchers.cpp:323-337)
+    const int cenA = __popc(ld.x ^ rdA.x) + __popc(ld.y ^ rdA.y) + __popc(ld.z ^ rdA.z) + __popc(ld.w ^ rdA.w);
+    const int cenB = __popc(ld.x ^ rdB.x) + __popc(ld.y ^ rdB.y) + __popc(ld.z ^ rdB.z) + __popc(ld.w ^ rdB.w);
+    const int cen_bA = (kClean || dA <= dmax_cen) ? cenA : 255;
+    const int cen_bB = (kClean || dB <= dmax_cen) ? cenB : 255;
+
+    // NCC: P exact in fp32 (< 2^24); scaling in fp64 left to right (matchers.cpp:200-201)
+    float PA = 0.f, PB = 0.f;
+#pragma unroll
+    for (int r = 0; r < 3; ++r)
+#pragma unroll
+      for (int c = 0; c < 3; ++c) {
+        PA = __fmaf_rn(l3[r][c], WV(r + 1, c + 2), PA);
+        PB = __fmaf_rn(l3[r][c], WV(r + 1, c + 1), PB);
+      }
+    const float numA = __fmaf_rn(9.0f, PA, -__fmul_rn(ls.A, rsA.A));
+    const float numB = __fmaf_rn(9.0f, PB, -__fmul_rn(ls.A, rsB.A));
+    float nccA = (float)__dmul_rn(__dmul_rn(-(double)numA, ls.C), rsA.C);
+    float nccB = (float)__dmul_rn(__dmul_rn(-(double)numB, ls.C), rsB.C);
+    nccA = (fabsf(nccA) <= 3.0e38f) ? nccA : 1.0f;  // either C was inf (flat window), :196,204
+    nccB = (fabsf(nccB) <= 3.0e38f) ? nccB : 1.0f;
+    nccA = (kClean || dA <= dmax_ncc) ? nccA : kFill;
+    nccB = (kClean || dB <= dmax_ncc) ? nccB : kFill;
+
+    // ZSAD: 25 taps row-major, ((L - mL) - R) + mR, sequential fp32 (matchers.cpp:499-506)
+    const f32x2 m2 = pk2(mBA.x, mBA.y);
+    f32x2 acc = pk2(0.f, 0.f);   // (dB, dA)
+#pragma unroll
+    for (int r = 0; r < 5; ++r) {
+      float a_first, a_last, dum, accA, accB;
+      upk2(ap[r][0], dum, a_first);   // L[r][0] - mL
+      upk2(ap[r][3], a_last, dum);    // L[r][4] - mL
+      upk2(acc, accB, accA);
+      accB = __fadd_rn(accB, fabsf(__fadd_rn(__fsub_rn(a_first, WV(r, 0)), mBA.x)));   // dB tap 0
+      acc = pk2(accB, accA);
+#pragma unroll
+      for (int j = 1; j <= 4; ++j) {
+        const float wj = WV(r, j);
+        const f32x2 u = add2(sub2(ap[r][j - 1], pk2(wj, wj)), m2);                    // dB tap j, dA tap j-1
+        acc = add2(acc, abs2(u));
+      }
+      upk2(acc, accB, accA);
+      accA = __fadd_rn(accA, fabsf(__fadd_rn(__fsub_rn(a_last, WV(r, 5)), mBA.y)));    // dA tap 4
+      acc = pk2(accB, accA);
+    }
+    float zA, zB;
+    upk2(acc, zB, zA);
+    zA = (kClean || dA <= dmax_sad) ? zA : kFill;
+    zB = (kClean || dB <= dmax_sad) ? zB : kFill;
+
+    const int dsA = kClean ? dA : min(dA, D);   // dummy steps (d >= D) park into the scratch plane
+    const int dsB = kClean ? dB : min(dB, D);
+    s_cen[dsA * kTile + px] = (uint8_t)cen_bA;
+    s_cen[dsB * kTile + px] = (uint8_t)cen_bB;
+    s_par[dsA * kTile + px] = nccA;
+    s_par[dsB * kTile + px] = nccB;
+    s_par[2 * PS + dsA * kTile + px] = zA;
+    s_par[2 * PS + dsB * kTile + px] = zB;
+    st.min_cen = min(st.min_cen, min(cen_bA, cen_bB));
+    st.min_ncc = fminf(st.min_ncc, fminf(nccA, nccB));
+    st.min_sad = fminf(st.min_sad, fminf(zA, zB));
+    // slide the window two columns left: the next pair's new columns 0 and 1
+    st.rfp -= 2; st.dscp -= 2; st.sttp -= 2; st.mnp -= 1;
+#pragma unroll
+    for (int r = 0; r < 5; ++r) {
+      st.wv[r][(0 + 12 - 2 * (sI + 1)) % 6] = st.rfp[r * L::RWF];
+      st.wv[r][(1 + 12 - 2 * (sI + 1)) % 6] = st.rfp[r * L::RWF + 1];
+    }
+#undef WV
+  }
+}
+
+// ---- phase 1 of a tile for one thread = (pixel px, d-group [d_lo, d_lo + DC)) ---------------
+// Per (pixel, d): census popcount, NCC (9 fp32 products of exact integers, fp64 scaling), ZSAD
+// over a register-resident right window that slides with d; raw costs are parked in shared
+// memory (ncc -> plane 0, zsad -> plane 2, census byte); running minima are returned.
+//
+// ZSAD evaluates disparities in pairs (dA = d, dB = d + 1) with packed FADD2, dB in the low
+// half.  The right windows of the pair overlap: dB's is dA's shifted one column left, so with
+// wv[r][j] = right pixel at column (X - dB - 2) + j, j = 0..5, tap c of dA reads wv[c+1] and
+// tap c of dB reads wv[c].  Pairing tap j of dB with tap j-1 of dA gives both halves the SAME
+// right pixel (a broadcast operand) and a constant left operand ap[r][j-1] =
+// (L[r][j] - mL, L[r][j-1] - mL), hoisted over all d (matchers.cpp:503).  Per window row: one
+// scalar step (dB tap 0), four packed steps, one scalar step (dA tap 4) -- each half still adds
+// its 25 taps in row-major order, every operation an IEEE fp32 add: bit-exact.
+//
+// The d-group is walked in BLOCKS of six disparities.  A cost exists for d <= dmax (the window must
+// fit left of x - d), so per warp (ballot, no divergence) a block is: clean -- every lane has every
+// cost: the body without validity selects; past the valid range of every lane (monotone in d:
+// nothing after it has a cost either) -- fill is parked and NOTHING is computed; else the generic
+// body.  Tiles near the left image border spend about half their blocks in the second kind.
+template <class L>
+__device__ __forceinline__ Phase1Out phase1_tile(const FusedArgs& a, const TileId& t, const unsigned char* stage,
+                                                 float* s_par, uint8_t* s_cen, const LeftRegs& lr, int px,
+                                                 int d_lo) {
+  constexpr int PS = L::PS;
+  const FusedGeom& g = a.g;
+  const int D = g.D, H = g.H, W = g.W;
+  const int X = t.x0 + px + g.bwl;        // bordered image column of this thread's pixel
+  const int Y = t.y + g.bh;               // bordered image row
+  const uint4 ld = lr.desc;
+  const RStat ls = *reinterpret_cast<const RStat*>(&lr.stat);
+  f32x2 ap[5][4];   // ap[r][j-1] for j = 1..4
+  float l3[3][3];   // centre 3x3 of L as float for NCC
+#pragma unroll
+  for (int r = 0; r < 5; ++r) {
+    float av[5];
+#pragma unroll
+    for (int c = 0; c < 5; ++c) {
+      av[c] = __fsub_rn(lr.px[r][c], ls.mean);
+      if (r >= 1 && r <= 3 && c >= 1 && c <= 3) l3[r - 1][c - 1] = lr.px[r][c];
+    }
+#pragma unroll
+    for (int j = 1; j <= 4; ++j) ap[r][j - 1] = pk2(av[j], av[j - 1]);
+  }
+  // validity: cost(y,x,d) exists iff the window origin is inside and x - wc >= d (and d < D)
+  // (dmax_* are local to the launch: disparity d0 + d of the image is step d here)
+  const int dmax_cen = min(D - 1, ((Y >= 5 && Y < H - 6 && X >= 5 && X < W - 6) ? X - 5 : -1) - g.d0);
+  const int dmax_ncc = min(D - 1, ((Y >= 1 && Y < H - 2 && X >= 1 && X < W - 2) ? X - 1 : -1) - g.d0);
+  const int dmax_sad = min(D - 1, ((Y >= 2 && Y < H - 3 && X >= 2 && X < W - 3) ? X - 2 : -1) - g.d0);
+
+  const uint4* s_desc = reinterpret_cast<const uint4*>(stage + L::st_desc);
+  const uint4* s_stat = reinterpret_cast<const uint4*>(stage + L::st_stat);
+  const float* s_rf = reinterpret_cast<const float*>(stage + L::st_rf);
+  // shared index of right column X - d is ir = px + L::kSl + (D-1) - d; falls by one per step
+  const int XbaseP = t.x0 + g.bwl - (g.d0 + D - 1) - L::kSl + g.padL;
+  const int shift = (XbaseP - 2) & 3;
+  const int ir0 = px + L::kSl + (D - 1) - d_lo;
+  P1State<L> st;
+  st.rfp = s_rf + shift + ir0 - 1;
+  st.dscp = s_desc + ir0;
+  st.sttp = s_stat + ir0;
+  // (mean[ir-1], mean[ir]) as one 8-byte aligned load: the plain copy when its float index is
+  // even, else the copy shifted by one (staged from the aligned column XbaseP & ~3)
+  const int im = (XbaseP & 3) + ir0 - 1;
+  st.mnp = reinterpret_cast<const float2*>(
+      reinterpret_cast<const float*>(stage + L::st_mean) + ((im & 1) ? L::RWF + im + 1 : im));
+#pragma unroll
+  for (int r = 0; r < 5; ++r)
+#pragma unroll
+    for (int j = 0; j < 6; ++j) st.wv[r][j] = st.rfp[r * L::RWF + j];
+  st.min_cen = 255;
+  st.min_ncc = kFill;
+  st.min_sad = kFill;
+
+  for (int base = 0; base < a.DC; base += 6) {
+    const int dblk = d_lo + base;
+    const int left = a.DC - base;                        // disparities left in the d-group (even)
+    const bool clean = (left >= 6) && (dblk + 5 <= dmax_cen);   // census has the tightest bound
+    const bool none = dblk > dmax_ncc;                          // NCC the loosest
+    if (__all_sync(0xffffffffu, clean)) {
+      p1_block<L, true>(st, dblk, 3, D, ap, l3, ld, ls, dmax_cen, dmax_ncc, dmax_sad, s_par, s_cen, px);
+    } else if (__all_sync(0xffffffffu, none)) {
+      const int nd = min(left, 6);
+#pragma unroll
+      for (int k = 0; k < 6; ++k) {
+        if (k >= nd) break;
+        const int ds = min(dblk + k, D);
+        s_cen[ds * kTile + px] = 255;
+        s_par[ds * kTile + px] = kFill;
+        s_par[2 * PS + ds * kTile + px] = kFill;
+      }
+      st.rfp -= 6; st.dscp -= 6; st.sttp -= 6; st.mnp -= 3;   // (the window registers are never used again)
+    } else {
+      p1_block<L, false>(st, dblk, min(left, 6) >> 1, D, ap, l3, ld, ls, dmax_cen, dmax_ncc, dmax_sad, s_par, s_cen, px);
+    }
+  }
+  Phase1Out o;
+  o.min_cen = st.min_cen;
+  o.min_ncc = st.min_ncc;
+  o.min_sad = st.min_sad;
+  o.dmax_sad = dmax_sad;
+  return o;
+}
+
+// After phase 1 and once the tile's SAD-of-Sobel costs have landed in plane 1: this thread's
+// disparities outside the valid region become fill; per-group minima go to s_red[grp][4][32].
+template <class L>
+__device__ __forceinline__ void finish_phase1(float* s_par, float* s_red, const Phase1Out& o, int px, int grp,
+                                              int d_lo, int d_end) {
+  float min_sob = kFill;
+  float* sp = s_par + L::PS + d_lo * kTile + px;
+#pragma unroll 4
+  for (int d = d_lo; d < d_end; ++d, sp += kTile) {
+    float v = *sp;
+    if (d > o.dmax_sad) {
+      v = kFill;
+      *sp = v;
+    }
+    min_sob = fminf(min_sob, v);
+  }
+  s_red[(grp * 4 + 0) * kTile + px] = (o.min_cen == 255) ? kFill : (float)o.min_cen;
+  s_red[(grp * 4 + 1) * kTile + px] = o.min_ncc;
+  s_red[(grp * 4 + 2) * kTile + px] = min_sob;
+  s_red[(grp * 4 + 3) * kTile + px] = o.min_sad;
+}
+
+// Stores four channel planes' 4-pixel row segments: 128-bit streaming stores when the rows are
+// 16 B aligned and the quad is fully inside the image (kVec), guarded scalars otherwise.
+template <bool kVec>
+__device__ __forceinline__ void store_quads(float* o, size_t chan, int nlive, const float4& c0, const float4& c1,
+                                            const float4& c2, const float4& c3) {
+  if (kVec) {
+    st_stream4(o, c0);
+    st_stream4(o + chan, c1);
+    st_stream4(o + 2 * chan, c2);
+    st_stream4(o + 3 * chan, c3);
+  } else {
+    const float cc[4][4] = {{c0.x, c0.y, c0.z, c0.w}, {c1.x, c1.y, c1.z, c1.w}, {c2.x, c2.y, c2.z, c2.w},
+                            {c3.x, c3.y, c3.z, c3.w}};
+#pragma unroll
+    for (int ch = 0; ch < 4; ++ch)
+#pragma unroll
+      for (int i = 0; i < 4; ++i)
+        if (i < nlive) st_stream(o + ch * chan + i, cc[ch][i]);
+  }
+}
+
+// ---- back half of a tile: channels 0-3, AML denominators, channels 4-7 --------------------
+// Channels 0-3 (cbmv_generator.py:283-287) for thread = (pixel quad q4, disparities d0, d0+16, ... < d1):
+// normalised costs stored as 128-bit row segments.
+template <bool kVec>
+__device__ __forceinline__ void store_ch03(const float* s_par, const uint8_t* s_cen, const float* s_lutn, int PS,
+                                           int q4, int d0, int d1, float* orow, size_t plane, size_t chan,
+                                           int nlive) {
+#pragma unroll 1
+  for (int d = d0; d < d1; d += 16) {
+    const float* e0 = s_par + d * kTile + q4;
+    const uchar4 cb = *reinterpret_cast<const uchar4*>(s_cen + d * kTile + q4);
+    const float4 v1 = *reinterpret_cast<const float4*>(e0);
+    const float4 v2 = *reinterpret_cast<const float4*>(e0 + PS);
+    const float4 v3 = *reinterpret_cast<const float4*>(e0 + 2 * PS);
+    const float4 c0 = make_float4(s_lutn[cb.x], s_lutn[cb.y], s_lutn[cb.z], s_lutn[cb.w]);
+    const float4 c1 = make_float4(normalise_cost(v1.x, 1), normalise_cost(v1.y, 1), normalise_cost(v1.z, 1),
+                                  normalise_cost(v1.w, 1));
+    const float4 c2 = make_float4(normalise_cost(v2.x, 2), normalise_cost(v2.y, 2), normalise_cost(v2.z, 2),
+                                  normalise_cost(v2.w, 2));
+    const float4 c3 = make_float4(normalise_cost(v3.x, 3), normalise_cost(v3.y, 3), normalise_cost(v3.z, 3),
+                                  normalise_cost(v3.w, 3));
+    store_quads<kVec>(orow + (size_t)d * plane, chan, nlive, c0, c1, c2, c3);
+  }
+}
+
+// Channels 4-7 = exp(-(c-m)^2/sigma) / den for thread = (pixel quad q4, disparities dl, dl+32, ...),
+// exponentials recomputed from the parked costs, 128-bit row segments.
+template <bool kVec>
+__device__ __forceinline__ void phase3_quads(const float* s_par, const uint8_t* s_cen, const float* s_lut,
+                                             const float* s_min, const float* s_inv, int PS, int q4, int dl, int D,
+                                             float* arow, size_t plane, size_t chan, int nlive, float k1, float k2) {
+  const float4 m_cen4 = *reinterpret_cast<const float4*>(s_min + q4);
+  const float4 m1 = *reinterpret_cast<const float4*>(s_min + kTile + q4);
+  const float4 m2 = *reinterpret_cast<const float4*>(s_min + 2 * kTile + q4);
+  const float4 m3 = *reinterpret_cast<const float4*>(s_min + 3 * kTile + q4);
+  const float4 i0 = *reinterpret_cast<const float4*>(s_inv + q4);
+  const float4 i1 = *reinterpret_cast<const float4*>(s_inv + kTile + q4);
+  const float4 i2 = *reinterpret_cast<const float4*>(s_inv + 2 * kTile + q4);
+  const float4 i3 = *reinterpret_cast<const float4*>(s_inv + 3 * kTile + q4);
+  const int mcx = (m_cen4.x == kFill) ? 0 : (int)m_cen4.x, mcy = (m_cen4.y == kFill) ? 0 : (int)m_cen4.y;
+  const int mcz = (m_cen4.z == kFill) ? 0 : (int)m_cen4.z, mcw = (m_cen4.w == kFill) ? 0 : (int)m_cen4.w;
+#pragma unroll 1
+  for (int d = dl; d < D; d += 32) {
+    const float* e0 = s_par + d * kTile + q4;
+    const uchar4 cb = *reinterpret_cast<const uchar4*>(s_cen + d * kTile + q4);
+    const float4 v1 = *reinterpret_cast<const float4*>(e0);
+    const float4 v2 = *reinterpret_cast<const float4*>(e0 + PS);
+    const float4 v3 = *reinterpret_cast<const float4*>(e0 + 2 * PS);
+    const float4 a0 = make_float4(s_lut[min((int)cb.x - mcx, 127)] * i0.x, s_lut[min((int)cb.y - mcy, 127)] * i0.y,
+                                  s_lut[min((int)cb.z - mcz, 127)] * i0.z, s_lut[min((int)cb.w - mcw, 127)] * i0.w);
+    const float4 a1 = make_float4(aml_e(v1.x, m1.x, k1) * i1.x, aml_e(v1.y, m1.y, k1) * i1.y,
+                                  aml_e(v1.z, m1.z, k1) * i1.z, aml_e(v1.w, m1.w, k1) * i1.w);
+    const float4 a2 = make_float4(aml_e(v2.x, m2.x, k2) * i2.x, aml_e(v2.y, m2.y, k2) * i2.y,
+                                  aml_e(v2.z, m2.z, k2) * i2.z, aml_e(v2.w, m2.w, k2) * i2.w);
+    const float4 a3 = make_float4(aml_e(v3.x, m3.x, k2) * i3.x, aml_e(v3.y, m3.y, k2) * i3.y,
+                                  aml_e(v3.z, m3.z, k2) * i3.z, aml_e(v3.w, m3.w, k2) * i3.w);
+    store_quads<kVec>(arow + (size_t)d * plane, chan, nlive, a0, a1, a2, a3);
+  }
+}
+
+// Phases 2 and 3 for the 256 threads of a CTA.  s_red holds the per-group minima of phase 1.
+//   phase 2 (warp-specialised; both halves only READ the parked costs, so they overlap without
+//            hazards):
+//     warps 0-3  one thread per (pixel, matcher): AML denominator, exponentials evaluated on
+//                the fly and added in the reference's order -- sequential fp32 over d
+//                (featextract.cpp:444-447; a tree sum is measurably outside the 2e-6 bound);
+//     warps 4-7  thread = (pixel quad, d): channels 0-3 normalised and stored.
+//   phase 3      all warps: channels 4-7.
+// Measured alternatives: writing each exponential back in place and adding
+// the denominators in a phase of their own (fewer instructions, 6 % slower: the chain is
+// exposed), the same behind a progress counter (slower still: the chain warps spin), handing
+// part of the channel 0-3 stores to the chain warps statically or through a work counter (no
+// gain: the halves are already balanced), a warp-specialised persistent producer/consumer
+// kernel (15 % slower).
+template <class L>
+__device__ __forceinline__ void tile_back_half(const FusedArgs& a, const TileId& t, int tid, const float* s_par,
+                                               const uint8_t* s_cen, const float* s_red, float* s_min,
+                                               float* s_inv, const float* s_lut, const float* s_lutn) {
+  constexpr int PS = L::PS;
+  const FusedGeom& g = a.g;
+  const int D = g.D;
+  const size_t plane = (size_t)g.h * g.w;
+  const size_t chan = plane * D;
+  if (tid < 4 * kTile) {  // minima across the d-groups
+    float v = kFill;
+#pragma unroll
+    for (int gq = 0; gq < kGroups; ++gq) v = fminf(v, s_red[gq * 4 * kTile + tid]);
+    s_min[tid] = v;
+  }
+  __syncthreads();
+  const int warp = tid >> 5, lane = tid & 31;
+  const int q4 = (tid & 7) * 4;
+  // 128-bit stores need 16-byte aligned rows
+  const bool vec_ok = ((g.w & 3) == 0) && ((reinterpret_cast<uintptr_t>(a.out) & 15) == 0);
+  float* orow = a.out + (size_t)t.n * a.out_channels * chan + (size_t)t.y * g.w + (t.x0 + q4);
+  const int nlive = min(4, g.w - (t.x0 + q4));  // live pixels of this quad (<= 0: none)
+  const bool vec = vec_ok && nlive == 4;
+  if (warp < 4) {
+    const float mm = s_min[warp * kTile + lane];
+    float den = 0.f;
+    const int Dfull = D & ~7;   // groups of 8 without guards, then a guarded tail
+    if (warp == 0) {
+      const int mc = (mm == kFill) ? 0 : (int)mm;
+      const uint8_t* c = s_cen + lane;
+      for (int d0 = 0; d0 < Dfull; d0 += 8, c += 8 * kTile) {
+        float ev[8];
+#pragma unroll
+        for (int j = 0; j < 8; ++j) ev[j] = s_lut[min((int)c[j * kTile] - mc, 127)];
+#pragma unroll
+        for (int j = 0; j < 8; ++j) den = __fadd_rn(den, ev[j]);
+      }
+      for (int d = Dfull; d < D; ++d, c += kTile) den = __fadd_rn(den, s_lut[min((int)c[0] - mc, 127)]);
+    } else {
+      const float kq = (warp == 1) ? a.k_ncc : a.k_sad;
+      const float* e = s_par + (warp - 1) * PS + lane;
+      for (int d0 = 0; d0 < Dfull; d0 += 8, e += 8 * kTile) {
+        float ev[8];
+#pragma unroll
+        for (int j = 0; j < 8; ++j) ev[j] = aml_e(e[j * kTile], mm, kq);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) den = __fadd_rn(den, ev[j]);
+      }
+      for (int d = Dfull; d < D; ++d, e += kTile) den = __fadd_rn(den, aml_e(e[0], mm, kq));
+    }
+    s_inv[warp * kTile + lane] = (mm == kFill) ? 0.f : 1.0f / den;
+  }
+  else {
+    // channels 0-3: thread = (pixel quad, d), 16 disparities per sweep of the four warps
+    if (vec) store_ch03<true>(s_par, s_cen, s_lutn, PS, q4, (tid >> 3) - 16, D, orow, plane, chan, nlive);
+    else store_ch03<false>(s_par, s_cen, s_lutn, PS, q4, (tid >> 3) - 16, D, orow, plane, chan, nlive);
+  }
+  __syncthreads();
+  const int dl = tid >> 3;
+  if (vec) phase3_quads<true>(s_par, s_cen, s_lut, s_min, s_inv, PS, q4, dl, D, orow + 4 * chan, plane, chan, nlive, a.k_ncc, a.k_sad);
+  else phase3_quads<false>(s_par, s_cen, s_lut, s_min, s_inv, PS, q4, dl, D, orow + 4 * chan, plane, chan, nlive, a.k_ncc, a.k_sad);
+}
+
+// Back half of a tile for DISPARITY-SLAB SHARDING (phase A of slab.cu): the AML
+// minimum and denominator need the other ranks' disparities, so the tile only stores channels
+// 0-3, parks the RAW costs in channels 4-7 (census as float; fill where there is no cost) and
+// writes the slab's per-pixel minima; slab_phase_b/c finish the job after the all-reduces.
+template <class L>
+__device__ __forceinline__ void tile_slab_a(const FusedArgs& a, const TileId& t, int tid, const float* s_par,
+                                            const uint8_t* s_cen, const float* s_red, const float* s_lutn) {
+  constexpr int PS = L::PS;
+  const FusedGeom& g = a.g;
+  const int D = g.D;
+  const size_t plane = (size_t)g.h * g.w;
+  const size_t chan = plane * a.out_D;
+  if (tid < 4 * kTile) {  // minima across the d-groups -> global
+    float v = kFill;
+#pragma unroll
+    for (int gq = 0; gq < kGroups; ++gq) v = fminf(v, s_red[gq * 4 * kTile + tid]);
+    const int m = tid / kTile, x = t.x0 + tid % kTile;
+    if (x < g.w) {
+      float* mp = a.mins + (((size_t)t.n * a.mins_planes + m) * g.h + t.y) * g.w + x;
+      *mp = a.mins_accumulate ? fminf(*mp, v) : v;
+    }
+  }
+  const int q4 = (tid & 7) * 4;
+  const int dl = tid >> 3;
+  const bool vec_ok = ((g.w & 3) == 0) && ((reinterpret_cast<uintptr_t>(a.out) & 15) == 0);
+  float* orow = a.out + (size_t)t.n * a.out_channels * chan + (size_t)t.y * g.w + (t.x0 + q4);
+  const int nlive = min(4, g.w - (t.x0 + q4));
+  const bool vec = vec_ok && nlive == 4;
+#pragma unroll 2
+  for (int d = dl; d < D; d += 32) {
+    const float* e0 = s_par + d * kTile + q4;
+    const uchar4 cb = *reinterpret_cast<const uchar4*>(s_cen + d * kTile + q4);
+    const float4 v1 = *reinterpret_cast<const float4*>(e0);
+    const float4 v2 = *reinterpret_cast<const float4*>(e0 + PS);
+    const float4 v3 = *reinterpret_cast<const float4*>(e0 + 2 * PS);
+    const float4 v0 = make_float4(cb.x == 255 ? kFill : (float)cb.x, cb.y == 255 ? kFill : (float)cb.y,
+                                  cb.z == 255 ? kFill : (float)cb.z, cb.w == 255 ? kFill : (float)cb.w);
+    const float4 c0 = make_float4(s_lutn[cb.x], s_lutn[cb.y], s_lutn[cb.z], s_lutn[cb.w]);
+    const float4 c1 = make_float4(normalise_cost(v1.x, 1), normalise_cost(v1.y, 1), normalise_cost(v1.z, 1),
+                                  normalise_cost(v1.w, 1));
+    const float4 c2 = make_float4(normalise_cost(v2.x, 2), normalise_cost(v2.y, 2), normalise_cost(v2.z, 2),
+                                  normalise_cost(v2.w, 2));
+    const float4 c3 = make_float4(normalise_cost(v3.x, 3), normalise_cost(v3.y, 3), normalise_cost(v3.z, 3),
+                                  normalise_cost(v3.w, 3));
+    float* o = orow + (size_t)(a.out_d0 + d) * plane;
+    if (vec) {
+      store_quads<true>(o, chan, nlive, c0, c1, c2, c3);
+      // parked raw costs are read again by slab_phase_b/c: plain (cached) stores
+      *reinterpret_cast<float4*>(o + 4 * chan) = v0;
+      *reinterpret_cast<float4*>(o + 5 * chan) = v1;
+      *reinterpret_cast<float4*>(o + 6 * chan) = v2;
+      *reinterpret_cast<float4*>(o + 7 * chan) = v3;
+    } else {
+      store_quads<false>(o, chan, nlive, c0, c1, c2, c3);
+      const float rr[4][4] = {{v0.x, v0.y, v0.z, v0.w}, {v1.x, v1.y, v1.z, v1.w}, {v2.x, v2.y, v2.z, v2.w},
+                              {v3.x, v3.y, v3.z, v3.w}};
+#pragma unroll
+      for (int ch = 0; ch < 4; ++ch)
+#pragma unroll
+        for (int i = 0; i < 4; ++i)
+          if (i < nlive) o[(4 + ch) * chan + i] = rr[ch][i];
+    }
+  }
+}
+
+// ---- one CTA per tile (fallback: any D up to 448, with or without TMA) ----------------------
+//   phase 1  thread = (pixel, d-group): 8 warps split D (phase1_tile)
+//   phase 2  thread = (pixel quad, d): channels 0-3 stored, costs -> AML exponentials in place
+//   phase 2b one thread per (pixel, matcher): sequential denominator
+//   phase 3  thread = (pixel quad, d): channels 4-7 = exponential / den
 // kTma: right-image rows and the SAD-of-Sobel tile arrive through cp.async.bulk /
 // cp.async.bulk.tensor (D <= 256: box limit); otherwise through LDGSTS.  The tensor copy's
 // inner coordinate must be a multiple of 16 bytes (measured: anything else raises an
@@ -323,90 +940,58 @@ __device__ __forceinline__ void stage_sad_tma(const FusedArgs& a, const CUtensor
 template <int DMAX, bool kTma, bool kSlabA>
 __global__ void __launch_bounds__(256, 2)
 ms_fused_kernel(const FusedArgs a, const __grid_constant__ CUtensorMap sad_map) {
-  using L = Lay3<DMAX>;
+  using L = Lay<DMAX, kSlack>;
   constexpr int NT = 256;
   constexpr int PS = L::PS;
   extern __shared__ __align__(128) unsigned char smem_raw[];  // TMA destinations need 128 B
   const FusedGeom& g = a.g;
   const int D = g.D;
   unsigned long long* s_bar = reinterpret_cast<unsigned long long*>(smem_raw + L::off_bar);  // [0] rows, [1] sadsob tile
-  float* s_red = reinterpret_cast<float*>(smem_raw + L::off_red);    // [16][4][32]
+  float* s_red = reinterpret_cast<float*>(smem_raw + L::off_red);    // [8][4][32]
   float* s_min = reinterpret_cast<float*>(smem_raw + L::off_min);
   float* s_inv = reinterpret_cast<float*>(smem_raw + L::off_inv);
+  float* s_lut = reinterpret_cast<float*>(smem_raw + L::off_lut);
+  float* s_lutn = reinterpret_cast<float*>(smem_raw + L::off_lutn);
   float* s_par = reinterpret_cast<float*>(smem_raw + L::off_par);    // [3][DS][32]
   uint8_t* s_cen = smem_raw + L::off_par + L::pk_cen;                // [DS][32]
   const int tid = threadIdx.x;
+  const int px = tid % kTile;             // phase 1: this thread's pixel ...
+  const int grp = tid / kTile;            // ... and d-group
   const TileId t = decode_tile(blockIdx.x, a);
-  const StageGeo sg = stage_geo(a, t);
+  const int d_lo = grp * a.DC;
+  const int d_end = min(D, d_lo + a.DC);  // real disparities of this thread: [d_lo, d_end)
   if (kTma) {
     if (tid == 0) {
       mbar_init(&s_bar[0], 1);
       mbar_init(&s_bar[1], 1);
       mbar_init_fence();
       // rows first: phase 1 waits for them; the SAD-of-Sobel box is only needed after phase 1
-      stage_rows<L, true, NT>(a, t, sg, smem_raw, &s_bar[0]);
+      stage_rows_tma<L>(a, t, smem_raw, &s_bar[0]);
       stage_sad_tma(a, &sad_map, t, s_par + PS, &s_bar[1]);
     }
   } else {
-    // the tile's SAD-of-Sobel costs: async global -> parked plane 1
+    // sadsob costs of this thread's own disparities: async global -> parked plane 1
     const size_t splane = (size_t)g.H * g.Ws;
-    const float* src = a.sadsob + ((size_t)t.n * D * g.H + (t.y + g.bh)) * g.Ws + (t.x0 + g.bwl + g.sxo);
-    for (int i = tid; i < D * kTile; i += NT) cp_async4(s_par + PS + i, src + (size_t)(i >> 5) * splane + (i & 31));
-    stage_rows<L, false, NT>(a, t, sg, smem_raw, nullptr);
+    const float* src = a.sadsob + ((size_t)t.n * D * g.H + (t.y + g.bh)) * g.Ws + (t.x0 + px + g.bwl + g.sxo) +
+                       (size_t)d_lo * splane;
+    float* dst = s_par + PS + d_lo * kTile + px;
+    for (int d = d_lo; d < d_end; ++d, src += splane, dst += kTile) cp_async4(dst, src);
+    stage_right<L, NT>(a, t, smem_raw);
   }
-
-  P1Ctx c;
-  c.pr = tid & 15;
-  const int grp = tid >> 4;
-  Left2 lr;
-  load_left2(a, t, c.pr, lr);
-  c.dA0 = grp * a.DC;
-  c.nsteps = a.DC;
-  c.cx0 = t.x0 + 2 * c.pr + g.bwl + g.padL - (g.d0 + c.dA0);
-  // largest local disparity with a cost, per pixel and matcher (-1 - d0 or less: none):
-  // cost(y,x,d) exists iff the window origin is inside the image and x - wc >= d (and d < D)
-  int dmaxCN[4], dmaxZA, dmaxZB;   // CN: census A, census B, ncc A, ncc B
-  {
-    const int H = g.H, W = g.W;
-    const int XA = t.x0 + 2 * c.pr + g.bwl, XB = XA + 1, Y = t.y + g.bh;
-    const bool yc = (Y >= 5 && Y < H - 6), yn = (Y >= 1 && Y < H - 2), yz = (Y >= 2 && Y < H - 3);
-    dmaxCN[0] = min(D - 1, ((yc && XA >= 5 && XA < W - 6) ? XA - 5 : -1) - g.d0);
-    dmaxCN[1] = min(D - 1, ((yc && XB >= 5 && XB < W - 6) ? XB - 5 : -1) - g.d0);
-    dmaxCN[2] = min(D - 1, ((yn && XA >= 1 && XA < W - 2) ? XA - 1 : -1) - g.d0);
-    dmaxCN[3] = min(D - 1, ((yn && XB >= 1 && XB < W - 2) ? XB - 1 : -1) - g.d0);
-    dmaxZA = min(D - 1, ((yz && XA >= 2 && XA < W - 3) ? XA - 2 : -1) - g.d0);
-    dmaxZB = min(D - 1, ((yz && XB >= 2 && XB < W - 3) ? XB - 2 : -1) - g.d0);
-  }
+  if (tid < 128) s_lut[tid] = __ldg(a.luts + tid);
+  s_lutn[tid] = __ldg(a.luts + 128 + tid);
+  LeftRegs lr;
+  load_left(a, t, px, lr);
   if (!kTma) cp_async_wait_all();
-  __syncthreads();                       // barrier init (and LDGSTS data) visible to everyone
+  __syncthreads();                       // barrier init, LUTs (and LDGSTS data) visible to everyone
   if (kTma) mbar_wait(&s_bar[0], 0);
 
-  P1Min mn;
-  mn.cenA = 255; mn.cenB = 255;
-  mn.nccA = kFill; mn.nccB = kFill; mn.sadA = kFill; mn.sadB = kFill;
-  if (grp == 0)
-    p1_extra_b0<L>(a, t, smem_raw, sg, s_par, s_cen, lr, c.pr, c.cx0 + 1, dmaxCN[1], dmaxCN[3], dmaxZB, mn);
-  p1_zsad<L>(a, smem_raw, sg, s_par, lr, c, dmaxZA, dmaxZB, mn);
-  p1_census_ncc<L>(a, t, smem_raw, sg, s_par, s_cen, c, dmaxCN, mn);
-  {
-    float* r0 = s_red + grp * 4 * kTile + 2 * c.pr;
-    r0[0] = (mn.cenA == 255) ? kFill : (float)mn.cenA;
-    r0[1] = (mn.cenB == 255) ? kFill : (float)mn.cenB;
-    r0[kTile] = mn.nccA;
-    r0[kTile + 1] = mn.nccB;
-    r0[3 * kTile] = mn.sadA;
-    r0[3 * kTile + 1] = mn.sadB;
-  }
-  if (kTma) mbar_wait(&s_bar[1], 0);   // (LDGSTS: landed before the first barrier)
-  {
-    const int Xl = t.x0 + g.bwl, Yr = t.y + g.bh;   // every pixel of the tile has a SAD-of-Sobel cost at every disparity?
-    const bool sob_all = (Xl - 2 >= g.d0 + D - 1) && (Xl + kTile - 1 < g.W - 3) && (Yr >= 2) && (Yr < g.H - 3);
-    sob_finish<L>(a, t, s_par, s_red, tid, sob_all);
-  }
+  const Phase1Out o = phase1_tile<L>(a, t, smem_raw, s_par, s_cen, lr, px, d_lo);
+  if (kTma) mbar_wait(&s_bar[1], 0);
+  finish_phase1<L>(s_par, s_red, o, px, grp, d_lo, d_end);
   __syncthreads();
-  if (kSlabA) tile_slab_a<L>(a, t, tid, s_par, s_cen, s_red);
-  else if (a.xflags & 2) tile_back_half_otf<L>(a, t, tid, s_par, s_cen, s_red, s_min, s_inv);
-  else tile_back_half<L>(a, t, tid, s_par, s_cen, reinterpret_cast<float*>(smem_raw + L::off_cene), s_red, s_min, s_inv);
+  if (kSlabA) tile_slab_a<L>(a, t, tid, s_par, s_cen, s_red, s_lutn);
+  else tile_back_half<L>(a, t, tid, s_par, s_cen, s_red, s_min, s_inv, s_lut, s_lutn);
 }
 
 // Optional per-kernel timing (msn_profile_enable): CUDA events recorded on the launch
@@ -448,7 +1033,7 @@ static bool tma_disabled() {
   return e && e[0] == '1';
 }
 
-// 3-D tensor map over the SAD-of-Sobel scratch [N*D][H][Ws], box 32 x 1 x D (cached)
+// 3-D tensor map over the SAD-of-Sobel scratch [N*D][H][Ws], box 32 x 1 x D (encoded once per scratch)
 static bool sad_tensor_map(const FusedGeom& g, int H, int N, const float* base, CUtensorMap* out) {
   const MapKey key{base, g.Ws, H, N * g.D, g.D};
   {
@@ -473,6 +1058,27 @@ static bool sad_tensor_map(const FusedGeom& g, int H, int N, const float* base, 
   if (g_maps.size() >= 64) g_maps.erase(g_maps.begin());
   g_maps.emplace_back(key, *out);
   return true;
+}
+
+// One launch of an instantiation; the dynamic shared-memory opt-in is set once per instantiation
+// and device, not per launch.
+template <int DMAX, bool kTma, bool kSlabA>
+static int launch_inst(const FusedArgs& a, const CUtensorMap& map, long long tiles, cudaStream_t s) {
+  auto kern = ms_fused_kernel<DMAX, kTma, kSlabA>;
+  constexpr size_t smem = Lay<DMAX, kSlack>::bytes;
+  static std::mutex mu;
+  static unsigned long long done_mask = 0;   // bit per device ordinal (< 64)
+  int dev = 0;
+  MSN_CUDA_OK(cudaGetDevice(&dev));
+  {
+    std::lock_guard<std::mutex> lk(mu);
+    if (dev >= 64 || !((done_mask >> dev) & 1ull)) {
+      MSN_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+      if (dev < 64) done_mask |= 1ull << dev;
+    }
+  }
+  kern<<<(unsigned)tiles, 256, smem, s>>>(a, map);
+  return 0;
 }
 
 int profile_enable(int on) {
@@ -519,27 +1125,6 @@ size_t fused_workspace_bytes(int N, int H, int W, int Dn, const msn_ms_params* p
   return ws.total;
 }
 
-// One launch of an instantiation; the dynamic shared-memory opt-in is set once per instantiation
-// and device.
-template <int DMAX, bool kTma, bool kSlabA>
-static int launch_inst(const FusedArgs& a, const CUtensorMap& map, long long tiles, cudaStream_t s) {
-  auto kern = ms_fused_kernel<DMAX, kTma, kSlabA>;
-  constexpr size_t smem = Lay3<DMAX>::bytes;
-  static std::mutex mu;
-  static unsigned long long done_mask = 0;   // bit per device ordinal (< 64)
-  int dev = 0;
-  MSN_CUDA_OK(cudaGetDevice(&dev));
-  {
-    std::lock_guard<std::mutex> lk(mu);
-    if (dev >= 64 || !((done_mask >> dev) & 1ull)) {
-      MSN_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-      if (dev < 64) done_mask |= 1ull << dev;
-    }
-  }
-  kern<<<(unsigned)tiles, 256, smem, s>>>(a, map);
-  return 0;
-}
-
 // d_mins == nullptr: the whole feature volume (p describes all disparities).  Otherwise phase A of
 // the slab path for disparities [p->d_begin, p->d_begin + p->d_count): the output tensor holds
 // out_D disparities per channel and the slab starts at out_d0 in it (a rank's own slab tensor:
@@ -568,8 +1153,9 @@ int launch_ms_fused(const uint8_t* d_left, const uint8_t* d_right, int N, int H,
   for (int i = 0; i < 2; ++i)
     MSN_CUDA_OK(cudaMemsetAsync(ws.sob[i], 0, (size_t)N * (H + kSadRowPad) * g.Ws * sizeof(float), s));
   dim3 pgrid(div_up(g.Wp, 128), g.Hp, 2 * N);
-  ms_prep_kernel<<<pgrid, 128, 0, s>>>(d_left, d_right, g, ws.desc[0], ws.desc[1], ws.statL, ws.aR, ws.cR, ws.meanR,
-                                       ws.fimg[0], ws.fimg[1], ws.sob[0], ws.sob[1]);
+  ms_prep_kernel<<<pgrid, 128, 0, s>>>(d_left, d_right, g, ws.desc[0], ws.desc[1], ws.stat[0], ws.stat[1],
+                                       ws.fimg[0], ws.fimg[1], ws.sob[0], ws.sob[1], ws.meanR[0], ws.meanR[1],
+                                       ws.luts, aml_scale(p->cens_sigma));
   MSN_LAUNCH_OK();
   if (prof) MSN_CUDA_OK(cudaEventRecord(rec.ev[1], s));
   if (launch_sadsob5_padded(ws.sob[0], ws.sob[1], N, H, W, g.D, g.d0, ws.sadsob + g.sxo, ws.sad_ws, s)) return 1;
@@ -578,9 +1164,10 @@ int launch_ms_fused(const uint8_t* d_left, const uint8_t* d_right, int N, int H,
   FusedArgs a;
   a.g = g;
   a.descL = ws.desc[0]; a.descR = ws.desc[1];
-  a.statL = ws.statL;
-  a.aR = ws.aR; a.cR = ws.cR; a.meanR = ws.meanR;
+  a.statL = ws.stat[0]; a.statR = ws.stat[1];
   a.fL = ws.fimg[0]; a.fR = ws.fimg[1];
+  a.meanR0 = ws.meanR[0]; a.meanR1 = ws.meanR[1];
+  a.luts = ws.luts;
   a.sadsob = ws.sadsob;
   a.out = d_out;
   a.mins = d_mins;
@@ -592,16 +1179,14 @@ int launch_ms_fused(const uint8_t* d_left, const uint8_t* d_right, int N, int H,
   a.k_cen = aml_scale(p->cens_sigma);
   a.k_ncc = aml_scale(p->ncc_sigma);
   a.k_sad = aml_scale(p->sad_sigma);
-  a.neg_zero = -0.0f;
-  { const char* e = getenv("MSNETS_X"); a.xflags = e ? atoi(e) : 0; }
   a.tiles_x = (g.w + kTile - 1) / kTile;
-  a.DC = (g.D + kG2 - 1) / kG2;
   const long long tiles = (long long)N * g.h * a.tiles_x;
   MSN_REQUIRE(tiles <= 2147483647LL, "ms_features: too many tiles for one launch");
   CUtensorMap sad_map;
   memset(&sad_map, 0, sizeof(sad_map));
   bool use_tma = g.D <= 256 && !tma_disabled();
   if (use_tma) use_tma = sad_tensor_map(g, H, N, ws.sadsob, &sad_map);
+  a.DC = 2 * (((g.D + kGroups - 1) / kGroups + 1) / 2);   // phase 1 walks disparity pairs
 #define MSN_FUSED_LAUNCH(DMAX, TMA)                                                \
   {                                                                                \
     if (d_mins) { if (launch_inst<DMAX, TMA, true>(a, sad_map, tiles, s)) return 1; } \
@@ -616,7 +1201,8 @@ int launch_ms_fused(const uint8_t* d_left, const uint8_t* d_right, int N, int H,
   MSN_FUSED_CASE(128)
   MSN_FUSED_CASE(192)
   MSN_FUSED_CASE(256)
-  MSN_FUSED_CASE(384) { return fail("ms_features: D=%d exceeds the fused kernel's limit", g.D); }
+  MSN_FUSED_CASE(384)
+  MSN_FUSED_CASE(448) { return fail("ms_features: D=%d exceeds the fused kernel's limit", g.D); }
 #undef MSN_FUSED_CASE
 #undef MSN_FUSED_LAUNCH
   MSN_LAUNCH_OK();
