@@ -12,10 +12,11 @@ step   : ours      -> prep + sadsob scan + fused volume kernel + soft-argmin ker
                       cuda:<local rank>, inputs resident in HBM (value), and the same
                       through the public API with pinned host buffers, H2D of the pairs
                       and D2H of the disparities inside the timed region (e2e).
-         reference -> the reference's own CPU implementation (oracle/_ref = unmodified
-                      matchers.cpp / featextract.cpp compiled in the build container,
-                      driven by the NumPy glue restated in oracle/ms_oracle.py) on a
-                      bounded sample of the same workload, host cores only.
+         reference -> the reference's own CPU implementation: its UNMODIFIED NumPy glue
+                      (cbmv_generator.py get_costs + extract_features_left) over oracle/_ref =
+                      the unmodified matchers.cpp / featextract.cpp compiled in the build
+                      container with THREADS_NUM_USED = the host's core count; one full
+                      540x960 pair per step (a row band only if the run would not fit).
 Multi-GPU: one process per GPU (torchrun), pairs are independent -> weak scaling, no
 data-path collective; time = max over ranks.
 Prints ONE JSON line on rank 0.
@@ -272,7 +273,7 @@ def run_ours(args):
     }
     cpu, dropin = None, None
     if world == 1:
-        cpu = cpu_baseline_sample(budget_s=20.0)
+        cpu = cpu_baseline_sample(budget_s=30.0)
         # drop-in NumPy API, one pair, full 3.2 GB volume copied back to the host
         t0 = time.time()
         vol = cbmv.ms_features(host_l[0, 0].numpy(), host_r[0, 0].numpy(), D_MAX, board_h=BORDER,
@@ -307,19 +308,73 @@ def run_ours(args):
 
 
 # ---------------------------------------------------------------- reference --
-def _reference_modules():
+class _Timed(object):
+    """Proxy of a native module that accumulates the wall time spent inside its functions (the
+    native-only subtotal BASELINE.md section 3 asks for: get_costs' matchers + 4x extract_likelihood,
+    as opposed to the NumPy glue around them)."""
+
+    def __init__(self, mod, acc):
+        self._mod, self._acc = mod, acc
+
+    def __getattr__(self, name):
+        fn = getattr(self._mod, name)
+        if not callable(fn):
+            return fn
+
+        def timed(*a, **k):
+            t0 = time.perf_counter()
+            try:
+                return fn(*a, **k)
+            finally:
+                self._acc[0] += time.perf_counter() - t0
+        return timed
+
+
+def _reference_arm(variant=None):
+    """-> dict(gen, kind, what, cores, native_s): the reference's own CPU path.  `gen` is the UNMODIFIED
+    src/dataloader/cbmv_generator.py (get_costs :27, extract_features_left :258) bound to oracle/_ref = the
+    unmodified matchers.cpp / featextract.cpp compiled in the build container; when neither travels, the
+    restated oracle (kind "port")."""
     from oracle import ms_oracle as O
-    ref = O.load_ref()
+    from oracle import ref_glue
+    ref = None
+    for v in ([variant] if variant else ["avx2_nproc", "avx2", "sse41"]):
+        if v in ("avx2", "avx2_nproc") and not O.cpu_has_avx2():
+            continue
+        ref = O.load_ref(v)
+        if ref is not None:
+            break
+    native = [0.0]
     if ref is not None:
-        return O, ref[0], ref[1], "reference", "oracle/_ref (%s build of the unmodified matchers.cpp/featextract.cpp)" % ref[2]
+        mtc, fte = _Timed(ref[0], native), _Timed(ref[1], native)
+        gen = ref_glue.load_generator(mtc, fte)
+        cores = int(ref[0].initthreads())
+        if gen is not None:
+            return {"gen": gen, "kind": "reference", "cores": cores, "native_s": native,
+                    "what": "unmodified cbmv_generator.py (get_costs + extract_features_left) over oracle/_ref/%s "
+                            "(unmodified matchers.cpp/featextract.cpp, %d OpenMP threads)" % (ref[2], cores)}
+
+        class G(object):   # the glue file did not travel: restated glue over the reference C++
+            get_costs = staticmethod(lambda *a: O.get_costs(*a, mtc=mtc, fte=fte))
+            extract_features_left = staticmethod(lambda *c: O.extract_features_left(*c, fte=fte))
+        return {"gen": G, "kind": "reference", "cores": cores, "native_s": native,
+                "what": "oracle/_ref/%s driven by the restated NumPy glue" % ref[2]}
     O.lib()
-    return O, O.MTC, O.FTE, "port", "oracle/libms_oracle.so (C restatement)"
+
+    class P(object):
+        get_costs = staticmethod(lambda *a: O.get_costs(*a))
+        extract_features_left = staticmethod(lambda *c: O.extract_features_left(*c))
+    return {"gen": P, "kind": "port", "cores": 1, "native_s": native, "what": "oracle/libms_oracle.so (C restatement)"}
 
 
-def _cpu_step(O, mtc, fte, L, R, logits):
+def _cpu_step(arm, L, R, logits):
+    """One reference step on the host: MS features of one pair + softmax/regression of one logit volume."""
     import torch
     import torch.nn.functional as F
-    f = O.ms_features(L, R, D_MAX, board_h=BORDER, board_w_left=BORDER, board_w_right=BORDER, mtc=mtc, fte=fte)
+    gen = arm["gen"]
+    costs = gen.get_costs(L, R, D_MAX, 11, 3, 5, 5, BORDER, BORDER, BORDER)      # cbmv_generator.py:826-834
+    f = gen.extract_features_left(*costs)                                         # :838
+    del costs
     x = torch.from_numpy(logits)
     prob = F.softmax(x, 1)                                    # gcnet_3dcnn.py:127
     d = torch.arange(D_MAX, dtype=torch.float32).view(1, D_MAX, 1, 1)
@@ -336,60 +391,79 @@ def _sample_inputs(rows):
     return L, R, logits
 
 
-def cpu_baseline_sample(budget_s=20.0):
-    """Times the CPU path on a bounded sample: a horizontal band of one 540x960 pair,
-    rows chosen from a 32-row calibration so the sample costs about budget_s."""
-    O, mtc, fte, kind, what = _reference_modules()
-    cores = int(mtc.initthreads()) if hasattr(mtc, "initthreads") else 1
+def _rows_for_budget(arm, steps, budget_s):
+    """Full 540-row frames when `steps` of them fit the budget (calibrated on a 32-row band), else the
+    largest band that does."""
     L, R, lg = _sample_inputs(32)
+    _cpu_step(arm, L, R, lg)
     t0 = time.time()
-    _cpu_step(O, mtc, fte, L, R, lg)
+    _cpu_step(arm, L, R, lg)
     t32 = max(time.time() - t0, 1e-3)
-    rows = int(max(32, min(H_IMG, 32 * budget_s / t32)))
-    L, R, lg = _sample_inputs(rows)
-    t0 = time.time()
-    _cpu_step(O, mtc, fte, L, R, lg)
-    dt = time.time() - t0
-    frac = rows / float(H_IMG)
-    return {"value": round(frac / dt, 4), "unit": "pairs/s", "cores": cores, "kind": kind,
-            "sample": "%d of 540 rows (x960, D=192) of one pair: get_costs + extract_features_left + "
-                      "softmax/regression via %s; %d OpenMP threads (THREADS_NUM_USED, paramSetting.hpp:11); "
-                      "%d host cpus" % (rows, what, cores, os.cpu_count() or 0),
-            "seconds": round(dt, 2)}
+    per_row = t32 / 32.0
+    if steps * per_row * H_IMG * 1.15 <= budget_s:
+        return H_IMG
+    return int(max(32, min(H_IMG, budget_s / max(steps, 1) / per_row)))
+
+
+def cpu_baseline_sample(budget_s=30.0):
+    """The reference's CPU path timed beside the GPU run (rank 0, N = 1): one full 540x960 frame per
+    build when it fits the budget -- the host-core-count build (value) and the shipped 8-thread build."""
+    out = None
+    for variant, key in (("avx2_nproc", None), ("avx2", "threads_as_shipped")):
+        arm = _reference_arm(variant)
+        if arm["kind"] != "reference" and key is not None:
+            continue
+        rows = _rows_for_budget(arm, 1, budget_s / 2)
+        L, R, lg = _sample_inputs(rows)
+        arm["native_s"][0] = 0.0
+        t0 = time.time()
+        _cpu_step(arm, L, R, lg)
+        dt = time.time() - t0
+        frac = rows / float(H_IMG)
+        rec = {"value": round(frac / dt, 4), "unit": "pairs/s", "cores": arm["cores"], "kind": arm["kind"],
+               "sample": "%d of 540 rows (x960, D=192) of one pair, one step: %s + softmax/regression; %d host cpus"
+                         % (rows, arm["what"], os.cpu_count() or 0),
+               "seconds": round(dt, 2), "native_only_seconds": round(arm["native_s"][0], 2),
+               "native_only_pairs_per_s": round(frac / max(arm["native_s"][0], 1e-9), 4)}
+        if key is None:
+            out = rec
+        elif out is not None:
+            out[key] = rec
+        if arm["kind"] != "reference":
+            break
+    return out
 
 
 def run_reference(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
-    O, mtc, fte, kind, what = _reference_modules()
-    cores = int(mtc.initthreads()) if hasattr(mtc, "initthreads") else 1
+    arm = _reference_arm()
     total = args.steps + args.warmup
-    L, R, lg = _sample_inputs(32)
-    t0 = time.time()
-    _cpu_step(O, mtc, fte, L, R, lg)
-    t32 = max(time.time() - t0, 1e-3)
-    per_step = 150.0 / max(total, 1)
-    rows = int(max(32, min(H_IMG, 32 * per_step / t32)))
+    rows = _rows_for_budget(arm, total, 420.0)
     L, R, lg = _sample_inputs(rows)
     for _ in range(args.warmup):
-        _cpu_step(O, mtc, fte, L, R, lg)
+        _cpu_step(arm, L, R, lg)
+    arm["native_s"][0] = 0.0
     t0 = time.time()
     for _ in range(args.steps):
-        _cpu_step(O, mtc, fte, L, R, lg)
+        _cpu_step(arm, L, R, lg)
     dt = time.time() - t0
     frac = rows / float(H_IMG)
     value = args.steps * frac / dt
-    sample = ("each step = %d of 540 rows (x960, D=192) of one pair through get_costs + extract_features_left "
-              "+ softmax/regression; %s; %d OpenMP threads; %d host cpus" % (rows, what, cores, os.cpu_count() or 0))
+    sample = ("each step = %d of 540 rows (x960, D=192) of one pair through %s + softmax/regression; %d host cpus"
+              % (rows, arm["what"], os.cpu_count() or 0))
     line = {
         "impl": "reference", "metric": METRIC, "value": round(value, 4), "unit": "pairs/s",
         "n_gpus": int(os.environ.get("WORLD_SIZE", "1")), "steps": args.steps, "warmup": args.warmup,
         "ms_per_step": round(1e3 * dt / args.steps, 2), "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": {"workload": "configs[1]: SceneFlow-shaped 540x960 D=192 MS features + soft-argmin, CPU reference",
-                   "sample_rows": rows},
-        "cpu_baseline": {"value": round(value, 4), "unit": "pairs/s", "cores": cores, "kind": kind, "sample": sample},
+        "config": {"workload": "configs[1]: SceneFlow-shaped 540x960 D=192 MS features + soft-argmin, CPU reference, "
+                               "one pair per step (%s)" % ("full frames" if rows == H_IMG else "%d-row band" % rows),
+                   "sample_rows": rows, "pairs_per_step": 1},
+        "cpu_baseline": {"value": round(value, 4), "unit": "pairs/s", "cores": arm["cores"], "kind": arm["kind"],
+                         "sample": sample,
+                         "native_only_pairs_per_s": round(args.steps * frac / max(arm["native_s"][0], 1e-9), 4)},
         "e2e": {"value": round(value, 4), "unit": "pairs/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }

@@ -164,6 +164,11 @@ MSN_API int msn_soft_argmin_dev(const float* d_logits, int N, int D, int H, int 
  * normalised -> sum_d d * prob_d. */
 MSN_API int msn_expect_disp_dev(const float* d_prob, int N, int D, int H, int W, float* d_disp, void* stream);
 MSN_API int msn_soft_argmin_host(const float* logits, int N, int D, int H, int W, float* disp);
+/* Backward of msn_soft_argmin_dev for training through the regression (the reference back-propagates
+ * through F.softmax + disparityregression, gcnet_3dcnn.py:127-141):
+ * grad_logits[n][d][p] = grad_disp[n][p] * softmax(logits)[n][d][p] * (d - disp[n][p]). */
+MSN_API int msn_soft_argmin_backward_dev(const float* d_logits, const float* d_disp, const float* d_grad_disp, int N,
+                                 int D, int H, int W, float* d_grad_logits, void* stream);
 /* Slab-sharded soft-argmin: per-pixel partial (max, sum e, sum d*e) over the
  * local D slab whose first disparity is d_begin -> [N][3][H][W]; merged by
  * msn_soft_argmin_merge_dev over `parts` gathered partials [parts][N][3][H][W]. */

@@ -34,16 +34,43 @@ def __getattr__(name):
 
 def install_dropin():
     """Makes `import src.cpp.lib.libmatchers as mtc` / `...libfeatextract as fte`
-    (cbmv_generator.py:16-17) resolve to the CUDA-backed mirrors."""
+    (cbmv_generator.py:16-17) resolve to the CUDA-backed mirrors.
+
+    The reference's own `src` / `src.cpp` packages are left alone: when they are importable (its
+    checkout is on sys.path, as it is when main_msnet.py runs) they are imported for real, so that
+    `from src.dataloader import cbmv_generator` keeps working afterwards; only the two native
+    modules under `src.cpp.lib` -- the directory the reference's CMake build writes its .so files to
+    (CMakeLists.txt:73) -- are replaced.  Packages that do not exist are stubbed."""
+    import importlib
+    import importlib.util
     import types
     from . import libfeatextract, libmatchers
+
+    def ensure(name):
+        if name in sys.modules:
+            return sys.modules[name]
+        try:
+            spec = importlib.util.find_spec(name)
+        except (ImportError, ValueError, AttributeError):
+            spec = None
+        if spec is not None:
+            try:
+                return importlib.import_module(name)
+            except Exception:   # e.g. a src/cpp/lib/__init__.py that needs the Boost-built .so files
+                sys.modules.pop(name, None)
+        m = types.ModuleType(name)
+        m.__path__ = []
+        sys.modules[name] = m
+        parent, _, leaf = name.rpartition(".")
+        if parent:
+            setattr(sys.modules[parent], leaf, m)
+        return m
+
     for pkg in ("src", "src.cpp", "src.cpp.lib"):
-        if pkg not in sys.modules:
-            m = types.ModuleType(pkg)
-            m.__path__ = []
-            sys.modules[pkg] = m
+        ensure(pkg)
+    lib = sys.modules["src.cpp.lib"]
     sys.modules["src.cpp.lib.libmatchers"] = libmatchers
     sys.modules["src.cpp.lib.libfeatextract"] = libfeatextract
-    sys.modules["src.cpp.lib"].libmatchers = libmatchers
-    sys.modules["src.cpp.lib"].libfeatextract = libfeatextract
+    lib.libmatchers = libmatchers
+    lib.libfeatextract = libfeatextract
     return libmatchers, libfeatextract

@@ -68,6 +68,7 @@ _SIGNATURES = {
     "msn_soft_argmin_dev": (c_int, [_P, c_int, c_int, c_int, c_int, _P, _P]),
     "msn_expect_disp_dev": (c_int, [_P, c_int, c_int, c_int, c_int, _P, _P]),
     "msn_soft_argmin_host": (c_int, [_P, c_int, c_int, c_int, c_int, _P]),
+    "msn_soft_argmin_backward_dev": (c_int, [_P, _P, _P, c_int, c_int, c_int, c_int, _P, _P]),
     "msn_soft_argmin_partial_dev": (c_int, [_P, c_int, c_int, c_int, c_int, c_int, _P, _P]),
     "msn_soft_argmin_merge_dev": (c_int, [_P, c_int, c_int, c_int, c_int, _P, _P]),
     "msn_wta_dev": (c_int, [_P, c_ll, c_int, c_int, _P, _P, _P, _P]),

@@ -681,6 +681,12 @@ int msn_expect_disp_dev(const float* d_prob, int N, int D, int H, int W, float* 
   return launch_soft_argmin(d_prob, N, D, H, W, 0, 2, d_disp, as_stream(stream));
 }
 
+int msn_soft_argmin_backward_dev(const float* d_logits, const float* d_disp, const float* d_grad_disp, int N, int D,
+                                 int H, int W, float* d_grad_logits, void* stream) {
+  MSN_REQUIRE(d_logits && d_disp && d_grad_disp && d_grad_logits, "soft_argmin_backward: null pointer argument");
+  return launch_soft_argmin_bwd(d_logits, d_disp, d_grad_disp, N, D, H, W, d_grad_logits, as_stream(stream));
+}
+
 int msn_soft_argmin_host(const float* logits, int N, int D, int H, int W, float* disp) {
   MSN_REQUIRE(logits && disp, "soft_argmin: null pointer argument");
   MSN_REQUIRE(N >= 0 && D >= 1 && H >= 0 && W >= 0, "soft_argmin: bad shape");

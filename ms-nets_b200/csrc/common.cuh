@@ -117,6 +117,8 @@ int launch_slab_phase_c(float* out, const float* gmin, const float* gden, long l
 // regress.cu
 int launch_soft_argmin(const float* logits, int N, int D, int H, int W, int d_begin, int mode,
                        float* out, cudaStream_t s);
+int launch_soft_argmin_bwd(const float* logits, const float* disp, const float* gout, int N, int D, int H, int W,
+                           float* gin, cudaStream_t s);
 int launch_soft_argmin_merge(const float* parts, int P, int N, int H, int W, float* disp, cudaStream_t s);
 int launch_shift_volume(const float* fl, const float* fr, int N, int C, int H, int W, int D, bool diff,
                         float* vol, cudaStream_t s);

@@ -112,6 +112,44 @@ int launch_soft_argmin(const float* logits, int N, int D, int H, int W, int d_be
   return 0;
 }
 
+// Backward of soft-argmin for training (the reference trains through F.softmax + disparityregression,
+// gcnet_3dcnn.py:127-141; psmnet_3dcnn.py:149-176):  d disp / d x_d = p_d * (d - disp), so
+// grad_x[n][d][p] = grad_out[n][p] * p_d * (d - disp[n][p]).  Two sweeps over the column: (max, sum)
+// online, then the gradient; thread = pixel, coalesced along W.
+__global__ void __launch_bounds__(256)
+soft_argmin_bwd_kernel(const float* __restrict__ logits, const float* __restrict__ disp,
+                       const float* __restrict__ gout, int D, long long HW, float* __restrict__ gin) {
+  const long long p = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  const int n = blockIdx.y;
+  if (p >= HW) return;
+  const float* x = logits + (size_t)n * D * HW + p;
+  float m = -INFINITY, s = 0.f;
+  for (int d = 0; d < D; ++d) {
+    const float v = x[(size_t)d * HW];
+    const float cm = fmaxf(m, v);
+    s = s * ex2_approx((m - cm) * kLog2e) + ex2_approx((v - cm) * kLog2e);
+    m = cm;
+  }
+  const float go = gout[(size_t)n * HW + p] / s, dv = disp[(size_t)n * HW + p];
+  float* g = gin + (size_t)n * D * HW + p;
+  for (int d = 0; d < D; ++d) {
+    const float e = ex2_approx((x[(size_t)d * HW] - m) * kLog2e);
+    g[(size_t)d * HW] = go * e * ((float)d - dv);
+  }
+}
+
+int launch_soft_argmin_bwd(const float* logits, const float* disp, const float* gout, int N, int D, int H, int W,
+                           float* gin, cudaStream_t s) {
+  MSN_REQUIRE(N >= 0 && D >= 1 && H >= 0 && W >= 0, "soft_argmin_backward: bad shape");
+  const long long HW = (long long)H * W;
+  if (N == 0 || HW == 0) return 0;
+  MSN_REQUIRE(N <= 65535, "soft_argmin_backward: N=%d too large", N);
+  dim3 grid(div_up(HW, 256), N);
+  soft_argmin_bwd_kernel<<<grid, 256, 0, s>>>(logits, disp, gout, D, HW, gin);
+  MSN_LAUNCH_OK();
+  return 0;
+}
+
 // parts: [P][N][3][HW] gathered slab partials -> disp [N][HW]
 __global__ void soft_argmin_merge_kernel(const float* __restrict__ parts, int P, long long NHW3, long long HW,
                                          long long total, float* __restrict__ disp) {

@@ -9,8 +9,18 @@ writes the two extension modules into oracle/_ref/<variant>/:
     libmatchers.so      (census, nccNister, zsad, sobel, sadsob, initthreads)
     libfeatextract.so   (swap_axes, get_right_cost, extract_likelihood, ...)
 
-Variants: ``sse41`` (-msse4.1, runs on any x86-64 box) and ``avx2``
-(-march=core-avx2, the flag the reference's own CMakeLists.txt:11 uses).
+Variants: ``sse41`` (-msse4.1, runs on any x86-64 box), ``avx2`` (-march=core-avx2,
+the flag the reference's own CMakeLists.txt:11 uses) -- both with the shipped
+``THREADS_NUM_USED 8`` (paramSetting.hpp:11) -- and ``avx2_nproc``: the same
+sources with THREADS_NUM_USED re-defined, from the command line (``-include``;
+still zero edits), to a run-time value = the host's core count (or
+MSN_REF_THREADS), which is the second build BASELINE.md section 3 asks for.
+
+It also copies the reference's NumPy glue ``src/dataloader/cbmv_generator.py``
+VERBATIM into ``oracle/_ref/pyref/`` (git-ignored like the .so files; it travels
+to the GPU box with them) so that the CPU baseline and the drop-in tests drive
+the UNMODIFIED ``get_costs`` / ``extract_features_left`` there as well
+(oracle/ref_glue.py imports it).
 The reference's cmake build itself is unbuildable here (needs Boost 1.72
 python37/numpy37, OpenCV 3, PythonLibs 3.7) -- see DESIGN.md.
 
@@ -36,7 +46,13 @@ VARIANTS = {
     # reference flags: -std=c++14 -msse4.1 -march=core-avx2 -O3 -funroll-loops (+OpenMP)
     "sse41": ["-msse4.1", "-mssse3"],
     "avx2": ["-msse4.1", "-march=core-avx2"],
+    # paramSetting.hpp is `#pragma once`: including it first and re-defining the macro afterwards
+    # overrides THREADS_NUM_USED for the translation unit without touching any reference file
+    "avx2_nproc": ["-msse4.1", "-march=core-avx2", "-include",
+                   os.path.join(REF_ROOT, "src/cpp/paramSetting.hpp"), "-include",
+                   os.path.join(HERE, "shim", "threads_override.h")],
 }
+GLUE = ["src/dataloader/cbmv_generator.py"]   # copied verbatim into _ref/pyref/
 
 
 def _includes():
@@ -58,6 +74,13 @@ def build(force=False, verbose=True):
         return [d for d in (os.path.join(OUT_ROOT, v) for v in VARIANTS)
                 if all(os.path.isfile(os.path.join(d, m + ".so")) for m in SOURCES)]
     done = []
+    import shutil
+    for rel in GLUE:
+        src = os.path.join(REF_ROOT, rel)
+        dst = os.path.join(OUT_ROOT, "pyref", rel)
+        os.makedirs(os.path.dirname(dst), exist_ok=True)
+        if force or not os.path.isfile(dst) or os.path.getmtime(dst) < os.path.getmtime(src):
+            shutil.copyfile(src, dst)
     for variant, arch_flags in VARIANTS.items():
         out_dir = os.path.join(OUT_ROOT, variant)
         os.makedirs(out_dir, exist_ok=True)
