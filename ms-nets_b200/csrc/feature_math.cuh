@@ -11,8 +11,12 @@ namespace msn {
 // is bit-exact; /2 and /8192 are exact power-of-two scalings.  fill -> 1.0.
 __device__ __forceinline__ float normalise_cost(float v, int matcher) {
   if (matcher == 0) return __fdiv_rn(fminf(fmaxf(v, 0.f), 120.f), 120.f);
-  if (matcher == 1) return __fmul_rn(__fadd_rn(1.f, fminf(fmaxf(v, -1.f), 1.f)), 0.5f);
-  return __fmul_rn(fminf(fmaxf(v, 0.f), 8192.f), 1.0f / 8192.f);
+  // One instruction each (FFMA.SAT / FMUL.SAT), bit-identical to the clip-then-scale forms:
+  //  (1 + clip(v,-1,1)) * 0.5: for |v| <= 1 the sum 1 + v is rounded once and the halving is exact, so it
+  //  equals round(0.5 v + 0.5) = fma(v, 0.5, 0.5); outside [-1,1] both forms give exactly 0 or 1.
+  //  clip(v,0,8192) / 8192: the scaling by 2^-13 is exact, so clipping before or after it is the same.
+  if (matcher == 1) return __saturatef(__fmaf_rn(v, 0.5f, 0.5f));
+  return __saturatef(__fmul_rn(v, 1.0f / 8192.f));
 }
 
 __device__ __forceinline__ float ex2_approx(float x) {

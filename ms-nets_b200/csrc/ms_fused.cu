@@ -87,10 +87,12 @@ FusedGeom make_geom(int N, int H, int W, const msn_ms_params* p) {
 
 struct FusedWs {
   uint4* desc[2];
-  RStat* stat[2];
+  RStat* stat[2];   // [1] (right image) is only read through the planes below
   float* fimg[2];
   float* sob[2];
-  float* meanR[2]; // ZSAD means of the right image as plain floats; copy 1 is shifted by one column
+  float* meanR;    // right image: ZSAD window means as a plain float plane
+  float* AR;       // right image: NCC window sums A as a plain float plane
+  double* CR;      // right image: NCC 1/sqrt(9B - A^2) as a plain double plane
   float* luts;     // [128] census AML exponentials + [256] census byte -> channel 0
   float* sadsob;   // [N][D][H][W]
   void* sad_ws;
@@ -103,7 +105,9 @@ struct FusedWs {
     for (int i = 0; i < 2; ++i) stat[i] = (RStat*)take(np * sizeof(RStat));
     for (int i = 0; i < 2; ++i) fimg[i] = (float*)take(np * sizeof(float));
     for (int i = 0; i < 2; ++i) sob[i] = (float*)take((size_t)g.N * (g.H + kSadRowPad) * g.Ws * sizeof(float));  // zero padded
-    for (int i = 0; i < 2; ++i) meanR[i] = (float*)take((np + 16) * sizeof(float));
+    meanR = (float*)take((np + 16) * sizeof(float));
+    AR = (float*)take((np + 16) * sizeof(float));
+    CR = (double*)take((np + 16) * sizeof(double));
     luts = (float*)take(384 * sizeof(float));
     sadsob = (float*)take((size_t)g.N * g.D * g.H * g.Ws * sizeof(float) + 256);
     sad_ws = take(sadsob_workspace_bytes_n(g.N, g.H, g.W, g.D, kSadW));
@@ -117,8 +121,8 @@ __global__ void __launch_bounds__(128)
 ms_prep_kernel(const uint8_t* __restrict__ left, const uint8_t* __restrict__ right, FusedGeom g,
                uint4* __restrict__ descL, uint4* __restrict__ descR, RStat* __restrict__ statL,
                RStat* __restrict__ statR, float* __restrict__ fL, float* __restrict__ fR,
-               float* __restrict__ sobL, float* __restrict__ sobR, float* __restrict__ meanR0,
-               float* __restrict__ meanR1, float* __restrict__ luts, float k_cen) {
+               float* __restrict__ sobL, float* __restrict__ sobR, float* __restrict__ meanR,
+               float* __restrict__ AR, double* __restrict__ CR, float* __restrict__ luts, float k_cen) {
   if (blockIdx.x == 0 && blockIdx.y == 0 && blockIdx.z == 0) {
     // tables for the fused kernel: census AML exponentials exp(-(k^2)/sigma), k = 0..120, and the
     // channel-0 value k/120 of a parked census byte (a true IEEE division; 255 = no cost ->
@@ -199,10 +203,11 @@ ms_prep_kernel(const uint8_t* __restrict__ left, const uint8_t* __restrict__ rig
   (side ? statR : statL)[po] = st;
   (side ? fR : fL)[po] = pix;
   if (side) {
-    // (mean[x-1], mean[x]) must be ONE aligned 64-bit shared load in the fused kernel whatever
-    // the parity of x: the second copy holds the same row shifted right by one element
-    meanR0[po] = st.mean;
-    meanR1[po + 1] = st.mean;
+    // the fused kernel reads the right image's statistics lane-per-column: separate planes keep
+    // those shared loads free of bank conflicts (a 16-byte struct per column is a 4-way conflict)
+    meanR[po] = st.mean;
+    AR[po] = st.A;
+    CR[po] = st.C;
   }
 }
 
@@ -212,7 +217,8 @@ struct FusedArgs {
   const uint4 *descL, *descR;
   const RStat *statL, *statR;
   const float *fL, *fR;
-  const float *meanR0, *meanR1;  // right-image ZSAD means; meanR1[x] = mean[x-1]
+  const float *meanR, *AR;       // right-image ZSAD means / NCC window sums, float planes
+  const double* CR;              // right-image NCC scale, double plane
   const float* luts;    // [128] + [256], see ms_prep_kernel
   const float* sadsob;  // [N][D][H][Ws] (+ slack)
   float* out;           // [N][8][D][h][w]
@@ -237,10 +243,9 @@ struct StageLay {
   static constexpr int RW = (DMAX + kTile - 1 + SLACK + 3) & ~3;   // desc / stat entries
   static constexpr int RWF = RW + 8;                               // float row: halo 2+2, align shift <= 3
   static constexpr size_t st_desc = 0;                                   // [RW] uint4 census codes
-  static constexpr size_t st_stat = st_desc + (size_t)RW * 16;           // [RW] RStat
-  static constexpr size_t st_rf = st_stat + (size_t)RW * 16;             // [5][RWF] float pixel rows
-  static constexpr size_t st_mean = st_rf + (size_t)5 * RWF * 4;         // [2][RWF] ZSAD means, copy 1 shifted by one
-  static constexpr size_t st_bytes = (st_mean + (size_t)2 * RWF * 4 + 127) & ~(size_t)127;
+  static constexpr size_t st_c = st_desc + (size_t)RW * 16;              // [RW + 2] double NCC scale C (aligned start: shift <= 1)
+  static constexpr size_t st_rf = st_c + (size_t)(RW + 2) * 8;           // [7][RWF] float rows: 5 pixel rows, NCC sums A, ZSAD means
+  static constexpr size_t st_bytes = (st_rf + (size_t)7 * RWF * 4 + 127) & ~(size_t)127;
 };
 
 // Parking buffer of one tile: raw costs (later: AML exponentials) for every (d, pixel).
@@ -341,6 +346,20 @@ __device__ __forceinline__ f32x2 sub2(f32x2 a, f32x2 b) {
   asm("sub.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b));
   return r;
 }
+__device__ __forceinline__ f32x2 mul2(f32x2 a, f32x2 b) {
+  f32x2 r;
+  asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b));
+  return r;
+}
+// AML exponentials of two costs at once: 2^(-(c-m)^2 k) for (c.lo, m.lo) and (c.hi, m.hi); the packed
+// subtract / square / scale round exactly like aml_e's scalar ones (each half is an IEEE fp32 operation)
+__device__ __forceinline__ void aml_e2(f32x2 c, f32x2 m, f32x2 negk, float& e_lo, float& e_hi) {
+  const f32x2 t = sub2(c, m);
+  float a_lo, a_hi;
+  upk2(mul2(mul2(t, t), negk), a_lo, a_hi);
+  e_lo = ex2_approx(a_lo);
+  e_hi = ex2_approx(a_hi);
+}
 __device__ __forceinline__ f32x2 abs2(f32x2 v) {
   float lo, hi;
   upk2(v, lo, hi);
@@ -372,13 +391,15 @@ __device__ __forceinline__ void stage_right(const FusedArgs& a, const TileId& t,
   const int Yp = t.y + g.bh + kPadT;
   const size_t img_off = (size_t)t.n * g.img_px();
   const uint4* gd = a.descR + img_off + (size_t)Yp * g.Wp + XbaseP;
-  const uint4* gs = reinterpret_cast<const uint4*>(a.statR + img_off + (size_t)Yp * g.Wp + XbaseP);
   uint4* s_desc = reinterpret_cast<uint4*>(buf + L::st_desc);
-  uint4* s_stat = reinterpret_cast<uint4*>(buf + L::st_stat);
   float* s_rf = reinterpret_cast<float*>(buf + L::st_rf);
-  for (int i = threadIdx.x; i < RWn; i += NT) {
-    cp_async16(s_desc + i, gd + i);
-    cp_async16(s_stat + i, gs + i);
+  for (int i = threadIdx.x; i < RWn; i += NT) cp_async16(s_desc + i, gd + i);
+  {   // NCC scale C: doubles from the even column at or before XbaseP
+    const int cstart = XbaseP & ~1;
+    const int nc = (RWn + 1 + 1) >> 1;   // 16-byte groups
+    const double* gc = a.CR + img_off + (size_t)Yp * g.Wp + cstart;
+    double* s_c = reinterpret_cast<double*>(buf + L::st_c);
+    for (int i = threadIdx.x; i < nc; i += NT) cp_async16(s_c + 2 * i, gc + 2 * i);
   }
   const int fstart = (XbaseP - 2) & ~3;                 // aligned first float column
   const int nvec = (RWn + 4 + 3 + 3) >> 2;              // 16-byte groups per row (covers any shift)
@@ -386,12 +407,9 @@ __device__ __forceinline__ void stage_right(const FusedArgs& a, const TileId& t,
     const int r = i / nvec, v = i - r * nvec;
     cp_async16(s_rf + r * L::RWF + 4 * v, a.fR + img_off + (size_t)(Yp - 2 + r) * g.Wp + fstart + 4 * v);
   }
-  float* s_mean = reinterpret_cast<float*>(buf + L::st_mean);
-  const int mstart = XbaseP & ~3;
-  const int nvm = (RWn + 3 + 3) >> 2;
-  for (int i = threadIdx.x; i < 2 * nvm; i += NT) {
-    const int c = i / nvm, v = i - c * nvm;
-    cp_async16(s_mean + c * L::RWF + 4 * v, (c ? a.meanR1 : a.meanR0) + img_off + (size_t)Yp * g.Wp + mstart + 4 * v);
+  for (int i = threadIdx.x; i < 2 * nvec; i += NT) {   // rows 5 (A) and 6 (mean), same alignment as the pixel rows
+    const int c = i / nvec, v = i - c * nvec;
+    cp_async16(s_rf + (5 + c) * L::RWF + 4 * v, (c ? a.meanR : a.AR) + img_off + (size_t)Yp * g.Wp + fstart + 4 * v);
   }
 }
 
@@ -409,18 +427,17 @@ __device__ __forceinline__ void stage_rows_tma(const FusedArgs& a, const TileId&
   const int fstart = (XbaseP - 2) & ~3;
   const int nvec = (RWn + 4 + 3 + 3) >> 2;
   const unsigned row_bytes = (unsigned)RWn * 16u, frow_bytes = (unsigned)nvec * 16u;
-  const int mstart = XbaseP & ~3;
-  const unsigned mrow_bytes = (unsigned)((RWn + 3 + 3) >> 2) * 16u;
-  mbar_expect_tx(bar, 2u * row_bytes + 5u * frow_bytes + 2u * mrow_bytes);
+  const int cstart = XbaseP & ~1;
+  const unsigned crow_bytes = (unsigned)((RWn + 1 + 1) >> 1) * 16u;
+  mbar_expect_tx(bar, row_bytes + crow_bytes + 7u * frow_bytes);
   bulk_load(buf + L::st_desc, a.descR + img_off + (size_t)Yp * g.Wp + XbaseP, row_bytes, bar);
-  bulk_load(buf + L::st_stat, a.statR + img_off + (size_t)Yp * g.Wp + XbaseP, row_bytes, bar);
+  bulk_load(buf + L::st_c, a.CR + img_off + (size_t)Yp * g.Wp + cstart, crow_bytes, bar);
   float* s_rf = reinterpret_cast<float*>(buf + L::st_rf);
 #pragma unroll
   for (int r = 0; r < 5; ++r)
     bulk_load(s_rf + r * L::RWF, a.fR + img_off + (size_t)(Yp - 2 + r) * g.Wp + fstart, frow_bytes, bar);
-  float* s_mean = reinterpret_cast<float*>(buf + L::st_mean);
-  bulk_load(s_mean, a.meanR0 + img_off + (size_t)Yp * g.Wp + mstart, mrow_bytes, bar);
-  bulk_load(s_mean + L::RWF, a.meanR1 + img_off + (size_t)Yp * g.Wp + mstart, mrow_bytes, bar);
+  bulk_load(s_rf + 5 * L::RWF, a.AR + img_off + (size_t)Yp * g.Wp + fstart, frow_bytes, bar);
+  bulk_load(s_rf + 6 * L::RWF, a.meanR + img_off + (size_t)Yp * g.Wp + fstart, frow_bytes, bar);
 }
 
 // The tile's D x 32 SAD-of-Sobel costs: ONE 3-D tensor copy straight into parking plane 1.
@@ -480,8 +497,7 @@ template <class L>
 struct P1State {
   const float* rfp;    // column (X - dB - 2) of the pair's second disparity
   const uint4* dscp;
-  const uint4* sttp;
-  const float2* mnp;
+  const double* ccp;   // NCC scale C of column X - dA (C of X - dB is ccp[-1])
   float wv[5][6];      // sliding 5x6 right window; logical column j lives in wv[.][(j - 2*s) mod 6]
   int min_cen;
   float min_ncc, min_sad;
@@ -502,10 +518,11 @@ __device__ __forceinline__ void p1_block(P1State<L>& st, int dblk, int steps, in
     if (!kClean && sI > 0 && sI >= steps) break;
     const int dA = dblk + 2 * sI, dB = dA + 1;
     const uint4 rdA = st.dscp[0], rdB = st.dscp[-1];
-    const uint4 rsA_raw = st.sttp[0], rsB_raw = st.sttp[-1];
-    const RStat rsA = *reinterpret_cast<const RStat*>(&rsA_raw);
-    const RStat rsB = *reinterpret_cast<const RStat*>(&rsB_raw);
-    const float2 mBA = *st.mnp;   // (mean at X - dB, mean at X - dA)
+    // rfp[2] / rfp[3] are columns X - dB / X - dA: rows 5 and 6 hold the NCC sums and the ZSAD means
+    RStat rsA, rsB;
+    rsA.A = st.rfp[5 * L::RWF + 3]; rsB.A = st.rfp[5 * L::RWF + 2];
+    rsA.C = st.ccp[0]; rsB.C = st.ccp[-1];
+    const float2 mBA = make_float2(st.rfp[6 * L::RWF + 2], st.rfp[6 * L::RWF + 3]);   // (mean at X - dB, mean at X - dA)
 
     // census: Hamming distance of the packed codes (matchers.cpp:323-337)
     const int cenA = __popc(ld.x ^ rdA.x) + __popc(ld.y ^ rdA.y) + __popc(ld.z ^ rdA.z) + __popc(ld.w ^ rdA.w);
@@ -569,7 +586,7 @@ __device__ __forceinline__ void p1_block(P1State<L>& st, int dblk, int steps, in
     st.min_ncc = fminf(st.min_ncc, fminf(nccA, nccB));
     st.min_sad = fminf(st.min_sad, fminf(zA, zB));
     // slide the window two columns left: the next pair's new columns 0 and 1
-    st.rfp -= 2; st.dscp -= 2; st.sttp -= 2; st.mnp -= 1;
+    st.rfp -= 2; st.dscp -= 2; st.ccp -= 2;
 #pragma unroll
     for (int r = 0; r < 5; ++r) {
       st.wv[r][(0 + 12 - 2 * (sI + 1)) % 6] = st.rfp[r * L::RWF];
@@ -620,7 +637,11 @@ __device__ __forceinline__ Phase1Out phase1_tile(const FusedArgs& a, const TileI
       if (r >= 1 && r <= 3 && c >= 1 && c <= 3) l3[r - 1][c - 1] = lr.px[r][c];
     }
 #pragma unroll
-    for (int j = 1; j <= 4; ++j) ap[r][j - 1] = pk2(av[j], av[j - 1]);
+    for (int j = 1; j <= 4; ++j) {
+      // + (+0, +0) is value-preserving (a difference is never -0) and makes the pair a value of its
+      // own to ptxas, which otherwise shares the overlapping halves and rebuilds the pairs with MOVs
+      ap[r][j - 1] = add2(pk2(av[j], av[j - 1]), pk2(0.f, 0.f));
+    }
   }
   // validity: cost(y,x,d) exists iff the window origin is inside and x - wc >= d (and d < D)
   // (dmax_* are local to the launch: disparity d0 + d of the image is step d here)
@@ -629,7 +650,7 @@ __device__ __forceinline__ Phase1Out phase1_tile(const FusedArgs& a, const TileI
   const int dmax_sad = min(D - 1, ((Y >= 2 && Y < H - 3 && X >= 2 && X < W - 3) ? X - 2 : -1) - g.d0);
 
   const uint4* s_desc = reinterpret_cast<const uint4*>(stage + L::st_desc);
-  const uint4* s_stat = reinterpret_cast<const uint4*>(stage + L::st_stat);
+  const double* s_c = reinterpret_cast<const double*>(stage + L::st_c);
   const float* s_rf = reinterpret_cast<const float*>(stage + L::st_rf);
   // shared index of right column X - d is ir = px + L::kSl + (D-1) - d; falls by one per step
   const int XbaseP = t.x0 + g.bwl - (g.d0 + D - 1) - L::kSl + g.padL;
@@ -638,12 +659,7 @@ __device__ __forceinline__ Phase1Out phase1_tile(const FusedArgs& a, const TileI
   P1State<L> st;
   st.rfp = s_rf + shift + ir0 - 1;
   st.dscp = s_desc + ir0;
-  st.sttp = s_stat + ir0;
-  // (mean[ir-1], mean[ir]) as one 8-byte aligned load: the plain copy when its float index is
-  // even, else the copy shifted by one (staged from the aligned column XbaseP & ~3)
-  const int im = (XbaseP & 3) + ir0 - 1;
-  st.mnp = reinterpret_cast<const float2*>(
-      reinterpret_cast<const float*>(stage + L::st_mean) + ((im & 1) ? L::RWF + im + 1 : im));
+  st.ccp = s_c + (XbaseP & 1) + ir0;
 #pragma unroll
   for (int r = 0; r < 5; ++r)
 #pragma unroll
@@ -669,7 +685,7 @@ __device__ __forceinline__ Phase1Out phase1_tile(const FusedArgs& a, const TileI
         s_par[ds * kTile + px] = kFill;
         s_par[2 * PS + ds * kTile + px] = kFill;
       }
-      st.rfp -= 6; st.dscp -= 6; st.sttp -= 6; st.mnp -= 3;   // (the window registers are never used again)
+      st.rfp -= 6; st.dscp -= 6; st.ccp -= 6;   // (the window registers are never used again)
     } else {
       p1_block<L, false>(st, dblk, min(left, 6) >> 1, D, ap, l3, ld, ls, dmax_cen, dmax_ncc, dmax_sad, s_par, s_cen, px);
     }
@@ -702,6 +718,29 @@ __device__ __forceinline__ void finish_phase1(float* s_par, float* s_red, const 
   s_red[(grp * 4 + 1) * kTile + px] = o.min_ncc;
   s_red[(grp * 4 + 2) * kTile + px] = min_sob;
   s_red[(grp * 4 + 3) * kTile + px] = o.min_sad;
+}
+
+// Census channels from a parked census byte (255 = no cost).  kCenLut: through the two shared-memory
+// tables (random indices: ~2.2 wavefronts per load); otherwise by arithmetic:
+//  channel 0 = min(k,120)/120 as q = k*r, q' = fma(fma(-120, q, k), r, q) with r = fl(1/120): correctly
+//  rounded (= the true IEEE division NumPy does) for every k in 0..255, checked exhaustively in
+//  tests/test_host_math.py;  AML term = 2^(-(k-m)^2 k_cen), 0 for "no cost" -- what the table holds.
+#ifndef MSN_CEN_LUT
+#define MSN_CEN_LUT 0
+#endif
+constexpr bool kCenLut = MSN_CEN_LUT != 0;
+__device__ __forceinline__ float cen_ch0(int cb, const float* s_lutn) {
+  if (kCenLut) return s_lutn[cb];
+  const float k = (float)min(cb, 120);
+  const float r = 1.0f / 120.0f;
+  const float q = __fmul_rn(k, r);
+  return __fmaf_rn(__fmaf_rn(-120.0f, q, k), r, q);
+}
+__device__ __forceinline__ float cen_e(int cb, int mc, const float* s_lut, float k_cen) {
+  if (kCenLut) return s_lut[min(cb - mc, 127)];
+  const float t = (float)(cb - mc);
+  const float e = ex2_approx(-(t * t) * k_cen);
+  return (cb - mc > 120) ? 0.f : e;
 }
 
 // Stores four channel planes' 4-pixel row segments: 128-bit streaming stores when the rows are
@@ -739,7 +778,7 @@ __device__ __forceinline__ void store_ch03(const float* s_par, const uint8_t* s_
     const float4 v1 = *reinterpret_cast<const float4*>(e0);
     const float4 v2 = *reinterpret_cast<const float4*>(e0 + PS);
     const float4 v3 = *reinterpret_cast<const float4*>(e0 + 2 * PS);
-    const float4 c0 = make_float4(s_lutn[cb.x], s_lutn[cb.y], s_lutn[cb.z], s_lutn[cb.w]);
+    const float4 c0 = make_float4(cen_ch0(cb.x, s_lutn), cen_ch0(cb.y, s_lutn), cen_ch0(cb.z, s_lutn), cen_ch0(cb.w, s_lutn));
     const float4 c1 = make_float4(normalise_cost(v1.x, 1), normalise_cost(v1.y, 1), normalise_cost(v1.z, 1),
                                   normalise_cost(v1.w, 1));
     const float4 c2 = make_float4(normalise_cost(v2.x, 2), normalise_cost(v2.y, 2), normalise_cost(v2.z, 2),
@@ -750,12 +789,22 @@ __device__ __forceinline__ void store_ch03(const float* s_par, const uint8_t* s_
   }
 }
 
+// Four pixels of one matcher: exp(-(c-m)^2/sigma) * (1/den), two pixels per packed operation.
+__device__ __forceinline__ void p3_quad(const float4& v, const f32x2 (&m)[2], const f32x2 (&inv)[2], f32x2 negk,
+                                        float4& out) {
+  float e0, e1, e2, e3;
+  aml_e2(pk2(v.x, v.y), m[0], negk, e0, e1);
+  aml_e2(pk2(v.z, v.w), m[1], negk, e2, e3);
+  upk2(mul2(pk2(e0, e1), inv[0]), out.x, out.y);
+  upk2(mul2(pk2(e2, e3), inv[1]), out.z, out.w);
+}
+
 // Channels 4-7 = exp(-(c-m)^2/sigma) / den for thread = (pixel quad q4, disparities dl, dl+32, ...),
 // exponentials recomputed from the parked costs, 128-bit row segments.
 template <bool kVec>
 __device__ __forceinline__ void phase3_quads(const float* s_par, const uint8_t* s_cen, const float* s_lut,
                                              const float* s_min, const float* s_inv, int PS, int q4, int dl, int D,
-                                             float* arow, size_t plane, size_t chan, int nlive, float k1, float k2) {
+                                             float* arow, size_t plane, size_t chan, int nlive, float k0, float k1, float k2) {
   const float4 m_cen4 = *reinterpret_cast<const float4*>(s_min + q4);
   const float4 m1 = *reinterpret_cast<const float4*>(s_min + kTile + q4);
   const float4 m2 = *reinterpret_cast<const float4*>(s_min + 2 * kTile + q4);
@@ -764,6 +813,10 @@ __device__ __forceinline__ void phase3_quads(const float* s_par, const uint8_t* 
   const float4 i1 = *reinterpret_cast<const float4*>(s_inv + kTile + q4);
   const float4 i2 = *reinterpret_cast<const float4*>(s_inv + 2 * kTile + q4);
   const float4 i3 = *reinterpret_cast<const float4*>(s_inv + 3 * kTile + q4);
+  const f32x2 mp1[2] = {pk2(m1.x, m1.y), pk2(m1.z, m1.w)}, ip1[2] = {pk2(i1.x, i1.y), pk2(i1.z, i1.w)};
+  const f32x2 mp2[2] = {pk2(m2.x, m2.y), pk2(m2.z, m2.w)}, ip2[2] = {pk2(i2.x, i2.y), pk2(i2.z, i2.w)};
+  const f32x2 mp3[2] = {pk2(m3.x, m3.y), pk2(m3.z, m3.w)}, ip3[2] = {pk2(i3.x, i3.y), pk2(i3.z, i3.w)};
+  const f32x2 nk1 = pk2(-k1, -k1), nk2 = pk2(-k2, -k2);
   const int mcx = (m_cen4.x == kFill) ? 0 : (int)m_cen4.x, mcy = (m_cen4.y == kFill) ? 0 : (int)m_cen4.y;
   const int mcz = (m_cen4.z == kFill) ? 0 : (int)m_cen4.z, mcw = (m_cen4.w == kFill) ? 0 : (int)m_cen4.w;
 #pragma unroll 1
@@ -773,14 +826,12 @@ __device__ __forceinline__ void phase3_quads(const float* s_par, const uint8_t* 
     const float4 v1 = *reinterpret_cast<const float4*>(e0);
     const float4 v2 = *reinterpret_cast<const float4*>(e0 + PS);
     const float4 v3 = *reinterpret_cast<const float4*>(e0 + 2 * PS);
-    const float4 a0 = make_float4(s_lut[min((int)cb.x - mcx, 127)] * i0.x, s_lut[min((int)cb.y - mcy, 127)] * i0.y,
-                                  s_lut[min((int)cb.z - mcz, 127)] * i0.z, s_lut[min((int)cb.w - mcw, 127)] * i0.w);
-    const float4 a1 = make_float4(aml_e(v1.x, m1.x, k1) * i1.x, aml_e(v1.y, m1.y, k1) * i1.y,
-                                  aml_e(v1.z, m1.z, k1) * i1.z, aml_e(v1.w, m1.w, k1) * i1.w);
-    const float4 a2 = make_float4(aml_e(v2.x, m2.x, k2) * i2.x, aml_e(v2.y, m2.y, k2) * i2.y,
-                                  aml_e(v2.z, m2.z, k2) * i2.z, aml_e(v2.w, m2.w, k2) * i2.w);
-    const float4 a3 = make_float4(aml_e(v3.x, m3.x, k2) * i3.x, aml_e(v3.y, m3.y, k2) * i3.y,
-                                  aml_e(v3.z, m3.z, k2) * i3.z, aml_e(v3.w, m3.w, k2) * i3.w);
+    const float4 a0 = make_float4(cen_e(cb.x, mcx, s_lut, k0) * i0.x, cen_e(cb.y, mcy, s_lut, k0) * i0.y,
+                                  cen_e(cb.z, mcz, s_lut, k0) * i0.z, cen_e(cb.w, mcw, s_lut, k0) * i0.w);
+    float4 a1, a2, a3;
+    p3_quad(v1, mp1, ip1, nk1, a1);
+    p3_quad(v2, mp2, ip2, nk2, a2);
+    p3_quad(v3, mp3, ip3, nk2, a3);
     store_quads<kVec>(arow + (size_t)d * plane, chan, nlive, a0, a1, a2, a3);
   }
 }
@@ -832,18 +883,19 @@ __device__ __forceinline__ void tile_back_half(const FusedArgs& a, const TileId&
       for (int d0 = 0; d0 < Dfull; d0 += 8, c += 8 * kTile) {
         float ev[8];
 #pragma unroll
-        for (int j = 0; j < 8; ++j) ev[j] = s_lut[min((int)c[j * kTile] - mc, 127)];
+        for (int j = 0; j < 8; ++j) ev[j] = cen_e(c[j * kTile], mc, s_lut, a.k_cen);
 #pragma unroll
         for (int j = 0; j < 8; ++j) den = __fadd_rn(den, ev[j]);
       }
-      for (int d = Dfull; d < D; ++d, c += kTile) den = __fadd_rn(den, s_lut[min((int)c[0] - mc, 127)]);
+      for (int d = Dfull; d < D; ++d, c += kTile) den = __fadd_rn(den, cen_e(c[0], mc, s_lut, a.k_cen));
     } else {
       const float kq = (warp == 1) ? a.k_ncc : a.k_sad;
+      const f32x2 mm2 = pk2(mm, mm), nkq = pk2(-kq, -kq);
       const float* e = s_par + (warp - 1) * PS + lane;
       for (int d0 = 0; d0 < Dfull; d0 += 8, e += 8 * kTile) {
         float ev[8];
 #pragma unroll
-        for (int j = 0; j < 8; ++j) ev[j] = aml_e(e[j * kTile], mm, kq);
+        for (int j = 0; j < 8; j += 2) aml_e2(pk2(e[j * kTile], e[(j + 1) * kTile]), mm2, nkq, ev[j], ev[j + 1]);
 #pragma unroll
         for (int j = 0; j < 8; ++j) den = __fadd_rn(den, ev[j]);
       }
@@ -858,8 +910,8 @@ __device__ __forceinline__ void tile_back_half(const FusedArgs& a, const TileId&
   }
   __syncthreads();
   const int dl = tid >> 3;
-  if (vec) phase3_quads<true>(s_par, s_cen, s_lut, s_min, s_inv, PS, q4, dl, D, orow + 4 * chan, plane, chan, nlive, a.k_ncc, a.k_sad);
-  else phase3_quads<false>(s_par, s_cen, s_lut, s_min, s_inv, PS, q4, dl, D, orow + 4 * chan, plane, chan, nlive, a.k_ncc, a.k_sad);
+  if (vec) phase3_quads<true>(s_par, s_cen, s_lut, s_min, s_inv, PS, q4, dl, D, orow + 4 * chan, plane, chan, nlive, a.k_cen, a.k_ncc, a.k_sad);
+  else phase3_quads<false>(s_par, s_cen, s_lut, s_min, s_inv, PS, q4, dl, D, orow + 4 * chan, plane, chan, nlive, a.k_cen, a.k_ncc, a.k_sad);
 }
 
 // Back half of a tile for DISPARITY-SLAB SHARDING (phase A of slab.cu): the AML
@@ -899,7 +951,7 @@ __device__ __forceinline__ void tile_slab_a(const FusedArgs& a, const TileId& t,
     const float4 v3 = *reinterpret_cast<const float4*>(e0 + 2 * PS);
     const float4 v0 = make_float4(cb.x == 255 ? kFill : (float)cb.x, cb.y == 255 ? kFill : (float)cb.y,
                                   cb.z == 255 ? kFill : (float)cb.z, cb.w == 255 ? kFill : (float)cb.w);
-    const float4 c0 = make_float4(s_lutn[cb.x], s_lutn[cb.y], s_lutn[cb.z], s_lutn[cb.w]);
+    const float4 c0 = make_float4(cen_ch0(cb.x, s_lutn), cen_ch0(cb.y, s_lutn), cen_ch0(cb.z, s_lutn), cen_ch0(cb.w, s_lutn));
     const float4 c1 = make_float4(normalise_cost(v1.x, 1), normalise_cost(v1.y, 1), normalise_cost(v1.z, 1),
                                   normalise_cost(v1.w, 1));
     const float4 c2 = make_float4(normalise_cost(v2.x, 2), normalise_cost(v2.y, 2), normalise_cost(v2.z, 2),
@@ -978,8 +1030,10 @@ ms_fused_kernel(const FusedArgs a, const __grid_constant__ CUtensorMap sad_map) 
     for (int d = d_lo; d < d_end; ++d, src += splane, dst += kTile) cp_async4(dst, src);
     stage_right<L, NT>(a, t, smem_raw);
   }
-  if (tid < 128) s_lut[tid] = __ldg(a.luts + tid);
-  s_lutn[tid] = __ldg(a.luts + 128 + tid);
+  if (kCenLut) {
+    if (tid < 128) s_lut[tid] = __ldg(a.luts + tid);
+    s_lutn[tid] = __ldg(a.luts + 128 + tid);
+  }
   LeftRegs lr;
   load_left(a, t, px, lr);
   if (!kTma) cp_async_wait_all();
@@ -1154,7 +1208,7 @@ int launch_ms_fused(const uint8_t* d_left, const uint8_t* d_right, int N, int H,
     MSN_CUDA_OK(cudaMemsetAsync(ws.sob[i], 0, (size_t)N * (H + kSadRowPad) * g.Ws * sizeof(float), s));
   dim3 pgrid(div_up(g.Wp, 128), g.Hp, 2 * N);
   ms_prep_kernel<<<pgrid, 128, 0, s>>>(d_left, d_right, g, ws.desc[0], ws.desc[1], ws.stat[0], ws.stat[1],
-                                       ws.fimg[0], ws.fimg[1], ws.sob[0], ws.sob[1], ws.meanR[0], ws.meanR[1],
+                                       ws.fimg[0], ws.fimg[1], ws.sob[0], ws.sob[1], ws.meanR, ws.AR, ws.CR,
                                        ws.luts, aml_scale(p->cens_sigma));
   MSN_LAUNCH_OK();
   if (prof) MSN_CUDA_OK(cudaEventRecord(rec.ev[1], s));
@@ -1166,7 +1220,7 @@ int launch_ms_fused(const uint8_t* d_left, const uint8_t* d_right, int N, int H,
   a.descL = ws.desc[0]; a.descR = ws.desc[1];
   a.statL = ws.stat[0]; a.statR = ws.stat[1];
   a.fL = ws.fimg[0]; a.fR = ws.fimg[1];
-  a.meanR0 = ws.meanR[0]; a.meanR1 = ws.meanR[1];
+  a.meanR = ws.meanR; a.AR = ws.AR; a.CR = ws.CR;
   a.luts = ws.luts;
   a.sadsob = ws.sadsob;
   a.out = d_out;
