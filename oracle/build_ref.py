@@ -52,7 +52,10 @@ VARIANTS = {
                    os.path.join(REF_ROOT, "src/cpp/paramSetting.hpp"), "-include",
                    os.path.join(HERE, "shim", "threads_override.h")],
 }
-GLUE = ["src/dataloader/cbmv_generator.py"]   # copied verbatim into _ref/pyref/
+# copied verbatim into _ref/pyref/: the generator plus the package files its relative imports need, so
+# that `from src.dataloader import cbmv_generator` works on the GPU box with oracle/_ref/pyref on sys.path
+GLUE = ["src/dataloader/cbmv_generator.py", "src/__init__.py", "src/cpp/__init__.py", "src/dataloader/__init__.py",
+        "src/pfmutil.py", "src/funcs_utili.py"]
 
 
 def _includes():

@@ -108,6 +108,41 @@ def test_install_dropin_registers_reference_import_names(ms):
         del sys.modules[k]
 
 
+def test_install_dropin_keeps_the_reference_package_importable(ms):
+    """install_dropin() BEFORE the reference package is imported (INTEGRATION.md option A): the real
+    `src` package must still import afterwards -- `from src.dataloader import cbmv_generator`
+    (main_msnet.py's import chain) -- and see the CUDA mirrors.  No compute here (CPU suite)."""
+    import types
+    import warnings
+    roots = [p for p in ("/root/reference", os.path.join(ROOT, "oracle", "_ref", "pyref"))
+             if os.path.isfile(os.path.join(p, "src", "dataloader", "cbmv_generator.py"))]
+    if not roots:
+        pytest.skip("no copy of the reference package available")
+    saved = {k: v for k, v in sys.modules.items()
+             if k == "src" or k.startswith("src.") or k.split(".")[0] in ("skimage", "matplotlib")}
+    for k in saved:
+        del sys.modules[k]
+    sys.path.insert(0, roots[0])
+    try:
+        for name in ("skimage", "skimage.transform", "matplotlib", "matplotlib.pyplot", "matplotlib.image"):
+            sys.modules[name] = types.ModuleType(name)
+        sys.modules["skimage"].transform = sys.modules["skimage.transform"]
+        sys.modules["matplotlib"].pyplot = sys.modules["matplotlib.pyplot"]
+        sys.modules["matplotlib"].image = sys.modules["matplotlib.image"]
+        mtc, fte = ms.install_dropin()
+        with warnings.catch_warnings():
+            warnings.simplefilter("ignore")
+            from src.dataloader import cbmv_generator
+        assert cbmv_generator.mtc is mtc and cbmv_generator.fte is fte
+        assert callable(cbmv_generator.get_costs) and callable(cbmv_generator.generate_test_cbmv)
+    finally:
+        sys.path.remove(roots[0])
+        for k in [k for k in sys.modules
+                  if k == "src" or k.startswith("src.") or k.split(".")[0] in ("skimage", "matplotlib")]:
+            del sys.modules[k]
+        sys.modules.update(saved)
+
+
 def test_product_never_imports_oracle():
     """The oracle is test infrastructure: nothing under ms-nets_b200/ may reference it."""
     pkg = os.path.join(ROOT, "ms-nets_b200")

@@ -55,6 +55,24 @@ def test_config_a_256x512_d192(oracle):
     _compare(got, want)
 
 
+def test_config_b_sceneflow_540x960_d192_full_compare(oracle):
+    """bench.py's own workload at full size, value by value: one 540x960 (560x980 bordered), D=192 pair
+    computed as member 1 of a batch of two through the batched device API (the bench path), against the
+    unmodified reference C++ (oracle/_ref) when it travelled, else the C oracle."""
+    import torch
+    import msnets_b200 as ms
+    D, border = 192, 10
+    pairs = [bordered_pair(540, 960, 1234 + i, border=border) for i in range(2)]
+    want, who = _reference_features(oracle, pairs[1][0], pairs[1][1], D, border)
+    l = torch.stack([torch.from_numpy(p[0]) for p in pairs]).cuda()
+    r = torch.stack([torch.from_numpy(p[1]) for p in pairs]).cuda()
+    ex = ms.cbmv.MSFeatureExtractor(2, 560, 980, maxdisp=D, board_h=border, board_w_left=border,
+                                    board_w_right=border)
+    got = ex(l, r)
+    assert tuple(got.shape) == (2, 8, 192, 540, 960)
+    _compare(got[1].cpu().numpy(), want)
+
+
 def test_config_c_kitti_375x1242_d192(oracle):
     import msnets_b200 as ms
     h, w = 375, 1242
@@ -136,3 +154,98 @@ def test_config_m_middlebury_slab(oracle):
     assert np.array_equal(win[0], (np.clip(cen, 0., 120.) / 120.).transpose(2, 0, 1))
     assert np.array_equal(win[1], (1 + np.clip(ncc, -1., 1.)) / 2)
     assert np.array_equal(win[3], np.clip(zs, 0., 2 ** 13) / float(2 ** 13))
+
+
+def _virtual_slab_ranks(L, R, D, border, world):
+    """The slab-sharded pipeline with `world` virtual ranks on one GPU: phase A per slab, the two
+    all-reduces done with torch ops, phases B and C -> the assembled [8, D, h, w] volume."""
+    import torch
+    from msnets_b200 import _lib, cbmv, sharding
+    lib = _lib.lib()
+    N, (H, W) = 1, L.shape
+    l, r = torch.from_numpy(L[None]).cuda(), torch.from_numpy(R[None]).cuda()
+    st = torch.cuda.current_stream().cuda_stream
+    slabs = []
+    for rank in range(world):
+        d0, dn = sharding.shard_range(D, rank, world)
+        p = cbmv.make_params(D, board_h=border, board_w_left=border, board_w_right=border, d_begin=d0, d_count=dn)
+        shape = cbmv.output_shape(N, H, W, p)
+        ws = torch.empty(lib.msn_ms_slab_workspace_bytes(N, H, W, ctypes.byref(p)), dtype=torch.uint8, device="cuda")
+        out = torch.empty(shape, dtype=torch.float32, device="cuda")
+        mins = torch.empty((N, 4, shape[3], shape[4]), dtype=torch.float32, device="cuda")
+        _lib.check(lib.msn_ms_slab_phase_a_dev(l.data_ptr(), r.data_ptr(), N, H, W, ctypes.byref(p), None,
+                                               out.data_ptr(), mins.data_ptr(), ws.data_ptr(), ws.numel(), st))
+        slabs.append((p, out, mins, shape))
+        del ws
+    gmin = slabs[0][2].clone()
+    for s_ in slabs[1:]:
+        gmin = torch.minimum(gmin, s_[2])                       # all-reduce(min)
+    gden = torch.zeros_like(gmin)
+    for p, out, _, shape in slabs:
+        den = torch.empty_like(gmin)
+        _lib.check(lib.msn_ms_slab_phase_b_dev(out.data_ptr(), gmin.data_ptr(), N, shape[3], shape[4],
+                                               ctypes.byref(p), den.data_ptr(), st))
+        gden += den                                              # all-reduce(sum), rank order
+    for p, out, _, shape in slabs:
+        _lib.check(lib.msn_ms_slab_phase_c_dev(out.data_ptr(), gmin.data_ptr(), gden.data_ptr(), N, shape[3],
+                                               shape[4], ctypes.byref(p), st))
+    torch.cuda.synchronize()
+    return torch.cat([s_[1] for s_ in slabs], dim=2)[0].cpu().numpy()
+
+
+def test_config_m_full_width_strip_all_channels_after_merge(oracle):
+    """Config M's width and disparity range on a row strip: 2880 (+20) columns, D = 640 in eight slabs
+    of 80, 76 (+20) rows.  Every channel of the merged volume is compared with the reference run on the
+    same strip: the SAD-of-Sobel channel (whole-row fp32 scans at W = 2900, sums far above 2^24) and
+    the AML channels after the cross-slab min / sum merges included."""
+    D, border = 640, 10
+    Lf, Rf = bordered_pair(1984, 2880, 99, border=0, shift=13)
+    L0, R0 = Lf[900:976], Rf[900:976]
+    L = np.ascontiguousarray(np.pad(L0, ((border, border), (border, border)), "constant"))
+    R = np.ascontiguousarray(np.pad(R0, ((border, border), (border, border)), "constant"))
+    want, who = _reference_features(oracle, L, R, D, border)
+    got = _virtual_slab_ranks(L, R, D, border, 8)
+    assert got.shape == want.shape == (8, 640, 76, 2880)
+    for c in range(4):
+        assert np.array_equal(got[c], want[c]), "channel %d must be bit-exact" % c
+    for c in range(4, 8):                                        # cross-slab sum order differs by construction
+        assert float(np.abs(got[c] - want[c]).max()) <= AML_DEGENERATE_ATOL
+        assert float((np.abs(got[c] - want[c]) > AML_ATOL).mean()) <= 1e-5
+
+
+def test_config_m_sadsob_deep_rows_full_width(oracle):
+    """SAD-of-Sobel at config M's width 330 rows down the frame (13 row bands of the scan): the fp32 table
+    of a row depends on every row above it, so the oracle runs on the top 336 rows at full width; one
+    slab of disparities (rank 2 of 8: [160, 240)) is compared bit for bit on rows 300..320."""
+    import msnets_b200 as ms
+    from msnets_b200 import sharding
+    border = 10
+    L, R = bordered_pair(1984, 2880, 99, border=border, shift=13)
+    Ls, Rs = np.ascontiguousarray(L[:336]), np.ascontiguousarray(R[:336])
+    d0, dn = sharding.shard_range(640, 2, 8)
+    sl, sr = oracle.sobel(Ls), oracle.sobel(Rs)
+    want = oracle.sadsob(sl, sr, d0 + dn, 5)[d0:, 300:320]        # [d, y, x], raw costs
+    mtc = ms.libmatchers
+    gl, gr = mtc.sobel(Ls), mtc.sobel(Rs)
+    assert np.array_equal(gl, sl) and np.array_equal(gr, sr)
+    got = mtc.sadsob(gl, gr, d0 + dn, 5)[d0:, 300:320]
+    assert np.array_equal(got, want)
+    assert float(want[want < 1e9].max()) > 2 ** 13 / 4
+    # the same rows through the slab path's own scan (sadsob_scan5_kernel, pitch 4096) and phase A: channel 2
+    import torch
+    from msnets_b200 import _lib, cbmv
+    lib = _lib.lib()
+    H, W = Ls.shape
+    p = cbmv.make_params(640, board_h=border, board_w_left=border, board_w_right=border, d_begin=d0, d_count=dn)
+    shape = cbmv.output_shape(1, H, W, p)
+    l, r = torch.from_numpy(Ls[None]).cuda(), torch.from_numpy(Rs[None]).cuda()
+    ws = torch.empty(lib.msn_ms_slab_workspace_bytes(1, H, W, ctypes.byref(p)), dtype=torch.uint8, device="cuda")
+    out = torch.empty(shape, dtype=torch.float32, device="cuda")
+    mins = torch.empty((1, 4, shape[3], shape[4]), dtype=torch.float32, device="cuda")
+    _lib.check(lib.msn_ms_slab_phase_a_dev(l.data_ptr(), r.data_ptr(), 1, H, W, ctypes.byref(p), None, out.data_ptr(),
+                                           mins.data_ptr(), ws.data_ptr(), ws.numel(),
+                                           torch.cuda.current_stream().cuda_stream))
+    torch.cuda.synchronize()
+    ch2 = out[0, 2, :, 300 - border:320 - border].cpu().numpy()                 # [d, y, x] cropped
+    want2 = (np.clip(want[:, :, border:W - border], 0., 2 ** 13) / float(2 ** 13)).astype(np.float32)
+    assert np.array_equal(ch2, want2)
