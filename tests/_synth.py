@@ -36,3 +36,21 @@ def bordered_pair(h, w, seed, border=10, shift=7, patches=False):
     pad = ((border, border), (border, border))
     return (np.ascontiguousarray(np.pad(L, pad, "constant")),
             np.ascontiguousarray(np.pad(R, pad, "constant")))
+
+
+# AML (extract_likelihood, channels 4-7) parity class of the FAST kernels (SFU ex2 instead of glibc expf):
+# |got - reference| <= 2e-6 on outputs in [0,1], except on rows that repeat one cost many times (zero padding,
+# flat regions): there the reference's sequential fp32 denominator rounds the SAME addend the SAME way up to D
+# times, a drift of up to D * 2^-24 = 1.1e-5 whose direction hangs on the last bit of expf.  Such voxels are held
+# to a hard cap of 1.2e-5 and must be rare (< 1e-6 of the voxels, or a handful on small inputs).
+AML_ATOL = 2e-6
+AML_HARD_CAP = 1.2e-5
+AML_RARE_FRACTION = 1e-6
+
+
+def assert_aml_close(got, want, what="AML"):
+    err = np.abs(np.asarray(got, np.float32) - np.asarray(want, np.float32))
+    assert float(err.max()) <= AML_HARD_CAP, "%s: max error %.3g above the hard cap" % (what, float(err.max()))
+    n_bad = int((err > AML_ATOL).sum())
+    assert n_bad <= max(4, int(AML_RARE_FRACTION * err.size)), "%s: %d of %d voxels above %.0e" % (
+        what, n_bad, err.size, AML_ATOL)

