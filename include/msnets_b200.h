@@ -142,6 +142,35 @@ MSN_API int msn_ms_slab_phase_b_dev(const float* d_out_ncdhw, const float* d_min
 MSN_API int msn_ms_slab_phase_c_dev(float* d_out_ncdhw, const float* d_min_n4hw, const float* d_den_n4hw,
                             int N, int h, int w, const msn_ms_params* p, void* stream);
 
+/* Disparity-slab sharding, fused with its exchange (replaces phases A/B/C and the two
+ * NCCL all-reduces between them when the slab fits the fused kernel: default windows, left view,
+ * d_count <= 448).  Every rank calls this for the SAME pair(s) with its own slab in p->d_begin / d_count;
+ * the kernel keeps a tile's costs in shared memory and trades the per-pixel AML minima and partial
+ * denominators with the other ranks through their exchange tables -- peer-mapped device memory written
+ * over NVLink / NVSwitch -- so the volume is written once (32 B per voxel) and never re-read.
+ *   tables[r]  device pointer, valid on THIS device, to rank r's exchange table (tables[rank] = own):
+ *              msn_ms_slab_exchange_bytes bytes, zeroed once at allocation, same size on every rank
+ *   epoch      > 0, the same on every rank, incremented for every frame (call) by every rank
+ * A rank whose peers never arrive traps after ~2 s instead of hanging. */
+typedef struct msn_slab_exchange {
+  void* tables[8];
+  int world;
+  int rank;
+  unsigned epoch;
+} msn_slab_exchange;
+MSN_API size_t msn_ms_slab_exchange_bytes(int N, int H, int W, const msn_ms_params* p, int world);
+MSN_API int msn_ms_slab_fused_dev(const uint8_t* d_left, const uint8_t* d_right, int N, int H, int W,
+                          const msn_ms_params* p, const msn_slab_exchange* xchg, float* d_out_ncdhw,
+                          void* d_workspace, size_t workspace_bytes, void* stream);
+/* Peer memory for the exchange tables: a zeroed cudaMalloc allocation on the current device, its 64-byte
+ * CUDA IPC handle (to be all-gathered by the host side), and the mapping of another process's handle into
+ * this one (peer access is enabled by the mapping).  One node only. */
+MSN_API int msn_peer_alloc(size_t bytes, void** d_ptr);
+MSN_API int msn_peer_free(void* d_ptr);
+MSN_API int msn_peer_export(void* d_ptr, unsigned char handle64[64]);
+MSN_API int msn_peer_open(const unsigned char handle64[64], void** d_ptr);
+MSN_API int msn_peer_close(void* d_ptr);
+
 /* ----------------------------------------------------- device-level pieces -- */
 MSN_API int msn_census_dev(const uint8_t* d_left, const uint8_t* d_right, int H, int W, int ndisp, int wsize,
                    float* d_out_hwd, void* stream);

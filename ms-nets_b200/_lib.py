@@ -21,6 +21,11 @@ class MsParams(ctypes.Structure):
                 ("sad_sigma", c_float), ("lr", c_int), ("d_begin", c_int), ("d_count", c_int)]
 
 
+class SlabExchange(ctypes.Structure):
+    """struct msn_slab_exchange (include/msnets_b200.h)."""
+    _fields_ = [("tables", c_void_p * 8), ("world", c_int), ("rank", c_int), ("epoch", ctypes.c_uint)]
+
+
 class MsnetsError(RuntimeError):
     pass
 
@@ -58,6 +63,13 @@ _SIGNATURES = {
                                         _P, _P, c_size_t, _P]),
     "msn_ms_slab_phase_b_dev": (c_int, [_P, _P, c_int, c_int, c_int, ctypes.POINTER(MsParams), _P, _P]),
     "msn_ms_slab_phase_c_dev": (c_int, [_P, _P, _P, c_int, c_int, c_int, ctypes.POINTER(MsParams), _P]),
+    "msn_ms_slab_exchange_bytes": (c_size_t, [c_int, c_int, c_int, ctypes.POINTER(MsParams), c_int]),
+    "msn_ms_slab_fused_dev": (c_int, [_P, _P, c_int, c_int, c_int, ctypes.POINTER(MsParams), _P, _P, _P, c_size_t, _P]),
+    "msn_peer_alloc": (c_int, [c_size_t, ctypes.POINTER(c_void_p)]),
+    "msn_peer_free": (c_int, [_P]),
+    "msn_peer_export": (c_int, [_P, _P]),
+    "msn_peer_open": (c_int, [_P, ctypes.POINTER(c_void_p)]),
+    "msn_peer_close": (c_int, [_P]),
     "msn_census_dev": (c_int, [_P, _P, c_int, c_int, c_int, c_int, _P, _P]),
     "msn_ncc_dev": (c_int, [_P, _P, c_int, c_int, c_int, c_int, _P, _P]),
     "msn_zsad_dev": (c_int, [_P, _P, c_int, c_int, c_int, c_int, _P, _P]),

@@ -645,6 +645,63 @@ int msn_ms_slab_phase_a_dev(const uint8_t* d_left, const uint8_t* d_right, int N
   return 0;
 }
 
+size_t msn_ms_slab_exchange_bytes(int N, int H, int W, const msn_ms_params* p, int world) {
+  Geometry g;
+  if (resolve(p, N, H, W, &g, "ms_slab_exchange_bytes")) return 0;
+  if (world < 1 || world > 8) { set_error("ms_slab_exchange_bytes: world %d not in 1..8", world); return 0; }
+  if (!slab_fused(p, g, W) || g.Dn > 448) {
+    set_error("ms_slab_exchange_bytes: the fused exchange needs the default windows, the left view and a slab of at most 448 disparities");
+    return 0;
+  }
+  return fused_exchange_bytes(N, H, W, p, world);
+}
+
+int msn_ms_slab_fused_dev(const uint8_t* d_left, const uint8_t* d_right, int N, int H, int W, const msn_ms_params* p,
+                          const msn_slab_exchange* xchg, float* d_out, void* d_workspace, size_t workspace_bytes,
+                          void* stream) {
+  Geometry g;
+  TRY(resolve(p, N, H, W, &g, "ms_slab_fused"));
+  MSN_REQUIRE(d_left && d_right && d_out && d_workspace && xchg, "ms_slab_fused: null pointer argument");
+  MSN_REQUIRE(slab_fused(p, g, W) && g.Dn <= 448,
+              "ms_slab_fused: needs the default windows, the left view and a slab of at most 448 disparities "
+              "(use msn_ms_slab_phase_*_dev otherwise)");
+  const size_t need = fused_workspace_bytes(N, H, W, g.Dn, p) + 256;
+  MSN_REQUIRE(workspace_bytes >= need, "ms_slab_fused: workspace too small (%zu < %zu)", workspace_bytes, need);
+  char* base = (char*)(((uintptr_t)d_workspace + 255) & ~(uintptr_t)255);
+  return launch_ms_fused(d_left, d_right, N, H, W, p, d_out, nullptr, base, as_stream(stream), g.Dn, 0, 0, xchg);
+}
+
+int msn_peer_alloc(size_t bytes, void** d_ptr) {
+  MSN_REQUIRE(d_ptr && bytes > 0, "peer_alloc: bad argument");
+  MSN_CUDA_OK(cudaMalloc(d_ptr, bytes));
+  MSN_CUDA_OK(cudaMemset(*d_ptr, 0, bytes));
+  MSN_CUDA_OK(cudaDeviceSynchronize());
+  return 0;
+}
+int msn_peer_free(void* d_ptr) {
+  if (d_ptr) MSN_CUDA_OK(cudaFree(d_ptr));
+  return 0;
+}
+int msn_peer_export(void* d_ptr, unsigned char handle64[64]) {
+  static_assert(sizeof(cudaIpcMemHandle_t) == 64, "CUDA IPC handle size");
+  MSN_REQUIRE(d_ptr && handle64, "peer_export: null pointer argument");
+  cudaIpcMemHandle_t h;
+  MSN_CUDA_OK(cudaIpcGetMemHandle(&h, d_ptr));
+  memcpy(handle64, &h, 64);
+  return 0;
+}
+int msn_peer_open(const unsigned char handle64[64], void** d_ptr) {
+  MSN_REQUIRE(d_ptr && handle64, "peer_open: null pointer argument");
+  cudaIpcMemHandle_t h;
+  memcpy(&h, handle64, 64);
+  MSN_CUDA_OK(cudaIpcOpenMemHandle(d_ptr, h, cudaIpcMemLazyEnablePeerAccess));
+  return 0;
+}
+int msn_peer_close(void* d_ptr) {
+  if (d_ptr) MSN_CUDA_OK(cudaIpcCloseMemHandle(d_ptr));
+  return 0;
+}
+
 int msn_ms_slab_phase_b_dev(const float* d_out, const float* d_min, int N, int h, int w, const msn_ms_params* p,
                             float* d_den, void* stream) {
   MSN_REQUIRE(p && d_out && d_min && d_den, "ms_slab_phase_b: null pointer argument");

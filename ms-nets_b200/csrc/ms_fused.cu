@@ -212,6 +212,13 @@ ms_prep_kernel(const uint8_t* __restrict__ left, const uint8_t* __restrict__ rig
 }
 
 // ----------------------------------------------------------------- fused --
+constexpr int kMaxRanks = 8;
+constexpr int kXLineWords = 32, kXLines = 5;   // 128 values travel as 5 lines of 31 values + 1 flag word
+struct FusedXchg {
+  unsigned* peer[kMaxRanks];
+  int G, rank;
+  unsigned epoch;     // > 0, the same on every rank, +1 per frame: flag value and (its low bit) table half
+};
 struct FusedArgs {
   FusedGeom g;
   const uint4 *descL, *descR;
@@ -230,9 +237,14 @@ struct FusedArgs {
   float k_cen, k_ncc, k_sad;
   int DC;               // disparity steps per d-group (even: phase 1 walks disparity pairs)
   int tiles_x;
+  // Disparity-slab exchange (mode kModeXchg): the tables of all ranks (xchg.peer[rank] is this rank's own),
+  // peer-mapped device pointers.  See tile_back_half.
+  FusedXchg xchg;
+  long long n_tiles;
 };
 
 constexpr int kTile = 32;   // pixels per tile: one output row segment of 128 bytes
+constexpr int kModeFull = 0, kModeSlabA = 1, kModeXchg = 2;
 
 // Staging buffer of one tile: right-image row data for the D + 31 (+ slack) columns the tile
 // can touch.  Row strides are compile-time so every shared access in the hot loop is
@@ -836,70 +848,152 @@ __device__ __forceinline__ void phase3_quads(const float* s_par, const uint8_t* 
   }
 }
 
+// AML denominator of one (pixel, matcher) over the launch's disparities: exponentials evaluated on the fly
+// and added in the reference's order -- sequential fp32 over d (featextract.cpp:444-447; a tree sum is
+// measurably outside the 2e-6 bound).  warp = matcher, lane = pixel, mm = the minimum the exponent refers to.
+template <class L>
+__device__ __forceinline__ float den_chain(const FusedArgs& a, int warp, int lane, float mm, const float* s_par,
+                                           const uint8_t* s_cen, const float* s_lut) {
+  constexpr int PS = L::PS;
+  const int D = a.g.D;
+  float den = 0.f;
+  const int Dfull = D & ~7;   // groups of 8 without guards, then a guarded tail
+  if (warp == 0) {
+    const int mc = (mm == kFill) ? 0 : (int)mm;
+    const uint8_t* c = s_cen + lane;
+    for (int d0 = 0; d0 < Dfull; d0 += 8, c += 8 * kTile) {
+      float ev[8];
+#pragma unroll
+      for (int j = 0; j < 8; ++j) ev[j] = cen_e(c[j * kTile], mc, s_lut, a.k_cen);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) den = __fadd_rn(den, ev[j]);
+    }
+    for (int d = Dfull; d < D; ++d, c += kTile) den = __fadd_rn(den, cen_e(c[0], mc, s_lut, a.k_cen));
+  } else {
+    const float kq = (warp == 1) ? a.k_ncc : a.k_sad;
+    const f32x2 mm2 = pk2(mm, mm), nkq = pk2(-kq, -kq);
+    const float* e = s_par + (warp - 1) * PS + lane;
+    for (int d0 = 0; d0 < Dfull; d0 += 8, e += 8 * kTile) {
+      float ev[8];
+#pragma unroll
+      for (int j = 0; j < 8; j += 2) aml_e2(pk2(e[j * kTile], e[(j + 1) * kTile]), mm2, nkq, ev[j], ev[j + 1]);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) den = __fadd_rn(den, ev[j]);
+    }
+    for (int d = Dfull; d < D; ++d, e += kTile) den = __fadd_rn(den, aml_e(e[0], mm, kq));
+  }
+  return den;
+}
+
+// ---- disparity-slab exchange between ranks, inside the tile -------------------------
+// Every rank computes its own slab of disparities for the SAME tiles; the AML minimum and denominator of
+// a pixel need all slabs.  Instead of parking raw costs in HBM and making two more passes over the volume
+// around two NCCL all-reduces, the tile keeps its costs in shared memory and trades 2 x 128 floats with the
+// other ranks through peer-mapped memory (NVLink / NVSwitch): it WRITES its per-pixel minima into every
+// rank's table and reads the other ranks' values from its own.  The payload travels LL128-style: a line is
+// 31 values + a flag word (the frame's epoch), written by one warp as one aligned 128-byte store, so a
+// reader that sees the flag in a line it loaded in one piece has the line's values -- no fence, no separate
+// flag round trip.  Tables are double-buffered by the epoch's low bit: a rank can only be two frames ahead
+// of a peer's unread data after that peer has finished the frame in between.
+__device__ __forceinline__ size_t xchg_line0(const FusedArgs& a, int round, long long tile, int src) {
+  return (((((size_t)(a.xchg.epoch & 1u) * 2 + round) * a.n_tiles + tile) * a.xchg.G + src) * kXLines) *
+         kXLineWords;
+}
+// Warps 0-3: the 128 values in vals[] (shared memory) go to every rank's table as lines k = warp (+ 4 for warp 0).
+__device__ __forceinline__ void xchg_publish(const FusedArgs& a, int round, long long tile, int warp, int lane,
+                                             const float* vals) {
+  for (int k = warp; k < kXLines; k += 4) {
+    const int i = 31 * k + lane;
+    const unsigned w = (lane == 31) ? a.xchg.epoch : ((i < 128) ? __float_as_uint(vals[i]) : 0u);
+    const size_t off = xchg_line0(a, round, tile, a.xchg.rank) + (size_t)k * kXLineWords + lane;
+    for (int p = 0; p < a.xchg.G; ++p)
+      asm volatile("st.volatile.global.u32 [%0], %1;" ::"l"(a.xchg.peer[p] + off), "r"(w) : "memory");
+  }
+}
+// Warps 0-3: waits for every rank's lines of this tile and folds them in rank order (kSum: a + b, else
+// min) into out[0..128).  A peer that never shows up (crashed rank, mismatched launch) trips a trap after
+// ~2 s instead of hanging the GPU.
+template <bool kSum>
+__device__ __forceinline__ void xchg_collect(const FusedArgs& a, int round, long long tile, int warp, int lane,
+                                             float* out) {
+  const unsigned* mine = a.xchg.peer[a.xchg.rank];
+  for (int k = warp; k < kXLines; k += 4) {
+    float acc = kSum ? 0.f : kFill;
+    for (int src = 0; src < a.xchg.G; ++src) {
+      const unsigned* line = mine + xchg_line0(a, round, tile, src) + (size_t)k * kXLineWords;
+      unsigned w;
+      long long t0 = 0;
+      for (unsigned spins = 0;; ++spins) {
+        asm volatile("ld.volatile.global.u32 %0, [%1];" : "=r"(w) : "l"(line + lane) : "memory");
+        if (__shfl_sync(0xffffffffu, w, 31) == a.xchg.epoch) break;
+        if (spins == 64) t0 = clock64();
+        if (spins > 64) {
+          __nanosleep(200);
+          if (clock64() - t0 > 4000000000LL) __trap();
+        }
+      }
+      const float v = __uint_as_float(w);
+      acc = kSum ? __fadd_rn(acc, v) : fminf(acc, v);
+    }
+    const int i = 31 * k + lane;
+    if (lane < 31 && i < 128) out[i] = acc;
+  }
+}
+__device__ __forceinline__ void bar_sync_128() { asm volatile("bar.sync 1, 128;" ::: "memory"); }
+
 // Phases 2 and 3 for the 256 threads of a CTA.  s_red holds the per-group minima of phase 1.
 //   phase 2 (warp-specialised; both halves only READ the parked costs, so they overlap without
 //            hazards):
-//     warps 0-3  one thread per (pixel, matcher): AML denominator, exponentials evaluated on
-//                the fly and added in the reference's order -- sequential fp32 over d
-//                (featextract.cpp:444-447; a tree sum is measurably outside the 2e-6 bound);
+//     warps 0-3  one thread per (pixel, matcher): AML denominator (den_chain);
 //     warps 4-7  thread = (pixel quad, d): channels 0-3 normalised and stored.
 //   phase 3      all warps: channels 4-7.
+// kXchg (disparity-slab sharding): warps 0-3 first trade the slab's minima with the other ranks, add the
+// denominator of their OWN disparities against the global minimum, trade the partial denominators and add
+// them in rank order -- while warps 4-7 store channels 0-3, which need nothing from anybody.
 // Measured alternatives: writing each exponential back in place and adding
 // the denominators in a phase of their own (fewer instructions, 6 % slower: the chain is
 // exposed), the same behind a progress counter (slower still: the chain warps spin), handing
 // part of the channel 0-3 stores to the chain warps statically or through a work counter (no
 // gain: the halves are already balanced), a warp-specialised persistent producer/consumer
 // kernel (15 % slower).
-template <class L>
-__device__ __forceinline__ void tile_back_half(const FusedArgs& a, const TileId& t, int tid, const float* s_par,
-                                               const uint8_t* s_cen, const float* s_red, float* s_min,
+template <class L, bool kXchg>
+__device__ __forceinline__ void tile_back_half(const FusedArgs& a, const TileId& t, long long tile, int tid,
+                                               const float* s_par, const uint8_t* s_cen, float* s_red, float* s_min,
                                                float* s_inv, const float* s_lut, const float* s_lutn) {
   constexpr int PS = L::PS;
   const FusedGeom& g = a.g;
   const int D = g.D;
   const size_t plane = (size_t)g.h * g.w;
-  const size_t chan = plane * D;
-  if (tid < 4 * kTile) {  // minima across the d-groups
+  const size_t chan = plane * a.out_D;
+  if (tid < 4 * kTile) {  // minima across the d-groups (kXchg: of this rank's slab, staged in s_inv)
     float v = kFill;
 #pragma unroll
     for (int gq = 0; gq < kGroups; ++gq) v = fminf(v, s_red[gq * 4 * kTile + tid]);
-    s_min[tid] = v;
+    (kXchg ? s_inv : s_min)[tid] = v;
   }
   __syncthreads();
   const int warp = tid >> 5, lane = tid & 31;
   const int q4 = (tid & 7) * 4;
   // 128-bit stores need 16-byte aligned rows
   const bool vec_ok = ((g.w & 3) == 0) && ((reinterpret_cast<uintptr_t>(a.out) & 15) == 0);
-  float* orow = a.out + (size_t)t.n * a.out_channels * chan + (size_t)t.y * g.w + (t.x0 + q4);
+  float* orow = a.out + (size_t)t.n * a.out_channels * chan + (size_t)a.out_d0 * plane + (size_t)t.y * g.w + (t.x0 + q4);
   const int nlive = min(4, g.w - (t.x0 + q4));  // live pixels of this quad (<= 0: none)
   const bool vec = vec_ok && nlive == 4;
   if (warp < 4) {
+    if (kXchg) {
+      xchg_publish(a, 0, tile, warp, lane, s_inv);
+      xchg_collect<false>(a, 0, tile, warp, lane, s_min);
+      bar_sync_128();
+    }
     const float mm = s_min[warp * kTile + lane];
-    float den = 0.f;
-    const int Dfull = D & ~7;   // groups of 8 without guards, then a guarded tail
-    if (warp == 0) {
-      const int mc = (mm == kFill) ? 0 : (int)mm;
-      const uint8_t* c = s_cen + lane;
-      for (int d0 = 0; d0 < Dfull; d0 += 8, c += 8 * kTile) {
-        float ev[8];
-#pragma unroll
-        for (int j = 0; j < 8; ++j) ev[j] = cen_e(c[j * kTile], mc, s_lut, a.k_cen);
-#pragma unroll
-        for (int j = 0; j < 8; ++j) den = __fadd_rn(den, ev[j]);
-      }
-      for (int d = Dfull; d < D; ++d, c += kTile) den = __fadd_rn(den, cen_e(c[0], mc, s_lut, a.k_cen));
-    } else {
-      const float kq = (warp == 1) ? a.k_ncc : a.k_sad;
-      const f32x2 mm2 = pk2(mm, mm), nkq = pk2(-kq, -kq);
-      const float* e = s_par + (warp - 1) * PS + lane;
-      for (int d0 = 0; d0 < Dfull; d0 += 8, e += 8 * kTile) {
-        float ev[8];
-#pragma unroll
-        for (int j = 0; j < 8; j += 2) aml_e2(pk2(e[j * kTile], e[(j + 1) * kTile]), mm2, nkq, ev[j], ev[j + 1]);
-#pragma unroll
-        for (int j = 0; j < 8; ++j) den = __fadd_rn(den, ev[j]);
-      }
-      for (int d = Dfull; d < D; ++d, e += kTile) den = __fadd_rn(den, aml_e(e[0], mm, kq));
+    float den = den_chain<L>(a, warp, lane, mm, s_par, s_cen, s_lut);
+    if (kXchg) {
+      s_red[warp * kTile + lane] = den;        // (the per-group minima are dead since the barrier above)
+      bar_sync_128();
+      xchg_publish(a, 1, tile, warp, lane, s_red);
+      xchg_collect<true>(a, 1, tile, warp, lane, s_red + 4 * kTile);
+      bar_sync_128();
+      den = s_red[4 * kTile + warp * kTile + lane];
     }
     s_inv[warp * kTile + lane] = (mm == kFill) ? 0.f : 1.0f / den;
   }
@@ -988,8 +1082,9 @@ __device__ __forceinline__ void tile_slab_a(const FusedArgs& a, const TileId& t,
 // cp.async.bulk.tensor (D <= 256: box limit); otherwise through LDGSTS.  The tensor copy's
 // inner coordinate must be a multiple of 16 bytes (measured: anything else raises an
 // illegal-instruction fault), which is why the scratch is stored with column offset sxo.
-// kSlabA: stop after phase 1 and emit what slab.cu's phase A emits (tile_slab_a).
-template <int DMAX, bool kTma, bool kSlabA>
+// kMode: kModeFull the whole volume; kModeSlabA stop after phase 1 and emit what slab.cu's phase A emits
+// (tile_slab_a); kModeXchg a rank's disparity slab, minima and denominators traded inside the tile.
+template <int DMAX, bool kTma, int kMode>
 __global__ void __launch_bounds__(256, 2)
 ms_fused_kernel(const FusedArgs a, const __grid_constant__ CUtensorMap sad_map) {
   using L = Lay<DMAX, kSlack>;
@@ -1044,8 +1139,8 @@ ms_fused_kernel(const FusedArgs a, const __grid_constant__ CUtensorMap sad_map) 
   if (kTma) mbar_wait(&s_bar[1], 0);
   finish_phase1<L>(s_par, s_red, o, px, grp, d_lo, d_end);
   __syncthreads();
-  if (kSlabA) tile_slab_a<L>(a, t, tid, s_par, s_cen, s_red, s_lutn);
-  else tile_back_half<L>(a, t, tid, s_par, s_cen, s_red, s_min, s_inv, s_lut, s_lutn);
+  if (kMode == kModeSlabA) tile_slab_a<L>(a, t, tid, s_par, s_cen, s_red, s_lutn);
+  else tile_back_half<L, kMode == kModeXchg>(a, t, blockIdx.x, tid, s_par, s_cen, s_red, s_min, s_inv, s_lut, s_lutn);
 }
 
 // Optional per-kernel timing (msn_profile_enable): CUDA events recorded on the launch
@@ -1116,9 +1211,9 @@ static bool sad_tensor_map(const FusedGeom& g, int H, int N, const float* base, 
 
 // One launch of an instantiation; the dynamic shared-memory opt-in is set once per instantiation
 // and device, not per launch.
-template <int DMAX, bool kTma, bool kSlabA>
+template <int DMAX, bool kTma, int kMode>
 static int launch_inst(const FusedArgs& a, const CUtensorMap& map, long long tiles, cudaStream_t s) {
-  auto kern = ms_fused_kernel<DMAX, kTma, kSlabA>;
+  auto kern = ms_fused_kernel<DMAX, kTma, kMode>;
   constexpr size_t smem = Lay<DMAX, kSlack>::bytes;
   static std::mutex mu;
   static unsigned long long done_mask = 0;   // bit per device ordinal (< 64)
@@ -1166,6 +1261,12 @@ int profile_read(double* prep_ms, double* sadsob_ms, double* fused_ms, int* call
   return 0;
 }
 
+size_t fused_exchange_bytes(int N, int H, int W, const msn_ms_params* p, int world) {
+  FusedGeom g = make_geom(N, H, W, p);
+  const long long tiles = (long long)N * g.h * ((g.w + kTile - 1) / kTile);
+  return (size_t)2 * 2 * tiles * world * kXLines * kXLineWords * sizeof(unsigned);   // [half][round][tile][rank][5][32]
+}
+
 bool fused_supported(const msn_ms_params* p, int Dn) {
   return p->censw == kCensW && p->nccw == kNccW && p->sadw == kSadW && p->sobelw == kSadW &&
          Dn <= kMaxFusedD;  // (image width is checked at launch; p->lr: the caller adds the right view)
@@ -1186,7 +1287,7 @@ size_t fused_workspace_bytes(int N, int H, int W, int Dn, const msn_ms_params* p
 // accumulate != 0 from the second slab on).
 int launch_ms_fused(const uint8_t* d_left, const uint8_t* d_right, int N, int H, int W, const msn_ms_params* p,
                     float* d_out, float* d_mins, char* workspace, cudaStream_t s, int out_D, int out_d0,
-                    int accumulate) {
+                    int accumulate, const msn_slab_exchange* xchg) {
   if (N == 0) return 0;
   FusedGeom g = make_geom(N, H, W, p);
   FusedWs ws;
@@ -1234,7 +1335,20 @@ int launch_ms_fused(const uint8_t* d_left, const uint8_t* d_right, int N, int H,
   a.k_ncc = aml_scale(p->ncc_sigma);
   a.k_sad = aml_scale(p->sad_sigma);
   a.tiles_x = (g.w + kTile - 1) / kTile;
+  memset(&a.xchg, 0, sizeof(a.xchg));
+  if (xchg) {
+    MSN_REQUIRE(!d_mins, "ms_slab_fused: the exchange path takes no minima buffer");
+    MSN_REQUIRE(xchg->world >= 1 && xchg->world <= kMaxRanks && xchg->rank >= 0 && xchg->rank < xchg->world,
+                "ms_slab_fused: rank %d / world %d out of range (at most %d ranks)", xchg->rank, xchg->world, kMaxRanks);
+    MSN_REQUIRE(xchg->epoch != 0, "ms_slab_fused: epoch must be > 0");
+    for (int r = 0; r < xchg->world; ++r) {
+      MSN_REQUIRE(xchg->tables[r] != nullptr, "ms_slab_fused: exchange table of rank %d is null", r);
+      a.xchg.peer[r] = reinterpret_cast<unsigned*>(xchg->tables[r]);
+    }
+    a.xchg.G = xchg->world; a.xchg.rank = xchg->rank; a.xchg.epoch = xchg->epoch;
+  }
   const long long tiles = (long long)N * g.h * a.tiles_x;
+  a.n_tiles = tiles;
   MSN_REQUIRE(tiles <= 2147483647LL, "ms_features: too many tiles for one launch");
   CUtensorMap sad_map;
   memset(&sad_map, 0, sizeof(sad_map));
@@ -1243,8 +1357,9 @@ int launch_ms_fused(const uint8_t* d_left, const uint8_t* d_right, int N, int H,
   a.DC = 2 * (((g.D + kGroups - 1) / kGroups + 1) / 2);   // phase 1 walks disparity pairs
 #define MSN_FUSED_LAUNCH(DMAX, TMA)                                                \
   {                                                                                \
-    if (d_mins) { if (launch_inst<DMAX, TMA, true>(a, sad_map, tiles, s)) return 1; } \
-    else { if (launch_inst<DMAX, TMA, false>(a, sad_map, tiles, s)) return 1; }    \
+    if (xchg) { if (launch_inst<DMAX, TMA, kModeXchg>(a, sad_map, tiles, s)) return 1; } \
+    else if (d_mins) { if (launch_inst<DMAX, TMA, kModeSlabA>(a, sad_map, tiles, s)) return 1; } \
+    else { if (launch_inst<DMAX, TMA, kModeFull>(a, sad_map, tiles, s)) return 1; }    \
   }
 #define MSN_FUSED_CASE(DMAX)                                                       \
   if (g.D <= DMAX) {                                                               \

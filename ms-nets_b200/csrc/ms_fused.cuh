@@ -16,7 +16,11 @@ size_t fused_workspace_bytes(int N, int H, int W, int Dn, const msn_ms_params* p
 // out_D / out_d0 / accumulate: see ms_fused.cu (slabs of one volume processed on one GPU).
 int launch_ms_fused(const uint8_t* d_left, const uint8_t* d_right, int N, int H, int W, const msn_ms_params* p,
                     float* d_out, float* d_mins, char* workspace, cudaStream_t s, int out_D = 0, int out_d0 = 0,
-                    int accumulate = 0);
+                    int accumulate = 0, const msn_slab_exchange* xchg = nullptr);
+// xchg != nullptr: this rank's disparity slab [p->d_begin, +p->d_count) with the AML minimum / denominator
+// traded with the other ranks INSIDE the kernel through their peer-mapped exchange tables (no d_mins, no
+// phases B/C).  Bytes of one rank's table:
+size_t fused_exchange_bytes(int N, int H, int W, const msn_ms_params* p, int world);
 constexpr int kFusedSlabD = 192;   // slab size when a volume above the fused kernel's limit is cut into slabs
 
 int profile_enable(int on);

@@ -176,6 +176,127 @@ class SlabShardedMSFeatures(object):
         return out
 
 
+class ExchangeSlabMSFeatures(object):
+    """Disparity-slab sharded MS volume with the exchange fused INTO the kernel (msn_ms_slab_fused_dev):
+    every rank calls this with the SAME pair(s) and receives its [N,8,D/G,h,w] slab.  A tile's raw costs
+    never leave shared memory; the per-pixel AML minima and partial denominators travel between the
+    ranks' GPUs inside the kernel, through exchange tables in peer-mapped device memory (NVLink /
+    NVSwitch writes), so the volume is written exactly once and torch.distributed only carries the
+    64-byte CUDA IPC handles at construction.
+
+    One process per GPU: the tables are cudaMalloc allocations exported with cudaIpcGetMemHandle and
+    all-gathered over `group`.  `connect=False` leaves the wiring to the caller (`table_ptr`, `wire`):
+    several virtual ranks inside one process, as the one-GPU tests do."""
+
+    def __init__(self, N, H, W, maxdisp=192, rank=None, world=None, group=None, device=None, connect=True, **kw):
+        import torch
+
+        from . import cbmv
+        dist = _dist()
+        if not torch.cuda.is_available():
+            raise _lib.MsnetsError("ExchangeSlabMSFeatures needs a CUDA device (no CPU fallback)")
+        if rank is None:
+            rank = dist.get_rank(group) if dist.is_initialized() else 0
+        if world is None:
+            world = dist.get_world_size(group) if dist.is_initialized() else 1
+        if world > 8:
+            raise ValueError("the fused slab exchange serves at most 8 ranks (one NVSwitch node)")
+        self.torch, self.group, self.rank, self.world = torch, group, rank, world
+        self.device = torch.device("cuda", torch.cuda.current_device()) if device is None else torch.device(device)
+        self.N, self.H, self.W = int(N), int(H), int(W)
+        self.d_begin, self.d_count = shard_range(maxdisp, rank, world)
+        if self.d_count < 1:
+            raise ValueError("more ranks than disparities")
+        if not kw.get("left_only", True):
+            raise NotImplementedError("slab sharding provides the 8-channel (left) volume")
+        self.params = cbmv.make_params(maxdisp, d_begin=self.d_begin, d_count=self.d_count, **kw)
+        # the table layout depends on the tile count only; size it with the widest slab so every rank agrees
+        self.shape = cbmv.output_shape(self.N, self.H, self.W, self.params)
+        self.h, self.w = self.shape[3], self.shape[4]
+        L = _lib.lib()
+        self._table = ctypes.c_void_p()
+        self._opened = []
+        self.epoch = 0
+        with torch.cuda.device(self.device):
+            nbytes = L.msn_ms_features_workspace_bytes(self.N, self.H, self.W, ctypes.byref(self.params))
+            self.table_bytes = L.msn_ms_slab_exchange_bytes(self.N, self.H, self.W, ctypes.byref(self.params), world)
+            if nbytes == 0 or self.table_bytes == 0:
+                raise _lib.MsnetsError(L.msn_last_error().decode())
+            self.workspace = torch.empty(nbytes + 256, dtype=torch.uint8, device=self.device)
+            _lib.check(L.msn_peer_alloc(self.table_bytes, ctypes.byref(self._table)))
+        self.xchg = _lib.SlabExchange()
+        self.xchg.world, self.xchg.rank = world, rank
+        self.xchg.tables[rank] = self._table.value
+        if connect:
+            self._connect_ipc()
+
+    @property
+    def table_ptr(self):
+        return self._table.value
+
+    def wire(self, table_ptrs):
+        """table_ptrs[r] = device pointer (valid on this device) of rank r's exchange table."""
+        if len(table_ptrs) != self.world or table_ptrs[self.rank] != self._table.value:
+            raise ValueError("wire: expected one pointer per rank, own table at index rank")
+        for r, ptr in enumerate(table_ptrs):
+            self.xchg.tables[r] = ptr
+
+    def _connect_ipc(self):
+        torch, L, dist = self.torch, _lib.lib(), _dist()
+        if self.world == 1:
+            return
+        handle = (ctypes.c_ubyte * 64)()
+        with torch.cuda.device(self.device):
+            _lib.check(L.msn_peer_export(self._table, handle))
+            mine = torch.tensor(list(handle), dtype=torch.uint8, device=self.device)
+            allh = torch.empty((self.world, 64), dtype=torch.uint8, device=self.device)
+            dist.all_gather_into_tensor(allh.view(-1), mine, group=self.group)
+            allh = allh.cpu().numpy()
+            for r in range(self.world):
+                if r == self.rank:
+                    continue
+                buf = (ctypes.c_ubyte * 64)(*[int(v) for v in allh[r]])
+                ptr = ctypes.c_void_p()
+                _lib.check(L.msn_peer_open(buf, ctypes.byref(ptr)))
+                self._opened.append(ptr)
+                self.xchg.tables[r] = ptr.value
+            dist.barrier(group=self.group)
+
+    def __call__(self, left, right, out=None):
+        torch, L = self.torch, _lib.lib()
+        for t in (left, right):
+            if t.dtype != torch.uint8 or tuple(t.shape) != (self.N, self.H, self.W) or not t.is_cuda \
+                    or not t.is_contiguous():
+                raise ValueError("expected contiguous uint8 CUDA tensors of shape %s" % ((self.N, self.H, self.W),))
+        if out is None:
+            out = torch.empty(self.shape, dtype=torch.float32, device=self.device)
+        self.epoch += 1
+        self.xchg.epoch = self.epoch & 0xFFFFFFFF or 1
+        with torch.cuda.device(self.device):
+            st = torch.cuda.current_stream().cuda_stream
+            _lib.check(L.msn_ms_slab_fused_dev(left.data_ptr(), right.data_ptr(), self.N, self.H, self.W,
+                                               ctypes.byref(self.params), ctypes.byref(self.xchg), out.data_ptr(),
+                                               self.workspace.data_ptr(), self.workspace.numel(), st))
+        return out
+
+    def close(self):
+        L = _lib.lib()
+        if self.torch.cuda.is_available():
+            self.torch.cuda.synchronize(self.device)
+        for ptr in self._opened:
+            L.msn_peer_close(ptr)
+        self._opened = []
+        if self._table:
+            L.msn_peer_free(self._table)
+            self._table = ctypes.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
 def slab_soft_argmin(logits_slab, d_begin, group=None):
     """Soft-argmin over a D-sharded logit volume: logits_slab [N,D/G,H,W] on each rank,
     d_begin = first disparity of the slab -> full-range disparity [N,H,W] on every rank."""

@@ -59,6 +59,49 @@ def test_slab_phases_match_single_pass(oracle):
     assert np.array_equal(got[:4], fused[:4]) and np.abs(got[4:] - fused[4:]).max() <= AML_ATOL
 
 
+def _virtual_exchange_ranks(L, R, D, border, world):
+    """`world` virtual ranks of the FUSED slab exchange inside one process on one GPU: one launch per
+    rank, each on its own stream, all resident at once (the tiles wait for each other's minima), tables
+    wired by plain device pointers."""
+    import torch
+    from msnets_b200 import sharding
+    N, (H, W) = 1, L.shape
+    l, r = torch.from_numpy(L[None]).cuda(), torch.from_numpy(R[None]).cuda()
+    ranks = [sharding.ExchangeSlabMSFeatures(N, H, W, maxdisp=D, rank=k, world=world, connect=False, board_h=border,
+                                             board_w_left=border, board_w_right=border) for k in range(world)]
+    ptrs = [x.table_ptr for x in ranks]
+    for x in ranks:
+        x.wire(ptrs)
+    outs = []
+    for frame in range(3):     # three frames: both halves of the double-buffered tables and an epoch wrap of the half
+        streams = [torch.cuda.Stream() for _ in ranks]
+        torch.cuda.synchronize()
+        outs = []
+        for x, st in zip(ranks, streams):
+            with torch.cuda.stream(st):
+                outs.append(x(l, r))
+        torch.cuda.synchronize()
+    vol = torch.cat(outs, dim=2)[0].cpu().numpy()
+    for x in ranks:
+        x.close()
+    return vol
+
+
+@pytest.mark.parametrize("world,H,W,D", [(1, 36, 70, 40), (2, 36, 70, 40), (2, 50, 116, 64), (4, 30, 84, 96)])
+def test_fused_slab_exchange_virtual_ranks(oracle, world, H, W, D):
+    """msn_ms_slab_fused_dev: the slab kernel with the min / denominator exchange inside the tile."""
+    import msnets_b200 as ms
+    L, R = bordered_pair(H, W, 11 + world, border=10, patches=True)
+    got = _virtual_exchange_ranks(L, R, D, 10, world)
+    want = oracle.ms_features(L, R, D)
+    assert got.shape == want.shape
+    assert np.array_equal(got[:4], want[:4])
+    assert np.abs(got[4:] - want[4:]).max() <= AML_ATOL
+    if world == 1:   # one rank: the same sums in the same order as the single-pass kernel
+        fused = ms.cbmv.ms_features(L, R, D, board_h=10, board_w_left=10, board_w_right=10)
+        assert np.array_equal(got, fused)
+
+
 def test_slab_wta_and_soft_argmin_single_rank(oracle):
     import torch
     import msnets_b200 as ms
