@@ -144,7 +144,7 @@ MSN_API int msn_ms_slab_phase_c_dev(float* d_out_ncdhw, const float* d_min_n4hw,
 
 /* Disparity-slab sharding, fused with its exchange (replaces phases A/B/C and the two
  * NCCL all-reduces between them when the slab fits the fused kernel: default windows, left view,
- * d_count <= 448).  Every rank calls this for the SAME pair(s) with its own slab in p->d_begin / d_count;
+ * d_count / subs <= 448).  Every rank calls this for the SAME pair(s) with its own slab in p->d_begin / d_count;
  * the kernel keeps a tile's costs in shared memory and trades the per-pixel AML minima and partial
  * denominators with the other ranks through their exchange tables -- peer-mapped device memory written
  * over NVLink / NVSwitch -- so the volume is written once (32 B per voxel) and never re-read.
@@ -157,8 +157,11 @@ typedef struct msn_slab_exchange {
   int world;
   int rank;
   unsigned epoch;
+  int subs;   /* 0 or 1: none.  > 1: every rank's slab is cut into `subs` equal sub-slabs that run as CTAs of the
+               * same launch and trade through the same tables (virtual ranks): slabs wider than the 256
+               * disparities a tile can park, on any number of GPUs including one.  Same value on every rank. */
 } msn_slab_exchange;
-MSN_API size_t msn_ms_slab_exchange_bytes(int N, int H, int W, const msn_ms_params* p, int world);
+MSN_API size_t msn_ms_slab_exchange_bytes(int N, int H, int W, const msn_ms_params* p, int world, int subs);
 MSN_API int msn_ms_slab_fused_dev(const uint8_t* d_left, const uint8_t* d_right, int N, int H, int W,
                           const msn_ms_params* p, const msn_slab_exchange* xchg, float* d_out_ncdhw,
                           void* d_workspace, size_t workspace_bytes, void* stream);

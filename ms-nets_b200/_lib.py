@@ -23,7 +23,8 @@ class MsParams(ctypes.Structure):
 
 class SlabExchange(ctypes.Structure):
     """struct msn_slab_exchange (include/msnets_b200.h)."""
-    _fields_ = [("tables", c_void_p * 8), ("world", c_int), ("rank", c_int), ("epoch", ctypes.c_uint)]
+    _fields_ = [("tables", c_void_p * 8), ("world", c_int), ("rank", c_int), ("epoch", ctypes.c_uint),
+                ("subs", c_int)]
 
 
 class MsnetsError(RuntimeError):
@@ -63,7 +64,7 @@ _SIGNATURES = {
                                         _P, _P, c_size_t, _P]),
     "msn_ms_slab_phase_b_dev": (c_int, [_P, _P, c_int, c_int, c_int, ctypes.POINTER(MsParams), _P, _P]),
     "msn_ms_slab_phase_c_dev": (c_int, [_P, _P, _P, c_int, c_int, c_int, ctypes.POINTER(MsParams), _P]),
-    "msn_ms_slab_exchange_bytes": (c_size_t, [c_int, c_int, c_int, ctypes.POINTER(MsParams), c_int]),
+    "msn_ms_slab_exchange_bytes": (c_size_t, [c_int, c_int, c_int, ctypes.POINTER(MsParams), c_int, c_int]),
     "msn_ms_slab_fused_dev": (c_int, [_P, _P, c_int, c_int, c_int, ctypes.POINTER(MsParams), _P, _P, _P, c_size_t, _P]),
     "msn_peer_alloc": (c_int, [c_size_t, ctypes.POINTER(c_void_p)]),
     "msn_peer_free": (c_int, [_P]),

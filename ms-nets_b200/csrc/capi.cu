@@ -645,15 +645,24 @@ int msn_ms_slab_phase_a_dev(const uint8_t* d_left, const uint8_t* d_right, int N
   return 0;
 }
 
-size_t msn_ms_slab_exchange_bytes(int N, int H, int W, const msn_ms_params* p, int world) {
+// the fused exchange serves the default windows, the left view and sub-slabs the fused kernel can park
+static bool exchange_ok(const msn_ms_params* p, const Geometry& g, int W, int subs) {
+  if (p->lr || subs < 1 || g.Dn % subs != 0) return false;
+  const int ds = g.Dn / subs;
+  return fused_supported(p, ds) && sadsob_fast_pitch(W + 35) > 0 && !force_generic();
+}
+
+size_t msn_ms_slab_exchange_bytes(int N, int H, int W, const msn_ms_params* p, int world, int subs) {
   Geometry g;
   if (resolve(p, N, H, W, &g, "ms_slab_exchange_bytes")) return 0;
+  if (subs < 1) subs = 1;
   if (world < 1 || world > 8) { set_error("ms_slab_exchange_bytes: world %d not in 1..8", world); return 0; }
-  if (!slab_fused(p, g, W) || g.Dn > 448) {
-    set_error("ms_slab_exchange_bytes: the fused exchange needs the default windows, the left view and a slab of at most 448 disparities");
+  if (!exchange_ok(p, g, W, subs)) {
+    set_error("ms_slab_exchange_bytes: the fused exchange needs the default windows, the left view and %d equal "
+              "sub-slabs of at most 448 disparities (slab: %d)", subs, g.Dn);
     return 0;
   }
-  return fused_exchange_bytes(N, H, W, p, world);
+  return fused_exchange_bytes(N, H, W, p, world * subs);
 }
 
 int msn_ms_slab_fused_dev(const uint8_t* d_left, const uint8_t* d_right, int N, int H, int W, const msn_ms_params* p,
@@ -662,8 +671,8 @@ int msn_ms_slab_fused_dev(const uint8_t* d_left, const uint8_t* d_right, int N, 
   Geometry g;
   TRY(resolve(p, N, H, W, &g, "ms_slab_fused"));
   MSN_REQUIRE(d_left && d_right && d_out && d_workspace && xchg, "ms_slab_fused: null pointer argument");
-  MSN_REQUIRE(slab_fused(p, g, W) && g.Dn <= 448,
-              "ms_slab_fused: needs the default windows, the left view and a slab of at most 448 disparities "
+  MSN_REQUIRE(exchange_ok(p, g, W, xchg->subs > 1 ? xchg->subs : 1),
+              "ms_slab_fused: needs the default windows, the left view and equal sub-slabs of at most 448 disparities "
               "(use msn_ms_slab_phase_*_dev otherwise)");
   const size_t need = fused_workspace_bytes(N, H, W, g.Dn, p) + 256;
   MSN_REQUIRE(workspace_bytes >= need, "ms_slab_fused: workspace too small (%zu < %zu)", workspace_bytes, need);

@@ -64,6 +64,7 @@ struct FusedGeom {
   int N, H, W, h, w, bh, bwl;
   int D;    // disparities handled by this launch: [d0, d0 + D)
   int d0;   // first disparity (> 0 only for a disparity slab)
+  int Dl;   // disparities of the whole launch (= D unless the launch is cut into sub-slabs, kModeXchg)
   int Hp, Wp, padL;
   int sxo, Ws;   // SAD-of-Sobel scratch: column offset and row pitch (tile starts land on 16 B)
   __host__ __device__ size_t img_px() const { return (size_t)Hp * Wp; }
@@ -74,6 +75,7 @@ FusedGeom make_geom(int N, int H, int W, const msn_ms_params* p) {
   g.N = N; g.H = H; g.W = W;
   g.d0 = p->d_count > 0 ? p->d_begin : 0;
   g.D = p->d_count > 0 ? p->d_count : p->ndisp;
+  g.Dl = g.D;
   g.bh = p->board_h; g.bwl = p->board_w_left;
   g.h = H - 2 * p->board_h;
   g.w = W - p->board_w_left - p->board_w_right;
@@ -109,8 +111,8 @@ struct FusedWs {
     AR = (float*)take((np + 16) * sizeof(float));
     CR = (double*)take((np + 16) * sizeof(double));
     luts = (float*)take(384 * sizeof(float));
-    sadsob = (float*)take((size_t)g.N * g.D * g.H * g.Ws * sizeof(float) + 256);
-    sad_ws = take(sadsob_workspace_bytes_n(g.N, g.H, g.W, g.D, kSadW));
+    sadsob = (float*)take((size_t)g.N * g.Dl * g.H * g.Ws * sizeof(float) + 256);
+    sad_ws = take(sadsob_workspace_bytes_n(g.N, g.H, g.W, g.Dl, kSadW));
     total = off;
   }
 };
@@ -215,8 +217,9 @@ ms_prep_kernel(const uint8_t* __restrict__ left, const uint8_t* __restrict__ rig
 constexpr int kMaxRanks = 8;
 constexpr int kXLineWords = 32, kXLines = 5;   // 128 values travel as 5 lines of 31 values + 1 flag word
 struct FusedXchg {
-  unsigned* peer[kMaxRanks];
-  int G, rank;
+  unsigned* peer[kMaxRanks];   // table of every (physical) rank; peer[rank] is this rank's own
+  int G, rank;        // physical ranks (GPUs)
+  int V, v;           // virtual ranks = sources per tile (G x sub-slabs per launch) and this CTA's index among them
   unsigned epoch;     // > 0, the same on every rank, +1 per frame: flag value and (its low bit) table half
 };
 struct FusedArgs {
@@ -241,6 +244,7 @@ struct FusedArgs {
   // peer-mapped device pointers.  See tile_back_half.
   FusedXchg xchg;
   long long n_tiles;
+  int subs;             // kModeXchg: sub-slabs of g.D disparities the launch's slab is cut into (virtual ranks)
 };
 
 constexpr int kTile = 32;   // pixels per tile: one output row segment of 128 bytes
@@ -380,9 +384,15 @@ __device__ __forceinline__ f32x2 abs2(f32x2 v) {
 
 struct TileId {
   int n, y, x0;
+  int d0;     // first disparity of this CTA (the launch's, plus its sub-slab offset)
+  int sub0;   // offset of this CTA's sub-slab inside the launch's slab (0 unless the launch is cut, kModeXchg)
+  int v;      // kModeXchg: this CTA's virtual rank (row in the exchange tables)
 };
-__device__ __forceinline__ TileId decode_tile(int tile, const FusedArgs& a) {
+__device__ __forceinline__ TileId decode_tile(int tile, const FusedArgs& a, int sub = 0) {
   TileId t;
+  t.sub0 = sub * a.g.D;
+  t.d0 = a.g.d0 + t.sub0;
+  t.v = a.xchg.v + sub;
   const int xt = tile % a.tiles_x;
   tile /= a.tiles_x;
   t.y = tile % a.g.h;
@@ -399,7 +409,7 @@ __device__ __forceinline__ void stage_right(const FusedArgs& a, const TileId& t,
   const FusedGeom& g = a.g;
   const int D = g.D;
   const int RWn = D + kTile - 1 + L::kSl;
-  const int XbaseP = t.x0 + g.bwl - (g.d0 + D - 1) - L::kSl + g.padL;
+  const int XbaseP = t.x0 + g.bwl - (t.d0 + D - 1) - L::kSl + g.padL;
   const int Yp = t.y + g.bh + kPadT;
   const size_t img_off = (size_t)t.n * g.img_px();
   const uint4* gd = a.descR + img_off + (size_t)Yp * g.Wp + XbaseP;
@@ -433,7 +443,7 @@ __device__ __forceinline__ void stage_rows_tma(const FusedArgs& a, const TileId&
   const FusedGeom& g = a.g;
   const int D = g.D;
   const int RWn = D + kTile - 1 + L::kSl;
-  const int XbaseP = t.x0 + g.bwl - (g.d0 + D - 1) - L::kSl + g.padL;
+  const int XbaseP = t.x0 + g.bwl - (t.d0 + D - 1) - L::kSl + g.padL;
   const int Yp = t.y + g.bh + kPadT;
   const size_t img_off = (size_t)t.n * g.img_px();
   const int fstart = (XbaseP - 2) & ~3;
@@ -458,7 +468,7 @@ __device__ __forceinline__ void stage_sad_tma(const FusedArgs& a, const CUtensor
                                               float* park_plane1, unsigned long long* bar_sad) {
   const FusedGeom& g = a.g;
   mbar_expect_tx(bar_sad, (unsigned)g.D * kTile * 4u);
-  tma_load_3d(park_plane1, sad_map, t.x0 + g.bwl + g.sxo, t.y + g.bh, t.n * g.D, bar_sad);  // inner coordinate % 4 == 0
+  tma_load_3d(park_plane1, sad_map, t.x0 + g.bwl + g.sxo, t.y + g.bh, t.n * g.Dl + t.sub0, bar_sad);  // inner coordinate % 4 == 0
 }
 
 // A pixel's own left-image data: census code, stats, 5x5 float window.  Loaded straight from
@@ -657,15 +667,15 @@ __device__ __forceinline__ Phase1Out phase1_tile(const FusedArgs& a, const TileI
   }
   // validity: cost(y,x,d) exists iff the window origin is inside and x - wc >= d (and d < D)
   // (dmax_* are local to the launch: disparity d0 + d of the image is step d here)
-  const int dmax_cen = min(D - 1, ((Y >= 5 && Y < H - 6 && X >= 5 && X < W - 6) ? X - 5 : -1) - g.d0);
-  const int dmax_ncc = min(D - 1, ((Y >= 1 && Y < H - 2 && X >= 1 && X < W - 2) ? X - 1 : -1) - g.d0);
-  const int dmax_sad = min(D - 1, ((Y >= 2 && Y < H - 3 && X >= 2 && X < W - 3) ? X - 2 : -1) - g.d0);
+  const int dmax_cen = min(D - 1, ((Y >= 5 && Y < H - 6 && X >= 5 && X < W - 6) ? X - 5 : -1) - t.d0);
+  const int dmax_ncc = min(D - 1, ((Y >= 1 && Y < H - 2 && X >= 1 && X < W - 2) ? X - 1 : -1) - t.d0);
+  const int dmax_sad = min(D - 1, ((Y >= 2 && Y < H - 3 && X >= 2 && X < W - 3) ? X - 2 : -1) - t.d0);
 
   const uint4* s_desc = reinterpret_cast<const uint4*>(stage + L::st_desc);
   const double* s_c = reinterpret_cast<const double*>(stage + L::st_c);
   const float* s_rf = reinterpret_cast<const float*>(stage + L::st_rf);
   // shared index of right column X - d is ir = px + L::kSl + (D-1) - d; falls by one per step
-  const int XbaseP = t.x0 + g.bwl - (g.d0 + D - 1) - L::kSl + g.padL;
+  const int XbaseP = t.x0 + g.bwl - (t.d0 + D - 1) - L::kSl + g.padL;
   const int shift = (XbaseP - 2) & 3;
   const int ir0 = px + L::kSl + (D - 1) - d_lo;
   P1State<L> st;
@@ -896,16 +906,16 @@ __device__ __forceinline__ float den_chain(const FusedArgs& a, int warp, int lan
 // flag round trip.  Tables are double-buffered by the epoch's low bit: a rank can only be two frames ahead
 // of a peer's unread data after that peer has finished the frame in between.
 __device__ __forceinline__ size_t xchg_line0(const FusedArgs& a, int round, long long tile, int src) {
-  return (((((size_t)(a.xchg.epoch & 1u) * 2 + round) * a.n_tiles + tile) * a.xchg.G + src) * kXLines) *
+  return (((((size_t)(a.xchg.epoch & 1u) * 2 + round) * a.n_tiles + tile) * a.xchg.V + src) * kXLines) *
          kXLineWords;
 }
 // Warps 0-3: the 128 values in vals[] (shared memory) go to every rank's table as lines k = warp (+ 4 for warp 0).
-__device__ __forceinline__ void xchg_publish(const FusedArgs& a, int round, long long tile, int warp, int lane,
+__device__ __forceinline__ void xchg_publish(const FusedArgs& a, int round, long long tile, int v, int warp, int lane,
                                              const float* vals) {
   for (int k = warp; k < kXLines; k += 4) {
     const int i = 31 * k + lane;
     const unsigned w = (lane == 31) ? a.xchg.epoch : ((i < 128) ? __float_as_uint(vals[i]) : 0u);
-    const size_t off = xchg_line0(a, round, tile, a.xchg.rank) + (size_t)k * kXLineWords + lane;
+    const size_t off = xchg_line0(a, round, tile, v) + (size_t)k * kXLineWords + lane;
     for (int p = 0; p < a.xchg.G; ++p)
       asm volatile("st.volatile.global.u32 [%0], %1;" ::"l"(a.xchg.peer[p] + off), "r"(w) : "memory");
   }
@@ -919,7 +929,7 @@ __device__ __forceinline__ void xchg_collect(const FusedArgs& a, int round, long
   const unsigned* mine = a.xchg.peer[a.xchg.rank];
   for (int k = warp; k < kXLines; k += 4) {
     float acc = kSum ? 0.f : kFill;
-    for (int src = 0; src < a.xchg.G; ++src) {
+    for (int src = 0; src < a.xchg.V; ++src) {
       const unsigned* line = mine + xchg_line0(a, round, tile, src) + (size_t)k * kXLineWords;
       unsigned w;
       long long t0 = 0;
@@ -976,12 +986,12 @@ __device__ __forceinline__ void tile_back_half(const FusedArgs& a, const TileId&
   const int q4 = (tid & 7) * 4;
   // 128-bit stores need 16-byte aligned rows
   const bool vec_ok = ((g.w & 3) == 0) && ((reinterpret_cast<uintptr_t>(a.out) & 15) == 0);
-  float* orow = a.out + (size_t)t.n * a.out_channels * chan + (size_t)a.out_d0 * plane + (size_t)t.y * g.w + (t.x0 + q4);
+  float* orow = a.out + (size_t)t.n * a.out_channels * chan + (size_t)(a.out_d0 + t.sub0) * plane + (size_t)t.y * g.w + (t.x0 + q4);
   const int nlive = min(4, g.w - (t.x0 + q4));  // live pixels of this quad (<= 0: none)
   const bool vec = vec_ok && nlive == 4;
   if (warp < 4) {
     if (kXchg) {
-      xchg_publish(a, 0, tile, warp, lane, s_inv);
+      xchg_publish(a, 0, tile, t.v, warp, lane, s_inv);
       xchg_collect<false>(a, 0, tile, warp, lane, s_min);
       bar_sync_128();
     }
@@ -990,7 +1000,7 @@ __device__ __forceinline__ void tile_back_half(const FusedArgs& a, const TileId&
     if (kXchg) {
       s_red[warp * kTile + lane] = den;        // (the per-group minima are dead since the barrier above)
       bar_sync_128();
-      xchg_publish(a, 1, tile, warp, lane, s_red);
+      xchg_publish(a, 1, tile, t.v, warp, lane, s_red);
       xchg_collect<true>(a, 1, tile, warp, lane, s_red + 4 * kTile);
       bar_sync_128();
       den = s_red[4 * kTile + warp * kTile + lane];
@@ -1085,8 +1095,7 @@ __device__ __forceinline__ void tile_slab_a(const FusedArgs& a, const TileId& t,
 // kMode: kModeFull the whole volume; kModeSlabA stop after phase 1 and emit what slab.cu's phase A emits
 // (tile_slab_a); kModeXchg a rank's disparity slab, minima and denominators traded inside the tile.
 template <int DMAX, bool kTma, int kMode>
-__global__ void __launch_bounds__(256, 2)
-ms_fused_kernel(const FusedArgs a, const __grid_constant__ CUtensorMap sad_map) {
+__device__ __forceinline__ void fused_tile(const FusedArgs& a, const CUtensorMap& sad_map, long long tile, int sub) {
   using L = Lay<DMAX, kSlack>;
   constexpr int NT = 256;
   constexpr int PS = L::PS;
@@ -1104,7 +1113,7 @@ ms_fused_kernel(const FusedArgs a, const __grid_constant__ CUtensorMap sad_map) 
   const int tid = threadIdx.x;
   const int px = tid % kTile;             // phase 1: this thread's pixel ...
   const int grp = tid / kTile;            // ... and d-group
-  const TileId t = decode_tile(blockIdx.x, a);
+  const TileId t = decode_tile((int)tile, a, sub);
   const int d_lo = grp * a.DC;
   const int d_end = min(D, d_lo + a.DC);  // real disparities of this thread: [d_lo, d_end)
   if (kTma) {
@@ -1119,7 +1128,7 @@ ms_fused_kernel(const FusedArgs a, const __grid_constant__ CUtensorMap sad_map) 
   } else {
     // sadsob costs of this thread's own disparities: async global -> parked plane 1
     const size_t splane = (size_t)g.H * g.Ws;
-    const float* src = a.sadsob + ((size_t)t.n * D * g.H + (t.y + g.bh)) * g.Ws + (t.x0 + px + g.bwl + g.sxo) +
+    const float* src = a.sadsob + (((size_t)t.n * g.Dl + t.sub0) * g.H + (t.y + g.bh)) * g.Ws + (t.x0 + px + g.bwl + g.sxo) +
                        (size_t)d_lo * splane;
     float* dst = s_par + PS + d_lo * kTile + px;
     for (int d = d_lo; d < d_end; ++d, src += splane, dst += kTile) cp_async4(dst, src);
@@ -1140,7 +1149,19 @@ ms_fused_kernel(const FusedArgs a, const __grid_constant__ CUtensorMap sad_map) 
   finish_phase1<L>(s_par, s_red, o, px, grp, d_lo, d_end);
   __syncthreads();
   if (kMode == kModeSlabA) tile_slab_a<L>(a, t, tid, s_par, s_cen, s_red, s_lutn);
-  else tile_back_half<L, kMode == kModeXchg>(a, t, blockIdx.x, tid, s_par, s_cen, s_red, s_min, s_inv, s_lut, s_lutn);
+  else tile_back_half<L, kMode == kModeXchg>(a, t, tile, tid, s_par, s_cen, s_red, s_min, s_inv, s_lut, s_lutn);
+}
+
+template <int DMAX, bool kTma, int kMode>
+__global__ void __launch_bounds__(256, 2)
+ms_fused_kernel(const FusedArgs a, const __grid_constant__ CUtensorMap sad_map) {
+  if (kMode == kModeXchg) {
+    // CTA = (tile, sub-slab), sub-slab fastest: the CTAs that wait for each other's minima are dispatched
+    // together.  A sub-slab is a virtual rank: its own disparity offset, its own row in the exchange tables.
+    fused_tile<DMAX, kTma, kMode>(a, sad_map, blockIdx.x / (unsigned)a.subs, (int)(blockIdx.x % (unsigned)a.subs));
+  } else {
+    fused_tile<DMAX, kTma, kMode>(a, sad_map, blockIdx.x, 0);
+  }
 }
 
 // Optional per-kernel timing (msn_profile_enable): CUDA events recorded on the launch
@@ -1184,7 +1205,7 @@ static bool tma_disabled() {
 
 // 3-D tensor map over the SAD-of-Sobel scratch [N*D][H][Ws], box 32 x 1 x D (encoded once per scratch)
 static bool sad_tensor_map(const FusedGeom& g, int H, int N, const float* base, CUtensorMap* out) {
-  const MapKey key{base, g.Ws, H, N * g.D, g.D};
+  const MapKey key{base, g.Ws, H, N * g.Dl, g.D};
   {
     std::lock_guard<std::mutex> lk(g_map_mu);
     for (auto& kv : g_maps)
@@ -1195,7 +1216,7 @@ static bool sad_tensor_map(const FusedGeom& g, int H, int N, const float* base, 
   }
   PFN_encodeTiled enc = get_encode_fn();
   if (!enc) return false;
-  const cuuint64_t gdim[3] = {(cuuint64_t)g.Ws, (cuuint64_t)H, (cuuint64_t)N * g.D};
+  const cuuint64_t gdim[3] = {(cuuint64_t)g.Ws, (cuuint64_t)H, (cuuint64_t)N * g.Dl};
   const cuuint64_t gstr[2] = {(cuuint64_t)g.Ws * 4, (cuuint64_t)H * g.Ws * 4};
   const cuuint32_t box[3] = {(cuuint32_t)kTile, 1u, (cuuint32_t)g.D};
   const cuuint32_t estr[3] = {1u, 1u, 1u};
@@ -1226,7 +1247,7 @@ static int launch_inst(const FusedArgs& a, const CUtensorMap& map, long long til
       if (dev < 64) done_mask |= 1ull << dev;
     }
   }
-  kern<<<(unsigned)tiles, 256, smem, s>>>(a, map);
+  kern<<<(unsigned)(tiles * (kMode == kModeXchg ? a.subs : 1)), 256, smem, s>>>(a, map);
   return 0;
 }
 
@@ -1261,10 +1282,10 @@ int profile_read(double* prep_ms, double* sadsob_ms, double* fused_ms, int* call
   return 0;
 }
 
-size_t fused_exchange_bytes(int N, int H, int W, const msn_ms_params* p, int world) {
+size_t fused_exchange_bytes(int N, int H, int W, const msn_ms_params* p, int sources) {
   FusedGeom g = make_geom(N, H, W, p);
   const long long tiles = (long long)N * g.h * ((g.w + kTile - 1) / kTile);
-  return (size_t)2 * 2 * tiles * world * kXLines * kXLineWords * sizeof(unsigned);   // [half][round][tile][rank][5][32]
+  return (size_t)2 * 2 * tiles * sources * kXLines * kXLineWords * sizeof(unsigned);   // [half][round][tile][source][5][32]
 }
 
 bool fused_supported(const msn_ms_params* p, int Dn) {
@@ -1293,6 +1314,8 @@ int launch_ms_fused(const uint8_t* d_left, const uint8_t* d_right, int N, int H,
   FusedWs ws;
   ws.carve(workspace, g);
   MSN_REQUIRE(2 * N <= 65535 && g.Hp <= 65535, "ms_features: batch or image too large for one launch");
+  const int subs = (xchg && xchg->subs > 1) ? xchg->subs : 1;
+  MSN_REQUIRE(g.Dl % subs == 0, "ms_slab_fused: %d disparities do not split into %d equal sub-slabs", g.Dl, subs);
 
   bool prof;
   ProfRec rec;
@@ -1313,9 +1336,10 @@ int launch_ms_fused(const uint8_t* d_left, const uint8_t* d_right, int N, int H,
                                        ws.luts, aml_scale(p->cens_sigma));
   MSN_LAUNCH_OK();
   if (prof) MSN_CUDA_OK(cudaEventRecord(rec.ev[1], s));
-  if (launch_sadsob5_padded(ws.sob[0], ws.sob[1], N, H, W, g.D, g.d0, ws.sadsob + g.sxo, ws.sad_ws, s)) return 1;
+  if (launch_sadsob5_padded(ws.sob[0], ws.sob[1], N, H, W, g.Dl, g.d0, ws.sadsob + g.sxo, ws.sad_ws, s)) return 1;
   if (prof) MSN_CUDA_OK(cudaEventRecord(rec.ev[2], s));
 
+  g.D = g.Dl / subs;   // what one CTA handles (the scan above covered the launch's whole slab)
   FusedArgs a;
   a.g = g;
   a.descL = ws.desc[0]; a.descR = ws.desc[1];
@@ -1346,10 +1370,12 @@ int launch_ms_fused(const uint8_t* d_left, const uint8_t* d_right, int N, int H,
       a.xchg.peer[r] = reinterpret_cast<unsigned*>(xchg->tables[r]);
     }
     a.xchg.G = xchg->world; a.xchg.rank = xchg->rank; a.xchg.epoch = xchg->epoch;
+    a.xchg.V = xchg->world * subs; a.xchg.v = xchg->rank * subs;
   }
+  a.subs = subs;
   const long long tiles = (long long)N * g.h * a.tiles_x;
   a.n_tiles = tiles;
-  MSN_REQUIRE(tiles <= 2147483647LL, "ms_features: too many tiles for one launch");
+  MSN_REQUIRE(tiles * subs <= 2147483647LL, "ms_features: too many tiles for one launch");
   CUtensorMap sad_map;
   memset(&sad_map, 0, sizeof(sad_map));
   bool use_tma = g.D <= 256 && !tma_disabled();

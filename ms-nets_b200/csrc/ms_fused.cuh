@@ -20,7 +20,7 @@ int launch_ms_fused(const uint8_t* d_left, const uint8_t* d_right, int N, int H,
 // xchg != nullptr: this rank's disparity slab [p->d_begin, +p->d_count) with the AML minimum / denominator
 // traded with the other ranks INSIDE the kernel through their peer-mapped exchange tables (no d_mins, no
 // phases B/C).  Bytes of one rank's table:
-size_t fused_exchange_bytes(int N, int H, int W, const msn_ms_params* p, int world);
+size_t fused_exchange_bytes(int N, int H, int W, const msn_ms_params* p, int sources);   // sources = ranks x sub-slabs
 constexpr int kFusedSlabD = 192;   // slab size when a volume above the fused kernel's limit is cut into slabs
 
 int profile_enable(int on);

@@ -188,6 +188,16 @@ class ExchangeSlabMSFeatures(object):
     all-gathered over `group`.  `connect=False` leaves the wiring to the caller (`table_ptr`, `wire`):
     several virtual ranks inside one process, as the one-GPU tests do."""
 
+    MAX_TILE_D = 192    # widest sub-slab (the fused kernel's TMA instantiations park up to 256 disparities)
+
+    @staticmethod
+    def sub_slabs(maxdisp, world):
+        """Sub-slabs per rank: the widest rank slab cut into equal parts of at most MAX_TILE_D disparities
+        (the same number on every rank); None when some rank's slab does not divide evenly."""
+        counts = [shard_range(maxdisp, r, world)[1] for r in range(world)]
+        subs = -(-max(counts) // ExchangeSlabMSFeatures.MAX_TILE_D)
+        return subs if all(c % subs == 0 and c > 0 for c in counts) else None
+
     def __init__(self, N, H, W, maxdisp=192, rank=None, world=None, group=None, device=None, connect=True, **kw):
         import torch
 
@@ -209,8 +219,11 @@ class ExchangeSlabMSFeatures(object):
             raise ValueError("more ranks than disparities")
         if not kw.get("left_only", True):
             raise NotImplementedError("slab sharding provides the 8-channel (left) volume")
+        self.subs = self.sub_slabs(maxdisp, world)
+        if self.subs is None:
+            raise ValueError("maxdisp=%d over %d ranks does not cut into equal sub-slabs: use SlabShardedMSFeatures"
+                             % (maxdisp, world))
         self.params = cbmv.make_params(maxdisp, d_begin=self.d_begin, d_count=self.d_count, **kw)
-        # the table layout depends on the tile count only; size it with the widest slab so every rank agrees
         self.shape = cbmv.output_shape(self.N, self.H, self.W, self.params)
         self.h, self.w = self.shape[3], self.shape[4]
         L = _lib.lib()
@@ -219,13 +232,14 @@ class ExchangeSlabMSFeatures(object):
         self.epoch = 0
         with torch.cuda.device(self.device):
             nbytes = L.msn_ms_features_workspace_bytes(self.N, self.H, self.W, ctypes.byref(self.params))
-            self.table_bytes = L.msn_ms_slab_exchange_bytes(self.N, self.H, self.W, ctypes.byref(self.params), world)
+            self.table_bytes = L.msn_ms_slab_exchange_bytes(self.N, self.H, self.W, ctypes.byref(self.params), world,
+                                                            self.subs)
             if nbytes == 0 or self.table_bytes == 0:
                 raise _lib.MsnetsError(L.msn_last_error().decode())
             self.workspace = torch.empty(nbytes + 256, dtype=torch.uint8, device=self.device)
             _lib.check(L.msn_peer_alloc(self.table_bytes, ctypes.byref(self._table)))
         self.xchg = _lib.SlabExchange()
-        self.xchg.world, self.xchg.rank = world, rank
+        self.xchg.world, self.xchg.rank, self.xchg.subs = world, rank, self.subs
         self.xchg.tables[rank] = self._table.value
         if connect:
             self._connect_ipc()
