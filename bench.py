@@ -240,6 +240,14 @@ def run_ours(args):
     torch.cuda.synchronize()
     sa_ms = e0.elapsed_time(e1) / args.steps
 
+    slab = None
+    if world > 1:
+        # BASELINE configs[4] on the same launch: one Middlebury-shaped frame, disparity-slab sharded over the
+        # ranks -- the one mode of the path with a data-plane exchange between the GPUs
+        del feats, logits, disp, stage_l, stage_r, disp2, dev_l, dev_r, ex
+        torch.cuda.empty_cache()
+        slab = slab_config_m(dev, rank, world)
+
     if rank != 0:
         if world > 1:
             dist.destroy_process_group()
@@ -302,9 +310,84 @@ def run_ours(args):
         "cpu_baseline": cpu,
         "numpy_dropin": dropin,
     }
+    if slab is not None:
+        line["slab_config_m"] = slab
     print(json.dumps(line))
     if world > 1:
         dist.destroy_process_group()
+
+
+def slab_config_m(dev, rank, world, steps=3, warmup=2):
+    """BASELINE configs[4]: one Middlebury-shaped 1984x2880, D=640 frame, every rank owning D/world
+    disparities.  Per frame: the slab volume through ExchangeSlabMSFeatures (minima / denominators traded
+    inside the kernel over peer-mapped memory; falls back to the three-phase NCCL path when the slab does not
+    cut into equal sub-slabs), WTA over the sharded census channel (int64 key all-reduce) and soft-argmin over
+    a sharded logit volume (all-gather of partials).  Timed with CUDA events, max over ranks."""
+    import torch
+    import torch.distributed as dist
+    from msnets_b200 import sharding
+    from tests._synth import bordered_pair
+    H, W, D, B = 1984, 2880, 640, BORDER
+    L, R = bordered_pair(H, W, 99, border=B, shift=13)
+    l, r = torch.from_numpy(L[None]).to(dev), torch.from_numpy(R[None]).to(dev)
+    mode = "exchange"
+    try:
+        ex = sharding.ExchangeSlabMSFeatures(1, H + 2 * B, W + 2 * B, maxdisp=D, board_h=B, board_w_left=B,
+                                             board_w_right=B)
+    except ValueError:
+        mode = "phases"
+        ex = sharding.SlabShardedMSFeatures(1, H + 2 * B, W + 2 * B, maxdisp=D, board_h=B, board_w_left=B,
+                                            board_w_right=B)
+    out = torch.empty(ex.shape, dtype=torch.float32, device=dev)
+    gen = torch.Generator(device=dev)
+    gen.manual_seed(77 + rank)
+    logits = torch.randn((1, ex.d_count, H, W), generator=gen, device=dev, dtype=torch.float32)
+
+    def step():
+        ex(l, r, out=out)
+        am, m1 = sharding.slab_wta(out[0, 0], ex.d_begin, layout="dhw")
+        return am, sharding.slab_soft_argmin(logits, ex.d_begin)
+
+    for _ in range(warmup):
+        step()
+    torch.cuda.synchronize()
+    dist.barrier()
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(steps):
+        am, disp = step()
+    e1.record()
+    torch.cuda.synchronize()
+    t = torch.tensor([e0.elapsed_time(e1) / steps], device=dev, dtype=torch.float64)
+    dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms = float(t.item())
+    col = out[0, 4:8].sum(1)                      # AML columns over ALL ranks' disparities sum to 1
+    dist.all_reduce(col, op=dist.ReduceOp.SUM)
+    err = float((col[col > 0.5] - 1).abs().max())
+    peak, _ = peaks()
+    vox = D * H * W
+    tiles = H * ((W + 31) // 32)
+    subs = getattr(ex, "subs", 1) or 1
+    res = {
+        "workload": "configs[4]: Middlebury-shaped 1984x2880 D=640, one frame, disparity-slab sharded x%d "
+                    "(MS volume slab [1,8,%d,1984,2880] per GPU + WTA + soft-argmin merges)" % (world, ex.d_count),
+        "mode": mode, "ms_per_frame": round(ms, 3), "frames_per_s": round(1e3 / ms, 2), "steps": steps,
+        "algorithmic_GB_per_gpu": round((32.0 + 4.0) * vox / world / 1e9, 2),
+        "GBps_per_gpu": round((32.0 + 4.0) * vox / world / ms / 1e6, 1),
+        "frac_of_hbm_peak_per_gpu": round((32.0 + 4.0) * vox / world / ms / 1e6 / peak, 4),
+        "collectives_per_frame": {
+            "aml_min_and_den": ("in-kernel: %d sub-slab(s) per rank push 2 x 640 B per tile to %d peer(s) over NVLink "
+                                "= %.1f MB out per rank" % (subs, world - 1, tiles * subs * 2 * 640 * (world - 1) / 1e6))
+            if mode == "exchange" else "2 x NCCL all_reduce over [4,1984,2880] f32 = 91.4 MB each",
+            "wta": "NCCL all_reduce(min) over [1984,2880] int64 keys = 45.7 MB",
+            "soft_argmin": "NCCL all_gather of [3,1984,2880] f32 partials = 68.6 MB per rank"},
+        "aml_column_sum_max_err": err,
+    }
+    del out, logits
+    if hasattr(ex, "close"):
+        ex.close()
+    return res
 
 
 # ---------------------------------------------------------------- reference --
