@@ -748,18 +748,26 @@ __device__ __forceinline__ void finish_phase1(float* s_par, float* s_red, const 
 //  rounded (= the true IEEE division NumPy does) for every k in 0..255, checked exhaustively in
 //  tests/test_host_math.py;  AML term = 2^(-(k-m)^2 k_cen), 0 for "no cost" -- what the table holds.
 #ifndef MSN_CEN_LUT
-#define MSN_CEN_LUT 0
+#define MSN_CEN_LUT 1      // bit 0: denominator chain, bit 1: channel 0, bit 2: phase 3.  Measured at config B
+                           // (ms/pair): 0 -> 0.796, 1 -> 0.777 (the census chain is phase 2's critical path:
+                           // a table load is its cheapest step), 3 -> 0.787, 7 -> 0.786
 #endif
+constexpr bool kCenLutDen = (MSN_CEN_LUT & 1) != 0, kCenLutCh0 = (MSN_CEN_LUT & 2) != 0, kCenLutP3 = (MSN_CEN_LUT & 4) != 0;
 constexpr bool kCenLut = MSN_CEN_LUT != 0;
+#ifndef MSN_BACK_UNROLL
+#define MSN_BACK_UNROLL 1
+#endif
+constexpr int kBackUnroll = MSN_BACK_UNROLL;   // sweeps of phases 2/3 (measured: 1 is best)
 __device__ __forceinline__ float cen_ch0(int cb, const float* s_lutn) {
-  if (kCenLut) return s_lutn[cb];
+  if (kCenLutCh0) return s_lutn[cb];
   const float k = (float)min(cb, 120);
   const float r = 1.0f / 120.0f;
   const float q = __fmul_rn(k, r);
   return __fmaf_rn(__fmaf_rn(-120.0f, q, k), r, q);
 }
+template <bool kLut>
 __device__ __forceinline__ float cen_e(int cb, int mc, const float* s_lut, float k_cen) {
-  if (kCenLut) return s_lut[min(cb - mc, 127)];
+  if (kLut) return s_lut[min(cb - mc, 127)];
   const float t = (float)(cb - mc);
   const float e = ex2_approx(-(t * t) * k_cen);
   return (cb - mc > 120) ? 0.f : e;
@@ -793,7 +801,7 @@ template <bool kVec>
 __device__ __forceinline__ void store_ch03(const float* s_par, const uint8_t* s_cen, const float* s_lutn, int PS,
                                            int q4, int d0, int d1, float* orow, size_t plane, size_t chan,
                                            int nlive) {
-#pragma unroll 1
+#pragma unroll(kBackUnroll)
   for (int d = d0; d < d1; d += 16) {
     const float* e0 = s_par + d * kTile + q4;
     const uchar4 cb = *reinterpret_cast<const uchar4*>(s_cen + d * kTile + q4);
@@ -841,15 +849,15 @@ __device__ __forceinline__ void phase3_quads(const float* s_par, const uint8_t* 
   const f32x2 nk1 = pk2(-k1, -k1), nk2 = pk2(-k2, -k2);
   const int mcx = (m_cen4.x == kFill) ? 0 : (int)m_cen4.x, mcy = (m_cen4.y == kFill) ? 0 : (int)m_cen4.y;
   const int mcz = (m_cen4.z == kFill) ? 0 : (int)m_cen4.z, mcw = (m_cen4.w == kFill) ? 0 : (int)m_cen4.w;
-#pragma unroll 1
+#pragma unroll(kBackUnroll)
   for (int d = dl; d < D; d += 32) {
     const float* e0 = s_par + d * kTile + q4;
     const uchar4 cb = *reinterpret_cast<const uchar4*>(s_cen + d * kTile + q4);
     const float4 v1 = *reinterpret_cast<const float4*>(e0);
     const float4 v2 = *reinterpret_cast<const float4*>(e0 + PS);
     const float4 v3 = *reinterpret_cast<const float4*>(e0 + 2 * PS);
-    const float4 a0 = make_float4(cen_e(cb.x, mcx, s_lut, k0) * i0.x, cen_e(cb.y, mcy, s_lut, k0) * i0.y,
-                                  cen_e(cb.z, mcz, s_lut, k0) * i0.z, cen_e(cb.w, mcw, s_lut, k0) * i0.w);
+    const float4 a0 = make_float4(cen_e<kCenLutP3>(cb.x, mcx, s_lut, k0) * i0.x, cen_e<kCenLutP3>(cb.y, mcy, s_lut, k0) * i0.y,
+                                  cen_e<kCenLutP3>(cb.z, mcz, s_lut, k0) * i0.z, cen_e<kCenLutP3>(cb.w, mcw, s_lut, k0) * i0.w);
     float4 a1, a2, a3;
     p3_quad(v1, mp1, ip1, nk1, a1);
     p3_quad(v2, mp2, ip2, nk2, a2);
@@ -874,11 +882,11 @@ __device__ __forceinline__ float den_chain(const FusedArgs& a, int warp, int lan
     for (int d0 = 0; d0 < Dfull; d0 += 8, c += 8 * kTile) {
       float ev[8];
 #pragma unroll
-      for (int j = 0; j < 8; ++j) ev[j] = cen_e(c[j * kTile], mc, s_lut, a.k_cen);
+      for (int j = 0; j < 8; ++j) ev[j] = cen_e<kCenLutDen>(c[j * kTile], mc, s_lut, a.k_cen);
 #pragma unroll
       for (int j = 0; j < 8; ++j) den = __fadd_rn(den, ev[j]);
     }
-    for (int d = Dfull; d < D; ++d, c += kTile) den = __fadd_rn(den, cen_e(c[0], mc, s_lut, a.k_cen));
+    for (int d = Dfull; d < D; ++d, c += kTile) den = __fadd_rn(den, cen_e<kCenLutDen>(c[0], mc, s_lut, a.k_cen));
   } else {
     const float kq = (warp == 1) ? a.k_ncc : a.k_sad;
     const f32x2 mm2 = pk2(mm, mm), nkq = pk2(-kq, -kq);
