@@ -116,6 +116,16 @@ MSN_API int msn_ms_features_dev(const uint8_t* d_left, const uint8_t* d_right, i
                         const msn_ms_params* p, float* d_out_ncdhw, void* d_workspace,
                         size_t workspace_bytes, void* stream);
 
+/* The same with the confidence by-products of the fused kernel (default windows, left view, D <= 448): for
+ * each of channels 0-3 the winner-take-all disparity with np.argmin's tie rule -- what main_msnet.py:443-448
+ * computes on the host from a copy of the whole volume -- plus the smallest and second smallest channel value
+ * (second-min / peak-ratio), as [N][4][h][w] planes taken from the costs while they
+ * are still in shared memory: no extra pass over the volume.  All three pointers or none (NULL). */
+MSN_API int msn_ms_features_wta_dev(const uint8_t* d_left, const uint8_t* d_right, int N, int H, int W,
+                            const msn_ms_params* p, float* d_out_ncdhw, int32_t* d_wta_idx_n4hw,
+                            float* d_wta_min1_n4hw, float* d_wta_min2_n4hw, void* d_workspace,
+                            size_t workspace_bytes, void* stream);
+
 /* Measurement aid for bench.py: when enabled, msn_ms_features_dev brackets the kernels of
  * the fused sequence (prep | sadsob scan | fused volume) with CUDA events on the launch
  * stream; msn_profile_read synchronises, returns the summed milliseconds and the number
@@ -164,7 +174,13 @@ typedef struct msn_slab_exchange {
 MSN_API size_t msn_ms_slab_exchange_bytes(int N, int H, int W, const msn_ms_params* p, int world, int subs);
 MSN_API int msn_ms_slab_fused_dev(const uint8_t* d_left, const uint8_t* d_right, int N, int H, int W,
                           const msn_ms_params* p, const msn_slab_exchange* xchg, float* d_out_ncdhw,
-                          void* d_workspace, size_t workspace_bytes, void* stream);
+                          int32_t* d_wta_idx, float* d_wta_min1, float* d_wta_min2, void* d_workspace,
+                          size_t workspace_bytes, void* stream);
+/* d_wta_*: NULL, or the slab's WTA by-product as [subs][N][4][h][w] planes (absolute disparity indices), to be
+ * merged over ranks (all-gather, ranks ascending) and sub-slabs by msn_wta_merge_dev: parts [P][n] ordered by
+ * ascending disparity range -> the global (argmin, min, second min) of every pixel. */
+MSN_API int msn_wta_merge_dev(const int32_t* d_idx_parts, const float* d_min1_parts, const float* d_min2_parts,
+                      int parts, long long n, int32_t* d_idx, float* d_min1, float* d_min2, void* stream);
 /* Peer memory for the exchange tables: a zeroed cudaMalloc allocation on the current device, its 64-byte
  * CUDA IPC handle (to be all-gathered by the host side), and the mapping of another process's handle into
  * this one (peer access is enabled by the mapping).  One node only. */

@@ -65,7 +65,11 @@ _SIGNATURES = {
     "msn_ms_slab_phase_b_dev": (c_int, [_P, _P, c_int, c_int, c_int, ctypes.POINTER(MsParams), _P, _P]),
     "msn_ms_slab_phase_c_dev": (c_int, [_P, _P, _P, c_int, c_int, c_int, ctypes.POINTER(MsParams), _P]),
     "msn_ms_slab_exchange_bytes": (c_size_t, [c_int, c_int, c_int, ctypes.POINTER(MsParams), c_int, c_int]),
-    "msn_ms_slab_fused_dev": (c_int, [_P, _P, c_int, c_int, c_int, ctypes.POINTER(MsParams), _P, _P, _P, c_size_t, _P]),
+    "msn_ms_slab_fused_dev": (c_int, [_P, _P, c_int, c_int, c_int, ctypes.POINTER(MsParams), _P, _P, _P, _P, _P, _P,
+                                      c_size_t, _P]),
+    "msn_wta_merge_dev": (c_int, [_P, _P, _P, c_int, c_ll, _P, _P, _P, _P]),
+    "msn_ms_features_wta_dev": (c_int, [_P, _P, c_int, c_int, c_int, ctypes.POINTER(MsParams), _P, _P, _P, _P, _P,
+                                        c_size_t, _P]),
     "msn_peer_alloc": (c_int, [c_size_t, ctypes.POINTER(c_void_p)]),
     "msn_peer_free": (c_int, [_P]),
     "msn_peer_export": (c_int, [_P, _P]),

@@ -141,7 +141,18 @@ class MSFeatureExtractor(object):
     def empty_output(self):
         return self.torch.empty(self.shape, dtype=self.torch.float32, device=self.device)
 
-    def __call__(self, left, right, out=None):
+    def empty_wta(self):
+        """(argmin int32, min1 float32, min2 float32), each [N,4,h,w]: buffers for the `wta=` by-product."""
+        torch, shp = self.torch, (self.N, 4, self.shape[3], self.shape[4])
+        return (torch.empty(shp, dtype=torch.int32, device=self.device),
+                torch.empty(shp, dtype=torch.float32, device=self.device),
+                torch.empty(shp, dtype=torch.float32, device=self.device))
+
+    def __call__(self, left, right, out=None, wta=None):
+        """wta: None, or the three tensors of empty_wta(): filled with, for each of channels 0-3, the
+        winner-take-all disparity (np.argmin's rule: what main_msnet.py:443-448 computes from a host copy of
+        the volume), the smallest and the second smallest channel value -- taken inside the kernel from the
+        costs in shared memory, no pass over the volume."""
         torch = self.torch
         for t in (left, right):
             if t.dtype != torch.uint8 or tuple(t.shape) != (self.N, self.H, self.W) or not t.is_cuda \
@@ -153,9 +164,20 @@ class MSFeatureExtractor(object):
             raise ValueError("out must be a contiguous float32 tensor of shape %s" % (self.shape,))
         with torch.cuda.device(self.device):
             stream = torch.cuda.current_stream().cuda_stream
-            _lib.check(_lib.lib().msn_ms_features_dev(left.data_ptr(), right.data_ptr(), self.N, self.H, self.W,
-                                                      ctypes.byref(self.params), out.data_ptr(),
-                                                      self.workspace.data_ptr(), self.workspace.numel(), stream))
+            if wta is None:
+                _lib.check(_lib.lib().msn_ms_features_dev(left.data_ptr(), right.data_ptr(), self.N, self.H, self.W,
+                                                          ctypes.byref(self.params), out.data_ptr(),
+                                                          self.workspace.data_ptr(), self.workspace.numel(), stream))
+            else:
+                am, m1, m2 = wta
+                shp = (self.N, 4, self.shape[3], self.shape[4])
+                for t, dt in ((am, torch.int32), (m1, torch.float32), (m2, torch.float32)):
+                    if tuple(t.shape) != shp or t.dtype != dt or not t.is_contiguous() or not t.is_cuda:
+                        raise ValueError("wta: expected the three contiguous CUDA tensors of empty_wta()")
+                _lib.check(_lib.lib().msn_ms_features_wta_dev(
+                    left.data_ptr(), right.data_ptr(), self.N, self.H, self.W, ctypes.byref(self.params),
+                    out.data_ptr(), am.data_ptr(), m1.data_ptr(), m2.data_ptr(), self.workspace.data_ptr(),
+                    self.workspace.numel(), stream))
         return out
 
 

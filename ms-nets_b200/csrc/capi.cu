@@ -515,8 +515,21 @@ size_t msn_ms_features_workspace_bytes(int N, int H, int W, const msn_ms_params*
 int msn_ms_features_dev(const uint8_t* d_left, const uint8_t* d_right, int N, int H, int W,
                         const msn_ms_params* p, float* d_out, void* d_workspace, size_t workspace_bytes,
                         void* stream) {
+  return msn_ms_features_wta_dev(d_left, d_right, N, H, W, p, d_out, nullptr, nullptr, nullptr, d_workspace,
+                                 workspace_bytes, stream);
+}
+
+int msn_ms_features_wta_dev(const uint8_t* d_left, const uint8_t* d_right, int N, int H, int W,
+                            const msn_ms_params* p, float* d_out, int32_t* d_wta_idx, float* d_wta_min1,
+                            float* d_wta_min2, void* d_workspace, size_t workspace_bytes, void* stream) {
   Geometry g;
   TRY(resolve(p, N, H, W, &g, "ms_features"));
+  const bool want_wta = d_wta_idx || d_wta_min1 || d_wta_min2;
+  MSN_REQUIRE(!want_wta || (d_wta_idx && d_wta_min1 && d_wta_min2), "ms_features: pass all three WTA planes or none");
+  MSN_REQUIRE(!want_wta || (use_fused(p, g, W) && !p->lr),
+              "ms_features: the WTA by-product comes from the fused kernel (default windows, left view, D <= 448); "
+              "use msn_wta_dev on the volume otherwise");
+  const FusedWta wta{d_wta_idx, d_wta_min1, d_wta_min2};
   MSN_REQUIRE(d_left && d_right && d_out && d_workspace, "ms_features: null pointer argument");
   MSN_REQUIRE(workspace_bytes >= msn_ms_features_workspace_bytes(N, H, W, p),
               "ms_features: workspace too small (%zu < %zu)", workspace_bytes,
@@ -526,7 +539,7 @@ int msn_ms_features_dev(const uint8_t* d_left, const uint8_t* d_right, int N, in
   char* base = (char*)(((uintptr_t)d_workspace + 255) & ~(uintptr_t)255);
   const size_t n = (size_t)g.h * g.w;
   if (use_fused(p, g, W)) {
-    if (!p->lr) return launch_ms_fused(d_left, d_right, N, H, W, p, d_out, nullptr, base, s);
+    if (!p->lr) return launch_ms_fused(d_left, d_right, N, H, W, p, d_out, nullptr, base, s, 0, 0, 0, nullptr, &wta);
     const size_t stat_bytes = align256((size_t)N * 8 * n * sizeof(float));
     float* mins = reinterpret_cast<float*>(base + align256(fused_workspace_bytes(N, H, W, g.Dn, p)));
     float* den = reinterpret_cast<float*>(reinterpret_cast<char*>(mins) + stat_bytes);
@@ -666,8 +679,8 @@ size_t msn_ms_slab_exchange_bytes(int N, int H, int W, const msn_ms_params* p, i
 }
 
 int msn_ms_slab_fused_dev(const uint8_t* d_left, const uint8_t* d_right, int N, int H, int W, const msn_ms_params* p,
-                          const msn_slab_exchange* xchg, float* d_out, void* d_workspace, size_t workspace_bytes,
-                          void* stream) {
+                          const msn_slab_exchange* xchg, float* d_out, int32_t* d_wta_idx, float* d_wta_min1,
+                          float* d_wta_min2, void* d_workspace, size_t workspace_bytes, void* stream) {
   Geometry g;
   TRY(resolve(p, N, H, W, &g, "ms_slab_fused"));
   MSN_REQUIRE(d_left && d_right && d_out && d_workspace && xchg, "ms_slab_fused: null pointer argument");
@@ -677,7 +690,17 @@ int msn_ms_slab_fused_dev(const uint8_t* d_left, const uint8_t* d_right, int N, 
   const size_t need = fused_workspace_bytes(N, H, W, g.Dn, p) + 256;
   MSN_REQUIRE(workspace_bytes >= need, "ms_slab_fused: workspace too small (%zu < %zu)", workspace_bytes, need);
   char* base = (char*)(((uintptr_t)d_workspace + 255) & ~(uintptr_t)255);
-  return launch_ms_fused(d_left, d_right, N, H, W, p, d_out, nullptr, base, as_stream(stream), g.Dn, 0, 0, xchg);
+  const bool want_wta = d_wta_idx || d_wta_min1 || d_wta_min2;
+  MSN_REQUIRE(!want_wta || (d_wta_idx && d_wta_min1 && d_wta_min2), "ms_slab_fused: pass all three WTA planes or none");
+  const FusedWta wta{d_wta_idx, d_wta_min1, d_wta_min2};
+  return launch_ms_fused(d_left, d_right, N, H, W, p, d_out, nullptr, base, as_stream(stream), g.Dn, 0, 0, xchg, &wta);
+}
+
+int msn_wta_merge_dev(const int32_t* d_idx_parts, const float* d_min1_parts, const float* d_min2_parts, int parts,
+                      long long n, int32_t* d_idx, float* d_min1, float* d_min2, void* stream) {
+  MSN_REQUIRE(d_idx_parts && d_min1_parts && d_min2_parts && d_idx && d_min1 && d_min2, "wta_merge: null pointer argument");
+  MSN_REQUIRE(parts >= 1 && n >= 0, "wta_merge: bad shape");
+  return launch_wta_merge(d_idx_parts, d_min1_parts, d_min2_parts, parts, n, d_idx, d_min1, d_min2, as_stream(stream));
 }
 
 int msn_peer_alloc(size_t bytes, void** d_ptr) {

@@ -97,6 +97,8 @@ int launch_pkrn_rows(const float* cost, long long n, int D, float e, float* out,
 int launch_wta(const float* cost, long long n, int D, int layout, int d_begin, int32_t* amin, float* m1,
                float* m2, long long* keys, cudaStream_t s);
 int launch_wta_unpack(const long long* keys, long long n, int32_t* amin, float* m1, cudaStream_t s);
+int launch_wta_merge(const int32_t* idx_p, const float* m1_p, const float* m2_p, int parts, long long n, int32_t* idx,
+                     float* m1, float* m2, cudaStream_t s);
 int launch_pkrn_conf(const float* m1, const float* m2, long long n, float e, float* conf, cudaStream_t s);
 int launch_lrc(const float* c, int H, int W, int D, int thresh, int32_t* dl, int32_t* dr, uint8_t* mask,
                cudaStream_t s);

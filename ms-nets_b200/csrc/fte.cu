@@ -345,6 +345,34 @@ __global__ void wta_unpack_kernel(const long long* __restrict__ keys, long long 
   if (m1) m1[p] = key_float((uint32_t)(k >> 32));
 }
 
+// Merge of per-slab WTA triples ("all-gather per-GPU (min1, min2) pairs then local reduce"):
+// parts ordered by ascending disparity range, each [n] (argmin with absolute disparity, smallest, second
+// smallest).  Global smallest; on ties the FIRST part wins (np.argmin's lowest index); the second smallest is
+// the second entry of the sorted multiset of all parts' pairs, duplicates counted.
+__global__ void wta_merge_kernel(const int32_t* __restrict__ idx_p, const float* __restrict__ m1_p,
+                                 const float* __restrict__ m2_p, int parts, long long n, int32_t* __restrict__ idx,
+                                 float* __restrict__ m1, float* __restrict__ m2) {
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  float a = INFINITY, b = INFINITY;
+  int k = 0;
+  for (int p = 0; p < parts; ++p) {
+    const float v1 = m1_p[(size_t)p * n + i], v2 = m2_p[(size_t)p * n + i];
+    if (v1 < a) { b = a; a = v1; k = idx_p[(size_t)p * n + i]; }
+    else if (v1 < b) b = v1;
+    if (v2 < b) b = v2;      // v2 >= v1 >= a here
+  }
+  idx[i] = k; m1[i] = a; m2[i] = b;
+}
+
+int launch_wta_merge(const int32_t* idx_p, const float* m1_p, const float* m2_p, int parts, long long n, int32_t* idx,
+                     float* m1, float* m2, cudaStream_t s) {
+  if (n == 0) return 0;
+  wta_merge_kernel<<<div_up(n, 256), 256, 0, s>>>(idx_p, m1_p, m2_p, parts, n, idx, m1, m2);
+  MSN_LAUNCH_OK();
+  return 0;
+}
+
 int launch_wta_unpack(const long long* keys, long long n, int32_t* amin, float* m1, cudaStream_t s) {
   if (n == 0) return 0;
   wta_unpack_kernel<<<div_up(n, 256), 256, 0, s>>>(keys, n, amin, m1);

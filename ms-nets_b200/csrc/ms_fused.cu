@@ -244,6 +244,11 @@ struct FusedArgs {
   // peer-mapped device pointers.  See tile_back_half.
   FusedXchg xchg;
   long long n_tiles;
+  // optional by-products (nullptr: off): winner-take-all over each of channels 0-3 -- np.argmin's rule, what
+  // main_msnet.py:443-448 does on the host with the whole volume -- and the two smallest values, as planes
+  // [subs][N][4][h][w]; the disparity index is absolute (first disparity of the launch / sub-slab added)
+  int32_t* wta_idx;
+  float *wta_min1, *wta_min2;
   int subs;             // kModeXchg: sub-slabs of g.D disparities the launch's slab is cut into (virtual ranks)
 };
 
@@ -959,6 +964,43 @@ __device__ __forceinline__ void xchg_collect(const FusedArgs& a, int round, long
 }
 __device__ __forceinline__ void bar_sync_128() { asm volatile("bar.sync 1, 128;" ::: "memory"); }
 
+// Winner-take-all by-product for one (pixel, matcher): a sequential sweep over the parked costs with the values
+// channels 0-3 carry (the reference takes np.argmin of those, main_msnet.py:444-448): first minimal index wins;
+// min2 is the second smallest entry counting duplicates (oracle/ms_oracle.py wta).  m = matcher, lane = pixel.
+template <class L>
+__device__ __forceinline__ void wta_scan(const FusedArgs& a, const TileId& t, int m, int lane, const float* s_par,
+                                         const uint8_t* s_cen) {
+  constexpr int PS = L::PS;
+  const int D = a.g.D;
+  float m1 = INFINITY, m2 = INFINITY;
+  int idx = 0;
+  if (m == 0) {
+    const uint8_t* c = s_cen + lane;
+#pragma unroll 4
+    for (int d = 0; d < D; ++d) {
+      const float v = cen_ch0(c[d * kTile], nullptr);
+      if (v < m1) { m2 = m1; m1 = v; idx = d; }
+      else if (v < m2) m2 = v;
+    }
+  } else {
+    const float* e = s_par + (m - 1) * PS + lane;
+#pragma unroll 4
+    for (int d = 0; d < D; ++d) {
+      const float v = normalise_cost(e[d * kTile], m);
+      if (v < m1) { m2 = m1; m1 = v; idx = d; }
+      else if (v < m2) m2 = v;
+    }
+  }
+  const int x = t.x0 + lane;
+  if (x < a.g.w) {
+    const size_t plane = (size_t)a.g.h * a.g.w;
+    const size_t o = (((size_t)(t.sub0 / a.g.D) * a.g.N + t.n) * 4 + m) * plane + (size_t)t.y * a.g.w + x;
+    a.wta_idx[o] = t.d0 + idx;
+    a.wta_min1[o] = m1;
+    a.wta_min2[o] = m2;
+  }
+}
+
 // Phases 2 and 3 for the 256 threads of a CTA.  s_red holds the per-group minima of phase 1.
 //   phase 2 (warp-specialised; both halves only READ the parked costs, so they overlap without
 //            hazards):
@@ -1019,6 +1061,7 @@ __device__ __forceinline__ void tile_back_half(const FusedArgs& a, const TileId&
     // channels 0-3: thread = (pixel quad, d), 16 disparities per sweep of the four warps
     if (vec) store_ch03<true>(s_par, s_cen, s_lutn, PS, q4, (tid >> 3) - 16, D, orow, plane, chan, nlive);
     else store_ch03<false>(s_par, s_cen, s_lutn, PS, q4, (tid >> 3) - 16, D, orow, plane, chan, nlive);
+    if (a.wta_idx) wta_scan<L>(a, t, warp - 4, lane, s_par, s_cen);
   }
   __syncthreads();
   const int dl = tid >> 3;
@@ -1316,7 +1359,7 @@ size_t fused_workspace_bytes(int N, int H, int W, int Dn, const msn_ms_params* p
 // accumulate != 0 from the second slab on).
 int launch_ms_fused(const uint8_t* d_left, const uint8_t* d_right, int N, int H, int W, const msn_ms_params* p,
                     float* d_out, float* d_mins, char* workspace, cudaStream_t s, int out_D, int out_d0,
-                    int accumulate, const msn_slab_exchange* xchg) {
+                    int accumulate, const msn_slab_exchange* xchg, const FusedWta* wta) {
   if (N == 0) return 0;
   FusedGeom g = make_geom(N, H, W, p);
   FusedWs ws;
@@ -1367,6 +1410,12 @@ int launch_ms_fused(const uint8_t* d_left, const uint8_t* d_right, int N, int H,
   a.k_ncc = aml_scale(p->ncc_sigma);
   a.k_sad = aml_scale(p->sad_sigma);
   a.tiles_x = (g.w + kTile - 1) / kTile;
+  a.wta_idx = nullptr; a.wta_min1 = a.wta_min2 = nullptr;
+  if (wta && wta->idx) {
+    MSN_REQUIRE(!d_mins && wta->min1 && wta->min2, "ms_features: the WTA by-product needs all three planes and the one-pass path");
+    MSN_REQUIRE(!kCenLutCh0, "ms_features: WTA by-product is built for the arithmetic channel-0 form");
+    a.wta_idx = wta->idx; a.wta_min1 = wta->min1; a.wta_min2 = wta->min2;
+  }
   memset(&a.xchg, 0, sizeof(a.xchg));
   if (xchg) {
     MSN_REQUIRE(!d_mins, "ms_slab_fused: the exchange path takes no minima buffer");

@@ -4,6 +4,13 @@
 
 namespace msn {
 
+// Optional WTA by-product of launch_ms_fused: [subs][N][4][h][w] planes (argmin over each of channels 0-3 with
+// np.argmin's tie rule, smallest and second smallest value); all three or none.
+struct FusedWta {
+  int32_t* idx;
+  float *min1, *min2;
+};
+
 // true when (windows, disparity count) match what the fused kernel is specialised for.  With
 // p->lr the kernel still produces the LEFT view only, laid out for a 16-channel tensor (phase A
 // form); slab.cu's launch_slab_right_view derives channels 8-15 from the parked costs.
@@ -16,7 +23,7 @@ size_t fused_workspace_bytes(int N, int H, int W, int Dn, const msn_ms_params* p
 // out_D / out_d0 / accumulate: see ms_fused.cu (slabs of one volume processed on one GPU).
 int launch_ms_fused(const uint8_t* d_left, const uint8_t* d_right, int N, int H, int W, const msn_ms_params* p,
                     float* d_out, float* d_mins, char* workspace, cudaStream_t s, int out_D = 0, int out_d0 = 0,
-                    int accumulate = 0, const msn_slab_exchange* xchg = nullptr);
+                    int accumulate = 0, const msn_slab_exchange* xchg = nullptr, const FusedWta* wta = nullptr);
 // xchg != nullptr: this rank's disparity slab [p->d_begin, +p->d_count) with the AML minimum / denominator
 // traded with the other ranks INSIDE the kernel through their peer-mapped exchange tables (no d_mins, no
 // phases B/C).  Bytes of one rank's table:

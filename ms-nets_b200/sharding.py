@@ -276,7 +276,16 @@ class ExchangeSlabMSFeatures(object):
                 self.xchg.tables[r] = ptr.value
             dist.barrier(group=self.group)
 
-    def __call__(self, left, right, out=None):
+    def empty_wta_parts(self):
+        """Buffers for the `wta=` by-product: (argmin int32, min1, min2 float32), each [subs,N,4,h,w]."""
+        torch, shp = self.torch, (self.subs, self.N, 4, self.h, self.w)
+        return (torch.empty(shp, dtype=torch.int32, device=self.device),
+                torch.empty(shp, dtype=torch.float32, device=self.device),
+                torch.empty(shp, dtype=torch.float32, device=self.device))
+
+    def __call__(self, left, right, out=None, wta=None):
+        """wta: None or the tensors of empty_wta_parts(): this rank's WTA triples per sub-slab, to be merged
+        over the ranks with slab_wta_merge()."""
         torch, L = self.torch, _lib.lib()
         for t in (left, right):
             if t.dtype != torch.uint8 or tuple(t.shape) != (self.N, self.H, self.W) or not t.is_cuda \
@@ -284,13 +293,15 @@ class ExchangeSlabMSFeatures(object):
                 raise ValueError("expected contiguous uint8 CUDA tensors of shape %s" % ((self.N, self.H, self.W),))
         if out is None:
             out = torch.empty(self.shape, dtype=torch.float32, device=self.device)
+        wp = (None, None, None) if wta is None else tuple(t.data_ptr() for t in wta)
         self.epoch += 1
         self.xchg.epoch = self.epoch & 0xFFFFFFFF or 1
         with torch.cuda.device(self.device):
             st = torch.cuda.current_stream().cuda_stream
             _lib.check(L.msn_ms_slab_fused_dev(left.data_ptr(), right.data_ptr(), self.N, self.H, self.W,
                                                ctypes.byref(self.params), ctypes.byref(self.xchg), out.data_ptr(),
-                                               self.workspace.data_ptr(), self.workspace.numel(), st))
+                                               wp[0], wp[1], wp[2], self.workspace.data_ptr(),
+                                               self.workspace.numel(), st))
         return out
 
     def close(self):
@@ -309,6 +320,65 @@ class ExchangeSlabMSFeatures(object):
             self.close()
         except Exception:
             pass
+
+
+def wta_merge_reference(idx_parts, min1_parts, min2_parts):
+    """torch restatement of msn_wta_merge_dev for the CPU tests: parts [P,...] ordered by ascending
+    disparity range -> (argmin, min1, min2)."""
+    import torch
+    P = idx_parts.shape[0]
+    a = torch.full_like(min1_parts[0], float("inf"))
+    b = torch.full_like(a, float("inf"))
+    k = torch.zeros_like(idx_parts[0])
+    for p in range(P):
+        v1, v2 = min1_parts[p], min2_parts[p]
+        less = v1 < a
+        b = torch.where(less, a, torch.where(v1 < b, v1, b))
+        k = torch.where(less, idx_parts[p], k)
+        a = torch.where(less, v1, a)
+        b = torch.where(v2 < b, v2, b)
+    return k, a, b
+
+
+def gather_wta_parts(idx_parts, min1_parts, min2_parts, group=None):
+    """all_gather of the per-rank WTA triples [subs, ...] -> [world*subs, ...], rank-major = ascending
+    disparity ranges (the collective half of slab_wta_merge; gloo-testable)."""
+    import torch
+    dist = _dist()
+    parts = [t.contiguous() for t in (idx_parts, min1_parts, min2_parts)]
+    if dist.is_initialized() and dist.get_world_size(group) > 1:
+        world = dist.get_world_size(group)
+        gathered = []
+        for t in parts:
+            g = torch.empty((world * t.shape[0],) + tuple(t.shape[1:]), dtype=t.dtype, device=t.device)
+            dist.all_gather_into_tensor(g, t, group=group)
+            gathered.append(g)
+        parts = gathered
+    return parts
+
+
+def slab_wta_merge(idx_parts, min1_parts, min2_parts, group=None):
+    """Merge of the per-slab WTA triples (argmin with absolute disparity, smallest, second smallest) that
+    the slab kernels emit as a by-product -- SURVEY.md 8e(3): all-gather the per-GPU pairs, reduce locally
+    (msn_wta_merge_dev).  *_parts: this rank's [subs, ...] CUDA tensors; returns (argmin int32, min1, min2)
+    over ALL disparities, on every rank.  Peak ratio: confidence.pkrn_confidence(min1, min2)."""
+    import torch
+    if not idx_parts.is_cuda:
+        raise _lib.MsnetsError("slab_wta_merge: expected CUDA tensors (no CPU fallback)")
+    parts = gather_wta_parts(idx_parts, min1_parts, min2_parts, group)
+    P = parts[0].shape[0]
+    shp = tuple(parts[0].shape[1:])
+    n = 1
+    for v in shp:
+        n *= v
+    idx = torch.empty(shp, dtype=torch.int32, device=parts[0].device)
+    m1 = torch.empty(shp, dtype=torch.float32, device=parts[0].device)
+    m2 = torch.empty(shp, dtype=torch.float32, device=parts[0].device)
+    with torch.cuda.device(parts[0].device):
+        _lib.check(_lib.lib().msn_wta_merge_dev(parts[0].data_ptr(), parts[1].data_ptr(), parts[2].data_ptr(), P, n,
+                                                idx.data_ptr(), m1.data_ptr(), m2.data_ptr(),
+                                                torch.cuda.current_stream().cuda_stream))
+    return idx, m1, m2
 
 
 def slab_soft_argmin(logits_slab, d_begin, group=None):

@@ -321,3 +321,32 @@ def test_generate_test_cbmv_device_resident(ms, oracle, golden_dir, left_only):
     assert np.abs(sub - ref).max() <= AML_ATOL
     with pytest.raises(NotImplementedError):
         ms.cbmv.generate_test_cbmv(g["L"], g["R"], args_dict={"ds_scale": 2})
+
+
+@pytest.mark.parametrize("H,W,D,seed", [(40, 70, 24, 5), (37, 101, 64, 6), (48, 60, 130, 7)])
+def test_fused_wta_byproduct_matches_argmin_of_the_volume(ms, oracle, H, W, D, seed):
+    """msn_ms_features_wta_dev: argmin / min / second min of channels 0-3 straight from the fused kernel equal
+    what the reference's consumer computes from the volume (np.argmin over D, main_msnet.py:444-448) and the
+    oracle's second minimum -- on the kernel's own volume AND on the oracle's."""
+    import torch
+    L, R = bordered_pair(H, W, seed, border=10, patches=True)
+    Hb, Wb = L.shape
+    ex = ms.cbmv.MSFeatureExtractor(2, Hb, Wb, maxdisp=D, board_h=10, board_w_left=10, board_w_right=10)
+    l = torch.from_numpy(np.stack([L, R])).cuda()          # second pair: swapped images, different content
+    r = torch.from_numpy(np.stack([R, L])).cuda()
+    wta = ex.empty_wta()
+    vol = ex(l, r, wta=wta)
+    torch.cuda.synchronize()
+    vol = vol.cpu().numpy()
+    am, m1, m2 = [t.cpu().numpy() for t in wta]
+    want = oracle.ms_features(L, R, D)
+    for n in range(2):
+        for c in range(4):
+            hwd = np.ascontiguousarray(vol[n, c].transpose(1, 2, 0))
+            wi, w1, w2 = oracle.wta(hwd)
+            assert np.array_equal(am[n, c], wi) and np.array_equal(m1[n, c], w1) and np.array_equal(m2[n, c], w2)
+            assert np.array_equal(am[n, c], np.argmin(vol[n, c], axis=0))
+    for c in range(4):
+        assert np.array_equal(am[0, c], np.argmin(want[c], axis=0))
+    conf = ms.confidence.pkrn_confidence(wta[1], wta[2], 0.01).cpu().numpy()
+    assert np.array_equal(conf, oracle.pkrn_confidence(m1, m2, 0.01))

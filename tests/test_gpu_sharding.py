@@ -103,6 +103,40 @@ def test_fused_slab_exchange_virtual_ranks(oracle, world, H, W, D):
         assert np.array_equal(got, fused)
 
 
+@pytest.mark.parametrize("world,D", [(2, 64), (4, 96), (1, 384)])
+def test_fused_slab_wta_parts_merge(oracle, world, D):
+    """The slab kernels' WTA by-product per virtual rank / sub-slab, merged by msn_wta_merge_dev, equals
+    (argmin, min, second min) over ALL disparities of channels 0-3."""
+    import torch
+    from msnets_b200 import sharding
+    L, R = bordered_pair(30, 84, 21, border=10, patches=True)
+    H, W = L.shape
+    l, r = torch.from_numpy(L[None]).cuda(), torch.from_numpy(R[None]).cuda()
+    ranks = [sharding.ExchangeSlabMSFeatures(1, H, W, maxdisp=D, rank=k, world=world, connect=False, board_h=10,
+                                             board_w_left=10, board_w_right=10) for k in range(world)]
+    ptrs = [x.table_ptr for x in ranks]
+    for x in ranks:
+        x.wire(ptrs)
+    streams = [torch.cuda.Stream() for _ in ranks]
+    parts = [x.empty_wta_parts() for x in ranks]
+    torch.cuda.synchronize()
+    outs = []
+    for x, st, wp in zip(ranks, streams, parts):
+        with torch.cuda.stream(st):
+            outs.append(x(l, r, wta=wp))
+    torch.cuda.synchronize()
+    cat = [torch.cat([p[i] for p in parts], dim=0) for i in range(3)]       # what the all-gather yields
+    idx, m1, m2 = sharding.slab_wta_merge(*cat)
+    torch.cuda.synchronize()
+    want = oracle.ms_features(L, R, D)
+    for c in range(4):
+        wi, w1, w2 = oracle.wta(np.ascontiguousarray(want[c].transpose(1, 2, 0)))
+        assert np.array_equal(idx[0, c].cpu().numpy(), wi)
+        assert np.array_equal(m1[0, c].cpu().numpy(), w1) and np.array_equal(m2[0, c].cpu().numpy(), w2)
+    for x in ranks:
+        x.close()
+
+
 def test_slab_wta_and_soft_argmin_single_rank(oracle):
     import torch
     import msnets_b200 as ms

@@ -70,6 +70,16 @@ def _worker(rank, world, port, ret):
         parts = sharding.gather_parts(part)
         disp = sharding.softargmin_merge_reference(parts).numpy()
         sa_err = float(np.abs(disp - O.soft_argmin(x)).max())
+        # --- (argmin, min1, min2) triple merge: all-gather + local reduce on census channel 0,
+        #     whose integer values tie across slabs
+        ch0 = np.ascontiguousarray(full[0].transpose(1, 2, 0))                    # [h,w,D]
+        li, l1, l2 = O.wta(ch0[:, :, d0:d0 + dn])
+        gp = sharding.gather_wta_parts(torch.from_numpy(li + d0)[None], torch.from_numpy(l1)[None],
+                                       torch.from_numpy(l2)[None])
+        gi, g1, g2 = sharding.wta_merge_reference(*gp)
+        wi, w1, w2 = O.wta(ch0)
+        wta_ok = wta_ok and bool(np.array_equal(gi.numpy(), wi) and np.array_equal(g1.numpy(), w1)
+                                 and np.array_equal(g2.numpy(), w2))
         ret[rank] = (err, wta_ok, sa_err, tuple(parts.shape))
     finally:
         dist.destroy_process_group()
