@@ -190,6 +190,20 @@ MSN_API int msn_peer_export(void* d_ptr, unsigned char handle64[64]);
 MSN_API int msn_peer_open(const unsigned char handle64[64], void** d_ptr);
 MSN_API int msn_peer_close(void* d_ptr);
 
+/* Pre-matching image op on the device: down_sampling_input (cbmv_generator.py:465-482) =
+ * uint8 / 255 -> skimage.transform.rescale(anti_aliasing=True, order 1, mode='constant') -> * 255 -> uint8, i.e.
+ * (skimage >= 0.19) scipy.ndimage.gaussian_filter + scipy.ndimage.zoom(grid_mode) + range clip, replayed in
+ * scipy's arithmetic so the truncated uint8 result is identical.  N images [N][H][W] -> [N][out_h][out_w].
+ * w_rows / w_cols: HOST arrays of 2r+1 normalised Gaussian weights per axis (r < 0: no filtering along that
+ * axis), zoom_* = input extent / output extent; the Python mirror evaluates them with NumPy as scipy does. */
+MSN_API size_t msn_rescale_workspace_bytes(int N, int H, int W);
+MSN_API int msn_rescale_dev(const uint8_t* d_in, int N, int H, int W, int out_h, int out_w, const double* w_rows,
+                    int r_rows, const double* w_cols, int r_cols, double zoom_rows, double zoom_cols,
+                    uint8_t* d_out, void* d_workspace, size_t workspace_bytes, void* stream);
+MSN_API int msn_rescale_host(const uint8_t* in, int N, int H, int W, int out_h, int out_w, const double* w_rows,
+                     int r_rows, const double* w_cols, int r_cols, double zoom_rows, double zoom_cols,
+                     uint8_t* out);
+
 /* ----------------------------------------------------- device-level pieces -- */
 MSN_API int msn_census_dev(const uint8_t* d_left, const uint8_t* d_right, int H, int W, int ndisp, int wsize,
                    float* d_out_hwd, void* stream);

@@ -75,6 +75,11 @@ _SIGNATURES = {
     "msn_peer_export": (c_int, [_P, _P]),
     "msn_peer_open": (c_int, [_P, ctypes.POINTER(c_void_p)]),
     "msn_peer_close": (c_int, [_P]),
+    "msn_rescale_workspace_bytes": (c_size_t, [c_int, c_int, c_int]),
+    "msn_rescale_dev": (c_int, [_P, c_int, c_int, c_int, c_int, c_int, _P, c_int, _P, c_int, ctypes.c_double,
+                                ctypes.c_double, _P, _P, c_size_t, _P]),
+    "msn_rescale_host": (c_int, [_P, c_int, c_int, c_int, c_int, c_int, _P, c_int, _P, c_int, ctypes.c_double,
+                                 ctypes.c_double, _P]),
     "msn_census_dev": (c_int, [_P, _P, c_int, c_int, c_int, c_int, _P, _P]),
     "msn_ncc_dev": (c_int, [_P, _P, c_int, c_int, c_int, c_int, _P, _P]),
     "msn_zsad_dev": (c_int, [_P, _P, c_int, c_int, c_int, c_int, _P, _P]),

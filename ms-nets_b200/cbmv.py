@@ -6,6 +6,9 @@
     extract_features_lr    cbmv_generator.py:84-254
     get_default_args_dict  cbmv_generator.py:434-462
     generate_test_cbmv     cbmv_generator.py:727-861 (device-resident: returns a CUDA tensor)
+    generate_crop_train_cbmv  cbmv_generator.py:549-725 (device-resident features)
+    down_sampling_input    cbmv_generator.py:465-482 (anti-aliased rescale on the device)
+    get_crop_position      cbmv_generator.py:398-432
 
 plus the B200-native entry points that skip the reference's intermediate layouts:
 
@@ -184,39 +187,159 @@ class MSFeatureExtractor(object):
 _extractors = {}
 
 
+def _cached_extractor(dev, Hb, Wb, maxdisp, is_left_only, ad, board_h, board_w_left, board_w_right):
+    key = (dev.index, Hb, Wb, int(maxdisp), bool(is_left_only), ad["censw"], ad["nccw"], ad["sadw"], ad["sobelw"],
+           float(ad["cens_sigma"]), float(ad["ncc_sigma"]), float(ad["sad_sigma"]), board_h, board_w_left, board_w_right)
+    ex = _extractors.get(key)
+    if ex is None:
+        _extractors.clear()        # one cached workspace: the images of a run usually share a size
+        ex = MSFeatureExtractor(1, Hb, Wb, maxdisp=int(maxdisp), left_only=is_left_only, device=dev,
+                                censw=ad["censw"], nccw=ad["nccw"], sadw=ad["sadw"], sobelw=ad["sobelw"],
+                                board_h=board_h, board_w_left=board_w_left, board_w_right=board_w_right,
+                                cens_sigma=ad["cens_sigma"], ncc_sigma=ad["ncc_sigma"], sad_sigma=ad["sad_sigma"])
+        _extractors[key] = ex
+    return ex
+
+
+# ------------------------------------------------------- pre-matching image ops --
+def _rescale_plan(H, W, scale):
+    """What skimage.transform.rescale (>= 0.19: _warps.py rescale -> resize) derives from (shape, scale) for a
+    2-D image with anti_aliasing=True, order 1: output shape = round(scale * shape), per-axis zoom factor =
+    input / output extent, Gaussian sigma = max(0, (factor - 1) / 2), and scipy.ndimage's kernel for it
+    (_gaussian_kernel1d: radius int(4 sigma + 0.5), exp(-0.5 / sigma^2 * x^2) normalised) -- evaluated with
+    NumPy exactly as scipy evaluates it, because the device replay needs the same fp64 weights."""
+    oh, ow = (int(v) for v in np.round(np.asarray((H, W)) * scale))
+    if oh < 1 or ow < 1:
+        raise ValueError("rescale: scale %r leaves an empty image" % (scale,))
+    plan = []
+    for n_in, n_out in ((H, oh), (W, ow)):
+        factor = n_in / n_out
+        sigma = max(0.0, (factor - 1) / 2)
+        if sigma > 0:
+            r = int(4.0 * float(sigma) + 0.5)
+            x = np.arange(-r, r + 1)
+            w = np.exp(-0.5 / (sigma * sigma) * x ** 2)
+            w = np.ascontiguousarray(w / w.sum(), dtype=np.float64)
+        else:
+            r, w = -1, None
+        plan.append((r, w, float(factor)))
+    return oh, ow, plan
+
+
+def rescale_u8(img, scale):
+    """One half of down_sampling_input (cbmv_generator.py:465-482) for uint8 gray images [H,W] or [N,H,W]:
+    (img / 255 -> skimage.transform.rescale(scale, anti_aliasing=True, mode='constant') -> * 255).astype(uint8),
+    computed on the device (msn_rescale_*).  NumPy array in -> NumPy array out; CUDA tensor in -> CUDA tensor
+    out (stream ordered)."""
+    is_np = isinstance(img, np.ndarray)
+    a = np.ascontiguousarray(img) if is_np else img.contiguous()
+    if (a.dtype != np.uint8) if is_np else (str(a.dtype) != "torch.uint8"):
+        raise ValueError("rescale_u8: expected uint8 images")
+    if a.ndim not in (2, 3):
+        raise ValueError("rescale_u8: expected [H,W] or [N,H,W]")
+    single = a.ndim == 2
+    N = 1 if single else a.shape[0]
+    H, W = a.shape[-2], a.shape[-1]
+    oh, ow, ((rr, wr, zr), (rc, wc, zc)) = _rescale_plan(H, W, scale)
+    pr = wr.ctypes.data if wr is not None else None
+    pc = wc.ctypes.data if wc is not None else None
+    L = _lib.lib()
+    if is_np:
+        out = np.empty((oh, ow) if single else (N, oh, ow), np.uint8)
+        _lib.check(L.msn_rescale_host(a.ctypes.data, N, H, W, oh, ow, pr, rr, pc, rc, zr, zc, out.ctypes.data))
+        return out
+    import torch
+    if not a.is_cuda:
+        raise _lib.MsnetsError("rescale_u8: tensor must live on a CUDA device (no CPU fallback)")
+    out = torch.empty((oh, ow) if single else (N, oh, ow), dtype=torch.uint8, device=a.device)
+    with torch.cuda.device(a.device):
+        ws = torch.empty(L.msn_rescale_workspace_bytes(N, H, W), dtype=torch.uint8, device=a.device)
+        _lib.check(L.msn_rescale_dev(a.data_ptr(), N, H, W, oh, ow, pr, rr, pc, rc, zr, zc, out.data_ptr(),
+                                     ws.data_ptr(), ws.numel(), torch.cuda.current_stream().cuda_stream))
+    return out
+
+
+def down_sampling_input(ds_scale, imgl, imgr, anti_aliasing=True, multichannel=False, preserve_range=True):
+    """cbmv_generator.py:465-482, same arguments: -> (imgl, imgr) uint8, rescaled by `ds_scale` (e.g. 0.5)."""
+    if not anti_aliasing or multichannel or not preserve_range:
+        raise NotImplementedError("down_sampling_input: only the reference's own call form is provided "
+                                  "(anti_aliasing=True, multichannel=False, preserve_range=True)")
+    return rescale_u8(imgl, ds_scale), rescale_u8(imgr, ds_scale)
+
+
+def get_crop_position(w, h, crop_width=512, crop_height=256, board_w_left=256, board_w_right=0, board_h=10,
+                      is_fixed_center_around_crop=False):
+    """cbmv_generator.py:398-432: random (or centred) crop origin, the side borders halved once when the image is
+    too narrow; draws from Python's `random` exactly as the reference does (same stream for the same seed)."""
+    import random
+    tmp_diff = w - crop_width - board_w_left - board_w_right
+    if tmp_diff >= 0:
+        new_left, new_right = board_w_left, board_w_right
+    else:
+        while tmp_diff < 0:
+            new_left, new_right = board_w_left // 2, board_w_right // 2
+            tmp_diff = w - crop_width - new_left - new_right
+            if new_left == board_w_left // 2 and tmp_diff < 0:   # the reference would spin forever here
+                raise ValueError("get_crop_position: image width %d too small for a %d px crop" % (w, crop_width))
+    start_w = random.randint(0, w - crop_width - new_left - new_right)
+    start_h = random.randint(0, h - crop_height - 2 * board_h)
+    if is_fixed_center_around_crop:
+        start_w = (w - crop_width - new_left - new_right) // 2 - 1
+        start_h = (h - crop_height - 2 * board_h) // 2 - 1
+    finish_h = start_h + (crop_height + 2 * board_h)
+    finish_w = start_w + (crop_width + new_left + new_right)
+    return start_w, start_h, finish_w, finish_h, new_left, new_right
+
+
+def read_pfm(name):
+    """PFM reader (the reference's src/pfmutil.py readPFM): float32 [H,W], rows flipped to top-down."""
+    import re
+    with open(name, "rb") as f:
+        kind = f.readline().decode("latin-1")
+        if "PF" in kind:
+            channels = 3
+        elif "Pf" in kind:
+            channels = 1
+        else:
+            raise ValueError("%s: not a PFM file" % name)
+        width, height = (int(v) for v in re.findall(r"\d+", f.readline().decode("latin-1"))[:2])
+        big = "-" not in f.readline().decode("latin-1")
+        data = np.frombuffer(f.read(width * height * channels * 4), dtype=(">f4" if big else "<f4"))
+    return np.flipud(data.reshape(height, width)).astype(np.float32)
+
+
+def _read_gray(src, who):
+    if isinstance(src, str):
+        import cv2
+        im = cv2.imread(src, 0)
+        if im is None:
+            raise ValueError("%s: cannot read %r" % (who, src))
+        src = im
+    a = np.ascontiguousarray(src)
+    if a.dtype != np.uint8 or a.ndim != 2:
+        raise ValueError("%s: expected uint8 gray images [H,W]" % who)
+    return a
+
+
 def generate_test_cbmv(limg_name, rimg_name, crop_height=384, crop_width=1248, encoder_ds=64, maxdisp=192,
                        args_dict=None, is_left_only=True, device=None):
-    """cbmv_generator.py:727-861, device-resident: same arguments and return
-    tuple `(features, h, w, crop_height, crop_width)`, but `features` is a float32 CUDA tensor
-    [C, D, crop_height, crop_width] produced where the 3D CNN consumes it -- the caller's
+    """cbmv_generator.py:727-861, device-resident: same arguments, same defaults
+    (args_dict=None means get_default_args_dict(), ds_scale = 2) and the same return tuple
+    `(features, h, w, crop_height, crop_width)`, but `features` is a float32 CUDA tensor
+    [C, maxdisp/ds, crop_height/ds, crop_width/ds] produced where the 3D CNN consumes it -- the caller's
     `features.cuda()` (main_msnet.py:571-572) becomes a no-op.
 
     limg_name / rimg_name: file names (read with cv2.imread(name, 0) as the reference does) or
     uint8 gray images.  As in the reference, crop_height / crop_width are recomputed from the
     image size: zero padding on top and on the right up to a multiple of encoder_ds (:780-788),
-    then a 10-pixel zero border on all sides so the matchers' border fill lands outside the crop
-    (:819-834).  ds_scale (args_dict) must be 1: the reference's default 2 goes through
-    skimage.transform.rescale, which is not ported yet."""
+    the anti-aliased down-sampling by ds_scale (:802-803, rescale_u8 on the device), then a 10-pixel
+    zero border on all sides so the matchers' border fill lands outside the crop (:819-834)."""
     import torch
-    ad = get_default_args_dict()
-    ad["ds_scale"] = 1
-    if args_dict is not None:
-        ad.update(args_dict)
-    if int(ad["ds_scale"]) != 1:
-        raise NotImplementedError("generate_test_cbmv: ds_scale=%r needs the anti-aliased rescale "
-                                  "(skimage.transform.rescale), not ported yet" % (ad["ds_scale"],))
-    imgs = []
-    for src in (limg_name, rimg_name):
-        if isinstance(src, str):
-            import cv2
-            im = cv2.imread(src, 0)
-            if im is None:
-                raise ValueError("generate_test_cbmv: cannot read %r" % (src,))
-            src = im
-        a = np.ascontiguousarray(src)
-        if a.dtype != np.uint8 or a.ndim != 2:
-            raise ValueError("generate_test_cbmv: expected uint8 gray images [H,W]")
-        imgs.append(a)
+    ad = get_default_args_dict() if args_dict is None else dict(get_default_args_dict(), **args_dict)
+    ds = int(ad["ds_scale"])
+    if ds < 1:
+        raise ValueError("generate_test_cbmv: ds_scale must be >= 1")
+    imgs = [_read_gray(src, "generate_test_cbmv") for src in (limg_name, rimg_name)]
     if imgs[0].shape != imgs[1].shape:
         raise ValueError("generate_test_cbmv: left and right image sizes differ")
     h, w = imgs[0].shape
@@ -226,20 +349,81 @@ def generate_test_cbmv(limg_name, rimg_name, crop_height=384, crop_width=1248, e
         raise _lib.MsnetsError("generate_test_cbmv needs a CUDA device (no CPU fallback)")
     dev = torch.device("cuda", torch.cuda.current_device()) if device is None else torch.device(device)
     board = 10
-    Hb, Wb = crop_height + 2 * board, crop_width + 2 * board
-    pair = torch.zeros((2, 1, Hb, Wb), dtype=torch.uint8, device=dev)
-    for i, a in enumerate(imgs):   # top/right padding and the border are the zeros already there
-        pair[i, 0, board + crop_height - h:board + crop_height, board:board + w] = torch.from_numpy(a).to(dev)
-    key = (dev.index, Hb, Wb, int(maxdisp), bool(is_left_only), ad["censw"], ad["nccw"], ad["sadw"], ad["sobelw"],
-           float(ad["cens_sigma"]), float(ad["ncc_sigma"]), float(ad["sad_sigma"]))
-    ex = _extractors.get(key)
-    if ex is None:
-        _extractors.clear()        # one cached workspace: test images usually share a size
-        ex = MSFeatureExtractor(1, Hb, Wb, maxdisp=int(maxdisp) // int(ad["ds_scale"]), left_only=is_left_only,
-                                device=dev, censw=ad["censw"], nccw=ad["nccw"], sadw=ad["sadw"],
-                                sobelw=ad["sobelw"], board_h=board, board_w_left=board, board_w_right=board,
-                                cens_sigma=ad["cens_sigma"], ncc_sigma=ad["ncc_sigma"], sad_sigma=ad["sad_sigma"])
-        _extractors[key] = ex
     with torch.cuda.device(dev):
+        padded = torch.zeros((2, crop_height, crop_width), dtype=torch.uint8, device=dev)
+        for i, a in enumerate(imgs):   # top/right padding = the zeros already there
+            padded[i, crop_height - h:, :w] = torch.from_numpy(a).to(dev)
+        if ds > 1:
+            padded = rescale_u8(padded, 1.0 / float(ds))
+        ph, pw = padded.shape[1], padded.shape[2]
+        Hb, Wb = ph + 2 * board, pw + 2 * board
+        pair = torch.zeros((2, 1, Hb, Wb), dtype=torch.uint8, device=dev)
+        pair[:, 0, board:board + ph, board:board + pw] = padded
+        ex = _cached_extractor(dev, Hb, Wb, int(maxdisp) // ds, is_left_only, ad, board, board, board)
         features = ex(pair[0], pair[1])[0]
     return features, h, w, crop_height, crop_width
+
+
+def generate_crop_train_cbmv(limg_name, rimg_name, disp_name, lseg_name, crop_height=256, crop_width=512,
+                             maxdisp=192, is_fixed_center_around_crop=False, args_dict=None, is_left_only=True,
+                             device=None):
+    """cbmv_generator.py:549-725, device-resident: same arguments and return tuple
+    `(features, disp_image, imgl_rgb, imgr_rgb, semantic_label)`; `features` is a float32 CUDA tensor
+    [C, maxdisp/ds, crop_height/ds, crop_width/ds], the other four are the reference's CPU float tensors.
+
+    The random crop (get_crop_position, `random` module), the border policy (board_h rows above and below,
+    maxdisp columns on the left -- and on the right for the two-view volume -- halved when the image is too
+    narrow), the anti-aliased down-sampling of the cropped pair and the integer division of maxdisp and of the
+    borders by ds_scale follow the reference line by line; the pair is cropped on the host (two small uint8
+    arrays) and everything after it runs on the device.  This is the path that starves the reference's trainer
+    (do_main_msnet.sh:138-192): here a 256x512 crop costs a fraction of a millisecond."""
+    import cv2
+    import torch
+    ad = get_default_args_dict() if args_dict is None else dict(get_default_args_dict(), **args_dict)
+    ds = int(ad["ds_scale"])
+    board_h = int(ad["board_h"])
+    board_w_left = int(maxdisp)
+    board_w_right = 0 if is_left_only else int(maxdisp)
+    imgl = _read_gray(limg_name, "generate_crop_train_cbmv")
+    imgr = _read_gray(rimg_name, "generate_crop_train_cbmv")
+    imgl_rgb = cv2.imread(limg_name, 1).astype(np.uint8)[:, :, ::-1]
+    imgr_rgb = cv2.imread(rimg_name, 1).astype(np.uint8)[:, :, ::-1]
+    h, w = imgl.shape[:2]
+    start_w, start_h, finish_w, finish_h, board_w_left, board_w_right = get_crop_position(
+        w, h, crop_width, crop_height, board_w_left, board_w_right, board_h, is_fixed_center_around_crop)
+    vld_w_end = -board_w_right if board_w_right > 0 else None
+    vld_h_end = -board_h if board_h > 0 else None
+
+    def inner(a):                                                       # remove_border, :484-503
+        a = a[start_h:finish_h, start_w:finish_w]
+        return np.ascontiguousarray(a[board_h:vld_h_end][:, board_w_left:vld_w_end])
+    disp_image = read_pfm(disp_name)[start_h:finish_h, start_w:finish_w].copy()
+    disp_image[disp_image == np.inf] = .0
+    disp_image = np.ascontiguousarray(disp_image[board_h:vld_h_end][:, board_w_left:vld_w_end])
+    imgl_rgb, imgr_rgb = inner(imgl_rgb), inner(imgr_rgb)
+    if lseg_name is not None:
+        from PIL import Image
+        semantic_label = inner(np.asarray(Image.open(lseg_name), dtype=np.float32, order="C"))
+    else:
+        semantic_label = None
+    cl = np.ascontiguousarray(imgl[start_h:finish_h, start_w:finish_w])
+    cr = np.ascontiguousarray(imgr[start_h:finish_h, start_w:finish_w])
+    if not torch.cuda.is_available():
+        raise _lib.MsnetsError("generate_crop_train_cbmv needs a CUDA device (no CPU fallback)")
+    dev = torch.device("cuda", torch.cuda.current_device()) if device is None else torch.device(device)
+    with torch.cuda.device(dev):
+        pair = torch.from_numpy(np.stack([cl, cr])).to(dev)
+        if ds > 1:
+            pair = rescale_u8(pair, 1.0 / float(ds))
+        Hb, Wb = pair.shape[1], pair.shape[2]
+        ex = _cached_extractor(dev, Hb, Wb, int(maxdisp) // ds, is_left_only, ad, board_h // ds, board_w_left // ds,
+                               board_w_right // ds)
+        features = ex(pair[0:1].contiguous(), pair[1:2].contiguous())[0]
+    imgl_rgb = torch.from_numpy(imgl_rgb.transpose((2, 0, 1)).astype(np.float32) / 255.0).float()
+    imgr_rgb = torch.from_numpy(imgr_rgb.transpose((2, 0, 1)).astype(np.float32) / 255.0).float()
+    disp_image = torch.from_numpy(disp_image).float()
+    if semantic_label is not None:
+        semantic_label = torch.from_numpy(semantic_label[None, ...]).float()
+    else:
+        semantic_label = torch.zeros([1, disp_image.size()[0], disp_image.size(1)], dtype=torch.float32)
+    return features, disp_image, imgl_rgb, imgr_rgb, semantic_label

@@ -67,6 +67,9 @@ int launch_ncc_stats(const uint8_t* img, int H, int W, int wsize, unsigned long 
                      cudaStream_t s);
 int launch_sobel(const uint8_t* img, int H, int W, float* out, cudaStream_t s);
 int launch_fill(float* p, size_t n, float v, cudaStream_t s);
+int launch_rescale(const uint8_t* in, int N, int H, int W, int oh, int ow, const double* w_rows, int r_rows,
+                   const double* w_cols, int r_cols, double zoom_rows, double zoom_cols, uint8_t* out, float* tmp,
+                   int* minmax, cudaStream_t s);
 // matchers.cu
 int launch_census_cost_hwd(const uint32_t* dl, const uint32_t* dr, int H, int W, int D, int wsize,
                            float* out, cudaStream_t s);

@@ -16,11 +16,13 @@
 namespace msn {
 
 // ---------------------------------------------------------------- transposes --
-// in[A][B] -> out[B][A] through a 32x33 shared tile; both sides coalesced.
-__global__ void transpose2d_kernel(const float* __restrict__ in, long long A, long long B,
+// in[A][B] -> out[B][A] through a 32x33 shared tile; both sides coalesced.  Tiles are numbered along
+// grid.x only (a-tile slowest), so neither extent is bound by the 65535 limit of grid.y / grid.z.
+__global__ void transpose2d_kernel(const float* __restrict__ in, long long A, long long B, long long tiles_b,
                                    float* __restrict__ out) {
   __shared__ float tile[32][33];
-  const long long b0 = (long long)blockIdx.x * 32, a0 = (long long)blockIdx.y * 32;
+  const long long tb = (long long)blockIdx.x % tiles_b, ta = (long long)blockIdx.x / tiles_b;
+  const long long b0 = tb * 32, a0 = ta * 32;
   for (int r = threadIdx.y; r < 32; r += blockDim.y) {
     const long long a = a0 + r, b = b0 + threadIdx.x;
     if (a < A && b < B) tile[r][threadIdx.x] = in[a * B + b];
@@ -36,9 +38,8 @@ int launch_transpose2d(const float* in, long long A, long long B, float* out, cu
   if (A == 0 || B == 0) return 0;
   dim3 block(32, 8);
   const long long gx = (B + 31) / 32, gy = (A + 31) / 32;
-  MSN_REQUIRE(gy <= 65535, "transpose: leading extent %lld too large", A);
-  dim3 grid((unsigned)gx, (unsigned)gy);
-  transpose2d_kernel<<<grid, block, 0, s>>>(in, A, B, out);
+  MSN_REQUIRE(gx * gy <= 2147483647LL, "transpose: %lld x %lld is too large for one launch", A, B);
+  transpose2d_kernel<<<(unsigned)(gx * gy), block, 0, s>>>(in, A, B, gx, out);
   MSN_LAUNCH_OK();
   return 0;
 }

@@ -59,7 +59,7 @@ int launch_census_cost_hwd(const uint32_t* dl, const uint32_t* dr, int H, int W,
   const int nw = (wsize * wsize + 31) / 32;
   const int dq = (D + 3) / 4;
   dim3 block(256), grid(div_up((long long)W * dq, 256), H);
-  if (D % 4 == 0)
+  if (D % 4 == 0 && (reinterpret_cast<uintptr_t>(out) & 15) == 0)   // 128-bit stores need a 16-byte aligned volume
     census_cost_hwd_kernel<true><<<grid, block, 0, s>>>(dl, dr, H, W, D, wsize, nw, out);
   else
     census_cost_hwd_kernel<false><<<grid, block, 0, s>>>(dl, dr, H, W, D, wsize, nw, out);

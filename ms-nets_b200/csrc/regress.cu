@@ -213,7 +213,7 @@ shift_volume_kernel(const float* __restrict__ fl, const float* __restrict__ fr, 
     const int xr = x - d_lo;
     r[i] = (x < W && xr >= 0) ? rrow[xr] : 0.f;
   }
-  const bool vec = (W & 3) == 0;
+  const bool vec = (W & 3) == 0 && (reinterpret_cast<uintptr_t>(vol) & 15) == 0;   // 128-bit stores: aligned rows
   for (int d = d_lo; d < d_hi; ++d) {
     float a[4], b[4];
 #pragma unroll

@@ -281,18 +281,114 @@ def pad_test_pair(imgl, imgr, encoder_ds):
     return out[0], out[1], h, w, crop_h, crop_w
 
 
+def rescale_antialiased(img_f32, scale):
+    """skimage.transform.rescale(image, scale, anti_aliasing=True, preserve_range=True, mode='constant')
+    for a 2-D float32 image, order 1 -- the call down_sampling_input makes (cbmv_generator.py:465-482).
+    skimage is NOT installed in this image (PARITY UNPINNED against skimage itself); this restates what
+    skimage >= 0.19 does (transform/_warps.py: rescale -> resize) on top of scipy.ndimage, which IS
+    installed and is the engine skimage delegates to:
+        output_shape = round(scale * shape); factors = shape / output_shape
+        filtered = ndi.gaussian_filter(image, sigma=max(0,(factors-1)/2), mode='constant', cval=0)
+        out = ndi.zoom(filtered, 1/factors, order=1, mode='grid-constant', cval=0, grid_mode=True)
+        clip to [image.min(), image.max()]  (output pixels equal to cval stay cval)
+    float32 in, float32 out (skimage >= 0.19 keeps float32)."""
+    import scipy.ndimage as ndi
+    image = np.ascontiguousarray(img_f32, np.float32)
+    out_shape = tuple(int(v) for v in np.round(np.asarray(image.shape) * scale))
+    factors = np.asarray(image.shape, np.float64) / np.asarray(out_shape, np.float64)
+    sigma = np.maximum(0, (factors - 1) / 2)
+    filtered = ndi.gaussian_filter(image, sigma, cval=0, mode="constant")
+    zoom = [1 / f for f in factors]
+    out = ndi.zoom(filtered, zoom, order=1, mode="grid-constant", cval=0, grid_mode=True)
+    assert out.shape == out_shape and out.dtype == np.float32
+    lo, hi = image.min(), image.max()
+    preserve_cval = not (lo <= 0 <= hi)          # skimage _clip_warp_output, mode='constant', cval=0
+    if preserve_cval:
+        mask = out == 0
+    np.clip(out, lo, hi, out=out)
+    if preserve_cval:
+        out[mask] = 0
+    return out
+
+
+def rescale_antialiased_replay(img_f32, scale):
+    """The same, with scipy's arithmetic written out (ni_filters.c NI_Correlate1D symmetric branch,
+    ni_interpolation.c NI_ZoomShift order 1): the form the CUDA kernel follows.  Checked against
+    rescale_antialiased bit for bit in tests/test_oracle_golden.py."""
+    image = np.ascontiguousarray(img_f32, np.float32)
+    H, W = image.shape
+    oh, ow = (int(v) for v in np.round(np.asarray(image.shape) * scale))
+    cur = image
+    for axis, (n_in, n_out) in enumerate(((H, oh), (W, ow))):
+        sigma = max(0.0, (n_in / n_out - 1) / 2)
+        if sigma <= 0:
+            continue
+        r = int(4.0 * sigma + 0.5)
+        x = np.arange(-r, r + 1)
+        w = np.exp(-0.5 / (sigma * sigma) * x ** 2)
+        w = w / w.sum()
+        a = np.moveaxis(cur, axis, 0).astype(np.float64)
+        pad = np.zeros((r,) + a.shape[1:])
+        e = np.concatenate([pad, a, pad], 0)
+        n = a.shape[0]
+        t = e[r:r + n] * w[r]
+        for j in range(-r, 0):                          # farthest taps first, pairs added before the multiply
+            t = t + (e[r + j:r + j + n] + e[r - j:r - j + n]) * w[r + j]
+        cur = np.ascontiguousarray(np.moveaxis(t.astype(np.float32), 0, axis))
+    zr, zc = H / oh, W / ow
+
+    def taps(n_out, n_in, z):
+        c = (np.arange(n_out, dtype=np.float64) + 0.5) * z - 0.5
+        f = np.floor(c)
+        return f.astype(np.int64), c - f
+    fr, wr = taps(oh, H, zr)
+    fc, wc = taps(ow, W, zc)
+    g = np.pad(cur.astype(np.float64), 1)               # grid-constant: zeros outside
+    out = np.zeros((oh, ow), np.float64)
+    for i, wi in ((0, 1 - wr), (1, wr)):
+        for j, wj in ((0, 1 - wc), (1, wc)):
+            out += (g[np.ix_(fr + i + 1, fc + j + 1)] * wi[:, None]) * wj[None, :]
+    out = out.astype(np.float32)
+    lo, hi = image.min(), image.max()
+    preserve_cval = not (lo <= 0 <= hi)
+    if preserve_cval:
+        mask = out == 0
+    np.clip(out, lo, hi, out=out)
+    if preserve_cval:
+        out[mask] = 0
+    return out
+
+
+def down_sampling_input(ds_scale, imgl, imgr):
+    """cbmv_generator.py:465-482: uint8 -> float32/255 -> rescale -> *255 -> uint8 (truncation)."""
+    out = []
+    for im in (imgl, imgr):
+        f = im.astype(np.float32) / 255.0
+        z = rescale_antialiased(f, ds_scale)
+        out.append(np.ascontiguousarray((z * 255.0).astype(np.uint8)))
+    return out[0], out[1]
+
+
 def generate_test_cbmv(imgl, imgr, encoder_ds=64, maxdisp=192, args_dict=None, is_left_only=True):
     """cbmv_generator.py:727-861 on two uint8 gray images (the reference reads them with
-    cv2.imread(name, 0)); only the ds_scale == 1 branch (skimage's rescale is not restated).
+    cv2.imread(name, 0)).  ds_scale > 1 goes through down_sampling_input (rescale_antialiased: pinned to
+    scipy.ndimage, not to skimage itself -- see there).
     Returns (features float32 [C, D, crop_h, crop_w], h, w, crop_h, crop_w)."""
     ad = dict(censw=11, nccw=3, sadw=5, sobelw=5, cens_sigma=128.0, ncc_sigma=0.02, sad_sigma=20000.0,
               sobel_sigma=20000.0, ds_scale=1)
     if args_dict:
         ad.update(args_dict)
-    if int(ad["ds_scale"]) != 1:
-        raise NotImplementedError("oracle: ds_scale != 1 needs skimage.transform.rescale")
-    L, R, h, w, crop_h, crop_w = pad_test_pair(imgl, imgr, encoder_ds)
-    costs = get_costs(L, R, maxdisp // int(ad["ds_scale"]), ad["censw"], ad["nccw"], ad["sadw"], ad["sobelw"],
+    ds = int(ad["ds_scale"])
+    h, w = imgl.shape[:2]
+    crop_w = w + (encoder_ds - w % encoder_ds) % encoder_ds
+    crop_h = h + (encoder_ds - h % encoder_ds) % encoder_ds
+    pl = np.pad(imgl, ((crop_h - h, 0), (0, crop_w - w)), "constant").astype(np.uint8)
+    pr = np.pad(imgr, ((crop_h - h, 0), (0, crop_w - w)), "constant").astype(np.uint8)
+    if ds > 1:
+        pl, pr = down_sampling_input(1.0 / ds, pl, pr)                                  # :802-803
+    L = np.ascontiguousarray(np.pad(pl, ((10, 10), (10, 10)), "constant").astype(np.uint8))
+    R = np.ascontiguousarray(np.pad(pr, ((10, 10), (10, 10)), "constant").astype(np.uint8))
+    costs = get_costs(L, R, maxdisp // ds, ad["censw"], ad["nccw"], ad["sadw"], ad["sobelw"],
                       10, 10, 10)
     fn = extract_features_left if is_left_only else extract_features_lr
     f = fn(*costs, cens_sigma=ad["cens_sigma"], ncc_sigma=ad["ncc_sigma"], sad_sigma=ad["sad_sigma"])

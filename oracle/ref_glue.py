@@ -46,10 +46,27 @@ class _Stub(types.ModuleType):
         return lambda *a, **k: None
 
 
-def load_generator(mtc, fte):
+def _load_sibling(name, filename, gen_path):
+    """The reference's own src/<filename> (pfmutil.py: the PFM reader generate_crop_train_cbmv needs), executed
+    under the stubbed matplotlib; None when the file did not travel."""
+    path = os.path.join(os.path.dirname(os.path.dirname(gen_path)), filename)
+    if not os.path.isfile(path):
+        return None
+    spec = importlib.util.spec_from_file_location(name, path)
+    mod = importlib.util.module_from_spec(spec)
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore")
+        spec.loader.exec_module(mod)
+    return mod
+
+
+def load_generator(mtc, fte, rescale=None):
     """Executes the unmodified cbmv_generator.py in a private package namespace whose
     `src.cpp.lib.libmatchers` / `libfeatextract` are `mtc` / `fte`.  sys.modules is restored
     afterwards, so several bindings (reference C++, CUDA mirrors) can coexist in one process.
+    `rescale`: a stand-in for skimage.transform.rescale (absent from this image), called with the
+    reference's own keyword arguments -- oracle.ms_oracle.rescale_antialiased restates it over
+    scipy.ndimage -- so that the ds_scale = 2 default of generate_test_cbmv / generate_crop_train_cbmv runs.
     Returns the module, or None when the file is not available."""
     path = generator_path()
     if path is None:
@@ -72,13 +89,20 @@ def load_generator(mtc, fte):
         lib.libmatchers, lib.libfeatextract = mtc, fte
         sys.modules["src.cpp.lib.libmatchers"] = mtc
         sys.modules["src.cpp.lib.libfeatextract"] = fte
-        for name in ("src.pfmutil", "src.funcs_utili"):
-            sys.modules[name] = _Stub(name)
-        src.pfmutil, src.funcs_utili = sys.modules["src.pfmutil"], sys.modules["src.funcs_utili"]
         for name in ("skimage", "skimage.transform", "matplotlib", "matplotlib.pyplot", "matplotlib.image"):
             if name not in sys.modules:
                 sys.modules[name] = _Stub(name)
         sys.modules["skimage"].transform = sys.modules["skimage.transform"]
+        sys.modules["matplotlib"].pyplot = sys.modules["matplotlib.pyplot"]
+        sys.modules["matplotlib"].image = sys.modules["matplotlib.image"]
+        if rescale is not None:
+            def _rescale(image, scale, anti_aliasing=True, preserve_range=True, multichannel=False, mode="constant"):
+                assert anti_aliasing and preserve_range and not multichannel and mode == "constant"
+                return rescale(image, scale)
+            sys.modules["skimage.transform"].rescale = _rescale
+        sys.modules["src.funcs_utili"] = _Stub("src.funcs_utili")
+        sys.modules["src.pfmutil"] = _load_sibling("src.pfmutil", "pfmutil.py", path) or _Stub("src.pfmutil")
+        src.pfmutil, src.funcs_utili = sys.modules["src.pfmutil"], sys.modules["src.funcs_utili"]
         name = "src.dataloader.cbmv_generator"
         spec = importlib.util.spec_from_file_location(name, path)
         mod = importlib.util.module_from_spec(spec)

@@ -100,3 +100,37 @@ def test_oracle_generate_test_cbmv_matches_reference(oracle, golden_dir, tag, le
     assert [h, w, ch, cw] + list(f.shape) == g["meta_" + tag].tolist()
     assert digest(f) == str(g["sha_" + tag])
     assert np.array_equal(f.reshape(-1)[::5], g["sub_" + tag])
+
+
+@pytest.mark.parametrize("shape,scale", [((64, 96), 0.5), ((37, 53), 0.5), ((40, 60), 0.25), ((30, 30), 0.5)])
+def test_rescale_replay_equals_scipy_composition(oracle, shape, scale):
+    """rescale_antialiased = scipy.ndimage.gaussian_filter + zoom + clip as skimage >= 0.19 composes them;
+    rescale_antialiased_replay = the same arithmetic written out (the form the CUDA kernel follows)."""
+    rng = np.random.default_rng(7)
+    im = rng.integers(0, 256, shape, dtype=np.uint8)
+    if shape == (30, 30):
+        im = np.maximum(im, 17).astype(np.uint8)      # range clip with a positive minimum
+    f = im.astype(np.float32) / 255.0
+    a, b = oracle.rescale_antialiased(f, scale), oracle.rescale_antialiased_replay(f, scale)
+    assert a.dtype == b.dtype == np.float32 and np.array_equal(a, b)
+
+
+def test_oracle_generate_test_cbmv_ds2_equals_reference_function(oracle):
+    """The oracle's generate_test_cbmv at the reference's default ds_scale = 2 against the unmodified
+    reference function (its skimage.transform.rescale call served by the oracle's restatement)."""
+    import tempfile
+    import cv2
+    from oracle import ref_glue
+    oracle.lib()
+    gen = ref_glue.load_generator(oracle.MTC, oracle.FTE, rescale=oracle.rescale_antialiased)
+    if gen is None:
+        pytest.skip("cbmv_generator.py not available")
+    L, R = synth_pair(70, 150, 5, 6)
+    with tempfile.TemporaryDirectory() as td:
+        fl, fr = os.path.join(td, "l.png"), os.path.join(td, "r.png")
+        cv2.imwrite(fl, L)
+        cv2.imwrite(fr, R)
+        want, h, w, ch, cw = gen.generate_test_cbmv(fl, fr, encoder_ds=16, maxdisp=32)
+    got = oracle.generate_test_cbmv(L, R, encoder_ds=16, maxdisp=32, args_dict={"ds_scale": 2})
+    assert (h, w, ch, cw) == got[1:]
+    assert np.array_equal(want.numpy(), got[0])
