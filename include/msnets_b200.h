@@ -172,6 +172,7 @@ typedef struct msn_slab_exchange {
                * disparities a tile can park, on any number of GPUs including one.  Same value on every rank. */
 } msn_slab_exchange;
 MSN_API size_t msn_ms_slab_exchange_bytes(int N, int H, int W, const msn_ms_params* p, int world, int subs);
+MSN_API size_t msn_ms_slab_fused_workspace_bytes(int N, int H, int W, const msn_ms_params* p);
 MSN_API int msn_ms_slab_fused_dev(const uint8_t* d_left, const uint8_t* d_right, int N, int H, int W,
                           const msn_ms_params* p, const msn_slab_exchange* xchg, float* d_out_ncdhw,
                           int32_t* d_wta_idx, float* d_wta_min1, float* d_wta_min2, void* d_workspace,

@@ -65,6 +65,7 @@ _SIGNATURES = {
     "msn_ms_slab_phase_b_dev": (c_int, [_P, _P, c_int, c_int, c_int, ctypes.POINTER(MsParams), _P, _P]),
     "msn_ms_slab_phase_c_dev": (c_int, [_P, _P, _P, c_int, c_int, c_int, ctypes.POINTER(MsParams), _P]),
     "msn_ms_slab_exchange_bytes": (c_size_t, [c_int, c_int, c_int, ctypes.POINTER(MsParams), c_int, c_int]),
+    "msn_ms_slab_fused_workspace_bytes": (c_size_t, [c_int, c_int, c_int, ctypes.POINTER(MsParams)]),
     "msn_ms_slab_fused_dev": (c_int, [_P, _P, c_int, c_int, c_int, ctypes.POINTER(MsParams), _P, _P, _P, _P, _P, _P,
                                       c_size_t, _P]),
     "msn_wta_merge_dev": (c_int, [_P, _P, _P, c_int, c_ll, _P, _P, _P, _P]),

@@ -564,6 +564,20 @@ static bool use_fused_slabs(const msn_ms_params* p, const Geometry& g, int W) {
   return !p->lr && g.Dn == g.D && !fused_supported(p, g.Dn) && fused_supported(p, kFusedSlabD) &&
          sadsob_fast_pitch(W + 35) > 0 && !force_generic();
 }
+// ... and when those slabs can be EQUAL (D divisible by their number), they run as sub-slabs of ONE launch of
+// the fused kernel's exchange form instead (one rank, `subs` virtual ranks): the tiles of a pixel trade their
+// minima / denominators through a table in the workspace and the volume is written once -- no parked costs,
+// no phases B/C (2.5x less DRAM traffic).
+// Opt-in (MSNETS_ONE_GPU_EXCHANGE=1): measured on config M (1984x2880, D = 640, one B200) the two routes are
+// within 4 % of each other (78.8 vs 81.6 ms) -- with four sub-slabs in flight the 117 GB of scattered output
+// rows, not the parked-cost traffic, sets the pace -- and the exchange route needs the SAD-of-Sobel scratch of
+// all 640 disparities at once (21 GB instead of 6 GB).
+static int exchange_subs(const msn_ms_params* p, const Geometry& g, int W) {
+  const char* e = getenv("MSNETS_ONE_GPU_EXCHANGE");
+  if (!(e && e[0] == '1') || !use_fused_slabs(p, g, W)) return 0;
+  const int subs = (g.D + kFusedSlabD - 1) / kFusedSlabD;
+  return (g.D % subs == 0) ? subs : 0;
+}
 static msn_ms_params slab_params(const msn_ms_params* p, int d0, int dn) {
   msn_ms_params q = *p;
   q.d_begin = d0;
@@ -580,6 +594,8 @@ size_t msn_ms_features_workspace_bytes(int N, int H, int W, const msn_ms_params*
     if (p->lr) need += 2 * align256((size_t)N * 8 * g.h * g.w * sizeof(float));
     return need + 256;
   }
+  if (const int subs = exchange_subs(p, g, W))
+    return align256(fused_workspace_bytes(N, H, W, g.D, p)) + align256(fused_exchange_bytes(N, H, W, p, subs)) + 256;
   if (use_fused_slabs(p, g, W)) {
     // sized for the slab with the largest disparity offset (widest left padding) and a full count
     const msn_ms_params q = slab_params(p, g.D - kFusedSlabD, kFusedSlabD);
@@ -632,6 +648,15 @@ int msn_ms_features_wta_dev(const uint8_t* d_left, const uint8_t* d_right, int N
                               p->cens_sigma, p->ncc_sigma, p->sad_sigma, s));
     }
     return 0;
+  }
+  if (const int subs = exchange_subs(p, g, W)) {
+    char* table = base + align256(fused_workspace_bytes(N, H, W, g.D, p));
+    const size_t tb = fused_exchange_bytes(N, H, W, p, subs);
+    msn_slab_exchange x;
+    memset(&x, 0, sizeof(x));
+    x.tables[0] = table; x.world = 1; x.rank = 0; x.epoch = 1; x.subs = subs;
+    MSN_CUDA_OK(cudaMemsetAsync(table + tb / 2, 0, tb / 2, s));   // epoch 1 lives in the table's second half
+    return launch_ms_fused(d_left, d_right, N, H, W, p, d_out, nullptr, base, s, g.D, 0, 0, &x);
   }
   if (use_fused_slabs(p, g, W)) {
     const msn_ms_params q0 = slab_params(p, g.D - kFusedSlabD, kFusedSlabD);
@@ -755,6 +780,12 @@ size_t msn_ms_slab_exchange_bytes(int N, int H, int W, const msn_ms_params* p, i
     return 0;
   }
   return fused_exchange_bytes(N, H, W, p, world * subs);
+}
+
+size_t msn_ms_slab_fused_workspace_bytes(int N, int H, int W, const msn_ms_params* p) {
+  Geometry g;
+  if (resolve(p, N, H, W, &g, "ms_slab_fused_workspace_bytes")) return 0;
+  return fused_workspace_bytes(N, H, W, g.Dn, p) + 256;
 }
 
 int msn_ms_slab_fused_dev(const uint8_t* d_left, const uint8_t* d_right, int N, int H, int W, const msn_ms_params* p,

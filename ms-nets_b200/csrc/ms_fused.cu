@@ -96,7 +96,7 @@ struct FusedWs {
   float* AR;       // right image: NCC window sums A as a plain float plane
   double* CR;      // right image: NCC 1/sqrt(9B - A^2) as a plain double plane
   float* luts;     // [128] census AML exponentials + [256] census byte -> channel 0
-  float* sadsob;   // [N][D][H][W]
+  float* sadsob;   // [N][H][D][Ws]
   void* sad_ws;
   size_t total;
   void carve(char* base, const FusedGeom& g) {
@@ -230,7 +230,7 @@ struct FusedArgs {
   const float *meanR, *AR;       // right-image ZSAD means / NCC window sums, float planes
   const double* CR;              // right-image NCC scale, double plane
   const float* luts;    // [128] + [256], see ms_prep_kernel
-  const float* sadsob;  // [N][D][H][Ws] (+ slack)
+  const float* sadsob;  // [N][H][D][Ws] (+ slack)
   float* out;           // [N][8][D][h][w]
   float* mins;          // slab phase A only: [N][mins_planes][h][w], planes 0-3 = per-pixel minima of this launch's disparities
   int out_channels;     // channel count of the output tensor (pair stride): 8, or 16 when the caller adds the right view
@@ -473,7 +473,7 @@ __device__ __forceinline__ void stage_sad_tma(const FusedArgs& a, const CUtensor
                                               float* park_plane1, unsigned long long* bar_sad) {
   const FusedGeom& g = a.g;
   mbar_expect_tx(bar_sad, (unsigned)g.D * kTile * 4u);
-  tma_load_3d(park_plane1, sad_map, t.x0 + g.bwl + g.sxo, t.y + g.bh, t.n * g.Dl + t.sub0, bar_sad);  // inner coordinate % 4 == 0
+  tma_load_3d(park_plane1, sad_map, t.x0 + g.bwl + g.sxo, t.sub0, t.n * g.H + t.y + g.bh, bar_sad);  // inner coordinate % 4 == 0
 }
 
 // A pixel's own left-image data: census code, stats, 5x5 float window.  Loaded straight from
@@ -933,30 +933,45 @@ __device__ __forceinline__ void xchg_publish(const FusedArgs& a, int round, long
       asm volatile("st.volatile.global.u32 [%0], %1;" ::"l"(a.xchg.peer[p] + off), "r"(w) : "memory");
   }
 }
-// Warps 0-3: waits for every rank's lines of this tile and folds them in rank order (kSum: a + b, else
-// min) into out[0..128).  A peer that never shows up (crashed rank, mismatched launch) trips a trap after
-// ~2 s instead of hanging the GPU.
+// Warps 0-3: waits for every source's lines of this tile and folds them in source order (kSum: a + b, else
+// min) into out[0..128).  All the loads of a polling round are issued before the first flag is examined (8
+// sources at a time), so a round costs one trip to L2, not one per source.  A peer that never shows up
+// (crashed rank, mismatched launch) trips a trap after ~2 s instead of hanging the GPU.
 template <bool kSum>
 __device__ __forceinline__ void xchg_collect(const FusedArgs& a, int round, long long tile, int warp, int lane,
                                              float* out) {
   const unsigned* mine = a.xchg.peer[a.xchg.rank];
+  const unsigned epoch = a.xchg.epoch;
   for (int k = warp; k < kXLines; k += 4) {
     float acc = kSum ? 0.f : kFill;
-    for (int src = 0; src < a.xchg.V; ++src) {
-      const unsigned* line = mine + xchg_line0(a, round, tile, src) + (size_t)k * kXLineWords;
-      unsigned w;
+    for (int s0 = 0; s0 < a.xchg.V; s0 += 8) {
+      const int ns = min(8, a.xchg.V - s0);
+      const unsigned* line = mine + xchg_line0(a, round, tile, s0) + (size_t)k * kXLineWords + lane;
+      unsigned w[8];
+      unsigned pending = (1u << ns) - 1u;
       long long t0 = 0;
-      for (unsigned spins = 0;; ++spins) {
-        asm volatile("ld.volatile.global.u32 %0, [%1];" : "=r"(w) : "l"(line + lane) : "memory");
-        if (__shfl_sync(0xffffffffu, w, 31) == a.xchg.epoch) break;
-        if (spins == 64) t0 = clock64();
-        if (spins > 64) {
-          __nanosleep(200);
-          if (clock64() - t0 > 4000000000LL) __trap();
+      for (unsigned spins = 0; pending; ++spins) {
+#pragma unroll
+        for (int j = 0; j < 8; ++j)
+          if ((pending >> j) & 1u)
+            asm volatile("ld.volatile.global.u32 %0, [%1];" : "=r"(w[j]) : "l"(line + (size_t)j * kXLines * kXLineWords) : "memory");
+#pragma unroll
+        for (int j = 0; j < 8; ++j)
+          if (((pending >> j) & 1u) && __shfl_sync(0xffffffffu, w[j], 31) == epoch) pending &= ~(1u << j);
+        if (pending) {
+          if (spins == 16) t0 = clock64();
+          if (spins > 16) {
+            __nanosleep(100);
+            if (clock64() - t0 > 4000000000LL) __trap();
+          }
         }
       }
-      const float v = __uint_as_float(w);
-      acc = kSum ? __fadd_rn(acc, v) : fminf(acc, v);
+#pragma unroll
+      for (int j = 0; j < 8; ++j)
+        if (j < ns) {
+          const float v = __uint_as_float(w[j]);
+          acc = kSum ? __fadd_rn(acc, v) : fminf(acc, v);
+        }
     }
     const int i = 31 * k + lane;
     if (lane < 31 && i < 128) out[i] = acc;
@@ -1178,8 +1193,8 @@ __device__ __forceinline__ void fused_tile(const FusedArgs& a, const CUtensorMap
     }
   } else {
     // sadsob costs of this thread's own disparities: async global -> parked plane 1
-    const size_t splane = (size_t)g.H * g.Ws;
-    const float* src = a.sadsob + (((size_t)t.n * g.Dl + t.sub0) * g.H + (t.y + g.bh)) * g.Ws + (t.x0 + px + g.bwl + g.sxo) +
+    const size_t splane = (size_t)g.Ws;   // scratch is [N][H][Dl][Ws]: the disparities of a row are adjacent
+    const float* src = a.sadsob + (((size_t)t.n * g.H + (t.y + g.bh)) * g.Dl + t.sub0) * g.Ws + (t.x0 + px + g.bwl + g.sxo) +
                        (size_t)d_lo * splane;
     float* dst = s_par + PS + d_lo * kTile + px;
     for (int d = d_lo; d < d_end; ++d, src += splane, dst += kTile) cp_async4(dst, src);
@@ -1254,7 +1269,7 @@ static bool tma_disabled() {
   return e && e[0] == '1';
 }
 
-// 3-D tensor map over the SAD-of-Sobel scratch [N*D][H][Ws], box 32 x 1 x D (encoded once per scratch)
+// 3-D tensor map over the SAD-of-Sobel scratch [N*H][D][Ws], box 32 x D x 1 (encoded once per scratch)
 static bool sad_tensor_map(const FusedGeom& g, int H, int N, const float* base, CUtensorMap* out) {
   const MapKey key{base, g.Ws, H, N * g.Dl, g.D};
   {
@@ -1267,9 +1282,9 @@ static bool sad_tensor_map(const FusedGeom& g, int H, int N, const float* base, 
   }
   PFN_encodeTiled enc = get_encode_fn();
   if (!enc) return false;
-  const cuuint64_t gdim[3] = {(cuuint64_t)g.Ws, (cuuint64_t)H, (cuuint64_t)N * g.Dl};
-  const cuuint64_t gstr[2] = {(cuuint64_t)g.Ws * 4, (cuuint64_t)H * g.Ws * 4};
-  const cuuint32_t box[3] = {(cuuint32_t)kTile, 1u, (cuuint32_t)g.D};
+  const cuuint64_t gdim[3] = {(cuuint64_t)g.Ws, (cuuint64_t)g.Dl, (cuuint64_t)N * H};
+  const cuuint64_t gstr[2] = {(cuuint64_t)g.Ws * 4, (cuuint64_t)g.Dl * g.Ws * 4};
+  const cuuint32_t box[3] = {(cuuint32_t)kTile, (cuuint32_t)g.D, 1u};
   const cuuint32_t estr[3] = {1u, 1u, 1u};
   if (enc(out, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3, const_cast<float*>(base), gdim, gstr, box, estr,
           CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_NONE,

@@ -231,7 +231,7 @@ class ExchangeSlabMSFeatures(object):
         self._opened = []
         self.epoch = 0
         with torch.cuda.device(self.device):
-            nbytes = L.msn_ms_features_workspace_bytes(self.N, self.H, self.W, ctypes.byref(self.params))
+            nbytes = L.msn_ms_slab_fused_workspace_bytes(self.N, self.H, self.W, ctypes.byref(self.params))
             self.table_bytes = L.msn_ms_slab_exchange_bytes(self.N, self.H, self.W, ctypes.byref(self.params), world,
                                                             self.subs)
             if nbytes == 0 or self.table_bytes == 0:

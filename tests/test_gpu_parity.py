@@ -304,7 +304,8 @@ def test_generate_test_cbmv_device_resident(ms, oracle, golden_dir, left_only):
     import torch
     g = np.load(os.path.join(golden_dir, "test_cbmv.npz"))
     tag = "left" if left_only else "lr"
-    f, h, w, ch, cw = ms.cbmv.generate_test_cbmv(g["L"], g["R"], encoder_ds=16, maxdisp=24, is_left_only=left_only)
+    f, h, w, ch, cw = ms.cbmv.generate_test_cbmv(g["L"], g["R"], encoder_ds=16, maxdisp=24, is_left_only=left_only,
+                                                 args_dict={"ds_scale": 1})
     assert isinstance(f, torch.Tensor) and f.is_cuda and f.dtype == torch.float32
     want, h2, w2, ch2, cw2 = oracle.generate_test_cbmv(g["L"], g["R"], encoder_ds=16, maxdisp=24,
                                                        is_left_only=left_only)
@@ -319,8 +320,9 @@ def test_generate_test_cbmv_device_resident(ms, oracle, golden_dir, left_only):
     chan = (np.arange(got.size)[::5] // (got.size // C)) % 8
     assert np.array_equal(sub[chan < 4], ref[chan < 4])
     assert np.abs(sub - ref).max() <= AML_ATOL
-    with pytest.raises(NotImplementedError):
-        ms.cbmv.generate_test_cbmv(g["L"], g["R"], args_dict={"ds_scale": 2})
+    # the reference's default (args_dict=None -> ds_scale = 2): half-size volume (tests/test_gpu_prematch.py)
+    f2 = ms.cbmv.generate_test_cbmv(g["L"], g["R"], encoder_ds=16, maxdisp=24, is_left_only=left_only)[0]
+    assert tuple(f2.shape) == (f.shape[0], 12, ch // 2, cw // 2)
 
 
 @pytest.mark.parametrize("H,W,D,seed", [(40, 70, 24, 5), (37, 101, 64, 6), (48, 60, 130, 7)])
