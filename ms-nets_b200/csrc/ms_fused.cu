@@ -1230,6 +1230,142 @@ ms_fused_kernel(const FusedArgs a, const __grid_constant__ CUtensorMap sad_map) 
   }
 }
 
+
+// ---- disparity-slab exchange, two tiles per CTA ---------------------------------------------------------
+// A narrow slab (<= 96 disparities per CTA: eight GPUs on a 640-disparity frame hold 80 each) leaves a tile
+// too little work to hide the two trips its minima and denominators make to the other GPUs.  Here a CTA
+// owns TWO neighbouring tiles a, b of a row, each with its own parking and staging area, and interleaves
+// them so that every trip has real work to hide behind:
+//     phase 1(a) -> publish minima(a) -> phase 1(b) -> publish minima(b)
+//     warps 0-3:  collect minima(a), denominators(a), publish(a); the same for b; collect den(a), den(b)
+//     warps 4-7:  channels 0-3 of a and b (and the WTA by-product)
+//     phase 3(a), phase 3(b)
+// minima(a) travel during phase 1(b); den(a) travels while b's chain runs.  Same tables, same protocol as
+// the one-tile form (a rank may not mix the two, the launch geometry is part of the contract).
+template <int DMAX>
+struct Lay2 {
+  using S = StageLay<DMAX, kSlack>;
+  using P = ParkLay<DMAX>;
+  static constexpr int PS = P::PS;
+  static constexpr size_t off_stage0 = 0, off_stage1 = S::st_bytes;
+  static constexpr size_t off_red = 2 * S::st_bytes;                        // [8][4][32], transient, shared by a and b
+  static constexpr size_t off_small = off_red + (size_t)kGroups * 4 * kTile * 4;  // per tile: loc, min, den, tot, inv = 5 x [4][32]
+  static constexpr size_t small_bytes = 5 * 4 * kTile * 4;
+  static constexpr size_t off_lut = off_small + 2 * small_bytes;            // [128] + [256] census tables
+  static constexpr size_t off_par0 = (off_lut + 384 * 4 + 127) & ~(size_t)127;
+  static constexpr size_t off_par1 = off_par0 + P::pk_bytes;
+  static constexpr size_t off_bar = off_par1 + P::pk_bytes;                 // 4 mbarriers
+  static constexpr size_t bytes = off_bar + 64;
+  // what the shared helpers expect from a layout
+  static constexpr int kSl = S::kSl, RW = S::RW, RWF = S::RWF;
+  static constexpr size_t st_desc = S::st_desc, st_c = S::st_c, st_rf = S::st_rf;
+};
+
+template <int DMAX>
+__global__ void __launch_bounds__(256, 2)
+ms_slab_x2_kernel(const FusedArgs a, const __grid_constant__ CUtensorMap sad_map) {
+  using L = Lay2<DMAX>;
+  constexpr int PS = L::PS;
+  extern __shared__ __align__(128) unsigned char smem_raw[];
+  const FusedGeom& g = a.g;
+  const int D = g.D;
+  const int tid = threadIdx.x, px = tid % kTile, grp = tid / kTile, warp = tid >> 5, lane = tid & 31;
+  const int d_lo = grp * a.DC, d_end = min(D, d_lo + a.DC);
+  const int sub = (int)(blockIdx.x % (unsigned)a.subs);
+  const unsigned pair = blockIdx.x / (unsigned)a.subs;
+  const int pairs_x = (a.tiles_x + 1) >> 1;
+  const int xp = (int)(pair % (unsigned)pairs_x);
+  const long long row = pair / (unsigned)pairs_x;                 // n * h + y
+  const long long tile_id[2] = {row * a.tiles_x + 2 * xp, row * a.tiles_x + 2 * xp + 1};
+  const int nt = (2 * xp + 1 < a.tiles_x) ? 2 : 1;
+  TileId tt[2];
+  tt[0] = decode_tile((int)tile_id[0], a, sub);
+  tt[1] = tt[0];
+  tt[1].x0 += kTile;
+  unsigned char* stage[2] = {smem_raw + L::off_stage0, smem_raw + L::off_stage1};
+  float* s_par[2] = {reinterpret_cast<float*>(smem_raw + L::off_par0), reinterpret_cast<float*>(smem_raw + L::off_par1)};
+  uint8_t* s_cen[2] = {smem_raw + L::off_par0 + L::P::pk_cen, smem_raw + L::off_par1 + L::P::pk_cen};
+  float* s_red = reinterpret_cast<float*>(smem_raw + L::off_red);
+  float* small[2] = {reinterpret_cast<float*>(smem_raw + L::off_small),
+                     reinterpret_cast<float*>(smem_raw + L::off_small + L::small_bytes)};
+  unsigned long long* s_bar = reinterpret_cast<unsigned long long*>(smem_raw + L::off_bar);
+  constexpr int kLoc = 0, kMin = 128, kDen = 256, kTot = 384, kInv = 512;   // offsets into small[i]
+  float* s_lut = reinterpret_cast<float*>(smem_raw + L::off_lut);
+  float* s_lutn = s_lut + 128;
+  if (kCenLut) {
+    if (tid < 128) s_lut[tid] = __ldg(a.luts + tid);
+    s_lutn[tid] = __ldg(a.luts + 128 + tid);
+  }
+  if (tid == 0) {
+    for (int i = 0; i < 4; ++i) mbar_init(&s_bar[i], 1);
+    mbar_init_fence();
+    for (int i = 0; i < nt; ++i) {
+      stage_rows_tma<L>(a, tt[i], stage[i], &s_bar[2 * i]);
+      stage_sad_tma(a, &sad_map, tt[i], s_par[i] + PS, &s_bar[2 * i + 1]);
+    }
+  }
+  __syncthreads();
+  for (int i = 0; i < nt; ++i) {
+    LeftRegs lr;
+    load_left(a, tt[i], px, lr);
+    mbar_wait(&s_bar[2 * i], 0);
+    const Phase1Out o = phase1_tile<L>(a, tt[i], stage[i], s_par[i], s_cen[i], lr, px, d_lo);
+    mbar_wait(&s_bar[2 * i + 1], 0);
+    finish_phase1<L>(s_par[i], s_red, o, px, grp, d_lo, d_end);
+    __syncthreads();
+    if (tid < 4 * kTile) {   // this slab's minima of tile i
+      float v = kFill;
+#pragma unroll
+      for (int gq = 0; gq < kGroups; ++gq) v = fminf(v, s_red[gq * 4 * kTile + tid]);
+      small[i][kLoc + tid] = v;
+    }
+    __syncthreads();         // (s_red is free for the next tile)
+    if (warp < 4) xchg_publish(a, 0, tile_id[i], tt[i].v, warp, lane, small[i] + kLoc);
+  }
+  const size_t plane = (size_t)g.h * g.w;
+  const size_t chan = plane * a.out_D;
+  const int q4 = (tid & 7) * 4;
+  const bool vec_ok = ((g.w & 3) == 0) && ((reinterpret_cast<uintptr_t>(a.out) & 15) == 0);
+  float* orow[2];
+  int nlive[2];
+  for (int i = 0; i < 2; ++i) {
+    orow[i] = a.out + (size_t)tt[i].n * a.out_channels * chan + (size_t)(a.out_d0 + tt[i].sub0) * plane +
+              (size_t)tt[i].y * g.w + (tt[i].x0 + q4);
+    nlive[i] = min(4, g.w - (tt[i].x0 + q4));
+  }
+  if (warp < 4) {
+    float mm[2] = {kFill, kFill};
+    for (int i = 0; i < nt; ++i) {
+      xchg_collect<false>(a, 0, tile_id[i], warp, lane, small[i] + kMin);
+      bar_sync_128();
+      mm[i] = small[i][kMin + warp * kTile + lane];
+      small[i][kDen + warp * kTile + lane] = den_chain<L>(a, warp, lane, mm[i], s_par[i], s_cen[i], s_lut);
+      bar_sync_128();
+      xchg_publish(a, 1, tile_id[i], tt[i].v, warp, lane, small[i] + kDen);
+    }
+    for (int i = 0; i < nt; ++i) {
+      xchg_collect<true>(a, 1, tile_id[i], warp, lane, small[i] + kTot);
+      bar_sync_128();
+      const float den = small[i][kTot + warp * kTile + lane];
+      small[i][kInv + warp * kTile + lane] = (mm[i] == kFill) ? 0.f : 1.0f / den;
+    }
+  } else {
+    for (int i = 0; i < nt; ++i) {
+      if (vec_ok && nlive[i] == 4) store_ch03<true>(s_par[i], s_cen[i], s_lutn, PS, q4, (tid >> 3) - 16, D, orow[i], plane, chan, nlive[i]);
+      else store_ch03<false>(s_par[i], s_cen[i], s_lutn, PS, q4, (tid >> 3) - 16, D, orow[i], plane, chan, nlive[i]);
+      if (a.wta_idx) wta_scan<L>(a, tt[i], warp - 4, lane, s_par[i], s_cen[i]);
+    }
+  }
+  __syncthreads();
+  const int dl = tid >> 3;
+  for (int i = 0; i < nt; ++i) {
+    if (vec_ok && nlive[i] == 4)
+      phase3_quads<true>(s_par[i], s_cen[i], s_lut, small[i] + kMin, small[i] + kInv, PS, q4, dl, D, orow[i] + 4 * chan, plane, chan, nlive[i], a.k_cen, a.k_ncc, a.k_sad);
+    else
+      phase3_quads<false>(s_par[i], s_cen[i], s_lut, small[i] + kMin, small[i] + kInv, PS, q4, dl, D, orow[i] + 4 * chan, plane, chan, nlive[i], a.k_cen, a.k_ncc, a.k_sad);
+  }
+}
+
 // Optional per-kernel timing (msn_profile_enable): CUDA events recorded on the launch
 // stream between the kernels of the fused sequence, read back by msn_profile_read.
 struct ProfRec { cudaEvent_t ev[4]; };
@@ -1263,6 +1399,13 @@ static PFN_encodeTiled get_encode_fn() {
     return (PFN_encodeTiled)p;
   }();
   return fn;
+}
+// The two-tiles-per-CTA exchange kernel is opt-in (MSNETS_X2=1): measured slower than the one-tile form both with
+// local virtual ranks (width 80: 1.47 vs 1.32 ms per config-B pair equivalent) and across 8 GPUs (config M:
+// 12.1 vs 10.7 ms) -- two long phase-1 stretches per CTA overlap worse with the co-resident CTA than four short ones.
+static bool x2_disabled() {
+  const char* e = getenv("MSNETS_X2");
+  return !(e && e[0] == '1');
 }
 static bool tma_disabled() {
   const char* e = getenv("MSNETS_NO_TMA");
@@ -1314,6 +1457,28 @@ static int launch_inst(const FusedArgs& a, const CUtensorMap& map, long long til
     }
   }
   kern<<<(unsigned)(tiles * (kMode == kModeXchg ? a.subs : 1)), 256, smem, s>>>(a, map);
+  return 0;
+}
+
+template <int DMAX>
+static int launch_x2(const FusedArgs& a, const CUtensorMap& map, long long tiles, cudaStream_t s) {
+  auto kern = ms_slab_x2_kernel<DMAX>;
+  constexpr size_t smem = Lay2<DMAX>::bytes;
+  static std::mutex mu;
+  static unsigned long long done_mask = 0;
+  int dev = 0;
+  MSN_CUDA_OK(cudaGetDevice(&dev));
+  {
+    std::lock_guard<std::mutex> lk(mu);
+    if (dev >= 64 || !((done_mask >> dev) & 1ull)) {
+      MSN_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+      if (dev < 64) done_mask |= 1ull << dev;
+    }
+  }
+  const long long rows = tiles / a.tiles_x;
+  const long long ctas = rows * ((a.tiles_x + 1) / 2) * a.subs;
+  MSN_REQUIRE(ctas <= 2147483647LL, "ms_slab_fused: too many tiles for one launch");
+  kern<<<(unsigned)ctas, 256, smem, s>>>(a, map);
   return 0;
 }
 
@@ -1453,6 +1618,18 @@ int launch_ms_fused(const uint8_t* d_left, const uint8_t* d_right, int N, int H,
   bool use_tma = g.D <= 256 && !tma_disabled();
   if (use_tma) use_tma = sad_tensor_map(g, H, N, ws.sadsob, &sad_map);
   a.DC = 2 * (((g.D + kGroups - 1) / kGroups + 1) / 2);   // phase 1 walks disparity pairs
+  // narrow exchange slabs: two tiles per CTA (ms_slab_x2_kernel)
+  if (xchg && use_tma && g.D <= 96 && !x2_disabled()) {
+    if (g.D <= 64) { if (launch_x2<64>(a, sad_map, tiles, s)) return 1; }
+    else { if (launch_x2<96>(a, sad_map, tiles, s)) return 1; }
+    MSN_LAUNCH_OK();
+    if (prof) {
+      MSN_CUDA_OK(cudaEventRecord(rec.ev[3], s));
+      std::lock_guard<std::mutex> lk(g_prof_mu);
+      g_prof.push_back(rec);
+    }
+    return 0;
+  }
 #define MSN_FUSED_LAUNCH(DMAX, TMA)                                                \
   {                                                                                \
     if (xchg) { if (launch_inst<DMAX, TMA, kModeXchg>(a, sad_map, tiles, s)) return 1; } \

@@ -188,15 +188,23 @@ class ExchangeSlabMSFeatures(object):
     all-gathered over `group`.  `connect=False` leaves the wiring to the caller (`table_ptr`, `wire`):
     several virtual ranks inside one process, as the one-GPU tests do."""
 
-    MAX_TILE_D = 192    # widest sub-slab (the fused kernel's TMA instantiations park up to 256 disparities)
+    # sub-slab widths tried in turn.  192 is the widest a tile parks on the TMA path and the most efficient
+    # (per-tile fixed costs amortise over more disparities: 0.94 ms per config-B pair equivalent at 192, 1.07 at
+    # 128, 1.32 at 80 -- profiles/xchg_grid.py)
+    TILE_D_CHOICES = (192,)
 
     @staticmethod
     def sub_slabs(maxdisp, world):
-        """Sub-slabs per rank: the widest rank slab cut into equal parts of at most MAX_TILE_D disparities
-        (the same number on every rank); None when some rank's slab does not divide evenly."""
+        """Sub-slabs per rank: every rank's slab cut into the same number of equal parts, as narrow as the
+        first width of TILE_D_CHOICES that divides every slab evenly; None when none does."""
         counts = [shard_range(maxdisp, r, world)[1] for r in range(world)]
-        subs = -(-max(counts) // ExchangeSlabMSFeatures.MAX_TILE_D)
-        return subs if all(c % subs == 0 and c > 0 for c in counts) else None
+        if min(counts) < 1:
+            return None
+        for width in ExchangeSlabMSFeatures.TILE_D_CHOICES:
+            subs = -(-max(counts) // width)
+            if subs * world <= 32 and all(c % subs == 0 for c in counts):
+                return subs
+        return None
 
     def __init__(self, N, H, W, maxdisp=192, rank=None, world=None, group=None, device=None, connect=True, **kw):
         import torch

@@ -19,11 +19,11 @@ def timed(fn, n=3):
     return c.value / k.value
 
 
-for ds in (96, 128, 160, 192):
+for ds in (tuple(int(v) for v in sys.argv[1:]) or (64, 80, 96, 128, 160, 192)):
     row = []
     for S in (1, 2, 3, 4):
         D = ds * S
-        sharding.ExchangeSlabMSFeatures.MAX_TILE_D = ds
+        sharding.ExchangeSlabMSFeatures.TILE_D_CHOICES = (ds,)
         xs = sharding.ExchangeSlabMSFeatures(1, H + 2 * B, W + 2 * B, maxdisp=D, rank=0, world=1, connect=False, board_h=B,
                                              board_w_left=B, board_w_right=B)
         assert xs.subs == S

@@ -88,7 +88,8 @@ def _virtual_exchange_ranks(L, R, D, border, world):
 
 
 @pytest.mark.parametrize("world,H,W,D", [(1, 36, 70, 40), (2, 36, 70, 40), (2, 50, 116, 64), (4, 30, 84, 96),
-                                          (1, 34, 70, 384), (2, 30, 52, 640)])   # last two: 2 sub-slabs per rank
+                                          (1, 34, 70, 384), (2, 30, 52, 640),   # two sub-slabs per rank (192 / 160 wide)
+                                          (1, 36, 70, 191), (2, 36, 70, 262)])
 def test_fused_slab_exchange_virtual_ranks(oracle, world, H, W, D):
     """msn_ms_slab_fused_dev: the slab kernel with the min / denominator exchange inside the tile."""
     import msnets_b200 as ms
@@ -135,6 +136,19 @@ def test_fused_slab_wta_parts_merge(oracle, world, D):
         assert np.array_equal(m1[0, c].cpu().numpy(), w1) and np.array_equal(m2[0, c].cpu().numpy(), w2)
     for x in ranks:
         x.close()
+
+
+def test_fused_slab_exchange_two_tiles_per_cta_form(oracle, monkeypatch):
+    """ms_slab_x2_kernel (opt-in, MSNETS_X2=1): narrow sub-slabs, two tiles per CTA, the same tables."""
+    from msnets_b200 import sharding
+    monkeypatch.setenv("MSNETS_X2", "1")
+    monkeypatch.setattr(sharding.ExchangeSlabMSFeatures, "TILE_D_CHOICES", (96,))
+    for world, H, W, D in ((2, 36, 70, 40), (1, 34, 70, 384), (2, 30, 52, 640), (2, 34, 100, 128)):
+        L, R = bordered_pair(H, W, 31 + world, border=10, patches=True)
+        got = _virtual_exchange_ranks(L, R, D, 10, world)
+        want = oracle.ms_features(L, R, D)
+        assert np.array_equal(got[:4], want[:4])
+        assert np.abs(got[4:] - want[4:]).max() <= AML_ATOL
 
 
 def test_slab_wta_and_soft_argmin_single_rank(oracle):
