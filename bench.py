@@ -343,9 +343,15 @@ def slab_config_m(dev, rank, world, steps=3, warmup=2):
     gen.manual_seed(77 + rank)
     logits = torch.randn((1, ex.d_count, H, W), generator=gen, device=dev, dtype=torch.float32)
 
+    parts = ex.empty_wta_parts() if mode == "exchange" else None
+
     def step():
-        ex(l, r, out=out)
-        am, m1 = sharding.slab_wta(out[0, 0], ex.d_begin, layout="dhw")
+        if mode == "exchange":     # WTA / second-min triples are a by-product of the slab kernel: merge them
+            ex(l, r, out=out, wta=parts)
+            am, m1, m2 = sharding.slab_wta_merge(*parts)
+        else:
+            ex(l, r, out=out)
+            am, m1 = sharding.slab_wta(out[0, 0], ex.d_begin, layout="dhw")
         return am, sharding.slab_soft_argmin(logits, ex.d_begin)
 
     for _ in range(warmup):
@@ -380,7 +386,9 @@ def slab_config_m(dev, rank, world, steps=3, warmup=2):
             "aml_min_and_den": ("in-kernel: %d sub-slab(s) per rank push 2 x 640 B per tile to %d peer(s) over NVLink "
                                 "= %.1f MB out per rank" % (subs, world - 1, tiles * subs * 2 * 640 * (world - 1) / 1e6))
             if mode == "exchange" else "2 x NCCL all_reduce over [4,1984,2880] f32 = 91.4 MB each",
-            "wta": "NCCL all_reduce(min) over [1984,2880] int64 keys = 45.7 MB",
+            "wta": ("NCCL all_gather of the kernel's (argmin, min1, min2) by-product, 4 channels: 3 x [%d,1,4,1984,2880] "
+                    "x 4 B = %.1f MB per rank, merged by msn_wta_merge_dev" % (subs, 3 * subs * 4 * H * W * 4 / 1e6))
+            if mode == "exchange" else "NCCL all_reduce(min) over [1984,2880] int64 keys = 45.7 MB",
             "soft_argmin": "NCCL all_gather of [3,1984,2880] f32 partials = 68.6 MB per rank"},
         "aml_column_sum_max_err": err,
     }
@@ -488,32 +496,38 @@ def _rows_for_budget(arm, steps, budget_s):
     return int(max(32, min(H_IMG, budget_s / max(steps, 1) / per_row)))
 
 
+def _cpu_sample_one(variant, budget_s):
+    """One full-frame (or largest fitting band) step of the reference's CPU path with one build of oracle/_ref."""
+    arm = _reference_arm(variant)
+    rows = _rows_for_budget(arm, 1, budget_s)
+    L, R, lg = _sample_inputs(rows)
+    arm["native_s"][0] = 0.0
+    t0 = time.time()
+    _cpu_step(arm, L, R, lg)
+    dt = time.time() - t0
+    frac = rows / float(H_IMG)
+    return {"value": round(frac / dt, 4), "unit": "pairs/s", "cores": arm["cores"], "kind": arm["kind"],
+            "sample": "%d of 540 rows (x960, D=192) of one pair, one step: %s + softmax/regression; %d host cpus"
+                      % (rows, arm["what"], os.cpu_count() or 0),
+            "seconds": round(dt, 2), "native_only_seconds": round(arm["native_s"][0], 2),
+            "native_only_pairs_per_s": round(frac / max(arm["native_s"][0], 1e-9), 4)}
+
+
 def cpu_baseline_sample(budget_s=30.0):
     """The reference's CPU path timed beside the GPU run (rank 0, N = 1): one full 540x960 frame per
-    build when it fits the budget -- the host-core-count build (value) and the shipped 8-thread build."""
-    out = None
-    for variant, key in (("avx2_nproc", None), ("avx2", "threads_as_shipped")):
-        arm = _reference_arm(variant)
-        if arm["kind"] != "reference" and key is not None:
-            continue
-        rows = _rows_for_budget(arm, 1, budget_s / 2)
-        L, R, lg = _sample_inputs(rows)
-        arm["native_s"][0] = 0.0
-        t0 = time.time()
-        _cpu_step(arm, L, R, lg)
-        dt = time.time() - t0
-        frac = rows / float(H_IMG)
-        rec = {"value": round(frac / dt, 4), "unit": "pairs/s", "cores": arm["cores"], "kind": arm["kind"],
-               "sample": "%d of 540 rows (x960, D=192) of one pair, one step: %s + softmax/regression; %d host cpus"
-                         % (rows, arm["what"], os.cpu_count() or 0),
-               "seconds": round(dt, 2), "native_only_seconds": round(arm["native_s"][0], 2),
-               "native_only_pairs_per_s": round(frac / max(arm["native_s"][0], 1e-9), 4)}
-        if key is None:
-            out = rec
-        elif out is not None:
-            out[key] = rec
-        if arm["kind"] != "reference":
-            break
+    build when it fits the budget -- the host-core-count build (value) and the shipped 8-thread build.  The
+    second build runs in a child process: two builds of one extension module (same PyInit name) cannot be
+    loaded side by side."""
+    import subprocess
+    out = _cpu_sample_one(None if not os.path.isdir(os.path.join(ROOT, "oracle", "_ref", "avx2_nproc")) else "avx2_nproc",
+                          budget_s / 2)
+    if out["kind"] == "reference":
+        try:
+            r = subprocess.run([sys.executable, os.path.abspath(__file__), "--cpu-sample", "avx2", "--budget",
+                                str(budget_s / 2)], capture_output=True, text=True, timeout=300)
+            out["threads_as_shipped"] = json.loads(r.stdout.strip().splitlines()[-1])
+        except Exception as e:
+            out["threads_as_shipped"] = {"unavailable": "%s: %s" % (type(e).__name__, e)}
     return out
 
 
@@ -559,7 +573,12 @@ def main():
     ap.add_argument("--steps", type=int, default=10)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--cpu-sample", default=None, help="internal: time one reference step with this oracle/_ref build")
+    ap.add_argument("--budget", type=float, default=15.0)
     args = ap.parse_args()
+    if args.cpu_sample:
+        print(json.dumps(_cpu_sample_one(args.cpu_sample, args.budget)))
+        return
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
     if args.impl == "reference":
         run_reference(args)

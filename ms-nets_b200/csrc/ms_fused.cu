@@ -64,6 +64,7 @@ struct FusedGeom {
   int N, H, W, h, w, bh, bwl;
   int D;    // disparities handled by this launch: [d0, d0 + D)
   int d0;   // first disparity (> 0 only for a disparity slab)
+  int d_inner;  // SAD-of-Sobel scratch layout: 0 [N][Dl][H][Ws], 1 [N][H][Dl][Ws] (sub-slab launches, see sadsob.cu)
   int Dl;   // disparities of the whole launch (= D unless the launch is cut into sub-slabs, kModeXchg)
   int Hp, Wp, padL;
   int sxo, Ws;   // SAD-of-Sobel scratch: column offset and row pitch (tile starts land on 16 B)
@@ -75,7 +76,7 @@ FusedGeom make_geom(int N, int H, int W, const msn_ms_params* p) {
   g.N = N; g.H = H; g.W = W;
   g.d0 = p->d_count > 0 ? p->d_begin : 0;
   g.D = p->d_count > 0 ? p->d_count : p->ndisp;
-  g.Dl = g.D;
+  g.Dl = g.D; g.d_inner = 0;
   g.bh = p->board_h; g.bwl = p->board_w_left;
   g.h = H - 2 * p->board_h;
   g.w = W - p->board_w_left - p->board_w_right;
@@ -96,7 +97,7 @@ struct FusedWs {
   float* AR;       // right image: NCC window sums A as a plain float plane
   double* CR;      // right image: NCC 1/sqrt(9B - A^2) as a plain double plane
   float* luts;     // [128] census AML exponentials + [256] census byte -> channel 0
-  float* sadsob;   // [N][H][D][Ws]
+  float* sadsob;   // [N][D][H][Ws], or [N][H][D][Ws] (FusedGeom::d_inner)
   void* sad_ws;
   size_t total;
   void carve(char* base, const FusedGeom& g) {
@@ -230,7 +231,7 @@ struct FusedArgs {
   const float *meanR, *AR;       // right-image ZSAD means / NCC window sums, float planes
   const double* CR;              // right-image NCC scale, double plane
   const float* luts;    // [128] + [256], see ms_prep_kernel
-  const float* sadsob;  // [N][H][D][Ws] (+ slack)
+  const float* sadsob;  // see FusedWs
   float* out;           // [N][8][D][h][w]
   float* mins;          // slab phase A only: [N][mins_planes][h][w], planes 0-3 = per-pixel minima of this launch's disparities
   int out_channels;     // channel count of the output tensor (pair stride): 8, or 16 when the caller adds the right view
@@ -473,7 +474,8 @@ __device__ __forceinline__ void stage_sad_tma(const FusedArgs& a, const CUtensor
                                               float* park_plane1, unsigned long long* bar_sad) {
   const FusedGeom& g = a.g;
   mbar_expect_tx(bar_sad, (unsigned)g.D * kTile * 4u);
-  tma_load_3d(park_plane1, sad_map, t.x0 + g.bwl + g.sxo, t.sub0, t.n * g.H + t.y + g.bh, bar_sad);  // inner coordinate % 4 == 0
+  if (g.d_inner) tma_load_3d(park_plane1, sad_map, t.x0 + g.bwl + g.sxo, t.sub0, t.n * g.H + t.y + g.bh, bar_sad);
+  else tma_load_3d(park_plane1, sad_map, t.x0 + g.bwl + g.sxo, t.y + g.bh, t.n * g.Dl + t.sub0, bar_sad);  // inner coordinate % 4 == 0
 }
 
 // A pixel's own left-image data: census code, stats, 5x5 float window.  Loaded straight from
@@ -1193,9 +1195,10 @@ __device__ __forceinline__ void fused_tile(const FusedArgs& a, const CUtensorMap
     }
   } else {
     // sadsob costs of this thread's own disparities: async global -> parked plane 1
-    const size_t splane = (size_t)g.Ws;   // scratch is [N][H][Dl][Ws]: the disparities of a row are adjacent
-    const float* src = a.sadsob + (((size_t)t.n * g.H + (t.y + g.bh)) * g.Dl + t.sub0) * g.Ws + (t.x0 + px + g.bwl + g.sxo) +
-                       (size_t)d_lo * splane;
+    const size_t splane = g.d_inner ? (size_t)g.Ws : (size_t)g.H * g.Ws;
+    const size_t row0 = g.d_inner ? (((size_t)t.n * g.H + (t.y + g.bh)) * g.Dl + t.sub0) * g.Ws
+                                  : (((size_t)t.n * g.Dl + t.sub0) * g.H + (t.y + g.bh)) * g.Ws;
+    const float* src = a.sadsob + row0 + (t.x0 + px + g.bwl + g.sxo) + (size_t)d_lo * splane;
     float* dst = s_par + PS + d_lo * kTile + px;
     for (int d = d_lo; d < d_end; ++d, src += splane, dst += kTile) cp_async4(dst, src);
     stage_right<L, NT>(a, t, smem_raw);
@@ -1377,8 +1380,8 @@ constexpr size_t kProfMaxPending = 4096;   // records kept when nobody calls msn
 // cuTensorMapEncodeTiled results, keyed by what they describe (a launch sequence repeats the same map)
 struct MapKey {
   const void* base;
-  int Ws, H, ND, D;
-  bool operator==(const MapKey& o) const { return base == o.base && Ws == o.Ws && H == o.H && ND == o.ND && D == o.D; }
+  int Ws, H, ND, D, inner;
+  bool operator==(const MapKey& o) const { return base == o.base && Ws == o.Ws && H == o.H && ND == o.ND && D == o.D && inner == o.inner; }
 };
 std::mutex g_map_mu;
 std::vector<std::pair<MapKey, CUtensorMap>> g_maps;
@@ -1412,9 +1415,9 @@ static bool tma_disabled() {
   return e && e[0] == '1';
 }
 
-// 3-D tensor map over the SAD-of-Sobel scratch [N*H][D][Ws], box 32 x D x 1 (encoded once per scratch)
+// 3-D tensor map over the SAD-of-Sobel scratch: [N*D][H][Ws], box 32 x 1 x D -- or, d_inner, [N*H][D][Ws], box 32 x D x 1
 static bool sad_tensor_map(const FusedGeom& g, int H, int N, const float* base, CUtensorMap* out) {
-  const MapKey key{base, g.Ws, H, N * g.Dl, g.D};
+  const MapKey key{base, g.Ws, H, N * g.Dl, g.D, g.d_inner};
   {
     std::lock_guard<std::mutex> lk(g_map_mu);
     for (auto& kv : g_maps)
@@ -1425,9 +1428,14 @@ static bool sad_tensor_map(const FusedGeom& g, int H, int N, const float* base, 
   }
   PFN_encodeTiled enc = get_encode_fn();
   if (!enc) return false;
-  const cuuint64_t gdim[3] = {(cuuint64_t)g.Ws, (cuuint64_t)g.Dl, (cuuint64_t)N * H};
-  const cuuint64_t gstr[2] = {(cuuint64_t)g.Ws * 4, (cuuint64_t)g.Dl * g.Ws * 4};
-  const cuuint32_t box[3] = {(cuuint32_t)kTile, (cuuint32_t)g.D, 1u};
+  cuuint64_t gdim[3] = {(cuuint64_t)g.Ws, (cuuint64_t)H, (cuuint64_t)N * g.Dl};
+  cuuint64_t gstr[2] = {(cuuint64_t)g.Ws * 4, (cuuint64_t)H * g.Ws * 4};
+  cuuint32_t box[3] = {(cuuint32_t)kTile, 1u, (cuuint32_t)g.D};
+  if (g.d_inner) {
+    gdim[1] = (cuuint64_t)g.Dl; gdim[2] = (cuuint64_t)N * H;
+    gstr[1] = (cuuint64_t)g.Dl * g.Ws * 4;
+    box[1] = (cuuint32_t)g.D; box[2] = 1u;
+  }
   const cuuint32_t estr[3] = {1u, 1u, 1u};
   if (enc(out, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3, const_cast<float*>(base), gdim, gstr, box, estr,
           CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_NONE,
@@ -1567,7 +1575,8 @@ int launch_ms_fused(const uint8_t* d_left, const uint8_t* d_right, int N, int H,
                                        ws.luts, aml_scale(p->cens_sigma));
   MSN_LAUNCH_OK();
   if (prof) MSN_CUDA_OK(cudaEventRecord(rec.ev[1], s));
-  if (launch_sadsob5_padded(ws.sob[0], ws.sob[1], N, H, W, g.Dl, g.d0, ws.sadsob + g.sxo, ws.sad_ws, s)) return 1;
+  g.d_inner = subs > 1 ? 1 : 0;   // several sub-slabs in flight: keep a tile's scratch rows on one page
+  if (launch_sadsob5_padded(ws.sob[0], ws.sob[1], N, H, W, g.Dl, g.d0, ws.sadsob + g.sxo, ws.sad_ws, s, g.d_inner != 0)) return 1;
   if (prof) MSN_CUDA_OK(cudaEventRecord(rec.ev[2], s));
 
   g.D = g.Dl / subs;   // what one CTA handles (the scan above covered the launch's whole slab)

@@ -91,7 +91,7 @@ sadsob_scan_kernel(const float* __restrict__ L, const float* __restrict__ R, int
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int job = blockIdx.x * kSadWarps + warp;
   if (job >= Dn * NB) return;  // whole warp exits together
-  const int dd = job % Dn, b = job / Dn, n = blockIdx.z;
+  const int dd = job / NB, b = job % NB, n = blockIdx.z;
   const int d = d_begin + dd;
   const int IW = W + 1, wc = wsize / 2;
   const int i0 = b * RB;
@@ -196,22 +196,22 @@ __device__ __forceinline__ void s5_vertical(const float* __restrict__ lp, const 
 
 // SP: row pitch in floats of BOTH the Sobel images and the output volume (compile-time so
 // that every row offset is an immediate); W <= SP.
-template <int SP>
+template <int SP, bool kDInner>
 __global__ void __launch_bounds__(kS5Warps * 32, 4)
 sadsob_scan5_kernel(const float* __restrict__ L, const float* __restrict__ R, int H, int W, int Dn, int d_begin,
                     int NB, size_t img_stride, const float* __restrict__ Vb, float* __restrict__ out,
                     size_t out_stride) {
-  // The output is [N][H][Dn][SP]: the Dn rows of one image row lie side by side, so the fused kernel's tile
-  // (one row y, all disparities) reads ONE contiguous Dn x 4 KB span instead of Dn rows megabytes apart -- a
-  // Middlebury-sized volume (21 GB of scratch) otherwise runs out of TLB reach (measured: 2.5x slower).
-  // Jobs are numbered disparity-fastest for the same reason: neighbouring warps write neighbouring rows and
-  // read the same rows of L.
+  // kDInner: the output is [N][H][Dn][SP] -- the Dn rows of one image row lie side by side, so the fused
+  // kernel's tile (one row y, all disparities) reads ONE contiguous Dn x 4 KB span instead of Dn rows megabytes
+  // apart: a Middlebury-sized volume cut into sub-slabs of one launch (12+ GB of scratch) otherwise falls off
+  // the TLB (measured 1.5x slower); jobs are then numbered disparity-fastest, so neighbouring warps write
+  // neighbouring rows.  Otherwise [N][Dn][H][SP] with compile-time row offsets (5 % faster at config B).
   __shared__ float sT[kS5Warps][kSadTile * kS5Stride];
   constexpr int RB = kSadTile - kS5W;  // 27 origin rows per band
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int job = blockIdx.x * kS5Warps + warp;
   if (job >= Dn * NB) return;  // whole warp exits together
-  const int dd = job / NB, b = job % NB, n = blockIdx.z;
+  const int dd = kDInner ? job % Dn : job / NB, b = kDInner ? job / Dn : job % NB, n = blockIdx.z;
   const int d = d_begin + dd;
   const int IW = W + 1;
   const int i0 = b * RB;
@@ -219,8 +219,9 @@ sadsob_scan5_kernel(const float* __restrict__ L, const float* __restrict__ R, in
   const float* Ln = L + n * img_stride + (size_t)i0 * SP;
   const float* Rn = R + n * img_stride + (size_t)i0 * SP - d;
   const float* vb = Vb + (((size_t)n * Dn + dd) * NB + b) * IW;
-  const size_t row_stride = (size_t)Dn * SP;
-  float* o = out + n * out_stride + ((size_t)(i0 + 2) * Dn + dd) * SP + 2;
+  const size_t row_stride = kDInner ? (size_t)Dn * SP : (size_t)SP;
+  float* o = kDInner ? out + n * out_stride + ((size_t)(i0 + 2) * Dn + dd) * SP + 2
+                     : out + n * out_stride + (size_t)dd * H * SP + (size_t)(i0 + 2) * SP + 2;
   const int rmax = min(RB, H - kS5W - i0);          // origin rows produced by this band
 
   const int t0 = d / kSadTile, t1 = (W - 1) / kSadTile;
@@ -271,7 +272,7 @@ sadsob_scan5_kernel(const float* __restrict__ L, const float* __restrict__ R, in
         const float bl = T[(r + kS5W) * kS5Stride + lane];
         const float br = T[(r + kS5W) * kS5Stride + lane + kS5W];
         const float val = __fadd_rn(__fsub_rn(__fsub_rn(br, bl), hi[r % kS5W]), lo[r % kS5W]);
-        if (r < rmax) st_stream(op + r * row_stride, val);
+        if (r < rmax) st_stream(kDInner ? op + r * row_stride : op + r * SP, val);
         lo[r % kS5W] = bl;
         hi[r % kS5W] = br;
       }
@@ -327,11 +328,11 @@ int launch_sadsob_n(const float* L, const float* R, int N, int H, int W, int Dn,
 }
 
 // Fast form for the fused path (window 5): L/R are [N][H + kSadRowPad][SP] with ZERO padding
-// rows/columns, out is [N][H][Dn][SP]; SP = sadsob_fast_pitch(W) is one of 1024/2048/4096.
+// rows/columns, out is [N][Dn][H][SP] (d_inner: [N][H][Dn][SP]); SP = sadsob_fast_pitch(W) is one of 1024/2048/4096.
 int sadsob_fast_pitch(int W) { return W <= 1024 ? 1024 : W <= 2048 ? 2048 : W <= 4096 ? 4096 : 0; }
 
 int launch_sadsob5_padded(const float* L, const float* R, int N, int H, int W, int Dn, int d_begin, float* out,
-                          void* workspace, cudaStream_t s) {
+                          void* workspace, cudaStream_t s, bool d_inner) {
   const int SP = sadsob_fast_pitch(W);
   MSN_REQUIRE(SP > 0, "sadsob: W=%d too wide for the padded window-5 scan", W);
   int RB, NB;
@@ -344,12 +345,15 @@ int launch_sadsob5_padded(const float* L, const float* R, int N, int H, int W, i
   sadsob_vband_kernel<<<g1, 128, 0, s>>>(L, R, H, W, SP, d_begin, RB, NB, img_stride, Vb);
   MSN_LAUNCH_OK();
   dim3 g5(div_up((long long)Dn * NB, kS5Warps), 1, N);
-  if (SP == 1024)
-    sadsob_scan5_kernel<1024><<<g5, kS5Warps * 32, 0, s>>>(L, R, H, W, Dn, d_begin, NB, img_stride, Vb, out, out_stride);
-  else if (SP == 2048)
-    sadsob_scan5_kernel<2048><<<g5, kS5Warps * 32, 0, s>>>(L, R, H, W, Dn, d_begin, NB, img_stride, Vb, out, out_stride);
-  else
-    sadsob_scan5_kernel<4096><<<g5, kS5Warps * 32, 0, s>>>(L, R, H, W, Dn, d_begin, NB, img_stride, Vb, out, out_stride);
+#define MSN_SCAN5(P)                                                                                             \
+  {                                                                                                              \
+    if (d_inner) sadsob_scan5_kernel<P, true><<<g5, kS5Warps * 32, 0, s>>>(L, R, H, W, Dn, d_begin, NB, img_stride, Vb, out, out_stride); \
+    else sadsob_scan5_kernel<P, false><<<g5, kS5Warps * 32, 0, s>>>(L, R, H, W, Dn, d_begin, NB, img_stride, Vb, out, out_stride);        \
+  }
+  if (SP == 1024) MSN_SCAN5(1024)
+  else if (SP == 2048) MSN_SCAN5(2048)
+  else MSN_SCAN5(4096)
+#undef MSN_SCAN5
   MSN_LAUNCH_OK();
   return 0;
 }
