@@ -352,3 +352,31 @@ def test_fused_wta_byproduct_matches_argmin_of_the_volume(ms, oracle, H, W, D, s
         assert np.array_equal(am[0, c], np.argmin(want[c], axis=0))
     conf = ms.confidence.pkrn_confidence(wta[1], wta[2], 0.01).cpu().numpy()
     assert np.array_equal(conf, oracle.pkrn_confidence(m1, m2, 0.01))
+
+
+def test_soft_argmin_autograd(ms):
+    """The reference trains THROUGH F.softmax + disparityregression (gcnet_3dcnn.py:127-141): the kernels carry
+    gradients (msn_soft_argmin_backward_dev; expectation backward = grad x arange(D))."""
+    import torch
+    import torch.nn.functional as F
+    g = torch.Generator("cuda").manual_seed(3)
+    x = (torch.randn((2, 48, 9, 20), generator=g, device="cuda") * 2).requires_grad_(True)
+    w = torch.randn((2, 9, 20), generator=g, device="cuda")
+    disp = ms.regression.soft_argmin(x)
+    assert disp.grad_fn is not None
+    (disp * w).sum().backward()
+    got = x.grad.clone()
+    x.grad = None
+    dvec = torch.arange(48, device="cuda", dtype=torch.float32).view(1, 48, 1, 1)
+    ref = torch.sum(F.softmax(x, 1) * dvec, 1)
+    (ref * w).sum().backward()
+    assert float((disp - ref).abs().max()) <= SOFTARGMIN_ATOL
+    assert float((got - x.grad).abs().max()) <= 1e-5 * max(1.0, float(x.grad.abs().max()))
+    # the regression half alone, as the patched model uses it
+    p = F.softmax(x.detach(), 1).requires_grad_(True)
+    e = ms.regression.expected_disparity(p)
+    assert e.grad_fn is not None
+    (e * w).sum().backward()
+    assert torch.allclose(p.grad, w.unsqueeze(1) * dvec)
+    with torch.no_grad():
+        assert ms.regression.soft_argmin(x).grad_fn is None
