@@ -126,6 +126,13 @@ MSN_API int msn_ms_features_wta_dev(const uint8_t* d_left, const uint8_t* d_righ
                             float* d_wta_min1_n4hw, float* d_wta_min2_n4hw, void* d_workspace,
                             size_t workspace_bytes, void* stream);
 
+/* bf16 volume: the same [N][8][D][h][w] volume with every value rounded to nearest-even
+ * bfloat16 inside the fused kernel (default windows, left view, D <= 448) -- half the bytes for a consumer
+ * that runs its first Conv3d under bf16 autocast.  Identical to converting the fp32 volume afterwards. */
+MSN_API int msn_ms_features_bf16_dev(const uint8_t* d_left, const uint8_t* d_right, int N, int H, int W,
+                             const msn_ms_params* p, void* d_out_bf16_ncdhw, void* d_workspace,
+                             size_t workspace_bytes, void* stream);
+
 /* Measurement aid for bench.py: when enabled, msn_ms_features_dev brackets the kernels of
  * the fused sequence (prep | sadsob scan | fused volume) with CUDA events on the launch
  * stream; msn_profile_read synchronises, returns the summed milliseconds and the number

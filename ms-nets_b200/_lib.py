@@ -56,6 +56,7 @@ _SIGNATURES = {
     "msn_ms_features_workspace_bytes": (c_size_t, [c_int, c_int, c_int, ctypes.POINTER(MsParams)]),
     "msn_ms_features_dev": (c_int, [_P, _P, c_int, c_int, c_int, ctypes.POINTER(MsParams), _P, _P,
                                     c_size_t, _P]),
+    "msn_ms_features_bf16_dev": (c_int, [_P, _P, c_int, c_int, c_int, ctypes.POINTER(MsParams), _P, _P, c_size_t, _P]),
     "msn_profile_enable": (c_int, [c_int]),
     "msn_profile_read": (c_int, [ctypes.POINTER(ctypes.c_double), ctypes.POINTER(ctypes.c_double),
                                  ctypes.POINTER(ctypes.c_double), ctypes.POINTER(c_int)]),

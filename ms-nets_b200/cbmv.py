@@ -126,7 +126,9 @@ class MSFeatureExtractor(object):
     DataLoader-worker CPU extraction + `cost.cuda()` copy (main_msnet.py:375-377,
     571-572): the 3.2 GB/pair volume is produced where the 3D CNN consumes it."""
 
-    def __init__(self, N, H, W, maxdisp=192, left_only=True, device=None, **kw):
+    def __init__(self, N, H, W, maxdisp=192, left_only=True, device=None, out_dtype=None, **kw):
+        """out_dtype: torch.float32 (default) or torch.bfloat16 -- the volume rounded to bf16 inside the kernel
+        (msn_ms_features_bf16_dev), half the bytes for a consumer under bf16 autocast."""
         import torch
         if not torch.cuda.is_available():
             raise _lib.MsnetsError("MSFeatureExtractor needs a CUDA device (no CPU fallback)")
@@ -135,6 +137,9 @@ class MSFeatureExtractor(object):
         self.N, self.H, self.W = int(N), int(H), int(W)
         self.params = make_params(maxdisp, left_only=left_only, **kw)
         self.shape = output_shape(self.N, self.H, self.W, self.params)
+        self.out_dtype = torch.float32 if out_dtype is None else out_dtype
+        if self.out_dtype not in (torch.float32, torch.bfloat16):
+            raise ValueError("out_dtype must be torch.float32 or torch.bfloat16")
         with torch.cuda.device(self.device):
             nbytes = _lib.lib().msn_ms_features_workspace_bytes(self.N, self.H, self.W, ctypes.byref(self.params))
             if nbytes == 0:
@@ -142,7 +147,7 @@ class MSFeatureExtractor(object):
             self.workspace = torch.empty(nbytes, dtype=torch.uint8, device=self.device)
 
     def empty_output(self):
-        return self.torch.empty(self.shape, dtype=self.torch.float32, device=self.device)
+        return self.torch.empty(self.shape, dtype=self.out_dtype, device=self.device)
 
     def empty_wta(self):
         """(argmin int32, min1 float32, min2 float32), each [N,4,h,w]: buffers for the `wta=` by-product."""
@@ -163,11 +168,18 @@ class MSFeatureExtractor(object):
                 raise ValueError("expected contiguous uint8 CUDA tensors of shape %s" % ((self.N, self.H, self.W),))
         if out is None:
             out = self.empty_output()
-        elif tuple(out.shape) != self.shape or out.dtype != torch.float32 or not out.is_contiguous():
-            raise ValueError("out must be a contiguous float32 tensor of shape %s" % (self.shape,))
+        elif tuple(out.shape) != self.shape or out.dtype != self.out_dtype or not out.is_contiguous():
+            raise ValueError("out must be a contiguous %s tensor of shape %s" % (self.out_dtype, self.shape))
         with torch.cuda.device(self.device):
             stream = torch.cuda.current_stream().cuda_stream
-            if wta is None:
+            if self.out_dtype == torch.bfloat16:
+                if wta is not None:
+                    raise ValueError("wta= is not combined with the bf16 volume")
+                _lib.check(_lib.lib().msn_ms_features_bf16_dev(left.data_ptr(), right.data_ptr(), self.N, self.H,
+                                                               self.W, ctypes.byref(self.params), out.data_ptr(),
+                                                               self.workspace.data_ptr(), self.workspace.numel(),
+                                                               stream))
+            elif wta is None:
                 _lib.check(_lib.lib().msn_ms_features_dev(left.data_ptr(), right.data_ptr(), self.N, self.H, self.W,
                                                           ctypes.byref(self.params), out.data_ptr(),
                                                           self.workspace.data_ptr(), self.workspace.numel(), stream))

@@ -689,6 +689,19 @@ int msn_ms_features_wta_dev(const uint8_t* d_left, const uint8_t* d_right, int N
   return 0;
 }
 
+int msn_ms_features_bf16_dev(const uint8_t* d_left, const uint8_t* d_right, int N, int H, int W, const msn_ms_params* p,
+                             void* d_out_bf16, void* d_workspace, size_t workspace_bytes, void* stream) {
+  Geometry g;
+  TRY(resolve(p, N, H, W, &g, "ms_features_bf16"));
+  MSN_REQUIRE(d_left && d_right && d_out_bf16 && d_workspace, "ms_features_bf16: null pointer argument");
+  MSN_REQUIRE(use_fused(p, g, W) && !p->lr && g.d_begin == 0 && g.Dn == g.D,
+              "ms_features_bf16: the bf16 volume comes from the fused kernel (default windows, left view, D <= 448)");
+  MSN_REQUIRE(workspace_bytes >= msn_ms_features_workspace_bytes(N, H, W, p), "ms_features_bf16: workspace too small");
+  char* base = (char*)(((uintptr_t)d_workspace + 255) & ~(uintptr_t)255);
+  return launch_ms_fused(d_left, d_right, N, H, W, p, reinterpret_cast<float*>(d_out_bf16), nullptr, base,
+                         as_stream(stream), 0, 0, 0, nullptr, nullptr, true);
+}
+
 int msn_ms_features_host(const uint8_t* left, const uint8_t* right, int N, int H, int W, const msn_ms_params* p,
                          float* out_ncdhw) {
   Geometry g;

@@ -1,5 +1,6 @@
 // common.cuh -- shared helpers for the msnets_b200 kernels (sm_100a only).
 #pragma once
+#include <cuda_bf16.h>
 #include <cuda_runtime.h>
 #include <stdint.h>
 #include <stdio.h>
@@ -58,6 +59,16 @@ struct Win {
 // streaming (evict-first) stores for the write-once cost volumes
 __device__ __forceinline__ void st_stream(float* p, float v) { __stcs(p, v); }
 __device__ __forceinline__ void st_stream4(float* p, float4 v) { __stcs(reinterpret_cast<float4*>(p), v); }
+// bf16 volume: the same values rounded to nearest even, four pixels per 64-bit store
+__device__ __forceinline__ void st_stream4(__nv_bfloat16* p, const float4& v) {
+  const __nv_bfloat162 lo = __floats2bfloat162_rn(v.x, v.y), hi = __floats2bfloat162_rn(v.z, v.w);
+  uint2 u;
+  u.x = *reinterpret_cast<const unsigned*>(&lo);
+  u.y = *reinterpret_cast<const unsigned*>(&hi);
+  __stcs(reinterpret_cast<uint2*>(p), u);
+}
+__device__ __forceinline__ void st_stream(__nv_bfloat16* p, float v) { *p = __float2bfloat16_rn(v); }
+
 
 // ---- host-side launchers (each returns 0 or sets the error and returns 1) ---
 // prep.cu

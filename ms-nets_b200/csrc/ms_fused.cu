@@ -35,6 +35,7 @@
 #include "ms_fused.cuh"
 
 #include <cuda.h>
+#include <cuda_bf16.h>
 #include <stdlib.h>
 
 #include <mutex>
@@ -254,7 +255,7 @@ struct FusedArgs {
 };
 
 constexpr int kTile = 32;   // pixels per tile: one output row segment of 128 bytes
-constexpr int kModeFull = 0, kModeSlabA = 1, kModeXchg = 2;
+constexpr int kModeFull = 0, kModeSlabA = 1, kModeXchg = 2, kModeBf16 = 3;   // kModeBf16: kModeFull writing a bf16 volume
 
 // Staging buffer of one tile: right-image row data for the D + 31 (+ slack) columns the tile
 // can touch.  Row strides are compile-time so every shared access in the hot loop is
@@ -782,8 +783,8 @@ __device__ __forceinline__ float cen_e(int cb, int mc, const float* s_lut, float
 
 // Stores four channel planes' 4-pixel row segments: 128-bit streaming stores when the rows are
 // 16 B aligned and the quad is fully inside the image (kVec), guarded scalars otherwise.
-template <bool kVec>
-__device__ __forceinline__ void store_quads(float* o, size_t chan, int nlive, const float4& c0, const float4& c1,
+template <bool kVec, class T>
+__device__ __forceinline__ void store_quads(T* o, size_t chan, int nlive, const float4& c0, const float4& c1,
                                             const float4& c2, const float4& c3) {
   if (kVec) {
     st_stream4(o, c0);
@@ -804,9 +805,9 @@ __device__ __forceinline__ void store_quads(float* o, size_t chan, int nlive, co
 // ---- back half of a tile: channels 0-3, AML denominators, channels 4-7 --------------------
 // Channels 0-3 (cbmv_generator.py:283-287) for thread = (pixel quad q4, disparities d0, d0+16, ... < d1):
 // normalised costs stored as 128-bit row segments.
-template <bool kVec>
+template <bool kVec, class T>
 __device__ __forceinline__ void store_ch03(const float* s_par, const uint8_t* s_cen, const float* s_lutn, int PS,
-                                           int q4, int d0, int d1, float* orow, size_t plane, size_t chan,
+                                           int q4, int d0, int d1, T* orow, size_t plane, size_t chan,
                                            int nlive) {
 #pragma unroll(kBackUnroll)
   for (int d = d0; d < d1; d += 16) {
@@ -838,10 +839,10 @@ __device__ __forceinline__ void p3_quad(const float4& v, const f32x2 (&m)[2], co
 
 // Channels 4-7 = exp(-(c-m)^2/sigma) / den for thread = (pixel quad q4, disparities dl, dl+32, ...),
 // exponentials recomputed from the parked costs, 128-bit row segments.
-template <bool kVec>
+template <bool kVec, class T>
 __device__ __forceinline__ void phase3_quads(const float* s_par, const uint8_t* s_cen, const float* s_lut,
                                              const float* s_min, const float* s_inv, int PS, int q4, int dl, int D,
-                                             float* arow, size_t plane, size_t chan, int nlive, float k0, float k1, float k2) {
+                                             T* arow, size_t plane, size_t chan, int nlive, float k0, float k1, float k2) {
   const float4 m_cen4 = *reinterpret_cast<const float4*>(s_min + q4);
   const float4 m1 = *reinterpret_cast<const float4*>(s_min + kTile + q4);
   const float4 m2 = *reinterpret_cast<const float4*>(s_min + 2 * kTile + q4);
@@ -1033,7 +1034,7 @@ __device__ __forceinline__ void wta_scan(const FusedArgs& a, const TileId& t, in
 // part of the channel 0-3 stores to the chain warps statically or through a work counter (no
 // gain: the halves are already balanced), a warp-specialised persistent producer/consumer
 // kernel (15 % slower).
-template <class L, bool kXchg>
+template <class L, bool kXchg, class T = float>
 __device__ __forceinline__ void tile_back_half(const FusedArgs& a, const TileId& t, long long tile, int tid,
                                                const float* s_par, const uint8_t* s_cen, float* s_red, float* s_min,
                                                float* s_inv, const float* s_lut, const float* s_lutn) {
@@ -1053,7 +1054,7 @@ __device__ __forceinline__ void tile_back_half(const FusedArgs& a, const TileId&
   const int q4 = (tid & 7) * 4;
   // 128-bit stores need 16-byte aligned rows
   const bool vec_ok = ((g.w & 3) == 0) && ((reinterpret_cast<uintptr_t>(a.out) & 15) == 0);
-  float* orow = a.out + (size_t)t.n * a.out_channels * chan + (size_t)(a.out_d0 + t.sub0) * plane + (size_t)t.y * g.w + (t.x0 + q4);
+  T* orow = reinterpret_cast<T*>(a.out) + (size_t)t.n * a.out_channels * chan + (size_t)(a.out_d0 + t.sub0) * plane + (size_t)t.y * g.w + (t.x0 + q4);
   const int nlive = min(4, g.w - (t.x0 + q4));  // live pixels of this quad (<= 0: none)
   const bool vec = vec_ok && nlive == 4;
   if (warp < 4) {
@@ -1218,6 +1219,7 @@ __device__ __forceinline__ void fused_tile(const FusedArgs& a, const CUtensorMap
   finish_phase1<L>(s_par, s_red, o, px, grp, d_lo, d_end);
   __syncthreads();
   if (kMode == kModeSlabA) tile_slab_a<L>(a, t, tid, s_par, s_cen, s_red, s_lutn);
+  else if (kMode == kModeBf16) tile_back_half<L, false, __nv_bfloat16>(a, t, tile, tid, s_par, s_cen, s_red, s_min, s_inv, s_lut, s_lutn);
   else tile_back_half<L, kMode == kModeXchg>(a, t, tile, tid, s_par, s_cen, s_red, s_min, s_inv, s_lut, s_lutn);
 }
 
@@ -1547,7 +1549,8 @@ size_t fused_workspace_bytes(int N, int H, int W, int Dn, const msn_ms_params* p
 // accumulate != 0 from the second slab on).
 int launch_ms_fused(const uint8_t* d_left, const uint8_t* d_right, int N, int H, int W, const msn_ms_params* p,
                     float* d_out, float* d_mins, char* workspace, cudaStream_t s, int out_D, int out_d0,
-                    int accumulate, const msn_slab_exchange* xchg, const FusedWta* wta) {
+                    int accumulate, const msn_slab_exchange* xchg, const FusedWta* wta, bool out_bf16) {
+  MSN_REQUIRE(!out_bf16 || (!xchg && !d_mins), "ms_features: the bf16 volume is written by the one-pass kernel only");
   if (N == 0) return 0;
   FusedGeom g = make_geom(N, H, W, p);
   FusedWs ws;
@@ -1641,7 +1644,8 @@ int launch_ms_fused(const uint8_t* d_left, const uint8_t* d_right, int N, int H,
   }
 #define MSN_FUSED_LAUNCH(DMAX, TMA)                                                \
   {                                                                                \
-    if (xchg) { if (launch_inst<DMAX, TMA, kModeXchg>(a, sad_map, tiles, s)) return 1; } \
+    if (out_bf16) { if (launch_inst<DMAX, TMA, kModeBf16>(a, sad_map, tiles, s)) return 1; } \
+    else if (xchg) { if (launch_inst<DMAX, TMA, kModeXchg>(a, sad_map, tiles, s)) return 1; } \
     else if (d_mins) { if (launch_inst<DMAX, TMA, kModeSlabA>(a, sad_map, tiles, s)) return 1; } \
     else { if (launch_inst<DMAX, TMA, kModeFull>(a, sad_map, tiles, s)) return 1; }    \
   }

@@ -23,7 +23,8 @@ size_t fused_workspace_bytes(int N, int H, int W, int Dn, const msn_ms_params* p
 // out_D / out_d0 / accumulate: see ms_fused.cu (slabs of one volume processed on one GPU).
 int launch_ms_fused(const uint8_t* d_left, const uint8_t* d_right, int N, int H, int W, const msn_ms_params* p,
                     float* d_out, float* d_mins, char* workspace, cudaStream_t s, int out_D = 0, int out_d0 = 0,
-                    int accumulate = 0, const msn_slab_exchange* xchg = nullptr, const FusedWta* wta = nullptr);
+                    int accumulate = 0, const msn_slab_exchange* xchg = nullptr, const FusedWta* wta = nullptr,
+                    bool out_bf16 = false);   // out_bf16: d_out holds __nv_bfloat16 (same shape), one-pass path only
 // xchg != nullptr: this rank's disparity slab [p->d_begin, +p->d_count) with the AML minimum / denominator
 // traded with the other ranks INSIDE the kernel through their peer-mapped exchange tables (no d_mins, no
 // phases B/C).  Bytes of one rank's table:

@@ -380,3 +380,16 @@ def test_soft_argmin_autograd(ms):
     assert torch.allclose(p.grad, w.unsqueeze(1) * dvec)
     with torch.no_grad():
         assert ms.regression.soft_argmin(x).grad_fn is None
+
+
+@pytest.mark.parametrize("H,W,D", [(40, 70, 24), (37, 101, 64)])
+def test_bf16_volume_is_the_rounded_fp32_volume(ms, H, W, D):
+    """msn_ms_features_bf16_dev: round-to-nearest-even of the fp32 volume, bit for bit."""
+    import torch
+    L, R = bordered_pair(H, W, 3, border=10, patches=True)
+    l, r = torch.from_numpy(L[None]).cuda(), torch.from_numpy(R[None]).cuda()
+    kw = dict(maxdisp=D, board_h=10, board_w_left=10, board_w_right=10)
+    f32 = ms.cbmv.MSFeatureExtractor(1, L.shape[0], L.shape[1], **kw)(l, r)
+    b16 = ms.cbmv.MSFeatureExtractor(1, L.shape[0], L.shape[1], out_dtype=torch.bfloat16, **kw)(l, r)
+    assert b16.dtype == torch.bfloat16 and b16.shape == f32.shape
+    assert torch.equal(b16, f32.to(torch.bfloat16))
