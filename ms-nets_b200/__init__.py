@@ -20,7 +20,21 @@ from . import _lib
 from ._lib import MsnetsError, device_count
 
 __all__ = ["libmatchers", "libfeatextract", "cbmv", "regression", "confidence", "volume", "sharding",
-           "install_dropin", "MsnetsError", "device_count"]
+           "install_dropin", "set_aml_exact", "aml_exact", "MsnetsError", "device_count"]
+
+
+def set_aml_exact(on=True):
+    """Process-wide AML arithmetic mode (msn_set_aml_exact).  False (default): SFU exponential, within 2e-6 of the
+    reference (1.2e-5 on rare degenerate rows).  True: the reference's own fp32 operations with glibc's expf
+    replayed bit for bit -- extract_likelihood and feature channels 4-7 / 12-15 BIT-EXACT (featextract.cpp:435-453),
+    about 1.3x slower on the fused path.  Returns the previous setting."""
+    prev = bool(_lib.lib().msn_get_aml_exact())
+    _lib.check(_lib.lib().msn_set_aml_exact(1 if on else 0))
+    return prev
+
+
+def aml_exact():
+    return bool(_lib.lib().msn_get_aml_exact())
 
 
 def __getattr__(name):

@@ -57,6 +57,8 @@ _SIGNATURES = {
     "msn_ms_features_dev": (c_int, [_P, _P, c_int, c_int, c_int, ctypes.POINTER(MsParams), _P, _P,
                                     c_size_t, _P]),
     "msn_ms_features_bf16_dev": (c_int, [_P, _P, c_int, c_int, c_int, ctypes.POINTER(MsParams), _P, _P, c_size_t, _P]),
+    "msn_set_aml_exact": (c_int, [c_int]),
+    "msn_get_aml_exact": (c_int, []),
     "msn_profile_enable": (c_int, [c_int]),
     "msn_profile_read": (c_int, [ctypes.POINTER(ctypes.c_double), ctypes.POINTER(ctypes.c_double),
                                  ctypes.POINTER(ctypes.c_double), ctypes.POINTER(c_int)]),

@@ -15,6 +15,7 @@
 #include "ms_fused.cuh"
 
 namespace msn {
+int g_aml_exact = 0;   // msn_set_aml_exact: AML in the reference's own fp32 operations (feature_math.cuh)
 
 static thread_local char g_err[768] = "";
 
@@ -825,6 +826,12 @@ int msn_wta_merge_dev(const int32_t* d_idx_parts, const float* d_min1_parts, con
   MSN_REQUIRE(parts >= 1 && n >= 0, "wta_merge: bad shape");
   return launch_wta_merge(d_idx_parts, d_min1_parts, d_min2_parts, parts, n, d_idx, d_min1, d_min2, as_stream(stream));
 }
+
+int msn_set_aml_exact(int on) {
+  g_aml_exact = on ? 1 : 0;
+  return 0;
+}
+int msn_get_aml_exact(void) { return g_aml_exact; }
 
 int msn_peer_alloc(size_t bytes, void** d_ptr) {
   MSN_REQUIRE(d_ptr && bytes > 0, "peer_alloc: bad argument");

@@ -73,13 +73,13 @@ features_from_costs_kernel(const float* __restrict__ c0, const float* __restrict
 #pragma unroll 8
       for (int d = 0; d < D; ++d) den = __fadd_rn(den, tile[d * 33 + lane]);
     }
-    s_inv[lane] = (mn == kFill) ? 0.f : 1.0f / den;
+    s_inv[lane] = aml_row_scale(den, mn != kFill, k);
   }
   __syncthreads();
   if (!live) return;
   const float inv = s_inv[lane];
   float* o_aml = out + ((size_t)((right ? 8 : 0) + 4 + m) * D) * n + p;
-  for (int d = warp; d < D; d += kFeatWarps) st_stream(o_aml + (size_t)d * n, tile[d * 33 + lane] * inv);
+  for (int d = warp; d < D; d += kFeatWarps) st_stream(o_aml + (size_t)d * n, aml_apply(tile[d * 33 + lane], inv, k));
 }
 
 int launch_features_from_costs(const float* census, const float* ncc, const float* sobel, const float* sad,

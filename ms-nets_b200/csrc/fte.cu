@@ -128,14 +128,14 @@ aml_rows_kernel(const float* __restrict__ cost, long long n, int D, float k, flo
 #pragma unroll 8
       for (int d = 0; d < D; ++d) den = __fadd_rn(den, tile[d * 33 + lane]);
     }
-    s_inv[lane] = (s_min[lane] == kFill) ? 0.f : 1.0f / den;
+    s_inv[lane] = aml_row_scale(den, s_min[lane] != kFill, k);
   }
   __syncthreads();
   for (int r = warp; r < kAmlRows; r += kAmlWarps) {
     if (r0 + r >= n) break;
     const float inv = s_inv[r];
     float* o = out + (r0 + r) * D;
-    for (int d = lane; d < D; d += 32) st_stream(o + d, tile[d * 33 + r] * inv);
+    for (int d = lane; d < D; d += 32) st_stream(o + d, aml_apply(tile[d * 33 + r], inv, k));
   }
 }
 

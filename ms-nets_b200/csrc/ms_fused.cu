@@ -132,7 +132,7 @@ ms_prep_kernel(const uint8_t* __restrict__ left, const uint8_t* __restrict__ rig
     // channel-0 value k/120 of a parked census byte (a true IEEE division; 255 = no cost ->
     // clip(fill, 0, 120)/120 = 1)
     for (int kk = threadIdx.x; kk < 256; kk += blockDim.x) {
-      if (kk < 128) luts[kk] = (kk <= 120) ? ex2_approx(-(float)(kk * kk) * k_cen) : 0.f;
+      if (kk < 128) luts[kk] = (kk <= 120) ? aml_e((float)kk, 0.f, k_cen) : 0.f;   // (either AML mode)
       luts[128 + kk] = (kk <= 120) ? __fdiv_rn((float)kk, 120.0f) : 1.0f;
     }
   }
@@ -255,7 +255,7 @@ struct FusedArgs {
 };
 
 constexpr int kTile = 32;   // pixels per tile: one output row segment of 128 bytes
-constexpr int kModeFull = 0, kModeSlabA = 1, kModeXchg = 2, kModeBf16 = 3;   // kModeBf16: kModeFull writing a bf16 volume
+constexpr int kModeFull = 0, kModeSlabA = 1, kModeXchg = 2, kModeBf16 = 3, kModeExact = 4;   // kModeBf16: kModeFull writing a bf16 volume; kModeExact: kModeFull with the reference's own AML arithmetic
 
 // Staging buffer of one tile: right-image row data for the D + 31 (+ slack) columns the tile
 // can touch.  Row strides are compile-time so every shared access in the hot loop is
@@ -773,12 +773,17 @@ __device__ __forceinline__ float cen_ch0(int cb, const float* s_lutn) {
   const float q = __fmul_rn(k, r);
   return __fmaf_rn(__fmaf_rn(-120.0f, q, k), r, q);
 }
-template <bool kLut>
+template <bool kLut, bool kExact = false>
 __device__ __forceinline__ float cen_e(int cb, int mc, const float* s_lut, float k_cen) {
-  if (kLut) return s_lut[min(cb - mc, 127)];
+  if (kLut) return s_lut[min(cb - mc, 127)];     // (the table is built in the launch's AML mode)
   const float t = (float)(cb - mc);
-  const float e = ex2_approx(-(t * t) * k_cen);
+  const float e = kExact ? aml_e_exact(t, 0.f, -k_cen) : aml_e_fast(t, 0.f, k_cen);
   return (cb - mc > 120) ? 0.f : e;
+}
+// AML term in the kernel's mode: kExact instantiations carry k = -sigma (feature_math.cuh)
+template <bool kExact>
+__device__ __forceinline__ float aml_t(float c, float m, float k) {
+  return kExact ? aml_e_exact(c, m, -k) : aml_e_fast(c, m, k);
 }
 
 // Stores four channel planes' 4-pixel row segments: 128-bit streaming stores when the rows are
@@ -837,9 +842,16 @@ __device__ __forceinline__ void p3_quad(const float4& v, const f32x2 (&m)[2], co
   upk2(mul2(pk2(e2, e3), inv[1]), out.z, out.w);
 }
 
+__device__ __forceinline__ void p3_quad_exact(const float4& v, const float4& m, const float4& den, float sigma, float4& out) {
+  out.x = __fdiv_rn(aml_e_exact(v.x, m.x, sigma), den.x);
+  out.y = __fdiv_rn(aml_e_exact(v.y, m.y, sigma), den.y);
+  out.z = __fdiv_rn(aml_e_exact(v.z, m.z, sigma), den.z);
+  out.w = __fdiv_rn(aml_e_exact(v.w, m.w, sigma), den.w);
+}
+
 // Channels 4-7 = exp(-(c-m)^2/sigma) / den for thread = (pixel quad q4, disparities dl, dl+32, ...),
 // exponentials recomputed from the parked costs, 128-bit row segments.
-template <bool kVec, class T>
+template <bool kVec, class T, bool kExact = false>
 __device__ __forceinline__ void phase3_quads(const float* s_par, const uint8_t* s_cen, const float* s_lut,
                                              const float* s_min, const float* s_inv, int PS, int q4, int dl, int D,
                                              T* arow, size_t plane, size_t chan, int nlive, float k0, float k1, float k2) {
@@ -864,12 +876,20 @@ __device__ __forceinline__ void phase3_quads(const float* s_par, const uint8_t* 
     const float4 v1 = *reinterpret_cast<const float4*>(e0);
     const float4 v2 = *reinterpret_cast<const float4*>(e0 + PS);
     const float4 v3 = *reinterpret_cast<const float4*>(e0 + 2 * PS);
-    const float4 a0 = make_float4(cen_e<kCenLutP3>(cb.x, mcx, s_lut, k0) * i0.x, cen_e<kCenLutP3>(cb.y, mcy, s_lut, k0) * i0.y,
-                                  cen_e<kCenLutP3>(cb.z, mcz, s_lut, k0) * i0.z, cen_e<kCenLutP3>(cb.w, mcw, s_lut, k0) * i0.w);
-    float4 a1, a2, a3;
-    p3_quad(v1, mp1, ip1, nk1, a1);
-    p3_quad(v2, mp2, ip2, nk2, a2);
-    p3_quad(v3, mp3, ip3, nk2, a3);
+    float4 a0, a1, a2, a3;
+    if (kExact) {   // s_inv holds the denominators themselves (INFINITY where the pixel has no cost)
+      a0 = make_float4(__fdiv_rn(cen_e<kCenLutP3, true>(cb.x, mcx, s_lut, k0), i0.x), __fdiv_rn(cen_e<kCenLutP3, true>(cb.y, mcy, s_lut, k0), i0.y),
+                       __fdiv_rn(cen_e<kCenLutP3, true>(cb.z, mcz, s_lut, k0), i0.z), __fdiv_rn(cen_e<kCenLutP3, true>(cb.w, mcw, s_lut, k0), i0.w));
+      p3_quad_exact(v1, m1, i1, -k1, a1);
+      p3_quad_exact(v2, m2, i2, -k2, a2);
+      p3_quad_exact(v3, m3, i3, -k2, a3);
+    } else {
+      a0 = make_float4(cen_e<kCenLutP3>(cb.x, mcx, s_lut, k0) * i0.x, cen_e<kCenLutP3>(cb.y, mcy, s_lut, k0) * i0.y,
+                       cen_e<kCenLutP3>(cb.z, mcz, s_lut, k0) * i0.z, cen_e<kCenLutP3>(cb.w, mcw, s_lut, k0) * i0.w);
+      p3_quad(v1, mp1, ip1, nk1, a1);
+      p3_quad(v2, mp2, ip2, nk2, a2);
+      p3_quad(v3, mp3, ip3, nk2, a3);
+    }
     store_quads<kVec>(arow + (size_t)d * plane, chan, nlive, a0, a1, a2, a3);
   }
 }
@@ -877,7 +897,7 @@ __device__ __forceinline__ void phase3_quads(const float* s_par, const uint8_t* 
 // AML denominator of one (pixel, matcher) over the launch's disparities: exponentials evaluated on the fly
 // and added in the reference's order -- sequential fp32 over d (featextract.cpp:444-447; a tree sum is
 // measurably outside the 2e-6 bound).  warp = matcher, lane = pixel, mm = the minimum the exponent refers to.
-template <class L>
+template <class L, bool kExact = false>
 __device__ __forceinline__ float den_chain(const FusedArgs& a, int warp, int lane, float mm, const float* s_par,
                                            const uint8_t* s_cen, const float* s_lut) {
   constexpr int PS = L::PS;
@@ -890,11 +910,11 @@ __device__ __forceinline__ float den_chain(const FusedArgs& a, int warp, int lan
     for (int d0 = 0; d0 < Dfull; d0 += 8, c += 8 * kTile) {
       float ev[8];
 #pragma unroll
-      for (int j = 0; j < 8; ++j) ev[j] = cen_e<kCenLutDen>(c[j * kTile], mc, s_lut, a.k_cen);
+      for (int j = 0; j < 8; ++j) ev[j] = cen_e<kCenLutDen, kExact>(c[j * kTile], mc, s_lut, a.k_cen);
 #pragma unroll
       for (int j = 0; j < 8; ++j) den = __fadd_rn(den, ev[j]);
     }
-    for (int d = Dfull; d < D; ++d, c += kTile) den = __fadd_rn(den, cen_e<kCenLutDen>(c[0], mc, s_lut, a.k_cen));
+    for (int d = Dfull; d < D; ++d, c += kTile) den = __fadd_rn(den, cen_e<kCenLutDen, kExact>(c[0], mc, s_lut, a.k_cen));
   } else {
     const float kq = (warp == 1) ? a.k_ncc : a.k_sad;
     const f32x2 mm2 = pk2(mm, mm), nkq = pk2(-kq, -kq);
@@ -902,11 +922,14 @@ __device__ __forceinline__ float den_chain(const FusedArgs& a, int warp, int lan
     for (int d0 = 0; d0 < Dfull; d0 += 8, e += 8 * kTile) {
       float ev[8];
 #pragma unroll
-      for (int j = 0; j < 8; j += 2) aml_e2(pk2(e[j * kTile], e[(j + 1) * kTile]), mm2, nkq, ev[j], ev[j + 1]);
+      for (int j = 0; j < 8; j += 2) {
+        if (kExact) { ev[j] = aml_e_exact(e[j * kTile], mm, -kq); ev[j + 1] = aml_e_exact(e[(j + 1) * kTile], mm, -kq); }
+        else aml_e2(pk2(e[j * kTile], e[(j + 1) * kTile]), mm2, nkq, ev[j], ev[j + 1]);
+      }
 #pragma unroll
       for (int j = 0; j < 8; ++j) den = __fadd_rn(den, ev[j]);
     }
-    for (int d = Dfull; d < D; ++d, e += kTile) den = __fadd_rn(den, aml_e(e[0], mm, kq));
+    for (int d = Dfull; d < D; ++d, e += kTile) den = __fadd_rn(den, aml_t<kExact>(e[0], mm, kq));
   }
   return den;
 }
@@ -1034,7 +1057,7 @@ __device__ __forceinline__ void wta_scan(const FusedArgs& a, const TileId& t, in
 // part of the channel 0-3 stores to the chain warps statically or through a work counter (no
 // gain: the halves are already balanced), a warp-specialised persistent producer/consumer
 // kernel (15 % slower).
-template <class L, bool kXchg, class T = float>
+template <class L, bool kXchg, class T = float, bool kExact = false>
 __device__ __forceinline__ void tile_back_half(const FusedArgs& a, const TileId& t, long long tile, int tid,
                                                const float* s_par, const uint8_t* s_cen, float* s_red, float* s_min,
                                                float* s_inv, const float* s_lut, const float* s_lutn) {
@@ -1064,7 +1087,7 @@ __device__ __forceinline__ void tile_back_half(const FusedArgs& a, const TileId&
       bar_sync_128();
     }
     const float mm = s_min[warp * kTile + lane];
-    float den = den_chain<L>(a, warp, lane, mm, s_par, s_cen, s_lut);
+    float den = den_chain<L, kExact>(a, warp, lane, mm, s_par, s_cen, s_lut);
     if (kXchg) {
       s_red[warp * kTile + lane] = den;        // (the per-group minima are dead since the barrier above)
       bar_sync_128();
@@ -1073,7 +1096,7 @@ __device__ __forceinline__ void tile_back_half(const FusedArgs& a, const TileId&
       bar_sync_128();
       den = s_red[4 * kTile + warp * kTile + lane];
     }
-    s_inv[warp * kTile + lane] = (mm == kFill) ? 0.f : 1.0f / den;
+    s_inv[warp * kTile + lane] = kExact ? ((mm == kFill) ? INFINITY : den) : ((mm == kFill) ? 0.f : 1.0f / den);
   }
   else {
     // channels 0-3: thread = (pixel quad, d), 16 disparities per sweep of the four warps
@@ -1083,8 +1106,8 @@ __device__ __forceinline__ void tile_back_half(const FusedArgs& a, const TileId&
   }
   __syncthreads();
   const int dl = tid >> 3;
-  if (vec) phase3_quads<true>(s_par, s_cen, s_lut, s_min, s_inv, PS, q4, dl, D, orow + 4 * chan, plane, chan, nlive, a.k_cen, a.k_ncc, a.k_sad);
-  else phase3_quads<false>(s_par, s_cen, s_lut, s_min, s_inv, PS, q4, dl, D, orow + 4 * chan, plane, chan, nlive, a.k_cen, a.k_ncc, a.k_sad);
+  if (vec) phase3_quads<true, T, kExact>(s_par, s_cen, s_lut, s_min, s_inv, PS, q4, dl, D, orow + 4 * chan, plane, chan, nlive, a.k_cen, a.k_ncc, a.k_sad);
+  else phase3_quads<false, T, kExact>(s_par, s_cen, s_lut, s_min, s_inv, PS, q4, dl, D, orow + 4 * chan, plane, chan, nlive, a.k_cen, a.k_ncc, a.k_sad);
 }
 
 // Back half of a tile for DISPARITY-SLAB SHARDING (phase A of slab.cu): the AML
@@ -1219,6 +1242,7 @@ __device__ __forceinline__ void fused_tile(const FusedArgs& a, const CUtensorMap
   finish_phase1<L>(s_par, s_red, o, px, grp, d_lo, d_end);
   __syncthreads();
   if (kMode == kModeSlabA) tile_slab_a<L>(a, t, tid, s_par, s_cen, s_red, s_lutn);
+  else if (kMode == kModeExact) tile_back_half<L, false, float, true>(a, t, tile, tid, s_par, s_cen, s_red, s_min, s_inv, s_lut, s_lutn);
   else if (kMode == kModeBf16) tile_back_half<L, false, __nv_bfloat16>(a, t, tile, tid, s_par, s_cen, s_red, s_min, s_inv, s_lut, s_lutn);
   else tile_back_half<L, kMode == kModeXchg>(a, t, tile, tid, s_par, s_cen, s_red, s_min, s_inv, s_lut, s_lutn);
 }
@@ -1551,6 +1575,8 @@ int launch_ms_fused(const uint8_t* d_left, const uint8_t* d_right, int N, int H,
                     float* d_out, float* d_mins, char* workspace, cudaStream_t s, int out_D, int out_d0,
                     int accumulate, const msn_slab_exchange* xchg, const FusedWta* wta, bool out_bf16) {
   MSN_REQUIRE(!out_bf16 || (!xchg && !d_mins), "ms_features: the bf16 volume is written by the one-pass kernel only");
+  const bool exact = g_aml_exact != 0 && !d_mins;   // (the phase-A form computes no AML: phases B/C follow the mode)
+  MSN_REQUIRE(!exact || (!xchg && !out_bf16), "ms_features: the exact AML mode is not served by the slab exchange / bf16 forms");
   if (N == 0) return 0;
   FusedGeom g = make_geom(N, H, W, p);
   FusedWs ws;
@@ -1644,7 +1670,8 @@ int launch_ms_fused(const uint8_t* d_left, const uint8_t* d_right, int N, int H,
   }
 #define MSN_FUSED_LAUNCH(DMAX, TMA)                                                \
   {                                                                                \
-    if (out_bf16) { if (launch_inst<DMAX, TMA, kModeBf16>(a, sad_map, tiles, s)) return 1; } \
+    if (exact) { if (launch_inst<DMAX, TMA, kModeExact>(a, sad_map, tiles, s)) return 1; } \
+    else if (out_bf16) { if (launch_inst<DMAX, TMA, kModeBf16>(a, sad_map, tiles, s)) return 1; } \
     else if (xchg) { if (launch_inst<DMAX, TMA, kModeXchg>(a, sad_map, tiles, s)) return 1; } \
     else if (d_mins) { if (launch_inst<DMAX, TMA, kModeSlabA>(a, sad_map, tiles, s)) return 1; } \
     else { if (launch_inst<DMAX, TMA, kModeFull>(a, sad_map, tiles, s)) return 1; }    \

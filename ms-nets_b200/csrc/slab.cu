@@ -134,12 +134,12 @@ slab_phase_c_kernel(float* __restrict__ out, const float* __restrict__ gmin, con
   if (p >= n) return;
   const float m = gmin[(size_t)i * n + p];
   const float k = sc.k[i & 3];
-  const float inv = (m == kFill) ? 0.f : 1.0f / gden[(size_t)i * n + p];
+  const float inv = aml_row_scale(gden[(size_t)i * n + p], m != kFill, k);
   float* c = out + (size_t)aml_channel(i) * Dn * n + p;
 #pragma unroll 4
   for (int dd = 0; dd < Dn; ++dd) {
     const float v = c[(size_t)dd * n];
-    st_stream(c + (size_t)dd * n, aml_e(v, m, k) * inv);
+    st_stream(c + (size_t)dd * n, aml_apply(aml_e(v, m, k), inv, k));
   }
 }
 

@@ -249,3 +249,17 @@ def test_config_m_sadsob_deep_rows_full_width(oracle):
     ch2 = out[0, 2, :, 300 - border:320 - border].cpu().numpy()                 # [d, y, x] cropped
     want2 = (np.clip(want[:, :, border:W - border], 0., 2 ** 13) / float(2 ** 13)).astype(np.float32)
     assert np.array_equal(ch2, want2)
+
+
+def test_config_a_exact_aml_mode_all_channels_bit_exact(oracle):
+    """Config A (256x512, D=192) with msn_set_aml_exact(1): all eight channels array_equal to the unmodified
+    reference C++ -- no tolerance class at all."""
+    import msnets_b200 as ms
+    L, R = bordered_pair(256, 512, 1234, border=10)
+    want, who = _reference_features(oracle, L, R, 192, 10)
+    prev = ms.set_aml_exact(True)
+    try:
+        got = ms.cbmv.ms_features(L, R, 192, board_h=10, board_w_left=10, board_w_right=10)
+    finally:
+        ms.set_aml_exact(prev)
+    assert np.array_equal(got, want)

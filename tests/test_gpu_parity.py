@@ -370,7 +370,7 @@ def test_soft_argmin_autograd(ms):
     dvec = torch.arange(48, device="cuda", dtype=torch.float32).view(1, 48, 1, 1)
     ref = torch.sum(F.softmax(x, 1) * dvec, 1)
     (ref * w).sum().backward()
-    assert float((disp - ref).abs().max()) <= SOFTARGMIN_ATOL
+    assert float((disp - ref).detach().abs().max()) <= SOFTARGMIN_ATOL
     assert float((got - x.grad).abs().max()) <= 1e-5 * max(1.0, float(x.grad.abs().max()))
     # the regression half alone, as the patched model uses it
     p = F.softmax(x.detach(), 1).requires_grad_(True)
@@ -393,3 +393,43 @@ def test_bf16_volume_is_the_rounded_fp32_volume(ms, H, W, D):
     b16 = ms.cbmv.MSFeatureExtractor(1, L.shape[0], L.shape[1], out_dtype=torch.bfloat16, **kw)(l, r)
     assert b16.dtype == torch.bfloat16 and b16.shape == f32.shape
     assert torch.equal(b16, f32.to(torch.bfloat16))
+
+
+@pytest.fixture
+def exact_aml(ms):
+    prev = ms.set_aml_exact(True)
+    yield ms
+    ms.set_aml_exact(prev)
+
+
+def test_exact_aml_mode_is_bit_exact_everywhere(exact_aml, oracle, golden_dir):
+    """msn_set_aml_exact(1): the reference's fp32 operations with glibc's expf replayed (feature_math.cuh) --
+    extract_likelihood, extract_features_left / _lr and the fused volume equal the reference BIT FOR BIT, AML
+    channels included: against the golden vectors the unmodified reference produced and against the oracle."""
+    import torch
+    ms = exact_aml
+    assert ms.aml_exact()
+    for case in ("small_a", "small_b", "small_c"):
+        g = np.load(os.path.join(golden_dir, case + ".npz"))
+        H, W, D, seed, shift, border = [int(v) for v in g["meta"]]
+        costs = ms.cbmv.get_costs(g["L"], g["R"], D, 11, 3, 5, 5, border, border, border)
+        aml = ms.libfeatextract.extract_likelihood(costs[3].reshape(-1, D), 20000.0)
+        assert np.array_equal(aml, g["aml_sad"])                                  # featextract.cpp:415-462
+        f8 = ms.cbmv.extract_features_left(*costs)
+        assert np.array_equal(f8, g["features_left"])                             # all 8 channels
+        from tests._synth import digest
+        assert digest(ms.cbmv.extract_features_lr(*costs)) == str(g["sha_features_lr"])   # all 16 channels
+        fused = ms.cbmv.ms_features(g["L"], g["R"], D, board_h=border, board_w_left=border, board_w_right=border)
+        assert np.array_equal(fused, g["features_left"])                          # the one-pass kernel
+    # larger, D = 192, degenerate rows included (zero border, flat patch): the fused kernel vs the oracle
+    L, R = bordered_pair(70, 260, 17, border=10, patches=True)
+    got = ms.cbmv.ms_features(L, R, 192, board_h=10, board_w_left=10, board_w_right=10)
+    assert np.array_equal(got, oracle.ms_features(L, R, 192))
+    # D > 448: slabs of 192 through phase A, then phases B / C (generic AML kernels in exact mode)
+    L, R = bordered_pair(30, 60, 18, border=10, patches=True)
+    got = ms.cbmv.ms_features(L, R, 500, board_h=10, board_w_left=10, board_w_right=10)
+    assert np.array_equal(got, oracle.ms_features(L, R, 500))
+    with pytest.raises(ms.MsnetsError):
+        ms.cbmv.MSFeatureExtractor(1, L.shape[0], L.shape[1], maxdisp=64, out_dtype=torch.bfloat16, board_h=10,
+                                   board_w_left=10, board_w_right=10)(torch.from_numpy(L[None]).cuda(),
+                                                                      torch.from_numpy(R[None]).cuda())
