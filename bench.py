@@ -331,28 +331,32 @@ def slab_config_m(dev, rank, world, steps=3, warmup=2):
     L, R = bordered_pair(H, W, 99, border=B, shift=13)
     l, r = torch.from_numpy(L[None]).to(dev), torch.from_numpy(R[None]).to(dev)
     mode = "exchange"
+    bands, grp = 1, None
     try:
-        ex = sharding.ExchangeSlabMSFeatures(1, H + 2 * B, W + 2 * B, maxdisp=D, board_h=B, board_w_left=B,
-                                             board_w_right=B)
+        bands = sharding.ExchangeSlabMSFeatures.default_row_bands(D, world)
+        ex = sharding.ExchangeSlabMSFeatures(1, H + 2 * B, W + 2 * B, maxdisp=D, row_bands=bands, board_h=B,
+                                             board_w_left=B, board_w_right=B)
+        grp = ex.slab_group
     except ValueError:
-        mode = "phases"
+        mode, bands = "phases", 1
         ex = sharding.SlabShardedMSFeatures(1, H + 2 * B, W + 2 * B, maxdisp=D, board_h=B, board_w_left=B,
                                             board_w_right=B)
     out = torch.empty(ex.shape, dtype=torch.float32, device=dev)
     gen = torch.Generator(device=dev)
     gen.manual_seed(77 + rank)
-    logits = torch.randn((1, ex.d_count, H, W), generator=gen, device=dev, dtype=torch.float32)
+    rows = ex.shape[3]
+    logits = torch.randn((1, ex.d_count, rows, W), generator=gen, device=dev, dtype=torch.float32)
 
     parts = ex.empty_wta_parts() if mode == "exchange" else None
 
     def step():
         if mode == "exchange":     # WTA / second-min triples are a by-product of the slab kernel: merge them
             ex(l, r, out=out, wta=parts)
-            am, m1, m2 = sharding.slab_wta_merge(*parts)
+            am, m1, m2 = sharding.slab_wta_merge(*parts, group=grp)
         else:
             ex(l, r, out=out)
             am, m1 = sharding.slab_wta(out[0, 0], ex.d_begin, layout="dhw")
-        return am, sharding.slab_soft_argmin(logits, ex.d_begin)
+        return am, sharding.slab_soft_argmin(logits, ex.d_begin, group=grp)
 
     for _ in range(warmup):
         step()
@@ -368,28 +372,31 @@ def slab_config_m(dev, rank, world, steps=3, warmup=2):
     t = torch.tensor([e0.elapsed_time(e1) / steps], device=dev, dtype=torch.float64)
     dist.all_reduce(t, op=dist.ReduceOp.MAX)
     ms = float(t.item())
-    col = out[0, 4:8].sum(1)                      # AML columns over ALL ranks' disparities sum to 1
-    dist.all_reduce(col, op=dist.ReduceOp.SUM)
+    col = out[0, 4:8].sum(1)                      # AML columns over ALL slabs' disparities sum to 1
+    if getattr(ex, "slabs", world) > 1:
+        dist.all_reduce(col, op=dist.ReduceOp.SUM, group=grp)
     err = float((col[col > 0.5] - 1).abs().max())
     peak, _ = peaks()
     vox = D * H * W
-    tiles = H * ((W + 31) // 32)
+    tiles = rows * ((W + 31) // 32)
     subs = getattr(ex, "subs", 1) or 1
+    slabs = getattr(ex, "slabs", world)
     res = {
-        "workload": "configs[4]: Middlebury-shaped 1984x2880 D=640, one frame, disparity-slab sharded x%d "
-                    "(MS volume slab [1,8,%d,1984,2880] per GPU + WTA + soft-argmin merges)" % (world, ex.d_count),
-        "mode": mode, "ms_per_frame": round(ms, 3), "frames_per_s": round(1e3 / ms, 2), "steps": steps,
+        "workload": "configs[4]: Middlebury-shaped 1984x2880 D=640, one frame over %d GPUs: %d disparity slab(s) x %d row "
+                    "band(s) (MS volume [1,8,%d,%d,2880] per GPU + WTA + soft-argmin merges)"
+                    % (world, slabs, bands, ex.d_count, rows),
+        "mode": mode, "slabs": slabs, "row_bands": bands, "ms_per_frame": round(ms, 3), "frames_per_s": round(1e3 / ms, 2), "steps": steps,
         "algorithmic_GB_per_gpu": round((32.0 + 4.0) * vox / world / 1e9, 2),
         "GBps_per_gpu": round((32.0 + 4.0) * vox / world / ms / 1e6, 1),
         "frac_of_hbm_peak_per_gpu": round((32.0 + 4.0) * vox / world / ms / 1e6 / peak, 4),
         "collectives_per_frame": {
-            "aml_min_and_den": ("in-kernel: %d sub-slab(s) per rank push 2 x 640 B per tile to %d peer(s) over NVLink "
-                                "= %.1f MB out per rank" % (subs, world - 1, tiles * subs * 2 * 640 * (world - 1) / 1e6))
+            "aml_min_and_den": ("in-kernel: %d sub-slab(s) per rank push 2 x 640 B per tile to the %d other rank(s) of the row band "
+                                "over NVLink = %.1f MB out per rank" % (subs, slabs - 1, tiles * subs * 2 * 640 * (slabs - 1) / 1e6))
             if mode == "exchange" else "2 x NCCL all_reduce over [4,1984,2880] f32 = 91.4 MB each",
-            "wta": ("NCCL all_gather of the kernel's (argmin, min1, min2) by-product, 4 channels: 3 x [%d,1,4,1984,2880] "
-                    "x 4 B = %.1f MB per rank, merged by msn_wta_merge_dev" % (subs, 3 * subs * 4 * H * W * 4 / 1e6))
+            "wta": ("NCCL all_gather of the kernel's (argmin, min1, min2) by-product, 4 channels: 3 x [%d,1,4,%d,2880] "
+                    "x 4 B = %.1f MB per rank, merged by msn_wta_merge_dev" % (subs, rows, 3 * subs * 4 * rows * W * 4 / 1e6))
             if mode == "exchange" else "NCCL all_reduce(min) over [1984,2880] int64 keys = 45.7 MB",
-            "soft_argmin": "NCCL all_gather of [3,1984,2880] f32 partials = 68.6 MB per rank"},
+            "soft_argmin": "NCCL all_gather of [3,%d,2880] f32 partials = %.1f MB per rank" % (rows, 3 * rows * W * 4 / 1e6)},
         "aml_column_sum_max_err": err,
     }
     del out, logits

@@ -95,6 +95,11 @@ typedef struct msn_ms_params {
   int lr;             /* 0: 8 channels (extract_features_left); 1: 16 (.._lr)   */
   int d_begin, d_count; /* disparity slab [d_begin, d_begin+d_count) to produce; *
                        * d_count = 0 means the whole range (single-GPU case)    */
+  int row_begin, row_count; /* row band [row_begin, row_begin+row_count) of the CROPPED image to produce  *
+                       * (output [N][C][Dp][row_count][w]); row_count = 0 means all rows.  A frame sharded by  *
+                       * rows needs no exchange: every matcher is a window, and the SAD-of-Sobel table of a   *
+                       * row -- which depends on every row above it -- is still built from row 0.  Served by  *
+                       * the fused paths (msn_ms_features_dev with the default windows, msn_ms_slab_fused_dev). */
 } msn_ms_params;
 MSN_API void msn_ms_params_default(msn_ms_params* p);
 

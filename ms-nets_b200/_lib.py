@@ -18,7 +18,8 @@ class MsParams(ctypes.Structure):
     _fields_ = [("ndisp", c_int), ("censw", c_int), ("nccw", c_int), ("sadw", c_int),
                 ("sobelw", c_int), ("board_h", c_int), ("board_w_left", c_int),
                 ("board_w_right", c_int), ("cens_sigma", c_float), ("ncc_sigma", c_float),
-                ("sad_sigma", c_float), ("lr", c_int), ("d_begin", c_int), ("d_count", c_int)]
+                ("sad_sigma", c_float), ("lr", c_int), ("d_begin", c_int), ("d_count", c_int),
+                ("row_begin", c_int), ("row_count", c_int)]
 
 
 class SlabExchange(ctypes.Structure):

@@ -82,18 +82,20 @@ def extract_features_lr(census, ncc, sobel, sad, cens_sigma=128.0, ncc_sigma=0.0
 
 def make_params(maxdisp=192, censw=11, nccw=3, sadw=5, sobelw=5, board_h=10, board_w_left=10,
                 board_w_right=0, cens_sigma=128.0, ncc_sigma=0.02, sad_sigma=20000.0, left_only=True,
-                d_begin=0, d_count=0):
+                d_begin=0, d_count=0, row_begin=0, row_count=0):
     return _lib.default_params(ndisp=int(maxdisp), censw=int(censw), nccw=int(nccw), sadw=int(sadw),
                                sobelw=int(sobelw), board_h=int(board_h), board_w_left=int(board_w_left),
                                board_w_right=int(board_w_right), cens_sigma=float(cens_sigma),
                                ncc_sigma=float(ncc_sigma), sad_sigma=float(sad_sigma),
-                               lr=0 if left_only else 1, d_begin=int(d_begin), d_count=int(d_count))
+                               lr=0 if left_only else 1, d_begin=int(d_begin), d_count=int(d_count),
+                               row_begin=int(row_begin), row_count=int(row_count))
 
 
 def output_shape(N, H, W, p):
     C = 16 if p.lr else 8
     Dn = p.d_count if p.d_count > 0 else p.ndisp
-    return (N, C, Dn, H - 2 * p.board_h, W - p.board_w_left - p.board_w_right)
+    h = p.row_count if p.row_count > 0 else H - 2 * p.board_h
+    return (N, C, Dn, h, W - p.board_w_left - p.board_w_right)
 
 
 def ms_features(iml, imr, maxdisp=192, left_only=True, **kw):

@@ -205,6 +205,7 @@ void msn_ms_params_default(msn_ms_params* p) {
   p->cens_sigma = 128.0f; p->ncc_sigma = 0.02f; p->sad_sigma = 20000.0f;  // :441-444
   p->lr = 0;
   p->d_begin = 0; p->d_count = 0;
+  p->row_begin = 0; p->row_count = 0;
 }
 
 // ------------------------------------------------------- device matchers --
@@ -470,7 +471,8 @@ int msn_features_from_costs_host(const float* census_hwd, const float* ncc_hwd, 
 namespace {
 
 struct Geometry {
-  int H, W, h, w, D, d_begin, Dn, C;
+  int H, W, h, w, D, d_begin, Dn, C;   // h: output rows (the row band's when one is requested)
+  bool band;
 };
 
 int resolve(const msn_ms_params* p, int N, int H, int W, Geometry* g, const char* who) {
@@ -487,6 +489,12 @@ int resolve(const msn_ms_params* p, int N, int H, int W, Geometry* g, const char
   g->w = W - p->board_w_left - p->board_w_right;
   MSN_REQUIRE(g->h >= 1 && g->w >= 1, "%s: borders (%d,%d,%d) leave nothing of a %dx%d image", who, p->board_h,
               p->board_w_left, p->board_w_right, H, W);
+  g->band = p->row_count > 0;
+  if (g->band) {
+    MSN_REQUIRE(p->row_begin >= 0 && p->row_begin + p->row_count <= g->h, "%s: row band [%d,%d) outside [0,%d)", who,
+                p->row_begin, p->row_begin + p->row_count, g->h);
+    g->h = p->row_count;
+  }
   g->D = p->ndisp;
   g->d_begin = p->d_count > 0 ? p->d_begin : 0;
   g->Dn = p->d_count > 0 ? p->d_count : p->ndisp;
@@ -631,6 +639,7 @@ int msn_ms_features_wta_dev(const uint8_t* d_left, const uint8_t* d_right, int N
               "ms_features: workspace too small (%zu < %zu)", workspace_bytes,
               msn_ms_features_workspace_bytes(N, H, W, p));
   MSN_REQUIRE(g.d_begin == 0 && g.Dn == g.D, "ms_features: slabs go through msn_ms_slab_phase_*_dev");
+  MSN_REQUIRE(!g.band || (use_fused(p, g, W) && !p->lr), "ms_features: a row band needs the fused path (default windows, left view, D <= 448)");
   cudaStream_t s = as_stream(stream);
   char* base = (char*)(((uintptr_t)d_workspace + 255) & ~(uintptr_t)255);
   const size_t n = (size_t)g.h * g.w;
@@ -752,6 +761,7 @@ int msn_ms_slab_phase_a_dev(const uint8_t* d_left, const uint8_t* d_right, int N
                             void* d_workspace, size_t workspace_bytes, void* stream) {
   Geometry g;
   TRY(resolve(p, N, H, W, &g, "ms_slab_phase_a"));
+  MSN_REQUIRE(!g.band, "ms_slab_phase_a: row bands are served by msn_ms_slab_fused_dev");
   MSN_REQUIRE(d_left && d_right && d_out && d_min && d_workspace, "ms_slab_phase_a: null pointer argument");
   MSN_REQUIRE(workspace_bytes >= msn_ms_slab_workspace_bytes(N, H, W, p), "ms_slab_phase_a: workspace too small");
   cudaStream_t s = as_stream(stream);

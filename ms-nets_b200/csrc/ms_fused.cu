@@ -62,7 +62,8 @@ struct __align__(16) RStat {
 };
 
 struct FusedGeom {
-  int N, H, W, h, w, bh, bwl;
+  int N, H, W, h, w, bh, bwl;   // h: output rows of THIS launch (a row band when y0 / row_count are set)
+  int y0;   // first cropped-image row of the band (0 unless the caller shards a frame by rows)
   int D;    // disparities handled by this launch: [d0, d0 + D)
   int d0;   // first disparity (> 0 only for a disparity slab)
   int d_inner;  // SAD-of-Sobel scratch layout: 0 [N][Dl][H][Ws], 1 [N][H][Dl][Ws] (sub-slab launches, see sadsob.cu)
@@ -79,7 +80,8 @@ FusedGeom make_geom(int N, int H, int W, const msn_ms_params* p) {
   g.D = p->d_count > 0 ? p->d_count : p->ndisp;
   g.Dl = g.D; g.d_inner = 0;
   g.bh = p->board_h; g.bwl = p->board_w_left;
-  g.h = H - 2 * p->board_h;
+  g.h = p->row_count > 0 ? p->row_count : H - 2 * p->board_h;
+  g.y0 = p->row_count > 0 ? p->row_begin : 0;
   g.w = W - p->board_w_left - p->board_w_right;
   g.padL = (g.d0 + g.D + 1 + kSlack + 8 + 7) & ~7;  // d0+D-1 columns of disparity + dummy-step slack + halo/alignment
   g.Hp = H + 2 * kPadT;
@@ -390,7 +392,8 @@ __device__ __forceinline__ f32x2 abs2(f32x2 v) {
 }
 
 struct TileId {
-  int n, y, x0;
+  int n, y, x0;   // y: row of the cropped image
+  int yl;     // row inside this launch's band (output indexing)
   int d0;     // first disparity of this CTA (the launch's, plus its sub-slab offset)
   int sub0;   // offset of this CTA's sub-slab inside the launch's slab (0 unless the launch is cut, kModeXchg)
   int v;      // kModeXchg: this CTA's virtual rank (row in the exchange tables)
@@ -402,7 +405,8 @@ __device__ __forceinline__ TileId decode_tile(int tile, const FusedArgs& a, int 
   t.v = a.xchg.v + sub;
   const int xt = tile % a.tiles_x;
   tile /= a.tiles_x;
-  t.y = tile % a.g.h;
+  t.yl = tile % a.g.h;
+  t.y = t.yl + a.g.y0;
   t.n = tile / a.g.h;
   t.x0 = xt * kTile;
   return t;
@@ -1035,7 +1039,7 @@ __device__ __forceinline__ void wta_scan(const FusedArgs& a, const TileId& t, in
   const int x = t.x0 + lane;
   if (x < a.g.w) {
     const size_t plane = (size_t)a.g.h * a.g.w;
-    const size_t o = (((size_t)(t.sub0 / a.g.D) * a.g.N + t.n) * 4 + m) * plane + (size_t)t.y * a.g.w + x;
+    const size_t o = (((size_t)(t.sub0 / a.g.D) * a.g.N + t.n) * 4 + m) * plane + (size_t)t.yl * a.g.w + x;
     a.wta_idx[o] = t.d0 + idx;
     a.wta_min1[o] = m1;
     a.wta_min2[o] = m2;
@@ -1077,7 +1081,7 @@ __device__ __forceinline__ void tile_back_half(const FusedArgs& a, const TileId&
   const int q4 = (tid & 7) * 4;
   // 128-bit stores need 16-byte aligned rows
   const bool vec_ok = ((g.w & 3) == 0) && ((reinterpret_cast<uintptr_t>(a.out) & 15) == 0);
-  T* orow = reinterpret_cast<T*>(a.out) + (size_t)t.n * a.out_channels * chan + (size_t)(a.out_d0 + t.sub0) * plane + (size_t)t.y * g.w + (t.x0 + q4);
+  T* orow = reinterpret_cast<T*>(a.out) + (size_t)t.n * a.out_channels * chan + (size_t)(a.out_d0 + t.sub0) * plane + (size_t)t.yl * g.w + (t.x0 + q4);
   const int nlive = min(4, g.w - (t.x0 + q4));  // live pixels of this quad (<= 0: none)
   const bool vec = vec_ok && nlive == 4;
   if (warp < 4) {
@@ -1128,14 +1132,14 @@ __device__ __forceinline__ void tile_slab_a(const FusedArgs& a, const TileId& t,
     for (int gq = 0; gq < kGroups; ++gq) v = fminf(v, s_red[gq * 4 * kTile + tid]);
     const int m = tid / kTile, x = t.x0 + tid % kTile;
     if (x < g.w) {
-      float* mp = a.mins + (((size_t)t.n * a.mins_planes + m) * g.h + t.y) * g.w + x;
+      float* mp = a.mins + (((size_t)t.n * a.mins_planes + m) * g.h + t.yl) * g.w + x;
       *mp = a.mins_accumulate ? fminf(*mp, v) : v;
     }
   }
   const int q4 = (tid & 7) * 4;
   const int dl = tid >> 3;
   const bool vec_ok = ((g.w & 3) == 0) && ((reinterpret_cast<uintptr_t>(a.out) & 15) == 0);
-  float* orow = a.out + (size_t)t.n * a.out_channels * chan + (size_t)t.y * g.w + (t.x0 + q4);
+  float* orow = a.out + (size_t)t.n * a.out_channels * chan + (size_t)t.yl * g.w + (t.x0 + q4);
   const int nlive = min(4, g.w - (t.x0 + q4));
   const bool vec = vec_ok && nlive == 4;
 #pragma unroll 2
@@ -1359,7 +1363,7 @@ ms_slab_x2_kernel(const FusedArgs a, const __grid_constant__ CUtensorMap sad_map
   int nlive[2];
   for (int i = 0; i < 2; ++i) {
     orow[i] = a.out + (size_t)tt[i].n * a.out_channels * chan + (size_t)(a.out_d0 + tt[i].sub0) * plane +
-              (size_t)tt[i].y * g.w + (tt[i].x0 + q4);
+              (size_t)tt[i].yl * g.w + (tt[i].x0 + q4);
     nlive[i] = min(4, g.w - (tt[i].x0 + q4));
   }
   if (warp < 4) {
@@ -1605,7 +1609,9 @@ int launch_ms_fused(const uint8_t* d_left, const uint8_t* d_right, int N, int H,
   MSN_LAUNCH_OK();
   if (prof) MSN_CUDA_OK(cudaEventRecord(rec.ev[1], s));
   g.d_inner = subs > 1 ? 1 : 0;   // several sub-slabs in flight: keep a tile's scratch rows on one page
-  if (launch_sadsob5_padded(ws.sob[0], ws.sob[1], N, H, W, g.Dl, g.d0, ws.sadsob + g.sxo, ws.sad_ws, s, g.d_inner != 0)) return 1;
+  if (launch_sadsob5_padded(ws.sob[0], ws.sob[1], N, H, W, g.Dl, g.d0, ws.sadsob + g.sxo, ws.sad_ws, s, g.d_inner != 0,
+                            g.y0 + g.bh, g.y0 + g.bh + g.h))
+    return 1;
   if (prof) MSN_CUDA_OK(cudaEventRecord(rec.ev[2], s));
 
   g.D = g.Dl / subs;   // what one CTA handles (the scan above covered the launch's whole slab)

@@ -199,7 +199,7 @@ __device__ __forceinline__ void s5_vertical(const float* __restrict__ lp, const 
 template <int SP, bool kDInner>
 __global__ void __launch_bounds__(kS5Warps * 32, 4)
 sadsob_scan5_kernel(const float* __restrict__ L, const float* __restrict__ R, int H, int W, int Dn, int d_begin,
-                    int NB, size_t img_stride, const float* __restrict__ Vb, float* __restrict__ out,
+                    int NB, int b_min, size_t img_stride, const float* __restrict__ Vb, float* __restrict__ out,
                     size_t out_stride) {
   // kDInner: the output is [N][H][Dn][SP] -- the Dn rows of one image row lie side by side, so the fused
   // kernel's tile (one row y, all disparities) reads ONE contiguous Dn x 4 KB span instead of Dn rows megabytes
@@ -210,8 +210,9 @@ sadsob_scan5_kernel(const float* __restrict__ L, const float* __restrict__ R, in
   constexpr int RB = kSadTile - kS5W;  // 27 origin rows per band
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int job = blockIdx.x * kS5Warps + warp;
-  if (job >= Dn * NB) return;  // whole warp exits together
-  const int dd = kDInner ? job % Dn : job / NB, b = kDInner ? job / Dn : job % NB, n = blockIdx.z;
+  const int nbs = NB - b_min;     // bands b_min .. NB-1 are scanned (all of them unless the caller wants a row range)
+  if (job >= Dn * nbs) return;  // whole warp exits together
+  const int dd = kDInner ? job % Dn : job / nbs, b = b_min + (kDInner ? job / Dn : job % nbs), n = blockIdx.z;
   const int d = d_begin + dd;
   const int IW = W + 1;
   const int i0 = b * RB;
@@ -332,23 +333,32 @@ int launch_sadsob_n(const float* L, const float* R, int N, int H, int W, int Dn,
 int sadsob_fast_pitch(int W) { return W <= 1024 ? 1024 : W <= 2048 ? 2048 : W <= 4096 ? 4096 : 0; }
 
 int launch_sadsob5_padded(const float* L, const float* R, int N, int H, int W, int Dn, int d_begin, float* out,
-                          void* workspace, cudaStream_t s, bool d_inner) {
+                          void* workspace, cudaStream_t s, bool d_inner, int row_lo, int row_hi) {
   const int SP = sadsob_fast_pitch(W);
   MSN_REQUIRE(SP > 0, "sadsob: W=%d too wide for the padded window-5 scan", W);
   int RB, NB;
   sadsob_geom(H, kS5W, &RB, &NB);
   if (NB <= 0 || W - kS5W <= 0 || Dn <= 0) return 0;
+  // band b holds output rows [b*RB + 2, b*RB + 2 + RB): the bands a row range needs
+  int b_min = 0;
+  if (row_hi >= 0) {
+    b_min = (row_lo - 2 < 0 ? 0 : row_lo - 2) / RB;
+    const int b_max = (row_hi - 1 - 2 < 0 ? 0 : row_hi - 1 - 2) / RB;
+    if (b_min >= NB) return 0;
+    NB = (b_max + 1 < NB) ? b_max + 1 : NB;      // prefixes below the last needed band are never read
+  }
   float* Vb = static_cast<float*>(workspace);
   const size_t img_stride = (size_t)(H + kSadRowPad) * SP;
   const size_t out_stride = (size_t)Dn * H * SP;
   dim3 g1(div_up(W, 128), Dn, N);
   sadsob_vband_kernel<<<g1, 128, 0, s>>>(L, R, H, W, SP, d_begin, RB, NB, img_stride, Vb);
   MSN_LAUNCH_OK();
-  dim3 g5(div_up((long long)Dn * NB, kS5Warps), 1, N);
+  const int nbs = NB - b_min;
+  dim3 g5(div_up((long long)Dn * nbs, kS5Warps), 1, N);
 #define MSN_SCAN5(P)                                                                                             \
   {                                                                                                              \
-    if (d_inner) sadsob_scan5_kernel<P, true><<<g5, kS5Warps * 32, 0, s>>>(L, R, H, W, Dn, d_begin, NB, img_stride, Vb, out, out_stride); \
-    else sadsob_scan5_kernel<P, false><<<g5, kS5Warps * 32, 0, s>>>(L, R, H, W, Dn, d_begin, NB, img_stride, Vb, out, out_stride);        \
+    if (d_inner) sadsob_scan5_kernel<P, true><<<g5, kS5Warps * 32, 0, s>>>(L, R, H, W, Dn, d_begin, NB, b_min, img_stride, Vb, out, out_stride); \
+    else sadsob_scan5_kernel<P, false><<<g5, kS5Warps * 32, 0, s>>>(L, R, H, W, Dn, d_begin, NB, b_min, img_stride, Vb, out, out_stride);        \
   }
   if (SP == 1024) MSN_SCAN5(1024)
   else if (SP == 2048) MSN_SCAN5(2048)

@@ -206,7 +206,21 @@ class ExchangeSlabMSFeatures(object):
                 return subs
         return None
 
-    def __init__(self, N, H, W, maxdisp=192, rank=None, world=None, group=None, device=None, connect=True, **kw):
+    @staticmethod
+    def default_row_bands(maxdisp, world, min_slab=160):
+        """Row bands for `world` ranks on a `maxdisp`-disparity frame: a tile amortises its fixed costs over the
+        disparities it holds (0.94 ms per config-B pair equivalent at 192 per CTA, 1.32 at 80), so slabs stay at
+        least `min_slab` wide and the remaining ranks split the ROWS, which costs no exchange at all."""
+        slabs = max(1, min(world, int(maxdisp) // int(min_slab)))
+        while world % slabs:
+            slabs -= 1
+        return world // slabs
+
+    def __init__(self, N, H, W, maxdisp=192, rank=None, world=None, group=None, device=None, connect=True,
+                 row_bands=1, **kw):
+        """row_bands > 1: 2-D sharding of one frame -- rank = band * slabs + slab with slabs = world / row_bands:
+        the rank computes disparity slab `slab` of row band `band` of the cropped image; only the `slabs` ranks of a
+        band trade minima / denominators (row bands need no exchange).  Output [N, 8, D / slabs, h / row_bands, w]."""
         import torch
 
         from . import cbmv
@@ -217,21 +231,31 @@ class ExchangeSlabMSFeatures(object):
             rank = dist.get_rank(group) if dist.is_initialized() else 0
         if world is None:
             world = dist.get_world_size(group) if dist.is_initialized() else 1
-        if world > 8:
-            raise ValueError("the fused slab exchange serves at most 8 ranks (one NVSwitch node)")
+        row_bands = int(row_bands)
+        if row_bands < 1 or world % row_bands:
+            raise ValueError("row_bands must divide the number of ranks")
+        slabs = world // row_bands
+        if slabs > 8:
+            raise ValueError("the fused slab exchange serves at most 8 slabs per row band (one NVSwitch node)")
         self.torch, self.group, self.rank, self.world = torch, group, rank, world
+        self.row_bands, self.slabs, self.band, self.slab = row_bands, slabs, rank // slabs, rank % slabs
         self.device = torch.device("cuda", torch.cuda.current_device()) if device is None else torch.device(device)
         self.N, self.H, self.W = int(N), int(H), int(W)
-        self.d_begin, self.d_count = shard_range(maxdisp, rank, world)
+        self.d_begin, self.d_count = shard_range(maxdisp, self.slab, slabs)
         if self.d_count < 1:
-            raise ValueError("more ranks than disparities")
+            raise ValueError("more slabs than disparities")
         if not kw.get("left_only", True):
             raise NotImplementedError("slab sharding provides the 8-channel (left) volume")
-        self.subs = self.sub_slabs(maxdisp, world)
+        self.subs = self.sub_slabs(maxdisp, slabs)
         if self.subs is None:
-            raise ValueError("maxdisp=%d over %d ranks does not cut into equal sub-slabs: use SlabShardedMSFeatures"
-                             % (maxdisp, world))
-        self.params = cbmv.make_params(maxdisp, d_begin=self.d_begin, d_count=self.d_count, **kw)
+            raise ValueError("maxdisp=%d over %d slabs does not cut into equal sub-slabs: use SlabShardedMSFeatures"
+                             % (maxdisp, slabs))
+        h_full = self.H - 2 * int(kw.get("board_h", 10))
+        self.row_begin, self.row_count = shard_range(h_full, self.band, row_bands) if row_bands > 1 else (0, 0)
+        if row_bands > 1 and self.row_count < 1:
+            raise ValueError("more row bands than rows")
+        self.params = cbmv.make_params(maxdisp, d_begin=self.d_begin, d_count=self.d_count, row_begin=self.row_begin,
+                                       row_count=self.row_count, **kw)
         self.shape = cbmv.output_shape(self.N, self.H, self.W, self.params)
         self.h, self.w = self.shape[3], self.shape[4]
         L = _lib.lib()
@@ -240,15 +264,16 @@ class ExchangeSlabMSFeatures(object):
         self.epoch = 0
         with torch.cuda.device(self.device):
             nbytes = L.msn_ms_slab_fused_workspace_bytes(self.N, self.H, self.W, ctypes.byref(self.params))
-            self.table_bytes = L.msn_ms_slab_exchange_bytes(self.N, self.H, self.W, ctypes.byref(self.params), world,
+            self.table_bytes = L.msn_ms_slab_exchange_bytes(self.N, self.H, self.W, ctypes.byref(self.params), slabs,
                                                             self.subs)
             if nbytes == 0 or self.table_bytes == 0:
                 raise _lib.MsnetsError(L.msn_last_error().decode())
             self.workspace = torch.empty(nbytes + 256, dtype=torch.uint8, device=self.device)
             _lib.check(L.msn_peer_alloc(self.table_bytes, ctypes.byref(self._table)))
         self.xchg = _lib.SlabExchange()
-        self.xchg.world, self.xchg.rank, self.xchg.subs = world, rank, self.subs
-        self.xchg.tables[rank] = self._table.value
+        self.xchg.world, self.xchg.rank, self.xchg.subs = slabs, self.slab, self.subs   # the exchange group = one band
+        self.xchg.tables[self.slab] = self._table.value
+        self.slab_group = None     # torch.distributed group of this band's ranks (row_bands > 1, set by _connect_ipc)
         if connect:
             self._connect_ipc()
 
@@ -257,15 +282,18 @@ class ExchangeSlabMSFeatures(object):
         return self._table.value
 
     def wire(self, table_ptrs):
-        """table_ptrs[r] = device pointer (valid on this device) of rank r's exchange table."""
+        """table_ptrs[r] = device pointer (valid on this device) of rank r's exchange table, one per rank of the
+        whole launch; only the pointers of this rank's row band are used."""
         if len(table_ptrs) != self.world or table_ptrs[self.rank] != self._table.value:
             raise ValueError("wire: expected one pointer per rank, own table at index rank")
-        for r, ptr in enumerate(table_ptrs):
-            self.xchg.tables[r] = ptr
+        for s in range(self.slabs):
+            self.xchg.tables[s] = table_ptrs[self.band * self.slabs + s]
 
     def _connect_ipc(self):
         torch, L, dist = self.torch, _lib.lib(), _dist()
         if self.world == 1:
+            return
+        if self.slabs == 1 and self.row_bands == 1:
             return
         handle = (ctypes.c_ubyte * 64)()
         with torch.cuda.device(self.device):
@@ -274,14 +302,22 @@ class ExchangeSlabMSFeatures(object):
             allh = torch.empty((self.world, 64), dtype=torch.uint8, device=self.device)
             dist.all_gather_into_tensor(allh.view(-1), mine, group=self.group)
             allh = allh.cpu().numpy()
-            for r in range(self.world):
+            for s in range(self.slabs):
+                r = self.band * self.slabs + s
                 if r == self.rank:
                     continue
                 buf = (ctypes.c_ubyte * 64)(*[int(v) for v in allh[r]])
                 ptr = ctypes.c_void_p()
                 _lib.check(L.msn_peer_open(buf, ctypes.byref(ptr)))
                 self._opened.append(ptr)
-                self.xchg.tables[r] = ptr.value
+                self.xchg.tables[s] = ptr.value
+            if self.row_bands > 1:      # every rank creates every band's group (torch.distributed's rule)
+                for b in range(self.row_bands):
+                    grp = dist.new_group(list(range(b * self.slabs, (b + 1) * self.slabs)))
+                    if b == self.band:
+                        self.slab_group = grp
+            else:
+                self.slab_group = self.group
             dist.barrier(group=self.group)
 
     def empty_wta_parts(self):

@@ -238,3 +238,56 @@ def test_slab_sharding_two_gpus_nccl():
     for rank in range(2):
         exact, err, wta_ok, sa_err = ret[rank]
         assert exact and err <= AML_ATOL and wta_ok and sa_err <= 1e-3, (rank, ret[rank])
+
+
+def test_row_band_of_the_fused_volume(oracle):
+    """msn_ms_params.row_begin / row_count: a band of rows through the fused kernel equals those rows of the full
+    volume bit for bit -- the SAD-of-Sobel table of a row is built from row 0 even when only the band is scanned."""
+    import torch
+    import msnets_b200 as ms
+    L, R = bordered_pair(120, 84, 5, border=10, patches=True)
+    H, W = L.shape
+    l, r = torch.from_numpy(L[None]).cuda(), torch.from_numpy(R[None]).cuda()
+    kw = dict(maxdisp=48, board_h=10, board_w_left=10, board_w_right=10)
+    full = ms.cbmv.MSFeatureExtractor(1, H, W, **kw)(l, r)
+    for y0, yn in ((0, 17), (31, 60), (95, 25), (119, 1)):
+        band = ms.cbmv.MSFeatureExtractor(1, H, W, row_begin=y0, row_count=yn, **kw)(l, r)
+        assert tuple(band.shape) == (1, 8, 48, yn, 84)
+        assert torch.equal(band, full[:, :, :, y0:y0 + yn])
+    want = oracle.ms_features(L, R, 48)
+    assert np.array_equal(full[0, :4].cpu().numpy(), want[:4])
+
+
+@pytest.mark.parametrize("world,bands,H,W,D", [(4, 2, 44, 84, 64), (4, 4, 40, 52, 40), (2, 2, 36, 70, 40)])
+def test_fused_slab_exchange_with_row_bands(oracle, world, bands, H, W, D):
+    """2-D sharding of one frame: row bands x disparity slabs, virtual ranks on one GPU; only the ranks of a band
+    trade minima / denominators.  The assembled volume equals the reference."""
+    import torch
+    from msnets_b200 import sharding
+    L, R = bordered_pair(H, W, 41 + world, border=10, patches=True)
+    Hb, Wb = L.shape
+    l, r = torch.from_numpy(L[None]).cuda(), torch.from_numpy(R[None]).cuda()
+    ranks = [sharding.ExchangeSlabMSFeatures(1, Hb, Wb, maxdisp=D, rank=k, world=world, connect=False, row_bands=bands,
+                                             board_h=10, board_w_left=10, board_w_right=10) for k in range(world)]
+    ptrs = [x.table_ptr for x in ranks]
+    for x in ranks:
+        x.wire(ptrs)
+    streams = [torch.cuda.Stream() for _ in ranks]
+    torch.cuda.synchronize()
+    outs = []
+    for x, st in zip(ranks, streams):
+        with torch.cuda.stream(st):
+            outs.append(x(l, r))
+    torch.cuda.synchronize()
+    slabs = world // bands
+    rows = [torch.cat(outs[b * slabs:(b + 1) * slabs], dim=2) for b in range(bands)]     # slabs along D
+    got = torch.cat(rows, dim=3)[0].cpu().numpy()                                        # bands along rows
+    want = oracle.ms_features(L, R, D)
+    assert got.shape == want.shape
+    assert np.array_equal(got[:4], want[:4])
+    assert np.abs(got[4:] - want[4:]).max() <= AML_ATOL
+    for x in ranks:
+        x.close()
+    assert sharding.ExchangeSlabMSFeatures.default_row_bands(640, 8) == 2
+    assert sharding.ExchangeSlabMSFeatures.default_row_bands(640, 4) == 1
+    assert sharding.ExchangeSlabMSFeatures.default_row_bands(192, 8) == 8
