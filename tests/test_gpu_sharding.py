@@ -288,6 +288,7 @@ def test_fused_slab_exchange_with_row_bands(oracle, world, bands, H, W, D):
     assert np.abs(got[4:] - want[4:]).max() <= AML_ATOL
     for x in ranks:
         x.close()
-    assert sharding.ExchangeSlabMSFeatures.default_row_bands(640, 8) == 2
-    assert sharding.ExchangeSlabMSFeatures.default_row_bands(640, 4) == 1
+    assert sharding.ExchangeSlabMSFeatures.default_row_bands(640, 8) == 4
+    assert sharding.ExchangeSlabMSFeatures.default_row_bands(640, 4) == 2
+    assert sharding.ExchangeSlabMSFeatures.default_row_bands(640, 2) == 1
     assert sharding.ExchangeSlabMSFeatures.default_row_bands(192, 8) == 8
