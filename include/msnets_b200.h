@@ -141,7 +141,7 @@ MSN_API int msn_ms_features_bf16_dev(const uint8_t* d_left, const uint8_t* d_rig
 /* AML arithmetic mode, process-wide.  0 (default): SFU exponential and reciprocal multiply -- within 2e-6 of the
  * reference (1.2e-5 on rare degenerate rows).  1: the reference's own fp32 operations with glibc's expf replayed
  * bit for bit (featextract.cpp:435-453) -- extract_likelihood and feature channels 4-7 / 12-15 BIT-EXACT, about
- * 1.3x slower on the fused path.  Served by every entry point except msn_ms_slab_fused_dev and
+ * 6x slower on the fused path (0.78 -> 4.7 ms per config-B pair: the fp64 pipe).  Served by every entry point except msn_ms_slab_fused_dev and
  * msn_ms_features_bf16_dev. */
 MSN_API int msn_set_aml_exact(int on);
 MSN_API int msn_get_aml_exact(void);

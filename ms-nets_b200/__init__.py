@@ -27,7 +27,7 @@ def set_aml_exact(on=True):
     """Process-wide AML arithmetic mode (msn_set_aml_exact).  False (default): SFU exponential, within 2e-6 of the
     reference (1.2e-5 on rare degenerate rows).  True: the reference's own fp32 operations with glibc's expf
     replayed bit for bit -- extract_likelihood and feature channels 4-7 / 12-15 BIT-EXACT (featextract.cpp:435-453),
-    about 1.3x slower on the fused path.  Returns the previous setting."""
+    about 6x slower on the fused path (fp64 pipe).  Returns the previous setting."""
     prev = bool(_lib.lib().msn_get_aml_exact())
     _lib.check(_lib.lib().msn_set_aml_exact(1 if on else 0))
     return prev
