@@ -393,8 +393,9 @@ def slab_config_m(dev, rank, world, steps=3, warmup=2):
             "aml_min_and_den": ("in-kernel: %d sub-slab(s) per rank push 2 x 640 B per tile to the %d other rank(s) of the row band "
                                 "over NVLink = %.1f MB out per rank" % (subs, slabs - 1, tiles * subs * 2 * 640 * (slabs - 1) / 1e6))
             if mode == "exchange" else "2 x NCCL all_reduce over [4,1984,2880] f32 = 91.4 MB each",
-            "wta": ("NCCL all_gather of the kernel's (argmin, min1, min2) by-product, 4 channels: 3 x [%d,1,4,%d,2880] "
-                    "x 4 B = %.1f MB per rank, merged by msn_wta_merge_dev" % (subs, rows, 3 * subs * 4 * rows * W * 4 / 1e6))
+            "wta": ("NCCL all_gather of the kernel's (argmin, min1, min2) by-product, 4 channels: 3 x [1,4,%d,2880] "
+                    "x 4 B = %.1f MB per rank (sub-slabs merged locally first), merged by msn_wta_merge_dev"
+                    % (rows, 3 * 4 * rows * W * 4 / 1e6))
             if mode == "exchange" else "NCCL all_reduce(min) over [1984,2880] int64 keys = 45.7 MB",
             "soft_argmin": "NCCL all_gather of [3,%d,2880] f32 partials = %.1f MB per rank" % (rows, 3 * rows * W * 4 / 1e6)},
         "aml_column_sum_max_err": err,

@@ -402,15 +402,8 @@ def gather_wta_parts(idx_parts, min1_parts, min2_parts, group=None):
     return parts
 
 
-def slab_wta_merge(idx_parts, min1_parts, min2_parts, group=None):
-    """Merge of the per-slab WTA triples (argmin with absolute disparity, smallest, second smallest) that
-    the slab kernels emit as a by-product -- SURVEY.md 8e(3): all-gather the per-GPU pairs, reduce locally
-    (msn_wta_merge_dev).  *_parts: this rank's [subs, ...] CUDA tensors; returns (argmin int32, min1, min2)
-    over ALL disparities, on every rank.  Peak ratio: confidence.pkrn_confidence(min1, min2)."""
+def _wta_merge_local(parts):
     import torch
-    if not idx_parts.is_cuda:
-        raise _lib.MsnetsError("slab_wta_merge: expected CUDA tensors (no CPU fallback)")
-    parts = gather_wta_parts(idx_parts, min1_parts, min2_parts, group)
     P = parts[0].shape[0]
     shp = tuple(parts[0].shape[1:])
     n = 1
@@ -424,6 +417,23 @@ def slab_wta_merge(idx_parts, min1_parts, min2_parts, group=None):
                                                 idx.data_ptr(), m1.data_ptr(), m2.data_ptr(),
                                                 torch.cuda.current_stream().cuda_stream))
     return idx, m1, m2
+
+
+def slab_wta_merge(idx_parts, min1_parts, min2_parts, group=None):
+    """Merge of the per-slab WTA triples (argmin with absolute disparity, smallest, second smallest) that
+    the slab kernels emit as a by-product -- SURVEY.md 8e(3): all-gather the per-GPU pairs, reduce locally
+    (msn_wta_merge_dev).  *_parts: this rank's [subs, ...] CUDA tensors; returns (argmin int32, min1, min2)
+    over ALL disparities, on every rank.  This rank's sub-slabs are merged first, so one triple per rank
+    crosses NVLink.  Peak ratio: confidence.pkrn_confidence(min1, min2)."""
+    if not idx_parts.is_cuda:
+        raise _lib.MsnetsError("slab_wta_merge: expected CUDA tensors (no CPU fallback)")
+    parts = [t.contiguous() for t in (idx_parts, min1_parts, min2_parts)]
+    dist = _dist()
+    if dist.is_initialized() and dist.get_world_size(group) > 1:
+        if parts[0].shape[0] > 1:
+            parts = [t.unsqueeze(0) for t in _wta_merge_local(parts)]
+        parts = gather_wta_parts(parts[0], parts[1], parts[2], group)
+    return _wta_merge_local(parts)
 
 
 def slab_soft_argmin(logits_slab, d_begin, group=None):
