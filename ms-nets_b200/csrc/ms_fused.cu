@@ -376,6 +376,11 @@ __device__ __forceinline__ f32x2 mul2(f32x2 a, f32x2 b) {
   asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b));
   return r;
 }
+__device__ __forceinline__ f32x2 fma2(f32x2 a, f32x2 b, f32x2 c) {
+  f32x2 r;
+  asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(r) : "l"(a), "l"(b), "l"(c));
+  return r;
+}
 // AML exponentials of two costs at once: 2^(-(c-m)^2 k) for (c.lo, m.lo) and (c.hi, m.hi); the packed
 // subtract / square / scale round exactly like aml_e's scalar ones (each half is an IEEE fp32 operation)
 __device__ __forceinline__ void aml_e2(f32x2 c, f32x2 m, f32x2 negk, float& e_lo, float& e_hi) {
@@ -739,14 +744,26 @@ __device__ __forceinline__ void finish_phase1(float* s_par, float* s_red, const 
                                               int d_lo, int d_end) {
   float min_sob = kFill;
   float* sp = s_par + L::PS + d_lo * kTile + px;
-#pragma unroll 4
-  for (int d = d_lo; d < d_end; ++d, sp += kTile) {
-    float v = *sp;
-    if (d > o.dmax_sad) {
-      v = kFill;
-      *sp = v;
+  if (__all_sync(0xffffffffu, d_end - 1 <= o.dmax_sad)) {
+    // every disparity of the warp's group has its cost (most tiles): loads and three-input minima only --
+    // the guarded form below spends 7.5 mostly ALU-pipe instructions per voxel-row on predicates
+    int d = d_lo;
+    for (; d + 4 <= d_end; d += 4, sp += 4 * kTile) {
+      const float v0 = sp[0], v1 = sp[kTile], v2 = sp[2 * kTile], v3 = sp[3 * kTile];
+      min_sob = fminf(fminf(min_sob, v0), v1);
+      min_sob = fminf(fminf(min_sob, v2), v3);
     }
-    min_sob = fminf(min_sob, v);
+    for (; d < d_end; ++d, sp += kTile) min_sob = fminf(min_sob, *sp);
+  } else {
+#pragma unroll 4
+    for (int d = d_lo; d < d_end; ++d, sp += kTile) {
+      float v = *sp;
+      if (d > o.dmax_sad) {
+        v = kFill;
+        *sp = v;
+      }
+      min_sob = fminf(min_sob, v);
+    }
   }
   s_red[(grp * 4 + 0) * kTile + px] = (o.min_cen == 255) ? kFill : (float)o.min_cen;
   s_red[(grp * 4 + 1) * kTile + px] = o.min_ncc;
@@ -776,6 +793,43 @@ __device__ __forceinline__ float cen_ch0(int cb, const float* s_lutn) {
   const float r = 1.0f / 120.0f;
   const float q = __fmul_rn(k, r);
   return __fmaf_rn(__fmaf_rn(-120.0f, q, k), r, q);
+}
+// The four parked census bytes of a pixel quad as floats WITHOUT integer conversions: PRMT drops a byte into
+// the mantissa of 2^23, so as_float(word) - 2^23 is the byte (one packed FADD2 per two pixels, and the
+// subtraction can carry any other integer with it).  kSignFill: bit 7 of the byte (set only by the 255 that
+// stands for "no cost") is replicated into mantissa bits 8-15, so "no cost" becomes 65535 -- an AML argument
+// that underflows to exactly 0 for every sigma below 1e7 (checked by the launcher), which is what the
+// reference's fill does.
+template <unsigned kSel>   // prmt.b32 in its default mode: a selector nibble with bit 3 set replicates the byte's sign
+__device__ __forceinline__ float prmt_f(uint32_t a, uint32_t b) {   // (__byte_perm masks that bit away)
+  float r;
+  asm("prmt.b32 %0, %1, %2, %3;" : "=f"(r) : "r"(a), "r"(b), "n"(kSel));
+  return r;
+}
+template <bool kSignFill>
+__device__ __forceinline__ float4 cen_bytes_as_biased_floats(uint32_t cw) {
+  constexpr unsigned base = 0x4B000000u;   // 2^23
+  float4 f;
+  f.x = prmt_f<kSignFill ? 0x7480u : 0x7440u>(cw, base);
+  f.y = prmt_f<kSignFill ? 0x7491u : 0x7441u>(cw, base);
+  f.z = prmt_f<kSignFill ? 0x74A2u : 0x7442u>(cw, base);
+  f.w = prmt_f<kSignFill ? 0x74B3u : 0x7443u>(cw, base);
+  return f;
+}
+// Channel 0 of four pixels, min(k,120)/120 with cen_ch0's three operations per value, packed.  The clamp moves to
+// the end as a free saturation: k <= 120 gives a quotient <= 1 that the saturation leaves alone, and the only other
+// byte, 255 ("no cost"), gives 2.125, which saturates to the 1.0 that clip(fill, 0, 120) / 120 is.
+__device__ __forceinline__ float4 cen_ch0_quad(uint32_t cw) {
+  const float4 f = cen_bytes_as_biased_floats<false>(cw);
+  const f32x2 b2 = pk2(8388608.0f, 8388608.0f), r2 = pk2(1.0f / 120.0f, 1.0f / 120.0f), n2 = pk2(-120.0f, -120.0f);
+  const f32x2 k01 = sub2(pk2(f.x, f.y), b2), k23 = sub2(pk2(f.z, f.w), b2);
+  const f32x2 q01 = mul2(k01, r2), q23 = mul2(k23, r2);
+  float4 q, e;
+  upk2(q01, q.x, q.y); upk2(q23, q.z, q.w);
+  upk2(fma2(n2, q01, k01), e.x, e.y); upk2(fma2(n2, q23, k23), e.z, e.w);
+  const float r = 1.0f / 120.0f;
+  return make_float4(__saturatef(__fmaf_rn(e.x, r, q.x)), __saturatef(__fmaf_rn(e.y, r, q.y)),
+                     __saturatef(__fmaf_rn(e.z, r, q.z)), __saturatef(__fmaf_rn(e.w, r, q.w)));
 }
 template <bool kLut, bool kExact = false>
 __device__ __forceinline__ float cen_e(int cb, int mc, const float* s_lut, float k_cen) {
@@ -818,21 +872,27 @@ template <bool kVec, class T>
 __device__ __forceinline__ void store_ch03(const float* s_par, const uint8_t* s_cen, const float* s_lutn, int PS,
                                            int q4, int d0, int d1, T* orow, size_t plane, size_t chan,
                                            int nlive) {
+  // (the output row is a pointer that advances by 16 planes per sweep: written as orow + d * plane, ptxas
+  // redoes the 64-bit product every iteration -- ten more ALU-pipe instructions per four stores)
+  T* o = orow + (size_t)d0 * plane;
+  const size_t ostep = 16 * plane;
 #pragma unroll(kBackUnroll)
-  for (int d = d0; d < d1; d += 16) {
+  for (int d = d0; d < d1; d += 16, o += ostep) {
     const float* e0 = s_par + d * kTile + q4;
-    const uchar4 cb = *reinterpret_cast<const uchar4*>(s_cen + d * kTile + q4);
+    const uint32_t cw = *reinterpret_cast<const uint32_t*>(s_cen + d * kTile + q4);
     const float4 v1 = *reinterpret_cast<const float4*>(e0);
     const float4 v2 = *reinterpret_cast<const float4*>(e0 + PS);
     const float4 v3 = *reinterpret_cast<const float4*>(e0 + 2 * PS);
-    const float4 c0 = make_float4(cen_ch0(cb.x, s_lutn), cen_ch0(cb.y, s_lutn), cen_ch0(cb.z, s_lutn), cen_ch0(cb.w, s_lutn));
+    float4 c0;
+    if (kCenLutCh0) c0 = make_float4(s_lutn[cw & 255u], s_lutn[(cw >> 8) & 255u], s_lutn[(cw >> 16) & 255u], s_lutn[cw >> 24]);
+    else c0 = cen_ch0_quad(cw);
     const float4 c1 = make_float4(normalise_cost(v1.x, 1), normalise_cost(v1.y, 1), normalise_cost(v1.z, 1),
                                   normalise_cost(v1.w, 1));
     const float4 c2 = make_float4(normalise_cost(v2.x, 2), normalise_cost(v2.y, 2), normalise_cost(v2.z, 2),
                                   normalise_cost(v2.w, 2));
     const float4 c3 = make_float4(normalise_cost(v3.x, 3), normalise_cost(v3.y, 3), normalise_cost(v3.z, 3),
                                   normalise_cost(v3.w, 3));
-    store_quads<kVec>(orow + (size_t)d * plane, chan, nlive, c0, c1, c2, c3);
+    store_quads<kVec>(o, chan, nlive, c0, c1, c2, c3);
   }
 }
 
@@ -870,9 +930,12 @@ __device__ __forceinline__ void phase3_quads(const float* s_par, const uint8_t* 
   const f32x2 mp1[2] = {pk2(m1.x, m1.y), pk2(m1.z, m1.w)}, ip1[2] = {pk2(i1.x, i1.y), pk2(i1.z, i1.w)};
   const f32x2 mp2[2] = {pk2(m2.x, m2.y), pk2(m2.z, m2.w)}, ip2[2] = {pk2(i2.x, i2.y), pk2(i2.z, i2.w)};
   const f32x2 mp3[2] = {pk2(m3.x, m3.y), pk2(m3.z, m3.w)}, ip3[2] = {pk2(i3.x, i3.y), pk2(i3.z, i3.w)};
-  const f32x2 nk1 = pk2(-k1, -k1), nk2 = pk2(-k2, -k2);
+  const f32x2 nk1 = pk2(-k1, -k1), nk2 = pk2(-k2, -k2), nk0 = pk2(-k0, -k0);
   const int mcx = (m_cen4.x == kFill) ? 0 : (int)m_cen4.x, mcy = (m_cen4.y == kFill) ? 0 : (int)m_cen4.y;
   const int mcz = (m_cen4.z == kFill) ? 0 : (int)m_cen4.z, mcw = (m_cen4.w == kFill) ? 0 : (int)m_cen4.w;
+  // census minima biased by 2^23 (exact: the minima are integers <= 120), see cen_bytes_as_biased_floats
+  const f32x2 mp0[2] = {pk2(8388608.0f + (float)mcx, 8388608.0f + (float)mcy), pk2(8388608.0f + (float)mcz, 8388608.0f + (float)mcw)};
+  const f32x2 ip0[2] = {pk2(i0.x, i0.y), pk2(i0.z, i0.w)};
 #pragma unroll(kBackUnroll)
   for (int d = dl; d < D; d += 32) {
     const float* e0 = s_par + d * kTile + q4;
@@ -888,8 +951,13 @@ __device__ __forceinline__ void phase3_quads(const float* s_par, const uint8_t* 
       p3_quad_exact(v2, m2, i2, -k2, a2);
       p3_quad_exact(v3, m3, i3, -k2, a3);
     } else {
-      a0 = make_float4(cen_e<kCenLutP3>(cb.x, mcx, s_lut, k0) * i0.x, cen_e<kCenLutP3>(cb.y, mcy, s_lut, k0) * i0.y,
-                       cen_e<kCenLutP3>(cb.z, mcz, s_lut, k0) * i0.z, cen_e<kCenLutP3>(cb.w, mcw, s_lut, k0) * i0.w);
+      if (kCenLutP3) {
+        a0 = make_float4(cen_e<true>(cb.x, mcx, s_lut, k0) * i0.x, cen_e<true>(cb.y, mcy, s_lut, k0) * i0.y,
+                         cen_e<true>(cb.z, mcz, s_lut, k0) * i0.z, cen_e<true>(cb.w, mcw, s_lut, k0) * i0.w);
+      } else {
+        // (byte + 2^23) - (min + 2^23) = the integer difference cen_e squares; "no cost" is 65535 - min: exactly 0
+        p3_quad(cen_bytes_as_biased_floats<true>(*reinterpret_cast<const uint32_t*>(&cb)), mp0, ip0, nk0, a0);
+      }
       p3_quad(v1, mp1, ip1, nk1, a1);
       p3_quad(v2, mp2, ip2, nk2, a2);
       p3_quad(v3, mp3, ip3, nk2, a3);
@@ -1558,8 +1626,9 @@ size_t fused_exchange_bytes(int N, int H, int W, const msn_ms_params* p, int sou
 }
 
 bool fused_supported(const msn_ms_params* p, int Dn) {
+  // cens_sigma < 1e7: the back half lets "no cost" underflow the census AML term to 0 (cen_bytes_as_biased_floats)
   return p->censw == kCensW && p->nccw == kNccW && p->sadw == kSadW && p->sobelw == kSadW &&
-         Dn <= kMaxFusedD;  // (image width is checked at launch; p->lr: the caller adds the right view)
+         p->cens_sigma < 1.0e7f && Dn <= kMaxFusedD;  // (image width is checked at launch; p->lr: the caller adds the right view)
 }
 
 size_t fused_workspace_bytes(int N, int H, int W, int Dn, const msn_ms_params* p) {
