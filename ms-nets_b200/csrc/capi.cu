@@ -645,6 +645,10 @@ int msn_ms_features_wta_dev(const uint8_t* d_left, const uint8_t* d_right, int N
   const size_t n = (size_t)g.h * g.w;
   if (use_fused(p, g, W)) {
     if (!p->lr) return launch_ms_fused(d_left, d_right, N, H, W, p, d_out, nullptr, base, s, 0, 0, 0, nullptr, &wta);
+    // both views, fast AML mode: two one-pass launches -- the left view as above into channels 0-7, then the right
+    // view (channels 8-15) recomputed from the images with the roles swapped (ms_fused.cu: phase1_tile_right); the
+    // volume is written once and never re-read.  The exact AML mode keeps the three-phase route below.
+    if (!g_aml_exact) return launch_ms_fused(d_left, d_right, N, H, W, p, d_out, nullptr, base, s);
     const size_t stat_bytes = align256((size_t)N * 8 * n * sizeof(float));
     float* mins = reinterpret_cast<float*>(base + align256(fused_workspace_bytes(N, H, W, g.Dn, p)));
     float* den = reinterpret_cast<float*>(reinterpret_cast<char*>(mins) + stat_bytes);

@@ -70,6 +70,8 @@ struct FusedGeom {
   int Dl;   // disparities of the whole launch (= D unless the launch is cut into sub-slabs, kModeXchg)
   int Hp, Wp, padL;
   int sxo, Ws;   // SAD-of-Sobel scratch: column offset and row pitch (tile starts land on 16 B)
+  int lr;        // both views (p->lr): the right-view tiles slide the LEFT window rightwards, so the planes carry
+                 // D + slack padded columns on the right as well, and the left image's statistics get planes too
   __host__ __device__ size_t img_px() const { return (size_t)Hp * Wp; }
 };
 
@@ -85,7 +87,8 @@ FusedGeom make_geom(int N, int H, int W, const msn_ms_params* p) {
   g.w = W - p->board_w_left - p->board_w_right;
   g.padL = (g.d0 + g.D + 1 + kSlack + 8 + 7) & ~7;  // d0+D-1 columns of disparity + dummy-step slack + halo/alignment
   g.Hp = H + 2 * kPadT;
-  g.Wp = (W + g.padL + kPadR + 3) & ~3;
+  g.lr = p->lr ? 1 : 0;
+  g.Wp = (W + g.padL + (g.lr ? g.D + kSlack + kPadR + 16 : kPadR) + 3) & ~3;
   g.sxo = (4 - (g.bwl & 3)) & 3;            // x0 + bwl + sxo is a multiple of 4 for every tile
   g.Ws = sadsob_fast_pitch(W + g.sxo + kTileMax);  // compile-time pitch of the scan kernels (0: too wide)
   return g;
@@ -99,6 +102,10 @@ struct FusedWs {
   float* meanR;    // right image: ZSAD window means as a plain float plane
   float* AR;       // right image: NCC window sums A as a plain float plane
   double* CR;      // right image: NCC 1/sqrt(9B - A^2) as a plain double plane
+  float* meanL;    // left image: the same three planes (both views only: the right-view tiles read them per column)
+  float* AL;
+  double* CL;
+  float* first4;   // [N][4] raw costs of cropped voxel (0,0,0): what get_right_cost fills with (featextract.cpp:151)
   float* luts;     // [128] census AML exponentials + [256] census byte -> channel 0
   float* sadsob;   // [N][D][H][Ws], or [N][H][D][Ws] (FusedGeom::d_inner)
   void* sad_ws;
@@ -114,6 +121,13 @@ struct FusedWs {
     meanR = (float*)take((np + 16) * sizeof(float));
     AR = (float*)take((np + 16) * sizeof(float));
     CR = (double*)take((np + 16) * sizeof(double));
+    meanL = AL = first4 = nullptr; CL = nullptr;
+    if (g.lr) {
+      meanL = (float*)take((np + 16) * sizeof(float));
+      AL = (float*)take((np + 16) * sizeof(float));
+      CL = (double*)take((np + 16) * sizeof(double));
+      first4 = (float*)take((size_t)g.N * 4 * sizeof(float));
+    }
     luts = (float*)take(384 * sizeof(float));
     sadsob = (float*)take((size_t)g.N * g.Dl * g.H * g.Ws * sizeof(float) + 256);
     sad_ws = take(sadsob_workspace_bytes_n(g.N, g.H, g.W, g.Dl, kSadW));
@@ -128,7 +142,8 @@ ms_prep_kernel(const uint8_t* __restrict__ left, const uint8_t* __restrict__ rig
                uint4* __restrict__ descL, uint4* __restrict__ descR, RStat* __restrict__ statL,
                RStat* __restrict__ statR, float* __restrict__ fL, float* __restrict__ fR,
                float* __restrict__ sobL, float* __restrict__ sobR, float* __restrict__ meanR,
-               float* __restrict__ AR, double* __restrict__ CR, float* __restrict__ luts, float k_cen) {
+               float* __restrict__ AR, double* __restrict__ CR, float* __restrict__ meanL,
+               float* __restrict__ AL, double* __restrict__ CL, float* __restrict__ luts, float k_cen) {
   if (blockIdx.x == 0 && blockIdx.y == 0 && blockIdx.z == 0) {
     // tables for the fused kernel: census AML exponentials exp(-(k^2)/sigma), k = 0..120, and the
     // channel-0 value k/120 of a parked census byte (a true IEEE division; 255 = no cost ->
@@ -214,6 +229,10 @@ ms_prep_kernel(const uint8_t* __restrict__ left, const uint8_t* __restrict__ rig
     meanR[po] = st.mean;
     AR[po] = st.A;
     CR[po] = st.C;
+  } else if (meanL) {   // both views: the right-view tiles read the left image the same way
+    meanL[po] = st.mean;
+    AL[po] = st.A;
+    CL[po] = st.C;
   }
 }
 
@@ -233,6 +252,11 @@ struct FusedArgs {
   const float *fL, *fR;
   const float *meanR, *AR;       // right-image ZSAD means / NCC window sums, float planes
   const double* CR;              // right-image NCC scale, double plane
+  const float *meanL, *AL;       // the left image's planes (kModeRight)
+  const double* CL;
+  const float* first4;           // kModeRight: [N][4] raw costs that stand in where x + d >= w (get_right_cost's fill)
+  float* first4_out;             // full mode, both views requested: where the left-view launch leaves those four
+  int out_ch0;                   // first channel this launch writes (8 for the right view)
   const float* luts;    // [128] + [256], see ms_prep_kernel
   const float* sadsob;  // see FusedWs
   float* out;           // [N][8][D][h][w]
@@ -257,6 +281,7 @@ struct FusedArgs {
 };
 
 constexpr int kTile = 32;   // pixels per tile: one output row segment of 128 bytes
+constexpr int kModeRight = 5;   // the RIGHT view (channels 8-15 of extract_features_lr): see phase1_tile_right
 constexpr int kModeFull = 0, kModeSlabA = 1, kModeXchg = 2, kModeBf16 = 3, kModeExact = 4;   // kModeBf16: kModeFull writing a bf16 volume; kModeExact: kModeFull with the reference's own AML arithmetic
 
 // Staging buffer of one tile: right-image row data for the D + 31 (+ slack) columns the tile
@@ -453,13 +478,14 @@ __device__ __forceinline__ void stage_right(const FusedArgs& a, const TileId& t,
 
 // Same data through the TMA engine: nine 1-D bulk copies issued by a single thread,
 // completion counted in bytes on `bar`.
-template <class L>
+// kRightView: the LEFT image's rows for columns X0 + d0 .. (the window of a right-view tile slides rightwards).
+template <class L, bool kRightView = false>
 __device__ __forceinline__ void stage_rows_tma(const FusedArgs& a, const TileId& t, unsigned char* buf,
                                                unsigned long long* bar) {
   const FusedGeom& g = a.g;
   const int D = g.D;
   const int RWn = D + kTile - 1 + L::kSl;
-  const int XbaseP = t.x0 + g.bwl - (t.d0 + D - 1) - L::kSl + g.padL;
+  const int XbaseP = kRightView ? t.x0 + g.bwl + t.d0 + g.padL : t.x0 + g.bwl - (t.d0 + D - 1) - L::kSl + g.padL;
   const int Yp = t.y + g.bh + kPadT;
   const size_t img_off = (size_t)t.n * g.img_px();
   const int fstart = (XbaseP - 2) & ~3;
@@ -467,15 +493,20 @@ __device__ __forceinline__ void stage_rows_tma(const FusedArgs& a, const TileId&
   const unsigned row_bytes = (unsigned)RWn * 16u, frow_bytes = (unsigned)nvec * 16u;
   const int cstart = XbaseP & ~1;
   const unsigned crow_bytes = (unsigned)((RWn + 1 + 1) >> 1) * 16u;
+  const uint4* desc = kRightView ? a.descL : a.descR;
+  const double* C = kRightView ? a.CL : a.CR;
+  const float* f = kRightView ? a.fL : a.fR;
+  const float* A = kRightView ? a.AL : a.AR;
+  const float* mean = kRightView ? a.meanL : a.meanR;
   mbar_expect_tx(bar, row_bytes + crow_bytes + 7u * frow_bytes);
-  bulk_load(buf + L::st_desc, a.descR + img_off + (size_t)Yp * g.Wp + XbaseP, row_bytes, bar);
-  bulk_load(buf + L::st_c, a.CR + img_off + (size_t)Yp * g.Wp + cstart, crow_bytes, bar);
+  bulk_load(buf + L::st_desc, desc + img_off + (size_t)Yp * g.Wp + XbaseP, row_bytes, bar);
+  bulk_load(buf + L::st_c, C + img_off + (size_t)Yp * g.Wp + cstart, crow_bytes, bar);
   float* s_rf = reinterpret_cast<float*>(buf + L::st_rf);
 #pragma unroll
   for (int r = 0; r < 5; ++r)
-    bulk_load(s_rf + r * L::RWF, a.fR + img_off + (size_t)(Yp - 2 + r) * g.Wp + fstart, frow_bytes, bar);
-  bulk_load(s_rf + 5 * L::RWF, a.AR + img_off + (size_t)Yp * g.Wp + fstart, frow_bytes, bar);
-  bulk_load(s_rf + 6 * L::RWF, a.meanR + img_off + (size_t)Yp * g.Wp + fstart, frow_bytes, bar);
+    bulk_load(s_rf + r * L::RWF, f + img_off + (size_t)(Yp - 2 + r) * g.Wp + fstart, frow_bytes, bar);
+  bulk_load(s_rf + 5 * L::RWF, A + img_off + (size_t)Yp * g.Wp + fstart, frow_bytes, bar);
+  bulk_load(s_rf + 6 * L::RWF, mean + img_off + (size_t)Yp * g.Wp + fstart, frow_bytes, bar);
 }
 
 // The tile's D x 32 SAD-of-Sobel costs: ONE 3-D tensor copy straight into parking plane 1.
@@ -496,16 +527,17 @@ struct LeftRegs {
   uint4 stat;
   float px[5][5];
 };
+template <bool kRightView = false>   // kRightView: the pixel's RIGHT-image data (the fixed side of a right-view tile)
 __device__ __forceinline__ void load_left(const FusedArgs& a, const TileId& t, int px, LeftRegs& lr) {
   const FusedGeom& g = a.g;
   const int Yp = t.y + g.bh + kPadT;
   const int Xp = t.x0 + px + g.bwl + g.padL;
   const size_t img_off = (size_t)t.n * g.img_px();
-  lr.desc = __ldg(a.descL + img_off + (size_t)Yp * g.Wp + Xp);
-  lr.stat = __ldg(reinterpret_cast<const uint4*>(a.statL + img_off + (size_t)Yp * g.Wp + Xp));
+  lr.desc = __ldg((kRightView ? a.descR : a.descL) + img_off + (size_t)Yp * g.Wp + Xp);
+  lr.stat = __ldg(reinterpret_cast<const uint4*>((kRightView ? a.statR : a.statL) + img_off + (size_t)Yp * g.Wp + Xp));
 #pragma unroll
   for (int r = 0; r < 5; ++r) {
-    const float* gf = a.fL + img_off + (size_t)(Yp - 2 + r) * g.Wp + (Xp - 2);
+    const float* gf = (kRightView ? a.fR : a.fL) + img_off + (size_t)(Yp - 2 + r) * g.Wp + (Xp - 2);
 #pragma unroll
     for (int c = 0; c < 5; ++c) lr.px[r][c] = __ldg(gf + c);
   }
@@ -735,6 +767,225 @@ __device__ __forceinline__ Phase1Out phase1_tile(const FusedArgs& a, const TileI
   o.min_sad = st.min_sad;
   o.dmax_sad = dmax_sad;
   return o;
+}
+
+// ---- phase 1 of a RIGHT-VIEW tile (channels 8-15 of extract_features_lr, cbmv_generator.py:84-254) ----------
+// get_right_cost (featextract.cpp:136-172): right(y, x, d) = cost(y, x + d, d) for x + d < w, else c.flat[0].
+// A right-view tile therefore needs the costs of a PARALLELOGRAM of the left-view volume; instead of parking
+// raw costs in HBM and gathering them back (the three-phase route of slab.cu: 2.7x the traffic), the tile
+// recomputes them with the roles swapped: thread = (RIGHT pixel xr, d-group), the right window is fixed in
+// registers and the LEFT window (pixel xr + d) slides rightwards with d.  Every cost is the same sequence of IEEE
+// operations as in the left-view tile:
+//  census  popc(codeL[xr+d] ^ codeR[xr]);
+//  NCC     9P - A_L A_R exact in fp32, then (-num * C_L) * C_R in fp64 -- the LEFT scale first (matchers.cpp:200);
+//  ZSAD    ((L - mL) - R) + mR per tap, row-major.  Disparities dA = d, dB = d + 1 are packed: tap j of dA and
+//          tap j-1 of dB read the SAME left pixel (a broadcast operand).  Both mL and L change with d, so a tap
+//          is evaluated NEGATED, three packed operations: (mL - L) + R - mR = -(((L - mL) - R) + mR) -- each step
+//          is the exact negative of the reference's (round-to-nearest is symmetric) and |.| drops the sign.
+//          100 adds per voxel instead of the left view's 75 (the left view hoists L - mL over d).
+// Validity: the cost exists iff the LEFT window at xr + d is inside -- d <= dmax with dmax falling as xr grows --
+// and xr itself is right of the window radius; beyond x + d = w - 1 the caller's first4 stands in (finish_right).
+template <class L, bool kClean>
+__device__ __forceinline__ void p1_block_right(P1State<L>& st, int dblk, int steps, int D, const f32x2 (&rp)[5][4],
+                                               const float (&r3)[3][3],
+                                               const uint4& rd, const RStat& rs, int dmax_cen, int dmax_ncc,
+                                               int dmax_sad, float* s_par, uint8_t* s_cen, int px) {
+  constexpr int PS = L::PS;
+  const f32x2 mR2 = pk2(rs.mean, rs.mean);
+#pragma unroll
+  for (int sI = 0; sI < 3; ++sI) {
+#define LV(r, j) st.wv[r][((j) + 2 * sI) % 6]
+    if (!kClean && sI > 0 && sI >= steps) break;
+    const int dA = dblk + 2 * sI, dB = dA + 1;
+    const uint4 ldA = st.dscp[0], ldB = st.dscp[1];
+    // rfp[2] / rfp[3] are left columns xr + dA / xr + dB: rows 5 and 6 hold the NCC sums and the ZSAD means
+    const float aLA = st.rfp[5 * L::RWF + 2], aLB = st.rfp[5 * L::RWF + 3];
+    const double cLA = st.ccp[0], cLB = st.ccp[1];
+    const float mLA = st.rfp[6 * L::RWF + 2], mLB = st.rfp[6 * L::RWF + 3];
+
+    const int cenA = __popc(ldA.x ^ rd.x) + __popc(ldA.y ^ rd.y) + __popc(ldA.z ^ rd.z) + __popc(ldA.w ^ rd.w);
+    const int cenB = __popc(ldB.x ^ rd.x) + __popc(ldB.y ^ rd.y) + __popc(ldB.z ^ rd.z) + __popc(ldB.w ^ rd.w);
+    const int cen_bA = (kClean || dA <= dmax_cen) ? cenA : 255;
+    const int cen_bB = (kClean || dB <= dmax_cen) ? cenB : 255;
+
+    float PA = 0.f, PB = 0.f;
+#pragma unroll
+    for (int r = 0; r < 3; ++r)
+#pragma unroll
+      for (int c = 0; c < 3; ++c) {
+        PA = __fmaf_rn(LV(r + 1, c + 1), r3[r][c], PA);
+        PB = __fmaf_rn(LV(r + 1, c + 2), r3[r][c], PB);
+      }
+    const float numA = __fmaf_rn(9.0f, PA, -__fmul_rn(aLA, rs.A));
+    const float numB = __fmaf_rn(9.0f, PB, -__fmul_rn(aLB, rs.A));
+    float nccA = (float)__dmul_rn(__dmul_rn(-(double)numA, cLA), rs.C);
+    float nccB = (float)__dmul_rn(__dmul_rn(-(double)numB, cLB), rs.C);
+    nccA = (fabsf(nccA) <= 3.0e38f) ? nccA : 1.0f;
+    nccB = (fabsf(nccB) <= 3.0e38f) ? nccB : 1.0f;
+    nccA = (kClean || dA <= dmax_ncc) ? nccA : kFill;
+    nccB = (kClean || dB <= dmax_ncc) ? nccB : kFill;
+
+    const f32x2 mL2 = pk2(mLA, mLB);
+    f32x2 acc = pk2(0.f, 0.f);   // (dA, dB)
+#pragma unroll
+    for (int r = 0; r < 5; ++r) {
+      float accA, accB, r0, r4, dum;
+      upk2(rp[r][0], dum, r0);   // R[r][0] and R[r][4] are halves of the hoisted pairs
+      upk2(rp[r][3], r4, dum);
+      upk2(acc, accA, accB);
+      accA = __fadd_rn(accA, fabsf(__fadd_rn(__fsub_rn(__fsub_rn(LV(r, 0), mLA), r0), rs.mean)));   // dA tap 0
+      acc = pk2(accA, accB);
+#pragma unroll
+      for (int j = 1; j <= 4; ++j) {
+        const float lj = LV(r, j);
+        const f32x2 n = sub2(add2(sub2(mL2, pk2(lj, lj)), rp[r][j - 1]), mR2);   // dA tap j, dB tap j-1 (negated)
+        acc = add2(acc, abs2(n));
+      }
+      upk2(acc, accA, accB);
+      accB = __fadd_rn(accB, fabsf(__fadd_rn(__fsub_rn(__fsub_rn(LV(r, 5), mLB), r4), rs.mean)));   // dB tap 4
+      acc = pk2(accA, accB);
+    }
+    float zA, zB;
+    upk2(acc, zA, zB);
+    zA = (kClean || dA <= dmax_sad) ? zA : kFill;
+    zB = (kClean || dB <= dmax_sad) ? zB : kFill;
+
+    const int dsA = kClean ? dA : min(dA, D);
+    const int dsB = kClean ? dB : min(dB, D);
+    s_cen[dsA * kTile + px] = (uint8_t)cen_bA;
+    s_cen[dsB * kTile + px] = (uint8_t)cen_bB;
+    s_par[dsA * kTile + px] = nccA;
+    s_par[dsB * kTile + px] = nccB;
+    s_par[2 * PS + dsA * kTile + px] = zA;
+    s_par[2 * PS + dsB * kTile + px] = zB;
+    st.min_cen = min(st.min_cen, min(cen_bA, cen_bB));
+    st.min_ncc = fminf(st.min_ncc, fminf(nccA, nccB));
+    st.min_sad = fminf(st.min_sad, fminf(zA, zB));
+    // slide the window two columns right: the next pair's new columns 4 and 5
+    st.rfp += 2; st.dscp += 2; st.ccp += 2;
+#pragma unroll
+    for (int r = 0; r < 5; ++r) {
+      st.wv[r][(4 + 2 * (sI + 1)) % 6] = st.rfp[r * L::RWF + 4];
+      st.wv[r][(5 + 2 * (sI + 1)) % 6] = st.rfp[r * L::RWF + 5];
+    }
+#undef LV
+  }
+}
+
+struct Phase1RightOut {
+  Phase1Out o;
+  int dcrop;   // last disparity (local to the launch) with x + d < w: beyond it first4 stands in
+};
+
+template <class L>
+__device__ __forceinline__ Phase1RightOut phase1_tile_right(const FusedArgs& a, const TileId& t, const unsigned char* stage,
+                                                            float* s_par, uint8_t* s_cen, const LeftRegs& rr, int px,
+                                                            int d_lo) {
+  constexpr int PS = L::PS;
+  const FusedGeom& g = a.g;
+  const int D = g.D, H = g.H, W = g.W;
+  const int Xr = t.x0 + px + g.bwl;       // bordered image column of this thread's RIGHT pixel
+  const int Y = t.y + g.bh;
+  const uint4 rd = rr.desc;
+  const RStat rs = *reinterpret_cast<const RStat*>(&rr.stat);
+  f32x2 rp[5][4];   // rp[r][j-1] = (R[r][j], R[r][j-1]) for j = 1..4
+  float r3[3][3];
+#pragma unroll
+  for (int r = 0; r < 5; ++r) {
+#pragma unroll
+    for (int c = 0; c < 5; ++c)
+      if (r >= 1 && r <= 3 && c >= 1 && c <= 3) r3[r - 1][c - 1] = rr.px[r][c];
+#pragma unroll
+    for (int j = 1; j <= 4; ++j) rp[r][j - 1] = add2(pk2(rr.px[r][j], rr.px[r][j - 1]), pk2(0.f, 0.f));   // (own value per pair, see phase1_tile)
+  }
+  // the cost of (xr, d) is the left-view cost of pixel X = xr + d: window origin inside <=> X below the right
+  // margin; X - wc >= d <=> xr >= wc
+  const int dcrop = (g.w - 1 - (t.x0 + px)) - t.d0;
+  const int dmax_cen = min(min(D - 1, dcrop), ((Y >= 5 && Y < H - 6 && Xr >= 5) ? W - 7 - Xr : -1) - t.d0);
+  const int dmax_ncc = min(min(D - 1, dcrop), ((Y >= 1 && Y < H - 2 && Xr >= 1) ? W - 3 - Xr : -1) - t.d0);
+  const int dmax_sad = min(min(D - 1, dcrop), ((Y >= 2 && Y < H - 3 && Xr >= 2) ? W - 4 - Xr : -1) - t.d0);
+
+  const uint4* s_desc = reinterpret_cast<const uint4*>(stage + L::st_desc);
+  const double* s_c = reinterpret_cast<const double*>(stage + L::st_c);
+  const float* s_rf = reinterpret_cast<const float*>(stage + L::st_rf);
+  // shared index of left column xr + d is px + d; rises by one per step
+  const int XbaseP = t.x0 + g.bwl + t.d0 + g.padL;
+  const int shift = (XbaseP - 2) & 3;
+  P1State<L> st;
+  st.rfp = s_rf + shift + px + d_lo;        // column (xr + dA) - 2 of the pair's first disparity
+  st.dscp = s_desc + px + d_lo;
+  st.ccp = s_c + (XbaseP & 1) + px + d_lo;
+#pragma unroll
+  for (int r = 0; r < 5; ++r)
+#pragma unroll
+    for (int j = 0; j < 6; ++j) st.wv[r][j] = st.rfp[r * L::RWF + j];
+  st.min_cen = 255;
+  st.min_ncc = kFill;
+  st.min_sad = kFill;
+
+  for (int base = 0; base < a.DC; base += 6) {
+    const int dblk = d_lo + base;
+    const int left = a.DC - base;
+    const bool clean = (left >= 6) && (dblk + 5 <= dmax_cen);
+    const bool none = dblk > dmax_ncc;
+    if (__all_sync(0xffffffffu, clean)) {
+      p1_block_right<L, true>(st, dblk, 3, D, rp, r3, rd, rs, dmax_cen, dmax_ncc, dmax_sad, s_par, s_cen, px);
+    } else if (__all_sync(0xffffffffu, none)) {
+      const int nd = min(left, 6);
+#pragma unroll
+      for (int k = 0; k < 6; ++k) {
+        if (k >= nd) break;
+        const int ds = min(dblk + k, D);
+        s_cen[ds * kTile + px] = 255;
+        s_par[ds * kTile + px] = kFill;
+        s_par[2 * PS + ds * kTile + px] = kFill;
+      }
+      st.rfp += 6; st.dscp += 6; st.ccp += 6;
+    } else {
+      p1_block_right<L, false>(st, dblk, min(left, 6) >> 1, D, rp, r3, rd, rs, dmax_cen, dmax_ncc, dmax_sad, s_par, s_cen, px);
+    }
+  }
+  Phase1RightOut o;
+  o.o.min_cen = st.min_cen;
+  o.o.min_ncc = st.min_ncc;
+  o.o.min_sad = st.min_sad;
+  o.o.dmax_sad = dmax_sad;
+  o.dcrop = dcrop;
+  return o;
+}
+
+// Right view, after phase 1: SAD-of-Sobel validity and minima as in finish_phase1, then get_right_cost's fill --
+// where x + d >= w all four matchers hold the volume's first element (featextract.cpp:151), which takes part in
+// the minima like any cost.
+template <class L>
+__device__ __forceinline__ void finish_right(float* s_par, uint8_t* s_cen, float* s_red, const Phase1RightOut& ro,
+                                             const float* first4, int px, int grp, int d_lo, int d_end) {
+  constexpr int PS = L::PS;
+  const Phase1Out& o = ro.o;
+  float mn[4] = {(o.min_cen == 255) ? kFill : (float)o.min_cen, o.min_ncc, kFill, o.min_sad};
+  float* sp = s_par + PS + d_lo * kTile + px;
+  for (int d = d_lo; d < d_end; ++d, sp += kTile) {
+    float v = *sp;
+    if (d > o.dmax_sad) {
+      v = kFill;
+      *sp = v;
+    }
+    mn[2] = fminf(mn[2], v);
+  }
+  const int df = max(d_lo, ro.dcrop + 1);
+  if (df < d_end) {
+    const float f0 = first4[0], f1 = first4[1], f2 = first4[2], f3 = first4[3];
+    const uint8_t b0 = (f0 == kFill) ? (uint8_t)255 : (uint8_t)f0;
+    for (int d = df; d < d_end; ++d) {
+      s_cen[d * kTile + px] = b0;
+      s_par[d * kTile + px] = f1;
+      s_par[PS + d * kTile + px] = f2;
+      s_par[2 * PS + d * kTile + px] = f3;
+    }
+    mn[0] = fminf(mn[0], f0); mn[1] = fminf(mn[1], f1); mn[2] = fminf(mn[2], f2); mn[3] = fminf(mn[3], f3);
+  }
+#pragma unroll
+  for (int m = 0; m < 4; ++m) s_red[(grp * 4 + m) * kTile + px] = mn[m];
 }
 
 // After phase 1 and once the tile's SAD-of-Sobel costs have landed in plane 1: this thread's
@@ -1149,7 +1400,7 @@ __device__ __forceinline__ void tile_back_half(const FusedArgs& a, const TileId&
   const int q4 = (tid & 7) * 4;
   // 128-bit stores need 16-byte aligned rows
   const bool vec_ok = ((g.w & 3) == 0) && ((reinterpret_cast<uintptr_t>(a.out) & 15) == 0);
-  T* orow = reinterpret_cast<T*>(a.out) + (size_t)t.n * a.out_channels * chan + (size_t)(a.out_d0 + t.sub0) * plane + (size_t)t.yl * g.w + (t.x0 + q4);
+  T* orow = reinterpret_cast<T*>(a.out) + ((size_t)t.n * a.out_channels + a.out_ch0) * chan + (size_t)(a.out_d0 + t.sub0) * plane + (size_t)t.yl * g.w + (t.x0 + q4);
   const int nlive = min(4, g.w - (t.x0 + q4));  // live pixels of this quad (<= 0: none)
   const bool vec = vec_ok && nlive == 4;
   if (warp < 4) {
@@ -1280,6 +1531,42 @@ __device__ __forceinline__ void fused_tile(const FusedArgs& a, const CUtensorMap
   const TileId t = decode_tile((int)tile, a, sub);
   const int d_lo = grp * a.DC;
   const int d_end = min(D, d_lo + a.DC);  // real disparities of this thread: [d_lo, d_end)
+  if (kMode == kModeRight) {
+    // The right view: left-image rows through bulk copies (any D: no tensor box), this thread's own SAD-of-Sobel
+    // costs -- right(xr, d) = scratch(d, y, xr + d), a diagonal no box describes -- through LDGSTS, only where
+    // the cost exists (finish_right fills the rest).
+    if (tid == 0) {
+      mbar_init(&s_bar[0], 1);
+      mbar_init_fence();
+      stage_rows_tma<L, true>(a, t, smem_raw, &s_bar[0]);
+    }
+    if (kCenLut) {
+      if (tid < 128) s_lut[tid] = __ldg(a.luts + tid);
+      s_lutn[tid] = __ldg(a.luts + 128 + tid);
+    }
+    {
+      const int Xr = t.x0 + px + g.bwl, Y = t.y + g.bh;
+      const int dcrop = (g.w - 1 - (t.x0 + px)) - t.d0;
+      const int dmax_sad = min(min(D - 1, dcrop), ((Y >= 2 && Y < g.H - 3 && Xr >= 2) ? g.W - 4 - Xr : -1) - t.d0);
+      const size_t splane = g.d_inner ? (size_t)g.Ws : (size_t)g.H * g.Ws;
+      const size_t row0 = g.d_inner ? (((size_t)t.n * g.H + (t.y + g.bh)) * g.Dl + t.sub0) * g.Ws
+                                    : (((size_t)t.n * g.Dl + t.sub0) * g.H + (t.y + g.bh)) * g.Ws;
+      const float* src = a.sadsob + row0 + (Xr + t.d0 + g.sxo) + (size_t)d_lo * (splane + 1);
+      float* dst = s_par + PS + d_lo * kTile + px;
+      const int dl = min(d_end, dmax_sad + 1);
+      for (int d = d_lo; d < dl; ++d, src += splane + 1, dst += kTile) cp_async4(dst, src);
+    }
+    LeftRegs rr;
+    load_left<true>(a, t, px, rr);
+    __syncthreads();
+    mbar_wait(&s_bar[0], 0);
+    const Phase1RightOut ro = phase1_tile_right<L>(a, t, smem_raw, s_par, s_cen, rr, px, d_lo);
+    cp_async_wait_all();
+    finish_right<L>(s_par, s_cen, s_red, ro, a.first4 + 4 * t.n, px, grp, d_lo, d_end);
+    __syncthreads();
+    tile_back_half<L, false>(a, t, tile, tid, s_par, s_cen, s_red, s_min, s_inv, s_lut, s_lutn);
+    return;
+  }
   if (kTma) {
     if (tid == 0) {
       mbar_init(&s_bar[0], 1);
@@ -1313,6 +1600,13 @@ __device__ __forceinline__ void fused_tile(const FusedArgs& a, const CUtensorMap
   if (kTma) mbar_wait(&s_bar[1], 0);
   finish_phase1<L>(s_par, s_red, o, px, grp, d_lo, d_end);
   __syncthreads();
+  if (kMode == kModeFull || kMode == kModeExact) {
+    // both views requested: the raw costs of cropped voxel (0, 0, 0) are what get_right_cost fills with
+    if (a.first4_out && tid < 4 && t.yl == 0 && g.y0 == 0 && t.x0 == 0 && t.d0 == 0) {
+      const float v = (tid == 0) ? ((s_cen[0] == 255) ? kFill : (float)s_cen[0]) : s_par[(tid - 1) * PS];
+      a.first4_out[4 * t.n + tid] = v;
+    }
+  }
   if (kMode == kModeSlabA) tile_slab_a<L>(a, t, tid, s_par, s_cen, s_red, s_lutn);
   else if (kMode == kModeExact) tile_back_half<L, false, float, true>(a, t, tile, tid, s_par, s_cen, s_red, s_min, s_inv, s_lut, s_lutn);
   else if (kMode == kModeBf16) tile_back_half<L, false, __nv_bfloat16>(a, t, tile, tid, s_par, s_cen, s_red, s_min, s_inv, s_lut, s_lutn);
@@ -1674,7 +1968,7 @@ int launch_ms_fused(const uint8_t* d_left, const uint8_t* d_right, int N, int H,
   dim3 pgrid(div_up(g.Wp, 128), g.Hp, 2 * N);
   ms_prep_kernel<<<pgrid, 128, 0, s>>>(d_left, d_right, g, ws.desc[0], ws.desc[1], ws.stat[0], ws.stat[1],
                                        ws.fimg[0], ws.fimg[1], ws.sob[0], ws.sob[1], ws.meanR, ws.AR, ws.CR,
-                                       ws.luts, aml_scale(p->cens_sigma));
+                                       ws.meanL, ws.AL, ws.CL, ws.luts, aml_scale(p->cens_sigma));
   MSN_LAUNCH_OK();
   if (prof) MSN_CUDA_OK(cudaEventRecord(rec.ev[1], s));
   g.d_inner = subs > 1 ? 1 : 0;   // several sub-slabs in flight: keep a tile's scratch rows on one page
@@ -1690,6 +1984,15 @@ int launch_ms_fused(const uint8_t* d_left, const uint8_t* d_right, int N, int H,
   a.statL = ws.stat[0]; a.statR = ws.stat[1];
   a.fL = ws.fimg[0]; a.fR = ws.fimg[1];
   a.meanR = ws.meanR; a.AR = ws.AR; a.CR = ws.CR;
+  a.meanL = ws.meanL; a.AL = ws.AL; a.CL = ws.CL;
+  // both views in one call (p->lr, no minima buffer): this launch writes channels 0-7 and leaves the raw costs of
+  // cropped voxel (0,0,0) for the right-view launch below, which writes channels 8-15
+  const bool both_views = p->lr && !d_mins;
+  MSN_REQUIRE(!both_views || (!exact && !xchg && !out_bf16 && g.d0 == 0 && !(wta && wta->idx)),
+              "ms_features: both views come from the one-pass kernels in the fast AML mode only (no slab, bf16 or WTA form)");
+  a.first4 = nullptr;
+  a.first4_out = both_views ? ws.first4 : nullptr;
+  a.out_ch0 = 0;
   a.luts = ws.luts;
   a.sadsob = ws.sadsob;
   a.out = d_out;
@@ -1765,6 +2068,21 @@ int launch_ms_fused(const uint8_t* d_left, const uint8_t* d_right, int N, int H,
 #undef MSN_FUSED_CASE
 #undef MSN_FUSED_LAUNCH
   MSN_LAUNCH_OK();
+  if (both_views) {
+    a.first4 = ws.first4;
+    a.first4_out = nullptr;
+    a.out_ch0 = 8;
+#define MSN_RIGHT_CASE(DMAX) \
+  if (g.D <= DMAX) { if (launch_inst<DMAX, true, kModeRight>(a, sad_map, tiles, s)) return 1; } else
+    MSN_RIGHT_CASE(64)
+    MSN_RIGHT_CASE(128)
+    MSN_RIGHT_CASE(192)
+    MSN_RIGHT_CASE(256)
+    MSN_RIGHT_CASE(384)
+    MSN_RIGHT_CASE(448) { return fail("ms_features: D=%d exceeds the fused kernel's limit", g.D); }
+#undef MSN_RIGHT_CASE
+    MSN_LAUNCH_OK();
+  }
   if (prof) {
     MSN_CUDA_OK(cudaEventRecord(rec.ev[3], s));
     std::lock_guard<std::mutex> lk(g_prof_mu);

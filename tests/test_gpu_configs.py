@@ -55,6 +55,20 @@ def test_config_a_256x512_d192(oracle):
     _compare(got, want)
 
 
+def test_config_a_256x512_d192_both_views(oracle):
+    """configs[0] with is_left_only=False: all 16 channels (extract_features_lr, cbmv_generator.py:84-254) from the
+    two one-pass launches, against the unmodified reference C++ when it travelled, else the C oracle."""
+    import msnets_b200 as ms
+    L, R = bordered_pair(256, 512, 4321, border=10)
+    ref = oracle.load_ref()
+    kw = dict(board_h=10, board_w_left=10, board_w_right=10, left_only=False)
+    want = oracle.ms_features(L, R, 192, mtc=ref[0], fte=ref[1], **kw) if ref is not None else oracle.ms_features(L, R, 192, **kw)
+    got = ms.cbmv.ms_features(L, R, 192, **kw)
+    assert got.shape == (16, 192, 256, 512)
+    _compare(got[:8], want[:8])
+    _compare(got[8:], want[8:])
+
+
 def test_config_b_sceneflow_540x960_d192_full_compare(oracle):
     """bench.py's own workload at full size, value by value: one 540x960 (560x980 bordered), D=192 pair
     computed as member 1 of a batch of two through the batched device API (the bench path), against the

@@ -172,6 +172,33 @@ def test_ms_features_fused_interior_tiles(ms, oracle):
     _check_features(got, want)
 
 
+@pytest.mark.parametrize("H,W,D,bl,br", [(34, 300, 48, 10, 10), (33, 420, 192, 10, 0), (32, 352, 300, 12, 10),
+                                         (31, 275, 64, 0, 3)])
+def test_ms_features_both_views_one_pass(ms, oracle, H, W, D, bl, br):
+    """extract_features_lr through the two one-pass launches: the right view (channels 8-15) is recomputed
+    by tiles that fix the right pixel and slide the left window (ms_fused.cu: phase1_tile_right).  Images wide
+    enough for interior (guard-free) blocks, every kernel size, ragged widths, right border 0 (the c.flat[0] fill
+    of get_right_cost, featextract.cpp:151, then starts inside the valid costs) and a left border of 0."""
+    L, R = synth_pair(H, W, 4100 + D, shift=7)
+    got = ms.cbmv.ms_features(L, R, D, left_only=False, board_h=10, board_w_left=bl, board_w_right=br)
+    want = oracle.ms_features(L, R, D, left_only=False, board_h=10, board_w_left=bl, board_w_right=br)
+    _check_features(got, want, lr=True)
+
+
+def test_ms_features_both_views_batched_matches_single(ms):
+    """A batch through the device API: every pair's right view uses its OWN first-element fill."""
+    import torch
+    H, W, D, B = 40, 200, 64, 10
+    pairs = [synth_pair(H, W, 9000 + i, shift=3 + i) for i in range(3)]
+    ex = ms.cbmv.MSFeatureExtractor(3, H, W, maxdisp=D, left_only=False, board_h=B, board_w_left=B, board_w_right=B)
+    l = torch.stack([torch.from_numpy(p[0]) for p in pairs]).cuda()
+    r = torch.stack([torch.from_numpy(p[1]) for p in pairs]).cuda()
+    got = ex(l, r).cpu().numpy()
+    for i, (L, R) in enumerate(pairs):
+        one = ms.cbmv.ms_features(L, R, D, left_only=False, board_h=B, board_w_left=B, board_w_right=B)
+        assert np.array_equal(got[i], one)
+
+
 def test_ms_features_generic_path_matches(ms, oracle, monkeypatch):
     """the three-phase global-memory path (used for slabs and non-default windows)."""
     monkeypatch.setenv("MSNETS_FORCE_GENERIC", "1")
