@@ -1389,13 +1389,16 @@ __device__ __forceinline__ void tile_back_half(const FusedArgs& a, const TileId&
   const int D = g.D;
   const size_t plane = (size_t)g.h * g.w;
   const size_t chan = plane * a.out_D;
-  if (tid < 4 * kTile) {  // minima across the d-groups (kXchg: of this rank's slab, staged in s_inv)
-    float v = kFill;
+  // Minima across the d-groups.  Only the chain warps need them before phase 3 and thread tid < 128 is exactly the
+  // (matcher, pixel) whose chain it runs, so outside the exchange form each of them folds its own eight values and
+  // no barrier separates this from phase 2 (the store warps start on channels 0-3 at once).
+  float mm_own = kFill;
+  if (tid < 4 * kTile) {
 #pragma unroll
-    for (int gq = 0; gq < kGroups; ++gq) v = fminf(v, s_red[gq * 4 * kTile + tid]);
-    (kXchg ? s_inv : s_min)[tid] = v;
+    for (int gq = 0; gq < kGroups; ++gq) mm_own = fminf(mm_own, s_red[gq * 4 * kTile + tid]);
+    (kXchg ? s_inv : s_min)[tid] = mm_own;   // (kXchg: this rank's slab minima, staged in s_inv for the exchange)
   }
-  __syncthreads();
+  if (kXchg) __syncthreads();
   const int warp = tid >> 5, lane = tid & 31;
   const int q4 = (tid & 7) * 4;
   // 128-bit stores need 16-byte aligned rows
@@ -1409,7 +1412,7 @@ __device__ __forceinline__ void tile_back_half(const FusedArgs& a, const TileId&
       xchg_collect<false>(a, 0, tile, warp, lane, s_min);
       bar_sync_128();
     }
-    const float mm = s_min[warp * kTile + lane];
+    const float mm = kXchg ? s_min[warp * kTile + lane] : mm_own;
     float den = den_chain<L, kExact>(a, warp, lane, mm, s_par, s_cen, s_lut);
     if (kXchg) {
       s_red[warp * kTile + lane] = den;        // (the per-group minima are dead since the barrier above)
