@@ -158,6 +158,22 @@ ms_prep_kernel(const uint8_t* __restrict__ left, const uint8_t* __restrict__ rig
   const int n = blockIdx.z >> 1, side = blockIdx.z & 1;
   if (xp >= g.Wp) return;
   const int H = g.H, W = g.W;
+  // A row band (the caller shards a frame by rows): the tiles only read padded rows [y0 + bh, y0 + bh + h + 3]
+  // (the band's rows and the ZSAD halo); every other row only feeds the SAD-of-Sobel table, whose scan walks down
+  // from row 0 -- and nothing below the band's last scan band is read at all.
+  const bool feat_row = yp >= g.y0 + g.bh && yp <= g.y0 + g.bh + g.h + 2 * kPadT - 1;
+  if (!feat_row) {
+    const int Xs = xp - g.padL, Ys = yp - kPadT;
+    if (Ys < 0 || Ys >= H || Xs < 0 || Xs >= W || Ys > g.y0 + g.bh + g.h + 40) return;   // (the last scan band reads 27 rows past the band)
+    const uint8_t* im = (side ? right : left) + (size_t)n * H * W;
+    float sv = 0.f;
+    if (Ys >= 1 && Ys < H - 2 && Xs >= 1 && Xs < W - 2) {
+      const uint8_t* p = im + (size_t)(Ys - 1) * W + (Xs - 1);
+      sv = (float)(((int)p[2] - (int)p[0]) + 2 * ((int)p[W + 2] - (int)p[W]) + ((int)p[2 * W + 2] - (int)p[2 * W]));
+    }
+    (side ? sobR : sobL)[(size_t)n * (H + kSadRowPad) * g.Ws + (size_t)Ys * g.Ws + Xs] = sv;
+    return;
+  }
   const uint8_t* img = (side ? right : left) + (size_t)n * H * W;
   const int X = xp - g.padL, Y = yp - kPadT;
   const bool inside = (X >= 0 && X < W && Y >= 0 && Y < H);
@@ -1038,6 +1054,14 @@ constexpr bool kCenLut = MSN_CEN_LUT != 0;
 #define MSN_BACK_UNROLL 1
 #endif
 constexpr int kBackUnroll = MSN_BACK_UNROLL;   // sweeps of phases 2/3 (measured: 1 is best)
+#ifndef MSN_P3_UNROLL
+#define MSN_P3_UNROLL MSN_BACK_UNROLL
+#endif
+constexpr int kP3Unroll = MSN_P3_UNROLL;
+#ifndef MSN_DEN_BATCH
+#define MSN_DEN_BATCH 8
+#endif
+constexpr int kDenBatch = MSN_DEN_BATCH;       // exponentials evaluated ahead of the denominator's dependent adds
 __device__ __forceinline__ float cen_ch0(int cb, const float* s_lutn) {
   if (kCenLutCh0) return s_lutn[cb];
   const float k = (float)min(cb, 120);
@@ -1187,7 +1211,7 @@ __device__ __forceinline__ void phase3_quads(const float* s_par, const uint8_t* 
   // census minima biased by 2^23 (exact: the minima are integers <= 120), see cen_bytes_as_biased_floats
   const f32x2 mp0[2] = {pk2(8388608.0f + (float)mcx, 8388608.0f + (float)mcy), pk2(8388608.0f + (float)mcz, 8388608.0f + (float)mcw)};
   const f32x2 ip0[2] = {pk2(i0.x, i0.y), pk2(i0.z, i0.w)};
-#pragma unroll(kBackUnroll)
+#pragma unroll(kP3Unroll)
   for (int d = dl; d < D; d += 32) {
     const float* e0 = s_par + d * kTile + q4;
     const uchar4 cb = *reinterpret_cast<const uchar4*>(s_cen + d * kTile + q4);
@@ -1226,31 +1250,32 @@ __device__ __forceinline__ float den_chain(const FusedArgs& a, int warp, int lan
   constexpr int PS = L::PS;
   const int D = a.g.D;
   float den = 0.f;
-  const int Dfull = D & ~7;   // groups of 8 without guards, then a guarded tail
+  constexpr int B = kDenBatch;
+  const int Dfull = D - D % B;   // groups of B without guards, then a guarded tail
   if (warp == 0) {
     const int mc = (mm == kFill) ? 0 : (int)mm;
     const uint8_t* c = s_cen + lane;
-    for (int d0 = 0; d0 < Dfull; d0 += 8, c += 8 * kTile) {
-      float ev[8];
+    for (int d0 = 0; d0 < Dfull; d0 += B, c += B * kTile) {
+      float ev[B];
 #pragma unroll
-      for (int j = 0; j < 8; ++j) ev[j] = cen_e<kCenLutDen, kExact>(c[j * kTile], mc, s_lut, a.k_cen);
+      for (int j = 0; j < B; ++j) ev[j] = cen_e<kCenLutDen, kExact>(c[j * kTile], mc, s_lut, a.k_cen);
 #pragma unroll
-      for (int j = 0; j < 8; ++j) den = __fadd_rn(den, ev[j]);
+      for (int j = 0; j < B; ++j) den = __fadd_rn(den, ev[j]);
     }
     for (int d = Dfull; d < D; ++d, c += kTile) den = __fadd_rn(den, cen_e<kCenLutDen, kExact>(c[0], mc, s_lut, a.k_cen));
   } else {
     const float kq = (warp == 1) ? a.k_ncc : a.k_sad;
     const f32x2 mm2 = pk2(mm, mm), nkq = pk2(-kq, -kq);
     const float* e = s_par + (warp - 1) * PS + lane;
-    for (int d0 = 0; d0 < Dfull; d0 += 8, e += 8 * kTile) {
-      float ev[8];
+    for (int d0 = 0; d0 < Dfull; d0 += B, e += B * kTile) {
+      float ev[B];
 #pragma unroll
-      for (int j = 0; j < 8; j += 2) {
+      for (int j = 0; j < B; j += 2) {
         if (kExact) { ev[j] = aml_e_exact(e[j * kTile], mm, -kq); ev[j + 1] = aml_e_exact(e[(j + 1) * kTile], mm, -kq); }
         else aml_e2(pk2(e[j * kTile], e[(j + 1) * kTile]), mm2, nkq, ev[j], ev[j + 1]);
       }
 #pragma unroll
-      for (int j = 0; j < 8; ++j) den = __fadd_rn(den, ev[j]);
+      for (int j = 0; j < B; ++j) den = __fadd_rn(den, ev[j]);
     }
     for (int d = Dfull; d < D; ++d, e += kTile) den = __fadd_rn(den, aml_t<kExact>(e[0], mm, kq));
   }
