@@ -437,6 +437,9 @@ __device__ __forceinline__ f32x2 abs2(f32x2 v) {
   return pk2(fabsf(lo), fabsf(hi));
 }
 
+#ifdef MSN_EXP_NOPOPC   // timing experiment only (wrong results): what the census popcounts cost
+#define __popc(x) ((int)((x) & 31u))
+#endif
 struct TileId {
   int n, y, x0;   // y: row of the cropped image
   int yl;     // row inside this launch's band (output indexing)
@@ -1431,6 +1434,12 @@ __device__ __forceinline__ void tile_back_half(const FusedArgs& a, const TileId&
   T* orow = reinterpret_cast<T*>(a.out) + ((size_t)t.n * a.out_channels + a.out_ch0) * chan + (size_t)(a.out_d0 + t.sub0) * plane + (size_t)t.yl * g.w + (t.x0 + q4);
   const int nlive = min(4, g.w - (t.x0 + q4));  // live pixels of this quad (<= 0: none)
   const bool vec = vec_ok && nlive == 4;
+#ifdef MSN_EXP_LINEAR   // timing experiment only (scrambled output): every tile writes ONE contiguous 8 x D x 128 B block
+  const size_t plane_x = kTile, chan_x = (size_t)D * kTile;
+  orow = reinterpret_cast<T*>(a.out) + (size_t)tile * 8 * D * kTile + q4;
+#define plane plane_x
+#define chan chan_x
+#endif
   if (warp < 4) {
     if (kXchg) {
       xchg_publish(a, 0, tile, t.v, warp, lane, s_inv);
@@ -1438,7 +1447,11 @@ __device__ __forceinline__ void tile_back_half(const FusedArgs& a, const TileId&
       bar_sync_128();
     }
     const float mm = kXchg ? s_min[warp * kTile + lane] : mm_own;
+#ifdef MSN_EXP_NOCHAIN   // timing experiment only: no denominator chain
+    float den = 1.0f + mm * 1e-30f;
+#else
     float den = den_chain<L, kExact>(a, warp, lane, mm, s_par, s_cen, s_lut);
+#endif
     if (kXchg) {
       s_red[warp * kTile + lane] = den;        // (the per-group minima are dead since the barrier above)
       bar_sync_128();
@@ -1451,14 +1464,23 @@ __device__ __forceinline__ void tile_back_half(const FusedArgs& a, const TileId&
   }
   else {
     // channels 0-3: thread = (pixel quad, d), 16 disparities per sweep of the four warps
+#ifndef MSN_EXP_NOCH03   // timing experiment only: channels 0-3 are never written
     if (vec) store_ch03<true>(s_par, s_cen, s_lutn, PS, q4, (tid >> 3) - 16, D, orow, plane, chan, nlive);
     else store_ch03<false>(s_par, s_cen, s_lutn, PS, q4, (tid >> 3) - 16, D, orow, plane, chan, nlive);
+#endif
     if (a.wta_idx) wta_scan<L>(a, t, warp - 4, lane, s_par, s_cen);
   }
   __syncthreads();
+#ifdef MSN_EXP_NOP3      // timing experiment only: channels 4-7 are never written
+  return;
+#endif
   const int dl = tid >> 3;
   if (vec) phase3_quads<true, T, kExact>(s_par, s_cen, s_lut, s_min, s_inv, PS, q4, dl, D, orow + 4 * chan, plane, chan, nlive, a.k_cen, a.k_ncc, a.k_sad);
   else phase3_quads<false, T, kExact>(s_par, s_cen, s_lut, s_min, s_inv, PS, q4, dl, D, orow + 4 * chan, plane, chan, nlive, a.k_cen, a.k_ncc, a.k_sad);
+#ifdef MSN_EXP_LINEAR
+#undef plane
+#undef chan
+#endif
 }
 
 // Back half of a tile for DISPARITY-SLAB SHARDING (phase A of slab.cu): the AML
