@@ -1241,6 +1241,15 @@ __device__ __forceinline__ void phase3_quads(const float* s_par, const uint8_t* 
       p3_quad(v3, mp3, ip3, nk2, a3);
     }
     store_quads<kVec>(arow + (size_t)d * plane, chan, nlive, a0, a1, a2, a3);
+#ifdef MSN_FUSE_CH03   // A/B: channels 0-3 from the same loads in this sweep instead of warps 4-7 during the chain
+    {
+      const float4 c0 = cen_ch0_quad(*reinterpret_cast<const uint32_t*>(&cb));
+      const float4 c1 = make_float4(normalise_cost(v1.x, 1), normalise_cost(v1.y, 1), normalise_cost(v1.z, 1), normalise_cost(v1.w, 1));
+      const float4 c2 = make_float4(normalise_cost(v2.x, 2), normalise_cost(v2.y, 2), normalise_cost(v2.z, 2), normalise_cost(v2.w, 2));
+      const float4 c3 = make_float4(normalise_cost(v3.x, 3), normalise_cost(v3.y, 3), normalise_cost(v3.z, 3), normalise_cost(v3.w, 3));
+      store_quads<kVec>(arow - 4 * chan + (size_t)d * plane, chan, nlive, c0, c1, c2, c3);
+    }
+#endif
   }
 }
 
@@ -1464,7 +1473,7 @@ __device__ __forceinline__ void tile_back_half(const FusedArgs& a, const TileId&
   }
   else {
     // channels 0-3: thread = (pixel quad, d), 16 disparities per sweep of the four warps
-#ifndef MSN_EXP_NOCH03   // timing experiment only: channels 0-3 are never written
+#if !defined(MSN_EXP_NOCH03) && !defined(MSN_FUSE_CH03)   // (NOCH03: timing experiment only, channels 0-3 never written)
     if (vec) store_ch03<true>(s_par, s_cen, s_lutn, PS, q4, (tid >> 3) - 16, D, orow, plane, chan, nlive);
     else store_ch03<false>(s_par, s_cen, s_lutn, PS, q4, (tid >> 3) - 16, D, orow, plane, chan, nlive);
 #endif
