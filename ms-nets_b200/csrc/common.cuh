@@ -106,7 +106,8 @@ int launch_sadsob_n(const float* L, const float* R, int N, int H, int W, int Dn,
 constexpr int kSadRowPad = 32;  // zero rows below an image that enable the unguarded window-5 scan
 int sadsob_fast_pitch(int W);    // 1024 / 2048 / 4096, or 0 when W is too wide
 int launch_sadsob5_padded(const float* L, const float* R, int N, int H, int W, int Dn, int d_begin, float* out,
-                          void* workspace, cudaStream_t s, bool d_inner = false, int row_lo = 0, int row_hi = -1);
+                          void* workspace, cudaStream_t s, bool d_inner = false, int row_lo = 0, int row_hi = -1,
+                          bool tall_ok = true);
 // row_lo / row_hi: only output rows [row_lo, row_hi) of the (bordered) image are needed (a row band of a frame
 // sharded by rows): the band prefixes still start at row 0 -- the table of a row depends on every row above it --
 // but only the bands that hold those rows are scanned.

@@ -164,7 +164,7 @@ ms_prep_kernel(const uint8_t* __restrict__ left, const uint8_t* __restrict__ rig
   const bool feat_row = yp >= g.y0 + g.bh && yp <= g.y0 + g.bh + g.h + 2 * kPadT - 1;
   if (!feat_row) {
     const int Xs = xp - g.padL, Ys = yp - kPadT;
-    if (Ys < 0 || Ys >= H || Xs < 0 || Xs >= W || Ys > g.y0 + g.bh + g.h + 40) return;   // (the last scan band reads 27 rows past the band)
+    if (Ys < 0 || Ys >= H || Xs < 0 || Xs >= W || Ys > g.y0 + g.bh + g.h + 64) return;   // (the last scan band reads up to 59 rows past the band)
     const uint8_t* im = (side ? right : left) + (size_t)n * H * W;
     float sv = 0.f;
     if (Ys >= 1 && Ys < H - 2 && Xs >= 1 && Xs < W - 2) {
@@ -273,6 +273,7 @@ struct FusedArgs {
   const float* first4;           // kModeRight: [N][4] raw costs that stand in where x + d >= w (get_right_cost's fill)
   float* first4_out;             // full mode, both views requested: where the left-view launch leaves those four
   int out_ch0;                   // first channel this launch writes (8 for the right view)
+  int tma_out;                   // channels 5-7 leave through the TMA engine (tile_back_half), see there
   const float* luts;    // [128] + [256], see ms_prep_kernel
   const float* sadsob;  // see FusedWs
   float* out;           // [N][8][D][h][w]
@@ -390,6 +391,17 @@ __device__ __forceinline__ void tma_load_3d(void* dst, const CUtensorMap* map, i
       "cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3, %4}], [%5];" ::"r"(
           smem_u32(dst)), "l"(reinterpret_cast<uint64_t>(map)), "r"(c0), "r"(c1), "r"(c2), "r"(smem_u32(bar)) : "memory");
 }
+
+// 3-D tiled tensor copy shared -> global (bulk async-group completion); elements outside the tensor are not written
+__device__ __forceinline__ void tma_store_3d(const CUtensorMap* map, const void* src, int c0, int c1, int c2) {
+  asm volatile("cp.async.bulk.tensor.3d.global.shared::cta.bulk_group [%0, {%2, %3, %4}], [%1];" ::"l"(
+                   reinterpret_cast<uint64_t>(map)), "r"(smem_u32(src)), "r"(c0), "r"(c1), "r"(c2) : "memory");
+}
+__device__ __forceinline__ void tma_store_commit_and_wait_read() {   // shared memory may be reused / released after this
+  asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+  asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+}
+__device__ __forceinline__ void fence_proxy_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
 
 // ---- packed fp32x2 arithmetic (Blackwell FADD2: two IEEE round-to-nearest adds per issue slot;
 //      operand B may be a scalar register broadcast to both halves, |x| is an operand modifier)
@@ -1061,6 +1073,10 @@ constexpr int kBackUnroll = MSN_BACK_UNROLL;   // sweeps of phases 2/3 (measured
 #define MSN_P3_UNROLL MSN_BACK_UNROLL
 #endif
 constexpr int kP3Unroll = MSN_P3_UNROLL;
+#ifndef MSN_TMA_OUT
+#define MSN_TMA_OUT 0      // 1: build the TMA road for channels 5-7 (tile_back_half, kTmaOk); then MSNETS_TMA_OUT=1 selects it
+#endif
+constexpr bool kTmaOutBuilt = MSN_TMA_OUT != 0;
 #ifndef MSN_DEN_BATCH
 #define MSN_DEN_BATCH 8
 #endif
@@ -1193,8 +1209,8 @@ __device__ __forceinline__ void p3_quad_exact(const float4& v, const float4& m, 
 
 // Channels 4-7 = exp(-(c-m)^2/sigma) / den for thread = (pixel quad q4, disparities dl, dl+32, ...),
 // exponentials recomputed from the parked costs, 128-bit row segments.
-template <bool kVec, class T, bool kExact = false>
-__device__ __forceinline__ void phase3_quads(const float* s_par, const uint8_t* s_cen, const float* s_lut,
+template <bool kVec, class T, bool kExact = false, bool kTmaOut = false>
+__device__ __forceinline__ void phase3_quads(float* s_par, const uint8_t* s_cen, const float* s_lut,
                                              const float* s_min, const float* s_inv, int PS, int q4, int dl, int D,
                                              T* arow, size_t plane, size_t chan, int nlive, float k0, float k1, float k2) {
   const float4 m_cen4 = *reinterpret_cast<const float4*>(s_min + q4);
@@ -1216,7 +1232,7 @@ __device__ __forceinline__ void phase3_quads(const float* s_par, const uint8_t* 
   const f32x2 ip0[2] = {pk2(i0.x, i0.y), pk2(i0.z, i0.w)};
 #pragma unroll(kP3Unroll)
   for (int d = dl; d < D; d += 32) {
-    const float* e0 = s_par + d * kTile + q4;
+    float* e0 = s_par + d * kTile + q4;
     const uchar4 cb = *reinterpret_cast<const uchar4*>(s_cen + d * kTile + q4);
     const float4 v1 = *reinterpret_cast<const float4*>(e0);
     const float4 v2 = *reinterpret_cast<const float4*>(e0 + PS);
@@ -1240,7 +1256,23 @@ __device__ __forceinline__ void phase3_quads(const float* s_par, const uint8_t* 
       p3_quad(v2, mp2, ip2, nk2, a2);
       p3_quad(v3, mp3, ip3, nk2, a3);
     }
-    store_quads<kVec>(arow + (size_t)d * plane, chan, nlive, a0, a1, a2, a3);
+    if (kTmaOut) {
+      // channels 5-7 replace the parked costs they were made from (this thread is the only reader and writer of the
+      // quad); the tile's three planes leave through the TMA engine after the sweep.  Channel 4 has no float plane.
+      *reinterpret_cast<float4*>(e0) = a1;
+      *reinterpret_cast<float4*>(e0 + PS) = a2;
+      *reinterpret_cast<float4*>(e0 + 2 * PS) = a3;
+      T* o4 = arow + (size_t)d * plane;
+      if (kVec) st_stream4(o4, a0);
+      else {
+        const float c4[4] = {a0.x, a0.y, a0.z, a0.w};
+#pragma unroll
+        for (int i = 0; i < 4; ++i)
+          if (i < nlive) st_stream(o4 + i, c4[i]);
+      }
+    } else {
+      store_quads<kVec>(arow + (size_t)d * plane, chan, nlive, a0, a1, a2, a3);
+    }
 #ifdef MSN_FUSE_CH03   // A/B: channels 0-3 from the same loads in this sweep instead of warps 4-7 during the chain
     {
       const float4 c0 = cen_ch0_quad(*reinterpret_cast<const uint32_t*>(&cb));
@@ -1417,10 +1449,16 @@ __device__ __forceinline__ void wta_scan(const FusedArgs& a, const TileId& t, in
 // part of the channel 0-3 stores to the chain warps statically or through a work counter (no
 // gain: the halves are already balanced), a warp-specialised persistent producer/consumer
 // kernel (15 % slower).
-template <class L, bool kXchg, class T = float, bool kExact = false>
+// kTmaOk (the fp32 one-pass forms): when the launcher built a tensor map over the volume (a.tma_out), phase 3 writes
+// channels 5-7 over the parked costs they come from and one thread hands the three [D][32] planes to the TMA engine
+// (cp.async.bulk.tensor, shared -> global, clipped at the image edge).  Reason (profiles/micro/store_pattern.cu): an
+// SM's LSU store path takes about 32 bytes per clock, and both sweeps of the back half run exactly at that rate --
+// 98 KB in ~3 k cycles each; the bulk copies take another road.
+template <class L, bool kXchg, class T = float, bool kExact = false, bool kTmaOk = false>
 __device__ __forceinline__ void tile_back_half(const FusedArgs& a, const TileId& t, long long tile, int tid,
-                                               const float* s_par, const uint8_t* s_cen, float* s_red, float* s_min,
-                                               float* s_inv, const float* s_lut, const float* s_lutn) {
+                                               float* s_par, const uint8_t* s_cen, float* s_red, float* s_min,
+                                               float* s_inv, const float* s_lut, const float* s_lutn,
+                                               const CUtensorMap* out_map = nullptr) {
   constexpr int PS = L::PS;
   const FusedGeom& g = a.g;
   const int D = g.D;
@@ -1484,6 +1522,19 @@ __device__ __forceinline__ void tile_back_half(const FusedArgs& a, const TileId&
   return;
 #endif
   const int dl = tid >> 3;
+  if (kTmaOk && kTmaOutBuilt && a.tma_out) {
+    if (vec) phase3_quads<true, T, kExact, true>(s_par, s_cen, s_lut, s_min, s_inv, PS, q4, dl, D, orow + 4 * chan, plane, chan, nlive, a.k_cen, a.k_ncc, a.k_sad);
+    else phase3_quads<false, T, kExact, true>(s_par, s_cen, s_lut, s_min, s_inv, PS, q4, dl, D, orow + 4 * chan, plane, chan, nlive, a.k_cen, a.k_ncc, a.k_sad);
+    fence_proxy_async_smem();          // this thread's shared-memory writes -> visible to the async (TMA) proxy
+    __syncthreads();
+    if (tid == 0) {
+      const int z0 = (t.n * a.out_channels + a.out_ch0 + 5) * a.out_D + a.out_d0 + t.sub0;
+#pragma unroll
+      for (int m = 0; m < 3; ++m) tma_store_3d(out_map, s_par + m * PS, t.x0, t.yl, z0 + m * a.out_D);
+      tma_store_commit_and_wait_read();   // the CTA's shared memory must outlive the engine's reads
+    }
+    return;
+  }
   if (vec) phase3_quads<true, T, kExact>(s_par, s_cen, s_lut, s_min, s_inv, PS, q4, dl, D, orow + 4 * chan, plane, chan, nlive, a.k_cen, a.k_ncc, a.k_sad);
   else phase3_quads<false, T, kExact>(s_par, s_cen, s_lut, s_min, s_inv, PS, q4, dl, D, orow + 4 * chan, plane, chan, nlive, a.k_cen, a.k_ncc, a.k_sad);
 #ifdef MSN_EXP_LINEAR
@@ -1569,7 +1620,8 @@ __device__ __forceinline__ void tile_slab_a(const FusedArgs& a, const TileId& t,
 // kMode: kModeFull the whole volume; kModeSlabA stop after phase 1 and emit what slab.cu's phase A emits
 // (tile_slab_a); kModeXchg a rank's disparity slab, minima and denominators traded inside the tile.
 template <int DMAX, bool kTma, int kMode>
-__device__ __forceinline__ void fused_tile(const FusedArgs& a, const CUtensorMap& sad_map, long long tile, int sub) {
+__device__ __forceinline__ void fused_tile(const FusedArgs& a, const CUtensorMap& sad_map, const CUtensorMap& out_map,
+                                           long long tile, int sub) {
   using L = Lay<DMAX, kSlack>;
   constexpr int NT = 256;
   constexpr int PS = L::PS;
@@ -1623,7 +1675,7 @@ __device__ __forceinline__ void fused_tile(const FusedArgs& a, const CUtensorMap
     cp_async_wait_all();
     finish_right<L>(s_par, s_cen, s_red, ro, a.first4 + 4 * t.n, px, grp, d_lo, d_end);
     __syncthreads();
-    tile_back_half<L, false>(a, t, tile, tid, s_par, s_cen, s_red, s_min, s_inv, s_lut, s_lutn);
+    tile_back_half<L, false, float, false, true>(a, t, tile, tid, s_par, s_cen, s_red, s_min, s_inv, s_lut, s_lutn, &out_map);
     return;
   }
   if (kTma) {
@@ -1669,18 +1721,20 @@ __device__ __forceinline__ void fused_tile(const FusedArgs& a, const CUtensorMap
   if (kMode == kModeSlabA) tile_slab_a<L>(a, t, tid, s_par, s_cen, s_red, s_lutn);
   else if (kMode == kModeExact) tile_back_half<L, false, float, true>(a, t, tile, tid, s_par, s_cen, s_red, s_min, s_inv, s_lut, s_lutn);
   else if (kMode == kModeBf16) tile_back_half<L, false, __nv_bfloat16>(a, t, tile, tid, s_par, s_cen, s_red, s_min, s_inv, s_lut, s_lutn);
-  else tile_back_half<L, kMode == kModeXchg>(a, t, tile, tid, s_par, s_cen, s_red, s_min, s_inv, s_lut, s_lutn);
+  else if (kMode == kModeXchg) tile_back_half<L, true>(a, t, tile, tid, s_par, s_cen, s_red, s_min, s_inv, s_lut, s_lutn);
+  else tile_back_half<L, false, float, false, true>(a, t, tile, tid, s_par, s_cen, s_red, s_min, s_inv, s_lut, s_lutn, &out_map);
 }
 
 template <int DMAX, bool kTma, int kMode>
 __global__ void __launch_bounds__(256, 2)
-ms_fused_kernel(const FusedArgs a, const __grid_constant__ CUtensorMap sad_map) {
+ms_fused_kernel(const FusedArgs a, const __grid_constant__ CUtensorMap sad_map,
+                const __grid_constant__ CUtensorMap out_map) {
   if (kMode == kModeXchg) {
     // CTA = (tile, sub-slab), sub-slab fastest: the CTAs that wait for each other's minima are dispatched
     // together.  A sub-slab is a virtual rank: its own disparity offset, its own row in the exchange tables.
-    fused_tile<DMAX, kTma, kMode>(a, sad_map, blockIdx.x / (unsigned)a.subs, (int)(blockIdx.x % (unsigned)a.subs));
+    fused_tile<DMAX, kTma, kMode>(a, sad_map, out_map, blockIdx.x / (unsigned)a.subs, (int)(blockIdx.x % (unsigned)a.subs));
   } else {
-    fused_tile<DMAX, kTma, kMode>(a, sad_map, blockIdx.x, 0);
+    fused_tile<DMAX, kTma, kMode>(a, sad_map, out_map, blockIdx.x, 0);
   }
 }
 
@@ -1898,10 +1952,48 @@ static bool sad_tensor_map(const FusedGeom& g, int H, int N, const float* base, 
   return true;
 }
 
+// 3-D tensor map over the output volume [planes = N*C*out_D][h][w] fp32, box 32 x 1 x D: one tile's [D][32] plane of a
+// channel (tile_back_half, kTmaOk).  Needs 16-byte aligned rows and base.
+static bool out_tensor_map(const float* base, int w, int h, long long planes, int D, CUtensorMap* out) {
+  if ((w & 3) || (reinterpret_cast<uintptr_t>(base) & 15) || D > 256 || planes > 2147483647LL) return false;
+  const MapKey key{base, w, h, (int)planes, D, 2};
+  {
+    std::lock_guard<std::mutex> lk(g_map_mu);
+    for (auto& kv : g_maps)
+      if (kv.first == key) {
+        *out = kv.second;
+        return true;
+      }
+  }
+  PFN_encodeTiled enc = get_encode_fn();
+  if (!enc) return false;
+  const cuuint64_t gdim[3] = {(cuuint64_t)w, (cuuint64_t)h, (cuuint64_t)planes};
+  const cuuint64_t gstr[2] = {(cuuint64_t)w * 4, (cuuint64_t)h * w * 4};
+  const cuuint32_t box[3] = {(cuuint32_t)kTile, 1u, (cuuint32_t)D};
+  const cuuint32_t estr[3] = {1u, 1u, 1u};
+  if (enc(out, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3, const_cast<float*>(base), gdim, gstr, box, estr,
+          CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_NONE,
+          CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) != CUDA_SUCCESS)
+    return false;
+  std::lock_guard<std::mutex> lk(g_map_mu);
+  if (g_maps.size() >= 64) g_maps.erase(g_maps.begin());
+  g_maps.emplace_back(key, *out);
+  return true;
+}
+// Opt-in (a -DMSN_TMA_OUT=1 build, profiles/ab_variants.py, and MSNETS_TMA_OUT=1 at run time; the GPU suite passed
+// with it switched on, ragged right edge and both views included): measured at config B the TMA road is 1.2 % SLOWER (0.787 vs 0.778 ms per pair) although it
+// takes three of phase 3's four stores off the LSU path -- the sweep's time does not follow its store traffic any
+// more than its instruction count and the issuing thread's wait at the end of the tile costs.
+static bool tma_out_disabled() {
+  if (!kTmaOutBuilt) return true;   // (a -DMSN_TMA_OUT=1 build; the default library carries no code for it)
+  const char* e = getenv("MSNETS_TMA_OUT");
+  return !(e && e[0] == '1');
+}
+
 // One launch of an instantiation; the dynamic shared-memory opt-in is set once per instantiation
 // and device, not per launch.
 template <int DMAX, bool kTma, int kMode>
-static int launch_inst(const FusedArgs& a, const CUtensorMap& map, long long tiles, cudaStream_t s) {
+static int launch_inst(const FusedArgs& a, const CUtensorMap& map, const CUtensorMap& omap, long long tiles, cudaStream_t s) {
   auto kern = ms_fused_kernel<DMAX, kTma, kMode>;
   constexpr size_t smem = Lay<DMAX, kSlack>::bytes;
   static std::mutex mu;
@@ -1915,7 +2007,7 @@ static int launch_inst(const FusedArgs& a, const CUtensorMap& map, long long til
       if (dev < 64) done_mask |= 1ull << dev;
     }
   }
-  kern<<<(unsigned)(tiles * (kMode == kModeXchg ? a.subs : 1)), 256, smem, s>>>(a, map);
+  kern<<<(unsigned)(tiles * (kMode == kModeXchg ? a.subs : 1)), 256, smem, s>>>(a, map, omap);
   return 0;
 }
 
@@ -2032,7 +2124,7 @@ int launch_ms_fused(const uint8_t* d_left, const uint8_t* d_right, int N, int H,
   if (prof) MSN_CUDA_OK(cudaEventRecord(rec.ev[1], s));
   g.d_inner = subs > 1 ? 1 : 0;   // several sub-slabs in flight: keep a tile's scratch rows on one page
   if (launch_sadsob5_padded(ws.sob[0], ws.sob[1], N, H, W, g.Dl, g.d0, ws.sadsob + g.sxo, ws.sad_ws, s, g.d_inner != 0,
-                            g.y0 + g.bh, g.y0 + g.bh + g.h))
+                            g.y0 + g.bh, g.y0 + g.bh + g.h, xchg == nullptr))
     return 1;
   if (prof) MSN_CUDA_OK(cudaEventRecord(rec.ev[2], s));
 
@@ -2093,6 +2185,13 @@ int launch_ms_fused(const uint8_t* d_left, const uint8_t* d_right, int N, int H,
   bool use_tma = g.D <= 256 && !tma_disabled();
   if (use_tma) use_tma = sad_tensor_map(g, H, N, ws.sadsob, &sad_map);
   a.DC = 2 * (((g.D + kGroups - 1) / kGroups + 1) / 2);   // phase 1 walks disparity pairs
+  // channels 5-7 (and 13-15) through the TMA engine: the fp32 one-pass forms
+  CUtensorMap out_map;
+  memset(&out_map, 0, sizeof(out_map));
+  a.tma_out = 0;
+  if (!exact && !out_bf16 && !xchg && !d_mins && !tma_disabled() && !tma_out_disabled() &&
+      out_tensor_map(d_out, g.w, g.h, (long long)N * a.out_channels * a.out_D, g.D, &out_map))
+    a.tma_out = 1;
   // narrow exchange slabs: two tiles per CTA (ms_slab_x2_kernel)
   if (xchg && use_tma && g.D <= 96 && !x2_disabled()) {
     if (g.D <= 64) { if (launch_x2<64>(a, sad_map, tiles, s)) return 1; }
@@ -2107,11 +2206,11 @@ int launch_ms_fused(const uint8_t* d_left, const uint8_t* d_right, int N, int H,
   }
 #define MSN_FUSED_LAUNCH(DMAX, TMA)                                                \
   {                                                                                \
-    if (exact) { if (launch_inst<DMAX, TMA, kModeExact>(a, sad_map, tiles, s)) return 1; } \
-    else if (out_bf16) { if (launch_inst<DMAX, TMA, kModeBf16>(a, sad_map, tiles, s)) return 1; } \
-    else if (xchg) { if (launch_inst<DMAX, TMA, kModeXchg>(a, sad_map, tiles, s)) return 1; } \
-    else if (d_mins) { if (launch_inst<DMAX, TMA, kModeSlabA>(a, sad_map, tiles, s)) return 1; } \
-    else { if (launch_inst<DMAX, TMA, kModeFull>(a, sad_map, tiles, s)) return 1; }    \
+    if (exact) { if (launch_inst<DMAX, TMA, kModeExact>(a, sad_map, out_map, tiles, s)) return 1; } \
+    else if (out_bf16) { if (launch_inst<DMAX, TMA, kModeBf16>(a, sad_map, out_map, tiles, s)) return 1; } \
+    else if (xchg) { if (launch_inst<DMAX, TMA, kModeXchg>(a, sad_map, out_map, tiles, s)) return 1; } \
+    else if (d_mins) { if (launch_inst<DMAX, TMA, kModeSlabA>(a, sad_map, out_map, tiles, s)) return 1; } \
+    else { if (launch_inst<DMAX, TMA, kModeFull>(a, sad_map, out_map, tiles, s)) return 1; }    \
   }
 #define MSN_FUSED_CASE(DMAX)                                                       \
   if (g.D <= DMAX) {                                                               \
@@ -2132,7 +2231,7 @@ int launch_ms_fused(const uint8_t* d_left, const uint8_t* d_right, int N, int H,
     a.first4_out = nullptr;
     a.out_ch0 = 8;
 #define MSN_RIGHT_CASE(DMAX) \
-  if (g.D <= DMAX) { if (launch_inst<DMAX, true, kModeRight>(a, sad_map, tiles, s)) return 1; } else
+  if (g.D <= DMAX) { if (launch_inst<DMAX, true, kModeRight>(a, sad_map, out_map, tiles, s)) return 1; } else
     MSN_RIGHT_CASE(64)
     MSN_RIGHT_CASE(128)
     MSN_RIGHT_CASE(192)

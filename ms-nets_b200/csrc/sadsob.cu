@@ -21,6 +21,8 @@
 //
 // A band holds 32 table rows, i.e. 32 - wsize output rows (the box needs rows i
 // and i + wsize), so bands overlap by wsize rows.
+#include <stdlib.h>
+
 #include "common.cuh"
 
 namespace msn {
@@ -352,6 +354,141 @@ sadsob_scan5_kernel(const float* __restrict__ L, const float* __restrict__ R, in
   }
 }
 
+// ---------------------------------------------------------------------------
+// The same sweep over bands of 64 table rows = 59 origin rows: neighbouring bands still share five table rows, but
+// that is 8 % of a band instead of 16 %, and a lane owns TWO rows in the horizontal step (two independent chains).
+// By wavefront count (the kernel is bound by the L1 data pipe) a tile of 59 x 32 costs 127 global-load, 59
+// global-store and 330 shared wavefronts = 8.75 per output row against 9.44.  A band whose second half holds no
+// origin row (the last band of an image, a row range) is processed as a 32-row band.
+constexpr int kS5Rows2 = 2 * kSadTile;          // 64 table rows
+constexpr int kS5RB2 = kS5Rows2 - kS5W;          // 59 origin rows per band
+
+template <int SP, bool kDInner>
+__global__ void __launch_bounds__(kS5Warps * 32, 4)
+sadsob_scan5x2_kernel(const float* __restrict__ L, const float* __restrict__ R, int H, int W, int Dn, int d_begin,
+                      int NB, int b_min, size_t img_stride, const float* __restrict__ Vb, float* __restrict__ out,
+                      size_t out_stride) {
+  __shared__ float sT[kS5Warps][kS5Rows2 * kS5Stride];
+  constexpr int RB = kS5RB2;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int job = blockIdx.x * kS5Warps + warp;
+  const int nbs = NB - b_min;
+  if (job >= Dn * nbs) return;
+  const int dd = kDInner ? job % Dn : job / nbs, b = b_min + (kDInner ? job / Dn : job % nbs), n = blockIdx.z;
+  const int d = d_begin + dd;
+  const int IW = W + 1;
+  const int i0 = b * RB;
+  float* T = sT[warp];
+  const float* Ln = L + n * img_stride + (size_t)i0 * SP;
+  const float* Rn = R + n * img_stride + (size_t)i0 * SP - d;
+  const float* vb = Vb + (((size_t)n * Dn + dd) * NB + b) * IW;
+  const size_t row_stride = kDInner ? (size_t)Dn * SP : (size_t)SP;
+  float* o = kDInner ? out + n * out_stride + ((size_t)(i0 + 2) * Dn + dd) * SP + 2
+                     : out + n * out_stride + (size_t)dd * H * SP + (size_t)(i0 + 2) * SP + 2;
+  const int rmax = min(RB, H - kS5W - i0);          // origin rows produced by this band
+  const bool two = rmax > kSadTile - kS5W;          // the second half holds origin rows (else: a 32-row band)
+
+  const int t0 = d / kSadTile, t1 = (W - 1) / kSadTile;
+  float s0 = 0.f, s1 = 0.f;                         // horizontal carries of table rows i0 + lane, i0 + 32 + lane
+  float h0[kS5W] = {0.f, 0.f, 0.f, 0.f, 0.f}, h1[kS5W] = {0.f, 0.f, 0.f, 0.f, 0.f};   // their last five S values
+  float* trow0 = T + lane * kS5Stride;
+  float* trow1 = trow0 + kSadTile * kS5Stride;
+  for (int t = t0; t <= t1; ++t) {
+    // (a) lanes own table columns: vertical prefix, 31 (+ 32) image rows, loads first, then the chain
+    const int j = t * kSadTile + lane + 1;
+    const int jc = j - 1;
+    float v = (j < IW) ? __ldg(vb + j) : 0.f;
+    const bool edge = (t == t0 || t == t1);
+    const bool active = (j < IW) && (jc >= d);
+    const int jsafe = edge ? min(max(jc, d), W - 1) : jc;      // masked lanes load a valid address
+    const float* lp = Ln + jsafe;
+    const float* rp = Rn + jsafe;
+    {
+      float av[kSadTile - 1];
+#pragma unroll
+      for (int r = 0; r < kSadTile - 1; ++r) {
+        const float x = absdiff_rn(__ldg(lp + r * SP), __ldg(rp + r * SP));
+        av[r] = (!edge || active) ? x : 0.f;
+      }
+      T[kS5W + lane] = v;
+#pragma unroll
+      for (int r = 1; r < kSadTile; ++r) {
+        v = __fadd_rn(v, av[r - 1]);
+        T[r * kS5Stride + kS5W + lane] = v;
+      }
+    }
+    if (two) {
+      float av[kSadTile];
+#pragma unroll
+      for (int r = 0; r < kSadTile; ++r) {
+        const float x = absdiff_rn(__ldg(lp + (kSadTile - 1 + r) * SP), __ldg(rp + (kSadTile - 1 + r) * SP));
+        av[r] = (!edge || active) ? x : 0.f;
+      }
+#pragma unroll
+      for (int r = 0; r < kSadTile; ++r) {
+        v = __fadd_rn(v, av[r]);
+        T[(kSadTile + r) * kS5Stride + kS5W + lane] = v;
+      }
+    }
+    __syncwarp();
+    // (b) lanes own table rows lane and 32 + lane: halo from registers, two horizontal chains in place
+#pragma unroll
+    for (int k = 0; k < kS5W; ++k) trow0[k] = h0[k];
+    if (two) {
+#pragma unroll
+      for (int k = 0; k < kS5W; ++k) trow1[k] = h1[k];
+#pragma unroll
+      for (int c = 0; c < kSadTile; ++c) {
+        s0 = __fadd_rn(s0, trow0[kS5W + c]);
+        s1 = __fadd_rn(s1, trow1[kS5W + c]);
+        trow0[kS5W + c] = s0;
+        trow1[kS5W + c] = s1;
+        if (c >= kSadTile - kS5W) { h0[c - (kSadTile - kS5W)] = s0; h1[c - (kSadTile - kS5W)] = s1; }
+      }
+    } else {
+#pragma unroll
+      for (int c = 0; c < kSadTile; ++c) {
+        s0 = __fadd_rn(s0, trow0[kS5W + c]);
+        trow0[kS5W + c] = s0;
+        if (c >= kSadTile - kS5W) h0[c - (kSadTile - kS5W)] = s0;
+      }
+    }
+    __syncwarp();
+    // (c) lanes own origin columns: out(r) = ((S[r+5][j+5] - S[r+5][j]) - S[r][j+5]) + S[r][j]
+    const int jo = t * kSadTile + 1 - kS5W + lane;
+    if (jo >= d && jo < W - kS5W) {
+      float lo[kS5W], hi[kS5W];
+#pragma unroll
+      for (int r = 0; r < kS5W; ++r) {
+        lo[r] = T[r * kS5Stride + lane];
+        hi[r] = T[r * kS5Stride + lane + kS5W];
+      }
+      float* op = o + jo;
+#pragma unroll
+      for (int r = 0; r < kSadTile - kS5W; ++r) {
+        const float bl = T[(r + kS5W) * kS5Stride + lane];
+        const float br = T[(r + kS5W) * kS5Stride + lane + kS5W];
+        const float val = __fadd_rn(__fsub_rn(__fsub_rn(br, bl), hi[r % kS5W]), lo[r % kS5W]);
+        if (r < rmax) st_stream(kDInner ? op + r * row_stride : op + r * SP, val);
+        lo[r % kS5W] = bl;
+        hi[r % kS5W] = br;
+      }
+      if (two) {
+#pragma unroll
+        for (int r = kSadTile - kS5W; r < RB; ++r) {
+          const float bl = T[(r + kS5W) * kS5Stride + lane];
+          const float br = T[(r + kS5W) * kS5Stride + lane + kS5W];
+          const float val = __fadd_rn(__fsub_rn(__fsub_rn(br, bl), hi[r % kS5W]), lo[r % kS5W]);
+          if (r < rmax) st_stream(kDInner ? op + r * row_stride : op + r * SP, val);
+          lo[r % kS5W] = bl;
+          hi[r % kS5W] = br;
+        }
+      }
+    }
+    __syncwarp();
+  }
+}
+
 static inline void sadsob_geom(int H, int wsize, int* RB, int* NB) {
   *RB = kSadTile - wsize;
   const int rows = H - wsize;  // origin rows i in [0, H - wsize)
@@ -403,12 +540,22 @@ int launch_sadsob_n(const float* L, const float* R, int N, int H, int W, int Dn,
 int sadsob_fast_pitch(int W) { return W <= 1024 ? 1024 : W <= 2048 ? 2048 : W <= 4096 ? 4096 : 0; }
 
 int launch_sadsob5_padded(const float* L, const float* R, int N, int H, int W, int Dn, int d_begin, float* out,
-                          void* workspace, cudaStream_t s, bool d_inner, int row_lo, int row_hi) {
+                          void* workspace, cudaStream_t s, bool d_inner, int row_lo, int row_hi, bool tall_ok) {
   const int SP = sadsob_fast_pitch(W);
   MSN_REQUIRE(SP > 0, "sadsob: W=%d too wide for the padded window-5 scan", W);
   int RB, NB;
   sadsob_geom(H, kS5W, &RB, &NB);
   if (NB <= 0 || W - kS5W <= 0 || Dn <= 0) return 0;
+  // bands of 64 table rows (sadsob_scan5x2_kernel) unless MSNETS_SCAN32=1 asks for the 32-row form
+  // (tall_ok = false: launches of the slab exchange.  Their tiles WAIT for other ranks; when those ranks are other
+  // streams of the same GPU -- the virtual-rank tests -- a waiting kernel's CTAs leave 27 KB of shared memory per SM,
+  // which the 32-row form's blocks fit into and the 64-row form's 38 KB do not: the peers' scans would never run.)
+  static const bool tall_env = [] { const char* e = getenv("MSNETS_SCAN32"); return !(e && e[0] == '1'); }();
+  const bool tall = tall_env && tall_ok;
+  if (tall) {
+    RB = kS5RB2;
+    NB = (H - kS5W + RB - 1) / RB;
+  }
   // band b holds output rows [b*RB + 2, b*RB + 2 + RB): the bands a row range needs
   int b_min = 0;
   if (row_hi >= 0) {
@@ -431,7 +578,10 @@ int launch_sadsob5_padded(const float* L, const float* R, int N, int H, int W, i
   dim3 g5(div_up((long long)Dn * nbs, kS5Warps), 1, N);
 #define MSN_SCAN5(P)                                                                                             \
   {                                                                                                              \
-    if (d_inner) sadsob_scan5_kernel<P, true><<<g5, kS5Warps * 32, 0, s>>>(L, R, H, W, Dn, d_begin, NB, b_min, img_stride, Vb, out, out_stride); \
+    if (tall) {                                                                                                  \
+      if (d_inner) sadsob_scan5x2_kernel<P, true><<<g5, kS5Warps * 32, 0, s>>>(L, R, H, W, Dn, d_begin, NB, b_min, img_stride, Vb, out, out_stride); \
+      else sadsob_scan5x2_kernel<P, false><<<g5, kS5Warps * 32, 0, s>>>(L, R, H, W, Dn, d_begin, NB, b_min, img_stride, Vb, out, out_stride);        \
+    } else if (d_inner) sadsob_scan5_kernel<P, true><<<g5, kS5Warps * 32, 0, s>>>(L, R, H, W, Dn, d_begin, NB, b_min, img_stride, Vb, out, out_stride); \
     else sadsob_scan5_kernel<P, false><<<g5, kS5Warps * 32, 0, s>>>(L, R, H, W, Dn, d_begin, NB, b_min, img_stride, Vb, out, out_stride);        \
   }
   if (SP == 1024) MSN_SCAN5(1024)

@@ -8,10 +8,11 @@
 #include <cstdio>
 #include <cuda_runtime.h>
 template <int MODE>
-__global__ void __launch_bounds__(256, 2) k(float* out, int N, int D, int h, int w) {
+__global__ void __launch_bounds__(256, 2) k(float* out, int N, int D, int h, int w, int n_tiles) {
   extern __shared__ float sm[];
   const int tiles_x = w / 32;
-  int tile = blockIdx.x;
+  for (int tile0 = blockIdx.x; tile0 < n_tiles; tile0 += gridDim.x) {   // (one tile per CTA when the grid covers them all)
+  int tile = tile0;
   const int xt = tile % tiles_x; tile /= tiles_x;
   const int y = tile % h, n = tile / h;
   const size_t plane = (size_t)h * w, chan = plane * D;
@@ -21,7 +22,7 @@ __global__ void __launch_bounds__(256, 2) k(float* out, int N, int D, int h, int
   const float v = sm[0] + tid;
   if (MODE == 0 || MODE == 2) {
     const int q4 = (tid & 7) * 4;
-    float* base = (MODE == 2) ? out + (size_t)blockIdx.x * 8 * D * 32 + q4
+    float* base = (MODE == 2) ? out + (size_t)tile0 * 8 * D * 32 + q4
                               : out + (size_t)n * 8 * chan + (size_t)y * w + xt * 32 + q4;
     const size_t pl = (MODE == 2) ? 32 : plane, ch = (MODE == 2) ? (size_t)D * 32 : chan;
     for (int pass = 0; pass < 2; ++pass)
@@ -35,18 +36,22 @@ __global__ void __launch_bounds__(256, 2) k(float* out, int N, int D, int h, int
     for (int c = 0; c < 8; ++c)
       for (int d = warp; d < D; d += 8) __stcs(base + c * chan + (size_t)d * plane, v + d);
   }
+  }
 }
-template <int MODE> void run(const char* name, float* out, int N, int D, int h, int w) {
+// ctas > 0: that many persistent CTAs walk the tiles (few CTAs = the store rate ONE SM reaches with DRAM far from busy)
+template <int MODE> void run(const char* name, float* out, int N, int D, int h, int w, int ctas = 0) {
   cudaFuncSetAttribute(k<MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024);
-  const int grid = N * h * (w / 32);
+  const int n_tiles = ctas > 0 ? ctas * 64 : N * h * (w / 32);
+  const int grid = ctas > 0 ? ctas : n_tiles;
   cudaEvent_t e0, e1; cudaEventCreate(&e0); cudaEventCreate(&e1);
-  for (int i = 0; i < 2; ++i) k<MODE><<<grid, 256, 100 * 1024>>>(out, N, D, h, w);
+  for (int i = 0; i < 2; ++i) k<MODE><<<grid, 256, 100 * 1024>>>(out, N, D, h, w, n_tiles);
   cudaEventRecord(e0);
-  for (int i = 0; i < 5; ++i) k<MODE><<<grid, 256, 100 * 1024>>>(out, N, D, h, w);
+  for (int i = 0; i < 5; ++i) k<MODE><<<grid, 256, 100 * 1024>>>(out, N, D, h, w, n_tiles);
   cudaEventRecord(e1); cudaEventSynchronize(e1);
   float ms; cudaEventElapsedTime(&ms, e0, e1); ms /= 5;
-  const double bytes = (double)N * 8 * D * h * w * 4;
-  printf("%-44s %.3f ms per %d pairs = %.3f ms/pair  %.0f GB/s\n", name, ms, N, ms / N, bytes / ms * 1e-6);
+  const double bytes = (double)n_tiles * 8 * D * 32 * 4;
+  if (ctas > 0) printf("%-44s %d CTAs (one per SM): %.1f GB/s per CTA = %.1f B/clk at 1.93 GHz\n", name, ctas, bytes / ms * 1e-6 / ctas, bytes / ms * 1e-6 / ctas / 1.93);
+  else printf("%-44s %.3f ms per %d pairs = %.3f ms/pair  %.0f GB/s\n", name, ms, N, ms / N, bytes / ms * 1e-6);
 }
 int main() {
   const int N = 4, D = 192, h = 540, w = 960;
@@ -54,6 +59,10 @@ int main() {
   run<0>("128-bit stores, 4 row segments per instruction", out, N, D, h, w);
   run<1>("32-bit stores, 1 row segment per instruction", out, N, D, h, w);
   run<2>("128-bit stores, contiguous block per tile", out, N, D, h, w);
+  run<0>("128-bit stores, 4 row segments per instruction", out, N, D, h, w, 16);
+  run<0>("128-bit stores, 4 row segments per instruction", out, N, D, h, w, 148);
+  run<0>("128-bit stores, 4 row segments per instruction", out, N, D, h, w, 296);
+  run<2>("128-bit stores, contiguous block per tile", out, N, D, h, w, 16);
   printf("%s\n", cudaGetErrorString(cudaDeviceSynchronize()));
   return 0;
 }
