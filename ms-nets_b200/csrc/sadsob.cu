@@ -550,8 +550,14 @@ int launch_sadsob5_padded(const float* L, const float* R, int N, int H, int W, i
   // (tall_ok = false: launches of the slab exchange.  Their tiles WAIT for other ranks; when those ranks are other
   // streams of the same GPU -- the virtual-rank tests -- a waiting kernel's CTAs leave 27 KB of shared memory per SM,
   // which the 32-row form's blocks fit into and the 64-row form's 38 KB do not: the peers' scans would never run.)
-  static const bool tall_env = [] { const char* e = getenv("MSNETS_SCAN32"); return !(e && e[0] == '1'); }();
-  const bool tall = tall_env && tall_ok;
+  const char* e32 = getenv("MSNETS_SCAN32");
+  const bool tall_env = !(e32 && e32[0] == '1');
+  // ... and only when the taller (half as many, twice as long) jobs still fill the machine: a single small pair is
+  // faster in 32-row bands (config A: 0.358 vs 0.364 ms per step; two config-B pairs: 0.313 vs 0.318 ms)
+  // (at two waves of jobs and up; MSNETS_SCAN64=1 forces it for the tests)
+  const long long jobs64 = (long long)Dn * ((H - kS5W + kS5RB2 - 1) / kS5RB2) * N;
+  const char* force = getenv("MSNETS_SCAN64");
+  const bool tall = tall_env && tall_ok && (jobs64 >= 4736 || (force && force[0] == '1'));
   if (tall) {
     RB = kS5RB2;
     NB = (H - kS5W + RB - 1) / RB;

@@ -199,6 +199,22 @@ def test_ms_features_both_views_batched_matches_single(ms):
         assert np.array_equal(got[i], one)
 
 
+@pytest.mark.parametrize("H,W,D", [(150, 140, 32), (75, 96, 16), (100, 200, 48), (64, 70, 16)])
+def test_sadsob_scan_64_row_bands(ms, oracle, monkeypatch, H, W, D):
+    """The SAD-of-Sobel scan of the fused path on bands of 64 table rows (sadsob_scan5x2_kernel; batches that fill
+    the machine pick it by themselves, MSNETS_SCAN64=1 forces it here): images with several bands, a last band whose
+    second half is empty (processed as a 32-row band) and one whose second half is partial; bit-exact channel 2."""
+    monkeypatch.setenv("MSNETS_SCAN64", "1")
+    L, R = synth_pair(H, W, 7300 + H, shift=5)
+    got = ms.cbmv.ms_features(L, R, D, board_h=10, board_w_left=10, board_w_right=10)
+    want = oracle.ms_features(L, R, D, board_h=10, board_w_left=10, board_w_right=10)
+    assert np.array_equal(got[:4], want[:4]), "channels 0-3 (2 = SAD-of-Sobel) must be bit-exact"
+    from tests._synth import assert_aml_close          # (the one stated AML class, degenerate rows included)
+    assert_aml_close(got[4:], want[4:])
+    monkeypatch.setenv("MSNETS_SCAN32", "1")          # and the 32-row form gives the same bits
+    assert np.array_equal(ms.cbmv.ms_features(L, R, D, board_h=10, board_w_left=10, board_w_right=10), got)
+
+
 def test_ms_features_generic_path_matches(ms, oracle, monkeypatch):
     """the three-phase global-memory path (used for slabs and non-default windows)."""
     monkeypatch.setenv("MSNETS_FORCE_GENERIC", "1")
