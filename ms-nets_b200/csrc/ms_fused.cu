@@ -2007,6 +2007,12 @@ static int launch_inst(const FusedArgs& a, const CUtensorMap& map, const CUtenso
       if (dev < 64) done_mask |= 1ull << dev;
     }
   }
+  if (const char* e = getenv("MSNETS_EXP_EXTRA_SMEM")) {   // experiment: extra dynamic shared memory = fewer CTAs per SM
+    const size_t big = smem + (size_t)atoi(e);
+    MSN_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)big));
+    kern<<<(unsigned)(tiles * (kMode == kModeXchg ? a.subs : 1)), 256, big, s>>>(a, map, omap);
+    return 0;
+  }
   kern<<<(unsigned)(tiles * (kMode == kModeXchg ? a.subs : 1)), 256, smem, s>>>(a, map, omap);
   return 0;
 }
