@@ -1230,14 +1230,32 @@ __device__ __forceinline__ void phase3_quads(float* s_par, const uint8_t* s_cen,
   // census minima biased by 2^23 (exact: the minima are integers <= 120), see cen_bytes_as_biased_floats
   const f32x2 mp0[2] = {pk2(8388608.0f + (float)mcx, 8388608.0f + (float)mcy), pk2(8388608.0f + (float)mcz, 8388608.0f + (float)mcw)};
   const f32x2 ip0[2] = {pk2(i0.x, i0.y), pk2(i0.z, i0.w)};
+#ifdef MSN_P3_HALFWARPS   // A/B: phase 3 by warps 0-3 only (16 disparities per sweep), warps 4-7 leave the tile early
+  constexpr int kP3Step = 16;
+#else
+  constexpr int kP3Step = 32;
+#endif
 #pragma unroll(kP3Unroll)
-  for (int d = dl; d < D; d += 32) {
+  for (int d = dl; d < D; d += kP3Step) {
     float* e0 = s_par + d * kTile + q4;
+#ifdef MSN_EXP_NOP3LDS   // timing experiment only: phase 3 without its shared-memory reads
+    const float fd = (float)d;
+    const uchar4 cb = make_uchar4((unsigned char)d, (unsigned char)(d + 1), (unsigned char)(d + 2), (unsigned char)(d + 3));
+    const float4 v1 = make_float4(fd, fd + 1.f, fd + 2.f, fd + 3.f), v2 = make_float4(fd * 3.f, fd, fd + 5.f, fd), v3 = v1;
+#else
     const uchar4 cb = *reinterpret_cast<const uchar4*>(s_cen + d * kTile + q4);
     const float4 v1 = *reinterpret_cast<const float4*>(e0);
     const float4 v2 = *reinterpret_cast<const float4*>(e0 + PS);
     const float4 v3 = *reinterpret_cast<const float4*>(e0 + 2 * PS);
+#endif
     float4 a0, a1, a2, a3;
+#ifdef MSN_EXP_NOP3COMPUTE   // timing experiment only: phase 3 stores what it loaded
+    if (!kExact) {
+      a0 = make_float4((float)cb.x, (float)cb.y, (float)cb.z, (float)cb.w); a1 = v1; a2 = v2; a3 = v3;
+      store_quads<kVec>(arow + (size_t)d * plane, chan, nlive, a0, a1, a2, a3);
+      continue;
+    }
+#endif
     if (kExact) {   // s_inv holds the denominators themselves (INFINITY where the pixel has no cost)
       a0 = make_float4(__fdiv_rn(cen_e<kCenLutP3, true>(cb.x, mcx, s_lut, k0), i0.x), __fdiv_rn(cen_e<kCenLutP3, true>(cb.y, mcy, s_lut, k0), i0.y),
                        __fdiv_rn(cen_e<kCenLutP3, true>(cb.z, mcz, s_lut, k0), i0.z), __fdiv_rn(cen_e<kCenLutP3, true>(cb.w, mcw, s_lut, k0), i0.w));
@@ -1481,6 +1499,9 @@ __device__ __forceinline__ void tile_back_half(const FusedArgs& a, const TileId&
   T* orow = reinterpret_cast<T*>(a.out) + ((size_t)t.n * a.out_channels + a.out_ch0) * chan + (size_t)(a.out_d0 + t.sub0) * plane + (size_t)t.yl * g.w + (t.x0 + q4);
   const int nlive = min(4, g.w - (t.x0 + q4));  // live pixels of this quad (<= 0: none)
   const bool vec = vec_ok && nlive == 4;
+#ifdef MSN_EXP_SAMEADDR   // timing experiment only: every tile of an SM-resident pair of CTAs writes the SAME 8 x D row segments
+  orow = reinterpret_cast<T*>(a.out) + (size_t)(blockIdx.x % 296) * kTile + q4;   // (stays in L2: the stores cost no DRAM traffic)
+#endif
 #ifdef MSN_EXP_LINEAR   // timing experiment only (scrambled output): every tile writes ONE contiguous 8 x D x 128 B block
   const size_t plane_x = kTile, chan_x = (size_t)D * kTile;
   orow = reinterpret_cast<T*>(a.out) + (size_t)tile * 8 * D * kTile + q4;
@@ -1520,6 +1541,9 @@ __device__ __forceinline__ void tile_back_half(const FusedArgs& a, const TileId&
   __syncthreads();
 #ifdef MSN_EXP_NOP3      // timing experiment only: channels 4-7 are never written
   return;
+#endif
+#ifdef MSN_P3_HALFWARPS
+  if (warp >= 4) return;
 #endif
   const int dl = tid >> 3;
   if (kTmaOk && kTmaOutBuilt && a.tma_out) {

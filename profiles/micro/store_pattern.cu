@@ -30,6 +30,15 @@ __global__ void __launch_bounds__(256, 2) k(float* out, int N, int D, int h, int
 #pragma unroll
         for (int c = 0; c < 4; ++c)
           __stcs(reinterpret_cast<float4*>(base + (pass * 4 + c) * ch + (size_t)d * pl), make_float4(v, v + 1, v + 2, v + d));
+  } else if (MODE == 4) {
+    const int o8 = (tid & 3) * 8;
+    float* base = out + (size_t)n * 8 * chan + (size_t)y * w + xt * 32 + o8;
+    for (int c = 0; c < 8; ++c)
+      for (int d = tid >> 2; d < D; d += 64) {
+        float* p = base + c * chan + (size_t)d * plane;
+        asm volatile("st.global.cs.v8.f32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};" ::"l"(p), "f"(v), "f"(v + 1), "f"(v + 2),
+                     "f"(v + 3), "f"(v + 4), "f"(v + 5), "f"(v + 6), "f"(v + d) : "memory");
+      }
   } else {
     const int lane = tid & 31, warp = tid >> 5;
     float* base = out + (size_t)n * 8 * chan + (size_t)y * w + xt * 32 + lane;
@@ -63,6 +72,9 @@ int main() {
   run<0>("128-bit stores, 4 row segments per instruction", out, N, D, h, w, 148);
   run<0>("128-bit stores, 4 row segments per instruction", out, N, D, h, w, 296);
   run<2>("128-bit stores, contiguous block per tile", out, N, D, h, w, 16);
+  run<4>("256-bit stores, 8 row segments per instruction", out, N, D, h, w);
+  run<4>("256-bit stores, 8 row segments per instruction", out, N, D, h, w, 16);
+  run<1>("32-bit stores, 1 row segment per instruction", out, N, D, h, w, 16);
   printf("%s\n", cudaGetErrorString(cudaDeviceSynchronize()));
   return 0;
 }
