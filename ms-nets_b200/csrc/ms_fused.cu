@@ -603,6 +603,10 @@ struct P1State {
   float wv[5][6];      // sliding 5x6 right window; logical column j lives in wv[.][(j - 2*s) mod 6]
   int min_cen;
   float min_ncc, min_sad;
+#ifdef MSN_EXP_P1STORE   // timing experiment (clean blocks only): channels 1 and 3 leave the SM while phase 1 runs
+  float* optr;         // channel 1, row of the pair's first disparity, this thread's pixel (nullptr: pixel outside)
+  size_t oplane, ochan2;
+#endif
 };
 
 // One BLOCK of phase 1 = three disparity pairs (the rotation period of the window registers).
@@ -684,6 +688,15 @@ __device__ __forceinline__ void p1_block(P1State<L>& st, int dblk, int steps, in
     s_par[dsB * kTile + px] = nccB;
     s_par[2 * PS + dsA * kTile + px] = zA;
     s_par[2 * PS + dsB * kTile + px] = zB;
+#ifdef MSN_EXP_P1STORE
+    if (kClean && st.optr) {
+      st_stream(st.optr, normalise_cost(nccA, 1));
+      st_stream(st.optr + st.oplane, normalise_cost(nccB, 1));
+      st_stream(st.optr + st.ochan2, normalise_cost(zA, 3));
+      st_stream(st.optr + st.ochan2 + st.oplane, normalise_cost(zB, 3));
+    }
+    if (st.optr) st.optr += 2 * st.oplane;
+#endif
     st.min_cen = min(st.min_cen, min(cen_bA, cen_bB));
     st.min_ncc = fminf(st.min_ncc, fminf(nccA, nccB));
     st.min_sad = fminf(st.min_sad, fminf(zA, zB));
@@ -766,6 +779,15 @@ __device__ __forceinline__ Phase1Out phase1_tile(const FusedArgs& a, const TileI
   for (int r = 0; r < 5; ++r)
 #pragma unroll
     for (int j = 0; j < 6; ++j) st.wv[r][j] = st.rfp[r * L::RWF + j];
+#ifdef MSN_EXP_P1STORE
+  {
+    const size_t plane = (size_t)g.h * g.w, chan = plane * a.out_D;
+    st.oplane = plane; st.ochan2 = 2 * chan;
+    st.optr = (t.x0 + px < g.w) ? a.out + ((size_t)t.n * a.out_channels + a.out_ch0 + 1) * chan +
+                                      (size_t)(a.out_d0 + t.sub0 + d_lo) * plane + (size_t)t.yl * g.w + t.x0 + px
+                                : nullptr;
+  }
+#endif
   st.min_cen = 255;
   st.min_ncc = kFill;
   st.min_sad = kFill;
@@ -788,6 +810,9 @@ __device__ __forceinline__ Phase1Out phase1_tile(const FusedArgs& a, const TileI
         s_par[2 * PS + ds * kTile + px] = kFill;
       }
       st.rfp -= 6; st.dscp -= 6; st.ccp -= 6;   // (the window registers are never used again)
+#ifdef MSN_EXP_P1STORE
+      if (st.optr) st.optr += 6 * st.oplane;
+#endif
     } else {
       p1_block<L, false>(st, dblk, min(left, 6) >> 1, D, ap, l3, ld, ls, dmax_cen, dmax_ncc, dmax_sad, s_par, s_cen, px);
     }
@@ -1186,7 +1211,12 @@ __device__ __forceinline__ void store_ch03(const float* s_par, const uint8_t* s_
                                   normalise_cost(v2.w, 2));
     const float4 c3 = make_float4(normalise_cost(v3.x, 3), normalise_cost(v3.y, 3), normalise_cost(v3.z, 3),
                                   normalise_cost(v3.w, 3));
+#ifdef MSN_EXP_P1STORE
+    if (kVec) { st_stream4(o, c0); st_stream4(o + 2 * chan, c2); }
+    else store_quads<kVec>(o, chan, nlive, c0, c1, c2, c3);
+#else
     store_quads<kVec>(o, chan, nlive, c0, c1, c2, c3);
+#endif
   }
 }
 
